@@ -1,0 +1,174 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes loader for oracle/liboracle.so (the CPU restatement / "port").
+
+Same surface as oracle/refvamp.py so tests can swap one for the other. Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+ROBOT_ID = {"panda": 0, "fetch": 1}
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", _HERE, "oracle"], check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    L = C.CDLL(LIB_PATH)
+    L.or_env_create.restype = C.c_void_p
+    L.or_env_destroy.argtypes = [C.c_void_p]
+    L.or_env_add_sphere.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
+    L.or_env_add_cuboid.argtypes = [C.c_void_p, _f32p, C.c_int]
+    L.or_env_add_capsule.argtypes = [C.c_void_p, _f32p, C.c_int]
+    L.or_env_add_capt.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _u32p, _f32p, C.c_int64, _f32p,
+                                  C.c_float, C.c_float, C.c_float]
+    L.or_env_sort.argtypes = [C.c_void_p]
+    L.or_env_min_distances.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.or_env_min_distances.restype = C.c_int64
+    L.or_validate_motions.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int64, C.c_int, _u8p, C.c_void_p, C.c_int]
+    L.or_edge_min_clearance.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int64, C.c_int, _f64p, C.c_int]
+    L.or_sphere_fk.argtypes = [C.c_int, _f32p, C.c_int64, _f32p]
+    L.or_robot_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 4 + [_f32p, _f32p]
+    L.or_trig.argtypes = [_f32p, C.c_int64, _f32p, _f32p]
+    L.or_knn.argtypes = [_f64p, C.c_int64, _f64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                         _i64p, _f64p, C.c_int]
+    L.or_knn_radius.argtypes = [_f64p, C.c_int64, _f64p, C.c_int, C.c_double, C.c_int, C.c_double, _i64p, _f64p, C.c_int64]
+    L.or_knn_radius.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def robot_info(robot: str):
+    L = lib()
+    d, nf, nl, res = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    lo = np.zeros(16, np.float32)
+    hi = np.zeros(16, np.float32)
+    assert L.or_robot_info(ROBOT_ID[robot], d, nf, nl, res, lo, hi) == 0
+    return dict(dim=d.value, n_fine=nf.value, n_links=nl.value, resolution=res.value,
+                lo=lo[:d.value].copy(), hi=hi[:d.value].copy())
+
+
+def bounds(robot: str):
+    i = robot_info(robot)
+    return i["lo"], i["hi"]
+
+
+def trig(x):
+    x = _f32(x).reshape(-1)
+    s = np.zeros_like(x)
+    c = np.zeros_like(x)
+    lib().or_trig(x, x.size, s, c)
+    return s, c
+
+
+def sphere_fk(robot: str, q) -> np.ndarray:
+    q = _f32(q)
+    nf = robot_info(robot)["n_fine"]
+    out = np.zeros((q.shape[0], nf, 4), np.float32)
+    assert lib().or_sphere_fk(ROBOT_ID[robot], q, q.shape[0], out) == 0
+    return out
+
+
+class PortEnvironment:
+    def __init__(self):
+        self._L = lib()
+        self._h = C.c_void_p(self._L.or_env_create())
+
+    def __del__(self):
+        try:
+            self._L.or_env_destroy(self._h)
+        except Exception:
+            pass
+
+    def add_spheres(self, xyzr):
+        for s in _f32(xyzr).reshape(-1, 4):
+            self._L.or_env_add_sphere(self._h, *[float(v) for v in s])
+
+    def add_cuboids(self, c15, z_aligned=False):
+        for c in _f32(c15).reshape(-1, 15):
+            self._L.or_env_add_cuboid(self._h, np.ascontiguousarray(c), int(z_aligned))
+
+    def add_capsules(self, c7, z_aligned=False):
+        for c in _f32(c7).reshape(-1, 7):
+            self._L.or_env_add_capsule(self._h, np.ascontiguousarray(c), int(z_aligned))
+
+    def add_capt(self, t: dict):
+        aff = np.ascontiguousarray(t["aff"], np.float32)
+        self._L.or_env_add_capt(self._h, int(t["nlog2"]), _f32(t["tests"]), _f32(t["aabbs"]),
+                                np.ascontiguousarray(t["aff_starts"], np.uint32), aff, aff.shape[1] // 8,
+                                _f32(t["top"]), t["r_min"], t["r_max"], t["r_point"])
+
+    def sort(self):
+        self._L.or_env_sort(self._h)
+
+    def finalize(self):
+        pass
+
+    def min_distances(self, kind: int) -> np.ndarray:
+        n = self._L.or_env_min_distances(self._h, kind, None)
+        out = np.zeros(n, dtype=np.float32)
+        if n:
+            self._L.or_env_min_distances(self._h, kind, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def validate_motions(self, robot, q0, q1, resolution=0, nthreads=1, want_flops=False):
+        q0 = _f32(q0)
+        q1 = _f32(q1)
+        out = np.zeros(q0.shape[0], np.uint8)
+        fl = np.zeros(q0.shape[0], np.float64) if want_flops else None
+        rc = self._L.or_validate_motions(self._h, ROBOT_ID[robot], q0, q1, q0.shape[0], resolution, out,
+                                         fl.ctypes.data_as(C.c_void_p) if want_flops else None, nthreads)
+        assert rc == 0
+        return (out, fl) if want_flops else out
+
+    def validate_states(self, robot, q, nthreads=1):
+        return self.validate_motions(robot, q, q, resolution=1, nthreads=nthreads)
+
+    def edge_min_clearance(self, robot, q0, q1, resolution=0, nthreads=1):
+        q0 = _f32(q0)
+        q1 = _f32(q1)
+        out = np.zeros(q0.shape[0], np.float64)
+        assert self._L.or_edge_min_clearance(self._h, ROBOT_ID[robot], q0, q1, q0.shape[0], resolution, out, nthreads) == 0
+        return out
+
+
+def knn(db, q, k, metric=0, param=0.0, exclude_self=False, nthreads=1):
+    db = np.ascontiguousarray(db, np.float64)
+    q = np.ascontiguousarray(q, np.float64)
+    idx = np.zeros((q.shape[0], k), np.int64)
+    dist = np.zeros((q.shape[0], k), np.float64)
+    assert lib().or_knn(db, db.shape[0], q, q.shape[0], db.shape[1], k, metric, param, int(exclude_self), idx, dist, nthreads) == 0
+    return idx, dist
+
+
+def knn_radius(db, q, radius, metric=0, param=0.0):
+    db = np.ascontiguousarray(db, np.float64)
+    q = np.ascontiguousarray(q, np.float64).reshape(-1)
+    idx = np.zeros(db.shape[0], np.int64)
+    dist = np.zeros(db.shape[0], np.float64)
+    n = lib().or_knn_radius(db, db.shape[0], q, db.shape[1], radius, metric, param, idx, dist, db.shape[0])
+    return idx[:n], dist[:n]

@@ -1,0 +1,310 @@
+#!/usr/bin/env python3
+"""Generate robot-specific code from ompl_b200/robots/<robot>.json (no reference access needed).
+
+Emits
+  ompl_b200/csrc/robots/<robot>_gen.cuh   link-by-link forward kinematics for the CUDA engine:
+        one `frame<K>()` per actuated joint (parent frame x constant origin x joint motion, with
+        zero / unit coefficients folded away at generation time) plus sphere / link / pair tables.
+  oracle/robots_gen.h                      plain C tables for the table-driven CPU oracle.
+
+This is our own structured generator (frames -> spheres), not the reference's flat traced program
+(external/vamp/src/impl/vamp/robots/panda.hh:5226-5539 is the behaviour it must reproduce).
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.normpath(os.path.join(HERE, ".."))
+EPS = 1e-9
+
+
+def f32(v: float) -> str:
+    """C float literal of the float32 nearest to the double v (single cast, like the reference's
+    scalar-broadcast operators)."""
+    x = float(np.float32(v))
+    s = repr(x)
+    if "e" not in s and "." not in s and "inf" not in s:
+        s += ".0"
+    return s + "f"
+
+
+class Emitter:
+    """Tiny symbolic layer: values are python floats (constants) or C expression strings."""
+
+    def __init__(self):
+        self.lines = []
+        self.n = 0
+
+    @staticmethod
+    def is_c(v):
+        return isinstance(v, float)
+
+    def mul(self, a, b):
+        if self.is_c(a) and self.is_c(b):
+            return a * b
+        if self.is_c(b):
+            a, b = b, a
+        if self.is_c(a):
+            if abs(a) < EPS:
+                return 0.0
+            if abs(a - 1) < EPS:
+                return b
+            if abs(a + 1) < EPS:
+                return self.neg(b)
+            return f"({f32(a)} * {b})"
+        return f"({a} * {b})"
+
+    def neg(self, a):
+        if self.is_c(a):
+            return -a
+        if a.startswith("(-") and a.endswith(")") and a.count("(") == 1:
+            return a[2:-1]
+        return f"(-{a})"
+
+    def add(self, a, b):
+        if self.is_c(a) and self.is_c(b):
+            return a + b
+        if self.is_c(a):
+            a, b = b, a
+        if self.is_c(b):
+            if abs(b) < EPS:
+                return a
+            return f"({a} + {f32(b)})"
+        return f"({a} + {b})"
+
+    def sum(self, terms):
+        acc = 0.0
+        for t in terms:
+            acc = self.add(acc, t)
+        return acc
+
+    def lit(self, v):
+        return f32(v) if self.is_c(v) else v
+
+    def assign(self, name, v):
+        self.lines.append(f"{name} = {self.lit(v)};")
+
+
+def gen_frame(em: Emitter, fr: dict, parent_is_world: bool):
+    """Emit code computing frame F (R row-major r[9], t[3]) from parent P."""
+    rc = np.asarray(fr["R"], dtype=np.float64)
+    tc = np.asarray(fr["t"], dtype=np.float64)
+    if parent_is_world:
+        pr = [[float(i == j) for j in range(3)] for i in range(3)]
+        pt = [0.0, 0.0, 0.0]
+    else:
+        pr = [[f"P.r[{3 * i + j}]" for j in range(3)] for i in range(3)]
+        pt = [f"P.t[{i}]" for i in range(3)]
+    # A = Pr * Rc ; t = pt + Pr * tc
+    a = [[em.sum([em.mul(pr[i][k], float(rc[k][j])) for k in range(3)]) for j in range(3)] for i in range(3)]
+    t = [em.add(em.sum([em.mul(pr[i][k], float(tc[k])) for k in range(3)]), pt[i]) for i in range(3)]
+    axis = np.asarray(fr["axis"], dtype=np.float64)
+    ai = int(np.argmax(np.abs(axis)))
+    sgn = float(np.sign(axis[ai]))
+    assert abs(abs(axis[ai]) - 1) < 1e-12 and np.abs(axis).sum() - 1 < 1e-12, "axis-aligned joints only"
+    if fr["type"] in ("revolute", "continuous"):
+        # materialise A's two rotating columns as temporaries when they are expressions
+        s = "s" if sgn > 0 else "(-s)"
+        u, v = [(1, 2), (2, 0), (0, 1)][ai]  # rotation about axis ai mixes columns u, v: u' = c u + s v ; v' = -s u + c v
+        r = [[None] * 3 for _ in range(3)]
+        for i in range(3):
+            cu, cv = a[i][u], a[i][v]
+            r[i][ai] = a[i][ai]
+            r[i][u] = em.add(em.mul(cu, "c"), em.mul(cv, s))
+            r[i][v] = em.add(em.mul(em.neg(cu), s), em.mul(cv, "c"))
+    elif fr["type"] == "prismatic":
+        r = a
+        t = [em.add(t[i], em.mul(a[i][ai], "q" if sgn > 0 else "(-q)")) for i in range(3)]
+    else:
+        raise ValueError(fr["type"])
+    for i in range(3):
+        for j in range(3):
+            em.assign(f"F.r[{3 * i + j}]", r[i][j])
+    for i in range(3):
+        em.assign(f"F.t[{i}]", t[i])
+
+
+def gen_cuda(model: dict) -> str:
+    name = model["name"]
+    cname = name.capitalize()
+    frames = model["frames"]
+    links = model["links"]
+    # process links in frame order (base -> tip) so frames stream; keep the reference's env order as data
+    order = sorted(range(len(links)), key=lambda i: (links[i]["frame"], -i))
+    fine_sorted = []
+    link_rows = []
+    for li in order:
+        l = links[li]
+        b = len(fine_sorted)
+        for f in l["fine"]:
+            fine_sorted.append((f["c"], f["r"], f["id"]))
+        link_rows.append(dict(ref_index=li, name=l["name"], frame=l["frame"], begin=b, end=len(fine_sorted),
+                              coarse=l["coarse"]))
+    new_index = {row["ref_index"]: i for i, row in enumerate(link_rows)}
+    pairs = [(new_index[a], new_index[b]) for a, b in model["self_pairs"]]
+    # order pairs by the later frame so frames stream in stage 2
+    pairs.sort(key=lambda p: (max(link_rows[p[0]]["frame"], link_rows[p[1]]["frame"]), p))
+
+    lo = [float(np.float32(a)) for a in model["s_a"]]
+    hi = [float(np.float32(np.float32(a) + np.float32(m))) for a, m in zip(model["s_a"], model["s_m"])]
+
+    out = []
+    w = out.append
+    w(f"// GENERATED by tools/gen_robot_code.py from ompl_b200/robots/{name}.json -- do not edit.")
+    w(f"// Link-by-link forward kinematics + collision-sphere tables for the '{name}' robot.")
+    w(f"// Behaviour to reproduce: vamp::robots::{cname}::fkcc (external/vamp/src/impl/vamp/robots/{name}.hh).")
+    w("#pragma once")
+    w('#include "../robot_common.cuh"')
+    w("")
+    w("namespace b200mp {")
+    w("")
+    nl, nf, npairs = len(link_rows), len(fine_sorted), len(pairs)
+    w(f"struct {cname}Tables {{")
+    w(f"    float4 coarse[{nl}];        // frame-local centre + radius of each link's bounding sphere")
+    w(f"    float4 fine[{nf}];          // frame-local centre + radius, grouped by link")
+    w(f"    short link_begin[{nl + 1}]; // fine-sphere range of link l = [link_begin[l], link_begin[l+1])")
+    w(f"    short pair_a[{npairs}], pair_b[{npairs}];")
+    w("};")
+    w("")
+    w(f"__constant__ {cname}Tables k{cname}Tables = {{")
+    w("    {" + ", ".join("{%s, %s, %s, %s}" % (f32(r["coarse"]["c"][0]), f32(r["coarse"]["c"][1]),
+                                                 f32(r["coarse"]["c"][2]), f32(r["coarse"]["r"])) for r in link_rows) + "},")
+    w("    {" + ",\n     ".join("{%s, %s, %s, %s}" % (f32(c[0]), f32(c[1]), f32(c[2]), f32(r)) for c, r, _ in fine_sorted) + "},")
+    w("    {" + ", ".join(str(r["begin"]) for r in link_rows) + f", {nf}" + "},")
+    w("    {" + ", ".join(str(a) for a, _ in pairs) + "},")
+    w("    {" + ", ".join(str(b) for _, b in pairs) + "},")
+    w("};")
+    w("")
+    w(f"struct {cname} {{")
+    w(f"    static constexpr int kDim = {model['dimension']};")
+    w(f"    static constexpr int kFrames = {len(frames)};   // frame 0 = world")
+    w(f"    static constexpr int kLinks = {nl};")
+    w(f"    static constexpr int kFine = {nf};")
+    w(f"    static constexpr int kPairs = {npairs};")
+    w(f"    static constexpr int kResolution = {model['resolution']};")
+    w(f"    static constexpr int kRobotId = {0 if name == 'panda' else 1 if name == 'fetch' else 9};")
+    w(f"    using Tables = {cname}Tables;")
+    w(f"    __device__ static __forceinline__ const Tables &tables() {{ return k{cname}Tables; }}")
+    w("")
+    w("    // frame each link's spheres live in; links are stored base -> tip")
+    w("    __host__ __device__ static constexpr int link_frame(int l) {")
+    w("        constexpr int v[kLinks] = {" + ", ".join(str(r["frame"]) for r in link_rows) + "};")
+    w("        return v[l];")
+    w("    }")
+    w("    __host__ __device__ static constexpr int frame_parent(int f) {")
+    w("        constexpr int v[kFrames] = {" + ", ".join(str(fr["parent"]) for fr in frames) + "};")
+    w("        return v[f];")
+    w("    }")
+    w("    __host__ __device__ static constexpr int frame_joint(int f) {   // index into q; -1 for world")
+    w("        constexpr int v[kFrames] = {" + ", ".join(str(fr.get("q_index", -1)) for fr in frames) + "};")
+    w("        return v[f];")
+    w("    }")
+    w("    __host__ __device__ static constexpr bool frame_revolute(int f) {")
+    w("        constexpr bool v[kFrames] = {" + ", ".join("true" if fr.get("type") in ("revolute", "continuous") else "false" for fr in frames) + "};")
+    w("        return v[f];")
+    w("    }")
+    w("    __host__ __device__ static constexpr int pair_a(int p) {")
+    w("        constexpr int v[kPairs] = {" + ", ".join(str(a) for a, _ in pairs) + "};")
+    w("        return v[p];")
+    w("    }")
+    w("    __host__ __device__ static constexpr int pair_b(int p) {")
+    w("        constexpr int v[kPairs] = {" + ", ".join(str(b) for _, b in pairs) + "};")
+    w("        return v[p];")
+    w("    }")
+    w("    __host__ __device__ static constexpr int link_begin(int l) {")
+    w("        constexpr int v[kLinks + 1] = {" + ", ".join(str(r["begin"]) for r in link_rows) + f", {nf}" + "};")
+    w("        return v[l];")
+    w("    }")
+    w("    static constexpr float kLo[kDim] = {" + ", ".join(f32(v) for v in lo) + "};")
+    w("    static constexpr float kHi[kDim] = {" + ", ".join(f32(v) for v in hi) + "};")
+    w("")
+    w("    // F = P * origin(K) * motion(q).  s, c = vamp_sin(q), vamp_cos(q) for revolute joints; q raw for prismatic.")
+    w("    template <int K>")
+    w("    __device__ static __forceinline__ void frame(const Frame &P, float q, float s, float c, Frame &F);")
+    w("};")
+    w("")
+    for fr in frames[1:]:
+        em = Emitter()
+        gen_frame(em, fr, parent_is_world=(fr["parent"] == 0))
+        w(f"// frame {fr['id']}: joint '{fr['joint']}' ({fr['type']}), parent frame {fr['parent']}")
+        w("template <>")
+        w(f"__device__ __forceinline__ void {cname}::frame<{fr['id']}>(const Frame &P, float q, float s, float c, Frame &F) {{")
+        w("    (void)P; (void)q; (void)s; (void)c;")
+        for ln in em.lines:
+            w("    " + ln)
+        w("}")
+        w("")
+    w("}  // namespace b200mp")
+    return "\n".join(out) + "\n", link_rows, fine_sorted, pairs
+
+
+def gen_oracle_tables(models: list) -> str:
+    out = []
+    w = out.append
+    w("/* GENERATED by tools/gen_robot_code.py from ompl_b200/robots/*.json -- do not edit.")
+    w(" * TEST INFRASTRUCTURE ONLY: robot tables for the table-driven CPU oracle (oracle/oracle_validate.cpp).")
+    w(" * Links are listed in the reference's own environment-test order; doubles keep full URDF precision. */")
+    w("#pragma once")
+    w("typedef struct { int parent; int q_index; int type; /* 0 revolute, 1 prismatic */ double axis[3]; double R[9]; double t[3]; } OrFrame;")
+    w("typedef struct { double c[3]; double r; } OrSphere;")
+    w("typedef struct { int frame; OrSphere coarse; int fine_begin, fine_end; } OrLink;")
+    w("typedef struct { const char *name; int dim, n_frames, n_links, n_fine, n_pairs, resolution;")
+    w("                 const OrFrame *frames; const OrLink *links; const OrSphere *fine; const int *fine_id; const int (*pairs)[2];")
+    w("                 const float *lo; const float *hi; } OrRobot;")
+    for m in models:
+        n = m["name"]
+        frames = m["frames"]
+        w(f"static const OrFrame {n}_frames[] = {{")
+        for fr in frames:
+            if fr["id"] == 0:
+                w("  {-1, -1, 0, {0,0,1}, {1,0,0,0,1,0,0,0,1}, {0,0,0}},")
+                continue
+            r = np.asarray(fr["R"]).reshape(-1)
+            w("  {%d, %d, %d, {%s}, {%s}, {%s}}," % (
+                fr["parent"], fr["q_index"], 0 if fr["type"] in ("revolute", "continuous") else 1,
+                ", ".join(repr(float(v)) for v in fr["axis"]),
+                ", ".join(repr(float(v)) for v in r), ", ".join(repr(float(v)) for v in fr["t"])))
+        w("};")
+        fine = []
+        w(f"static const OrLink {n}_links[] = {{")
+        for l in m["links"]:
+            b = len(fine)
+            fine.extend(l["fine"])
+            c = l["coarse"]
+            w("  {%d, {{%s}, %s}, %d, %d}," % (l["frame"], ", ".join(repr(float(v)) for v in c["c"]), repr(float(c["r"])), b, len(fine)))
+        w("};")
+        w(f"static const OrSphere {n}_fine[] = {{")
+        for f in fine:
+            w("  {{%s}, %s}," % (", ".join(repr(float(v)) for v in f["c"]), repr(float(f["r"]))))
+        w("};")
+        w(f"static const int {n}_fine_id[] = {{" + ", ".join(str(f["id"]) for f in fine) + "};  /* reference sphere index */")
+        w(f"static const int {n}_pairs[][2] = {{" + ", ".join("{%d,%d}" % (a, b) for a, b in m["self_pairs"]) + "};")
+        lo = [float(np.float32(a)) for a in m["s_a"]]
+        hi = [float(np.float32(np.float32(a) + np.float32(mm))) for a, mm in zip(m["s_a"], m["s_m"])]
+        w(f"static const float {n}_lo[] = {{" + ", ".join(f32(v) for v in lo) + "};")
+        w(f"static const float {n}_hi[] = {{" + ", ".join(f32(v) for v in hi) + "};")
+        w(f"static const OrRobot {n}_robot = {{\"{n}\", {m['dimension']}, {len(frames)}, {len(m['links'])}, {len(fine)}, "
+          f"{len(m['self_pairs'])}, {m['resolution']}, {n}_frames, {n}_links, {n}_fine, {n}_fine_id, {n}_pairs, {n}_lo, {n}_hi}};")
+    return "\n".join(out) + "\n"
+
+
+if __name__ == "__main__":
+    models = []
+    for r in ("panda", "fetch"):
+        p = os.path.join(ROOT, "ompl_b200", "robots", f"{r}.json")
+        if not os.path.exists(p):
+            continue
+        m = json.load(open(p))
+        models.append(m)
+        code, *_ = gen_cuda(m)
+        os.makedirs(os.path.join(ROOT, "ompl_b200", "csrc", "robots"), exist_ok=True)
+        with open(os.path.join(ROOT, "ompl_b200", "csrc", "robots", f"{r}_gen.cuh"), "w") as f:
+            f.write(code)
+    with open(os.path.join(ROOT, "oracle", "robots_gen.h"), "w") as f:
+        f.write(gen_oracle_tables(models))
+    print("generated", [m["name"] for m in models])
