@@ -1,0 +1,117 @@
+/* b200mp -- B200-native batched motion validation and nearest-neighbour engine: C ABI.
+ *
+ * This is the drop-in boundary. Host code (the OMPL adapters in include/b200mp_ompl.hpp, or any FFI) talks to
+ * the CUDA engine only through these entry points: opaque handles, plain pointers and sizes, int status codes,
+ * no exceptions and no C++/torch types cross it. Paths below are relative to the reference checkout.
+ *
+ * What each entry point replaces in the reference:
+ *   b200mp_validate_states    ompl::vamp::VampStateValidityChecker::isValid      src/ompl/vamp/VampStateValidityChecker.h:37-41
+ *                             (= vamp::planning::validate_motion<Robot, 8, 1>(q, q, env))
+ *   b200mp_validate_motions   ompl::vamp::VampMotionValidator::checkMotion       src/ompl/vamp/VampMotionValidator.h:37-52
+ *                             (= validate_motion<Robot, 8, Robot::resolution>)  external/vamp/src/impl/vamp/planning/validate.hh:23-77
+ *   b200mp_env_*              vamp::collision::Environment<float> + sort()       external/vamp/src/impl/vamp/collision/environment.hh:14-85
+ *                             and the shape constructors' min_distance           external/vamp/src/impl/vamp/collision/shapes.hh:52-67,165-189,236-239
+ *   b200mp_env_add_capt       vamp::collision::CAPT (prebuilt tree arrays)       external/vamp/src/impl/vamp/collision/capt.hh:61-618
+ *   b200mp_robot_info         Robot::dimension / resolution / joint bounds       src/ompl/vamp/VampStateSpace.h:10-36
+ *   b200mp_knn_*              ompl::NearestNeighbors<_T> (Linear semantics)      src/ompl/datastructures/NearestNeighbors.h:46-115,
+ *                                                                                src/ompl/datastructures/NearestNeighborsLinear.h:65-142
+ *                             metric: RealVectorStateSpace::distance            src/ompl/base/spaces/src/RealVectorStateSpace.cpp:230-242
+ *
+ * Conventions: every function returns B200MP_OK (0) or an error code; b200mp_last_error() gives the text for the
+ * calling thread. Batch buffers are caller-owned, contiguous, row-major. "_device" variants take device pointers
+ * that live on the context's GPU and an optional cudaStream_t passed as void* (NULL = the context's own stream);
+ * they do not synchronise. Host variants are synchronous and thread-safe (calls on one context are serialised).
+ * There is no CPU fallback: without a CUDA device b200mp_create fails with B200MP_ERR_NO_DEVICE.
+ */
+#ifndef B200MP_H
+#define B200MP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MP_VERSION 1
+
+typedef struct b200mp_ctx b200mp_ctx;
+typedef struct b200mp_env b200mp_env;
+typedef struct b200mp_knn b200mp_knn;
+
+enum {
+    B200MP_OK = 0,
+    B200MP_ERR_INVALID = 1,    /* bad argument */
+    B200MP_ERR_CUDA = 2,       /* a CUDA runtime call failed; see b200mp_last_error() */
+    B200MP_ERR_NO_DEVICE = 3,  /* no usable GPU (there is no CPU fallback) */
+    B200MP_ERR_CAPACITY = 4,   /* scene or request exceeds an engine limit */
+    B200MP_ERR_STATE = 5,      /* call order violated, e.g. environment not committed */
+    B200MP_ERR_EMPTY = 6       /* "No elements found in nearest neighbors data structure" */
+};
+
+enum { B200MP_ROBOT_PANDA = 0, B200MP_ROBOT_FETCH = 1 };
+enum { B200MP_METRIC_L2 = 0 };
+
+int b200mp_version(void);
+const char *b200mp_last_error(void);
+
+/* ---- context: one per GPU (one process per GPU in multi-GPU jobs) -------------------------------------------- */
+int b200mp_create(int device, b200mp_ctx **out);
+void b200mp_destroy(b200mp_ctx *ctx);
+int b200mp_device(const b200mp_ctx *ctx, int *device, int *sm_count);
+int b200mp_synchronize(b200mp_ctx *ctx);
+
+/* ---- robots ----------------------------------------------------------------------------------------------- */
+/* lo/hi: dim floats each (may be NULL). */
+int b200mp_robot_info(int robot, int *dim, int *n_spheres, int *resolution, float *lo, float *hi);
+
+/* ---- environment -------------------------------------------------------------------------------------------- */
+int b200mp_env_create(b200mp_ctx *ctx, b200mp_env **out);
+void b200mp_env_destroy(b200mp_env *env);
+/* xyzr[n][4] */
+int b200mp_env_add_spheres(b200mp_env *env, const float *xyzr, int n);
+/* c[n][15] = centre(3), axis1(3), axis2(3), axis3(3), half extents(3). z_aligned selects the reference's
+ * z_aligned_cuboids list (only axis1.xy, axis2.xy and half extents are then used). */
+int b200mp_env_add_cuboids(b200mp_env *env, const float *c, int n, int z_aligned);
+/* c[n][7] = p1(3), v = p2 - p1 (3), radius. rdv = 1 / (v.v) is derived here. */
+int b200mp_env_add_capsules(b200mp_env *env, const float *c, int n, int z_aligned);
+/* Prebuilt collision-affording point tree, arrays laid out as the reference stores them:
+ * tests[2^nlog2 - 1], aabbs[2^nlog2][6] (lower xyz, upper xyz), aff_starts[2^nlog2 + 1] (in units of 8-point
+ * vectors), aff[3][n_aff8 * 8] (x row, y row, z row), top[6]. */
+int b200mp_env_add_capt(b200mp_env *env, int nlog2, const float *tests, const float *aabbs, const uint32_t *aff_starts,
+                        const float *aff, int64_t n_aff8, const float *top, float r_min, float r_max, float r_point);
+/* Sort every shape list by min_distance (Environment::sort). Obstacles are otherwise tested in insertion
+ * order with the reference's ordered-scan-with-break semantics. */
+int b200mp_env_sort(b200mp_env *env);
+/* Upload to the GPU. Must be called after the last add/sort and before validation. */
+int b200mp_env_commit(b200mp_env *env);
+/* kind: 0 spheres, 1 capsules, 2 z-capsules, 3 cuboids, 4 z-cuboids. out may be NULL. */
+int64_t b200mp_env_min_distances(const b200mp_env *env, int kind, float *out);
+
+/* ---- validation --------------------------------------------------------------------------------------------- */
+/* q[m][dim] host floats -> valid[m] (1 = collision free). */
+int b200mp_validate_states(b200mp_ctx *ctx, int robot, const b200mp_env *env, const float *q, int64_t m, uint8_t *valid);
+/* q0, q1[m][dim] host floats -> valid[m]. resolution 0 = the robot's default (32). The states tested on an edge
+ * are exactly the reference's: t = j/(8n), j = 1..8n, n = max(ceil(|q1-q0| / 8 * resolution), 1). */
+int b200mp_validate_motions(b200mp_ctx *ctx, int robot, const b200mp_env *env, const float *q0, const float *q1, int64_t m,
+                            int resolution, uint8_t *valid);
+/* Same with double states as OMPL stores them (cast to float per ompl_to_vamp, src/ompl/vamp/Utils.h:16-30). */
+int b200mp_validate_states_f64(b200mp_ctx *ctx, int robot, const b200mp_env *env, const double *q, int64_t m, uint8_t *valid);
+int b200mp_validate_motions_f64(b200mp_ctx *ctx, int robot, const b200mp_env *env, const double *q0, const double *q1,
+                                int64_t m, int resolution, uint8_t *valid);
+/* Device-resident variants (asynchronous on `stream`). */
+int b200mp_validate_states_device(b200mp_ctx *ctx, int robot, const b200mp_env *env, const float *d_q, int64_t m,
+                                  uint8_t *d_valid, void *stream);
+int b200mp_validate_motions_device(b200mp_ctx *ctx, int robot, const b200mp_env *env, const float *d_q0, const float *d_q1,
+                                   int64_t m, int resolution, uint8_t *d_valid, void *stream);
+/* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
+int64_t b200mp_launch_count(const b200mp_ctx *ctx);
+
+/* FP32 FMA micro-benchmark used as the measured roofline denominator of the collision kernels:
+ * runs `iters` dependent-chain FFMA blocks on every SM and returns achieved TFLOP/s. */
+int b200mp_fp32_peak(b200mp_ctx *ctx, int iters, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MP_H */

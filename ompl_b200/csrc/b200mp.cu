@@ -1,0 +1,557 @@
+// b200mp C ABI implementation: contexts, environments, validation launches (see include/b200mp.h).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/b200mp.h"
+#include "validate.cuh"
+#include "robots/panda_gen.cuh"
+#include "robots/fetch_gen.cuh"
+#include "host_common.hpp"
+
+using namespace b200mp;
+
+namespace b200mp {
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+}  // namespace b200mp
+
+// ---------------------------------------------------------------------------------------------------- environment
+namespace {
+
+struct HSphere { float x, y, z, r, min_d; };
+struct HCapsule { float x1, y1, z1, xv, yv, zv, r, rdv, min_d; };
+struct HCuboid { float c[3], a1[3], a2[3], a3[3], h[3], min_d; };
+
+struct DeviceCapt {
+    float *tests = nullptr, *aabbs = nullptr, *aff = nullptr;
+    uint32_t *aff_starts = nullptr;
+    CaptView view{};
+};
+
+inline float dot3(float ax, float ay, float az, float bx, float by, float bz) { return ax * bx + ay * by + az * bz; }
+inline float clampf(float v, float lo, float hi) { return std::max(std::min(v, hi), lo); }
+
+}  // namespace
+
+struct b200mp_env {
+    b200mp_ctx *ctx = nullptr;
+    std::vector<HSphere> spheres;
+    std::vector<HCapsule> capsules, zcapsules;
+    std::vector<HCuboid> cuboids, zcuboids;
+    std::vector<DeviceCapt> pcs;
+    float *d_blob = nullptr;
+    SceneDesc desc{};
+    bool committed = false;
+};
+
+extern "C" {
+
+int b200mp_version(void) { return B200MP_VERSION; }
+const char *b200mp_last_error(void) { return g_last_error.c_str(); }
+
+int b200mp_create(int device, b200mp_ctx **out) {
+    if (!out) return fail(B200MP_ERR_INVALID, "b200mp_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(B200MP_ERR_NO_DEVICE, "b200mp_create: no CUDA device (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(B200MP_ERR_INVALID, "b200mp_create: device %d out of range [0,%d)", device, n);
+    auto *c = new b200mp_ctx();
+    c->device = device;
+    B200_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    c->cc_major = prop.major;
+    if (prop.major < 10) {
+        delete c;
+        return fail(B200MP_ERR_NO_DEVICE, "b200mp_create: device %d is sm_%d%d; kernels are built for sm_100a only", device,
+                    prop.major, prop.minor);
+    }
+    B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaMalloc(&c->d_counters, sizeof(LaunchCounters)));
+    *out = c;
+    return B200MP_OK;
+}
+
+void b200mp_destroy(b200mp_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->scratch.release();
+    cudaFree(c->d_counters);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int b200mp_device(const b200mp_ctx *c, int *device, int *sm_count) {
+    if (!c) return fail(B200MP_ERR_INVALID, "b200mp_device: ctx is NULL");
+    if (device) *device = c->device;
+    if (sm_count) *sm_count = c->sm_count;
+    return B200MP_OK;
+}
+
+int b200mp_synchronize(b200mp_ctx *c) {
+    if (!c) return fail(B200MP_ERR_INVALID, "b200mp_synchronize: ctx is NULL");
+    B200_CUDA(cudaSetDevice(c->device));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    return B200MP_OK;
+}
+
+int64_t b200mp_launch_count(const b200mp_ctx *c) { return c ? c->launches.load() : -1; }
+
+int b200mp_robot_info(int robot, int *dim, int *n_spheres, int *resolution, float *lo, float *hi) {
+    auto fill = [&](auto tag) {
+        using R = decltype(tag);
+        if (dim) *dim = R::kDim;
+        if (n_spheres) *n_spheres = R::kFine;
+        if (resolution) *resolution = R::kResolution;
+        for (int j = 0; j < R::kDim; ++j) {
+            if (lo) lo[j] = R::kLo[j];
+            if (hi) hi[j] = R::kHi[j];
+        }
+    };
+    switch (robot) {
+        case B200MP_ROBOT_PANDA: fill(Panda{}); return B200MP_OK;
+        case B200MP_ROBOT_FETCH: fill(Fetch{}); return B200MP_OK;
+        default: return fail(B200MP_ERR_INVALID, "b200mp_robot_info: unknown robot %d", robot);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ environment
+int b200mp_env_create(b200mp_ctx *ctx, b200mp_env **out) {
+    if (!ctx || !out) return fail(B200MP_ERR_INVALID, "b200mp_env_create: NULL argument");
+    auto *e = new b200mp_env();
+    e->ctx = ctx;
+    *out = e;
+    return B200MP_OK;
+}
+
+static void env_free_device(b200mp_env *e) {
+    if (e->d_blob) cudaFree(e->d_blob);
+    e->d_blob = nullptr;
+    e->committed = false;
+}
+
+void b200mp_env_destroy(b200mp_env *e) {
+    if (!e) return;
+    cudaSetDevice(e->ctx->device);
+    env_free_device(e);
+    for (auto &p : e->pcs) {
+        cudaFree(p.tests);
+        cudaFree(p.aabbs);
+        cudaFree(p.aff);
+        cudaFree(p.aff_starts);
+    }
+    delete e;
+}
+
+int b200mp_env_add_spheres(b200mp_env *e, const float *s, int n) {
+    if (!e || (!s && n > 0) || n < 0) return fail(B200MP_ERR_INVALID, "b200mp_env_add_spheres: bad argument");
+    for (int i = 0; i < n; ++i) {
+        HSphere h{s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3], 0};
+        h.min_d = std::sqrt(h.x * h.x + h.y * h.y + h.z * h.z) - h.r;  // shapes.hh:236-239
+        e->spheres.push_back(h);
+    }
+    e->committed = false;
+    return B200MP_OK;
+}
+
+int b200mp_env_add_cuboids(b200mp_env *e, const float *c, int n, int z_aligned) {
+    if (!e || (!c && n > 0) || n < 0) return fail(B200MP_ERR_INVALID, "b200mp_env_add_cuboids: bad argument");
+    for (int i = 0; i < n; ++i) {
+        const float *p = c + 15 * i;
+        HCuboid h{};
+        std::memcpy(h.c, p, 12);
+        std::memcpy(h.a1, p + 3, 12);
+        std::memcpy(h.a2, p + 6, 12);
+        std::memcpy(h.a3, p + 9, 12);
+        std::memcpy(h.h, p + 12, 12);
+        // closest point of the box to the world origin (shapes.hh:52-67)
+        const float d1 = dot3(-h.c[0], -h.c[1], -h.c[2], h.a1[0], h.a1[1], h.a1[2]);
+        const float d2 = dot3(-h.c[0], -h.c[1], -h.c[2], h.a2[0], h.a2[1], h.a2[2]);
+        const float d3 = dot3(-h.c[0], -h.c[1], -h.c[2], h.a3[0], h.a3[1], h.a3[2]);
+        const float v1 = clampf(d1, -h.h[0], h.h[0]), v2 = clampf(d2, -h.h[1], h.h[1]), v3 = clampf(d3, -h.h[2], h.h[2]);
+        const float xn = h.c[0] + h.a1[0] * v1 + h.a2[0] * v2 + h.a3[0] * v3;
+        const float yn = h.c[1] + h.a1[1] * v1 + h.a2[1] * v2 + h.a3[1] * v3;
+        const float zn = h.c[2] + h.a1[2] * v1 + h.a2[2] * v2 + h.a3[2] * v3;
+        h.min_d = std::sqrt(xn * xn + yn * yn + zn * zn);
+        (z_aligned ? e->zcuboids : e->cuboids).push_back(h);
+    }
+    e->committed = false;
+    return B200MP_OK;
+}
+
+int b200mp_env_add_capsules(b200mp_env *e, const float *c, int n, int z_aligned) {
+    if (!e || (!c && n > 0) || n < 0) return fail(B200MP_ERR_INVALID, "b200mp_env_add_capsules: bad argument");
+    for (int i = 0; i < n; ++i) {
+        const float *p = c + 7 * i;
+        HCapsule h{p[0], p[1], p[2], p[3], p[4], p[5], p[6], 0, 0};
+        h.rdv = static_cast<float>(1.0 / dot3(h.xv, h.yv, h.zv, h.xv, h.yv, h.zv));  // factory.hh:110-126
+        // closest point of the capsule to the world origin (shapes.hh:165-189)
+        const float t = clampf(dot3(-h.x1, -h.y1, -h.z1, h.xv, h.yv, h.zv) * h.rdv, 0.F, 1.F);
+        const float xp = h.x1 + h.xv * t, yp = h.y1 + h.yv * t, zp = h.z1 + h.zv * t;
+        float xo = -xp, yo = -yp, zo = -zp;
+        const float ol = std::sqrt(dot3(xo, yo, zo, xo, yo, zo));
+        xo = xo / ol;
+        yo = yo / ol;
+        zo = zo / ol;
+        const float ro = clampf(ol, 0.F, h.r);
+        const float xn = xp + ro * xo, yn = yp + ro * yo, zn = zp + ro * zo;
+        h.min_d = std::sqrt(xn * xn + yn * yn + zn * zn);
+        (z_aligned ? e->zcapsules : e->capsules).push_back(h);
+    }
+    e->committed = false;
+    return B200MP_OK;
+}
+
+int b200mp_env_add_capt(b200mp_env *e, int nlog2, const float *tests, const float *aabbs, const uint32_t *aff_starts,
+                        const float *aff, int64_t n_aff8, const float *top, float r_min, float r_max, float r_point) {
+    (void)r_min;
+    (void)r_max;
+    if (!e || !tests || !aabbs || !aff_starts || !aff || !top || nlog2 < 0 || nlog2 > 30 || n_aff8 < 0)
+        return fail(B200MP_ERR_INVALID, "b200mp_env_add_capt: bad argument");
+    if (e->pcs.size() >= kMaxPointClouds) return fail(B200MP_ERR_CAPACITY, "b200mp_env_add_capt: at most %d point clouds", kMaxPointClouds);
+    B200_CUDA(cudaSetDevice(e->ctx->device));
+    const size_t nl = size_t(1) << nlog2, nt = nl - 1;
+    DeviceCapt d;
+    B200_CUDA(cudaMalloc(&d.tests, std::max<size_t>(nt, 1) * 4));
+    B200_CUDA(cudaMalloc(&d.aabbs, nl * 6 * 4));
+    B200_CUDA(cudaMalloc(&d.aff_starts, (nl + 1) * 4));
+    B200_CUDA(cudaMalloc(&d.aff, std::max<size_t>(3 * n_aff8 * 8, 4) * 4));
+    B200_CUDA(cudaMemcpy(d.tests, tests, nt * 4, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(d.aabbs, aabbs, nl * 6 * 4, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(d.aff_starts, aff_starts, (nl + 1) * 4, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(d.aff, aff, 3 * n_aff8 * 8 * 4, cudaMemcpyHostToDevice));
+    d.view.tests = d.tests;
+    d.view.aabbs = d.aabbs;
+    d.view.aff_starts = d.aff_starts;
+    d.view.aff = d.aff;
+    d.view.n_aff8 = n_aff8;
+    std::memcpy(d.view.top, top, 24);
+    d.view.r_point = r_point;
+    d.view.nlog2 = nlog2;
+    d.view.n_tests = static_cast<int>(nt);
+    e->pcs.push_back(d);
+    e->committed = false;
+    return B200MP_OK;
+}
+
+int b200mp_env_sort(b200mp_env *e) {
+    if (!e) return fail(B200MP_ERR_INVALID, "b200mp_env_sort: env is NULL");
+    auto by = [](const auto &a, const auto &b) { return a.min_d < b.min_d; };  // environment.hh:43-69
+    std::sort(e->spheres.begin(), e->spheres.end(), by);
+    std::sort(e->capsules.begin(), e->capsules.end(), by);
+    std::sort(e->zcapsules.begin(), e->zcapsules.end(), by);
+    std::sort(e->cuboids.begin(), e->cuboids.end(), by);
+    std::sort(e->zcuboids.begin(), e->zcuboids.end(), by);
+    e->committed = false;
+    return B200MP_OK;
+}
+
+int64_t b200mp_env_min_distances(const b200mp_env *e, int kind, float *out) {
+    if (!e) return -1;
+    auto dump = [&](const auto &v) -> int64_t {
+        if (out) for (size_t i = 0; i < v.size(); ++i) out[i] = v[i].min_d;
+        return static_cast<int64_t>(v.size());
+    };
+    switch (kind) {
+        case 0: return dump(e->spheres);
+        case 1: return dump(e->capsules);
+        case 2: return dump(e->zcapsules);
+        case 3: return dump(e->cuboids);
+        case 4: return dump(e->zcuboids);
+        default: return -1;
+    }
+}
+
+int b200mp_env_commit(b200mp_env *e) {
+    if (!e) return fail(B200MP_ERR_INVALID, "b200mp_env_commit: env is NULL");
+    B200_CUDA(cudaSetDevice(e->ctx->device));
+    std::vector<float> blob;
+    auto align4 = [&]() { while (blob.size() % 4) blob.push_back(0.f); };
+    // prefmax[i] = max(min_d[0..i]): the ordered scan of a sphere with extent `ext` reaches obstacle i
+    // iff prefmax[i-1] < ext ... i.e. it tests exactly the first #{prefmax < ext} obstacles (validity.hh:61-67).
+    auto push_pm = [&](const auto &v) {
+        float m = -INFINITY;
+        for (const auto &o : v) {
+            m = std::max(m, o.min_d);
+            blob.push_back(m);
+        }
+        align4();
+    };
+    SceneDesc d{};
+    d.n_sph = static_cast<int>(e->spheres.size());
+    d.n_cap = static_cast<int>(e->capsules.size());
+    d.n_zcap = static_cast<int>(e->zcapsules.size());
+    d.n_cub = static_cast<int>(e->cuboids.size());
+    d.n_zcub = static_cast<int>(e->zcuboids.size());
+    d.off_sph = static_cast<int>(blob.size());
+    for (const auto &s : e->spheres) blob.insert(blob.end(), {s.x, s.y, s.z, s.r});
+    d.off_sph_pm = static_cast<int>(blob.size());
+    push_pm(e->spheres);
+    d.off_cap = static_cast<int>(blob.size());
+    for (const auto &c : e->capsules) blob.insert(blob.end(), {c.x1, c.y1, c.z1, c.r, c.xv, c.yv, c.zv, c.rdv});
+    d.off_cap_pm = static_cast<int>(blob.size());
+    push_pm(e->capsules);
+    d.off_zcap = static_cast<int>(blob.size());
+    for (const auto &c : e->zcapsules) blob.insert(blob.end(), {c.x1, c.y1, c.z1, c.r, c.zv, c.rdv, 0.f, 0.f});
+    d.off_zcap_pm = static_cast<int>(blob.size());
+    push_pm(e->zcapsules);
+    d.off_cub = static_cast<int>(blob.size());
+    for (const auto &c : e->cuboids)
+        blob.insert(blob.end(), {c.c[0], c.c[1], c.c[2], c.h[0], c.a1[0], c.a1[1], c.a1[2], c.h[1], c.a2[0], c.a2[1], c.a2[2], c.h[2],
+                                 c.a3[0], c.a3[1], c.a3[2], 0.f});
+    d.off_cub_pm = static_cast<int>(blob.size());
+    push_pm(e->cuboids);
+    d.off_zcub = static_cast<int>(blob.size());
+    for (const auto &c : e->zcuboids)
+        blob.insert(blob.end(), {c.c[0], c.c[1], c.c[2], c.h[2], c.a1[0], c.a1[1], c.h[0], 0.f, c.a2[0], c.a2[1], c.h[1], 0.f});
+    d.off_zcub_pm = static_cast<int>(blob.size());
+    push_pm(e->zcuboids);
+    align4();
+    d.blob_floats = static_cast<int>(blob.size());
+    const size_t bytes = blob.size() * 4;
+    // dynamic shared memory budget: opt-in maximum minus static use (barrier) and a margin
+    const size_t budget = static_cast<size_t>(e->ctx->max_smem_optin) - 1024;
+    if (bytes * 2 > budget && bytes > budget)
+        return fail(B200MP_ERR_CAPACITY, "b200mp_env_commit: scene needs %zu bytes of shared memory, limit %zu", bytes, budget);
+    env_free_device(e);
+    B200_CUDA(cudaMalloc(&e->d_blob, std::max<size_t>(bytes, 16)));
+    if (bytes) B200_CUDA(cudaMemcpy(e->d_blob, blob.data(), bytes, cudaMemcpyHostToDevice));
+    d.blob = e->d_blob;
+    d.n_pc = static_cast<int>(e->pcs.size());
+    for (int i = 0; i < d.n_pc; ++i) d.pc[i] = e->pcs[i].view;
+    e->desc = d;
+    e->committed = true;
+    return B200MP_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------- launches
+namespace {
+
+template <class R>
+int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const float *d_q1, int64_t m, int resolution,
+                   uint8_t *d_valid, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4;
+    auto kern = validate_motions_kernel<R>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
+    if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_motions: kernel does not fit on an SM with %zu B of scene", smem);
+    const long long warps_needed = m;
+    long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    blocks = std::max<long long>(blocks, 1);
+    B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(LaunchCounters), st));
+    kern<<<static_cast<unsigned>(blocks), kBlockThreads, smem, st>>>(e->desc, d_q0, d_q1, m, resolution, d_valid,
+                                                                     static_cast<LaunchCounters *>(c->d_counters));
+    B200_CUDA(cudaGetLastError());
+    c->launches.fetch_add(1);
+    return B200MP_OK;
+}
+
+template <class R>
+int launch_states(b200mp_ctx *c, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4;
+    auto kern = validate_states_kernel<R>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
+    if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_states: kernel does not fit on an SM with %zu B of scene", smem);
+    const long long warps_needed = (m + 31) / 32;
+    long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    blocks = std::max<long long>(blocks, 1);
+    B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(LaunchCounters), st));
+    kern<<<static_cast<unsigned>(blocks), kBlockThreads, smem, st>>>(e->desc, d_q, m, d_valid, static_cast<LaunchCounters *>(c->d_counters));
+    B200_CUDA(cudaGetLastError());
+    c->launches.fetch_add(1);
+    return B200MP_OK;
+}
+
+int check_common(const char *who, b200mp_ctx *c, const b200mp_env *e, const void *a, const void *out, int64_t m) {
+    if (!c || !e) return fail(B200MP_ERR_INVALID, "%s: NULL handle", who);
+    if (e->ctx != c) return fail(B200MP_ERR_INVALID, "%s: environment belongs to another context", who);
+    if (!e->committed) return fail(B200MP_ERR_STATE, "%s: environment not committed (call b200mp_env_commit)", who);
+    if (m < 0 || (m > 0 && (!a || !out))) return fail(B200MP_ERR_INVALID, "%s: bad buffer or count", who);
+    return B200MP_OK;
+}
+
+// host float -> device float (direct) or host double -> pinned float staging -> device
+template <typename T>
+int upload_states(b200mp_ctx *c, const T *h, int64_t count, float *d, cudaStream_t st) {
+    if (std::is_same<T, float>::value) {
+        B200_CUDA(cudaMemcpyAsync(d, h, count * sizeof(float), cudaMemcpyHostToDevice, st));
+        return B200MP_OK;
+    }
+    float *stage = nullptr;
+    B200_CUDA(cudaMallocHost(&stage, std::max<int64_t>(count, 1) * sizeof(float)));
+    for (int64_t i = 0; i < count; ++i) stage[i] = static_cast<float>(h[i]);  // ompl_to_vamp: static_cast<float>(values[i])
+    cudaError_t err = cudaMemcpyAsync(d, stage, count * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    cudaFreeHost(stage);
+    B200_CUDA(err);
+    return B200MP_OK;
+}
+
+template <typename T>
+int validate_motions_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T *q0, const T *q1, int64_t m, int resolution,
+                          uint8_t *valid) {
+    int rc = check_common("b200mp_validate_motions", c, e, q0, valid, m);
+    if (rc) return rc;
+    if (m > 0 && !q1) return fail(B200MP_ERR_INVALID, "b200mp_validate_motions: q1 is NULL");
+    int dim = 0, res = 0;
+    rc = b200mp_robot_info(robot, &dim, nullptr, &res, nullptr, nullptr);
+    if (rc) return rc;
+    if (m == 0) return B200MP_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    B200_CUDA(cudaSetDevice(c->device));
+    const size_t qbytes = static_cast<size_t>(m) * dim * sizeof(float);
+    rc = c->scratch.reserve(2 * qbytes + static_cast<size_t>(m) + 256);
+    if (rc) return rc;
+    float *d_q0 = reinterpret_cast<float *>(c->scratch.ptr);
+    float *d_q1 = reinterpret_cast<float *>(c->scratch.ptr + qbytes);
+    uint8_t *d_valid = reinterpret_cast<uint8_t *>(c->scratch.ptr + 2 * qbytes);
+    if ((rc = upload_states(c, q0, m * dim, d_q0, c->stream))) return rc;
+    if ((rc = upload_states(c, q1, m * dim, d_q1, c->stream))) return rc;
+    rc = b200mp_validate_motions_device(c, robot, e, d_q0, d_q1, m, resolution, d_valid, c->stream);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(valid, d_valid, static_cast<size_t>(m), cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    return B200MP_OK;
+}
+
+template <typename T>
+int validate_states_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T *q, int64_t m, uint8_t *valid) {
+    int rc = check_common("b200mp_validate_states", c, e, q, valid, m);
+    if (rc) return rc;
+    int dim = 0;
+    rc = b200mp_robot_info(robot, &dim, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (m == 0) return B200MP_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    B200_CUDA(cudaSetDevice(c->device));
+    const size_t qbytes = static_cast<size_t>(m) * dim * sizeof(float);
+    rc = c->scratch.reserve(qbytes + static_cast<size_t>(m) + 256);
+    if (rc) return rc;
+    float *d_q = reinterpret_cast<float *>(c->scratch.ptr);
+    uint8_t *d_valid = reinterpret_cast<uint8_t *>(c->scratch.ptr + qbytes);
+    if ((rc = upload_states(c, q, m * dim, d_q, c->stream))) return rc;
+    rc = b200mp_validate_states_device(c, robot, e, d_q, m, d_valid, c->stream);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(valid, d_valid, static_cast<size_t>(m), cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    return B200MP_OK;
+}
+
+// dependent FFMA chains: 8 independent accumulators per thread
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200mp_validate_motions_device(b200mp_ctx *c, int robot, const b200mp_env *e, const float *d_q0, const float *d_q1, int64_t m,
+                                   int resolution, uint8_t *d_valid, void *stream) {
+    int rc = check_common("b200mp_validate_motions_device", c, e, d_q0, d_valid, m);
+    if (rc) return rc;
+    if (m == 0) return B200MP_OK;
+    if (!d_q1) return fail(B200MP_ERR_INVALID, "b200mp_validate_motions_device: d_q1 is NULL");
+    if (resolution < 0) return fail(B200MP_ERR_INVALID, "b200mp_validate_motions_device: negative resolution");
+    B200_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    switch (robot) {
+        case B200MP_ROBOT_PANDA: return launch_motions<Panda>(c, e, d_q0, d_q1, m, resolution ? resolution : Panda::kResolution, d_valid, st);
+        case B200MP_ROBOT_FETCH: return launch_motions<Fetch>(c, e, d_q0, d_q1, m, resolution ? resolution : Fetch::kResolution, d_valid, st);
+        default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
+    }
+}
+
+int b200mp_validate_states_device(b200mp_ctx *c, int robot, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid,
+                                  void *stream) {
+    int rc = check_common("b200mp_validate_states_device", c, e, d_q, d_valid, m);
+    if (rc) return rc;
+    if (m == 0) return B200MP_OK;
+    B200_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    switch (robot) {
+        case B200MP_ROBOT_PANDA: return launch_states<Panda>(c, e, d_q, m, d_valid, st);
+        case B200MP_ROBOT_FETCH: return launch_states<Fetch>(c, e, d_q, m, d_valid, st);
+        default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
+    }
+}
+
+int b200mp_validate_motions(b200mp_ctx *c, int robot, const b200mp_env *e, const float *q0, const float *q1, int64_t m, int resolution,
+                            uint8_t *valid) {
+    return validate_motions_host<float>(c, robot, e, q0, q1, m, resolution, valid);
+}
+int b200mp_validate_motions_f64(b200mp_ctx *c, int robot, const b200mp_env *e, const double *q0, const double *q1, int64_t m,
+                                int resolution, uint8_t *valid) {
+    return validate_motions_host<double>(c, robot, e, q0, q1, m, resolution, valid);
+}
+int b200mp_validate_states(b200mp_ctx *c, int robot, const b200mp_env *e, const float *q, int64_t m, uint8_t *valid) {
+    return validate_states_host<float>(c, robot, e, q, m, valid);
+}
+int b200mp_validate_states_f64(b200mp_ctx *c, int robot, const b200mp_env *e, const double *q, int64_t m, uint8_t *valid) {
+    return validate_states_host<double>(c, robot, e, q, m, valid);
+}
+
+int b200mp_fp32_peak(b200mp_ctx *c, int iters, double *tflops) {
+    if (!c || !tflops || iters < 1) return fail(B200MP_ERR_INVALID, "b200mp_fp32_peak: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    B200_CUDA(cudaSetDevice(c->device));
+    const int blocks = c->sm_count * 8, threads = 256;
+    int rc = c->scratch.reserve(static_cast<size_t>(blocks) * threads * 4);
+    if (rc) return rc;
+    cudaEvent_t a, b;
+    B200_CUDA(cudaEventCreate(&a));
+    B200_CUDA(cudaEventCreate(&b));
+    fp32_peak_kernel<<<blocks, threads, 0, c->stream>>>(reinterpret_cast<float *>(c->scratch.ptr), 16, 0.999f, 1e-3f);  // warm up
+    B200_CUDA(cudaEventRecord(a, c->stream));
+    fp32_peak_kernel<<<blocks, threads, 0, c->stream>>>(reinterpret_cast<float *>(c->scratch.ptr), iters, 0.999f, 1e-3f);
+    B200_CUDA(cudaEventRecord(b, c->stream));
+    B200_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    B200_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    c->launches.fetch_add(2);
+    const double flops = 2.0 * 8 * 16 * static_cast<double>(iters) * blocks * threads;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return B200MP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// Host-side state shared by the translation units of libb200mp.so.
+#pragma once
+#include <atomic>
+#include <cstddef>
+#include <cstdint>
+#include <mutex>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/b200mp.h"
+
+namespace b200mp {
+
+int fail(int code, const char *fmt, ...);
+
+#define B200_CUDA(expr)                                                                                         \
+    do {                                                                                                        \
+        cudaError_t _e = (expr);                                                                                \
+        if (_e != cudaSuccess) {                                                                                \
+            cudaGetLastError();                                                                                 \
+            return ::b200mp::fail(B200MP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        }                                                                                                       \
+    } while (0)
+
+// grow-only device scratch buffer
+struct Scratch {
+    char *ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return B200MP_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        B200_CUDA(cudaMalloc(&ptr, want));
+        cap = want;
+        return B200MP_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace b200mp
+
+struct b200mp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int cc_major = 0;
+    cudaStream_t stream = nullptr;
+    void *d_counters = nullptr;
+    b200mp::Scratch scratch;
+    std::mutex mu;
+    std::atomic<long long> launches{0};
+};

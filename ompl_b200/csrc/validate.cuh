@@ -1,0 +1,569 @@
+// Motion / state validation kernels (sm_100a).
+//
+// One warp per motion: lane l of a pass holds the state of rake (l >> 3), sample (l & 7), i.e. the warp covers 4 of
+// the reference's 8-wide "rakes" per pass (external/vamp/src/impl/vamp/planning/validate.hh:23-67). Every lane runs
+// the robot's forward kinematics in registers, link by link (generated robots/<robot>_gen.cuh), and tests the link's
+// bounding sphere, then its fine spheres, against the scene staged in shared memory with the reference's decision
+// semantics (external/vamp/src/impl/vamp/collision/validity.hh:46-150):
+//   * obstacles of each class are scanned in stored order; the scan of a sphere stops at the first obstacle whose
+//     min_distance is >= the sphere's max_extent in all 8 lanes of its rake  -> here: prefix length b = #{prefmax < ext}
+//     with ext taken as the max over the 8-lane group, found by binary search instead of a per-obstacle test;
+//   * collision <=> sign bit of (squared distance - squared radius sum)  -> strict `< 0`;
+//   * a coarse hit in any lane of a rake triggers the fine tests for the whole rake; a fine hit invalidates the motion.
+// Control flow is warp-uniform: loop bounds are warp maxima, lanes mask their own results, exits are warp votes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "robot_common.cuh"
+
+namespace b200mp {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxPointClouds = 4;
+
+// Point-cloud tree in global memory (arrays as external/vamp/src/impl/vamp/collision/capt.hh:571-613 stores them).
+struct CaptView {
+    const float *tests;
+    const float *aabbs;           // [leaf][6]
+    const uint32_t *aff_starts;   // [leaves + 1], units of 8-point vectors
+    const float *aff;             // [3][n_aff8 * 8]
+    long long n_aff8;
+    float top[6];
+    float r_point;
+    int nlog2;
+    int n_tests;
+};
+
+// Scene as one packed float blob (16-byte aligned sections). Offsets are in floats.
+struct SceneDesc {
+    const float *blob;
+    int blob_floats;  // multiple of 4
+    int n_sph, n_cap, n_zcap, n_cub, n_zcub;
+    int off_sph, off_sph_pm;      // float4 (x,y,z,r)                                  ; prefmax[n]
+    int off_cap, off_cap_pm;      // 2 x float4 (x1,y1,z1,r) (xv,yv,zv,rdv)
+    int off_zcap, off_zcap_pm;    // 2 x float4 (x1,y1,z1,r) (zv,rdv,0,0)
+    int off_cub, off_cub_pm;      // 4 x float4 (cx,cy,cz,h1) (a1x,a1y,a1z,h2) (a2x,a2y,a2z,h3) (a3x,a3y,a3z,0)
+    int off_zcub, off_zcub_pm;    // 3 x float4 (cx,cy,cz,h3) (a1x,a1y,h1,0) (a2x,a2y,h2,0)
+    int n_pc;
+    CaptView pc[kMaxPointClouds];
+};
+
+// Pointers into the staged copy.
+struct Scene {
+    const float4 *sph; const float *sph_pm; int n_sph;
+    const float4 *cap; const float *cap_pm; int n_cap;
+    const float4 *zcap; const float *zcap_pm; int n_zcap;
+    const float4 *cub; const float *cub_pm; int n_cub;
+    const float4 *zcub; const float *zcub_pm; int n_zcub;
+};
+
+__device__ __forceinline__ Scene scene_view(const SceneDesc &d, const float *base) {
+    Scene s;
+    s.sph = reinterpret_cast<const float4 *>(base + d.off_sph); s.sph_pm = base + d.off_sph_pm; s.n_sph = d.n_sph;
+    s.cap = reinterpret_cast<const float4 *>(base + d.off_cap); s.cap_pm = base + d.off_cap_pm; s.n_cap = d.n_cap;
+    s.zcap = reinterpret_cast<const float4 *>(base + d.off_zcap); s.zcap_pm = base + d.off_zcap_pm; s.n_zcap = d.n_zcap;
+    s.cub = reinterpret_cast<const float4 *>(base + d.off_cub); s.cub_pm = base + d.off_cub_pm; s.n_cub = d.n_cub;
+    s.zcub = reinterpret_cast<const float4 *>(base + d.off_zcub); s.zcub_pm = base + d.off_zcub_pm; s.n_zcub = d.n_zcub;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------ TMA bulk staging
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// Copy the scene blob global -> shared with the bulk async-copy engine (cp.async.bulk, SASS UBLKCP), completion
+// tracked by an mbarrier. Called by the whole block; returns after the data has landed and is visible to all threads.
+__device__ __forceinline__ void stage_scene(float *dst, const float *src, int n_floats, unsigned long long *bar) {
+    const uint32_t bar_a = smem_u32(bar);
+    const uint32_t bytes = static_cast<uint32_t>(n_floats) * 4u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bytes > 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        constexpr uint32_t kChunk = 32768u;
+        for (uint32_t off = 0; off < bytes; off += kChunk) {
+            const uint32_t n = min(kChunk, bytes - off);
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(smem_u32(reinterpret_cast<char *>(dst) + off)), "l"(reinterpret_cast<const char *>(src) + off), "r"(n),
+                "r"(bar_a)
+                : "memory");
+        }
+    }
+    if (bytes > 0) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_a)
+                : "memory");
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+// number of leading entries of the non-decreasing array pm[0..n) that are < ext
+__device__ __forceinline__ int count_lt(const float *pm, int n, float ext) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pm[mid] < ext) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+    if (G >= 2) v = fmaxf(v, __shfl_xor_sync(kFull, v, 1));
+    if (G >= 4) v = fmaxf(v, __shfl_xor_sync(kFull, v, 2));
+    if (G >= 8) v = fmaxf(v, __shfl_xor_sync(kFull, v, 4));
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ bool group_any(bool p) {
+    if (G == 1) return p;
+    const unsigned b = __ballot_sync(kFull, p);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned gm = ((1u << G) - 1u) << (lane & ~(static_cast<unsigned>(G) - 1u));
+    return (b & gm) != 0u;
+}
+
+// Exit policy of a scan loop, evaluated every 8 obstacles:
+//  kUntilAllHit : stop once every lane has a hit or is not participating (coarse tests; state kernel)
+//  kAnyHit      : stop as soon as any participating lane has a hit (fine tests of the motion kernel: the motion is dead)
+enum ExitPolicy { kUntilAllHit = 0, kAnyHit = 1 };
+
+template <int POLICY>
+__device__ __forceinline__ bool scan_should_stop(bool hit, bool participating) {
+    if (POLICY == kAnyHit) return __any_sync(kFull, hit);
+    return __all_sync(kFull, hit || !participating);
+}
+
+// T robot spheres per lane against every obstacle class. b* are per-sphere prefix lengths (0 for idle slots).
+template <int T>
+struct Tile {
+    float x[T], y[T], z[T], r[T];
+    float ext[T];  // group max_extent, -inf for idle slots / idle lanes
+};
+
+template <int T, int POLICY>
+__device__ __forceinline__ bool scan_scene(const Scene &sc, const Tile<T> &s, bool participating) {
+    bool hit = false;
+    int b[T];
+
+    // ---- spheres (collision/sphere_sphere.hh:10-23)
+    if (sc.n_sph > 0) {
+        int bl = 0;
+#pragma unroll
+        for (int t = 0; t < T; ++t) { b[t] = count_lt(sc.sph_pm, sc.n_sph, s.ext[t]); bl = max(bl, b[t]); }
+        const int B = __reduce_max_sync(kFull, bl);
+#pragma unroll 2
+        for (int i = 0; i < B; ++i) {
+            const float4 o = sc.sph[i];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const float xs = o.x - s.x[t], ys = o.y - s.y[t], zs = o.z - s.z[t];
+                const float sum = fmaf(zs, zs, fmaf(ys, ys, xs * xs));
+                const float rs = o.w + s.r[t];
+                const float d = fmaf(-rs, rs, sum);
+                hit |= (d < 0.0f) & (i < b[t]);
+            }
+            if ((i & 7) == 7 && scan_should_stop<POLICY>(hit, participating)) break;
+        }
+        if (scan_should_stop<POLICY>(hit, participating)) return hit;
+    }
+    // ---- capsules (collision/sphere_capsule.hh:9-23)
+    if (sc.n_cap > 0) {
+        int bl = 0;
+#pragma unroll
+        for (int t = 0; t < T; ++t) { b[t] = count_lt(sc.cap_pm, sc.n_cap, s.ext[t]); bl = max(bl, b[t]); }
+        const int B = __reduce_max_sync(kFull, bl);
+        for (int i = 0; i < B; ++i) {
+            const float4 p = sc.cap[2 * i], v = sc.cap[2 * i + 1];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const float dot = fmaf(s.z[t] - p.z, v.z, fmaf(s.y[t] - p.y, v.y, (s.x[t] - p.x) * v.x));
+                const float cdf = fminf(fmaxf(dot * v.w, 0.0f), 1.0f);
+                const float xs = s.x[t] - fmaf(v.x, cdf, p.x), ys = s.y[t] - fmaf(v.y, cdf, p.y), zs = s.z[t] - fmaf(v.z, cdf, p.z);
+                const float sum = fmaf(zs, zs, fmaf(ys, ys, xs * xs));
+                const float rs = s.r[t] + p.w;
+                const float d = fmaf(-rs, rs, sum);
+                hit |= (d < 0.0f) & (i < b[t]);
+            }
+            if ((i & 7) == 7 && scan_should_stop<POLICY>(hit, participating)) break;
+        }
+        if (scan_should_stop<POLICY>(hit, participating)) return hit;
+    }
+    // ---- z-aligned capsules (collision/sphere_capsule.hh:31-44)
+    if (sc.n_zcap > 0) {
+        int bl = 0;
+#pragma unroll
+        for (int t = 0; t < T; ++t) { b[t] = count_lt(sc.zcap_pm, sc.n_zcap, s.ext[t]); bl = max(bl, b[t]); }
+        const int B = __reduce_max_sync(kFull, bl);
+        for (int i = 0; i < B; ++i) {
+            const float4 p = sc.zcap[2 * i], v = sc.zcap[2 * i + 1];  // v.x = zv, v.y = rdv
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const float dot = (s.z[t] - p.z) * v.x;
+                const float cdf = fminf(fmaxf(dot * v.y, 0.0f), 1.0f);
+                const float xs = s.x[t] - p.x, ys = s.y[t] - p.y, zs = s.z[t] - fmaf(v.x, cdf, p.z);
+                const float sum = fmaf(zs, zs, fmaf(ys, ys, xs * xs));
+                const float rs = s.r[t] + p.w;
+                const float d = fmaf(-rs, rs, sum);
+                hit |= (d < 0.0f) & (i < b[t]);
+            }
+            if ((i & 7) == 7 && scan_should_stop<POLICY>(hit, participating)) break;
+        }
+        if (scan_should_stop<POLICY>(hit, participating)) return hit;
+    }
+    // ---- cuboids (collision/sphere_cuboid.hh:9-27)
+    if (sc.n_cub > 0) {
+        int bl = 0;
+        float rsq[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) { b[t] = count_lt(sc.cub_pm, sc.n_cub, s.ext[t]); bl = max(bl, b[t]); rsq[t] = s.r[t] * s.r[t]; }
+        const int B = __reduce_max_sync(kFull, bl);
+        for (int i = 0; i < B; ++i) {
+            const float4 c = sc.cub[4 * i], a1 = sc.cub[4 * i + 1], a2 = sc.cub[4 * i + 2], a3 = sc.cub[4 * i + 3];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const float xs = s.x[t] - c.x, ys = s.y[t] - c.y, zs = s.z[t] - c.z;
+                const float e1 = fmaxf(fabsf(fmaf(a1.z, zs, fmaf(a1.y, ys, a1.x * xs))) - c.w, 0.0f);
+                const float e2 = fmaxf(fabsf(fmaf(a2.z, zs, fmaf(a2.y, ys, a2.x * xs))) - a1.w, 0.0f);
+                const float e3 = fmaxf(fabsf(fmaf(a3.z, zs, fmaf(a3.y, ys, a3.x * xs))) - a2.w, 0.0f);
+                const float d = fmaf(e3, e3, fmaf(e2, e2, e1 * e1)) - rsq[t];
+                hit |= (d < 0.0f) & (i < b[t]);
+            }
+            if ((i & 7) == 7 && scan_should_stop<POLICY>(hit, participating)) break;
+        }
+        if (scan_should_stop<POLICY>(hit, participating)) return hit;
+    }
+    // ---- z-aligned cuboids (collision/sphere_cuboid.hh:35-52)
+    if (sc.n_zcub > 0) {
+        int bl = 0;
+        float rsq[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) { b[t] = count_lt(sc.zcub_pm, sc.n_zcub, s.ext[t]); bl = max(bl, b[t]); rsq[t] = s.r[t] * s.r[t]; }
+        const int B = __reduce_max_sync(kFull, bl);
+        for (int i = 0; i < B; ++i) {
+            const float4 c = sc.zcub[3 * i], a1 = sc.zcub[3 * i + 1], a2 = sc.zcub[3 * i + 2];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const float xs = s.x[t] - c.x, ys = s.y[t] - c.y, zs = s.z[t] - c.z;
+                const float e1 = fmaxf(fabsf(fmaf(a1.y, ys, a1.x * xs)) - a1.z, 0.0f);
+                const float e2 = fmaxf(fabsf(fmaf(a2.y, ys, a2.x * xs)) - a2.z, 0.0f);
+                const float e3 = fmaxf(fabsf(zs) - c.w, 0.0f);
+                const float d = fmaf(e3, e3, fmaf(e2, e2, e1 * e1)) - rsq[t];
+                hit |= (d < 0.0f) & (i < b[t]);
+            }
+            if ((i & 7) == 7 && scan_should_stop<POLICY>(hit, participating)) break;
+        }
+    }
+    return hit;
+}
+
+// ------------------------------------------------------------------------------------------------ point clouds
+__device__ __forceinline__ float aabb_distsq(const float *bb, float x, float y, float z) {
+    const float d0 = x - fminf(fmaxf(x, bb[0]), bb[3]);
+    const float d1 = y - fminf(fmaxf(y, bb[1]), bb[4]);
+    const float d2 = z - fminf(fmaxf(z, bb[2]), bb[5]);
+    return d0 * d0 + d1 * d1 + d2 * d2;
+}
+
+// One sphere against one tree (collision/capt.hh:366-407 / :425-506): top AABB reject, nlog2 dependent loads down
+// the implicit tree, leaf AABB reject, then the leaf's affordance list; hit <=> distsq <= (r + r_point)^2.
+__device__ __forceinline__ bool capt_collides(const CaptView &t, float x, float y, float z, float r) {
+    r += t.r_point;
+    const float rsq = r * r;
+    if (aabb_distsq(t.top, x, y, z) > rsq) return false;
+    unsigned idx = 0;
+    float c0 = x, c1 = y, c2 = z;
+    for (int i = 0; i < t.nlog2; ++i) {
+        idx = 2u * idx + 1u + (c0 >= __ldg(t.tests + idx) ? 1u : 0u);
+        const float tmp = c0; c0 = c1; c1 = c2; c2 = tmp;  // cycle x, y, z
+    }
+    const unsigned leaf = idx - static_cast<unsigned>(t.n_tests);
+    const float *bb = t.aabbs + 6u * leaf;
+    float lb[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) lb[k] = __ldg(bb + k);
+    if (aabb_distsq(lb, x, y, z) > rsq) return false;
+    const unsigned beg = __ldg(t.aff_starts + leaf), end = __ldg(t.aff_starts + leaf + 1);
+    const float *ax = t.aff, *ay = t.aff + t.n_aff8 * 8, *az = t.aff + 2 * t.n_aff8 * 8;
+    for (unsigned i = beg * 8u; i < end * 8u; i += 4u) {
+        const float4 px = __ldg(reinterpret_cast<const float4 *>(ax + i));
+        const float4 py = __ldg(reinterpret_cast<const float4 *>(ay + i));
+        const float4 pz = __ldg(reinterpret_cast<const float4 *>(az + i));
+        float dx = px.x - x, dy = py.x - y, dz = pz.x - z;
+        bool h = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= rsq;
+        dx = px.y - x; dy = py.y - y; dz = pz.y - z;
+        h |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= rsq;
+        dx = px.z - x; dy = py.z - y; dz = pz.z - z;
+        h |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= rsq;
+        dx = px.w - x; dy = py.w - y; dz = pz.w - z;
+        h |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= rsq;
+        if (h) return true;
+    }
+    return false;
+}
+
+template <int T>
+__device__ __forceinline__ bool scan_pointclouds(const SceneDesc &d, const Tile<T> &s, bool participating) {
+    bool hit = false;
+    for (int p = 0; p < d.n_pc; ++p) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            // idle slots carry ext = -inf
+            if (participating && s.ext[t] > -1e30f && !hit) hit = capt_collides(d.pc[p], s.x[t], s.y[t], s.z[t], s.r[t]);
+        }
+    }
+    return hit;
+}
+
+// ------------------------------------------------------------------------------------------------ one state per lane
+// Returns true when this lane's state is collision free. `active` lanes take part; idle lanes only follow the
+// warp-uniform control flow. G = lanes per reference rake (8 for motions, 1 for single states).
+// EDGE: all lanes belong to one motion, so the first hit anywhere ends the whole warp's work.
+template <class R, int G, bool EDGE>
+__device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, bool active) {
+    constexpr int FT = 4;  // fine spheres processed together per lane
+    constexpr int POLICY = EDGE ? kAnyHit : kUntilAllHit;
+    const typename R::Tables &tb = R::tables();
+    bool alive = active;  // false once this lane's state is known to collide (or lane idle)
+
+    // ---------------- stage 1: environment vs robot, frames streamed base -> tip
+    Frame F;
+    frame_identity(F);
+#pragma unroll 1
+    for (int k = 0; k < R::kFrames; ++k) {
+        if (k > 0) R::advance(k, F, q);
+#pragma unroll 1
+        for (int l = tb.frame_link_begin[k]; l < tb.frame_link_begin[k + 1]; ++l) {
+            // bounding sphere of the link
+            Tile<1> c;
+            const float4 cl = tb.coarse[l];
+            frame_apply(F, cl.x, cl.y, cl.z, c.x[0], c.y[0], c.z[0]);
+            c.r[0] = cl.w;
+            const float ext = alive ? sqrtf(fmaf(c.z[0], c.z[0], fmaf(c.y[0], c.y[0], c.x[0] * c.x[0]))) + cl.w : -INFINITY;
+            c.ext[0] = group_max<G>(ext);
+            bool chit = scan_scene<1, kUntilAllHit>(sc, c, alive);
+            if (sd.n_pc > 0) chit |= scan_pointclouds<1>(sd, c, alive && !chit);
+            const bool need = group_any<G>(chit && alive) && alive;
+            if (!__any_sync(kFull, need)) continue;
+            // fine spheres of the link, FT at a time
+            const int fb = tb.link_begin[l], fe = tb.link_begin[l + 1];
+            bool fhit = false;
+#pragma unroll 1
+            for (int f0 = fb; f0 < fe; f0 += FT) {
+                Tile<FT> s;
+#pragma unroll
+                for (int t = 0; t < FT; ++t) {
+                    const int fi = min(f0 + t, fe - 1);
+                    const float4 fl = tb.fine[fi];
+                    frame_apply(F, fl.x, fl.y, fl.z, s.x[t], s.y[t], s.z[t]);
+                    s.r[t] = fl.w;
+                    const bool on = need && (f0 + t < fe);
+                    const float e = on ? sqrtf(fmaf(s.z[t], s.z[t], fmaf(s.y[t], s.y[t], s.x[t] * s.x[t]))) + fl.w : -INFINITY;
+                    s.ext[t] = group_max<G>(e);
+                    if (!on) s.ext[t] = -INFINITY;
+                }
+                fhit |= scan_scene<FT, POLICY>(sc, s, need && !fhit);
+                if (sd.n_pc > 0) fhit |= scan_pointclouds<FT>(sd, s, need && !fhit);
+                if (EDGE) {
+                    if (__any_sync(kFull, fhit)) return !fhit;
+                } else {
+                    if (__all_sync(kFull, fhit || !need)) break;
+                }
+            }
+            if (fhit) alive = false;
+            if (!EDGE && !__any_sync(kFull, alive)) return false;
+        }
+    }
+
+    // ---------------- stage 2: allowed self-collision pairs (collision/validity.hh:13-44), frames streamed again
+    Frame S[R::kSlots];
+#pragma unroll
+    for (int i = 0; i < R::kSlots; ++i) frame_identity(S[i]);
+    frame_identity(F);
+#pragma unroll 1
+    for (int k = 0; k < R::kFrames; ++k) {
+        if (k > 0) R::advance(k, F, q);
+#pragma unroll 1
+        for (int p = tb.pair_frame_begin[k]; p < tb.pair_frame_begin[k + 1]; ++p) {
+            const int la = tb.pair_a[p], lb = tb.pair_b[p], slot = tb.pair_slot[p];
+            Frame A;
+            if (slot == -2) frame_identity(A);
+            else if (slot == -1) A = F;
+            else {
+                A = S[0];
+#pragma unroll
+                for (int i = 1; i < R::kSlots; ++i) if (slot == i) A = S[i];
+            }
+            const float4 ca = tb.coarse[la], cb = tb.coarse[lb];
+            float ax, ay, az, bx, by, bz;
+            frame_apply(A, ca.x, ca.y, ca.z, ax, ay, az);
+            frame_apply(F, cb.x, cb.y, cb.z, bx, by, bz);
+            {
+                const float xs = ax - bx, ys = ay - by, zs = az - bz;
+                const float rs = ca.w + cb.w;
+                const float d = fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs)));
+                const bool need = group_any<G>((d < 0.0f) && alive) && alive;
+                if (!__any_sync(kFull, need)) continue;
+                const int ab = tb.link_begin[la], ae = tb.link_begin[la + 1];
+                const int bb = tb.link_begin[lb], be = tb.link_begin[lb + 1];
+                bool fhit = false;
+#pragma unroll 1
+                for (int j0 = bb; j0 < be; j0 += FT) {
+                    float px[FT], py[FT], pz[FT], pr[FT];
+#pragma unroll
+                    for (int t = 0; t < FT; ++t) {
+                        const float4 fl = tb.fine[min(j0 + t, be - 1)];
+                        frame_apply(F, fl.x, fl.y, fl.z, px[t], py[t], pz[t]);
+                        pr[t] = fl.w;  // idle slots (j0 + t >= be) are masked below
+                    }
+#pragma unroll 1
+                    for (int i = ab; i < ae; ++i) {
+                        const float4 al = tb.fine[i];
+                        float qx, qy, qz;
+                        frame_apply(A, al.x, al.y, al.z, qx, qy, qz);
+#pragma unroll
+                        for (int t = 0; t < FT; ++t) {
+                            const float xs2 = qx - px[t], ys2 = qy - py[t], zs2 = qz - pz[t];
+                            const float rs2 = al.w + pr[t];
+                            const float d2 = fmaf(-rs2, rs2, fmaf(zs2, zs2, fmaf(ys2, ys2, xs2 * xs2)));
+                            fhit |= (d2 < 0.0f) & (j0 + t < be);
+                        }
+                    }
+                    fhit &= need;
+                    if (EDGE) {
+                        if (__any_sync(kFull, fhit)) return !fhit;
+                    } else {
+                        if (__all_sync(kFull, fhit || !need)) break;
+                    }
+                }
+                if (fhit) alive = false;
+                if (!EDGE && !__any_sync(kFull, alive)) return false;
+            }
+        }
+        const int sv = tb.save_slot[k];
+        if (sv >= 0) {
+#pragma unroll
+            for (int i = 0; i < R::kSlots; ++i) if (sv == i) S[i] = F;
+        }
+    }
+    return alive;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct LaunchCounters {
+    unsigned long long next;  // dynamic work queue head
+};
+
+constexpr int kBlockThreads = 256;
+constexpr int kWarpsPerBlock = kBlockThreads / 32;
+
+// horizontal sum in the reference's order (external/vamp/src/impl/vamp/vector/avx.hh:442-452): lanes padded to 8
+template <int DIM>
+__device__ __forceinline__ float vamp_l2_norm(const float (&v)[DIM]) {
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) s[i & 7] = fmaf(v[i], v[i], s[i & 7]);  // rows are summed first (DIM <= 8: one row)
+    const float s0 = s[4] + s[0], s1 = s[5] + s[1], s2 = s[6] + s[2], s3 = s[7] + s[3];
+    return sqrtf((s0 + s2) + (s1 + s3));
+}
+
+// One warp per motion; motions are taken from a global queue (edge cost varies by 100x with early exit).
+template <class R>
+__global__ void __launch_bounds__(kBlockThreads, 2)
+validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float *__restrict__ q1, long long m, int resolution,
+                        uint8_t *__restrict__ valid, LaunchCounters *cnt) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ unsigned long long bar;
+    stage_scene(smem, sd.blob, sd.blob_floats, &bar);
+    const Scene sc = scene_view(sd, smem);
+    constexpr int D = R::kDim;
+    const int lane = threadIdx.x & 31;
+    const int rake_in_pass = lane >> 3;
+    const float pct = static_cast<float>((lane & 7) + 1) / 8.0f;
+
+    for (;;) {
+        unsigned long long e = 0;
+        if (lane == 0) e = atomicAdd(&cnt->next, 1ull);
+        e = __shfl_sync(kFull, e, 0);
+        if (e >= static_cast<unsigned long long>(m)) break;
+
+        float a[D], v[D], q[D], back[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            a[j] = __ldg(q0 + e * D + j);
+            v[j] = __ldg(q1 + e * D + j) - a[j];
+        }
+        const float dist = vamp_l2_norm<D>(v);
+        // n = max(ceil(dist / rake * resolution), 1)  (planning/validate.hh:41)
+        const float nf = fmaxf(ceilf(dist / 8.0f * static_cast<float>(resolution)), 1.0f);
+        const int n = static_cast<int>(nf);
+        const float denom = static_cast<float>(8 * n);
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            q[j] = fmaf(v[j], pct, a[j]);  // block = start + vector * percents
+            back[j] = v[j] / denom;        // backstep = vector / (rake * n)
+        }
+        // this lane's first rake: `rake_in_pass` sequential back-steps, exactly as the reference accumulates them
+        for (int r = 0; r < rake_in_pass; ++r) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) q[j] = q[j] - back[j];
+        }
+        bool ok = true;
+        for (int base = 0; base < n; base += 4) {
+            const bool active = (base + rake_in_pass) < n;
+            const bool good = check_state<R, 8, true>(q, sd, sc, active);
+            if (__any_sync(kFull, active && !good)) { ok = false; break; }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) q[j] = q[j] - back[j];
+            }
+        }
+        if (lane == 0) valid[e] = ok ? 1 : 0;
+    }
+}
+
+// One lane per state: VampStateValidityChecker::isValid = validate_motion<Robot, rake, 1>(q, q), i.e. one fkcc on
+// 8 identical lanes (src/ompl/vamp/VampStateValidityChecker.h:37-41) -> group size 1 here.
+template <class R>
+__global__ void __launch_bounds__(kBlockThreads, 2)
+validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, uint8_t *__restrict__ valid, LaunchCounters *cnt) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ unsigned long long bar;
+    stage_scene(smem, sd.blob, sd.blob_floats, &bar);
+    const Scene sc = scene_view(sd, smem);
+    constexpr int D = R::kDim;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(&cnt->next, 1ull);
+        w = __shfl_sync(kFull, w, 0);
+        const long long first = static_cast<long long>(w) * 32;
+        if (first >= m) break;
+        const long long i = first + lane;
+        const bool active = i < m;
+        float q[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) q[j] = active ? __ldg(qs + i * D + j) : 0.0f;
+        // validate_vector with start == goal: block = q + 0 * percents
+        const bool good = check_state<R, 1, false>(q, sd, sc, active);
+        if (active) valid[i] = good ? 1 : 0;
+    }
+}
+
+}  // namespace b200mp

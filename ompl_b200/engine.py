@@ -1,0 +1,221 @@
+"""ctypes binding of the b200mp C ABI (include/b200mp.h). No compute happens in Python and there is no
+CPU fallback: if the CUDA library is missing or no GPU is present, construction raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+ROBOTS = {"panda": 0, "fetch": 1}
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+
+
+class B200MPError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200mp error {code}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libb200mp.so")
+
+
+def load_library():
+    """Load libb200mp.so (built in-tree by __graft_entry__.build()). Raises if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise B200MPError(-1, f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+    L = C.CDLL(p)
+    L.b200mp_last_error.restype = C.c_char_p
+    L.b200mp_create.argtypes = [C.c_int, C.POINTER(_vp)]
+    L.b200mp_destroy.argtypes = [_vp]
+    L.b200mp_device.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.b200mp_synchronize.argtypes = [_vp]
+    L.b200mp_robot_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _vp]
+    L.b200mp_env_create.argtypes = [_vp, C.POINTER(_vp)]
+    L.b200mp_env_destroy.argtypes = [_vp]
+    L.b200mp_env_add_spheres.argtypes = [_vp, _vp, C.c_int]
+    L.b200mp_env_add_cuboids.argtypes = [_vp, _vp, C.c_int, C.c_int]
+    L.b200mp_env_add_capsules.argtypes = [_vp, _vp, C.c_int, C.c_int]
+    L.b200mp_env_add_capt.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, C.c_float, C.c_float, C.c_float]
+    L.b200mp_env_sort.argtypes = [_vp]
+    L.b200mp_env_commit.argtypes = [_vp]
+    L.b200mp_env_min_distances.argtypes = [_vp, C.c_int, _vp]
+    L.b200mp_env_min_distances.restype = _i64
+    L.b200mp_validate_states.argtypes = [_vp, C.c_int, _vp, _vp, _i64, _vp]
+    L.b200mp_validate_motions.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _vp]
+    L.b200mp_validate_states_f64.argtypes = [_vp, C.c_int, _vp, _vp, _i64, _vp]
+    L.b200mp_validate_motions_f64.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _vp]
+    L.b200mp_validate_states_device.argtypes = [_vp, C.c_int, _vp, _vp, _i64, _vp, _vp]
+    L.b200mp_validate_motions_device.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _vp, _vp]
+    L.b200mp_launch_count.argtypes = [_vp]
+    L.b200mp_launch_count.restype = _i64
+    L.b200mp_fp32_peak.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
+    _LIB = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise B200MPError(rc, load_library().b200mp_last_error().decode())
+
+
+def robot_info(robot: str) -> dict:
+    L = load_library()
+    d, ns, res = C.c_int(), C.c_int(), C.c_int()
+    lo = np.zeros(16, np.float32)
+    hi = np.zeros(16, np.float32)
+    _check(L.b200mp_robot_info(ROBOTS[robot], d, ns, res, lo.ctypes.data, hi.ctypes.data))
+    return dict(dim=d.value, n_spheres=ns.value, resolution=res.value, lo=lo[:d.value].copy(), hi=hi[:d.value].copy())
+
+
+def _host(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class Context:
+    """One engine context per GPU (b200mp_create)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        h = _vp()
+        _check(self._L.b200mp_create(device, C.byref(h)))
+        self._h = h
+        dev, sms = C.c_int(), C.c_int()
+        _check(self._L.b200mp_device(self._h, dev, sms))
+        self.device, self.sm_count = dev.value, sms.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200mp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(self._L.b200mp_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.b200mp_launch_count(self._h))
+
+    def fp32_peak_tflops(self, iters: int = 4096) -> float:
+        out = C.c_double()
+        _check(self._L.b200mp_fp32_peak(self._h, iters, C.byref(out)))
+        return out.value
+
+    # ---- host-buffer entry points (what the OMPL adapters call) ----
+    def validate_states(self, robot: str, env: "Environment", q) -> np.ndarray:
+        q = np.asarray(q)
+        dim = robot_info(robot)["dim"]
+        f64 = q.dtype == np.float64
+        q = _host(q, np.float64 if f64 else np.float32).reshape(-1, dim)
+        out = np.empty(q.shape[0], np.uint8)
+        fn = self._L.b200mp_validate_states_f64 if f64 else self._L.b200mp_validate_states
+        _check(fn(self._h, ROBOTS[robot], env._h, q.ctypes.data, q.shape[0], out.ctypes.data))
+        return out
+
+    def validate_motions(self, robot: str, env: "Environment", q0, q1, resolution: int = 0, out=None) -> np.ndarray:
+        q0 = np.asarray(q0)
+        dim = robot_info(robot)["dim"]
+        f64 = q0.dtype == np.float64
+        dt = np.float64 if f64 else np.float32
+        q0 = _host(q0, dt).reshape(-1, dim)
+        q1 = _host(q1, dt).reshape(-1, dim)
+        if q0.shape != q1.shape:
+            raise ValueError("q0 and q1 must have the same shape")
+        if out is None:
+            out = np.empty(q0.shape[0], np.uint8)
+        fn = self._L.b200mp_validate_motions_f64 if f64 else self._L.b200mp_validate_motions
+        _check(fn(self._h, ROBOTS[robot], env._h, q0.ctypes.data, q1.ctypes.data, q0.shape[0], resolution, out.ctypes.data))
+        return out
+
+    # ---- raw-pointer entry points (device or pinned host memory owned by the caller, e.g. torch tensors) ----
+    def validate_motions_ptr(self, robot: str, env: "Environment", q0_ptr: int, q1_ptr: int, m: int, valid_ptr: int,
+                             resolution: int = 0, device: bool = True, stream: int = 0):
+        if device:
+            _check(self._L.b200mp_validate_motions_device(self._h, ROBOTS[robot], env._h, q0_ptr, q1_ptr, m, resolution,
+                                                          valid_ptr, stream or None))
+        else:
+            _check(self._L.b200mp_validate_motions(self._h, ROBOTS[robot], env._h, q0_ptr, q1_ptr, m, resolution, valid_ptr))
+
+    def validate_states_ptr(self, robot: str, env: "Environment", q_ptr: int, m: int, valid_ptr: int, device: bool = True,
+                            stream: int = 0):
+        if device:
+            _check(self._L.b200mp_validate_states_device(self._h, ROBOTS[robot], env._h, q_ptr, m, valid_ptr, stream or None))
+        else:
+            _check(self._L.b200mp_validate_states(self._h, ROBOTS[robot], env._h, q_ptr, m, valid_ptr))
+
+
+class Environment:
+    """Mirror of vamp::collision::Environment<float> (collision/environment.hh:14-85): shape lists per class,
+    `sort()` by min_distance, then `commit()` uploads the scene to the GPU."""
+
+    def __init__(self, ctx: Context):
+        self._L = load_library()
+        self._ctx = ctx
+        h = _vp()
+        _check(self._L.b200mp_env_create(ctx._h, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._L.b200mp_env_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_spheres(self, xyzr):
+        a = _host(xyzr, np.float32).reshape(-1, 4)
+        _check(self._L.b200mp_env_add_spheres(self._h, a.ctypes.data, a.shape[0]))
+
+    def add_cuboids(self, c15, z_aligned: bool = False):
+        a = _host(c15, np.float32).reshape(-1, 15)
+        _check(self._L.b200mp_env_add_cuboids(self._h, a.ctypes.data, a.shape[0], int(z_aligned)))
+
+    def add_capsules(self, c7, z_aligned: bool = False):
+        a = _host(c7, np.float32).reshape(-1, 7)
+        _check(self._L.b200mp_env_add_capsules(self._h, a.ctypes.data, a.shape[0], int(z_aligned)))
+
+    def add_capt(self, t: dict):
+        tests = _host(t["tests"], np.float32)
+        aabbs = _host(t["aabbs"], np.float32)
+        starts = _host(t["aff_starts"], np.uint32)
+        aff = _host(t["aff"], np.float32)
+        top = _host(t["top"], np.float32)
+        _check(self._L.b200mp_env_add_capt(self._h, int(t["nlog2"]), tests.ctypes.data, aabbs.ctypes.data, starts.ctypes.data,
+                                           aff.ctypes.data, aff.shape[1] // 8, top.ctypes.data, t["r_min"], t["r_max"],
+                                           t["r_point"]))
+
+    def sort(self):
+        _check(self._L.b200mp_env_sort(self._h))
+
+    def commit(self):
+        _check(self._L.b200mp_env_commit(self._h))
+
+    finalize = commit
+
+    def min_distances(self, kind: int) -> np.ndarray:
+        n = self._L.b200mp_env_min_distances(self._h, kind, None)
+        out = np.zeros(max(n, 0), np.float32)
+        if n > 0:
+            self._L.b200mp_env_min_distances(self._h, kind, out.ctypes.data)
+        return out

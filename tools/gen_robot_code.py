@@ -146,9 +146,27 @@ def gen_cuda(model: dict) -> str:
         link_rows.append(dict(ref_index=li, name=l["name"], frame=l["frame"], begin=b, end=len(fine_sorted),
                               coarse=l["coarse"]))
     new_index = {row["ref_index"]: i for i, row in enumerate(link_rows)}
-    pairs = [(new_index[a], new_index[b]) for a, b in model["self_pairs"]]
-    # order pairs by the later frame so frames stream in stage 2
-    pairs.sort(key=lambda p: (max(link_rows[p[0]]["frame"], link_rows[p[1]]["frame"]), p))
+    # self pairs as (link on the earlier frame, link on the later frame), grouped by the later frame so that
+    # stage 2 can stream frames base -> tip and only keep the few "earlier" frames in saved slots
+    pairs = []
+    for a, b in model["self_pairs"]:
+        a, b = new_index[a], new_index[b]
+        if link_rows[a]["frame"] > link_rows[b]["frame"]:
+            a, b = b, a
+        pairs.append((a, b))
+    pairs.sort(key=lambda p: (link_rows[p[1]]["frame"], link_rows[p[0]]["frame"], p))
+    nfr = len(frames)
+    for fr in frames[1:]:
+        assert fr["parent"] == fr["id"] - 1, "frames must form a chain (tree robots need a saved-parent slot)"
+    frame_link_begin = [next((i for i, r in enumerate(link_rows) if r["frame"] >= k), len(link_rows)) for k in range(nfr)] + [len(link_rows)]
+    pair_frame_begin = [next((i for i, p in enumerate(pairs) if link_rows[p[1]]["frame"] >= k), len(pairs)) for k in range(nfr)] + [len(pairs)]
+    a_frames = sorted({link_rows[a]["frame"] for a, _ in pairs} - {0})
+    save_slot = [a_frames.index(k) if k in a_frames else -1 for k in range(nfr)]
+    # which saved slot holds the earlier link's frame: -2 = world, -1 = same frame as the later link
+    pair_slot = []
+    for a, b in pairs:
+        fa, fb = link_rows[a]["frame"], link_rows[b]["frame"]
+        pair_slot.append(-2 if fa == 0 else (-1 if fa == fb else a_frames.index(fa)))
 
     lo = [float(np.float32(a)) for a in model["s_a"]]
     hi = [float(np.float32(np.float32(a) + np.float32(m))) for a, m in zip(model["s_a"], model["s_m"])]
@@ -168,7 +186,10 @@ def gen_cuda(model: dict) -> str:
     w(f"    float4 coarse[{nl}];        // frame-local centre + radius of each link's bounding sphere")
     w(f"    float4 fine[{nf}];          // frame-local centre + radius, grouped by link")
     w(f"    short link_begin[{nl + 1}]; // fine-sphere range of link l = [link_begin[l], link_begin[l+1])")
-    w(f"    short pair_a[{npairs}], pair_b[{npairs}];")
+    w(f"    short pair_a[{npairs}], pair_b[{npairs}], pair_slot[{npairs}];  // earlier-frame link, later-frame link, saved slot of the earlier frame (-2 world, -1 same)")
+    w(f"    short frame_link_begin[{nfr + 1}];  // links living on frame k = [frame_link_begin[k], frame_link_begin[k+1])")
+    w(f"    short pair_frame_begin[{nfr + 1}];  // pairs whose later link lives on frame k")
+    w(f"    short save_slot[{nfr}];             // slot frame k is saved to for later pairs, or -1")
     w("};")
     w("")
     w(f"__constant__ {cname}Tables k{cname}Tables = {{")
@@ -178,54 +199,32 @@ def gen_cuda(model: dict) -> str:
     w("    {" + ", ".join(str(r["begin"]) for r in link_rows) + f", {nf}" + "},")
     w("    {" + ", ".join(str(a) for a, _ in pairs) + "},")
     w("    {" + ", ".join(str(b) for _, b in pairs) + "},")
+    w("    {" + ", ".join(str(v) for v in pair_slot) + "},")
+    w("    {" + ", ".join(str(v) for v in frame_link_begin) + "},")
+    w("    {" + ", ".join(str(v) for v in pair_frame_begin) + "},")
+    w("    {" + ", ".join(str(v) for v in save_slot) + "},")
     w("};")
     w("")
     w(f"struct {cname} {{")
     w(f"    static constexpr int kDim = {model['dimension']};")
-    w(f"    static constexpr int kFrames = {len(frames)};   // frame 0 = world")
+    w(f"    static constexpr int kFrames = {len(frames)};   // frame 0 = world; frames form a chain base -> tip")
     w(f"    static constexpr int kLinks = {nl};")
     w(f"    static constexpr int kFine = {nf};")
     w(f"    static constexpr int kPairs = {npairs};")
     w(f"    static constexpr int kResolution = {model['resolution']};")
+    w(f"    static constexpr int kSlots = {max(1, len(a_frames))};   // saved frames needed by the self-collision stage")
     w(f"    static constexpr int kRobotId = {0 if name == 'panda' else 1 if name == 'fetch' else 9};")
-    w(f"    using Tables = {cname}Tables;")
-    w(f"    __device__ static __forceinline__ const Tables &tables() {{ return k{cname}Tables; }}")
-    w("")
-    w("    // frame each link's spheres live in; links are stored base -> tip")
-    w("    __host__ __device__ static constexpr int link_frame(int l) {")
-    w("        constexpr int v[kLinks] = {" + ", ".join(str(r["frame"]) for r in link_rows) + "};")
-    w("        return v[l];")
-    w("    }")
-    w("    __host__ __device__ static constexpr int frame_parent(int f) {")
-    w("        constexpr int v[kFrames] = {" + ", ".join(str(fr["parent"]) for fr in frames) + "};")
-    w("        return v[f];")
-    w("    }")
-    w("    __host__ __device__ static constexpr int frame_joint(int f) {   // index into q; -1 for world")
-    w("        constexpr int v[kFrames] = {" + ", ".join(str(fr.get("q_index", -1)) for fr in frames) + "};")
-    w("        return v[f];")
-    w("    }")
-    w("    __host__ __device__ static constexpr bool frame_revolute(int f) {")
-    w("        constexpr bool v[kFrames] = {" + ", ".join("true" if fr.get("type") in ("revolute", "continuous") else "false" for fr in frames) + "};")
-    w("        return v[f];")
-    w("    }")
-    w("    __host__ __device__ static constexpr int pair_a(int p) {")
-    w("        constexpr int v[kPairs] = {" + ", ".join(str(a) for a, _ in pairs) + "};")
-    w("        return v[p];")
-    w("    }")
-    w("    __host__ __device__ static constexpr int pair_b(int p) {")
-    w("        constexpr int v[kPairs] = {" + ", ".join(str(b) for _, b in pairs) + "};")
-    w("        return v[p];")
-    w("    }")
-    w("    __host__ __device__ static constexpr int link_begin(int l) {")
-    w("        constexpr int v[kLinks + 1] = {" + ", ".join(str(r["begin"]) for r in link_rows) + f", {nf}" + "};")
-    w("        return v[l];")
-    w("    }")
     w("    static constexpr float kLo[kDim] = {" + ", ".join(f32(v) for v in lo) + "};")
     w("    static constexpr float kHi[kDim] = {" + ", ".join(f32(v) for v in hi) + "};")
+    w(f"    using Tables = {cname}Tables;")
+    w(f"    __device__ static __forceinline__ const Tables &tables() {{ return k{cname}Tables; }}")
     w("")
     w("    // F = P * origin(K) * motion(q).  s, c = vamp_sin(q), vamp_cos(q) for revolute joints; q raw for prismatic.")
     w("    template <int K>")
     w("    __device__ static __forceinline__ void frame(const Frame &P, float q, float s, float c, Frame &F);")
+    w("")
+    w("    // step the streaming frame from k-1 to k (k >= 1); uniform switch, static joint indices")
+    w("    __device__ static __forceinline__ void advance(int k, Frame &F, const float (&q)[kDim]);")
     w("};")
     w("")
     for fr in frames[1:]:
@@ -239,6 +238,19 @@ def gen_cuda(model: dict) -> str:
             w("    " + ln)
         w("}")
         w("")
+    w(f"__device__ __forceinline__ void {cname}::advance(int k, Frame &F, const float (&q)[kDim]) {{")
+    w("    const Frame P = F;")
+    w("    switch (k) {")
+    for fr in frames[1:]:
+        qi = fr["q_index"]
+        if fr["type"] in ("revolute", "continuous"):
+            w(f"        case {fr['id']}: frame<{fr['id']}>(P, q[{qi}], vamp_sin(q[{qi}]), vamp_cos(q[{qi}]), F); break;")
+        else:
+            w(f"        case {fr['id']}: frame<{fr['id']}>(P, q[{qi}], 0.0f, 1.0f, F); break;")
+    w("        default: break;")
+    w("    }")
+    w("}")
+    w("")
     w("}  // namespace b200mp")
     return "\n".join(out) + "\n", link_rows, fine_sorted, pairs
 
