@@ -1,0 +1,265 @@
+#!/usr/bin/env python3
+"""Headline benchmark: Panda edge checks/s at 64 interpolated states per edge (BASELINE.json config 2).
+
+Workload: scene seed 1234 = 500 spheres + 500 cuboids, sorted; 2^20 random Panda motions whose
+length puts the reference at n = 8 rakes = 64 states. One "step" = one pass of the validation kernel over the batch.
+
+  value     edges/s, whole job, inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e       edges/s through the C ABI host entry point (b200mp_validate_motions) with pinned HOST buffers:
+            H2D of both state arrays + kernel + D2H of the validity bytes inside the timed region
+  roofline  FP32-FMA roofline of the validation kernel on the all-valid sub-workload (no early exit hides work):
+            achieved = W_ref (flops the reference's sequential semantics execute, counted by the CPU oracle) / kernel time;
+            peak = FP32 FMA throughput measured on this GPU by b200mp_fp32_peak (MEASURED_PEAKS.json has no FP32 entry)
+  cpu_baseline   the reference's own CPU path (oracle/_ref, unmodified VAMP) or the port, all host threads, bounded sample
+
+`--impl reference` times the reference CPU implementation instead (rank 0 only).
+Multi-GPU: the path shards by motions with no data-path collective -> weak scaling, every rank validates its own 2^20 motions.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "panda_edge_checks_per_sec_at_64_steps"
+UNIT = "edges/s"
+M_EDGES = 1 << 20
+SCENE_SEED = 1234
+EDGE_SEED = 1234
+
+
+def workload_config(n_gpus):
+    return {"workload": "C2: 2^20 random Panda motions x 64 interpolated states vs 500 spheres + 500 cuboids (seed 1234, sorted)",
+            "motions_per_gpu": M_EDGES, "states_per_motion": 64, "obstacles": 1000, "robot": "panda",
+            "cache": "L2 flushed (256 MiB write) before every timed step", "parallelism": f"motions sharded x{n_gpus}, no collective"}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.max_mhz = None
+        self.reasons = set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_inputs(rank):
+    from ompl_b200 import synth
+    scene = synth.clutter_scene(SCENE_SEED, 500, 500)
+    q0, q1 = synth.fixed_length_edges("panda", M_EDGES, EDGE_SEED + 1000 * rank)
+    return scene, q0, q1
+
+
+def checker_env(scene):
+    """(env, kind): the compiled unmodified reference when oracle/_ref exists, else the CPU restatement."""
+    from ompl_b200 import synth
+    from oracle import port
+    try:
+        from oracle import refvamp
+        if refvamp.available():
+            return synth.fill_env(refvamp.RefEnvironment(), scene), "reference"
+    except Exception:
+        pass
+    return synth.fill_env(port.PortEnvironment(), scene), "port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene, q0, q1 = make_inputs(0)
+    env, kind = checker_env(scene)
+    cores = os.cpu_count() or 1
+    sample = 1 << 17  # bounded sample of the same motions per step
+    a, b = q0[:sample], q1[:sample]
+    for _ in range(max(args.warmup, 1)):
+        env.validate_motions("panda", a[:8192], b[:8192], nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        env.validate_motions("panda", a, b, nthreads=cores)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"first {sample} of the 2^20 motions per step, all host threads (dynamic chunks)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import ompl_b200
+    from ompl_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = ompl_b200.Context(local)
+    scene, q0, q1 = make_inputs(rank)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+
+    d0, d1 = torch.from_numpy(q0).to(dev), torch.from_numpy(q1).to(dev)
+    dv = torch.zeros(M_EDGES, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_pass(n_steps, a0, a1, out, m):
+        """returns summed kernel-only milliseconds over n_steps (L2 flushed before each)"""
+        total = 0.0
+        evs = []
+        with torch.cuda.stream(stream):
+            for _ in range(n_steps):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ctx.validate_motions_ptr("panda", env, a0.data_ptr(), a1.data_ptr(), m, out.data_ptr(), stream=stream.cuda_stream)
+                e1.record(stream)
+                evs.append((e0, e1))
+            stream.synchronize()
+        for e0, e1 in evs:
+            total += e0.elapsed_time(e1)
+        return total
+
+    # ---- device-resident throughput (value)
+    device_pass(args.warmup, d0, d1, dv, M_EDGES)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = ctx.launch_count
+    ms = device_pass(args.steps, d0, d1, dv, M_EDGES)
+    barrier()
+    launches = ctx.launch_count - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * M_EDGES * args.steps / (ms_max * 1e-3)
+    valid_frac = float(dv.float().mean().item())
+
+    # ---- end to end through the host C ABI with pinned host buffers
+    h0, h1 = torch.from_numpy(q0).pin_memory(), torch.from_numpy(q1).pin_memory()
+    hv = torch.zeros(M_EDGES, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        ctx.validate_motions_ptr("panda", env, h0.data_ptr(), h1.data_ptr(), M_EDGES, hv.data_ptr(), device=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.validate_motions_ptr("panda", env, h0.data_ptr(), h1.data_ptr(), M_EDGES, hv.data_ptr(), device=False)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = world * M_EDGES * args.steps / float(t.item())
+    assert np.array_equal(hv.numpy(), dv.cpu().numpy()), "host and device entry points disagree"
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline on the all-valid sub-workload + CPU baseline (rank 0, N = 1 semantics)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(q0.nbytes + q1.nbytes), "d2h_bytes_per_step": int(M_EDGES)},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "valid_fraction": valid_frac,
+            "states_per_sec_upper": value * 64}
+    if world == 1:
+        from oracle import port
+        pe = synth.fill_env(port.PortEnvironment(), scene)
+        valid_idx = np.nonzero(dv.cpu().numpy() == 1)[0]
+        peak = ctx.fp32_peak_tflops(4096)
+        # W_ref per valid edge from the instrumented oracle on a sample
+        samp = valid_idx[:512]
+        _, fl = pe.validate_motions("panda", q0[samp], q1[samp], nthreads=os.cpu_count() or 1, want_flops=True)
+        w_ref_edge = float(fl.mean())
+        rep = np.resize(valid_idx, 1 << 17)
+        a0, a1 = torch.from_numpy(q0[rep]).to(dev), torch.from_numpy(q1[rep]).to(dev)
+        av = torch.zeros(len(rep), dtype=torch.uint8, device=dev)
+        device_pass(3, a0, a1, av, len(rep))
+        l1 = ctx.launch_count
+        ms_av = device_pass(args.steps, a0, a1, av, len(rep)) / args.steps
+        assert ctx.launch_count - l1 == args.steps
+        achieved = w_ref_edge * len(rep) / (ms_av * 1e-3) / 1e12
+        line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                            "traffic": None, "kernel": "validate_motions_kernel<Panda>",
+                            "workload": f"all-valid sub-workload: {len(valid_idx)} oracle-valid motions of the batch tiled to 2^17",
+                            "work_per_launch_flops": w_ref_edge * len(rep), "w_ref_flops_per_edge": w_ref_edge,
+                            "ms_per_launch": ms_av, "states_per_sec": len(rep) * 64 / (ms_av * 1e-3),
+                            "peak_source": "measured: b200mp_fp32_peak FFMA microbenchmark on this GPU (nominal 148*128*2*1.965 GHz = 74.4)"}
+        if not args.no_cpu_baseline:
+            chk, kind = checker_env(scene)
+            cores = os.cpu_count() or 1
+            sample = 1 << 18
+            chk.validate_motions("panda", q0[:8192], q1[:8192], nthreads=cores)
+            t0 = time.perf_counter()
+            want = chk.validate_motions("panda", q0[:sample], q1[:sample], nthreads=cores)
+            dt = time.perf_counter() - t0
+            got = dv.cpu().numpy()[:sample]
+            mism = int((got != want).sum())
+            line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"first 2^18 of the 2^20 motions, all host threads; {mism} decisions differ from the GPU"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

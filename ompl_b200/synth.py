@@ -46,14 +46,15 @@ def _euler_xyz_axes(rho, theta, phi):
 
 
 def clutter_scene(seed: int = 1234, n_spheres: int = 500, n_cuboids: int = 500, n_capsules: int = 0,
-                  n_zcuboids: int = 0, n_zcapsules: int = 0, r_lo: float = 0.01, r_hi: float = 0.05) -> dict:
+                  n_zcuboids: int = 0, n_zcapsules: int = 0, r_lo: float = 0.01, r_hi: float = 0.05,
+                  rho_lo: float = 0.35, rho_hi: float = 1.30, z_lo: float = -0.2, z_hi: float = 1.2) -> dict:
     """C2 scene: obstacle centres cylindrical rho in U[0.35,1.30], theta in U[0,2pi), z in U[-0.2,1.2]."""
     rng = np.random.default_rng(seed)
 
     def centres(n):
-        rho = rng.uniform(0.35, 1.30, n)
+        rho = rng.uniform(rho_lo, rho_hi, n)
         th = rng.uniform(0, 2 * np.pi, n)
-        z = rng.uniform(-0.2, 1.2, n)
+        z = rng.uniform(z_lo, z_hi, n)
         return np.stack([rho * np.cos(th), rho * np.sin(th), z], axis=1)
 
     out = {}

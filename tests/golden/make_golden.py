@@ -1,0 +1,109 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED reference compiled in oracle/_ref (run where /root/reference
+exists: `make -C oracle ref && python tests/golden/make_golden.py`). Each file stores the inputs (scene arrays,
+states, motions) together with the reference's answers, so the fixtures do not depend on numpy's RNG staying stable.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from ompl_b200 import synth  # noqa: E402
+from oracle import refvamp  # noqa: E402
+
+
+def ref_nn():
+    import ctypes as C
+    L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_nn.so"))
+    f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+    L.refnn_create.restype = C.c_void_p
+    L.refnn_create.argtypes = [f64p, C.c_int64, C.c_int]
+    L.refnn_destroy.argtypes = [C.c_void_p]
+    L.refnn_nearest_k.restype = C.c_int64
+    L.refnn_nearest_k.argtypes = [C.c_void_p, f64p, C.c_int, i64p, f64p]
+    L.refnn_nearest_r.restype = C.c_int64
+    L.refnn_nearest_r.argtypes = [C.c_void_p, f64p, C.c_double, i64p, f64p, C.c_int64]
+    return L
+
+
+def validation_case(name, robot, scene, sort, n_states, n_motions, seed, len_hi=2.5):
+    env = synth.fill_env(refvamp.RefEnvironment(), scene, sort=sort)
+    q = synth.uniform_states(robot, n_states, seed)
+    sv = env.validate_states(robot, q)
+    starts = q[sv == 1]
+    if len(starts) < n_motions // 2:
+        starts = np.concatenate([starts, q[: n_motions // 2]])
+    starts = np.resize(starts, (n_motions // 2, q.shape[1]))
+    a0, a1 = synth.local_edges(robot, starts, seed + 1, 0.05, len_hi)
+    b0 = synth.uniform_states(robot, n_motions - len(a0), seed + 2)
+    b1 = synth.uniform_states(robot, n_motions - len(a0), seed + 3)
+    q0 = np.concatenate([a0, b0]).astype(np.float32)
+    q1 = np.concatenate([a1, b1]).astype(np.float32)
+    mv = env.validate_motions(robot, q0, q1)
+    out = dict(robot=np.array(robot), sorted=np.array(sort), states=q, states_valid=sv, q0=q0, q1=q1, motions_valid=mv)
+    for k, v in scene.items():
+        out["scene_" + k] = v
+    for kind in range(5):
+        out[f"min_d_{kind}"] = env.min_distances(kind)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: states valid {sv.mean():.3f}, motions valid {mv.mean():.3f}")
+
+
+def main():
+    validation_case("panda_cage", "panda", synth.cage_scene(), True, 3000, 1500, 101)
+    validation_case("panda_clutter", "panda",
+                    synth.clutter_scene(7, 120, 120, n_capsules=40, n_zcuboids=40, n_zcapsules=40), True, 3000, 1500, 202)
+    validation_case("panda_clutter_unsorted", "panda",
+                    synth.clutter_scene(8, 80, 80, n_capsules=20, n_zcuboids=20, n_zcapsules=20), False, 2000, 1000, 303)
+    validation_case("fetch_clutter", "fetch",
+                    synth.clutter_scene(9, 60, 60, n_capsules=20, n_zcuboids=20, n_zcapsules=20, rho_lo=0.6, rho_hi=1.4,
+                                        z_lo=0.2, z_hi=1.6), True, 2000, 1000, 404)
+    # known answers of the demo (demos/vamp/VAMPPlanning.cpp:43-47,87-88)
+    env = synth.fill_env(refvamp.RefEnvironment(), synth.cage_scene())
+    assert list(env.validate_states("panda", [synth.CAGE_START, synth.CAGE_GOAL])) == [1, 1]
+    assert list(env.validate_motions("panda", [synth.CAGE_START], [synth.CAGE_GOAL])) == [0]
+    # FK of the fine spheres
+    for robot in ("panda", "fetch"):
+        q = synth.uniform_states(robot, 256, 55)
+        np.savez_compressed(os.path.join(HERE, f"{robot}_sphere_fk.npz"), q=q, spheres=refvamp.sphere_fk(robot, q))
+    # nearest neighbours: NearestNeighborsLinear<unsigned long> over RealVectorStateSpace::distance
+    L = ref_nn()
+    rng = np.random.default_rng(77)
+    out = {}
+    for dim, n, k in ((7, 500, 10), (8, 300, 16), (20, 200, 30), (3, 12, 40)):
+        db = rng.uniform(-3, 3, (n, dim))
+        qs = rng.uniform(-3, 3, (40, dim))
+        qs[:5] = db[:5]  # queries that are database members (distance-0 self match)
+        h = L.refnn_create(np.ascontiguousarray(db), n, dim)
+        idx = np.full((len(qs), k), -1, np.int64)
+        dist = np.full((len(qs), k), np.inf)
+        cnt = np.zeros(len(qs), np.int64)
+        ridx, rcnt = [], []
+        for i, q in enumerate(qs):
+            ii = np.zeros(k, np.int64)
+            dd = np.zeros(k)
+            c = L.refnn_nearest_k(h, np.ascontiguousarray(q), k, ii, dd)
+            cnt[i] = c
+            idx[i, :c] = ii[:c]
+            dist[i, :c] = dd[:c]
+            ii = np.zeros(n, np.int64)
+            dd = np.zeros(n)
+            c = L.refnn_nearest_r(h, np.ascontiguousarray(q), 2.0, ii, dd, n)
+            ridx.append(ii[:c].copy())
+            rcnt.append(c)
+        L.refnn_destroy(h)
+        tag = f"d{dim}"
+        out[tag + "_db"], out[tag + "_q"], out[tag + "_k"] = db, qs, np.array(k)
+        out[tag + "_idx"], out[tag + "_dist"], out[tag + "_cnt"] = idx, dist, cnt
+        out[tag + "_rcnt"] = np.array(rcnt)
+        out[tag + "_ridx"] = np.concatenate(ridx) if ridx else np.zeros(0, np.int64)
+    np.savez_compressed(os.path.join(HERE, "knn_linear.npz"), **out)
+    print("knn golden written")
+
+
+if __name__ == "__main__":
+    main()

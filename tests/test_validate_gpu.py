@@ -1,0 +1,181 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the golden vectors of the unmodified
+reference and against the oracle on seeded inputs. Bit-exact except decisions whose min clearance is < 1e-5 m."""
+import numpy as np
+import pytest
+
+import ompl_b200
+from ompl_b200 import synth
+from oracle import port
+from tests.conftest import have_reference_build
+from tests.util import assert_validity_parity, load_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["panda_cage", "panda_clutter", "panda_clutter_unsorted", "fetch_clutter"]
+
+
+def clr_states(pe, robot, q):
+    return lambda b: pe.edge_min_clearance(robot, q[b], q[b], resolution=1)
+
+
+def clr_motions(pe, robot, q0, q1, res=0):
+    return lambda b: pe.edge_min_clearance(robot, q0[b], q1[b], resolution=res)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_validity(ctx, name):
+    z, scene, robot, is_sorted = load_golden(name)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene, sort=is_sorted)
+    pe = synth.fill_env(port.PortEnvironment(), scene, sort=is_sorted)
+    for kind in range(5):
+        np.testing.assert_allclose(env.min_distances(kind), z[f"min_d_{kind}"], rtol=0, atol=2.5e-7)
+    sv = ctx.validate_states(robot, env, z["states"])
+    assert_validity_parity(sv, z["states_valid"], clr_states(pe, robot, z["states"]), name + " states")
+    mv = ctx.validate_motions(robot, env, z["q0"], z["q1"])
+    assert_validity_parity(mv, z["motions_valid"], clr_motions(pe, robot, z["q0"], z["q1"]), name + " motions")
+
+
+def test_demo_known_answers(ctx):
+    env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
+    assert list(ctx.validate_states("panda", env, [synth.CAGE_START, synth.CAGE_GOAL])) == [1, 1]
+    assert list(ctx.validate_motions("panda", env, [synth.CAGE_START], [synth.CAGE_GOAL])) == [0]
+
+
+@pytest.mark.parametrize("robot,scene_kw", [
+    ("panda", dict(seed=31, n_spheres=300, n_cuboids=300, n_capsules=60, n_zcuboids=60, n_zcapsules=60)),
+    ("fetch", dict(seed=32, n_spheres=80, n_cuboids=80, n_capsules=20, n_zcuboids=20, n_zcapsules=20, rho_lo=0.6, rho_hi=1.4,
+                   z_lo=0.2, z_hi=1.6)),
+])
+def test_seeded_parity_vs_oracle(ctx, robot, scene_kw):
+    scene = synth.clutter_scene(**scene_kw)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+    pe = synth.fill_env(port.PortEnvironment(), scene)
+    q = synth.uniform_states(robot, 30000, 17)
+    want = pe.validate_states(robot, q, nthreads=8)
+    got = ctx.validate_states(robot, env, q)
+    assert_validity_parity(got, want, clr_states(pe, robot, q), "states")
+    starts = q[want == 1][:4000]
+    q0, q1 = synth.local_edges(robot, starts, 19, 0.02, 3.0)
+    want = pe.validate_motions(robot, q0, q1, nthreads=8)
+    got = ctx.validate_motions(robot, env, q0, q1)
+    assert 0.05 < want.mean() < 0.95
+    assert_validity_parity(got, want, clr_motions(pe, robot, q0, q1), "motions")
+
+
+@pytest.mark.skipif(not have_reference_build(), reason="oracle/_ref not built")
+def test_parity_vs_compiled_reference_c2_sample(ctx):
+    """A sample of BASELINE config 2 (500 spheres + 500 cuboids, 64-state motions) against the reference itself."""
+    from oracle import refvamp
+    scene = synth.clutter_scene(1234, 500, 500)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+    re_ = synth.fill_env(refvamp.RefEnvironment(), scene)
+    pe = synth.fill_env(port.PortEnvironment(), scene)
+    q0, q1 = synth.fixed_length_edges("panda", 1 << 16, 1234)
+    want = re_.validate_motions("panda", q0, q1, nthreads=8)
+    got = ctx.validate_motions("panda", env, q0, q1)
+    assert_validity_parity(got, want, clr_motions(pe, "panda", q0, q1), "C2 sample")
+
+
+def test_ragged_and_empty_batches(ctx):
+    scene = synth.clutter_scene(3, 40, 40)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+    pe = synth.fill_env(port.PortEnvironment(), scene)
+    q = synth.uniform_states("panda", 200, 2)
+    for m in (0, 1, 7, 31, 32, 33, 65, 200):
+        np.testing.assert_array_equal(ctx.validate_states("panda", env, q[:m]), pe.validate_states("panda", q[:m]))
+    q0, q1 = synth.local_edges("panda", q, 4, 0.0, 3.5)
+    for m in (0, 1, 3, 9, 200):
+        np.testing.assert_array_equal(ctx.validate_motions("panda", env, q0[:m], q1[:m]), pe.validate_motions("panda", q0[:m], q1[:m]))
+
+
+def test_empty_environment_and_zero_length_motion(ctx):
+    env = ompl_b200.Environment(ctx)
+    env.commit()
+    pe = port.PortEnvironment()
+    q = synth.uniform_states("panda", 2048, 8)
+    sv = ctx.validate_states("panda", env, q)
+    np.testing.assert_array_equal(sv, pe.validate_states("panda", q, nthreads=4))  # self-collision only
+    assert 0 < sv.sum() < len(sv)
+    np.testing.assert_array_equal(ctx.validate_motions("panda", env, q, q), sv)  # validate_motion(q, q): n = 1, 8 equal lanes
+
+
+def test_long_motions_many_rakes(ctx):
+    # corner-to-corner motions: |dq| ~ 14 rad -> n = 56 rakes = 448 states, several passes per warp
+    scene = synth.clutter_scene(12, 30, 30)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+    pe = synth.fill_env(port.PortEnvironment(), scene)
+    lo, hi = synth.BOUNDS["panda"]
+    rng = np.random.default_rng(5)
+    q0 = np.where(rng.random((300, 7)) < 0.5, lo, hi).astype(np.float32)
+    q1 = np.where(rng.random((300, 7)) < 0.5, lo, hi).astype(np.float32)
+    want = pe.validate_motions("panda", q0, q1, nthreads=8)
+    got = ctx.validate_motions("panda", env, q0, q1)
+    assert_validity_parity(got, want, clr_motions(pe, "panda", q0, q1), "long motions")
+
+
+def test_resolution_argument(ctx):
+    scene = synth.clutter_scene(14, 60, 60)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+    pe = synth.fill_env(port.PortEnvironment(), scene)
+    q = synth.uniform_states("panda", 4000, 3)
+    q0, q1 = synth.local_edges("panda", q, 5, 0.1, 2.0)
+    for res in (1, 8, 32, 64):
+        want = pe.validate_motions("panda", q0, q1, resolution=res, nthreads=8)
+        got = ctx.validate_motions("panda", env, q0, q1, resolution=res)
+        assert_validity_parity(got, want, clr_motions(pe, "panda", q0, q1, res), f"resolution {res}")
+
+
+def test_double_precision_entry_points(ctx):
+    # OMPL states are double; the bridge casts each coordinate to float (src/ompl/vamp/Utils.h:26)
+    scene = synth.clutter_scene(15, 60, 60)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+    rng = np.random.default_rng(1)
+    lo, hi = synth.BOUNDS["panda"]
+    q = rng.uniform(lo, hi, (3000, 7))  # float64
+    np.testing.assert_array_equal(ctx.validate_states("panda", env, q), ctx.validate_states("panda", env, q.astype(np.float32)))
+    q1 = np.clip(q + rng.normal(scale=0.3, size=q.shape), lo, hi)
+    np.testing.assert_array_equal(ctx.validate_motions("panda", env, q, q1),
+                                  ctx.validate_motions("panda", env, q.astype(np.float32), q1.astype(np.float32)))
+
+
+def test_device_pointer_entry_points(ctx):
+    import torch
+    scene = synth.clutter_scene(16, 60, 60)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+    q0, q1 = synth.fixed_length_edges("panda", 5000, 3)
+    want = ctx.validate_motions("panda", env, q0, q1)
+    d0, d1 = torch.from_numpy(q0).cuda(), torch.from_numpy(q1).cuda()
+    out = torch.zeros(len(q0), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    before = ctx.launch_count
+    ctx.validate_motions_ptr("panda", env, d0.data_ptr(), d1.data_ptr(), len(q0), out.data_ptr(), stream=st.cuda_stream)
+    st.synchronize()
+    assert ctx.launch_count == before + 1
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+def test_api_errors(ctx):
+    env = ompl_b200.Environment(ctx)
+    env.add_spheres([[1, 0, 0, 0.1]])
+    q = synth.uniform_states("panda", 4, 1)
+    with pytest.raises(ompl_b200.B200MPError) as e:   # not committed
+        ctx.validate_states("panda", env, q)
+    assert e.value.code == 5
+    env.commit()
+    ctx.validate_states("panda", env, q)
+
+
+def test_linearity_properties_full_size(ctx):
+    """Size-independent properties at BASELINE scale (2^20 motions): (i) a motion is valid only if both of the
+    reference's end samples are (goal state is tested, validate.hh:36-39); (ii) batch order does not matter."""
+    scene = synth.clutter_scene(1234, 500, 500)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+    q0, q1 = synth.fixed_length_edges("panda", 1 << 20, 99)
+    v = ctx.validate_motions("panda", env, q0, q1)
+    goal_ok = ctx.validate_states("panda", env, q1)
+    assert not (v & (1 - goal_ok)).any()
+    perm = np.random.default_rng(0).permutation(len(q0))
+    v2 = ctx.validate_motions("panda", env, q0[perm], q1[perm])
+    np.testing.assert_array_equal(v2, v[perm])
+    assert 0.001 < v.mean() < 0.2

@@ -38,15 +38,18 @@ def time_device(ctx, env, robot, q0, q1, reps=3):
     d0 = torch.from_numpy(q0).cuda()
     d1 = torch.from_numpy(q1).cuda()
     out = torch.empty(q0.shape[0], dtype=torch.uint8, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
-    ctx.validate_motions_ptr(robot, env, d0.data_ptr(), d1.data_ptr(), q0.shape[0], out.data_ptr(), stream=st)
+    ts = torch.cuda.Stream()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps):
+    with torch.cuda.stream(ts):
+        st = ts.cuda_stream
         ctx.validate_motions_ptr(robot, env, d0.data_ptr(), d1.data_ptr(), q0.shape[0], out.data_ptr(), stream=st)
-    b.record()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(ts)
+        for _ in range(reps):
+            ctx.validate_motions_ptr(robot, env, d0.data_ptr(), d1.data_ptr(), q0.shape[0], out.data_ptr(), stream=st)
+        b.record(ts)
+        torch.cuda.synchronize()
     return a.elapsed_time(b) / reps, out.cpu().numpy()
 
 
