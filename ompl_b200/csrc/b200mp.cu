@@ -308,27 +308,45 @@ int b200mp_env_commit(b200mp_env *e) {
     d.n_zcap = static_cast<int>(e->zcapsules.size());
     d.n_cub = static_cast<int>(e->cuboids.size());
     d.n_zcub = static_cast<int>(e->zcuboids.size());
+    // every class is padded to a multiple of kObsUnroll records with far-away dummies that can never collide,
+    // so the kernels scan whole blocks without a tail
+    constexpr float kFar = 1.0e9f;
+    auto pad_count = [](size_t n) { return (kObsUnroll - static_cast<int>(n % kObsUnroll)) % kObsUnroll; };
+    bool sorted = true;
+    auto is_sorted = [&](const auto &v) {
+        for (size_t i = 1; i < v.size(); ++i) if (v[i].min_d < v[i - 1].min_d) sorted = false;
+    };
+    is_sorted(e->spheres); is_sorted(e->capsules); is_sorted(e->zcapsules); is_sorted(e->cuboids); is_sorted(e->zcuboids);
+    d.sorted = sorted ? 1 : 0;
+
     d.off_sph = static_cast<int>(blob.size());
     for (const auto &s : e->spheres) blob.insert(blob.end(), {s.x, s.y, s.z, s.r});
+    for (int i = 0; i < pad_count(e->spheres.size()); ++i) blob.insert(blob.end(), {kFar, kFar, kFar, 0.f});
     d.off_sph_pm = static_cast<int>(blob.size());
     push_pm(e->spheres);
     d.off_cap = static_cast<int>(blob.size());
     for (const auto &c : e->capsules) blob.insert(blob.end(), {c.x1, c.y1, c.z1, c.r, c.xv, c.yv, c.zv, c.rdv});
+    for (int i = 0; i < pad_count(e->capsules.size()); ++i) blob.insert(blob.end(), {kFar, kFar, kFar, 0.f, 0.f, 0.f, 0.f, 0.f});
     d.off_cap_pm = static_cast<int>(blob.size());
     push_pm(e->capsules);
     d.off_zcap = static_cast<int>(blob.size());
     for (const auto &c : e->zcapsules) blob.insert(blob.end(), {c.x1, c.y1, c.z1, c.r, c.zv, c.rdv, 0.f, 0.f});
+    for (int i = 0; i < pad_count(e->zcapsules.size()); ++i) blob.insert(blob.end(), {kFar, kFar, kFar, 0.f, 0.f, 0.f, 0.f, 0.f});
     d.off_zcap_pm = static_cast<int>(blob.size());
     push_pm(e->zcapsules);
     d.off_cub = static_cast<int>(blob.size());
     for (const auto &c : e->cuboids)
         blob.insert(blob.end(), {c.c[0], c.c[1], c.c[2], c.h[0], c.a1[0], c.a1[1], c.a1[2], c.h[1], c.a2[0], c.a2[1], c.a2[2], c.h[2],
                                  c.a3[0], c.a3[1], c.a3[2], 0.f});
+    for (int i = 0; i < pad_count(e->cuboids.size()); ++i)
+        blob.insert(blob.end(), {kFar, kFar, kFar, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f});
     d.off_cub_pm = static_cast<int>(blob.size());
     push_pm(e->cuboids);
     d.off_zcub = static_cast<int>(blob.size());
     for (const auto &c : e->zcuboids)
         blob.insert(blob.end(), {c.c[0], c.c[1], c.c[2], c.h[2], c.a1[0], c.a1[1], c.h[0], 0.f, c.a2[0], c.a2[1], c.h[1], 0.f});
+    for (int i = 0; i < pad_count(e->zcuboids.size()); ++i)
+        blob.insert(blob.end(), {kFar, kFar, kFar, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f});
     d.off_zcub_pm = static_cast<int>(blob.size());
     push_pm(e->zcuboids);
     align4();
@@ -358,7 +376,7 @@ template <class R>
 int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const float *d_q1, int64_t m, int resolution,
                    uint8_t *d_valid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4;
-    auto kern = validate_motions_kernel<R>;
+    auto kern = e->desc.sorted ? validate_motions_kernel<R, false> : validate_motions_kernel<R, true>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
@@ -377,7 +395,7 @@ int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const 
 template <class R>
 int launch_states(b200mp_ctx *c, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4;
-    auto kern = validate_states_kernel<R>;
+    auto kern = e->desc.sorted ? validate_states_kernel<R, false> : validate_states_kernel<R, true>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));

@@ -45,6 +45,7 @@ struct SceneDesc {
     int off_zcap, off_zcap_pm;    // 2 x float4 (x1,y1,z1,r) (zv,rdv,0,0)
     int off_cub, off_cub_pm;      // 4 x float4 (cx,cy,cz,h1) (a1x,a1y,a1z,h2) (a2x,a2y,a2z,h3) (a3x,a3y,a3z,0)
     int off_zcub, off_zcub_pm;    // 3 x float4 (cx,cy,cz,h3) (a1x,a1y,h1,0) (a2x,a2y,h2,0)
+    int sorted;  // 1 when every class is in non-decreasing min_distance order (prefix masks are then redundant)
     int n_pc;
     CaptView pc[kMaxPointClouds];
 };
@@ -147,127 +148,131 @@ __device__ __forceinline__ bool scan_should_stop(bool hit, bool participating) {
     return __all_sync(kFull, hit || !participating);
 }
 
-// T robot spheres per lane against every obstacle class. b* are per-sphere prefix lengths (0 for idle slots).
+// T robot spheres per lane against every obstacle class.
 template <int T>
 struct Tile {
     float x[T], y[T], z[T], r[T];
     float ext[T];  // group max_extent, -inf for idle slots / idle lanes
 };
 
-template <int T, int POLICY>
-__device__ __forceinline__ bool scan_scene(const Scene &sc, const Tile<T> &s, bool participating) {
-    bool hit = false;
-    int b[T];
+// Primitive tests. Each returns d with sign bit set <=> collision. `o` points at the obstacle's float4 records.
+struct SphereTest {   // collision/sphere_sphere.hh:10-23
+    static constexpr int kRec = 1;
+    __device__ static __forceinline__ float test(const float4 *o, float x, float y, float z, float r, float) {
+        const float4 c = o[0];
+        const float xs = c.x - x, ys = c.y - y, zs = c.z - z;
+        const float sum = fmaf(zs, zs, fmaf(ys, ys, xs * xs));
+        const float rs = c.w + r;
+        return fmaf(-rs, rs, sum);
+    }
+};
+struct CapsuleTest {  // collision/sphere_capsule.hh:9-23; records (x1,y1,z1,r) (xv,yv,zv,rdv)
+    static constexpr int kRec = 2;
+    __device__ static __forceinline__ float test(const float4 *o, float x, float y, float z, float r, float) {
+        const float4 p = o[0], v = o[1];
+        const float dot = fmaf(z - p.z, v.z, fmaf(y - p.y, v.y, (x - p.x) * v.x));
+        const float cdf = fminf(fmaxf(dot * v.w, 0.0f), 1.0f);
+        const float xs = x - fmaf(v.x, cdf, p.x), ys = y - fmaf(v.y, cdf, p.y), zs = z - fmaf(v.z, cdf, p.z);
+        const float sum = fmaf(zs, zs, fmaf(ys, ys, xs * xs));
+        const float rs = r + p.w;
+        return fmaf(-rs, rs, sum);
+    }
+};
+struct ZCapsuleTest {  // collision/sphere_capsule.hh:31-44; records (x1,y1,z1,r) (zv,rdv,0,0)
+    static constexpr int kRec = 2;
+    __device__ static __forceinline__ float test(const float4 *o, float x, float y, float z, float r, float) {
+        const float4 p = o[0], v = o[1];
+        const float dot = (z - p.z) * v.x;
+        const float cdf = fminf(fmaxf(dot * v.y, 0.0f), 1.0f);
+        const float xs = x - p.x, ys = y - p.y, zs = z - fmaf(v.x, cdf, p.z);
+        const float sum = fmaf(zs, zs, fmaf(ys, ys, xs * xs));
+        const float rs = r + p.w;
+        return fmaf(-rs, rs, sum);
+    }
+};
+struct CuboidTest {  // collision/sphere_cuboid.hh:9-27; records (cx,cy,cz,h1) (a1,h2) (a2,h3) (a3,0)
+    static constexpr int kRec = 4;
+    __device__ static __forceinline__ float test(const float4 *o, float x, float y, float z, float, float rsq) {
+        const float4 c = o[0], a1 = o[1], a2 = o[2], a3 = o[3];
+        const float xs = x - c.x, ys = y - c.y, zs = z - c.z;
+        const float e1 = fmaxf(fabsf(fmaf(a1.z, zs, fmaf(a1.y, ys, a1.x * xs))) - c.w, 0.0f);
+        const float e2 = fmaxf(fabsf(fmaf(a2.z, zs, fmaf(a2.y, ys, a2.x * xs))) - a1.w, 0.0f);
+        const float e3 = fmaxf(fabsf(fmaf(a3.z, zs, fmaf(a3.y, ys, a3.x * xs))) - a2.w, 0.0f);
+        return fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, -rsq)));
+    }
+};
+struct ZCuboidTest {  // collision/sphere_cuboid.hh:35-52; records (cx,cy,cz,h3) (a1x,a1y,h1,0) (a2x,a2y,h2,0)
+    static constexpr int kRec = 3;
+    __device__ static __forceinline__ float test(const float4 *o, float x, float y, float z, float, float rsq) {
+        const float4 c = o[0], a1 = o[1], a2 = o[2];
+        const float xs = x - c.x, ys = y - c.y, zs = z - c.z;
+        const float e1 = fmaxf(fabsf(fmaf(a1.y, ys, a1.x * xs)) - a1.z, 0.0f);
+        const float e2 = fmaxf(fabsf(fmaf(a2.y, ys, a2.x * xs)) - a2.z, 0.0f);
+        const float e3 = fmaxf(fabsf(zs) - c.w, 0.0f);
+        return fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, -rsq)));
+    }
+};
 
-    // ---- spheres (collision/sphere_sphere.hh:10-23)
+// One obstacle class. The collision flag is the sign bit of `acc` (OR of the raw bits of every test value, exactly the
+// reference's testz sign-bit predicate). Arrays are padded to a multiple of kObsUnroll with far-away dummies, so the
+// loop runs whole blocks; one warp vote per block decides whether to stop.
+//   MASKED = false (sorted scenes): entries beyond a sphere's own prefix lie farther from the origin than the sphere
+//            reaches, their tests are non-negative by construction, so no per-test mask is needed;
+//   MASKED = true  (scenes given unsorted): the reference's `break` truncates the scan, so tests at i >= b are dropped.
+constexpr int kObsUnroll = 4;
+// position given to idle sphere slots: far from every obstacle and from the +1e9 padding records
+constexpr float kIdle = -1.0e9f;
+
+template <class Test, int T, int POLICY, bool MASKED>
+__device__ __forceinline__ int scan_class(const float4 *__restrict__ obs, const float *__restrict__ pm, int n, const Tile<T> &s,
+                                          const float (&rsq)[T], bool participating, int acc) {
+    int b[T];
+    int bl = 0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) { b[t] = count_lt(pm, n, s.ext[t]); bl = max(bl, b[t]); }
+    const int B = __reduce_max_sync(kFull, bl);
+#pragma unroll 1
+    for (int i = 0; i < B; i += kObsUnroll) {
+#pragma unroll
+        for (int u = 0; u < kObsUnroll; ++u) {
+            const float4 *o = obs + (i + u) * Test::kRec;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int bits = __float_as_int(Test::test(o, s.x[t], s.y[t], s.z[t], s.r[t], rsq[t]));
+                acc |= MASKED ? ((i + u < b[t]) ? bits : 0) : bits;
+            }
+        }
+        if (scan_should_stop<POLICY>(acc < 0, participating)) break;
+    }
+    return acc;
+}
+
+template <int T, int POLICY, bool MASKED>
+__device__ __forceinline__ bool scan_scene(const Scene &sc, const Tile<T> &s, bool participating) {
+    int acc = 0;
+    float rsq[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) rsq[t] = s.r[t] * s.r[t];
     if (sc.n_sph > 0) {
-        int bl = 0;
-#pragma unroll
-        for (int t = 0; t < T; ++t) { b[t] = count_lt(sc.sph_pm, sc.n_sph, s.ext[t]); bl = max(bl, b[t]); }
-        const int B = __reduce_max_sync(kFull, bl);
-#pragma unroll 2
-        for (int i = 0; i < B; ++i) {
-            const float4 o = sc.sph[i];
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const float xs = o.x - s.x[t], ys = o.y - s.y[t], zs = o.z - s.z[t];
-                const float sum = fmaf(zs, zs, fmaf(ys, ys, xs * xs));
-                const float rs = o.w + s.r[t];
-                const float d = fmaf(-rs, rs, sum);
-                hit |= (d < 0.0f) & (i < b[t]);
-            }
-            if ((i & 7) == 7 && scan_should_stop<POLICY>(hit, participating)) break;
-        }
-        if (scan_should_stop<POLICY>(hit, participating)) return hit;
+        acc = scan_class<SphereTest, T, POLICY, MASKED>(sc.sph, sc.sph_pm, sc.n_sph, s, rsq, participating, acc);
+        if (scan_should_stop<POLICY>(acc < 0, participating)) return acc < 0;
     }
-    // ---- capsules (collision/sphere_capsule.hh:9-23)
     if (sc.n_cap > 0) {
-        int bl = 0;
-#pragma unroll
-        for (int t = 0; t < T; ++t) { b[t] = count_lt(sc.cap_pm, sc.n_cap, s.ext[t]); bl = max(bl, b[t]); }
-        const int B = __reduce_max_sync(kFull, bl);
-        for (int i = 0; i < B; ++i) {
-            const float4 p = sc.cap[2 * i], v = sc.cap[2 * i + 1];
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const float dot = fmaf(s.z[t] - p.z, v.z, fmaf(s.y[t] - p.y, v.y, (s.x[t] - p.x) * v.x));
-                const float cdf = fminf(fmaxf(dot * v.w, 0.0f), 1.0f);
-                const float xs = s.x[t] - fmaf(v.x, cdf, p.x), ys = s.y[t] - fmaf(v.y, cdf, p.y), zs = s.z[t] - fmaf(v.z, cdf, p.z);
-                const float sum = fmaf(zs, zs, fmaf(ys, ys, xs * xs));
-                const float rs = s.r[t] + p.w;
-                const float d = fmaf(-rs, rs, sum);
-                hit |= (d < 0.0f) & (i < b[t]);
-            }
-            if ((i & 7) == 7 && scan_should_stop<POLICY>(hit, participating)) break;
-        }
-        if (scan_should_stop<POLICY>(hit, participating)) return hit;
+        acc = scan_class<CapsuleTest, T, POLICY, MASKED>(sc.cap, sc.cap_pm, sc.n_cap, s, rsq, participating, acc);
+        if (scan_should_stop<POLICY>(acc < 0, participating)) return acc < 0;
     }
-    // ---- z-aligned capsules (collision/sphere_capsule.hh:31-44)
     if (sc.n_zcap > 0) {
-        int bl = 0;
-#pragma unroll
-        for (int t = 0; t < T; ++t) { b[t] = count_lt(sc.zcap_pm, sc.n_zcap, s.ext[t]); bl = max(bl, b[t]); }
-        const int B = __reduce_max_sync(kFull, bl);
-        for (int i = 0; i < B; ++i) {
-            const float4 p = sc.zcap[2 * i], v = sc.zcap[2 * i + 1];  // v.x = zv, v.y = rdv
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const float dot = (s.z[t] - p.z) * v.x;
-                const float cdf = fminf(fmaxf(dot * v.y, 0.0f), 1.0f);
-                const float xs = s.x[t] - p.x, ys = s.y[t] - p.y, zs = s.z[t] - fmaf(v.x, cdf, p.z);
-                const float sum = fmaf(zs, zs, fmaf(ys, ys, xs * xs));
-                const float rs = s.r[t] + p.w;
-                const float d = fmaf(-rs, rs, sum);
-                hit |= (d < 0.0f) & (i < b[t]);
-            }
-            if ((i & 7) == 7 && scan_should_stop<POLICY>(hit, participating)) break;
-        }
-        if (scan_should_stop<POLICY>(hit, participating)) return hit;
+        acc = scan_class<ZCapsuleTest, T, POLICY, MASKED>(sc.zcap, sc.zcap_pm, sc.n_zcap, s, rsq, participating, acc);
+        if (scan_should_stop<POLICY>(acc < 0, participating)) return acc < 0;
     }
-    // ---- cuboids (collision/sphere_cuboid.hh:9-27)
     if (sc.n_cub > 0) {
-        int bl = 0;
-        float rsq[T];
-#pragma unroll
-        for (int t = 0; t < T; ++t) { b[t] = count_lt(sc.cub_pm, sc.n_cub, s.ext[t]); bl = max(bl, b[t]); rsq[t] = s.r[t] * s.r[t]; }
-        const int B = __reduce_max_sync(kFull, bl);
-        for (int i = 0; i < B; ++i) {
-            const float4 c = sc.cub[4 * i], a1 = sc.cub[4 * i + 1], a2 = sc.cub[4 * i + 2], a3 = sc.cub[4 * i + 3];
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const float xs = s.x[t] - c.x, ys = s.y[t] - c.y, zs = s.z[t] - c.z;
-                const float e1 = fmaxf(fabsf(fmaf(a1.z, zs, fmaf(a1.y, ys, a1.x * xs))) - c.w, 0.0f);
-                const float e2 = fmaxf(fabsf(fmaf(a2.z, zs, fmaf(a2.y, ys, a2.x * xs))) - a1.w, 0.0f);
-                const float e3 = fmaxf(fabsf(fmaf(a3.z, zs, fmaf(a3.y, ys, a3.x * xs))) - a2.w, 0.0f);
-                const float d = fmaf(e3, e3, fmaf(e2, e2, e1 * e1)) - rsq[t];
-                hit |= (d < 0.0f) & (i < b[t]);
-            }
-            if ((i & 7) == 7 && scan_should_stop<POLICY>(hit, participating)) break;
-        }
-        if (scan_should_stop<POLICY>(hit, participating)) return hit;
+        acc = scan_class<CuboidTest, T, POLICY, MASKED>(sc.cub, sc.cub_pm, sc.n_cub, s, rsq, participating, acc);
+        if (scan_should_stop<POLICY>(acc < 0, participating)) return acc < 0;
     }
-    // ---- z-aligned cuboids (collision/sphere_cuboid.hh:35-52)
     if (sc.n_zcub > 0) {
-        int bl = 0;
-        float rsq[T];
-#pragma unroll
-        for (int t = 0; t < T; ++t) { b[t] = count_lt(sc.zcub_pm, sc.n_zcub, s.ext[t]); bl = max(bl, b[t]); rsq[t] = s.r[t] * s.r[t]; }
-        const int B = __reduce_max_sync(kFull, bl);
-        for (int i = 0; i < B; ++i) {
-            const float4 c = sc.zcub[3 * i], a1 = sc.zcub[3 * i + 1], a2 = sc.zcub[3 * i + 2];
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const float xs = s.x[t] - c.x, ys = s.y[t] - c.y, zs = s.z[t] - c.z;
-                const float e1 = fmaxf(fabsf(fmaf(a1.y, ys, a1.x * xs)) - a1.z, 0.0f);
-                const float e2 = fmaxf(fabsf(fmaf(a2.y, ys, a2.x * xs)) - a2.z, 0.0f);
-                const float e3 = fmaxf(fabsf(zs) - c.w, 0.0f);
-                const float d = fmaf(e3, e3, fmaf(e2, e2, e1 * e1)) - rsq[t];
-                hit |= (d < 0.0f) & (i < b[t]);
-            }
-            if ((i & 7) == 7 && scan_should_stop<POLICY>(hit, participating)) break;
-        }
+        acc = scan_class<ZCuboidTest, T, POLICY, MASKED>(sc.zcub, sc.zcub_pm, sc.n_zcub, s, rsq, participating, acc);
     }
-    return hit;
+    return acc < 0;
 }
 
 // ------------------------------------------------------------------------------------------------ point clouds
@@ -332,21 +337,28 @@ __device__ __forceinline__ bool scan_pointclouds(const SceneDesc &d, const Tile<
 // Returns true when this lane's state is collision free. `active` lanes take part; idle lanes only follow the
 // warp-uniform control flow. G = lanes per reference rake (8 for motions, 1 for single states).
 // EDGE: all lanes belong to one motion, so the first hit anywhere ends the whole warp's work.
-template <class R, int G, bool EDGE>
+template <class R, int G, bool EDGE, bool MASKED>
 __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, bool active) {
     constexpr int FT = 4;  // fine spheres processed together per lane
     constexpr int POLICY = EDGE ? kAnyHit : kUntilAllHit;
     const typename R::Tables &tb = R::tables();
     bool alive = active;  // false once this lane's state is known to collide (or lane idle)
 
-    // ---------------- stage 1: environment vs robot, frames streamed base -> tip
+    float sn[R::kDim], cs[R::kDim];
+    R::trig(q, sn, cs);
+
+    // ---------------- stage 1: environment vs robot. Links are visited tip -> base, the reference's own order
+    // (distal links collide first, so colliding states exit early); the frame of each group of links is rebuilt from
+    // the cached sin / cos by walking the chain from the base (a few dozen FMAs per step).
     Frame F;
-    frame_identity(F);
 #pragma unroll 1
-    for (int k = 0; k < R::kFrames; ++k) {
-        if (k > 0) R::advance(k, F, q);
+    for (int k = R::kFrames - 1; k >= 0; --k) {
+        if (tb.frame_link_begin[k] == tb.frame_link_begin[k + 1]) continue;
+        frame_identity(F);
 #pragma unroll 1
-        for (int l = tb.frame_link_begin[k]; l < tb.frame_link_begin[k + 1]; ++l) {
+        for (int j = 1; j <= k; ++j) R::advance(j, F, q, sn, cs);
+#pragma unroll 1
+        for (int l = tb.frame_link_begin[k + 1] - 1; l >= tb.frame_link_begin[k]; --l) {
             // bounding sphere of the link
             Tile<1> c;
             const float4 cl = tb.coarse[l];
@@ -354,7 +366,8 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
             c.r[0] = cl.w;
             const float ext = alive ? sqrtf(fmaf(c.z[0], c.z[0], fmaf(c.y[0], c.y[0], c.x[0] * c.x[0]))) + cl.w : -INFINITY;
             c.ext[0] = group_max<G>(ext);
-            bool chit = scan_scene<1, kUntilAllHit>(sc, c, alive);
+            if (!alive) { c.x[0] = kIdle; c.y[0] = kIdle; c.z[0] = kIdle; }  // idle lanes must never raise the sign bit
+            bool chit = scan_scene<1, kUntilAllHit, MASKED>(sc, c, alive);
             if (sd.n_pc > 0) chit |= scan_pointclouds<1>(sd, c, alive && !chit);
             const bool need = group_any<G>(chit && alive) && alive;
             if (!__any_sync(kFull, need)) continue;
@@ -373,9 +386,9 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
                     const bool on = need && (f0 + t < fe);
                     const float e = on ? sqrtf(fmaf(s.z[t], s.z[t], fmaf(s.y[t], s.y[t], s.x[t] * s.x[t]))) + fl.w : -INFINITY;
                     s.ext[t] = group_max<G>(e);
-                    if (!on) s.ext[t] = -INFINITY;
+                    if (!on) { s.ext[t] = -INFINITY; s.x[t] = kIdle; s.y[t] = kIdle; s.z[t] = kIdle; }
                 }
-                fhit |= scan_scene<FT, POLICY>(sc, s, need && !fhit);
+                fhit |= scan_scene<FT, POLICY, MASKED>(sc, s, need && !fhit);
                 if (sd.n_pc > 0) fhit |= scan_pointclouds<FT>(sd, s, need && !fhit);
                 if (EDGE) {
                     if (__any_sync(kFull, fhit)) return !fhit;
@@ -395,7 +408,7 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
     frame_identity(F);
 #pragma unroll 1
     for (int k = 0; k < R::kFrames; ++k) {
-        if (k > 0) R::advance(k, F, q);
+        if (k > 0) R::advance(k, F, q, sn, cs);
 #pragma unroll 1
         for (int p = tb.pair_frame_begin[k]; p < tb.pair_frame_begin[k + 1]; ++p) {
             const int la = tb.pair_a[p], lb = tb.pair_b[p], slot = tb.pair_slot[p];
@@ -483,7 +496,7 @@ __device__ __forceinline__ float vamp_l2_norm(const float (&v)[DIM]) {
 }
 
 // One warp per motion; motions are taken from a global queue (edge cost varies by 100x with early exit).
-template <class R>
+template <class R, bool MASKED>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float *__restrict__ q1, long long m, int resolution,
                         uint8_t *__restrict__ valid, LaunchCounters *cnt) {
@@ -526,7 +539,7 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
         bool ok = true;
         for (int base = 0; base < n; base += 4) {
             const bool active = (base + rake_in_pass) < n;
-            const bool good = check_state<R, 8, true>(q, sd, sc, active);
+            const bool good = check_state<R, 8, true, MASKED>(q, sd, sc, active);
             if (__any_sync(kFull, active && !good)) { ok = false; break; }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -540,7 +553,7 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
 
 // One lane per state: VampStateValidityChecker::isValid = validate_motion<Robot, rake, 1>(q, q), i.e. one fkcc on
 // 8 identical lanes (src/ompl/vamp/VampStateValidityChecker.h:37-41) -> group size 1 here.
-template <class R>
+template <class R, bool MASKED>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, uint8_t *__restrict__ valid, LaunchCounters *cnt) {
     extern __shared__ __align__(16) float smem[];
@@ -561,7 +574,7 @@ validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, 
 #pragma unroll
         for (int j = 0; j < D; ++j) q[j] = active ? __ldg(qs + i * D + j) : 0.0f;
         // validate_vector with start == goal: block = q + 0 * percents
-        const bool good = check_state<R, 1, false>(q, sd, sc, active);
+        const bool good = check_state<R, 1, false, MASKED>(q, sd, sc, active);
         if (active) valid[i] = good ? 1 : 0;
     }
 }

@@ -223,8 +223,19 @@ def gen_cuda(model: dict) -> str:
     w("    template <int K>")
     w("    __device__ static __forceinline__ void frame(const Frame &P, float q, float s, float c, Frame &F);")
     w("")
+    w("    // sin / cos of every revolute joint (the reference's polynomials), computed once per state")
+    w("    __device__ static __forceinline__ void trig(const float (&q)[kDim], float (&sn)[kDim], float (&cs)[kDim]) {")
+    w("#pragma unroll")
+    w("        for (int j = 0; j < kDim; ++j) {")
+    w("            if (joint_revolute(j)) { sn[j] = vamp_sin(q[j]); cs[j] = vamp_cos(q[j]); } else { sn[j] = 0.0f; cs[j] = 1.0f; }")
+    w("        }")
+    w("    }")
+    w("    __host__ __device__ static constexpr bool joint_revolute(int j) {")
+    w("        constexpr bool v[kDim] = {" + ", ".join("true" if fr["type"] in ("revolute", "continuous") else "false" for fr in sorted(frames[1:], key=lambda f: f["q_index"])) + "};")
+    w("        return v[j];")
+    w("    }")
     w("    // step the streaming frame from k-1 to k (k >= 1); uniform switch, static joint indices")
-    w("    __device__ static __forceinline__ void advance(int k, Frame &F, const float (&q)[kDim]);")
+    w("    __device__ static __forceinline__ void advance(int k, Frame &F, const float (&q)[kDim], const float (&sn)[kDim], const float (&cs)[kDim]);")
     w("};")
     w("")
     for fr in frames[1:]:
@@ -238,15 +249,12 @@ def gen_cuda(model: dict) -> str:
             w("    " + ln)
         w("}")
         w("")
-    w(f"__device__ __forceinline__ void {cname}::advance(int k, Frame &F, const float (&q)[kDim]) {{")
+    w(f"__device__ __forceinline__ void {cname}::advance(int k, Frame &F, const float (&q)[kDim], const float (&sn)[kDim], const float (&cs)[kDim]) {{")
     w("    const Frame P = F;")
     w("    switch (k) {")
     for fr in frames[1:]:
         qi = fr["q_index"]
-        if fr["type"] in ("revolute", "continuous"):
-            w(f"        case {fr['id']}: frame<{fr['id']}>(P, q[{qi}], vamp_sin(q[{qi}]), vamp_cos(q[{qi}]), F); break;")
-        else:
-            w(f"        case {fr['id']}: frame<{fr['id']}>(P, q[{qi}], 0.0f, 1.0f, F); break;")
+        w(f"        case {fr['id']}: frame<{fr['id']}>(P, q[{qi}], sn[{qi}], cs[{qi}], F); break;")
     w("        default: break;")
     w("    }")
     w("}")
