@@ -107,6 +107,30 @@ int b200mp_validate_motions_device(b200mp_ctx *ctx, int robot, const b200mp_env 
 /* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
 int64_t b200mp_launch_count(const b200mp_ctx *ctx);
 
+/* ---- nearest neighbours ------------------------------------------------------------------------------------- */
+/* A container of `dim`-dimensional points with the NearestNeighbors<_T> contract. Points get consecutive ids in
+ * insertion order (the adapter maps ids <-> _T). Distances are the reference's doubles: sqrt(sum (a_i - b_i)^2). */
+int b200mp_knn_create(b200mp_ctx *ctx, int dim, int metric, b200mp_knn **out);
+void b200mp_knn_destroy(b200mp_knn *knn);
+int b200mp_knn_clear(b200mp_knn *knn);
+int64_t b200mp_knn_size(const b200mp_knn *knn);
+/* pts[n][dim] host doubles; *first_id (may be NULL) receives the id of pts[0]. */
+int b200mp_knn_add(b200mp_knn *knn, const double *pts, int64_t n, int64_t *first_id);
+/* Append device-resident fp32 points (exactly representable in fp64); max_norm >= max |p|. Asynchronous on `stream`. */
+int b200mp_knn_add_device_f32(b200mp_knn *knn, const float *d_pts, int64_t n, float max_norm, void *stream);
+int b200mp_knn_remove(b200mp_knn *knn, int64_t id);
+/* q[nq][dim] -> idx[nq][k], dist[nq][k] ascending by (distance, id); missing entries are -1 / +inf and counts[i]
+ * (may be NULL) is the number found. self_ids (may be NULL): id that query i must not return (PRM queries a milestone
+ * before inserting it, src/ompl/geometric/planners/prm/src/PRM.cpp:583,601). k <= 160. */
+int b200mp_knn_query(b200mp_knn *knn, const double *q, int64_t nq, int k, const int64_t *self_ids, int64_t *idx, double *dist,
+                     int *counts);
+/* Device buffers. exclude_self != 0: query i skips d_self_ids[i], or id self_base + i when d_self_ids is NULL. */
+int b200mp_knn_query_device(b200mp_knn *knn, const double *d_q, int64_t nq, int k, const int64_t *d_self_ids, int64_t self_base,
+                            int exclude_self, int64_t *d_idx, double *d_dist, int *d_counts, void *stream);
+/* nearestR: all points with distance <= radius, ascending; *count = how many exist, at most cap are written.
+ * radius = +inf gives the exhaustive sorted list used for nearestK with k >= size. */
+int b200mp_knn_radius(b200mp_knn *knn, const double *q, double radius, int64_t *idx, double *dist, int64_t cap, int64_t *count);
+
 /* FP32 FMA micro-benchmark used as the measured roofline denominator of the collision kernels:
  * runs `iters` dependent-chain FFMA blocks on every SM and returns achieved TFLOP/s. */
 int b200mp_fp32_peak(b200mp_ctx *ctx, int iters, double *tflops);

@@ -60,6 +60,17 @@ def load_library():
     L.b200mp_launch_count.argtypes = [_vp]
     L.b200mp_launch_count.restype = _i64
     L.b200mp_fp32_peak.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
+    L.b200mp_knn_create.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(_vp)]
+    L.b200mp_knn_destroy.argtypes = [_vp]
+    L.b200mp_knn_clear.argtypes = [_vp]
+    L.b200mp_knn_size.argtypes = [_vp]
+    L.b200mp_knn_size.restype = _i64
+    L.b200mp_knn_add.argtypes = [_vp, _vp, _i64, C.POINTER(_i64)]
+    L.b200mp_knn_add_device_f32.argtypes = [_vp, _vp, _i64, C.c_float, _vp]
+    L.b200mp_knn_remove.argtypes = [_vp, _i64]
+    L.b200mp_knn_query.argtypes = [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp]
+    L.b200mp_knn_query_device.argtypes = [_vp, _vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp, _vp, _vp, _vp]
+    L.b200mp_knn_radius.argtypes = [_vp, _vp, C.c_double, _vp, _vp, _i64, C.POINTER(_i64)]
     _LIB = L
     return L
 
@@ -219,3 +230,79 @@ class Environment:
         if n > 0:
             self._L.b200mp_env_min_distances(self._h, kind, out.ctypes.data)
         return out
+
+
+class NearestNeighbors:
+    """Mirror of ompl::NearestNeighbors<_T> (datastructures/NearestNeighbors.h:46-115) over point ids: add / remove /
+    nearest / nearestK / nearestR / size / clear, results sorted ascending, double distances."""
+
+    def __init__(self, ctx: Context, dim: int, metric: int = 0):
+        self._L = load_library()
+        self._ctx = ctx
+        self.dim = dim
+        h = _vp()
+        _check(self._L.b200mp_knn_create(ctx._h, dim, metric, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._L.b200mp_knn_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        _check(self._L.b200mp_knn_clear(self._h))
+
+    def size(self) -> int:
+        return int(self._L.b200mp_knn_size(self._h))
+
+    def add(self, pts) -> int:
+        a = _host(pts, np.float64).reshape(-1, self.dim)
+        first = _i64()
+        _check(self._L.b200mp_knn_add(self._h, a.ctypes.data, a.shape[0], C.byref(first)))
+        return int(first.value)
+
+    def add_device_f32(self, ptr: int, n: int, max_norm: float, stream: int = 0):
+        _check(self._L.b200mp_knn_add_device_f32(self._h, ptr, n, max_norm, stream or None))
+
+    def remove(self, idx: int):
+        _check(self._L.b200mp_knn_remove(self._h, idx))
+
+    def nearest_k(self, q, k: int, self_ids=None):
+        """-> (idx[nq][k] int64 (-1 padded), dist[nq][k] float64 (+inf padded), counts[nq])"""
+        q = _host(q, np.float64).reshape(-1, self.dim)
+        nq = q.shape[0]
+        idx = np.full((nq, k), -1, np.int64)
+        dist = np.full((nq, k), np.inf, np.float64)
+        cnt = np.zeros(nq, np.int32)
+        sp = None
+        if self_ids is not None:
+            sid = _host(self_ids, np.int64)
+            sp = sid.ctypes.data
+        _check(self._L.b200mp_knn_query(self._h, q.ctypes.data, nq, k, sp, idx.ctypes.data, dist.ctypes.data, cnt.ctypes.data))
+        return idx, dist, cnt
+
+    def nearest(self, q) -> int:
+        if self.size() == 0:
+            raise B200MPError(6, "No elements found in nearest neighbors data structure")
+        idx, _, _ = self.nearest_k(q, 1)
+        return int(idx[0, 0])
+
+    def nearest_r(self, q, radius: float):
+        q = _host(q, np.float64).reshape(-1)
+        cap = max(self.size(), 1)
+        idx = np.zeros(cap, np.int64)
+        dist = np.zeros(cap, np.float64)
+        cnt = _i64()
+        _check(self._L.b200mp_knn_radius(self._h, q.ctypes.data, radius, idx.ctypes.data, dist.ctypes.data, cap, C.byref(cnt)))
+        return idx[:cnt.value].copy(), dist[:cnt.value].copy()
+
+    def query_device(self, q_ptr: int, nq: int, k: int, idx_ptr: int, dist_ptr: int, self_base: int = 0, exclude_self: bool = False,
+                     self_ids_ptr: int = 0, counts_ptr: int = 0, stream: int = 0):
+        _check(self._L.b200mp_knn_query_device(self._h, q_ptr, nq, k, self_ids_ptr or None, self_base, int(exclude_self), idx_ptr,
+                                               dist_ptr, counts_ptr or None, stream or None))
