@@ -12,6 +12,7 @@
  *   b200mp_env_*              vamp::collision::Environment<float> + sort()       external/vamp/src/impl/vamp/collision/environment.hh:14-85
  *                             and the shape constructors' min_distance           external/vamp/src/impl/vamp/collision/shapes.hh:52-67,165-189,236-239
  *   b200mp_env_add_capt       vamp::collision::CAPT (prebuilt tree arrays)       external/vamp/src/impl/vamp/collision/capt.hh:61-618
+ *   b200mp_env_add_pointcloud vamp::collision::CAPT::CAPT / subdivide            external/vamp/src/impl/vamp/collision/capt.hh:104-365
  *   b200mp_robot_info         Robot::dimension / resolution / joint bounds       src/ompl/vamp/VampStateSpace.h:10-36
  *   b200mp_knn_*              ompl::NearestNeighbors<_T> (Linear semantics)      src/ompl/datastructures/NearestNeighbors.h:46-115,
  *                                                                                src/ompl/datastructures/NearestNeighborsLinear.h:65-142
@@ -38,6 +39,7 @@ extern "C" {
 typedef struct b200mp_ctx b200mp_ctx;
 typedef struct b200mp_env b200mp_env;
 typedef struct b200mp_knn b200mp_knn;
+typedef struct b200mp_capt b200mp_capt;
 
 enum {
     B200MP_OK = 0,
@@ -80,6 +82,15 @@ int b200mp_env_add_capsules(b200mp_env *env, const float *c, int n, int z_aligne
  * vectors), aff[3][n_aff8 * 8] (x row, y row, z row), top[6]. */
 int b200mp_env_add_capt(b200mp_env *env, int nlog2, const float *tests, const float *aabbs, const uint32_t *aff_starts,
                         const float *aff, int64_t n_aff8, const float *top, float r_min, float r_max, float r_point);
+/* Build the tree from raw points on the host exactly as the reference's constructor does
+ * (vamp::collision::CAPT(points, r_min, r_max, r_point), collision/capt.hh:294-365) and attach it. xyz[n][3]. */
+int b200mp_env_add_pointcloud(b200mp_env *env, const float *xyz, int64_t n, float r_min, float r_max, float r_point);
+/* The same build as a standalone host object (no GPU needed), e.g. to export the arrays.
+ * sizes[4] = nlog2, n_tests, n_leaves, n_aff8. Any output pointer of b200mp_capt_export may be NULL. */
+int b200mp_capt_build(const float *xyz, int64_t n, float r_min, float r_max, float r_point, b200mp_capt **out);
+void b200mp_capt_destroy(b200mp_capt *capt);
+int b200mp_capt_sizes(const b200mp_capt *capt, int64_t *sizes);
+int b200mp_capt_export(const b200mp_capt *capt, float *tests, float *aabbs, uint32_t *aff_starts, float *aff, float *top);
 /* Sort every shape list by min_distance (Environment::sort). Obstacles are otherwise tested in insertion
  * order with the reference's ordered-scan-with-break semantics. */
 int b200mp_env_sort(b200mp_env *env);
@@ -104,6 +115,10 @@ int b200mp_validate_states_device(b200mp_ctx *ctx, int robot, const b200mp_env *
                                   uint8_t *d_valid, void *stream);
 int b200mp_validate_motions_device(b200mp_ctx *ctx, int robot, const b200mp_env *env, const float *d_q0, const float *d_q1,
                                    int64_t m, int resolution, uint8_t *d_valid, void *stream);
+/* Motions given as index pairs into one device-resident state table: edge e runs from d_states[d_edges[2e]] to
+ * d_states[d_edges[2e+1]] (roadmap edges; PRM::addMilestone checks neighbour -> new milestone, PRM.cpp:585-598). */
+int b200mp_validate_edges_device(b200mp_ctx *ctx, int robot, const b200mp_env *env, const float *d_states, const int32_t *d_edges,
+                                 int64_t m, int resolution, uint8_t *d_valid, void *stream);
 /* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
 int64_t b200mp_launch_count(const b200mp_ctx *ctx);
 
@@ -127,9 +142,38 @@ int b200mp_knn_query(b200mp_knn *knn, const double *q, int64_t nq, int k, const 
 /* Device buffers. exclude_self != 0: query i skips d_self_ids[i], or id self_base + i when d_self_ids is NULL. */
 int b200mp_knn_query_device(b200mp_knn *knn, const double *d_q, int64_t nq, int k, const int64_t *d_self_ids, int64_t self_base,
                             int exclude_self, int64_t *d_idx, double *d_dist, int *d_counts, void *stream);
+/* Same with fp32 queries (converted exactly to fp64 on the device); query i skips id self_base + i when exclude_self. */
+int b200mp_knn_query_device_f32(b200mp_knn *knn, const float *d_q, int64_t nq, int k, int64_t self_base, int exclude_self,
+                                int64_t *d_idx, double *d_dist, int *d_counts, void *stream);
 /* nearestR: all points with distance <= radius, ascending; *count = how many exist, at most cap are written.
  * radius = +inf gives the exhaustive sorted list used for nearestK with k >= size. */
 int b200mp_knn_radius(b200mp_knn *knn, const double *q, double radius, int64_t *idx, double *dist, int64_t cap, int64_t *count);
+
+/* ---- batched PRM roadmap construction ------------------------------------------------------------------------- */
+/* Replaces the per-milestone loop of ompl::geometric::PRM (growRoadmap / addMilestone,
+ * src/ompl/geometric/planners/prm/src/PRM.cpp:240-270,570-604; KStrategy, ConnectionStrategy.h:78-82) by one pass
+ * per phase over the whole batch: sample -> state validity -> kNN (self excluded) -> edge list -> edge validity. */
+typedef struct b200mp_roadmap_stats {
+    int64_t n_states, n_candidates, n_edges, n_valid_edges;
+    double ms_sample, ms_knn, ms_edges, ms_validate, ms_total; /* device time per phase (CUDA events) */
+} b200mp_roadmap_stats;
+/* Phase 1. Candidates cand_first .. cand_first + cand_count - 1 of the sample stream of `seed` (candidate c is a pure
+ * function of (seed, c): Philox4x32-10 -> uniform in the robot's joint box) are validated and the valid ones are
+ * written, in stream order, to d_states[capacity][dim]. *n_valid = number of valid candidates (it may exceed
+ * capacity; only the first `capacity` are stored). Synchronises `stream`. */
+int b200mp_prm_sample_device(b200mp_ctx *ctx, int robot, const b200mp_env *env, uint64_t seed, uint64_t cand_first, int64_t cand_count,
+                             float *d_states, int64_t capacity, int64_t *n_valid, void *stream);
+/* Phase 3. From the neighbour table d_nbr[n][k] of ALL states (ids, -1 = none) keep, for the queries
+ * q_first .. q_first + q_count - 1, edge (i, j = d_nbr[i][s]) when i < j or i is not listed by j; written in (i, s)
+ * order as (min, max) index pairs to d_edges[capacity][2], with d_weights[e] = d_dist_local[(i - q_first) * k + s]
+ * (both may be NULL). Synchronises `stream`. */
+int b200mp_prm_edges_device(b200mp_ctx *ctx, const int64_t *d_nbr, const double *d_dist_local, int64_t n, int k, int64_t q_first,
+                            int64_t q_count, int32_t *d_edges, double *d_weights, int64_t capacity, int64_t *n_edges, void *stream);
+/* All phases on one GPU (phase 2 = b200mp_knn_add_device_f32 + b200mp_knn_query_device_f32, phase 4 =
+ * b200mp_validate_edges_device). Host outputs (any may be NULL): states[n][dim], edges[edge_capacity][2],
+ * valid[edge_capacity], weights[edge_capacity]; n * k always suffices for edge_capacity. */
+int b200mp_prm_build(b200mp_ctx *ctx, int robot, const b200mp_env *env, uint64_t seed, int64_t n, int k, int resolution, float *states,
+                     int32_t *edges, uint8_t *valid, double *weights, int64_t edge_capacity, b200mp_roadmap_stats *stats);
 
 /* FP32 FMA micro-benchmark used as the measured roofline denominator of the collision kernels:
  * runs `iters` dependent-chain FFMA blocks on every SM and returns achieved TFLOP/s. */

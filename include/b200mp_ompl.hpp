@@ -1,0 +1,504 @@
+// b200mp_ompl.hpp -- header-only C++ adapters that put the b200mp CUDA engine behind OMPL's plugin surface.
+//
+// Drop-in for the reference's VAMP bridge (paths relative to the reference checkout):
+//   ompl::b200::B200StateValidityChecker<Robot>  <->  ompl::vamp::VampStateValidityChecker<Robot>  src/ompl/vamp/VampStateValidityChecker.h:22-48
+//   ompl::b200::B200MotionValidator<Robot>       <->  ompl::vamp::VampMotionValidator<Robot>       src/ompl/vamp/VampMotionValidator.h:22-57
+//   ompl::b200::Environment                      <->  vamp::collision::Environment<float>          external/vamp/src/impl/vamp/collision/environment.hh:14-85
+//                                                     + vamp::collision::factory::*::array         external/vamp/src/impl/vamp/collision/factory.hh:26-190
+//   ompl::b200::getRobotBounds<Robot>()          <->  ompl::vamp::getRobotBounds<Robot>()          src/ompl/vamp/VampStateSpace.h:10-36
+//   ompl::b200::NearestNeighborsB200<_T>         <->  ompl::NearestNeighbors<_T> backends          src/ompl/datastructures/NearestNeighbors.h:46-115
+//                                                     (Linear semantics: NearestNeighborsLinear.h:65-142)
+// The classes derive from the real OMPL base classes, so planners install them through the usual calls
+// (SpaceInformation::setStateValidityChecker / setMotionValidator, src/ompl/base/SpaceInformation.h:146-172;
+// Planner::setNearestNeighbors<NearestNeighborsB200>(), PRM.h:254-265, RRTConnect.h:106-115, RRTstar.h:141-149).
+// Everything below the virtual calls goes through the C ABI of include/b200mp.h; errors surface as ompl::Exception.
+// There is no CPU fallback: constructing an Engine without a usable GPU throws.
+#pragma once
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <ompl/base/MotionValidator.h>
+#include <ompl/base/State.h>
+#include <ompl/base/StateValidityChecker.h>
+#include <ompl/datastructures/NearestNeighbors.h>
+#include <ompl/util/Exception.h>
+// RealVectorStateSpace::StateType (double *values). Tests substitute a layout-compatible mock because the genuine
+// header pulls in Boost/Eigen, which this build image does not have.
+#ifndef B200MP_OMPL_STATE_HEADER
+#define B200MP_OMPL_STATE_HEADER <ompl/base/spaces/RealVectorStateSpace.h>
+#endif
+#include B200MP_OMPL_STATE_HEADER
+
+#include "b200mp.h"
+
+namespace ompl::b200
+{
+    namespace ob = ompl::base;
+
+    inline void check(int rc, const char *what)
+    {
+        if (rc != B200MP_OK)
+            throw ompl::Exception(std::string("b200mp::") + what, b200mp_last_error());
+    }
+
+    // Robot tags; `dimension`/`resolution` mirror vamp::robots::<Robot> (robots/panda.hh:14-18, robots/fetch.hh:14-18).
+    struct Panda
+    {
+        static constexpr int id = B200MP_ROBOT_PANDA;
+        static constexpr std::size_t dimension = 7;
+        static constexpr int resolution = 32;
+    };
+    struct Fetch
+    {
+        static constexpr int id = B200MP_ROBOT_FETCH;
+        static constexpr std::size_t dimension = 8;
+        static constexpr int resolution = 32;
+    };
+
+    /// One engine context per GPU. Shared by validators, environments and nearest-neighbour containers.
+    class Engine
+    {
+    public:
+        explicit Engine(int device = 0)
+        {
+            check(b200mp_create(device, &ctx_), "Engine");
+        }
+        ~Engine()
+        {
+            b200mp_destroy(ctx_);
+        }
+        Engine(const Engine &) = delete;
+        Engine &operator=(const Engine &) = delete;
+        b200mp_ctx *get() const
+        {
+            return ctx_;
+        }
+        /// Process-wide default engine on `device` (created on first use). NearestNeighborsB200 is default
+        /// constructed by the planners, so it cannot be handed an engine explicitly.
+        static std::shared_ptr<Engine> shared(int device = 0)
+        {
+            static std::mutex mu;
+            static std::vector<std::shared_ptr<Engine>> engines;
+            std::lock_guard<std::mutex> lk(mu);
+            if (static_cast<int>(engines.size()) <= device)
+                engines.resize(device + 1);
+            if (!engines[device])
+                engines[device] = std::make_shared<Engine>(device);
+            return engines[device];
+        }
+
+    private:
+        b200mp_ctx *ctx_{nullptr};
+    };
+    using EnginePtr = std::shared_ptr<Engine>;
+
+    /// Joint limits as the bridge derives them (scale 0 and 1 through Robot::scale_configuration).
+    template <typename Robot>
+    inline void getRobotBounds(std::array<double, Robot::dimension> &lo, std::array<double, Robot::dimension> &hi)
+    {
+        float l[16], h[16];
+        int dim = 0;
+        check(b200mp_robot_info(Robot::id, &dim, nullptr, nullptr, l, h), "getRobotBounds");
+        for (std::size_t i = 0; i < Robot::dimension; ++i)
+        {
+            lo[i] = l[i];
+            hi[i] = h[i];
+        }
+    }
+
+    /// Scene description with the reference's shape classes and ordering rules. Obstacles are tested in insertion
+    /// order per class with the ordered-scan-with-break semantics unless sort() is called (environment.hh:43-69).
+    class Environment
+    {
+    public:
+        explicit Environment(EnginePtr engine) : engine_(std::move(engine))
+        {
+            check(b200mp_env_create(engine_->get(), &env_), "Environment");
+        }
+        ~Environment()
+        {
+            b200mp_env_destroy(env_);
+        }
+        Environment(const Environment &) = delete;
+        Environment &operator=(const Environment &) = delete;
+
+        /// factory::sphere::array(center, radius)  (factory.hh:160-172)
+        void addSphere(const std::array<float, 3> &c, float r)
+        {
+            const float s[4] = {c[0], c[1], c[2], r};
+            check(b200mp_env_add_spheres(env_, s, 1), "addSphere");
+        }
+        /// factory::cuboid::array(center, euler_xyz, half_extents)  (factory.hh:26-62). A box whose third axis is
+        /// +z goes to the z-aligned list exactly when the reference's Python binding would put it there
+        /// (bindings/environment.cc:110-145); the C++ demos push everything to `cuboids`, hence the flag.
+        void addCuboid(const std::array<float, 3> &c, const std::array<float, 3> &euler_xyz, const std::array<float, 3> &half,
+                       bool z_aligned_list = false)
+        {
+            float rec[15];
+            cuboidRecord(c, euler_xyz, half, rec);
+            check(b200mp_env_add_cuboids(env_, rec, 1, z_aligned_list ? 1 : 0), "addCuboid");
+        }
+        /// factory::capsule::endpoints::array(p1, p2, radius)  (factory.hh:110-126)
+        void addCapsule(const std::array<float, 3> &p1, const std::array<float, 3> &p2, float r, bool z_aligned_list = false)
+        {
+            const float rec[7] = {p1[0], p1[1], p1[2], p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2], r};
+            check(b200mp_env_add_capsules(env_, rec, 1, z_aligned_list ? 1 : 0), "addCapsule");
+        }
+        /// factory::cylinder::center::array(center, euler_xyz, radius, length) stored as a capsule, which is what the
+        /// reference's demo does because cylinders are never tested (demos/vamp/MotionBenchmakerDemo.cpp:173-206).
+        void addCylinderAsCapsule(const std::array<float, 3> &c, const std::array<float, 3> &euler_xyz, float r, float length)
+        {
+            float rec[15];
+            cuboidRecord(c, euler_xyz, {0.F, 0.F, 0.F}, rec);
+            const float hx = rec[9] * length / 2, hy = rec[10] * length / 2, hz = rec[11] * length / 2;  // third axis
+            addCapsule({c[0] - hx, c[1] - hy, c[2] - hz}, {c[0] + hx, c[1] + hy, c[2] + hz}, r);
+        }
+        /// vamp::collision::CAPT(points, r_min, r_max, r_point) built by the engine (capt.hh:294-365)
+        void addPointcloud(const float *xyz, std::size_t n, float r_min, float r_max, float r_point)
+        {
+            check(b200mp_env_add_pointcloud(env_, xyz, static_cast<int64_t>(n), r_min, r_max, r_point), "addPointcloud");
+        }
+        void sort()
+        {
+            check(b200mp_env_sort(env_), "sort");
+        }
+        /// Upload to the GPU; required after the last add/sort.
+        void commit()
+        {
+            check(b200mp_env_commit(env_), "commit");
+        }
+        b200mp_env *get() const
+        {
+            return env_;
+        }
+        const EnginePtr &engine() const
+        {
+            return engine_;
+        }
+
+    private:
+        static void cuboidRecord(const std::array<float, 3> &c, const std::array<float, 3> &e, const std::array<float, 3> &h, float *rec)
+        {
+            // R = Rz(e[2]) * Ry(e[1]) * Rx(e[0]); axes are the columns (factory.hh:26-62)
+            const double cr = std::cos(e[0]), sr = std::sin(e[0]), cp = std::cos(e[1]), sp = std::sin(e[1]), cy = std::cos(e[2]),
+                         sy = std::sin(e[2]);
+            const double R[3][3] = {{cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr},
+                                    {sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr},
+                                    {-sp, cp * sr, cp * cr}};
+            for (int i = 0; i < 3; ++i)
+                rec[i] = c[i];
+            for (int a = 0; a < 3; ++a)
+                for (int i = 0; i < 3; ++i)
+                    rec[3 + 3 * a + i] = static_cast<float>(R[i][a]);
+            for (int i = 0; i < 3; ++i)
+                rec[12 + i] = h[i];
+        }
+        EnginePtr engine_;
+        b200mp_env *env_{nullptr};
+    };
+    using EnvironmentPtr = std::shared_ptr<Environment>;
+
+    namespace detail
+    {
+        inline const double *values(const ob::State *s)
+        {
+            return s->as<ob::RealVectorStateSpace::StateType>()->values;
+        }
+        // gather `n` scattered OMPL states (each its own heap array, RealVectorStateSpace.cpp:272-277) into one row-major block
+        inline void gather(const ob::State *const *states, std::size_t n, std::size_t dim, std::vector<double> &out)
+        {
+            out.resize(n * dim);
+            for (std::size_t i = 0; i < n; ++i)
+                std::copy_n(values(states[i]), dim, out.data() + i * dim);
+        }
+    }  // namespace detail
+
+    /// isValid(state) == validate_motion<Robot, rake, 1>(q, q, env) of the reference bridge. Thread safe.
+    template <typename Robot>
+    class B200StateValidityChecker : public ob::StateValidityChecker
+    {
+    public:
+        B200StateValidityChecker(ob::SpaceInformation *si, EnvironmentPtr env) : ob::StateValidityChecker(si), env_(std::move(env))
+        {
+        }
+        B200StateValidityChecker(const ob::SpaceInformationPtr &si, EnvironmentPtr env)
+          : ob::StateValidityChecker(si), env_(std::move(env))
+        {
+        }
+
+        bool isValid(const ob::State *state) const override
+        {
+            std::uint8_t ok = 0;
+            check(b200mp_validate_states_f64(env_->engine()->get(), Robot::id, env_->get(), detail::values(state), 1, &ok), "isValid");
+            return ok != 0;
+        }
+
+        /// Batch extension (not part of the OMPL interface): out[i] = isValid(states[i]), one kernel launch.
+        void isValidBatch(const ob::State *const *states, std::size_t n, std::uint8_t *out) const
+        {
+            std::vector<double> q;
+            detail::gather(states, n, Robot::dimension, q);
+            check(b200mp_validate_states_f64(env_->engine()->get(), Robot::id, env_->get(), q.data(), static_cast<int64_t>(n), out),
+                  "isValidBatch");
+        }
+
+    private:
+        EnvironmentPtr env_;
+    };
+
+    /// checkMotion(s1, s2) == validate_motion<Robot, rake, Robot::resolution>(s1, s2, env). Like the reference bridge
+    /// it does not maintain valid_/invalid_ and the lastValid overload reports {nullptr, 0.0}
+    /// (src/ompl/vamp/VampMotionValidator.h:37-52). Thread safe.
+    template <typename Robot>
+    class B200MotionValidator : public ob::MotionValidator
+    {
+    public:
+        B200MotionValidator(ob::SpaceInformation *si, EnvironmentPtr env) : ob::MotionValidator(si), env_(std::move(env))
+        {
+        }
+        B200MotionValidator(const ob::SpaceInformationPtr &si, EnvironmentPtr env) : ob::MotionValidator(si), env_(std::move(env))
+        {
+        }
+
+        bool checkMotion(const ob::State *s1, const ob::State *s2) const override
+        {
+            std::uint8_t ok = 0;
+            check(b200mp_validate_motions_f64(env_->engine()->get(), Robot::id, env_->get(), detail::values(s1), detail::values(s2), 1,
+                                              Robot::resolution, &ok),
+                  "checkMotion");
+            return ok != 0;
+        }
+
+        bool checkMotion(const ob::State *s1, const ob::State *s2, std::pair<ob::State *, double> &lastValid) const override
+        {
+            lastValid.first = nullptr;
+            lastValid.second = 0.0;
+            return checkMotion(s1, s2);
+        }
+
+        /// Batch extension: out[i] = checkMotion(s1[i], s2[i]), one kernel launch (PRM::addMilestone
+        /// checks k edges that share an endpoint, RRT* rewiring checks a neighbourhood).
+        void checkMotions(const ob::State *const *s1, const ob::State *const *s2, std::size_t n, std::uint8_t *out) const
+        {
+            std::vector<double> a, b;
+            detail::gather(s1, n, Robot::dimension, a);
+            detail::gather(s2, n, Robot::dimension, b);
+            check(b200mp_validate_motions_f64(env_->engine()->get(), Robot::id, env_->get(), a.data(), b.data(), static_cast<int64_t>(n),
+                                              Robot::resolution, out),
+                  "checkMotions");
+        }
+
+    private:
+        EnvironmentPtr env_;
+    };
+
+    /// GPU nearest-neighbour container with the NearestNeighbors<_T> contract. OMPL hands a backend only opaque
+    /// elements (`unsigned long` vertices for PRM, `Motion *` for RRTConnect / RRT*) and a distance functor, so the
+    /// coordinates come through bind(): a function mapping an element to its `dim` doubles, e.g.
+    ///     auto &nn = dynamic_cast<NearestNeighborsB200<PRM::Vertex> &>(*prm.getNearestNeighbors());
+    ///     nn.bind(7, [&](const PRM::Vertex &v) { return stateProperty[v]->as<RealVectorStateSpace::StateType>()->values; });
+    /// The metric evaluated on the GPU is RealVectorStateSpace::distance (RealVectorStateSpace.cpp:230-242) in exact
+    /// fp64; on first use the container verifies that distFun_ agrees with it and throws otherwise. Results are
+    /// sorted ascending by (distance, insertion order). Not thread safe (like NearestNeighborsGNATNoThreadSafety).
+    template <typename _T>
+    class NearestNeighborsB200 : public ompl::NearestNeighbors<_T>
+    {
+    public:
+        using CoordFunction = std::function<const double *(const _T &)>;
+
+        NearestNeighborsB200() = default;
+        ~NearestNeighborsB200() override
+        {
+            if (knn_)
+                b200mp_knn_destroy(knn_);
+        }
+
+        /// Must be called before the first add(). `engine` defaults to the process-wide engine on device 0.
+        void bind(std::size_t dim, CoordFunction coords, EnginePtr engine = nullptr)
+        {
+            if (knn_)
+                throw ompl::Exception("NearestNeighborsB200", "bind() called twice");
+            engine_ = engine ? std::move(engine) : Engine::shared(0);
+            dim_ = dim;
+            coords_ = std::move(coords);
+            check(b200mp_knn_create(engine_->get(), static_cast<int>(dim), B200MP_METRIC_L2, &knn_), "knn_create");
+        }
+
+        bool reportsSortedResults() const override
+        {
+            return true;
+        }
+
+        void clear() override
+        {
+            elems_.clear();
+            alive_.clear();
+            pending_.clear();
+            live_ = 0;
+            verified_ = false;
+            if (knn_)
+                check(b200mp_knn_clear(knn_), "knn_clear");
+        }
+
+        void add(const _T &data) override
+        {
+            requireBound();
+            const double *c = coords_(data);
+            pending_.insert(pending_.end(), c, c + dim_);  // uploaded lazily, in one copy, before the next query
+            elems_.push_back(data);
+            alive_.push_back(1);
+            ++live_;
+        }
+
+        void add(const std::vector<_T> &data) override
+        {
+            elems_.reserve(elems_.size() + data.size());
+            for (const auto &d : data)
+                add(d);
+        }
+
+        bool remove(const _T &data) override
+        {
+            for (std::size_t i = elems_.size(); i-- > 0;)
+                if (alive_[i] && elems_[i] == data)
+                {
+                    flush();
+                    check(b200mp_knn_remove(knn_, static_cast<int64_t>(i)), "knn_remove");
+                    alive_[i] = 0;
+                    --live_;
+                    return true;
+                }
+            return false;
+        }
+
+        _T nearest(const _T &data) const override
+        {
+            if (live_ == 0)
+                throw ompl::Exception("No elements found in nearest neighbors data structure");
+            std::vector<_T> nbh;
+            nearestK(data, 1, nbh);
+            return nbh.front();
+        }
+
+        void nearestK(const _T &data, std::size_t k, std::vector<_T> &nbh) const override
+        {
+            nbh.clear();
+            if (k == 0 || live_ == 0)
+                return;
+            flush();
+            k = std::min(k, live_);
+            idx_.resize(k);
+            dist_.resize(k);
+            int found = 0;
+            check(b200mp_knn_query(knn_, coords_(data), 1, static_cast<int>(k), nullptr, idx_.data(), dist_.data(), &found), "knn_query");
+            nbh.reserve(found);
+            for (int i = 0; i < found; ++i)
+                nbh.push_back(elems_[idx_[i]]);
+            verifyMetric(data, nbh, found);
+        }
+
+        void nearestR(const _T &data, double radius, std::vector<_T> &nbh) const override
+        {
+            nbh.clear();
+            if (live_ == 0)
+                return;
+            flush();
+            idx_.resize(live_);
+            dist_.resize(live_);
+            int64_t found = 0;
+            check(b200mp_knn_radius(knn_, coords_(data), radius, idx_.data(), dist_.data(), static_cast<int64_t>(live_), &found),
+                  "knn_radius");
+            nbh.reserve(found);
+            for (int64_t i = 0; i < found; ++i)
+                nbh.push_back(elems_[idx_[i]]);
+        }
+
+        /// Batch extension: neighbours of many elements in one launch; nbh[i] as nearestK(data[i], k, .) would return.
+        void nearestKBatch(const std::vector<_T> &data, std::size_t k, std::vector<std::vector<_T>> &nbh) const
+        {
+            nbh.assign(data.size(), {});
+            if (k == 0 || live_ == 0 || data.empty())
+                return;
+            flush();
+            k = std::min(k, live_);
+            std::vector<double> q(data.size() * dim_);
+            for (std::size_t i = 0; i < data.size(); ++i)
+                std::copy_n(coords_(data[i]), dim_, q.data() + i * dim_);
+            std::vector<int64_t> idx(data.size() * k);
+            std::vector<double> dist(data.size() * k);
+            std::vector<int> cnt(data.size());
+            check(b200mp_knn_query(knn_, q.data(), static_cast<int64_t>(data.size()), static_cast<int>(k), nullptr, idx.data(), dist.data(),
+                                   cnt.data()),
+                  "knn_query");
+            for (std::size_t i = 0; i < data.size(); ++i)
+                for (int j = 0; j < cnt[i]; ++j)
+                    nbh[i].push_back(elems_[idx[i * k + j]]);
+        }
+
+        std::size_t size() const override
+        {
+            return live_;
+        }
+
+        void list(std::vector<_T> &data) const override
+        {
+            data.clear();
+            data.reserve(live_);
+            for (std::size_t i = 0; i < elems_.size(); ++i)
+                if (alive_[i])
+                    data.push_back(elems_[i]);
+        }
+
+    private:
+        void requireBound() const
+        {
+            if (!knn_)
+                throw ompl::Exception("NearestNeighborsB200", "bind(dim, coords) must be called before use: the backend needs "
+                                                              "coordinates, OMPL only hands it opaque elements");
+        }
+        void flush() const
+        {
+            requireBound();
+            if (pending_.empty())
+                return;
+            check(b200mp_knn_add(knn_, pending_.data(), static_cast<int64_t>(pending_.size() / dim_), nullptr), "knn_add");
+            pending_.clear();
+        }
+        // guards against a custom StateSpace::distance being silently replaced by L2 (SURVEY 7 hard part 5)
+        void verifyMetric(const _T &q, const std::vector<_T> &nbh, int found) const
+        {
+            if (verified_ || !this->distFun_ || found == 0)
+                return;
+            for (int i = 0; i < std::min(found, 4); ++i)
+            {
+                const double want = this->distFun_(q, nbh[i]);
+                if (std::fabs(want - dist_[i]) > 1e-9 * std::max(1.0, std::fabs(want)))
+                    throw ompl::Exception("NearestNeighborsB200", "the planner's distance function is not the Euclidean "
+                                                                  "RealVectorStateSpace metric evaluated on the GPU");
+            }
+            verified_ = true;
+        }
+
+        EnginePtr engine_;
+        b200mp_knn *knn_{nullptr};
+        std::size_t dim_{0};
+        CoordFunction coords_;
+        std::vector<_T> elems_;  // id -> element (ids are insertion order, tombstoned on remove)
+        std::vector<char> alive_;
+        std::size_t live_{0};
+        mutable std::vector<double> pending_;
+        mutable std::vector<int64_t> idx_;
+        mutable std::vector<double> dist_;
+        mutable bool verified_{false};
+    };
+}  // namespace ompl::b200

@@ -231,7 +231,7 @@ int b200mp_env_add_capt(b200mp_env *e, int nlog2, const float *tests, const floa
                         const float *aff, int64_t n_aff8, const float *top, float r_min, float r_max, float r_point) {
     (void)r_min;
     (void)r_max;
-    if (!e || !tests || !aabbs || !aff_starts || !aff || !top || nlog2 < 0 || nlog2 > 30 || n_aff8 < 0)
+    if (!e || (!tests && nlog2 > 0) || !aabbs || !aff_starts || !aff || !top || nlog2 < 0 || nlog2 > 30 || n_aff8 < 0)
         return fail(B200MP_ERR_INVALID, "b200mp_env_add_capt: bad argument");
     if (e->pcs.size() >= kMaxPointClouds) return fail(B200MP_ERR_CAPACITY, "b200mp_env_add_capt: at most %d point clouds", kMaxPointClouds);
     B200_CUDA(cudaSetDevice(e->ctx->device));
@@ -241,10 +241,10 @@ int b200mp_env_add_capt(b200mp_env *e, int nlog2, const float *tests, const floa
     B200_CUDA(cudaMalloc(&d.aabbs, nl * 6 * 4));
     B200_CUDA(cudaMalloc(&d.aff_starts, (nl + 1) * 4));
     B200_CUDA(cudaMalloc(&d.aff, std::max<size_t>(3 * n_aff8 * 8, 4) * 4));
-    B200_CUDA(cudaMemcpy(d.tests, tests, nt * 4, cudaMemcpyHostToDevice));
+    if (nt) B200_CUDA(cudaMemcpy(d.tests, tests, nt * 4, cudaMemcpyHostToDevice));
     B200_CUDA(cudaMemcpy(d.aabbs, aabbs, nl * 6 * 4, cudaMemcpyHostToDevice));
     B200_CUDA(cudaMemcpy(d.aff_starts, aff_starts, (nl + 1) * 4, cudaMemcpyHostToDevice));
-    B200_CUDA(cudaMemcpy(d.aff, aff, 3 * n_aff8 * 8 * 4, cudaMemcpyHostToDevice));
+    if (n_aff8) B200_CUDA(cudaMemcpy(d.aff, aff, 3 * n_aff8 * 8 * 4, cudaMemcpyHostToDevice));
     d.view.tests = d.tests;
     d.view.aabbs = d.aabbs;
     d.view.aff_starts = d.aff_starts;
@@ -373,8 +373,8 @@ int b200mp_env_commit(b200mp_env *e) {
 namespace {
 
 template <class R>
-int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const float *d_q1, int64_t m, int resolution,
-                   uint8_t *d_valid, cudaStream_t st) {
+int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const float *d_q1, const int2 *d_pairs, int64_t m,
+                   int resolution, uint8_t *d_valid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4;
     auto kern = e->desc.sorted ? validate_motions_kernel<R, false> : validate_motions_kernel<R, true>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -385,7 +385,7 @@ int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const 
     long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock);
     blocks = std::max<long long>(blocks, 1);
     B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), kBlockThreads, smem, st>>>(e->desc, d_q0, d_q1, m, resolution, d_valid,
+    kern<<<static_cast<unsigned>(blocks), kBlockThreads, smem, st>>>(e->desc, d_q0, d_q1, d_pairs, m, resolution, d_valid,
                                                                      static_cast<LaunchCounters *>(c->d_counters));
     B200_CUDA(cudaGetLastError());
     c->launches.fetch_add(1);
@@ -512,8 +512,25 @@ int b200mp_validate_motions_device(b200mp_ctx *c, int robot, const b200mp_env *e
     B200_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     switch (robot) {
-        case B200MP_ROBOT_PANDA: return launch_motions<Panda>(c, e, d_q0, d_q1, m, resolution ? resolution : Panda::kResolution, d_valid, st);
-        case B200MP_ROBOT_FETCH: return launch_motions<Fetch>(c, e, d_q0, d_q1, m, resolution ? resolution : Fetch::kResolution, d_valid, st);
+        case B200MP_ROBOT_PANDA: return launch_motions<Panda>(c, e, d_q0, d_q1, nullptr, m, resolution ? resolution : Panda::kResolution, d_valid, st);
+        case B200MP_ROBOT_FETCH: return launch_motions<Fetch>(c, e, d_q0, d_q1, nullptr, m, resolution ? resolution : Fetch::kResolution, d_valid, st);
+        default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
+    }
+}
+
+int b200mp_validate_edges_device(b200mp_ctx *c, int robot, const b200mp_env *e, const float *d_states, const int32_t *d_edges, int64_t m,
+                                 int resolution, uint8_t *d_valid, void *stream) {
+    int rc = check_common("b200mp_validate_edges_device", c, e, d_states, d_valid, m);
+    if (rc) return rc;
+    if (m == 0) return B200MP_OK;
+    if (!d_edges) return fail(B200MP_ERR_INVALID, "b200mp_validate_edges_device: d_edges is NULL");
+    if (resolution < 0) return fail(B200MP_ERR_INVALID, "b200mp_validate_edges_device: negative resolution");
+    B200_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    const int2 *pairs = reinterpret_cast<const int2 *>(d_edges);
+    switch (robot) {
+        case B200MP_ROBOT_PANDA: return launch_motions<Panda>(c, e, d_states, d_states, pairs, m, resolution ? resolution : Panda::kResolution, d_valid, st);
+        case B200MP_ROBOT_FETCH: return launch_motions<Fetch>(c, e, d_states, d_states, pairs, m, resolution ? resolution : Fetch::kResolution, d_valid, st);
         default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
     }
 }

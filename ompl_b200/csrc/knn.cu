@@ -298,6 +298,7 @@ struct b200mp_knn {
     std::vector<double> h_pts;      // host mirror (nearestR / list / small paths)
     std::vector<unsigned char> alive;
     Scratch scratch;
+    Scratch qscratch;  // fp64 copies of fp32 query blocks
 };
 
 namespace {
@@ -393,6 +394,7 @@ void b200mp_knn_destroy(b200mp_knn *k) {
     if (k->d_pts) cudaFree(k->d_pts);
     if (k->d_feat) cudaFree(k->d_feat);
     k->scratch.release();
+    k->qscratch.release();
     delete k;
 }
 
@@ -498,6 +500,22 @@ int b200mp_knn_query_device(b200mp_knn *k, const double *d_q, int64_t nq, int kq
         k->ctx->launches.fetch_add(1);
     }
     return B200MP_OK;
+}
+
+int b200mp_knn_query_device_f32(b200mp_knn *k, const float *d_q, int64_t nq, int kq, int64_t self_base, int exclude_self, int64_t *d_idx,
+                                double *d_dist, int *d_counts, void *stream) {
+    if (!k || nq < 0 || (nq > 0 && !d_q)) return fail(B200MP_ERR_INVALID, "b200mp_knn_query_device_f32: bad argument");
+    if (nq == 0) return B200MP_OK;
+    B200_CUDA(cudaSetDevice(k->ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : k->ctx->stream;
+    const long long cnt = static_cast<long long>(nq) * k->dim;
+    int rc = k->qscratch.reserve(static_cast<size_t>(cnt) * sizeof(double));
+    if (rc) return rc;
+    double *d_q64 = reinterpret_cast<double *>(k->qscratch.ptr);
+    knn_f32_to_f64_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(d_q, cnt, d_q64);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    return b200mp_knn_query_device(k, d_q64, nq, kq, nullptr, self_base, exclude_self, d_idx, d_dist, d_counts, st);
 }
 
 int b200mp_knn_query(b200mp_knn *k, const double *q, int64_t nq, int kq, const int64_t *self_ids, int64_t *idx, double *dist, int *counts) {

@@ -498,8 +498,8 @@ __device__ __forceinline__ float vamp_l2_norm(const float (&v)[DIM]) {
 // One warp per motion; motions are taken from a global queue (edge cost varies by 100x with early exit).
 template <class R, bool MASKED>
 __global__ void __launch_bounds__(kBlockThreads, 2)
-validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float *__restrict__ q1, long long m, int resolution,
-                        uint8_t *__restrict__ valid, LaunchCounters *cnt) {
+validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float *__restrict__ q1, const int2 *__restrict__ pairs,
+                        long long m, int resolution, uint8_t *__restrict__ valid, LaunchCounters *cnt) {
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long bar;
     stage_scene(smem, sd.blob, sd.blob_floats, &bar);
@@ -516,10 +516,17 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
         if (e >= static_cast<unsigned long long>(m)) break;
 
         float a[D], v[D], q[D], back[D];
+        // roadmap edges address their end points in one state table (pairs != nullptr: q0 == q1 == the table)
+        unsigned long long ia = e, ib = e;
+        if (pairs != nullptr) {
+            const int2 pr = __ldg(pairs + e);
+            ia = static_cast<unsigned long long>(pr.x);
+            ib = static_cast<unsigned long long>(pr.y);
+        }
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            a[j] = __ldg(q0 + e * D + j);
-            v[j] = __ldg(q1 + e * D + j) - a[j];
+            a[j] = __ldg(q0 + ia * D + j);
+            v[j] = __ldg(q1 + ib * D + j) - a[j];
         }
         const float dist = vamp_l2_norm<D>(v);
         // n = max(ceil(dist / rake * resolution), 1)  (planning/validate.hh:41)

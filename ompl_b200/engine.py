@@ -15,6 +15,16 @@ _vp = C.c_void_p
 _i64 = C.c_int64
 
 
+class RoadmapStats(C.Structure):
+    """b200mp_roadmap_stats (include/b200mp.h)."""
+    _fields_ = [("n_states", _i64), ("n_candidates", _i64), ("n_edges", _i64), ("n_valid_edges", _i64),
+                ("ms_sample", C.c_double), ("ms_knn", C.c_double), ("ms_edges", C.c_double), ("ms_validate", C.c_double),
+                ("ms_total", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class B200MPError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"b200mp error {code}: {msg}")
@@ -47,6 +57,11 @@ def load_library():
     L.b200mp_env_add_cuboids.argtypes = [_vp, _vp, C.c_int, C.c_int]
     L.b200mp_env_add_capsules.argtypes = [_vp, _vp, C.c_int, C.c_int]
     L.b200mp_env_add_capt.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, C.c_float, C.c_float, C.c_float]
+    L.b200mp_env_add_pointcloud.argtypes = [_vp, _vp, _i64, C.c_float, C.c_float, C.c_float]
+    L.b200mp_capt_build.argtypes = [_vp, _i64, C.c_float, C.c_float, C.c_float, C.POINTER(_vp)]
+    L.b200mp_capt_destroy.argtypes = [_vp]
+    L.b200mp_capt_sizes.argtypes = [_vp, _vp]
+    L.b200mp_capt_export.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
     L.b200mp_env_sort.argtypes = [_vp]
     L.b200mp_env_commit.argtypes = [_vp]
     L.b200mp_env_min_distances.argtypes = [_vp, C.c_int, _vp]
@@ -57,6 +72,12 @@ def load_library():
     L.b200mp_validate_motions_f64.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _vp]
     L.b200mp_validate_states_device.argtypes = [_vp, C.c_int, _vp, _vp, _i64, _vp, _vp]
     L.b200mp_validate_motions_device.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _vp, _vp]
+    L.b200mp_validate_edges_device.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _vp, _vp]
+    L.b200mp_prm_sample_device.argtypes = [_vp, C.c_int, _vp, C.c_uint64, C.c_uint64, _i64, _vp, _i64, C.POINTER(_i64), _vp]
+    L.b200mp_prm_edges_device.argtypes = [_vp, _vp, _vp, _i64, C.c_int, _i64, _i64, _vp, _vp, _i64, C.POINTER(_i64), _vp]
+    L.b200mp_prm_build.argtypes = [_vp, C.c_int, _vp, C.c_uint64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _i64,
+                                   C.POINTER(RoadmapStats)]
+    L.b200mp_knn_query_device_f32.argtypes = [_vp, _vp, _i64, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp]
     L.b200mp_launch_count.argtypes = [_vp]
     L.b200mp_launch_count.restype = _i64
     L.b200mp_fp32_peak.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
@@ -87,6 +108,29 @@ def robot_info(robot: str) -> dict:
     hi = np.zeros(16, np.float32)
     _check(L.b200mp_robot_info(ROBOTS[robot], d, ns, res, lo.ctypes.data, hi.ctypes.data))
     return dict(dim=d.value, n_spheres=ns.value, resolution=res.value, lo=lo[:d.value].copy(), hi=hi[:d.value].copy())
+
+
+def capt_build(xyz, r_min: float, r_max: float, r_point: float) -> dict:
+    """Host build of the point-cloud tree (b200mp_capt_build); returns the flat arrays in the layout of
+    b200mp_env_add_capt. Needs no GPU."""
+    L = load_library()
+    pts = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    h = _vp()
+    _check(L.b200mp_capt_build(pts.ctypes.data, pts.shape[0], r_min, r_max, r_point, C.byref(h)))
+    try:
+        sizes = np.zeros(4, np.int64)
+        _check(L.b200mp_capt_sizes(h, sizes.ctypes.data))
+        nlog2, nt, nl, na = (int(v) for v in sizes)
+        tests = np.zeros(nt, np.float32)
+        aabbs = np.zeros((nl, 6), np.float32)
+        starts = np.zeros(nl + 1, np.uint32)
+        aff = np.zeros((3, na * 8), np.float32)
+        top = np.zeros(6, np.float32)
+        _check(L.b200mp_capt_export(h, tests.ctypes.data, aabbs.ctypes.data, starts.ctypes.data, aff.ctypes.data, top.ctypes.data))
+    finally:
+        L.b200mp_capt_destroy(h)
+    return dict(nlog2=nlog2, tests=tests, aabbs=aabbs, aff_starts=starts, aff=aff, top=top, r_min=r_min, r_max=r_max,
+                r_point=r_point)
 
 
 def _host(a, dtype):
@@ -172,6 +216,43 @@ class Context:
             _check(self._L.b200mp_validate_states(self._h, ROBOTS[robot], env._h, q_ptr, m, valid_ptr))
 
 
+    def validate_edges_ptr(self, robot: str, env: "Environment", states_ptr: int, edges_ptr: int, m: int, valid_ptr: int,
+                           resolution: int = 0, stream: int = 0):
+        """Motions given as int32 index pairs into one device-resident state table (b200mp_validate_edges_device)."""
+        _check(self._L.b200mp_validate_edges_device(self._h, ROBOTS[robot], env._h, states_ptr, edges_ptr, m, resolution, valid_ptr,
+                                                    stream or None))
+
+    # ---- roadmap phases (device pointers; see ompl_b200/roadmap.py for the multi-GPU composition) ----
+    def prm_sample_ptr(self, robot: str, env: "Environment", seed: int, cand_first: int, cand_count: int, states_ptr: int,
+                       capacity: int, stream: int = 0) -> int:
+        n = _i64()
+        _check(self._L.b200mp_prm_sample_device(self._h, ROBOTS[robot], env._h, seed, cand_first, cand_count, states_ptr, capacity,
+                                                C.byref(n), stream or None))
+        return int(n.value)
+
+    def prm_edges_ptr(self, nbr_ptr: int, dist_local_ptr: int, n: int, k: int, q_first: int, q_count: int, edges_ptr: int,
+                      weights_ptr: int, capacity: int, stream: int = 0) -> int:
+        ne = _i64()
+        _check(self._L.b200mp_prm_edges_device(self._h, nbr_ptr, dist_local_ptr or None, n, k, q_first, q_count, edges_ptr,
+                                               weights_ptr or None, capacity, C.byref(ne), stream or None))
+        return int(ne.value)
+
+    def prm_build(self, robot: str, env: "Environment", n: int, k: int, seed: int, resolution: int = 0, want_weights: bool = True):
+        """Single-GPU roadmap (b200mp_prm_build) -> dict(states f32[n][dim], edges i32[E][2], valid u8[E], weights f64[E], stats)."""
+        dim = robot_info(robot)["dim"]
+        cap = n * k
+        states = np.empty((n, dim), np.float32)
+        edges = np.empty((cap, 2), np.int32)
+        valid = np.empty(cap, np.uint8)
+        weights = np.empty(cap, np.float64) if want_weights else None
+        st = RoadmapStats()
+        _check(self._L.b200mp_prm_build(self._h, ROBOTS[robot], env._h, seed, n, k, resolution, states.ctypes.data, edges.ctypes.data,
+                                        valid.ctypes.data, weights.ctypes.data if want_weights else None, cap, C.byref(st)))
+        e = int(st.n_edges)
+        return dict(states=states, edges=edges[:e].copy(), valid=valid[:e].copy(),
+                    weights=weights[:e].copy() if want_weights else None, stats=st.as_dict())
+
+
 class Environment:
     """Mirror of vamp::collision::Environment<float> (collision/environment.hh:14-85): shape lists per class,
     `sort()` by min_distance, then `commit()` uploads the scene to the GPU."""
@@ -215,6 +296,11 @@ class Environment:
         _check(self._L.b200mp_env_add_capt(self._h, int(t["nlog2"]), tests.ctypes.data, aabbs.ctypes.data, starts.ctypes.data,
                                            aff.ctypes.data, aff.shape[1] // 8, top.ctypes.data, t["r_min"], t["r_max"],
                                            t["r_point"]))
+
+    def add_pointcloud(self, xyz, r_min: float, r_max: float, r_point: float):
+        """vamp::collision::CAPT(points, r_min, r_max, r_point), built on the host by the engine."""
+        a = _host(xyz, np.float32).reshape(-1, 3)
+        _check(self._L.b200mp_env_add_pointcloud(self._h, a.ctypes.data, a.shape[0], r_min, r_max, r_point))
 
     def sort(self):
         _check(self._L.b200mp_env_sort(self._h))
@@ -301,6 +387,11 @@ class NearestNeighbors:
         cnt = _i64()
         _check(self._L.b200mp_knn_radius(self._h, q.ctypes.data, radius, idx.ctypes.data, dist.ctypes.data, cap, C.byref(cnt)))
         return idx[:cnt.value].copy(), dist[:cnt.value].copy()
+
+    def query_device_f32(self, q_ptr: int, nq: int, k: int, idx_ptr: int, dist_ptr: int, self_base: int = 0,
+                         exclude_self: bool = False, counts_ptr: int = 0, stream: int = 0):
+        _check(self._L.b200mp_knn_query_device_f32(self._h, q_ptr, nq, k, self_base, int(exclude_self), idx_ptr, dist_ptr,
+                                                   counts_ptr or None, stream or None))
 
     def query_device(self, q_ptr: int, nq: int, k: int, idx_ptr: int, dist_ptr: int, self_base: int = 0, exclude_self: bool = False,
                      self_ids_ptr: int = 0, counts_ptr: int = 0, stream: int = 0):

@@ -1,0 +1,188 @@
+"""Batched PRM roadmap builder, sharded over the GPUs of one node (one process per GPU).
+
+Replaces the per-milestone loop of ompl::geometric::PRM (src/ompl/geometric/planners/prm/src/PRM.cpp:240-270,570-604)
+by whole-batch phases (ompl_b200/csrc/roadmap.cu). Rank g of G owns the query block [g*B, (g+1)*B), B = ceil(n / G),
+and the edges its queries keep; the exchange steps are the ones SURVEY.md 8(e) lists:
+
+  1. sample     every rank validates a contiguous slice of the candidate stream; all-gather of the per-rank counts and
+                of the valid states (padded to the largest count) -> every rank holds all n states, in stream order.
+                The states are the first n valid candidates of the stream, independent of G.
+  2. kNN        each rank searches the full set for its own block (self excluded)
+  3. all-gather of the neighbour table (the de-duplication rule needs the lists of remote states)
+  4. edges      each rank keeps (i, j) for its i when i < j or i is not in kNN(j); validates them
+  5. all-gather of counts, edges, weights and validity -> every rank holds the whole roadmap, same order for any G
+
+All compute goes through the C ABI of the CUDA engine (`EngineBackend`); torch is used for device buffers and the NCCL
+collectives only. Any object with the four phase methods can stand in for the backend (the CPU gloo tests use a
+checker-backed one); there is no CPU fallback in this package.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import Context, Environment, NearestNeighbors, robot_info
+
+
+@dataclass
+class Roadmap:
+    states: torch.Tensor    # [n][dim] float32
+    edges: torch.Tensor     # [E][2] int32, (older milestone, newer milestone)
+    valid: torch.Tensor     # [E] uint8
+    weights: torch.Tensor   # [E] float64 = edge length (PRM's motionCost for path-length objectives)
+    stats: dict = field(default_factory=dict)
+
+    def to_planner_data(self):
+        """Vertices and valid edges in the form ompl::base::PlannerData takes (addVertex / addEdge with weight), ready for
+        ompl::geometric::PRM(const PlannerData &) (PRM.cpp:96-156)."""
+        keep = self.valid.bool()
+        return dict(vertices=self.states.double().cpu().numpy(), edges=self.edges[keep].cpu().numpy(),
+                    weights=self.weights[keep].cpu().numpy())
+
+
+class EngineBackend:
+    """The four roadmap phases on one GPU through the C ABI."""
+
+    def __init__(self, ctx: Context, env: Environment, robot: str):
+        self.ctx, self.env, self.robot = ctx, env, robot
+        self.dim = robot_info(robot)["dim"]
+        self.device = torch.device("cuda", ctx.device)
+        info = robot_info(robot)
+        self.max_norm = float(np.linalg.norm(np.maximum(np.abs(info["lo"]), np.abs(info["hi"])).astype(np.float64)))
+        self._knn = None
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def sample(self, seed: int, first: int, count: int, out: torch.Tensor) -> int:
+        return self.ctx.prm_sample_ptr(self.robot, self.env, seed, first, count, out.data_ptr(), out.shape[0], self._stream())
+
+    def neighbors(self, states: torch.Tensor, q_first: int, q_count: int, k: int):
+        if self._knn is not None:
+            self._knn.close()
+        self._knn = NearestNeighbors(self.ctx, self.dim)
+        self._knn.add_device_f32(states.data_ptr(), states.shape[0], self.max_norm, self._stream())
+        idx = torch.full((q_count, k), -1, dtype=torch.int64, device=self.device)
+        dst = torch.full((q_count, k), float("inf"), dtype=torch.float64, device=self.device)
+        if q_count:
+            self._knn.query_device_f32(states[q_first:].data_ptr(), q_count, k, idx.data_ptr(), dst.data_ptr(), self_base=q_first,
+                                       exclude_self=True, stream=self._stream())
+        return idx, dst
+
+    def edges(self, nbr: torch.Tensor, dist_local: torch.Tensor, q_first: int, q_count: int):
+        n, k = nbr.shape
+        cap = max(q_count * k, 1)
+        e = torch.empty((cap, 2), dtype=torch.int32, device=self.device)
+        w = torch.empty(cap, dtype=torch.float64, device=self.device)
+        ne = self.ctx.prm_edges_ptr(nbr.data_ptr(), dist_local.data_ptr(), n, k, q_first, q_count, e.data_ptr(), w.data_ptr(), cap,
+                                    self._stream())
+        return e[:ne], w[:ne]
+
+    def validate_edges(self, states: torch.Tensor, edges: torch.Tensor, resolution: int) -> torch.Tensor:
+        v = torch.empty(edges.shape[0], dtype=torch.uint8, device=self.device)
+        if edges.shape[0]:
+            self.ctx.validate_edges_ptr(self.robot, self.env, states.data_ptr(), edges.data_ptr(), edges.shape[0], v.data_ptr(),
+                                        resolution, self._stream())
+        return v
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def _all_gather_ragged(local: torch.Tensor, group, world: int):
+    """Concatenate per-rank tensors of different leading sizes, in rank order (counts all-gather + padded all-gather)."""
+    if world == 1:
+        return local
+    cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    cnts = torch.empty(world, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(cnts, cnt, group=group)
+    cnts = cnts.tolist()
+    m = max(max(cnts), 1)
+    pad = torch.zeros((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((world * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * m:r * m + c] for r, c in enumerate(cnts)], dim=0)
+
+
+class RoadmapBuilder:
+    def __init__(self, backend, group=None):
+        self.backend = backend
+        self.group = group
+        self.rank, self.world = _world(group)
+
+    def _sync(self):
+        if self.backend.device.type == "cuda":
+            torch.cuda.synchronize(self.backend.device)
+
+    def build(self, n: int, k: int, seed: int, resolution: int = 0, candidates_per_round: int | None = None) -> Roadmap:
+        be, G, g = self.backend, self.world, self.rank
+        dev, dim = be.device, be.dim
+        t = [time.perf_counter()]
+
+        def mark():
+            self._sync()
+            t.append(time.perf_counter())
+
+        # ---- 1. sample: rounds over the candidate stream, contiguous slice per rank, until n valid states exist
+        states = torch.empty((n, dim), dtype=torch.float32, device=dev)
+        have, drawn, rounds = 0, 0, 0
+        per_round = candidates_per_round or max(n, 1 << 16)
+        while have < n:
+            rounds += 1
+            if rounds > 4096:
+                raise RuntimeError(f"no valid states after {drawn} candidates")
+            per_rank = -(-per_round // G)
+            buf = torch.empty((per_rank, dim), dtype=torch.float32, device=dev)
+            got = be.sample(seed, drawn + g * per_rank, per_rank, buf)
+            block = _all_gather_ragged(buf[:got], self.group, G)
+            take = min(block.shape[0], n - have)
+            states[have:have + take] = block[:take]
+            have += take
+            drawn += per_rank * G
+            if have < n:
+                rate = max(1e-4, have / drawn)
+                per_round = max(1 << 16, int(1.05 * (n - have) / rate))
+        mark()
+        # ---- 2. kNN of the local query block against all states
+        B = -(-n // G)
+        q_first = min(g * B, n)
+        q_count = min(B, n - q_first)
+        kk = min(k, n - 1)
+        if kk < 1:
+            empty = torch.empty((0, 2), dtype=torch.int32, device=dev)
+            return Roadmap(states, empty, torch.empty(0, dtype=torch.uint8, device=dev), torch.empty(0, dtype=torch.float64, device=dev),
+                           dict(n_states=n, n_candidates=drawn, n_edges=0, n_valid_edges=0, world=G))
+        idx, dst = be.neighbors(states, q_first, q_count, kk)
+        mark()
+        # ---- 3. neighbour table of every state (padded block all-gather)
+        if G > 1:
+            pad = torch.full((B, kk), -1, dtype=torch.int64, device=dev)
+            pad[:q_count] = idx
+            nbr = torch.empty((G * B, kk), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(nbr, pad, group=self.group)
+            nbr = nbr[:n].contiguous()
+        else:
+            nbr = idx
+        # ---- 4. local edge list and its validity
+        e_loc, w_loc = be.edges(nbr, dst, q_first, q_count)
+        mark()
+        v_loc = be.validate_edges(states, e_loc, resolution)
+        mark()
+        # ---- 5. whole roadmap on every rank
+        edges = _all_gather_ragged(e_loc, self.group, G)
+        weights = _all_gather_ragged(w_loc, self.group, G)
+        valid = _all_gather_ragged(v_loc, self.group, G)
+        mark()
+        ms = [(b - a) * 1e3 for a, b in zip(t[:-1], t[1:])]
+        stats = dict(n_states=n, n_candidates=drawn, n_edges=int(edges.shape[0]), n_valid_edges=int(valid.sum().item()), world=G,
+                     sample_rounds=rounds, ms_sample=ms[0], ms_knn=ms[1], ms_edges=ms[2], ms_validate=ms[3], ms_gather=ms[4],
+                     ms_total=sum(ms), local_edges=int(e_loc.shape[0]))
+        return Roadmap(states, edges, valid, weights, stats)

@@ -152,3 +152,37 @@ def local_edges(robot: str, starts: np.ndarray, seed: int, len_lo: float = 0.05,
     ln = rng.uniform(len_lo, len_hi, (m, 1))
     q1 = np.clip(starts + v * ln, lo, hi).astype(np.float32)
     return starts.astype(np.float32), q1
+
+
+def shelf_boxes(robot: str = "fetch"):
+    """Bookshelf-style scene (after the MotionBenchMaker `bookshelf_tall` problems): two side panels, a back panel and
+    four shelves in front of the robot. Returns [(centre, half extents)] of axis-aligned boxes."""
+    x0, w, z0 = (0.95, 0.45, 0.35) if robot == "fetch" else (0.62, 0.40, 0.05)
+    depth, height, t = 0.18, 1.2, 0.015
+    boxes = [((x0, -w, z0 + height / 2), (depth, t, height / 2)), ((x0, w, z0 + height / 2), (depth, t, height / 2)),
+             ((x0 + depth, 0.0, z0 + height / 2), (t, w, height / 2))]
+    for i in range(4):
+        boxes.append(((x0, 0.0, z0 + 0.05 + i * (height - 0.1) / 3), (depth, w, t)))
+    return [(np.array(c, np.float64), np.array(h, np.float64)) for c, h in boxes]
+
+
+def shelf_cloud(n: int, seed: int = 7, robot: str = "fetch") -> np.ndarray:
+    """n points sampled uniformly (area weighted) on the surfaces of shelf_boxes(robot), float32 [n][3]."""
+    rng = np.random.default_rng(seed)
+    faces = []  # (centre, half, fixed axis, sign)
+    for c, h in shelf_boxes(robot):
+        for ax in range(3):
+            o = [a for a in range(3) if a != ax]
+            area = 4 * h[o[0]] * h[o[1]]
+            for sg in (-1.0, 1.0):
+                faces.append((c, h, ax, sg, area))
+    areas = np.array([f[4] for f in faces])
+    which = rng.choice(len(faces), size=n, p=areas / areas.sum())
+    u = rng.uniform(-1, 1, (n, 3))
+    pts = np.empty((n, 3))
+    for i, f in enumerate(which):
+        c, h, ax, sg, _ = faces[f]
+        p = c + u[i] * h
+        p[ax] = c[ax] + sg * h[ax]
+        pts[i] = p
+    return pts.astype(np.float32)

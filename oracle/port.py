@@ -172,3 +172,57 @@ def knn_radius(db, q, radius, metric=0, param=0.0):
     dist = np.zeros(db.shape[0], np.float64)
     n = lib().or_knn_radius(db, db.shape[0], q, db.shape[1], radius, metric, param, idx, dist, db.shape[0])
     return idx[:n], dist[:n]
+
+
+# ---------------------------------------------------------------------------------------------- roadmap sampler
+def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
+    """Philox4x32-10 (Salmon et al., SC'11; the Random123 reference algorithm). ctr [n][4], key [2] uint32 -> [n][4]."""
+    c = ctr.astype(np.uint64).copy()
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = m0 * c[:, 0]
+        p1 = m1 * c[:, 2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[:, 1] ^ k0, lo1, hi0 ^ c[:, 3] ^ k1, lo0], axis=1)
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c.astype(np.uint32)
+
+
+def prm_candidates(robot: str, seed: int, first: int, count: int) -> np.ndarray:
+    """Candidate states first .. first+count-1 of the roadmap sample stream (ompl_b200/csrc/roadmap.cu prm_sample_kernel):
+    q_j = fma(u_j, hi_j - lo_j, lo_j), u_j = (Philox word j >> 8) * 2^-24, counter = (c_lo, c_hi, j // 4, 0), key = seed."""
+    lo, hi = bounds(robot)
+    dim = len(lo)
+    c = np.arange(first, first + count, dtype=np.uint64)
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+    words = []
+    for sub in range(2):
+        ctr = np.stack([c & np.uint64(0xFFFFFFFF), c >> np.uint64(32), np.full(count, sub, np.uint64), np.zeros(count, np.uint64)], axis=1)
+        words.append(philox4x32_10(ctr, key))
+    w = np.concatenate(words, axis=1)[:, :dim]
+    u = (w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    span = (hi - lo).astype(np.float32)
+    # single-rounding fma: exact product and sum in float64 (24-bit x 24-bit products are exact), rounded once to float32
+    return (u.astype(np.float64) * span.astype(np.float64) + lo.astype(np.float64)).astype(np.float32)
+
+
+def prm_edge_list(nbr: np.ndarray, dist: np.ndarray, q_first: int = 0, q_count: int | None = None):
+    """Edge list rule of the batched builder: for query i (in order) and slot s, j = nbr[i][s] is kept when i < j or i is not in
+    nbr[j]; stored (min, max). Returns (edges int32 [E][2], weights [E])."""
+    n, k = nbr.shape
+    q_count = n - q_first if q_count is None else q_count
+    e, w = [], []
+    for i in range(q_first, q_first + q_count):
+        for s in range(k):
+            j = int(nbr[i, s])
+            if j < 0 or j == i:
+                continue
+            if j < i and i in nbr[j]:
+                continue
+            e.append((min(i, j), max(i, j)))
+            w.append(dist[i - q_first, s])
+    return np.array(e, np.int32).reshape(-1, 2), np.array(w, np.float64)

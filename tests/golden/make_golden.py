@@ -53,7 +53,32 @@ def validation_case(name, robot, scene, sort, n_states, n_motions, seed, len_hi=
     print(f"{name}: states valid {sv.mean():.3f}, motions valid {mv.mean():.3f}")
 
 
+def cloud_case(name, robot, radii, n_pts, scene, n_states, n_motions, seed):
+    """Point cloud (the reference builds its own CAPT from the raw points) + primitives."""
+    pts = synth.shelf_cloud(n_pts, seed=seed, robot=robot)
+    env = refvamp.RefEnvironment()
+    env.add_pointcloud(pts, *radii)
+    synth.fill_env(env, scene)
+    q = synth.uniform_states(robot, n_states, seed)
+    sv = env.validate_states(robot, q)
+    starts = np.resize(q[sv == 1], (n_motions, q.shape[1]))
+    q0, q1 = synth.local_edges(robot, starts, seed + 1, 0.05, 2.0)
+    mv = env.validate_motions(robot, q0, q1)
+    t = env.capt_export()
+    out = dict(robot=np.array(robot), points=pts, radii=np.array(radii, np.float32), states=q, states_valid=sv, q0=q0, q1=q1,
+               motions_valid=mv, capt_nlog2=np.array(t["nlog2"]), capt_tests=t["tests"], capt_aff_starts=t["aff_starts"],
+               capt_top=t["top"], capt_aabbs=t["aabbs"], capt_aff_sum=np.where(np.isfinite(t["aff"]), t["aff"], 0).sum(axis=1, dtype=np.float64))
+    for k, v in scene.items():
+        out["scene_" + k] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: states valid {sv.mean():.3f}, motions valid {mv.mean():.3f}, affordance records {t['aff'].shape[1] // 8}")
+
+
 def main():
+    if "--cloud" in sys.argv:
+        cloud_case("fetch_cloud", "fetch", (0.012, 0.24, 0.0025), 1500,
+                   synth.clutter_scene(11, 20, 20, rho_lo=0.6, rho_hi=1.4, z_lo=0.2, z_hi=1.6), 1500, 800, 505)
+        return
     validation_case("panda_cage", "panda", synth.cage_scene(), True, 3000, 1500, 101)
     validation_case("panda_clutter", "panda",
                     synth.clutter_scene(7, 120, 120, n_capsules=40, n_zcuboids=40, n_zcapsules=40), True, 3000, 1500, 202)

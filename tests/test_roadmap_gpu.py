@@ -1,0 +1,104 @@
+"""GPU parity tests of the batched PRM roadmap builder (ompl_b200/csrc/roadmap.cu, ompl_b200/roadmap.py) against the
+CPU checker: same sample stream, identical kNN index sets, the same edge list, edge validity bit-exact outside the
+1e-5 m clearance band."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ompl_b200
+from ompl_b200 import synth
+from ompl_b200.roadmap import EngineBackend, RoadmapBuilder
+from oracle import port
+from tests.checker_backend import CheckerBackend
+from tests.util import assert_validity_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(name):
+    return synth.cage_scene() if name == "cage" else synth.clutter_scene(1234, 500, 500)
+
+
+@pytest.mark.parametrize("scene,n,k,seed", [("cage", 3000, 8, 1), ("c2", 1500, 16, 42), ("cage", 5, 16, 3)])
+def test_prm_build_matches_checker(ctx, scene, n, k, seed):
+    sc = _scene(scene)
+    env = synth.fill_env(ompl_b200.Environment(ctx), sc)
+    pe = synth.fill_env(port.PortEnvironment(), sc)
+    got = ctx.prm_build("panda", env, n, k, seed)
+    want = RoadmapBuilder(CheckerBackend(pe, "panda", nthreads=8)).build(n, k, seed)
+    np.testing.assert_array_equal(got["states"], want.states.numpy())      # same Philox stream, same validity decisions
+    np.testing.assert_array_equal(got["edges"], want.edges.numpy())         # identical kNN sets -> identical edge list
+    np.testing.assert_array_equal(got["weights"], want.weights.numpy())     # fp64 distances bit-identical
+    s, e = got["states"], got["edges"]
+    assert_validity_parity(got["valid"], want.valid.numpy(), lambda b: pe.edge_min_clearance("panda", s[e[b, 0]], s[e[b, 1]]), "roadmap edges")
+    st = got["stats"]
+    assert st["n_states"] == n and st["n_edges"] == len(e) and st["n_valid_edges"] == int(got["valid"].sum())
+    assert st["n_candidates"] >= n
+
+
+def test_builder_with_engine_backend_equals_prm_build(ctx):
+    sc = _scene("cage")
+    env = synth.fill_env(ompl_b200.Environment(ctx), sc)
+    a = ctx.prm_build("panda", env, 20000, 16, 9)
+    rm = RoadmapBuilder(EngineBackend(ctx, env, "panda")).build(20000, 16, 9, candidates_per_round=30000)
+    np.testing.assert_array_equal(a["states"], rm.states.cpu().numpy())
+    np.testing.assert_array_equal(a["edges"], rm.edges.cpu().numpy())
+    np.testing.assert_array_equal(a["valid"], rm.valid.cpu().numpy())
+    np.testing.assert_array_equal(a["weights"], rm.weights.cpu().numpy())
+    pd = rm.to_planner_data()
+    assert pd["vertices"].shape == (20000, 7) and len(pd["edges"]) == int(a["valid"].sum())
+
+
+def test_roadmap_properties_at_scale(ctx):
+    """Size-independent properties at 2^17 states (the full 2^20 build runs in bench.py): every state valid, every vertex
+    has <= k kept + incoming edges consistent with the rule, no duplicate edges, weights = end-point distance."""
+    env = synth.fill_env(ompl_b200.Environment(ctx), _scene("c2"))
+    n, k = 1 << 17, 16
+    r = ctx.prm_build("panda", env, n, k, 42)
+    s, e, w = r["states"], r["edges"], r["weights"]
+    assert (ctx.validate_states("panda", env, s) == 1).all()
+    assert (e[:, 0] < e[:, 1]).all() and e.max() < n
+    key = e[:, 0].astype(np.int64) * n + e[:, 1]
+    assert len(np.unique(key)) == len(key)
+    assert n * k / 2 <= len(e) <= n * k
+    d = np.sqrt(((s[e[:, 0]].astype(np.float64) - s[e[:, 1]].astype(np.float64)) ** 2).sum(axis=1))
+    np.testing.assert_allclose(w, d, rtol=1e-12)
+    # edge validity is what the motion entry point says for the same end points
+    sub = np.random.default_rng(0).choice(len(e), 50000, replace=False)
+    np.testing.assert_array_equal(r["valid"][sub], ctx.validate_motions("panda", env, s[e[sub, 0]], s[e[sub, 1]]))
+
+
+def _nccl_worker(rank, world, port_no, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    c = ompl_b200.Context(rank)
+    env = synth.fill_env(ompl_b200.Environment(c), synth.cage_scene())
+    rm = RoadmapBuilder(EngineBackend(c, env, "panda")).build(30001, 16, 9)
+    q.put((rank, rm.states.cpu().numpy(), rm.edges.cpu().numpy(), rm.valid.cpu().numpy(), rm.weights.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_nccl_roadmap_equals_single_gpu(ctx):
+    import torch.multiprocessing as mp
+    env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
+    one = ctx.prm_build("panda", env, 30001, 16, 9)
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_nccl_worker, args=(r, 2, 29611, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for o in outs:
+        np.testing.assert_array_equal(o[1], one["states"])
+        np.testing.assert_array_equal(o[2], one["edges"])
+        np.testing.assert_array_equal(o[3], one["valid"])
+        np.testing.assert_array_equal(o[4], one["weights"])
