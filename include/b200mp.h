@@ -94,6 +94,10 @@ int b200mp_capt_export(const b200mp_capt *capt, float *tests, float *aabbs, uint
 /* Sort every shape list by min_distance (Environment::sort). Obstacles are otherwise tested in insertion
  * order with the reference's ordered-scan-with-break semantics. */
 int b200mp_env_sort(b200mp_env *env);
+/* Sorted scenes with >= 32 obstacles are indexed at commit by a uniform grid of candidate lists so a robot sphere is
+ * tested against the few obstacles near it instead of the whole list (same decisions; see GridView in
+ * ompl_b200/csrc/validate.cuh). enable = 0 keeps the plain ordered scan (A/B measurements, tests). Default: enabled. */
+int b200mp_env_set_grid(b200mp_env *env, int enable);
 /* Upload to the GPU. Must be called after the last add/sort and before validation. */
 int b200mp_env_commit(b200mp_env *env);
 /* kind: 0 spheres, 1 capsules, 2 z-capsules, 3 cuboids, 4 z-cuboids. out may be NULL. */

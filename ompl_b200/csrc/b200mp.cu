@@ -57,9 +57,160 @@ struct b200mp_env {
     std::vector<HCuboid> cuboids, zcuboids;
     std::vector<DeviceCapt> pcs;
     float *d_blob = nullptr;
+    void *d_grid = nullptr;
+    bool use_grid = true;
     SceneDesc desc{};
     bool committed = false;
 };
+
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+};
+
+// axis-aligned bounds of every obstacle, per class, in record order
+void obstacle_boxes(const b200mp_env *e, std::vector<Box> (&boxes)[kShapeClasses], bool *regular) {
+    *regular = true;
+    for (const auto &s : e->spheres) boxes[0].push_back({{s.x - s.r, s.y - s.r, s.z - s.r}, {s.x + s.r, s.y + s.r, s.z + s.r}});
+    auto capsule = [](const HCapsule &c) {
+        Box b;
+        const float p[3] = {c.x1, c.y1, c.z1}, v[3] = {c.xv, c.yv, c.zv};
+        for (int k = 0; k < 3; ++k) {
+            b.lo[k] = std::min(p[k], p[k] + v[k]) - c.r;
+            b.hi[k] = std::max(p[k], p[k] + v[k]) + c.r;
+        }
+        return b;
+    };
+    for (const auto &c : e->capsules) boxes[1].push_back(capsule(c));
+    for (auto c : e->zcapsules) {
+        c.xv = c.yv = 0.f;  // the z-aligned test only uses zv
+        boxes[2].push_back(capsule(c));
+    }
+    auto unit = [](const float *a) { return std::fabs(dot3(a[0], a[1], a[2], a[0], a[1], a[2]) - 1.f) < 1e-3f; };
+    auto ortho = [](const float *a, const float *b) { return std::fabs(dot3(a[0], a[1], a[2], b[0], b[1], b[2])) < 1e-3f; };
+    for (const auto &c : e->cuboids) {
+        if (!unit(c.a1) || !unit(c.a2) || !unit(c.a3) || !ortho(c.a1, c.a2) || !ortho(c.a1, c.a3) || !ortho(c.a2, c.a3)) *regular = false;
+        Box b;
+        for (int k = 0; k < 3; ++k) {
+            const float ext = std::fabs(c.a1[k]) * c.h[0] + std::fabs(c.a2[k]) * c.h[1] + std::fabs(c.a3[k]) * c.h[2];
+            b.lo[k] = c.c[k] - ext;
+            b.hi[k] = c.c[k] + ext;
+        }
+        boxes[3].push_back(b);
+    }
+    for (const auto &c : e->zcuboids) {
+        // the z-aligned test uses a1.xy, a2.xy and the world z axis
+        const float n1 = c.a1[0] * c.a1[0] + c.a1[1] * c.a1[1], n2 = c.a2[0] * c.a2[0] + c.a2[1] * c.a2[1];
+        if (std::fabs(n1 - 1.f) > 1e-3f || std::fabs(n2 - 1.f) > 1e-3f || std::fabs(c.a1[0] * c.a2[0] + c.a1[1] * c.a2[1]) > 1e-3f) *regular = false;
+        Box b;
+        for (int k = 0; k < 2; ++k) {
+            const float ext = std::fabs(c.a1[k]) * c.h[0] + std::fabs(c.a2[k]) * c.h[1];
+            b.lo[k] = c.c[k] - ext;
+            b.hi[k] = c.c[k] + ext;
+        }
+        b.lo[2] = c.c[2] - c.h[2];
+        b.hi[2] = c.c[2] + c.h[2];
+        boxes[4].push_back(b);
+    }
+}
+
+// Candidate grids of a sorted scene (see GridView). Returns B200MP_OK with d->n_grid = 0 when no grid is used.
+int build_grids(b200mp_env *e, SceneDesc *d) {
+    d->n_grid = 0;
+    const size_t total = e->spheres.size() + e->capsules.size() + e->zcapsules.size() + e->cuboids.size() + e->zcuboids.size();
+    if (!e->use_grid || !d->sorted || total < 32) return B200MP_OK;  // short lists: the ordered scan is already cheap
+    std::vector<Box> boxes[kShapeClasses];
+    bool regular = true;
+    obstacle_boxes(e, boxes, &regular);
+    if (!regular) return B200MP_OK;  // a cuboid with non-orthonormal axes has no simple bounding box: keep the full scan
+    for (const auto &cls : boxes)
+        if (cls.size() > 65535) return B200MP_OK;
+    const float reach[kGridLevels] = {0.0625f, 0.18f, 0.36f};
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (const auto &cls : boxes)
+        for (const auto &b : cls)
+            for (int k = 0; k < 3; ++k) {
+                if (!std::isfinite(b.lo[k]) || !std::isfinite(b.hi[k])) return B200MP_OK;
+                lo[k] = std::min(lo[k], b.lo[k]);
+                hi[k] = std::max(hi[k], b.hi[k]);
+            }
+    // cell size: at most ~32k cells, never below 6 cm
+    float h = 0.06f;
+    for (;; h *= 1.15f) {
+        double cells = 1;
+        for (int k = 0; k < 3; ++k) cells *= std::floor((hi[k] - lo[k]) / h) + 1;
+        if (cells <= 32768) break;
+    }
+    int n[3];
+    for (int k = 0; k < 3; ++k) n[k] = static_cast<int>(std::floor((hi[k] - lo[k]) / h)) + 1;
+    const size_t cells = static_cast<size_t>(n[0]) * n[1] * n[2];
+    const float inv_h = 1.0f / h;
+    auto cell_of = [&](float v, int k) {  // the device's grid_cell(), same float operations
+        const int c = static_cast<int>(std::floor((v - lo[k]) * inv_h));
+        return std::min(std::max(c, 0), n[k] - 1);
+    };
+    // layout of the device buffer: for level, class: start[cells + 1] (u32) then ids (u16), 16-byte aligned pieces
+    struct Piece { size_t start_off, ids_off; std::vector<unsigned> start; std::vector<unsigned short> ids; };
+    std::vector<Piece> pieces(kGridLevels * kShapeClasses);
+    size_t bytes = 0;
+    for (int l = 0; l < kGridLevels; ++l)
+        for (int t = 0; t < kShapeClasses; ++t) {
+            Piece &p = pieces[l * kShapeClasses + t];
+            const auto &cls = boxes[t];
+            if (cls.empty()) continue;
+            const float grow = reach[l] * 1.0001f + 1e-4f;  // slack covers rounding in the device-side tests
+            p.start.assign(cells + 1, 0u);
+            std::vector<int> rng(cls.size() * 6);
+            for (size_t i = 0; i < cls.size(); ++i) {
+                for (int k = 0; k < 3; ++k) {
+                    rng[6 * i + k] = cell_of(cls[i].lo[k] - grow, k);
+                    rng[6 * i + 3 + k] = cell_of(cls[i].hi[k] + grow, k);
+                }
+                for (int z = rng[6 * i + 2]; z <= rng[6 * i + 5]; ++z)
+                    for (int y = rng[6 * i + 1]; y <= rng[6 * i + 4]; ++y)
+                        for (int x = rng[6 * i]; x <= rng[6 * i + 3]; ++x) ++p.start[(static_cast<size_t>(z) * n[1] + y) * n[0] + x + 1];
+            }
+            for (size_t c = 0; c < cells; ++c) p.start[c + 1] += p.start[c];
+            p.ids.resize(p.start[cells]);
+            std::vector<unsigned> fill(p.start.begin(), p.start.end() - 1);
+            for (size_t i = 0; i < cls.size(); ++i)  // ascending record index inside every cell
+                for (int z = rng[6 * i + 2]; z <= rng[6 * i + 5]; ++z)
+                    for (int y = rng[6 * i + 1]; y <= rng[6 * i + 4]; ++y)
+                        for (int x = rng[6 * i]; x <= rng[6 * i + 3]; ++x)
+                            p.ids[fill[(static_cast<size_t>(z) * n[1] + y) * n[0] + x]++] = static_cast<unsigned short>(i);
+            p.start_off = bytes;
+            bytes += ((cells + 1) * sizeof(unsigned) + 15) / 16 * 16;
+            p.ids_off = bytes;
+            bytes += (p.ids.size() * sizeof(unsigned short) + 15) / 16 * 16 + 16;
+        }
+    if (bytes > (size_t(512) << 20)) return B200MP_OK;
+    std::vector<unsigned char> host(bytes, 0);
+    for (const auto &p : pieces) {
+        if (p.start.empty()) continue;
+        std::memcpy(host.data() + p.start_off, p.start.data(), p.start.size() * sizeof(unsigned));
+        if (!p.ids.empty()) std::memcpy(host.data() + p.ids_off, p.ids.data(), p.ids.size() * sizeof(unsigned short));
+    }
+    B200_CUDA(cudaMalloc(&e->d_grid, std::max<size_t>(bytes, 16)));
+    B200_CUDA(cudaMemcpy(e->d_grid, host.data(), bytes, cudaMemcpyHostToDevice));
+    const unsigned char *base = static_cast<const unsigned char *>(e->d_grid);
+    for (int l = 0; l < kGridLevels; ++l) {
+        GridView &g = d->grid[l];
+        g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+        g.inv_h = inv_h;
+        g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
+        g.reach = reach[l];
+        for (int t = 0; t < kShapeClasses; ++t) {
+            const Piece &p = pieces[l * kShapeClasses + t];
+            g.start[t] = p.start.empty() ? nullptr : reinterpret_cast<const unsigned *>(base + p.start_off);
+            g.ids[t] = p.start.empty() ? nullptr : reinterpret_cast<const unsigned short *>(base + p.ids_off);
+        }
+    }
+    d->n_grid = kGridLevels;
+    return B200MP_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -151,7 +302,9 @@ int b200mp_env_create(b200mp_ctx *ctx, b200mp_env **out) {
 
 static void env_free_device(b200mp_env *e) {
     if (e->d_blob) cudaFree(e->d_blob);
+    if (e->d_grid) cudaFree(e->d_grid);
     e->d_blob = nullptr;
+    e->d_grid = nullptr;
     e->committed = false;
 }
 
@@ -259,6 +412,13 @@ int b200mp_env_add_capt(b200mp_env *e, int nlog2, const float *tests, const floa
     return B200MP_OK;
 }
 
+int b200mp_env_set_grid(b200mp_env *e, int enable) {
+    if (!e) return fail(B200MP_ERR_INVALID, "b200mp_env_set_grid: env is NULL");
+    e->use_grid = enable != 0;
+    e->committed = false;
+    return B200MP_OK;
+}
+
 int b200mp_env_sort(b200mp_env *e) {
     if (!e) return fail(B200MP_ERR_INVALID, "b200mp_env_sort: env is NULL");
     auto by = [](const auto &a, const auto &b) { return a.min_d < b.min_d; };  // environment.hh:43-69
@@ -311,7 +471,8 @@ int b200mp_env_commit(b200mp_env *e) {
     // every class is padded to a multiple of kObsUnroll records with far-away dummies that can never collide,
     // so the kernels scan whole blocks without a tail
     constexpr float kFar = 1.0e9f;
-    auto pad_count = [](size_t n) { return (kObsUnroll - static_cast<int>(n % kObsUnroll)) % kObsUnroll; };
+    // (at least one per non-empty class: record n is the stand-in the grid-culled scans use for exhausted lists)
+    auto pad_count = [](size_t n) { return n == 0 ? 0 : kObsUnroll - static_cast<int>(n % kObsUnroll); };
     bool sorted = true;
     auto is_sorted = [&](const auto &v) {
         for (size_t i = 1; i < v.size(); ++i) if (v[i].min_d < v[i - 1].min_d) sorted = false;
@@ -360,6 +521,10 @@ int b200mp_env_commit(b200mp_env *e) {
     B200_CUDA(cudaMalloc(&e->d_blob, std::max<size_t>(bytes, 16)));
     if (bytes) B200_CUDA(cudaMemcpy(e->d_blob, blob.data(), bytes, cudaMemcpyHostToDevice));
     d.blob = e->d_blob;
+    {
+        const int grc = build_grids(e, &d);
+        if (grc) return grc;
+    }
     d.n_pc = static_cast<int>(e->pcs.size());
     for (int i = 0; i < d.n_pc; ++i) d.pc[i] = e->pcs[i].view;
     e->desc = d;
@@ -376,7 +541,8 @@ template <class R>
 int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const float *d_q1, const int2 *d_pairs, int64_t m,
                    int resolution, uint8_t *d_valid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4;
-    auto kern = e->desc.sorted ? validate_motions_kernel<R, false> : validate_motions_kernel<R, true>;
+    auto kern = e->desc.n_grid > 0 ? validate_motions_kernel<R, false, true>
+                                   : (e->desc.sorted ? validate_motions_kernel<R, false, false> : validate_motions_kernel<R, true, false>);
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
@@ -395,7 +561,8 @@ int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const 
 template <class R>
 int launch_states(b200mp_ctx *c, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4;
-    auto kern = e->desc.sorted ? validate_states_kernel<R, false> : validate_states_kernel<R, true>;
+    auto kern = e->desc.n_grid > 0 ? validate_states_kernel<R, false, true>
+                                   : (e->desc.sorted ? validate_states_kernel<R, false, false> : validate_states_kernel<R, true, false>);
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));

@@ -35,6 +35,22 @@ struct CaptView {
     int n_tests;
 };
 
+// Uniform grid over the obstacles of a SORTED scene (built at commit, lives in global memory / L2). Level L lists, per
+// cell and shape class, the records a sphere of radius <= reach centred in that cell can possibly touch (every obstacle
+// whose bounding box inflated by reach overlaps the cell; border cells extend to infinity, so any centre maps to a cell
+// that is conservative for it). In a sorted scene the reference's ordered scan stops only at obstacles that cannot
+// touch the sphere (min_distance >= max_extent), so "any listed obstacle has a negative test value" is the same
+// decision as the full scan, found with a few dozen tests instead of a thousand.
+constexpr int kGridLevels = 3;
+constexpr int kShapeClasses = 5;  // spheres, capsules, z-capsules, cuboids, z-cuboids
+struct GridView {
+    float ox, oy, oz, inv_h;
+    int nx, ny, nz;
+    float reach;
+    const unsigned *start[kShapeClasses];        // CSR row starts [cells + 1]
+    const unsigned short *ids[kShapeClasses];    // record indices into the staged class arrays
+};
+
 // Scene as one packed float blob (16-byte aligned sections). Offsets are in floats.
 struct SceneDesc {
     const float *blob;
@@ -48,6 +64,8 @@ struct SceneDesc {
     int sorted;  // 1 when every class is in non-decreasing min_distance order (prefix masks are then redundant)
     int n_pc;
     CaptView pc[kMaxPointClouds];
+    int n_grid;  // 0: no grid (unsorted or small scene) -> ordered scans
+    GridView grid[kGridLevels];
 };
 
 // Pointers into the staged copy.
@@ -275,6 +293,72 @@ __device__ __forceinline__ bool scan_scene(const Scene &sc, const Tile<T> &s, bo
     return acc < 0;
 }
 
+// ------------------------------------------------------------------------------------------------ grid-culled scans
+__device__ __forceinline__ int grid_cell(const GridView &g, float x, float y, float z) {
+    // monotone in each coordinate; the host maps inflated obstacle boxes to cell ranges with the same expression
+    const int cx = min(max(__float2int_rd((x - g.ox) * g.inv_h), 0), g.nx - 1);
+    const int cy = min(max(__float2int_rd((y - g.oy) * g.inv_h), 0), g.ny - 1);
+    const int cz = min(max(__float2int_rd((z - g.oz) * g.inv_h), 0), g.nz - 1);
+    return (cz * g.ny + cy) * g.nx + cx;
+}
+
+// smallest level whose reach covers radius r, or -1 (radii are per-sphere constants: warp-uniform)
+__device__ __forceinline__ int grid_level(const SceneDesc &d, float r) {
+    int lv = -1;
+#pragma unroll
+    for (int l = kGridLevels - 1; l >= 0; --l)
+        if (l < d.n_grid && r <= d.grid[l].reach) lv = l;
+    return lv;
+}
+
+// One shape class: every lane walks the candidate list of its own cell; record `n` (the first padding record) stands in
+// once a lane's list is exhausted, so the loop body needs no predication. One warp vote per 8 candidates.
+template <class Test, int POLICY>
+__device__ __forceinline__ int grid_scan_class(const unsigned *__restrict__ start, const unsigned short *__restrict__ ids, int cell,
+                                               const float4 *__restrict__ obs, int n, float x, float y, float z, float r, float rsq,
+                                               bool on, int acc) {
+    unsigned b = 0, cnt = 0;
+    if (on) {
+        b = __ldg(start + cell);
+        cnt = __ldg(start + cell + 1) - b;
+    }
+    const unsigned wmax = __reduce_max_sync(kFull, cnt);
+#pragma unroll 1
+    for (unsigned i = 0; i < wmax; i += 2) {
+        const int id0 = (i < cnt) ? static_cast<int>(__ldg(ids + b + i)) : n;
+        const int id1 = (i + 1 < cnt) ? static_cast<int>(__ldg(ids + b + i + 1)) : n;
+        acc |= __float_as_int(Test::test(obs + id0 * Test::kRec, x, y, z, r, rsq));
+        acc |= __float_as_int(Test::test(obs + id1 * Test::kRec, x, y, z, r, rsq));
+        if ((i & 6u) == 6u && scan_should_stop<POLICY>(acc < 0, on)) break;
+    }
+    return acc;
+}
+
+template <int POLICY>
+__device__ __forceinline__ bool grid_scan_scene(const GridView &g, const Scene &sc, float x, float y, float z, float r, bool on) {
+    const int cell = grid_cell(g, x, y, z);
+    const float rsq = r * r;
+    int acc = 0;
+    if (sc.n_sph > 0) {
+        acc = grid_scan_class<SphereTest, POLICY>(g.start[0], g.ids[0], cell, sc.sph, sc.n_sph, x, y, z, r, rsq, on, acc);
+        if (scan_should_stop<POLICY>(acc < 0, on)) return acc < 0;
+    }
+    if (sc.n_cap > 0) {
+        acc = grid_scan_class<CapsuleTest, POLICY>(g.start[1], g.ids[1], cell, sc.cap, sc.n_cap, x, y, z, r, rsq, on, acc);
+        if (scan_should_stop<POLICY>(acc < 0, on)) return acc < 0;
+    }
+    if (sc.n_zcap > 0) {
+        acc = grid_scan_class<ZCapsuleTest, POLICY>(g.start[2], g.ids[2], cell, sc.zcap, sc.n_zcap, x, y, z, r, rsq, on, acc);
+        if (scan_should_stop<POLICY>(acc < 0, on)) return acc < 0;
+    }
+    if (sc.n_cub > 0) {
+        acc = grid_scan_class<CuboidTest, POLICY>(g.start[3], g.ids[3], cell, sc.cub, sc.n_cub, x, y, z, r, rsq, on, acc);
+        if (scan_should_stop<POLICY>(acc < 0, on)) return acc < 0;
+    }
+    if (sc.n_zcub > 0) acc = grid_scan_class<ZCuboidTest, POLICY>(g.start[4], g.ids[4], cell, sc.zcub, sc.n_zcub, x, y, z, r, rsq, on, acc);
+    return acc < 0;
+}
+
 // ------------------------------------------------------------------------------------------------ point clouds
 __device__ __forceinline__ float aabb_distsq(const float *bb, float x, float y, float z) {
     const float d0 = x - fminf(fmaxf(x, bb[0]), bb[3]);
@@ -337,7 +421,7 @@ __device__ __forceinline__ bool scan_pointclouds(const SceneDesc &d, const Tile<
 // Returns true when this lane's state is collision free. `active` lanes take part; idle lanes only follow the
 // warp-uniform control flow. G = lanes per reference rake (8 for motions, 1 for single states).
 // EDGE: all lanes belong to one motion, so the first hit anywhere ends the whole warp's work.
-template <class R, int G, bool EDGE, bool MASKED>
+template <class R, int G, bool EDGE, bool MASKED, bool GRID>
 __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, bool active) {
     constexpr int FT = 4;  // fine spheres processed together per lane
     constexpr int POLICY = EDGE ? kAnyHit : kUntilAllHit;
@@ -367,13 +451,50 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
             const float ext = alive ? sqrtf(fmaf(c.z[0], c.z[0], fmaf(c.y[0], c.y[0], c.x[0] * c.x[0]))) + cl.w : -INFINITY;
             c.ext[0] = group_max<G>(ext);
             if (!alive) { c.x[0] = kIdle; c.y[0] = kIdle; c.z[0] = kIdle; }  // idle lanes must never raise the sign bit
-            bool chit = scan_scene<1, kUntilAllHit, MASKED>(sc, c, alive);
+            const int clv = GRID ? grid_level(sd, cl.w) : -1;
+            bool chit = (GRID && clv >= 0) ? grid_scan_scene<kUntilAllHit>(sd.grid[clv], sc, c.x[0], c.y[0], c.z[0], cl.w, alive)
+                                           : scan_scene<1, kUntilAllHit, MASKED>(sc, c, alive);
             if (sd.n_pc > 0) chit |= scan_pointclouds<1>(sd, c, alive && !chit);
             const bool need = group_any<G>(chit && alive) && alive;
             if (!__any_sync(kFull, need)) continue;
             // fine spheres of the link, FT at a time
             const int fb = tb.link_begin[l], fe = tb.link_begin[l + 1];
             bool fhit = false;
+            if (GRID) {
+                // one fine sphere per lane at a time, each against the short candidate list of its own cell
+#pragma unroll 1
+                for (int f = fb; f < fe; ++f) {
+                    const float4 fl = tb.fine[f];
+                    const int flv = grid_level(sd, fl.w);
+                    const bool on = need && !fhit;
+                    bool h;
+                    if (flv >= 0) {
+                        float x, y, z;
+                        frame_apply(F, fl.x, fl.y, fl.z, x, y, z);
+                        h = grid_scan_scene<POLICY>(sd.grid[flv], sc, x, y, z, fl.w, on);
+                        if (sd.n_pc > 0) {
+                            Tile<1> s1;
+                            s1.x[0] = x; s1.y[0] = y; s1.z[0] = z; s1.r[0] = fl.w; s1.ext[0] = on ? 0.0f : -INFINITY;
+                            h |= scan_pointclouds<1>(sd, s1, on && !h);
+                        }
+                    } else {
+                        Tile<1> s1;
+                        frame_apply(F, fl.x, fl.y, fl.z, s1.x[0], s1.y[0], s1.z[0]);
+                        s1.r[0] = fl.w;
+                        const float e = on ? sqrtf(fmaf(s1.z[0], s1.z[0], fmaf(s1.y[0], s1.y[0], s1.x[0] * s1.x[0]))) + fl.w : -INFINITY;
+                        s1.ext[0] = group_max<G>(e);
+                        if (!on) { s1.ext[0] = -INFINITY; s1.x[0] = kIdle; s1.y[0] = kIdle; s1.z[0] = kIdle; }
+                        h = scan_scene<1, POLICY, MASKED>(sc, s1, on);
+                        if (sd.n_pc > 0) h |= scan_pointclouds<1>(sd, s1, on && !h);
+                    }
+                    fhit |= h && on;
+                    if (EDGE) {
+                        if (__any_sync(kFull, fhit)) return !fhit;
+                    } else {
+                        if (__all_sync(kFull, fhit || !need)) break;
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int f0 = fb; f0 < fe; f0 += FT) {
                 Tile<FT> s;
@@ -395,6 +516,7 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
                 } else {
                     if (__all_sync(kFull, fhit || !need)) break;
                 }
+            }
             }
             if (fhit) alive = false;
             if (!EDGE && !__any_sync(kFull, alive)) return false;
@@ -496,7 +618,7 @@ __device__ __forceinline__ float vamp_l2_norm(const float (&v)[DIM]) {
 }
 
 // One warp per motion; motions are taken from a global queue (edge cost varies by 100x with early exit).
-template <class R, bool MASKED>
+template <class R, bool MASKED, bool GRID>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float *__restrict__ q1, const int2 *__restrict__ pairs,
                         long long m, int resolution, uint8_t *__restrict__ valid, LaunchCounters *cnt) {
@@ -546,7 +668,7 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
         bool ok = true;
         for (int base = 0; base < n; base += 4) {
             const bool active = (base + rake_in_pass) < n;
-            const bool good = check_state<R, 8, true, MASKED>(q, sd, sc, active);
+            const bool good = check_state<R, 8, true, MASKED, GRID>(q, sd, sc, active);
             if (__any_sync(kFull, active && !good)) { ok = false; break; }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -560,7 +682,7 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
 
 // One lane per state: VampStateValidityChecker::isValid = validate_motion<Robot, rake, 1>(q, q), i.e. one fkcc on
 // 8 identical lanes (src/ompl/vamp/VampStateValidityChecker.h:37-41) -> group size 1 here.
-template <class R, bool MASKED>
+template <class R, bool MASKED, bool GRID>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, uint8_t *__restrict__ valid, LaunchCounters *cnt) {
     extern __shared__ __align__(16) float smem[];
@@ -581,7 +703,7 @@ validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, 
 #pragma unroll
         for (int j = 0; j < D; ++j) q[j] = active ? __ldg(qs + i * D + j) : 0.0f;
         // validate_vector with start == goal: block = q + 0 * percents
-        const bool good = check_state<R, 1, false, MASKED>(q, sd, sc, active);
+        const bool good = check_state<R, 1, false, MASKED, GRID>(q, sd, sc, active);
         if (active) valid[i] = good ? 1 : 0;
     }
 }

@@ -63,6 +63,7 @@ def load_library():
     L.b200mp_capt_sizes.argtypes = [_vp, _vp]
     L.b200mp_capt_export.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
     L.b200mp_env_sort.argtypes = [_vp]
+    L.b200mp_env_set_grid.argtypes = [_vp, C.c_int]
     L.b200mp_env_commit.argtypes = [_vp]
     L.b200mp_env_min_distances.argtypes = [_vp, C.c_int, _vp]
     L.b200mp_env_min_distances.restype = _i64
@@ -301,6 +302,10 @@ class Environment:
         """vamp::collision::CAPT(points, r_min, r_max, r_point), built on the host by the engine."""
         a = _host(xyz, np.float32).reshape(-1, 3)
         _check(self._L.b200mp_env_add_pointcloud(self._h, a.ctypes.data, a.shape[0], r_min, r_max, r_point))
+
+    def set_grid(self, enable: bool):
+        """Candidate-grid culling of sorted scenes on/off (b200mp_env_set_grid); takes effect at the next commit()."""
+        _check(self._L.b200mp_env_set_grid(self._h, int(enable)))
 
     def sort(self):
         _check(self._L.b200mp_env_sort(self._h))

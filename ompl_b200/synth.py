@@ -91,8 +91,10 @@ def clutter_scene(seed: int = 1234, n_spheres: int = 500, n_cuboids: int = 500, 
     return out
 
 
-def fill_env(env, scene: dict, sort: bool = True):
+def fill_env(env, scene: dict, sort: bool = True, grid: bool | None = None):
     """Push a scene dict into any environment object exposing add_spheres/add_cuboids/add_capsules/sort."""
+    if grid is not None:
+        env.set_grid(grid)
     if "spheres" in scene and len(scene["spheres"]):
         env.add_spheres(scene["spheres"])
     if "capsules" in scene and len(scene["capsules"]):

@@ -179,3 +179,31 @@ def test_linearity_properties_full_size(ctx):
     v2 = ctx.validate_motions("panda", env, q0[perm], q1[perm])
     np.testing.assert_array_equal(v2, v[perm])
     assert 0.001 < v.mean() < 0.2
+
+
+@pytest.mark.parametrize("robot,scene_kw", [
+    ("panda", dict(seed=41, n_spheres=300, n_cuboids=300, n_capsules=60, n_zcuboids=60, n_zcapsules=60)),
+    ("panda", dict(seed=1234, n_spheres=500, n_cuboids=500)),
+    ("fetch", dict(seed=42, n_spheres=150, n_cuboids=150, n_capsules=30, n_zcuboids=30, n_zcapsules=30, rho_lo=0.5, rho_hi=1.6,
+                   z_lo=0.0, z_hi=1.8)),
+])
+def test_grid_culling_makes_the_same_decisions_as_the_ordered_scan(ctx, robot, scene_kw):
+    """Sorted scenes are validated through candidate grids; the plain ordered scan (grid off) is the reference semantics."""
+    scene = synth.clutter_scene(**scene_kw)
+    eg = synth.fill_env(ompl_b200.Environment(ctx), scene, grid=True)
+    es = synth.fill_env(ompl_b200.Environment(ctx), scene, grid=False)
+    pe = synth.fill_env(port.PortEnvironment(), scene)
+    q = synth.uniform_states(robot, 100000, 23)
+    a, b = ctx.validate_states(robot, eg, q), ctx.validate_states(robot, es, q)
+    assert_validity_parity(a, b, clr_states(pe, robot, q), "grid vs scan, states", band=1e-6)
+    starts = q[b == 1][:20000]
+    q0, q1 = synth.local_edges(robot, starts, 29, 0.02, 3.0)
+    a, b = ctx.validate_motions(robot, eg, q0, q1), ctx.validate_motions(robot, es, q0, q1)
+    assert 0.05 < b.mean() < 0.95
+    assert_validity_parity(a, b, clr_motions(pe, robot, q0, q1), "grid vs scan, motions", band=1e-6)
+    # obstacles far outside the grid's core region and huge ones still collide correctly (border cells are unbounded)
+    far = dict(spheres=np.concatenate([scene["spheres"], [[0.3, 0.0, 0.6, 0.25], [5.0, 5.0, 5.0, 0.1], [0.0, -0.4, 0.3, 0.02]]]).astype(np.float32),
+               cuboids=scene["cuboids"])
+    eg2 = synth.fill_env(ompl_b200.Environment(ctx), far, grid=True)
+    es2 = synth.fill_env(ompl_b200.Environment(ctx), far, grid=False)
+    np.testing.assert_array_equal(ctx.validate_states(robot, eg2, q[:30000]), ctx.validate_states(robot, es2, q[:30000]))

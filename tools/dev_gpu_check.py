@@ -61,6 +61,7 @@ def main():
                               ("clutter_all", synth.clutter_scene(3, 200, 200, n_capsules=50, n_zcuboids=50, n_zcapsules=50)),
                               ("C2", synth.clutter_scene(1234, 500, 500))):
         env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+        env_scan = synth.fill_env(ompl_b200.Environment(ctx), scene, grid=False)
         chk, kind = checker_env(scene)
         pe = synth.fill_env(port.PortEnvironment(), scene)
         q = synth.uniform_states("panda", 200000, 5)
@@ -85,6 +86,9 @@ def main():
             rep = np.resize(v, 1 << 16)
             ms, got = time_device(ctx, env, "panda", q0[rep], q1[rep])
             print(f"[{scene_name}] all-valid x{len(rep)} ({v.size} unique): {ms:.2f} ms = {len(rep)/ms*1e3:.3e} edges/s = {len(rep)*64/ms*1e3:.3e} states/s; gpu valid frac {got.mean():.4f}", flush=True)
+            ms2, _ = time_device(ctx, env_scan, "panda", q0[rep], q1[rep])
+            ms3, _ = time_device(ctx, env_scan, "panda", q0, q1)
+            print(f"[{scene_name}] grid off: all-valid {ms2:.2f} ms, mixed 2^18 {ms3:.2f} ms", flush=True)
 
 
 if __name__ == "__main__":
