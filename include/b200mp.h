@@ -132,6 +132,13 @@ int64_t b200mp_launch_count(const b200mp_ctx *ctx);
 int b200mp_knn_create(b200mp_ctx *ctx, int dim, int metric, b200mp_knn **out);
 void b200mp_knn_destroy(b200mp_knn *knn);
 int b200mp_knn_clear(b200mp_knn *knn);
+/* Batches of >= 4096 queries against >= 32768 points are answered through a cell index (Voronoi cells of strided pivots
+ * with bounding boxes, queries sorted by cell, exact pruning by box distance; same results as the exhaustive kernel).
+ * enable = 0 forces the exhaustive tiled kernel (A/B measurements, tests). Default: enabled. */
+int b200mp_knn_set_index(b200mp_knn *knn, int enable);
+/* Pruning statistics: candidate rows streamed per query block by the cell-index kernel, summed since creation
+ * (x block size = pair evaluations; the exhaustive kernel evaluates size x queries). */
+int64_t b200mp_knn_rows_visited(b200mp_knn *knn);
 int64_t b200mp_knn_size(const b200mp_knn *knn);
 /* pts[n][dim] host doubles; *first_id (may be NULL) receives the id of pts[0]. */
 int b200mp_knn_add(b200mp_knn *knn, const double *pts, int64_t n, int64_t *first_id);

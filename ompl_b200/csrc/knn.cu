@@ -284,6 +284,403 @@ __global__ void knn_all_distances_kernel(const double *__restrict__ pts, const f
     out[i] = isinf(feat[i * fw + fw - 1]) ? INFINITY : sqrt(d2);  // removed points report +inf
 }
 
+
+// ================================================================================================ cell index
+// Exact search with spatial pruning for large batches (roadmap construction: every state queries the whole set).
+// The database is partitioned into P cells (the Voronoi regions of P database points taken at a regular stride), stored
+// cell by cell, each with an axis-aligned bounding box. Queries are sorted by their own cell so a block's 256 queries are
+// neighbours in space; the block first searches the cells its queries live in, which gives every query a finite k-th
+// distance, and then visits only the cells whose box lies within the block's current worst k-th distance of the
+// block's query box, streaming each visited cell through shared memory exactly like the brute-force kernel (fp32 filter
+// with a rigorous error bound, fp64 re-evaluation of survivors in the reference's operation order). Pruning uses lower
+// bounds only, so the result is the same exact (distance, id)-ordered top-k as the exhaustive scan.
+constexpr int kCellTile = 512;
+constexpr int kCellThreads = 128;  // queries per block of the cell kernel
+constexpr int kRoundCells = kCellThreads;
+
+__global__ void knn_gather_pivots_kernel(const float *__restrict__ feat, long long n, int P, int fw, float *__restrict__ pivots) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P * fw) return;
+    const int p = t / fw, j = t - p * fw;
+    pivots[t] = feat[((static_cast<long long>(p) * n) / P) * fw + j];
+}
+
+// nearest pivot (fp32, any tie-break: the partition only has to be a partition)
+template <int NV>
+__global__ void __launch_bounds__(kKnnThreads)
+knn_assign_kernel(const float4 *__restrict__ rows, long long n, const float4 *__restrict__ pivots, int P, int *__restrict__ cell) {
+    __shared__ float4 tile[256 * NV];
+    const long long i = static_cast<long long>(blockIdx.x) * kKnnThreads + threadIdx.x;
+    float m2q[4 * NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const float4 r = i < n ? rows[i * NV + v] : make_float4(0.f, 0.f, 0.f, 0.f);
+        m2q[4 * v] = -2.f * r.x; m2q[4 * v + 1] = -2.f * r.y; m2q[4 * v + 2] = -2.f * r.z; m2q[4 * v + 3] = -2.f * r.w;
+    }
+    m2q[4 * NV - 1] = 1.0f;
+    float best = INFINITY;
+    int arg = 0;
+    for (int p0 = 0; p0 < P; p0 += 256) {
+        const int cnt = min(256, P - p0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt * NV; t += kKnnThreads) tile[t] = pivots[static_cast<long long>(p0) * NV + t];
+        __syncthreads();
+        for (int c = 0; c < cnt; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const float4 pv = tile[c * NV + v];
+                acc = fmaf(m2q[4 * v], pv.x, acc); acc = fmaf(m2q[4 * v + 1], pv.y, acc);
+                acc = fmaf(m2q[4 * v + 2], pv.z, acc); acc = fmaf(m2q[4 * v + 3], pv.w, acc);
+            }
+            if (acc < best) { best = acc; arg = p0 + c; }
+        }
+    }
+    if (i < n) cell[i] = arg;
+}
+
+__global__ void knn_cell_count_kernel(const int *__restrict__ cell, long long n, int *__restrict__ counts) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(counts + cell[i], 1);
+}
+
+// one block: counts[P] -> start[P + 1] (exclusive), cursor[P] = start
+__global__ void __launch_bounds__(1024) knn_cell_scan_kernel(const int *__restrict__ counts, int P, int *__restrict__ start, int *__restrict__ cursor) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < P; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < P ? counts[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFullMask, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int ex = carry + (wid ? warp_sums[wid - 1] : 0) + incl - v;
+        if (i < P) { start[i] = ex; cursor[i] = ex; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) start[P] = carry_s;
+}
+
+__global__ void knn_cell_slot_kernel(const int *__restrict__ cell, long long n, int *__restrict__ cursor, int *__restrict__ pos) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) pos[i] = atomicAdd(cursor + cell[i], 1);
+}
+
+__global__ void knn_permute_kernel(const float4 *__restrict__ feat, const double *__restrict__ pts, const int *__restrict__ pos, long long n, int dim,
+                                   int nv, float4 *__restrict__ feat_s, double *__restrict__ pts_s, int *__restrict__ orig) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long p = pos[i];
+    for (int v = 0; v < nv; ++v) feat_s[p * nv + v] = feat[i * nv + v];
+    for (int j = 0; j < dim; ++j) pts_s[p * dim + j] = pts[i * dim + j];
+    orig[p] = static_cast<int>(i);
+}
+
+// blocks needed per query cell: ceil(#queries in the cell / kCellThreads)
+__global__ void knn_cell_blocks_kernel(const int *__restrict__ q_start, int P, int *__restrict__ nblk) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < P) nblk[c] = (q_start[c + 1] - q_start[c] + kCellThreads - 1) / kCellThreads;
+}
+
+__global__ void knn_query_order_kernel(const int *__restrict__ cell, const int *__restrict__ pos, long long nq, int *__restrict__ order,
+                                       int *__restrict__ cell_sorted) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    order[pos[i]] = static_cast<int>(i);
+    cell_sorted[pos[i]] = cell[i];
+}
+
+// one warp per cell: bounding box of its rows (tombstoned rows skipped), widened by a few ulps so that it also bounds the
+// exact fp64 points the fp32 rows were rounded from
+__global__ void knn_cell_bounds_kernel(const float *__restrict__ feat_s, const int *__restrict__ start, int P, int fw, int dim,
+                                       float *__restrict__ lo, float *__restrict__ hi) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= P) return;
+    for (int j = 0; j < dim; ++j) {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int r = start[c] + lane; r < start[c + 1]; r += 32) {
+            if (isinf(feat_s[static_cast<long long>(r) * fw + fw - 1])) continue;
+            const float v = feat_s[static_cast<long long>(r) * fw + j];
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+        }
+        if (lane == 0) {
+            const bool empty = mn > mx;  // no live rows: a box at infinite distance from everything
+            lo[c * 24 + j] = empty ? INFINITY : mn - (fabsf(mn) * 4e-7f + 1e-30f);
+            hi[c * 24 + j] = empty ? -INFINITY : mx + (fabsf(mx) * 4e-7f + 1e-30f);
+        }
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kCellThreads)
+knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ pts_s, const int *__restrict__ orig, const int *__restrict__ cell_start,
+                 const float *__restrict__ clo, const float *__restrict__ chi, int P, int dim, const double *__restrict__ q64,
+                 const int *__restrict__ q_order, const int *__restrict__ q_start, const int *__restrict__ blk_start, long long nq, const long long *__restrict__ self_ids,
+                 long long self_base, int use_self, int kk, float err_scale, float cmax, Partial *__restrict__ partial,
+                 unsigned long long *__restrict__ rows_visited) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long bars[2];
+    __shared__ int s_job_row[2], s_job_cnt[2];
+    __shared__ int s_list[kRoundCells];
+    __shared__ int s_nlist;
+    __shared__ int s_wcnt[kCellThreads / 32];
+    __shared__ float s_wlo[kCellThreads / 32][24], s_whi[kCellThreads / 32][24], s_qlo[24], s_qhi[24];
+    __shared__ float s_wr[kCellThreads / 32];
+    __shared__ float s_rblk;
+    float4 *tiles = reinterpret_cast<float4 *>(smem_raw);                                           // [2][kCellTile][NV]
+    double *ld2 = reinterpret_cast<double *>(smem_raw + 2 * kCellTile * NV * sizeof(float4));      // [kk][threads]
+    int *lidx = reinterpret_cast<int *>(ld2 + static_cast<size_t>(kk) * kCellThreads);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // block -> (query cell, chunk of kCellThreads queries of that cell): all queries of a block live in one cell, so the
+    // block's query box is (part of) that cell's box
+    if (static_cast<int>(blockIdx.x) >= blk_start[P]) return;
+    int own;
+    {
+        int lo_c = 0, hi_c = P;  // last cell with blk_start[c] <= blockIdx.x
+        while (hi_c - lo_c > 1) {
+            const int mid = (lo_c + hi_c) >> 1;
+            if (blk_start[mid] <= static_cast<int>(blockIdx.x)) lo_c = mid; else hi_c = mid;
+        }
+        own = lo_c;
+    }
+    const long long qs = static_cast<long long>(q_start[own]) + static_cast<long long>(blockIdx.x - blk_start[own]) * kCellThreads + tid;
+    const bool has_q = qs < q_start[own + 1];
+    const long long qi = has_q ? q_order[qs] : 0;
+
+    float m2q[4 * NV];
+    float qn = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4 * NV; ++j) m2q[j] = 0.f;
+    double qd[4 * NV - 1];
+#pragma unroll
+    for (int j = 0; j < 4 * NV - 1; ++j) {
+        qd[j] = (has_q && j < dim) ? q64[qi * dim + j] : 0.0;
+        const float qf = static_cast<float>(qd[j]);
+        m2q[j] = -2.0f * qf;
+        qn = fmaf(qf, qf, qn);
+    }
+    m2q[4 * NV - 1] = 1.0f;
+    const long long self = !use_self ? -1 : (self_ids ? (has_q ? self_ids[qi] : -1) : self_base + qi);
+    const float qnorm = sqrtf(qn);
+    const float err = err_scale * (qnorm + cmax) * (qnorm + cmax);
+
+    for (int s = 0; s < kk; ++s) {
+        ld2[s * kCellThreads + tid] = INFINITY;
+        lidx[s * kCellThreads + tid] = -1;
+    }
+    double worst = INFINITY;
+    int worst_idx = 0x7fffffff, worst_slot = 0;
+    float thr = has_q ? INFINITY : -INFINITY;
+
+    // ---- bounding box of the block's queries (fp32 values of the queries, widened like the cell boxes)
+#pragma unroll
+    for (int j = 0; j < 4 * NV - 1; ++j) {
+        float mn = has_q ? -0.5f * m2q[j] : INFINITY, mx = has_q ? -0.5f * m2q[j] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+        }
+        if (lane == 0) { s_wlo[wid][j] = mn; s_whi[wid][j] = mx; }
+    }
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < 4 * NV - 1) {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int w = 0; w < kCellThreads / 32; ++w) { mn = fminf(mn, s_wlo[w][tid]); mx = fmaxf(mx, s_whi[w][tid]); }
+        s_qlo[tid] = mn - (fabsf(mn) * 4e-7f + 1e-30f);
+        s_qhi[tid] = mx + (fabsf(mx) * 4e-7f + 1e-30f);
+    }
+    const int own_lo = own, own_hi = own;
+    int it = 0;  // tile jobs issued so far: buffer = it & 1, mbarrier parity = (it >> 1) & 1
+    __syncthreads();
+
+    // stream the listed cells through shared memory, double buffered. Thread 0 walks the list (cell -> tiles of at most
+    // kCellTile rows), announces each tile in the 2-entry ring s_job_* and issues its bulk copy one tile ahead.
+    int gl = 0, gb = 0, ge = 0;  // generator state, meaningful in thread 0 only
+    auto next_job = [&](int slot_it) {
+        const int slot = slot_it & 1;
+        while (gb >= ge) {
+            if (gl >= s_nlist) { s_job_cnt[slot] = 0; return; }
+            const int c = s_list[gl++];
+            gb = cell_start[c];
+            ge = cell_start[c + 1];
+        }
+        const int cnt = min(kCellTile, ge - gb);
+        s_job_row[slot] = gb;
+        s_job_cnt[slot] = cnt;
+        const uint32_t bytes = static_cast<uint32_t>(cnt) * NV * sizeof(float4);
+        mbar_expect_tx(&bars[slot], bytes);
+        bulk_g2s(tiles + static_cast<size_t>(slot) * kCellTile * NV, feat_s + static_cast<long long>(gb) * NV, bytes, &bars[slot]);
+        gb += cnt;
+    };
+    unsigned long long visited = 0;  // rows streamed by this block (thread 0), for the pruning statistics
+    auto run_list = [&]() {
+        if (tid == 0) {
+            gl = 0; gb = 0; ge = 0;
+            next_job(it);
+        }
+        __syncthreads();
+        for (;;) {
+            const int slot = it & 1;
+            const int cnt = s_job_cnt[slot];
+            if (cnt == 0) break;
+            const int row0 = s_job_row[slot];
+            if (tid == 0) { next_job(it + 1); visited += cnt; }
+            mbar_wait(&bars[slot], (it >> 1) & 1);
+            const float4 *tile = tiles + static_cast<size_t>(slot) * kCellTile * NV;
+            for (int c0 = 0; c0 < cnt; c0 += 4) {
+                float sv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 *row = tile + static_cast<size_t>(min(c0 + u, cnt - 1)) * NV;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const float4 c = row[v];
+                        acc = fmaf(m2q[4 * v + 0], c.x, acc);
+                        acc = fmaf(m2q[4 * v + 1], c.y, acc);
+                        acc = fmaf(m2q[4 * v + 2], c.z, acc);
+                        acc = fmaf(m2q[4 * v + 3], c.w, acc);
+                    }
+                    sv[u] = acc;
+                }
+                const bool any = (sv[0] < thr) | (sv[1] < thr) | (sv[2] < thr) | (sv[3] < thr);
+                if (any) {
+#pragma unroll 1
+                    for (int u = 0; u < 4; ++u) {
+                        if (!(sv[u] < thr) || c0 + u >= cnt) continue;
+                        const long long r = row0 + c0 + u;
+                        const int id = orig[r];
+                        if (id == self) continue;
+                        double d2 = 0.0;
+#pragma unroll
+                        for (int j2 = 0; j2 < 4 * NV - 1; ++j2) {
+                            if (j2 < dim) {
+                                const double diff = pts_s[r * dim + j2] - qd[j2];
+                                d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+                            }
+                        }
+                        if (d2 < worst || (d2 == worst && id < worst_idx)) {
+                            ld2[worst_slot * kCellThreads + tid] = d2;
+                            lidx[worst_slot * kCellThreads + tid] = id;
+                            worst = -1.0;
+                            worst_idx = -1;
+                            for (int s2 = 0; s2 < kk; ++s2) {
+                                const double v = ld2[s2 * kCellThreads + tid];
+                                const int vi = lidx[s2 * kCellThreads + tid];
+                                const int key = vi < 0 ? 0x7fffffff : vi;
+                                if (v > worst || (v == worst && key > worst_idx)) { worst = v; worst_idx = key; worst_slot = s2; }
+                            }
+                            thr = (worst == INFINITY) ? INFINITY : __double2float_ru(worst - static_cast<double>(qn)) + err;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            ++it;
+        }
+        __syncthreads();
+    };
+    // block-wide maximum of the queries' squared k-th distances (rounded up)
+    auto refresh_bound = [&]() {
+        float r2 = !has_q ? -INFINITY : (worst == INFINITY ? INFINITY : __double2float_ru(worst) * 1.000001f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(kFullMask, r2, o));
+        if (lane == 0) s_wr[wid] = r2;
+        __syncthreads();
+        if (tid == 0) {
+            float m = -INFINITY;
+            for (int w = 0; w < kCellThreads / 32; ++w) m = fmaxf(m, s_wr[w]);
+            s_rblk = m;
+        }
+        __syncthreads();
+    };
+    // ---- the cells the block's own queries live in (contiguous in cell order)
+    for (int c0 = own_lo; c0 <= own_hi; c0 += kRoundCells) {
+        if (tid == 0) s_nlist = min(kRoundCells, own_hi - c0 + 1);
+        __syncthreads();
+        if (tid < s_nlist) s_list[tid] = c0 + tid;
+        __syncthreads();
+        run_list();
+    }
+    refresh_bound();
+    // ---- every other cell, 256 at a time: one thread tests one cell's box against the block's query box. Two sweeps: first
+    // the cells whose box overlaps the query box (they hold almost all true neighbours, so afterwards the k-th distances
+    // are nearly final), then the remaining cells that lie within the block's worst k-th distance.
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        for (int base = 0; base < P; base += kRoundCells) {
+            const int c = base + tid;
+            bool pass = false;
+            if (c < P && (c < own_lo || c > own_hi)) {
+                float d2 = 0.f;
+                for (int j = 0; j < dim; ++j) {
+                    const float gap = fmaxf(fmaxf(clo[c * 24 + j] - s_qhi[j], s_qlo[j] - chi[c * 24 + j]), 0.f);
+                    d2 = fmaf(gap, gap, d2);
+                }
+                // empty cells have gap = +inf: they never overlap and are harmless if listed
+                pass = sweep == 0 ? (d2 == 0.f) : (d2 > 0.f && d2 * 0.99999f <= s_rblk);
+            }
+            const unsigned bal = __ballot_sync(kFullMask, pass);
+            if (lane == 0) s_wcnt[wid] = __popc(bal);
+            __syncthreads();
+            int off = 0;
+            for (int w = 0; w < wid; ++w) off += s_wcnt[w];
+            if (pass) s_list[off + __popc(bal & ((1u << lane) - 1u))] = c;
+            if (tid == kCellThreads - 1) s_nlist = off + __popc(bal);
+            __syncthreads();
+            if (s_nlist > 0) {
+                run_list();
+                refresh_bound();
+            }
+        }
+    }
+    if (tid == 0 && rows_visited) atomicAdd(rows_visited, visited);
+    if (has_q) {
+        Partial *out = partial + qi * kk;
+        for (int s = 0; s < kk; ++s) {
+            Partial p;
+            p.d2 = ld2[s * kCellThreads + tid];
+            p.idx = lidx[s * kCellThreads + tid];
+            p.pad = 0;
+            out[s] = p;
+        }
+    }
+}
+
 }  // namespace
 
 struct b200mp_knn {
@@ -299,6 +696,18 @@ struct b200mp_knn {
     std::vector<unsigned char> alive;
     Scratch scratch;
     Scratch qscratch;  // fp64 copies of fp32 query blocks
+    // cell index over rows [0, index_n): rebuilt lazily when the database changed since it was built
+    bool use_index = true;
+    bool index_valid = false;
+    long long index_n = 0;
+    int index_P = 0;
+    Scratch index_mem;   // feat_sorted | pts_sorted | orig | cell_start | lo | hi
+    Scratch index_tmp;   // build / query-ordering temporaries
+    float4 *ix_feat = nullptr;
+    double *ix_pts = nullptr;
+    int *ix_orig = nullptr, *ix_start = nullptr;
+    float *ix_lo = nullptr, *ix_hi = nullptr, *ix_pivots = nullptr;
+    unsigned long long *d_rows_visited = nullptr;  // candidate rows streamed by the cell kernel since creation
 };
 
 namespace {
@@ -372,6 +781,159 @@ int knn_radius_impl(b200mp_knn *k, const double *q, double radius, int64_t self,
 
 }  // namespace
 
+
+namespace {
+
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+template <int NV>
+void launch_assign(const float4 *rows, long long n, const float4 *pivots, int P, int *cell, cudaStream_t st) {
+    knn_assign_kernel<NV><<<static_cast<unsigned>((n + kKnnThreads - 1) / kKnnThreads), kKnnThreads, 0, st>>>(rows, n, pivots, P, cell);
+}
+
+int knn_assign(b200mp_knn *k, const float *rows, long long n, int *cell, cudaStream_t st) {
+    const float4 *r4 = reinterpret_cast<const float4 *>(rows), *p4 = reinterpret_cast<const float4 *>(k->ix_pivots);
+    switch (k->nv) {
+        case 2: launch_assign<2>(r4, n, p4, k->index_P, cell, st); break;
+        case 3: launch_assign<3>(r4, n, p4, k->index_P, cell, st); break;
+        default: launch_assign<6>(r4, n, p4, k->index_P, cell, st); break;
+    }
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    return B200MP_OK;
+}
+
+// counting sort of `n` items by cell: start[P + 1] and the slot of every item (order inside a cell is arbitrary)
+int knn_cell_sort(b200mp_knn *k, const int *cell, long long n, int *counts, int *start, int *cursor, int *pos, cudaStream_t st) {
+    const int P = k->index_P;
+    B200_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * P, st));
+    const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+    knn_cell_count_kernel<<<blocks, 256, 0, st>>>(cell, n, counts);
+    knn_cell_scan_kernel<<<1, 1024, 0, st>>>(counts, P, start, cursor);
+    knn_cell_slot_kernel<<<blocks, 256, 0, st>>>(cell, n, cursor, pos);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(3);
+    return B200MP_OK;
+}
+
+int knn_build_index(b200mp_knn *k, cudaStream_t st) {
+    const long long n = k->n;
+    const int fw = k->nv * 4;
+    int P = 64;
+    while (P < 16384 && static_cast<long long>(P) * 128 < n) P *= 2;
+    k->index_P = P;
+    size_t off = 0;
+    const size_t o_feat = off; off += align256(static_cast<size_t>(n) * fw * sizeof(float));
+    const size_t o_pts = off;  off += align256(static_cast<size_t>(n) * k->dim * sizeof(double));
+    const size_t o_orig = off; off += align256(static_cast<size_t>(n) * sizeof(int));
+    const size_t o_start = off; off += align256(static_cast<size_t>(P + 1) * sizeof(int));
+    const size_t o_lo = off; off += align256(static_cast<size_t>(P) * 24 * sizeof(float));
+    const size_t o_hi = off; off += align256(static_cast<size_t>(P) * 24 * sizeof(float));
+    const size_t o_piv = off; off += align256(static_cast<size_t>(P) * fw * sizeof(float));
+    int rc = k->index_mem.reserve(off);
+    if (rc) return rc;
+    char *m = k->index_mem.ptr;
+    k->ix_feat = reinterpret_cast<float4 *>(m + o_feat);
+    k->ix_pts = reinterpret_cast<double *>(m + o_pts);
+    k->ix_orig = reinterpret_cast<int *>(m + o_orig);
+    k->ix_start = reinterpret_cast<int *>(m + o_start);
+    k->ix_lo = reinterpret_cast<float *>(m + o_lo);
+    k->ix_hi = reinterpret_cast<float *>(m + o_hi);
+    k->ix_pivots = reinterpret_cast<float *>(m + o_piv);
+    // temporaries: cell[n] | pos[n] | counts[P] | cursor[P]
+    rc = k->index_tmp.reserve(align256(static_cast<size_t>(n) * 4) * 2 + align256(static_cast<size_t>(P) * 4) * 2);
+    if (rc) return rc;
+    int *cell = reinterpret_cast<int *>(k->index_tmp.ptr);
+    int *pos = reinterpret_cast<int *>(k->index_tmp.ptr + align256(static_cast<size_t>(n) * 4));
+    int *counts = reinterpret_cast<int *>(k->index_tmp.ptr + 2 * align256(static_cast<size_t>(n) * 4));
+    int *cursor = counts + align256(static_cast<size_t>(P) * 4) / 4;
+    knn_gather_pivots_kernel<<<(P * fw + 255) / 256, 256, 0, st>>>(k->d_feat, n, P, fw, k->ix_pivots);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    if ((rc = knn_assign(k, k->d_feat, n, cell, st))) return rc;
+    if ((rc = knn_cell_sort(k, cell, n, counts, k->ix_start, cursor, pos, st))) return rc;
+    knn_permute_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(k->d_feat), k->d_pts, pos, n, k->dim,
+                                                                             k->nv, k->ix_feat, k->ix_pts, k->ix_orig);
+    knn_cell_bounds_kernel<<<(P * 32 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float *>(k->ix_feat), k->ix_start, P, fw, k->dim, k->ix_lo,
+                                                                 k->ix_hi);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(2);
+    k->index_valid = true;
+    k->index_n = n;
+    return B200MP_OK;
+}
+
+template <int NV>
+int launch_cells(b200mp_knn *k, const double *d_q, const int *q_order, const int *q_start, const int *blk_start, long long nq,
+                 const long long *d_self, long long self_base, int use_self, int kk, Partial *d_partial, cudaStream_t st) {
+    const size_t smem = 2 * kCellTile * NV * sizeof(float4) + static_cast<size_t>(kk) * kCellThreads * (sizeof(double) + sizeof(int));
+    auto kern = knn_cells_kernel<NV>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const float err_scale = 4.0f * (4 * NV + 2) * 5.96e-8f;
+    // upper bound on the number of blocks (sum over cells of ceil(queries / kCellThreads)); surplus blocks exit at once
+    const unsigned grid = static_cast<unsigned>(nq / kCellThreads + k->index_P + 1);
+    kern<<<grid, kCellThreads, smem, st>>>(k->ix_feat, k->ix_pts, k->ix_orig, k->ix_start, k->ix_lo, k->ix_hi, k->index_P, k->dim, d_q, q_order,
+                                           q_start, blk_start, nq, d_self, self_base, use_self, kk, err_scale, k->cmax, d_partial,
+                                           k->d_rows_visited);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    return B200MP_OK;
+}
+
+// large query batches against a large database: cell-pruned exact search
+int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, const long long *d_self, long long self_base, int use_self,
+                      long long *d_idx, double *d_dist, int *d_counts, cudaStream_t st) {
+    int rc;
+    if (!k->index_valid || k->index_n != k->n)
+        if ((rc = knn_build_index(k, st))) return rc;
+    const int fw = k->nv * 4, P = k->index_P;
+    // temporaries: qfeat[nq][fw] | cell[nq] | pos[nq] | order[nq] | cell_sorted[nq] | counts[P] | start[P+1] | cursor[P] | partial[nq][kq]
+    const size_t a_q = align256(static_cast<size_t>(nq) * 4);
+    size_t off = 0;
+    const size_t o_feat = off; off += align256(static_cast<size_t>(nq) * fw * sizeof(float));
+    const size_t o_cell = off; off += a_q;
+    const size_t o_pos = off; off += a_q;
+    const size_t o_order = off; off += a_q;
+    const size_t o_csort = off; off += a_q;
+    const size_t o_counts = off; off += align256(static_cast<size_t>(P) * 4);
+    const size_t o_start = off; off += align256(static_cast<size_t>(P + 1) * 4);
+    const size_t o_cursor = off; off += align256(static_cast<size_t>(P) * 4);
+    const size_t o_nblk = off; off += align256(static_cast<size_t>(P) * 4);
+    const size_t o_bstart = off; off += align256(static_cast<size_t>(P + 1) * 4);
+    const size_t o_partial = off; off += align256(static_cast<size_t>(nq) * kq * sizeof(Partial));
+    if ((rc = k->scratch.reserve(off))) return rc;
+    char *m = k->scratch.ptr;
+    float *qfeat = reinterpret_cast<float *>(m + o_feat);
+    int *cell = reinterpret_cast<int *>(m + o_cell), *pos = reinterpret_cast<int *>(m + o_pos);
+    int *order = reinterpret_cast<int *>(m + o_order), *csort = reinterpret_cast<int *>(m + o_csort);
+    int *counts = reinterpret_cast<int *>(m + o_counts), *start = reinterpret_cast<int *>(m + o_start), *cursor = reinterpret_cast<int *>(m + o_cursor);
+    int *nblk = reinterpret_cast<int *>(m + o_nblk), *bstart = reinterpret_cast<int *>(m + o_bstart);
+    Partial *partial = reinterpret_cast<Partial *>(m + o_partial);
+    const unsigned qblocks = static_cast<unsigned>((nq + 255) / 256);
+    knn_features_kernel<<<qblocks, 256, 0, st>>>(d_q, 0, nq, k->dim, fw, qfeat);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    if ((rc = knn_assign(k, qfeat, nq, cell, st))) return rc;
+    if ((rc = knn_cell_sort(k, cell, nq, counts, start, cursor, pos, st))) return rc;
+    knn_query_order_kernel<<<qblocks, 256, 0, st>>>(cell, pos, nq, order, csort);
+    knn_cell_blocks_kernel<<<(P + 255) / 256, 256, 0, st>>>(start, P, nblk);
+    knn_cell_scan_kernel<<<1, 1024, 0, st>>>(nblk, P, bstart, cursor);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(3);
+    switch (k->nv) {
+        case 2: rc = launch_cells<2>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st); break;
+        case 3: rc = launch_cells<3>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st); break;
+        default: rc = launch_cells<6>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st); break;
+    }
+    if (rc) return rc;
+    knn_merge_kernel<<<static_cast<unsigned>((nq * 32 + 255) / 256), 256, 0, st>>>(partial, nq, kq, kq, d_idx, d_dist, d_counts);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    return B200MP_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int b200mp_knn_create(b200mp_ctx *ctx, int dim, int metric, b200mp_knn **out) {
@@ -383,6 +945,12 @@ int b200mp_knn_create(b200mp_ctx *ctx, int dim, int metric, b200mp_knn **out) {
     k->dim = dim;
     k->metric = metric;
     k->nv = dim <= 7 ? 2 : (dim <= 11 ? 3 : 6);
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&k->d_rows_visited, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(k->d_rows_visited, 0, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaGetLastError();
+        delete k;
+        return fail(B200MP_ERR_CUDA, "b200mp_knn_create: device allocation failed");
+    }
     *out = k;
     return B200MP_OK;
 }
@@ -395,7 +963,25 @@ void b200mp_knn_destroy(b200mp_knn *k) {
     if (k->d_feat) cudaFree(k->d_feat);
     k->scratch.release();
     k->qscratch.release();
+    k->index_mem.release();
+    k->index_tmp.release();
+    if (k->d_rows_visited) cudaFree(k->d_rows_visited);
     delete k;
+}
+
+int b200mp_knn_set_index(b200mp_knn *k, int enable) {
+    if (!k) return fail(B200MP_ERR_INVALID, "b200mp_knn_set_index: NULL");
+    k->use_index = enable != 0;
+    return B200MP_OK;
+}
+
+int64_t b200mp_knn_rows_visited(b200mp_knn *k) {
+    if (!k) return -1;
+    unsigned long long v = 0;
+    cudaSetDevice(k->ctx->device);
+    cudaStreamSynchronize(k->ctx->stream);
+    if (cudaMemcpy(&v, k->d_rows_visited, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return static_cast<int64_t>(v);
 }
 
 int b200mp_knn_clear(b200mp_knn *k) {
@@ -403,6 +989,7 @@ int b200mp_knn_clear(b200mp_knn *k) {
     k->n = 0;
     k->n_removed = 0;
     k->cmax = 0.f;
+    k->index_valid = false;
     k->h_pts.clear();
     k->alive.clear();
     return B200MP_OK;
@@ -461,6 +1048,7 @@ int b200mp_knn_remove(b200mp_knn *k, int64_t id) {
     B200_CUDA(cudaMemcpy(k->d_feat + id * k->nv * 4 + (k->nv * 4 - 1), &inf, sizeof(float), cudaMemcpyHostToDevice));
     k->alive[id] = 0;
     k->n_removed++;
+    k->index_valid = false;
     return B200MP_OK;
 }
 
@@ -472,6 +1060,9 @@ int b200mp_knn_query_device(b200mp_knn *k, const double *d_q, int64_t nq, int kq
     B200_CUDA(cudaSetDevice(k->ctx->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : k->ctx->stream;
     const int kk = kq;  // survivors are evaluated exactly, so no guard band is needed
+    if (k->use_index && nq >= 4096 && k->n >= 32768 && kq <= 64 && k->n <= 0x7fffffffLL)
+        return knn_query_indexed(k, d_q, nq, kq, reinterpret_cast<const long long *>(d_self_ids), self_base, exclude_self,
+                                 reinterpret_cast<long long *>(d_idx), d_dist, d_counts, st);
     // split the database so that at least ~2 waves of blocks exist even for a single query
     const long long qblocks = (nq + kKnnThreads - 1) / kKnnThreads;
     long long splits = std::max<long long>(1, (2LL * k->ctx->sm_count + qblocks - 1) / qblocks);

@@ -85,6 +85,9 @@ def load_library():
     L.b200mp_knn_create.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(_vp)]
     L.b200mp_knn_destroy.argtypes = [_vp]
     L.b200mp_knn_clear.argtypes = [_vp]
+    L.b200mp_knn_set_index.argtypes = [_vp, C.c_int]
+    L.b200mp_knn_rows_visited.argtypes = [_vp]
+    L.b200mp_knn_rows_visited.restype = _i64
     L.b200mp_knn_size.argtypes = [_vp]
     L.b200mp_knn_size.restype = _i64
     L.b200mp_knn_add.argtypes = [_vp, _vp, _i64, C.POINTER(_i64)]
@@ -348,6 +351,13 @@ class NearestNeighbors:
 
     def clear(self):
         _check(self._L.b200mp_knn_clear(self._h))
+
+    def rows_visited(self) -> int:
+        return int(self._L.b200mp_knn_rows_visited(self._h))
+
+    def set_index(self, enable: bool):
+        """Cell-index pruning for large batches on/off (b200mp_knn_set_index)."""
+        _check(self._L.b200mp_knn_set_index(self._h, int(enable)))
 
     def size(self) -> int:
         return int(self._L.b200mp_knn_size(self._h))

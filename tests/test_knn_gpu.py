@@ -132,3 +132,43 @@ def test_single_query_large_database(ctx):
     ridx, rdist = port.knn(db, q, 16, nthreads=8)
     np.testing.assert_array_equal(idx, ridx)
     np.testing.assert_array_equal(dist, rdist)
+
+
+@pytest.mark.parametrize("dim,n,nq,k,kind", [(7, 40000, 40000, 16, "self"), (8, 50000, 6000, 10, "uniform"), (14, 33000, 5000, 32, "uniform"),
+                                              (7, 70000, 9000, 16, "clustered"), (3, 40000, 5000, 8, "duplicates")])
+def test_cell_index_equals_exhaustive_search(ctx, dim, n, nq, k, kind):
+    """Large batches go through the cell index (pruned, exact); the exhaustive tiled kernel is the same engine with the
+    index switched off, itself pinned on the oracle above. Results must be identical, ids and fp64 distances."""
+    rng = np.random.default_rng(dim * 7 + n)
+    if kind == "clustered":
+        centres = rng.uniform(-3, 3, (20, dim))
+        db = centres[rng.integers(0, 20, n)] + rng.normal(scale=0.05, size=(n, dim))
+    elif kind == "duplicates":
+        db = rng.integers(-3, 4, (n, dim)).astype(np.float64)      # 343 distinct points, thousands of exact ties
+    else:
+        db = rng.uniform(-3, 3, (n, dim))
+    db = db.astype(np.float32).astype(np.float64) if kind == "self" else db
+    qs = db[:nq] if kind == "self" else (db[rng.integers(0, n, nq)] + rng.normal(scale=0.3, size=(nq, dim)))
+    self_ids = np.arange(nq) if kind == "self" else None
+    nn = ompl_b200.NearestNeighbors(ctx, dim)
+    nn.add(db)
+    idx, dist, cnt = nn.nearest_k(qs, k, self_ids=self_ids)
+    nn.set_index(False)
+    ridx, rdist, rcnt = nn.nearest_k(qs, k, self_ids=self_ids)
+    np.testing.assert_array_equal(cnt, rcnt)
+    np.testing.assert_array_equal(dist, rdist)
+    np.testing.assert_array_equal(idx, ridx)
+    # and a sample against the CPU oracle
+    sub = rng.choice(nq, 64, replace=False)
+    oidx, odist = port.knn(db, qs[sub], k + 1, nthreads=8)
+    for r, i in enumerate(sub):
+        keep = np.ones(k + 1, bool)
+        if self_ids is not None:
+            keep = oidx[r] != self_ids[i]
+        np.testing.assert_array_equal(dist[i], odist[r][keep][:k])
+    # removal invalidates the index; the rebuilt one skips the tombstone
+    nn.set_index(True)
+    victim = int(idx[0, 0])
+    nn.remove(victim)
+    idx2, _, _ = nn.nearest_k(qs[:5000], k, self_ids=None if self_ids is None else self_ids[:5000])
+    assert victim not in idx2
