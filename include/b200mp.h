@@ -14,6 +14,10 @@
  *   b200mp_env_add_capt       vamp::collision::CAPT (prebuilt tree arrays)       external/vamp/src/impl/vamp/collision/capt.hh:61-618
  *   b200mp_env_add_pointcloud vamp::collision::CAPT::CAPT / subdivide            external/vamp/src/impl/vamp/collision/capt.hh:104-365
  *   b200mp_robot_info         Robot::dimension / resolution / joint bounds       src/ompl/vamp/VampStateSpace.h:10-36
+ *   b200mp_chain_*            KinematicChainSpace::distance / interpolate,        demos/KinematicChain.h:105-121,150-176
+ *                             KinematicChainValidityChecker::isValid,             demos/KinematicChain.h:209-276
+ *                             createHornEnvironment,                              demos/KinematicChain.h:279-315
+ *                             DiscreteMotionValidator::checkMotion (both forms)   src/ompl/base/src/DiscreteMotionValidator.cpp:48-145
  *   b200mp_knn_*              ompl::NearestNeighbors<_T> (Linear semantics)      src/ompl/datastructures/NearestNeighbors.h:46-115,
  *                                                                                src/ompl/datastructures/NearestNeighborsLinear.h:65-142
  *                             metric: RealVectorStateSpace::distance            src/ompl/base/spaces/src/RealVectorStateSpace.cpp:230-242
@@ -40,6 +44,7 @@ typedef struct b200mp_ctx b200mp_ctx;
 typedef struct b200mp_env b200mp_env;
 typedef struct b200mp_knn b200mp_knn;
 typedef struct b200mp_capt b200mp_capt;
+typedef struct b200mp_chain b200mp_chain;
 
 enum {
     B200MP_OK = 0,
@@ -52,7 +57,7 @@ enum {
 };
 
 enum { B200MP_ROBOT_PANDA = 0, B200MP_ROBOT_FETCH = 1 };
-enum { B200MP_METRIC_L2 = 0 };
+enum { B200MP_METRIC_L2 = 0, B200MP_METRIC_CHAIN = 1 };
 
 int b200mp_version(void);
 const char *b200mp_last_error(void);
@@ -130,6 +135,8 @@ int64_t b200mp_launch_count(const b200mp_ctx *ctx);
 /* A container of `dim`-dimensional points with the NearestNeighbors<_T> contract. Points get consecutive ids in
  * insertion order (the adapter maps ids <-> _T). Distances are the reference's doubles: sqrt(sum (a_i - b_i)^2). */
 int b200mp_knn_create(b200mp_ctx *ctx, int dim, int metric, b200mp_knn **out);
+/* Same container under KinematicChainSpace::distance (demos/KinematicChain.h:105-121): points are n_links joint angles. */
+int b200mp_knn_create_chain(b200mp_ctx *ctx, int n_links, double link_length, b200mp_knn **out);
 void b200mp_knn_destroy(b200mp_knn *knn);
 int b200mp_knn_clear(b200mp_knn *knn);
 /* Batches of >= 4096 queries against >= 32768 points are answered through a cell index (Voronoi cells of strided pivots
@@ -159,6 +166,27 @@ int b200mp_knn_query_device_f32(b200mp_knn *knn, const float *d_q, int64_t nq, i
 /* nearestR: all points with distance <= radius, ascending; *count = how many exist, at most cap are written.
  * radius = +inf gives the exhaustive sorted list used for nearestK with k >= size. */
 int b200mp_knn_radius(b200mp_knn *knn, const double *q, double radius, int64_t *idx, double *dist, int64_t cap, int64_t *count);
+
+/* ---- planar kinematic chain (fp64) ------------------------------------------------------------------------------ */
+/* createHornEnvironment(d, eps): *n_segments = 2 (d - 1); segments[n][4] = x0, y0, x1, y1 (may be NULL to query the count). */
+int b200mp_chain_horn_environment(int d, double eps, double *segments, int *n_segments);
+/* n_links <= 31 revolute joints in [-pi, pi), link length, environment segments[n_seg][4]; lvs_fraction = the state
+ * space's longest valid segment fraction (OMPL default 0.01) of the maximum extent 2 pi sqrt(n). */
+int b200mp_chain_create(b200mp_ctx *ctx, int n_links, double link_length, const double *segments, int n_seg, double lvs_fraction,
+                        b200mp_chain **out);
+void b200mp_chain_destroy(b200mp_chain *chain);
+double b200mp_chain_longest_valid_segment(const b200mp_chain *chain);
+/* KinematicChainSpace::distance(a[i], b[i]) and ::interpolate(a[i], b[i], t[i]); host buffers, rows of n_links doubles. */
+int b200mp_chain_distance(b200mp_chain *chain, const double *a, const double *b, int64_t m, double *out);
+int b200mp_chain_interpolate(b200mp_chain *chain, const double *a, const double *b, const double *t, int64_t m, double *out);
+/* KinematicChainValidityChecker::isValid: no self intersection and no intersection with the environment. */
+int b200mp_chain_validate_states(b200mp_chain *chain, const double *q, int64_t m, uint8_t *valid);
+/* DiscreteMotionValidator::checkMotion(a[i], b[i]): valid[i]; last_valid_t[i] (may be NULL) = lastValid.second of the
+ * three-argument form, -1 when the motion is valid; nd[i] (may be NULL) = validSegmentCount. */
+int b200mp_chain_check_motions(b200mp_chain *chain, const double *a, const double *b, int64_t m, uint8_t *valid, double *last_valid_t, int *nd);
+int b200mp_chain_validate_states_device(b200mp_chain *chain, const double *d_q, int64_t m, uint8_t *d_valid, void *stream);
+int b200mp_chain_check_motions_device(b200mp_chain *chain, const double *d_a, const double *d_b, int64_t m, uint8_t *d_valid,
+                                      double *d_last_valid_t, int *d_nd, void *stream);
 
 /* ---- batched PRM roadmap construction ------------------------------------------------------------------------- */
 /* Replaces the per-milestone loop of ompl::geometric::PRM (growRoadmap / addMilestone,

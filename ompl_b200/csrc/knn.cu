@@ -201,7 +201,7 @@ knn_tiled_kernel(const float4 *__restrict__ feat, const double *__restrict__ pts
 // finds the smallest entry strictly greater than the last one emitted (entries are unique by idx) with a lane-local
 // scan followed by a warp-shuffle arg-min, so nothing has to be retired or sorted in memory. dist = sqrt(d2).
 __global__ void knn_merge_kernel(const Partial *__restrict__ partial, long long nq, int n_cand, int k, long long *__restrict__ idx,
-                                 double *__restrict__ dist, int *__restrict__ counts) {
+                                 double *__restrict__ dist, int *__restrict__ counts, int take_sqrt) {
     const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nq) return;
@@ -239,7 +239,7 @@ __global__ void knn_merge_kernel(const Partial *__restrict__ partial, long long 
         if (bi == 0x7fffffff) break;
         if (lane == 0) {
             idx[w * k + r] = bi;
-            dist[w * k + r] = sqrt(bd);
+            dist[w * k + r] = take_sqrt ? sqrt(bd) : bd;
         }
         last_d = bd;
         last_i = bi;
@@ -681,6 +681,135 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
     }
 }
 
+
+// ================================================================================================ chain metric
+// KinematicChainSpace::distance (demos/KinematicChain.h:105-121): L * sum_i |p_i(a) - p_i(b)| over the joint end points
+// p_i = (sum_{j<=i} cos theta_j, sum_{j<=i} sin theta_j), theta_j the cumulative angle. Per point two tables are kept:
+// fp32 cumulative end points [2 NL] for the filter and fp64 per-link (cos, sin) [2 n] for the exact re-evaluation, which
+// accumulates dx += c1 - c2, dy += s1 - s2, dist += sqrt(dx^2 + dy^2) in the reference's order without contraction.
+__global__ void knn_chain_tables_kernel(const double *__restrict__ pts, long long first, long long count, int n, int nl, float *__restrict__ cum32,
+                                        double *__restrict__ link64) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double *p = pts + (first + i) * n;
+    float *f = cum32 + (first + i) * 2 * nl;
+    double *t = link64 + (first + i) * 2 * n;
+    double theta = 0.0, cx = 0.0, sy = 0.0;
+    for (int j = 0; j < nl; ++j) {
+        if (j < n) {
+            theta = __dadd_rn(theta, p[j]);
+            double c, s;
+            sincos(theta, &s, &c);
+            t[2 * j] = c;
+            t[2 * j + 1] = s;
+            cx += c;
+            sy += s;
+        }
+        f[2 * j] = static_cast<float>(cx);      // padding links repeat the last end point: they add 0 to every distance
+        f[2 * j + 1] = static_cast<float>(sy);
+    }
+}
+
+constexpr int kChainTile = 128;
+
+template <int NL>
+__global__ void __launch_bounds__(kKnnThreads)
+knn_chain_kernel(const float2 *__restrict__ cum32, const double *__restrict__ link64, const unsigned char *__restrict__ dead, long long n, int nlinks,
+                 double link_len, const float2 *__restrict__ qcum32, const double *__restrict__ qlink64, long long nq,
+                 const long long *__restrict__ self_ids, long long self_base, int use_self, int kk, Partial *__restrict__ partial, int splits) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long bars[2];
+    float2 *tiles = reinterpret_cast<float2 *>(smem_raw);                                          // [2][kChainTile][NL]
+    double *ld = reinterpret_cast<double *>(smem_raw + 2 * kChainTile * NL * sizeof(float2));     // [kk][threads] distances
+    int *lidx = reinterpret_cast<int *>(ld + static_cast<size_t>(kk) * kKnnThreads);
+    const int tid = threadIdx.x;
+    const long long qi = static_cast<long long>(blockIdx.x) * kKnnThreads + tid;
+    const bool has_q = qi < nq;
+    const long long per = (n + splits - 1) / splits;
+    const long long c_begin = min(static_cast<long long>(blockIdx.y) * per, n);
+    const long long c_end = min(c_begin + per, n);
+    const int n_tiles = static_cast<int>((c_end - c_begin + kChainTile - 1) / kChainTile);
+    float2 q[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) q[j] = has_q ? qcum32[qi * NL + j] : make_float2(0.f, 0.f);
+    const long long self = !use_self ? -1 : (self_ids ? (has_q ? self_ids[qi] : -1) : self_base + qi);
+    // fp32 filter error, in units of link lengths: every end-point coordinate (|.| <= n) carries <= 1 ulp(n) of rounding on
+    // both sides and the accumulation a few more; 16 ulp(n) per term is a comfortable bound
+    const float err = static_cast<float>(nlinks) * 16.0f * 1.1920929e-7f * static_cast<float>(nlinks);
+    for (int s = 0; s < kk; ++s) {
+        ld[s * kKnnThreads + tid] = INFINITY;
+        lidx[s * kKnnThreads + tid] = -1;
+    }
+    double worst = INFINITY;
+    int worst_idx = 0x7fffffff, worst_slot = 0;
+    float thr = has_q ? INFINITY : -INFINITY;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const long long b = c_begin + static_cast<long long>(t) * kChainTile;
+        const int cnt = static_cast<int>(min(static_cast<long long>(kChainTile), c_end - b));
+        const uint32_t bytes = static_cast<uint32_t>(cnt) * NL * sizeof(float2);
+        mbar_expect_tx(&bars[t & 1], bytes);
+        bulk_g2s(tiles + static_cast<size_t>(t & 1) * kChainTile * NL, cum32 + b * NL, bytes, &bars[t & 1]);
+    };
+    if (tid == 0 && n_tiles > 0) issue(0);
+    for (int t = 0; t < n_tiles; ++t) {
+        if (tid == 0 && t + 1 < n_tiles) issue(t + 1);
+        mbar_wait(&bars[t & 1], (t >> 1) & 1);
+        const float2 *tile = tiles + static_cast<size_t>(t & 1) * kChainTile * NL;
+        const long long base = c_begin + static_cast<long long>(t) * kChainTile;
+        const int cnt = static_cast<int>(min(static_cast<long long>(kChainTile), c_end - base));
+        for (int c0 = 0; c0 < cnt; ++c0) {
+            const float2 *row = tile + static_cast<size_t>(c0) * NL;
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < NL; ++j) {
+                const float2 c = row[j];
+                const float dx = c.x - q[j].x, dy = c.y - q[j].y;
+                acc += sqrtf(fmaf(dy, dy, dx * dx));
+            }
+            if (!(acc < thr)) continue;
+            const long long c = base + c0;
+            if (c == self || dead[c]) continue;
+            double dx = 0.0, dy = 0.0, dist = 0.0;
+            for (int j = 0; j < nlinks; ++j) {
+                dx = __dadd_rn(dx, __dsub_rn(link64[c * 2 * nlinks + 2 * j], qlink64[qi * 2 * nlinks + 2 * j]));
+                dy = __dadd_rn(dy, __dsub_rn(link64[c * 2 * nlinks + 2 * j + 1], qlink64[qi * 2 * nlinks + 2 * j + 1]));
+                dist = __dadd_rn(dist, sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+            }
+            const double d = __dmul_rn(dist, link_len);
+            if (d < worst || (d == worst && static_cast<int>(c) < worst_idx)) {
+                ld[worst_slot * kKnnThreads + tid] = d;
+                lidx[worst_slot * kKnnThreads + tid] = static_cast<int>(c);
+                worst = -1.0;
+                worst_idx = -1;
+                for (int s2 = 0; s2 < kk; ++s2) {
+                    const double v = ld[s2 * kKnnThreads + tid];
+                    const int vi = lidx[s2 * kKnnThreads + tid];
+                    const int key = vi < 0 ? 0x7fffffff : vi;
+                    if (v > worst || (v == worst && key > worst_idx)) { worst = v; worst_idx = key; worst_slot = s2; }
+                }
+                thr = (worst == INFINITY) ? INFINITY : __double2float_ru(worst / link_len) * 1.000001f + err;
+            }
+        }
+        __syncthreads();
+    }
+    if (has_q) {
+        Partial *out = partial + (qi * splits + blockIdx.y) * kk;
+        for (int s = 0; s < kk; ++s) {
+            Partial p;
+            p.d2 = ld[s * kKnnThreads + tid];
+            p.idx = lidx[s * kKnnThreads + tid];
+            p.pad = 0;
+            out[s] = p;
+        }
+    }
+}
+
 }  // namespace
 
 struct b200mp_knn {
@@ -692,6 +821,11 @@ struct b200mp_knn {
     double *d_pts = nullptr;
     float *d_feat = nullptr;
     float cmax = 0.f;  // largest |c| seen (filter error bound)
+    double link_len = 1.0;          // chain metric: link length
+    int nl = 0;                     // chain metric: links padded to the kernel's template size
+    float *d_cum32 = nullptr;       // chain metric: fp32 cumulative end points [cap][2 nl]
+    double *d_link64 = nullptr;     // chain metric: fp64 per-link (cos, sin) [cap][2 dim]
+    unsigned char *d_dead = nullptr;  // chain metric: tombstones [cap]
     std::vector<double> h_pts;      // host mirror (nearestR / list / small paths)
     std::vector<unsigned char> alive;
     Scratch scratch;
@@ -724,6 +858,27 @@ int knn_reserve(b200mp_knn *k, long long want) {
         B200_CUDA(cudaMemcpyAsync(nf, k->d_feat, static_cast<size_t>(k->n) * k->nv * 4 * sizeof(float), cudaMemcpyDeviceToDevice, k->ctx->stream));
         B200_CUDA(cudaStreamSynchronize(k->ctx->stream));
     }
+    if (k->metric == B200MP_METRIC_CHAIN) {
+        float *nc = nullptr;
+        double *nl64 = nullptr;
+        unsigned char *nd = nullptr;
+        B200_CUDA(cudaMalloc(&nc, static_cast<size_t>(ncap) * 2 * k->nl * sizeof(float)));
+        B200_CUDA(cudaMalloc(&nl64, static_cast<size_t>(ncap) * 2 * k->dim * sizeof(double)));
+        B200_CUDA(cudaMalloc(&nd, static_cast<size_t>(ncap)));
+        B200_CUDA(cudaMemsetAsync(nd, 0, static_cast<size_t>(ncap), k->ctx->stream));
+        if (k->n > 0) {
+            B200_CUDA(cudaMemcpyAsync(nc, k->d_cum32, static_cast<size_t>(k->n) * 2 * k->nl * sizeof(float), cudaMemcpyDeviceToDevice, k->ctx->stream));
+            B200_CUDA(cudaMemcpyAsync(nl64, k->d_link64, static_cast<size_t>(k->n) * 2 * k->dim * sizeof(double), cudaMemcpyDeviceToDevice, k->ctx->stream));
+            B200_CUDA(cudaMemcpyAsync(nd, k->d_dead, static_cast<size_t>(k->n), cudaMemcpyDeviceToDevice, k->ctx->stream));
+        }
+        B200_CUDA(cudaStreamSynchronize(k->ctx->stream));
+        if (k->d_cum32) cudaFree(k->d_cum32);
+        if (k->d_link64) cudaFree(k->d_link64);
+        if (k->d_dead) cudaFree(k->d_dead);
+        k->d_cum32 = nc;
+        k->d_link64 = nl64;
+        k->d_dead = nd;
+    }
     if (k->d_pts) cudaFree(k->d_pts);
     if (k->d_feat) cudaFree(k->d_feat);
     k->d_pts = np;
@@ -734,6 +889,12 @@ int knn_reserve(b200mp_knn *k, long long want) {
 
 int knn_build_features(b200mp_knn *k, long long first, long long count, cudaStream_t st) {
     if (count <= 0) return B200MP_OK;
+    if (k->metric == B200MP_METRIC_CHAIN) {
+        knn_chain_tables_kernel<<<static_cast<unsigned>((count + 127) / 128), 128, 0, st>>>(k->d_pts, first, count, k->dim, k->nl, k->d_cum32, k->d_link64);
+        B200_CUDA(cudaGetLastError());
+        k->ctx->launches.fetch_add(1);
+        return B200MP_OK;
+    }
     const int thr = 256;
     knn_features_kernel<<<static_cast<unsigned>((count + thr - 1) / thr), thr, 0, st>>>(k->d_pts, first, count, k->dim, k->nv * 4, k->d_feat);
     B200_CUDA(cudaGetLastError());
@@ -757,15 +918,36 @@ int launch_tiled(b200mp_knn *k, const double *d_q, long long nq, const long long
     return B200MP_OK;
 }
 
+__global__ void knn_chain_all_distances_kernel(const double *__restrict__ link64, const unsigned char *__restrict__ dead, long long n, int nlinks,
+                                               double link_len, const double *__restrict__ qlink64, double *__restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double dx = 0.0, dy = 0.0, dist = 0.0;
+    for (int j = 0; j < nlinks; ++j) {
+        dx = __dadd_rn(dx, __dsub_rn(link64[i * 2 * nlinks + 2 * j], qlink64[2 * j]));
+        dy = __dadd_rn(dy, __dsub_rn(link64[i * 2 * nlinks + 2 * j + 1], qlink64[2 * j + 1]));
+        dist = __dadd_rn(dist, sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+    }
+    out[i] = dead[i] ? INFINITY : __dmul_rn(dist, link_len);
+}
+
 // exact distance of one query to every point, filtered by radius, sorted by (distance, id); caller holds ctx->mu
 int knn_radius_impl(b200mp_knn *k, const double *q, double radius, int64_t self, std::vector<std::pair<double, int64_t>> &sel) {
     B200_CUDA(cudaSetDevice(k->ctx->device));
     cudaStream_t st = k->ctx->stream;
-    int rc = k->ctx->scratch.reserve(static_cast<size_t>(k->n) * sizeof(double) + k->dim * sizeof(double) + 256);
+    int rc = k->ctx->scratch.reserve(static_cast<size_t>(k->n) * sizeof(double) + static_cast<size_t>(k->dim) * 3 * sizeof(double) +
+                                     static_cast<size_t>(k->nl) * 2 * sizeof(float) + 512);
     if (rc) return rc;
     double *d_all = reinterpret_cast<double *>(k->ctx->scratch.ptr);
     double *d_q = d_all + k->n;
     B200_CUDA(cudaMemcpyAsync(d_q, q, k->dim * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (k->metric == B200MP_METRIC_CHAIN) {
+        double *d_ql = d_q + k->dim;
+        float *d_qc = reinterpret_cast<float *>(d_ql + 2 * k->dim);
+        knn_chain_tables_kernel<<<1, 128, 0, st>>>(d_q, 0, 1, k->dim, k->nl, d_qc, d_ql);
+        knn_chain_all_distances_kernel<<<static_cast<unsigned>((k->n + 255) / 256), 256, 0, st>>>(k->d_link64, k->d_dead, k->n, k->dim, k->link_len, d_ql, d_all);
+        k->ctx->launches.fetch_add(1);
+    } else
     knn_all_distances_kernel<<<static_cast<unsigned>((k->n + 255) / 256), 256, 0, st>>>(k->d_pts, k->d_feat, k->nv * 4, k->n, k->dim, d_q, d_all);
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(1);
@@ -926,7 +1108,55 @@ int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, co
         default: rc = launch_cells<6>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st); break;
     }
     if (rc) return rc;
-    knn_merge_kernel<<<static_cast<unsigned>((nq * 32 + 255) / 256), 256, 0, st>>>(partial, nq, kq, kq, d_idx, d_dist, d_counts);
+    knn_merge_kernel<<<static_cast<unsigned>((nq * 32 + 255) / 256), 256, 0, st>>>(partial, nq, kq, kq, d_idx, d_dist, d_counts, 1);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    return B200MP_OK;
+}
+
+}  // namespace
+
+
+namespace {
+
+template <int NL>
+int launch_chain(b200mp_knn *k, const float *qcum, const double *qlink, long long nq, const long long *d_self, long long self_base, int use_self,
+                 int kk, Partial *d_partial, int splits, cudaStream_t st) {
+    const size_t smem = 2 * kChainTile * NL * sizeof(float2) + static_cast<size_t>(kk) * kKnnThreads * (sizeof(double) + sizeof(int));
+    auto kern = knn_chain_kernel<NL>;
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 grid(static_cast<unsigned>((nq + kKnnThreads - 1) / kKnnThreads), static_cast<unsigned>(splits));
+    kern<<<grid, kKnnThreads, smem, st>>>(reinterpret_cast<const float2 *>(k->d_cum32), k->d_link64, k->d_dead, k->n, k->dim, k->link_len,
+                                         reinterpret_cast<const float2 *>(qcum), qlink, nq, d_self, self_base, use_self, kk, d_partial, splits);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    return B200MP_OK;
+}
+
+int knn_query_chain(b200mp_knn *k, const double *d_q, long long nq, int kq, const long long *d_self, long long self_base, int use_self,
+                    long long *d_idx, double *d_dist, int *d_counts, cudaStream_t st) {
+    const long long qblocks = (nq + kKnnThreads - 1) / kKnnThreads;
+    long long splits = std::max<long long>(1, (2LL * k->ctx->sm_count + qblocks - 1) / qblocks);
+    splits = std::min<long long>(splits, std::max<long long>(1, (k->n + kChainTile - 1) / kChainTile));
+    splits = std::min<long long>(splits, 1024);
+    const size_t o_cum = 0;
+    const size_t o_link = align256(static_cast<size_t>(nq) * 2 * k->nl * sizeof(float));
+    const size_t o_part = o_link + align256(static_cast<size_t>(nq) * 2 * k->dim * sizeof(double));
+    int rc = k->scratch.reserve(o_part + static_cast<size_t>(nq) * splits * kq * sizeof(Partial) + 256);
+    if (rc) return rc;
+    float *qcum = reinterpret_cast<float *>(k->scratch.ptr + o_cum);
+    double *qlink = reinterpret_cast<double *>(k->scratch.ptr + o_link);
+    Partial *partial = reinterpret_cast<Partial *>(k->scratch.ptr + o_part);
+    knn_chain_tables_kernel<<<static_cast<unsigned>((nq + 127) / 128), 128, 0, st>>>(d_q, 0, nq, k->dim, k->nl, qcum, qlink);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    switch (k->nl) {
+        case 8: rc = launch_chain<8>(k, qcum, qlink, nq, d_self, self_base, use_self, kq, partial, static_cast<int>(splits), st); break;
+        case 20: rc = launch_chain<20>(k, qcum, qlink, nq, d_self, self_base, use_self, kq, partial, static_cast<int>(splits), st); break;
+        default: rc = launch_chain<32>(k, qcum, qlink, nq, d_self, self_base, use_self, kq, partial, static_cast<int>(splits), st); break;
+    }
+    if (rc) return rc;
+    knn_merge_kernel<<<static_cast<unsigned>((nq * 32 + 255) / 256), 256, 0, st>>>(partial, nq, static_cast<int>(splits) * kq, kq, d_idx, d_dist, d_counts, 0);
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(1);
     return B200MP_OK;
@@ -955,12 +1185,36 @@ int b200mp_knn_create(b200mp_ctx *ctx, int dim, int metric, b200mp_knn **out) {
     return B200MP_OK;
 }
 
+int b200mp_knn_create_chain(b200mp_ctx *ctx, int n_links, double link_length, b200mp_knn **out) {
+    if (!ctx || !out || n_links < 1 || !(link_length > 0.0)) return fail(B200MP_ERR_INVALID, "b200mp_knn_create_chain: bad argument");
+    if (n_links > 32) return fail(B200MP_ERR_CAPACITY, "b200mp_knn_create_chain: at most 32 links");
+    auto *k = new b200mp_knn();
+    k->ctx = ctx;
+    k->dim = n_links;
+    k->metric = B200MP_METRIC_CHAIN;
+    k->nv = 1;  // the L2 feature rows are not used by this metric
+    k->nl = n_links <= 8 ? 8 : (n_links <= 20 ? 20 : 32);
+    k->link_len = link_length;
+    k->use_index = false;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&k->d_rows_visited, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(k->d_rows_visited, 0, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaGetLastError();
+        delete k;
+        return fail(B200MP_ERR_CUDA, "b200mp_knn_create_chain: device allocation failed");
+    }
+    *out = k;
+    return B200MP_OK;
+}
+
 void b200mp_knn_destroy(b200mp_knn *k) {
     if (!k) return;
     cudaSetDevice(k->ctx->device);
     cudaStreamSynchronize(k->ctx->stream);
     if (k->d_pts) cudaFree(k->d_pts);
     if (k->d_feat) cudaFree(k->d_feat);
+    if (k->d_cum32) cudaFree(k->d_cum32);
+    if (k->d_link64) cudaFree(k->d_link64);
+    if (k->d_dead) cudaFree(k->d_dead);
     k->scratch.release();
     k->qscratch.release();
     k->index_mem.release();
@@ -990,6 +1244,10 @@ int b200mp_knn_clear(b200mp_knn *k) {
     k->n_removed = 0;
     k->cmax = 0.f;
     k->index_valid = false;
+    if (k->d_dead && k->cap > 0) {
+        cudaSetDevice(k->ctx->device);
+        cudaMemset(k->d_dead, 0, static_cast<size_t>(k->cap));
+    }
     k->h_pts.clear();
     k->alive.clear();
     return B200MP_OK;
@@ -1044,8 +1302,13 @@ int b200mp_knn_remove(b200mp_knn *k, int64_t id) {
     if (id < 0 || id >= k->n || k->alive.empty() || !k->alive[id]) return fail(B200MP_ERR_INVALID, "b200mp_knn_remove: id %lld not present", (long long)id);
     std::lock_guard<std::mutex> lk(k->ctx->mu);
     B200_CUDA(cudaSetDevice(k->ctx->device));
-    const float inf = INFINITY;  // tombstone: |c|^2 = +inf never passes the filter
-    B200_CUDA(cudaMemcpy(k->d_feat + id * k->nv * 4 + (k->nv * 4 - 1), &inf, sizeof(float), cudaMemcpyHostToDevice));
+    if (k->metric == B200MP_METRIC_CHAIN) {
+        const unsigned char one = 1;
+        B200_CUDA(cudaMemcpy(k->d_dead + id, &one, 1, cudaMemcpyHostToDevice));
+    } else {
+        const float inf = INFINITY;  // tombstone: |c|^2 = +inf never passes the filter
+        B200_CUDA(cudaMemcpy(k->d_feat + id * k->nv * 4 + (k->nv * 4 - 1), &inf, sizeof(float), cudaMemcpyHostToDevice));
+    }
     k->alive[id] = 0;
     k->n_removed++;
     k->index_valid = false;
@@ -1060,6 +1323,9 @@ int b200mp_knn_query_device(b200mp_knn *k, const double *d_q, int64_t nq, int kq
     B200_CUDA(cudaSetDevice(k->ctx->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : k->ctx->stream;
     const int kk = kq;  // survivors are evaluated exactly, so no guard band is needed
+    if (k->metric == B200MP_METRIC_CHAIN)
+        return knn_query_chain(k, d_q, nq, kq, reinterpret_cast<const long long *>(d_self_ids), self_base, exclude_self,
+                               reinterpret_cast<long long *>(d_idx), d_dist, d_counts, st);
     if (k->use_index && nq >= 4096 && k->n >= 32768 && kq <= 64 && k->n <= 0x7fffffffLL)
         return knn_query_indexed(k, d_q, nq, kq, reinterpret_cast<const long long *>(d_self_ids), self_base, exclude_self,
                                  reinterpret_cast<long long *>(d_idx), d_dist, d_counts, st);
@@ -1086,7 +1352,7 @@ int b200mp_knn_query_device(b200mp_knn *k, const double *d_q, int64_t nq, int kq
         const long long warps = cnt;
         knn_merge_kernel<<<static_cast<unsigned>((warps * 32 + thr - 1) / thr), thr, 0, st>>>(
             d_partial, cnt, static_cast<int>(splits) * kk, kq, reinterpret_cast<long long *>(d_idx) + q0 * kq, d_dist + q0 * kq,
-            d_counts ? d_counts + q0 : nullptr);
+            d_counts ? d_counts + q0 : nullptr, k->metric == B200MP_METRIC_L2 ? 1 : 0);
         B200_CUDA(cudaGetLastError());
         k->ctx->launches.fetch_add(1);
     }

@@ -79,10 +79,22 @@ def load_library():
     L.b200mp_prm_build.argtypes = [_vp, C.c_int, _vp, C.c_uint64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _i64,
                                    C.POINTER(RoadmapStats)]
     L.b200mp_knn_query_device_f32.argtypes = [_vp, _vp, _i64, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp]
+    L.b200mp_chain_horn_environment.argtypes = [C.c_int, C.c_double, _vp, C.POINTER(C.c_int)]
+    L.b200mp_chain_create.argtypes = [_vp, C.c_int, C.c_double, _vp, C.c_int, C.c_double, C.POINTER(_vp)]
+    L.b200mp_chain_destroy.argtypes = [_vp]
+    L.b200mp_chain_longest_valid_segment.argtypes = [_vp]
+    L.b200mp_chain_longest_valid_segment.restype = C.c_double
+    L.b200mp_chain_distance.argtypes = [_vp, _vp, _vp, _i64, _vp]
+    L.b200mp_chain_interpolate.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp]
+    L.b200mp_chain_validate_states.argtypes = [_vp, _vp, _i64, _vp]
+    L.b200mp_chain_check_motions.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp, _vp]
+    L.b200mp_chain_validate_states_device.argtypes = [_vp, _vp, _i64, _vp, _vp]
+    L.b200mp_chain_check_motions_device.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]
     L.b200mp_launch_count.argtypes = [_vp]
     L.b200mp_launch_count.restype = _i64
     L.b200mp_fp32_peak.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
     L.b200mp_knn_create.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(_vp)]
+    L.b200mp_knn_create_chain.argtypes = [_vp, C.c_int, C.c_double, C.POINTER(_vp)]
     L.b200mp_knn_destroy.argtypes = [_vp]
     L.b200mp_knn_clear.argtypes = [_vp]
     L.b200mp_knn_set_index.argtypes = [_vp, C.c_int]
@@ -330,12 +342,16 @@ class NearestNeighbors:
     """Mirror of ompl::NearestNeighbors<_T> (datastructures/NearestNeighbors.h:46-115) over point ids: add / remove /
     nearest / nearestK / nearestR / size / clear, results sorted ascending, double distances."""
 
-    def __init__(self, ctx: Context, dim: int, metric: int = 0):
+    def __init__(self, ctx: Context, dim: int, metric: int = 0, link_length: float = 0.0):
+        """metric 0: RealVectorStateSpace::distance; metric 1: KinematicChainSpace::distance with `link_length`."""
         self._L = load_library()
         self._ctx = ctx
         self.dim = dim
         h = _vp()
-        _check(self._L.b200mp_knn_create(ctx._h, dim, metric, C.byref(h)))
+        if metric == 1:
+            _check(self._L.b200mp_knn_create_chain(ctx._h, dim, link_length, C.byref(h)))
+        else:
+            _check(self._L.b200mp_knn_create(ctx._h, dim, metric, C.byref(h)))
         self._h = h
 
     def close(self):
@@ -412,3 +428,77 @@ class NearestNeighbors:
                      self_ids_ptr: int = 0, counts_ptr: int = 0, stream: int = 0):
         _check(self._L.b200mp_knn_query_device(self._h, q_ptr, nq, k, self_ids_ptr or None, self_base, int(exclude_self), idx_ptr,
                                                dist_ptr, counts_ptr or None, stream or None))
+
+
+def horn_environment(d: int, eps: float) -> np.ndarray:
+    """createHornEnvironment(d, eps) (demos/KinematicChain.h:279-315) -> segments [2(d-1)][4]; host only."""
+    L = load_library()
+    n = C.c_int()
+    _check(L.b200mp_chain_horn_environment(d, eps, None, C.byref(n)))
+    out = np.zeros((n.value, 4), np.float64)
+    _check(L.b200mp_chain_horn_environment(d, eps, out.ctypes.data, C.byref(n)))
+    return out
+
+
+class KinematicChain:
+    """Planar n-link chain of demos/KinematicChain.h on the GPU (fp64): KinematicChainSpace::distance / interpolate,
+    KinematicChainValidityChecker::isValid and DiscreteMotionValidator::checkMotion over it."""
+
+    def __init__(self, ctx: Context, n_links: int, link_length: float, segments, lvs_fraction: float = 0.01):
+        self._L = load_library()
+        self._ctx = ctx
+        self.n = n_links
+        seg = _host(segments, np.float64).reshape(-1, 4)
+        h = _vp()
+        _check(self._L.b200mp_chain_create(ctx._h, n_links, link_length, seg.ctypes.data if len(seg) else None, len(seg), lvs_fraction,
+                                           C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._L.b200mp_chain_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def longest_valid_segment(self) -> float:
+        return float(self._L.b200mp_chain_longest_valid_segment(self._h))
+
+    def distance(self, a, b) -> np.ndarray:
+        a, b = _host(a, np.float64).reshape(-1, self.n), _host(b, np.float64).reshape(-1, self.n)
+        out = np.zeros(len(a))
+        _check(self._L.b200mp_chain_distance(self._h, a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data))
+        return out
+
+    def interpolate(self, a, b, t) -> np.ndarray:
+        a, b = _host(a, np.float64).reshape(-1, self.n), _host(b, np.float64).reshape(-1, self.n)
+        tt = _host(np.broadcast_to(t, (len(a),)), np.float64)
+        out = np.zeros_like(a)
+        _check(self._L.b200mp_chain_interpolate(self._h, a.ctypes.data, b.ctypes.data, tt.ctypes.data, len(a), out.ctypes.data))
+        return out
+
+    def validate_states(self, q) -> np.ndarray:
+        q = _host(q, np.float64).reshape(-1, self.n)
+        out = np.zeros(len(q), np.uint8)
+        _check(self._L.b200mp_chain_validate_states(self._h, q.ctypes.data, len(q), out.ctypes.data))
+        return out
+
+    def check_motions(self, a, b):
+        """-> (valid u8, last_valid_t f64 (-1 when valid), nd i32)"""
+        a, b = _host(a, np.float64).reshape(-1, self.n), _host(b, np.float64).reshape(-1, self.n)
+        out = np.zeros(len(a), np.uint8)
+        last = np.zeros(len(a))
+        nd = np.zeros(len(a), np.int32)
+        _check(self._L.b200mp_chain_check_motions(self._h, a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data, last.ctypes.data, nd.ctypes.data))
+        return out, last, nd
+
+    def validate_states_ptr(self, q_ptr: int, m: int, valid_ptr: int, stream: int = 0):
+        _check(self._L.b200mp_chain_validate_states_device(self._h, q_ptr, m, valid_ptr, stream or None))
+
+    def check_motions_ptr(self, a_ptr: int, b_ptr: int, m: int, valid_ptr: int, last_ptr: int = 0, nd_ptr: int = 0, stream: int = 0):
+        _check(self._L.b200mp_chain_check_motions_device(self._h, a_ptr, b_ptr, m, valid_ptr, last_ptr or None, nd_ptr or None, stream or None))

@@ -74,7 +74,37 @@ def cloud_case(name, robot, radii, n_pts, scene, n_states, n_motions, seed):
     print(f"{name}: states valid {sv.mean():.3f}, motions valid {mv.mean():.3f}, affordance records {t['aff'].shape[1] // 8}")
 
 
+def chain_case():
+    """Planar 20-link chain in the horn environment (KinematicChainBenchmark.cpp:48-49): answers of the UNMODIFIED
+    demos/KinematicChain.h + DiscreteMotionValidator.cpp (oracle/_ref/libref_chain.so)."""
+    from oracle import chain
+    n = 20
+    env = chain.RefChain.horn(n, np.log(n) / n)
+    R = chain.RefChain(n, 1.0 / n, env)
+    rng = np.random.default_rng(606)
+    q = rng.uniform(-np.pi, np.pi, (6000, n))
+    q[:3000] *= rng.uniform(0.02, 0.35, (3000, 1))      # gently curled chains: mostly valid
+    # chains that follow the horn (each wall segment turns by pi / n), with growing noise
+    q[3000:5000] = np.pi / n * rng.uniform(0.5, 1.5, (2000, 1)) + rng.normal(scale=1.0, size=(2000, n)) * rng.uniform(0.0, 0.12, (2000, 1))
+    q[3000:5000, 0] = rng.normal(scale=0.05, size=2000)
+    sv = R.validate_states(q)
+    ok = q[sv == 1]
+    a = ok[rng.integers(0, len(ok), 1500)]
+    b = np.concatenate([ok[rng.integers(0, len(ok), 1000)], q[rng.integers(0, len(q), 500)]])
+    b[:300] = a[:300] + rng.normal(scale=0.02, size=(300, n))   # short motions
+    v0, _, nd = R.check_motions(a, b, 0)
+    v1, last, _ = R.check_motions(a, b, 1)
+    t = rng.uniform(0, 1, len(a))
+    np.savez_compressed(os.path.join(HERE, "chain.npz"), n=np.array(n), env=env, lvs=np.array(R.longest_valid_segment), states=q, states_valid=sv,
+                        a=a, b=b, motions_valid=v0, motions_valid_form1=v1, last_t=last, nd=nd, dist=R.distance(a, b), t=t,
+                        interp=R.interpolate(a, b, t))
+    print(f"chain: states valid {sv.mean():.3f}, motions valid {v0.mean():.3f}, nd mean {nd.mean():.1f} max {nd.max()}")
+
+
 def main():
+    if "--chain" in sys.argv:
+        chain_case()
+        return
     if "--cloud" in sys.argv:
         cloud_case("fetch_cloud", "fetch", (0.012, 0.24, 0.0025), 1500,
                    synth.clutter_scene(11, 20, 20, rho_lo=0.6, rho_hi=1.4, z_lo=0.2, z_hi=1.6), 1500, 800, 505)
