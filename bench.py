@@ -12,8 +12,12 @@ length puts the reference at n = 8 rakes = 64 states. One "step" = one pass of t
             peak = FP32 FMA throughput measured on this GPU by b200mp_fp32_peak (MEASURED_PEAKS.json has no FP32 entry)
   cpu_baseline   the reference's own CPU path (oracle/_ref, unmodified VAMP) or the port, all host threads, bounded sample
 
+  roadmap   second half of BASELINE's metric: wall time to build a 2^20-sample, k = 16 Panda PRM roadmap in the same scene on
+            the N GPUs of the run (sample -> kNN -> edge list -> edge validity; NCCL all-gathers between phases), max over ranks
+
 `--impl reference` times the reference CPU implementation instead (rank 0 only).
-Multi-GPU: the path shards by motions with no data-path collective -> weak scaling, every rank validates its own 2^20 motions.
+Multi-GPU: motion validation shards by motions with no data-path collective -> weak scaling, every rank validates its own 2^20
+motions; the roadmap build is a fixed-size job split over the ranks (strong scaling, reported inside `roadmap`).
 """
 from __future__ import annotations
 
@@ -126,6 +130,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--roadmap-n", type=int, default=1 << 20, help="samples of the PRM roadmap build (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -209,27 +214,50 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- roadmap build (all ranks): BASELINE config 3, same scene
+    roadmap = None
+    if args.roadmap_n > 0:
+        from ompl_b200.roadmap import EngineBackend, RoadmapBuilder
+        builder = RoadmapBuilder(EngineBackend(ctx, env, "panda"))
+        builder.build(min(args.roadmap_n, 1 << 16), 16, 7)        # warm-up (allocations, NCCL channels)
+        barrier()
+        l0 = ctx.launch_count
+        rm = builder.build(args.roadmap_n, 16, 42)
+        barrier()
+        st = dict(rm.stats)
+        st["gpu_launches"] = int(ctx.launch_count - l0)
+        keys = ["ms_sample", "ms_knn", "ms_edges", "ms_validate", "ms_gather", "ms_total"]
+        t = torch.tensor([st[k] for k in keys], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for k, v in zip(keys, t.tolist()):
+            st[k] = v
+        roadmap = {"workload": f"PRM roadmap: {args.roadmap_n} valid Panda samples, k=16 (self excluded), undirected de-duplicated edges, "
+                               "resolution 32, C2 scene", "n_gpus": world, "scaling": "strong", "build_ms": st["ms_total"], **st}
+        del rm
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline on the all-valid sub-workload + CPU baseline (rank 0, N = 1 semantics)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(q0.nbytes + q1.nbytes), "d2h_bytes_per_step": int(M_EDGES)},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "valid_fraction": valid_frac,
             "states_per_sec_upper": value * 64}
+    if roadmap is not None:
+        line["roadmap"] = roadmap
     if world == 1:
+        # ---- roofline of the validation kernel on the all-valid sub-workload (no early exit hides work) + CPU baseline
         from oracle import port
         pe = synth.fill_env(port.PortEnvironment(), scene)
         valid_idx = np.nonzero(dv.cpu().numpy() == 1)[0]
         peak = ctx.fp32_peak_tflops(4096)
-        # W_ref per valid edge from the instrumented oracle on a sample
         samp = valid_idx[:512]
         _, fl = pe.validate_motions("panda", q0[samp], q1[samp], nthreads=os.cpu_count() or 1, want_flops=True)
-        w_ref_edge = float(fl.mean())
+        w_ref_edge = float(fl.mean())     # flops the reference's sequential semantics execute per valid motion (oracle walker)
         rep = np.resize(valid_idx, 1 << 17)
         a0, a1 = torch.from_numpy(q0[rep]).to(dev), torch.from_numpy(q1[rep]).to(dev)
         av = torch.zeros(len(rep), dtype=torch.uint8, device=dev)
@@ -237,13 +265,29 @@ def main():
         l1 = ctx.launch_count
         ms_av = device_pass(args.steps, a0, a1, av, len(rep)) / args.steps
         assert ctx.launch_count - l1 == args.steps
-        achieved = w_ref_edge * len(rep) / (ms_av * 1e-3) / 1e12
-        line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                            "traffic": None, "kernel": "validate_motions_kernel<Panda>",
-                            "workload": f"all-valid sub-workload: {len(valid_idx)} oracle-valid motions of the batch tiled to 2^17",
-                            "work_per_launch_flops": w_ref_edge * len(rep), "w_ref_flops_per_edge": w_ref_edge,
+        assert bool(av.all()), "all-valid sub-workload must validate as valid"
+        w_ref = w_ref_edge * len(rep) / (ms_av * 1e-3) / 1e12
+        # executed flops per launch of exactly this workload, counted by ncu (profiles/validate_flops.json)
+        w_exec_launch, src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "validate_flops.json")) as f:
+                pj = json.load(f)
+            if pj.get("motions") == len(rep) and pj.get("unique_valid") == int(len(valid_idx)):
+                w_exec_launch, src = float(pj["flops_per_launch"]), pj.get("source")
+        except Exception:
+            pass
+        achieved = (w_exec_launch / (ms_av * 1e-3) / 1e12) if w_exec_launch else w_ref
+        line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                            "kernel": "validate_motions_kernel<Panda, sorted, grid>",
+                            "achieved_is": ("executed FP32 flops (ncu-counted FFMA x2 + FADD + FMUL per launch of this workload: " + str(src) + ")")
+                            if w_exec_launch else "W_ref (no ncu flop count for this workload found)",
+                            "w_ref_tflops": w_ref, "w_ref_frac": w_ref / peak, "w_ref_flops_per_edge": w_ref_edge,
+                            "note": "W_ref = flops the reference's sequential scan semantics execute for the same motions (oracle-counted); the "
+                                    "grid-culled kernel reaches the same decisions with far fewer tests, so W_ref/time may exceed the FP32 peak",
+                            "workload": f"all-valid sub-workload: {len(valid_idx)} valid motions of the batch tiled to 2^17",
                             "ms_per_launch": ms_av, "states_per_sec": len(rep) * 64 / (ms_av * 1e-3),
-                            "peak_source": "measured: b200mp_fp32_peak FFMA microbenchmark on this GPU (nominal 148*128*2*1.965 GHz = 74.4)"}
+                            "peak_source": "measured: b200mp_fp32_peak FFMA microbenchmark on this GPU (MEASURED_PEAKS.json has no FP32 "
+                                           "entry; nominal 148*128*2*1.965 GHz = 74.4)"}
         if not args.no_cpu_baseline:
             chk, kind = checker_env(scene)
             cores = os.cpu_count() or 1
@@ -256,6 +300,15 @@ def main():
             mism = int((got != want).sum())
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"first 2^18 of the 2^20 motions, all host threads; {mism} decisions differ from the GPU"}
+            if roadmap is not None:
+                # CPU figure for the roadmap's kNN phase: the reference-faithful exhaustive search on a bounded query sample
+                nq = 512
+                states = synth.uniform_states("panda", 1 << 18, 5).astype(np.float64)
+                t0 = time.perf_counter()
+                port.knn(states, states[:nq], 16, nthreads=cores)
+                dt = time.perf_counter() - t0
+                line["roadmap"]["cpu_knn"] = {"queries_per_s_at_2^18": nq / dt, "cores": cores, "kind": "port",
+                                              "sample": f"{nq} queries against 2^18 states (cost is linear in the database size)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,14 +1,18 @@
 #!/usr/bin/env python3
-"""ncu target (GPU box): a handful of validation launches of known composition.
-launch 0: warm-up (C2 mixed, 2^14 motions)   launch 1: C2 mixed 2^18   launch 2: C2 all-valid 2^15
-launch 3: cage all-valid 2^16               launch 4: C2 states 2^20 uniform random"""
+"""ncu target (GPU box): the bench's own workloads as a short, fixed launch sequence.
+  validate_motions launches: #0 warm-up (2^14 mixed), #1 C2 mixed 2^20 (the bench step), #2 C2 all-valid 2^17 (the roofline launch)
+  then one single-GPU roadmap build (n = 2^18, k = 16): sample / validate_states / compaction / kNN index + cells / edges / validate
+Prints the facts profiles/validate_flops.json is keyed on (motions, unique_valid)."""
+import json
 import os
 import sys
 
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
 import ompl_b200  # noqa: E402
 from ompl_b200 import synth  # noqa: E402
 
@@ -25,16 +29,15 @@ def run(env, q0, q1):
     return out.cpu().numpy()
 
 
-c2 = synth.fill_env(ompl_b200.Environment(ctx), synth.clutter_scene(1234, 500, 500))
-cage = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
-q0, q1 = synth.fixed_length_edges("panda", 1 << 18, 1234)
-run(c2, q0[:1 << 14], q1[:1 << 14])
-v = run(c2, q0, q1)
-idx = np.resize(np.nonzero(v == 1)[0], 1 << 15)
-run(c2, q0[idx], q1[idx])
-vc = ctx.validate_motions("panda", cage, q0, q1)   # host path: launch not on our stream but still profiled (launch 3)
-idc = np.resize(np.nonzero(vc == 1)[0], 1 << 16)
-run(cage, q0[idc], q1[idc])
-q = synth.uniform_states("panda", 1 << 20, 3)
-ctx.validate_states("panda", c2, q)
-print("valid C2", v.mean(), "valid cage", vc.mean())
+scene, q0, q1 = bench.make_inputs(0)
+env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+run(env, q0[:1 << 14], q1[:1 << 14])
+v = run(env, q0, q1)
+valid_idx = np.nonzero(v == 1)[0]
+rep = np.resize(valid_idx, 1 << 17)
+va = run(env, q0[rep], q1[rep])
+assert va.all()
+if "--no-roadmap" not in sys.argv:
+    r = ctx.prm_build("panda", env, 1 << 18, 16, 42, want_weights=False)
+    print(json.dumps(r["stats"]))
+print(json.dumps({"motions": int(len(rep)), "unique_valid": int(len(valid_idx)), "mixed_valid_fraction": float(v.mean())}))
