@@ -163,6 +163,12 @@ int b200mp_knn_query_device(b200mp_knn *knn, const double *d_q, int64_t nq, int 
 /* Same with fp32 queries (converted exactly to fp64 on the device); query i skips id self_base + i when exclude_self. */
 int b200mp_knn_query_device_f32(b200mp_knn *knn, const float *d_q, int64_t nq, int k, int64_t self_base, int exclude_self,
                                 int64_t *d_idx, double *d_dist, int *d_counts, void *stream);
+/* Multi-GPU query sharing: computes the rows of part `part` of `n_parts` disjoint subsets that together cover the nq
+ * queries (whole index cells per part when the cell index is used, contiguous blocks otherwise) and leaves all other
+ * rows of d_idx / d_dist untouched, so that tables pre-filled with -1 / +inf combine across ranks with an element-wise
+ * max / min reduction. Every rank must hold the same database. */
+int b200mp_knn_query_part_device_f32(b200mp_knn *knn, const float *d_q, int64_t nq, int k, int64_t self_base, int exclude_self, int part,
+                                     int n_parts, int64_t *d_idx, double *d_dist, void *stream);
 /* nearestR: all points with distance <= radius, ascending; *count = how many exist, at most cap are written.
  * radius = +inf gives the exhaustive sorted list used for nearestK with k >= size. */
 int b200mp_knn_radius(b200mp_knn *knn, const double *q, double radius, int64_t *idx, double *dist, int64_t cap, int64_t *count);
@@ -203,7 +209,8 @@ typedef struct b200mp_roadmap_stats {
 int b200mp_prm_sample_device(b200mp_ctx *ctx, int robot, const b200mp_env *env, uint64_t seed, uint64_t cand_first, int64_t cand_count,
                              float *d_states, int64_t capacity, int64_t *n_valid, void *stream);
 /* Phase 3. From the neighbour table d_nbr[n][k] of ALL states (ids, -1 = none) keep, for the queries
- * q_first .. q_first + q_count - 1, edge (i, j = d_nbr[i][s]) when i < j or i is not listed by j; written in (i, s)
+ * q_first .. q_first + q_count - 1, edge (i, j = d_nbr[i][s]) when j does not list i, or when it does and i is the pair's
+ * designated keeper (the lower index if i + j is even, the higher if odd); written in (i, s)
  * order as (min, max) index pairs to d_edges[capacity][2], with d_weights[e] = d_dist_local[(i - q_first) * k + s]
  * (both may be NULL). Synchronises `stream`. */
 int b200mp_prm_edges_device(b200mp_ctx *ctx, const int64_t *d_nbr, const double *d_dist_local, int64_t n, int k, int64_t q_first,

@@ -201,10 +201,12 @@ knn_tiled_kernel(const float4 *__restrict__ feat, const double *__restrict__ pts
 // finds the smallest entry strictly greater than the last one emitted (entries are unique by idx) with a lane-local
 // scan followed by a warp-shuffle arg-min, so nothing has to be retired or sorted in memory. dist = sqrt(d2).
 __global__ void knn_merge_kernel(const Partial *__restrict__ partial, long long nq, int n_cand, int k, long long *__restrict__ idx,
-                                 double *__restrict__ dist, int *__restrict__ counts, int take_sqrt) {
+                                 double *__restrict__ dist, int *__restrict__ counts, int take_sqrt, const int *__restrict__ qcell = nullptr,
+                                 int parts = 1, int part = 0) {
     const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nq) return;
+    if (qcell != nullptr && qcell[w] % parts != part) return;  // row belongs to another part: left untouched
     const Partial *p = partial + w * n_cand;
     constexpr int kPer = 8;  // first 256 candidates live in registers; any further ones are re-read each round
     double d[kPer];
@@ -398,9 +400,9 @@ __global__ void knn_permute_kernel(const float4 *__restrict__ feat, const double
 }
 
 // blocks needed per query cell: ceil(#queries in the cell / kCellThreads)
-__global__ void knn_cell_blocks_kernel(const int *__restrict__ q_start, int P, int *__restrict__ nblk) {
+__global__ void knn_cell_blocks_kernel(const int *__restrict__ q_start, int P, int *__restrict__ nblk, int parts, int part) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < P) nblk[c] = (q_start[c + 1] - q_start[c] + kCellThreads - 1) / kCellThreads;
+    if (c < P) nblk[c] = (c % parts == part) ? (q_start[c + 1] - q_start[c] + kCellThreads - 1) / kCellThreads : 0;
 }
 
 __global__ void knn_query_order_kernel(const int *__restrict__ cell, const int *__restrict__ pos, long long nq, int *__restrict__ order,
@@ -465,12 +467,12 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
     if (static_cast<int>(blockIdx.x) >= blk_start[P]) return;
     int own;
     {
-        int lo_c = 0, hi_c = P;  // last cell with blk_start[c] <= blockIdx.x
+        int lo_c = 0, hi_c = P;  // the cell c with blk_start[c] <= blockIdx.x < blk_start[c + 1] (cells without blocks are skipped)
         while (hi_c - lo_c > 1) {
             const int mid = (lo_c + hi_c) >> 1;
             if (blk_start[mid] <= static_cast<int>(blockIdx.x)) lo_c = mid; else hi_c = mid;
         }
-        own = lo_c;
+        own = lo_c;  // blk_start[own] <= blockIdx.x < blk_start[own + 1]: cells without blocks can never satisfy this
     }
     const long long qs = static_cast<long long>(q_start[own]) + static_cast<long long>(blockIdx.x - blk_start[own]) * kCellThreads + tid;
     const bool has_q = qs < q_start[own + 1];
@@ -1064,7 +1066,7 @@ int launch_cells(b200mp_knn *k, const double *d_q, const int *q_order, const int
 
 // large query batches against a large database: cell-pruned exact search
 int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, const long long *d_self, long long self_base, int use_self,
-                      long long *d_idx, double *d_dist, int *d_counts, cudaStream_t st) {
+                      long long *d_idx, double *d_dist, int *d_counts, cudaStream_t st, int parts = 1, int part = 0) {
     int rc;
     if (!k->index_valid || k->index_n != k->n)
         if ((rc = knn_build_index(k, st))) return rc;
@@ -1098,7 +1100,7 @@ int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, co
     if ((rc = knn_assign(k, qfeat, nq, cell, st))) return rc;
     if ((rc = knn_cell_sort(k, cell, nq, counts, start, cursor, pos, st))) return rc;
     knn_query_order_kernel<<<qblocks, 256, 0, st>>>(cell, pos, nq, order, csort);
-    knn_cell_blocks_kernel<<<(P + 255) / 256, 256, 0, st>>>(start, P, nblk);
+    knn_cell_blocks_kernel<<<(P + 255) / 256, 256, 0, st>>>(start, P, nblk, parts, part);
     knn_cell_scan_kernel<<<1, 1024, 0, st>>>(nblk, P, bstart, cursor);
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(3);
@@ -1108,7 +1110,8 @@ int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, co
         default: rc = launch_cells<6>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st); break;
     }
     if (rc) return rc;
-    knn_merge_kernel<<<static_cast<unsigned>((nq * 32 + 255) / 256), 256, 0, st>>>(partial, nq, kq, kq, d_idx, d_dist, d_counts, 1);
+    knn_merge_kernel<<<static_cast<unsigned>((nq * 32 + 255) / 256), 256, 0, st>>>(partial, nq, kq, kq, d_idx, d_dist, d_counts, 1,
+                                                                                     parts > 1 ? cell : nullptr, parts, part);
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(1);
     return B200MP_OK;
@@ -1373,6 +1376,32 @@ int b200mp_knn_query_device_f32(b200mp_knn *k, const float *d_q, int64_t nq, int
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(1);
     return b200mp_knn_query_device(k, d_q64, nq, kq, nullptr, self_base, exclude_self, d_idx, d_dist, d_counts, st);
+}
+
+int b200mp_knn_query_part_device_f32(b200mp_knn *k, const float *d_q, int64_t nq, int kq, int64_t self_base, int exclude_self, int part, int n_parts,
+                                     int64_t *d_idx, double *d_dist, void *stream) {
+    if (!k || nq < 0 || kq < 1 || n_parts < 1 || part < 0 || part >= n_parts || (nq > 0 && (!d_q || !d_idx || !d_dist)))
+        return fail(B200MP_ERR_INVALID, "b200mp_knn_query_part_device_f32: bad argument");
+    if (nq == 0) return B200MP_OK;
+    if (kq > kMaxK) return fail(B200MP_ERR_CAPACITY, "b200mp_knn_query_part_device_f32: k %d > %d", kq, kMaxK);
+    B200_CUDA(cudaSetDevice(k->ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : k->ctx->stream;
+    const bool indexed = k->metric == B200MP_METRIC_L2 && k->use_index && nq >= 4096 && k->n >= 32768 && kq <= 64 && k->n <= 0x7fffffffLL;
+    if (!indexed) {
+        // contiguous share of the queries through the ordinary path
+        const int64_t per = (nq + n_parts - 1) / n_parts, b = std::min<int64_t>(per * part, nq), cnt = std::min<int64_t>(per, nq - b);
+        if (cnt <= 0) return B200MP_OK;
+        return b200mp_knn_query_device_f32(k, d_q + b * k->dim, cnt, kq, self_base + b, exclude_self, d_idx + b * kq, d_dist + b * kq, nullptr, st);
+    }
+    const long long cnt = static_cast<long long>(nq) * k->dim;
+    int rc = k->qscratch.reserve(static_cast<size_t>(cnt) * sizeof(double));
+    if (rc) return rc;
+    double *d_q64 = reinterpret_cast<double *>(k->qscratch.ptr);
+    knn_f32_to_f64_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(d_q, cnt, d_q64);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    // queries are shared out by the index cell they fall into (cell c -> part c mod n_parts): every part works on whole cells
+    return knn_query_indexed(k, d_q64, nq, kq, nullptr, self_base, exclude_self, reinterpret_cast<long long *>(d_idx), d_dist, nullptr, st, n_parts, part);
 }
 
 int b200mp_knn_query(b200mp_knn *k, const double *q, int64_t nq, int kq, const int64_t *self_ids, int64_t *idx, double *dist, int *counts) {

@@ -79,6 +79,7 @@ def load_library():
     L.b200mp_prm_build.argtypes = [_vp, C.c_int, _vp, C.c_uint64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _i64,
                                    C.POINTER(RoadmapStats)]
     L.b200mp_knn_query_device_f32.argtypes = [_vp, _vp, _i64, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp]
+    L.b200mp_knn_query_part_device_f32.argtypes = [_vp, _vp, _i64, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
     L.b200mp_chain_horn_environment.argtypes = [C.c_int, C.c_double, _vp, C.POINTER(C.c_int)]
     L.b200mp_chain_create.argtypes = [_vp, C.c_int, C.c_double, _vp, C.c_int, C.c_double, C.POINTER(_vp)]
     L.b200mp_chain_destroy.argtypes = [_vp]
@@ -423,6 +424,11 @@ class NearestNeighbors:
                          exclude_self: bool = False, counts_ptr: int = 0, stream: int = 0):
         _check(self._L.b200mp_knn_query_device_f32(self._h, q_ptr, nq, k, self_base, int(exclude_self), idx_ptr, dist_ptr,
                                                    counts_ptr or None, stream or None))
+
+    def query_part_device_f32(self, q_ptr: int, nq: int, k: int, idx_ptr: int, dist_ptr: int, part: int, n_parts: int, self_base: int = 0,
+                              exclude_self: bool = False, stream: int = 0):
+        _check(self._L.b200mp_knn_query_part_device_f32(self._h, q_ptr, nq, k, self_base, int(exclude_self), part, n_parts, idx_ptr,
+                                                        dist_ptr, stream or None))
 
     def query_device(self, q_ptr: int, nq: int, k: int, idx_ptr: int, dist_ptr: int, self_base: int = 0, exclude_self: bool = False,
                      self_ids_ptr: int = 0, counts_ptr: int = 0, stream: int = 0):

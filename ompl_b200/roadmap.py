@@ -7,9 +7,11 @@ and the edges its queries keep; the exchange steps are the ones SURVEY.md 8(e) l
   1. sample     every rank validates a contiguous slice of the candidate stream; all-gather of the per-rank counts and
                 of the valid states (padded to the largest count) -> every rank holds all n states, in stream order.
                 The states are the first n valid candidates of the stream, independent of G.
-  2. kNN        each rank searches the full set for its own block (self excluded)
-  3. all-gather of the neighbour table (the de-duplication rule needs the lists of remote states)
-  4. edges      each rank keeps (i, j) for its i when i < j or i is not in kNN(j); validates them
+  2. kNN        each rank answers a share of ALL queries (whole cells of the kNN index, so its blocks stay full) against the
+                full set, self excluded, into [n][k] tables pre-filled with -1 / +inf
+  3. all-reduce (max on ids, min on distances) merges the tables: every rank holds the neighbour lists of all states
+  4. edges      each rank keeps, for the states i of its block, (i, j) when j does not list i or i is the pair's keeper
+                (lower index if i + j even, higher if odd: balanced counts); validates them
   5. all-gather of counts, edges, weights and validity -> every rank holds the whole roadmap, same order for any G
 
 All compute goes through the C ABI of the CUDA engine (`EngineBackend`); torch is used for device buffers and the NCCL
@@ -18,6 +20,7 @@ checker-backed one); there is no CPU fallback in this package.
 """
 from __future__ import annotations
 
+import contextlib
 import time
 from dataclasses import dataclass, field
 
@@ -54,24 +57,30 @@ class EngineBackend:
         info = robot_info(robot)
         self.max_norm = float(np.linalg.norm(np.maximum(np.abs(info["lo"]), np.abs(info["hi"])).astype(np.float64)))
         self._knn = None
+        # One explicit (non-default) stream carries the engine kernels, the torch copies and the NCCL collectives of a
+        # build, so they are ordered with respect to each other. (Handing the C ABI the default stream's handle, 0, would
+        # mean "the context's own stream" there and break that ordering.)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def stream_context(self):
+        return torch.cuda.stream(self.stream)
 
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return self.stream.cuda_stream
 
     def sample(self, seed: int, first: int, count: int, out: torch.Tensor) -> int:
         return self.ctx.prm_sample_ptr(self.robot, self.env, seed, first, count, out.data_ptr(), out.shape[0], self._stream())
 
-    def neighbors(self, states: torch.Tensor, q_first: int, q_count: int, k: int):
+    def neighbors_part(self, states: torch.Tensor, k: int, part: int, parts: int, idx: torch.Tensor, dst: torch.Tensor):
+        """Fill the rows of this rank's share of ALL queries (every state against the whole set, self excluded) into the
+        [n][k] tables idx / dst; rows of other shares stay untouched (b200mp_knn_query_part_device_f32)."""
         if self._knn is not None:
             self._knn.close()
+        n = states.shape[0]
         self._knn = NearestNeighbors(self.ctx, self.dim)
-        self._knn.add_device_f32(states.data_ptr(), states.shape[0], self.max_norm, self._stream())
-        idx = torch.full((q_count, k), -1, dtype=torch.int64, device=self.device)
-        dst = torch.full((q_count, k), float("inf"), dtype=torch.float64, device=self.device)
-        if q_count:
-            self._knn.query_device_f32(states[q_first:].data_ptr(), q_count, k, idx.data_ptr(), dst.data_ptr(), self_base=q_first,
-                                       exclude_self=True, stream=self._stream())
-        return idx, dst
+        self._knn.add_device_f32(states.data_ptr(), n, self.max_norm, self._stream())
+        self._knn.query_part_device_f32(states.data_ptr(), n, k, idx.data_ptr(), dst.data_ptr(), part, parts, self_base=0, exclude_self=True,
+                                        stream=self._stream())
 
     def edges(self, nbr: torch.Tensor, dist_local: torch.Tensor, q_first: int, q_count: int):
         n, k = nbr.shape
@@ -123,6 +132,13 @@ class RoadmapBuilder:
             torch.cuda.synchronize(self.backend.device)
 
     def build(self, n: int, k: int, seed: int, resolution: int = 0, candidates_per_round: int | None = None) -> Roadmap:
+        ctx = self.backend.stream_context() if hasattr(self.backend, "stream_context") else contextlib.nullcontext()
+        with ctx:
+            rm = self._build(n, k, seed, resolution, candidates_per_round)
+        self._sync()
+        return rm
+
+    def _build(self, n, k, seed, resolution, candidates_per_round) -> Roadmap:
         be, G, g = self.backend, self.world, self.rank
         dev, dim = be.device, be.dim
         t = [time.perf_counter()]
@@ -151,7 +167,7 @@ class RoadmapBuilder:
                 rate = max(1e-4, have / drawn)
                 per_round = max(1 << 16, int(1.05 * (n - have) / rate))
         mark()
-        # ---- 2. kNN of the local query block against all states
+        # ---- 2. kNN: every rank answers its share of the queries (whole index cells), tables pre-filled with -1 / +inf
         B = -(-n // G)
         q_first = min(g * B, n)
         q_count = min(B, n - q_first)
@@ -160,19 +176,16 @@ class RoadmapBuilder:
             empty = torch.empty((0, 2), dtype=torch.int32, device=dev)
             return Roadmap(states, empty, torch.empty(0, dtype=torch.uint8, device=dev), torch.empty(0, dtype=torch.float64, device=dev),
                            dict(n_states=n, n_candidates=drawn, n_edges=0, n_valid_edges=0, world=G))
-        idx, dst = be.neighbors(states, q_first, q_count, kk)
+        nbr = torch.full((n, kk), -1, dtype=torch.int64, device=dev)
+        dst = torch.full((n, kk), float("inf"), dtype=torch.float64, device=dev)
+        be.neighbors_part(states, kk, g, G, nbr, dst)
         mark()
-        # ---- 3. neighbour table of every state (padded block all-gather)
+        # ---- 3. neighbour table of every state: element-wise max / min over the ranks' partially filled tables
         if G > 1:
-            pad = torch.full((B, kk), -1, dtype=torch.int64, device=dev)
-            pad[:q_count] = idx
-            nbr = torch.empty((G * B, kk), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(nbr, pad, group=self.group)
-            nbr = nbr[:n].contiguous()
-        else:
-            nbr = idx
-        # ---- 4. local edge list and its validity
-        e_loc, w_loc = be.edges(nbr, dst, q_first, q_count)
+            dist.all_reduce(nbr, op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(dst, op=dist.ReduceOp.MIN, group=self.group)
+        # ---- 4. edge list of the local index block and its validity
+        e_loc, w_loc = be.edges(nbr, dst[q_first:q_first + q_count], q_first, q_count)
         mark()
         v_loc = be.validate_edges(states, e_loc, resolution)
         mark()

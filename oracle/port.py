@@ -211,8 +211,9 @@ def prm_candidates(robot: str, seed: int, first: int, count: int) -> np.ndarray:
 
 
 def prm_edge_list(nbr: np.ndarray, dist: np.ndarray, q_first: int = 0, q_count: int | None = None):
-    """Edge list rule of the batched builder: for query i (in order) and slot s, j = nbr[i][s] is kept when i < j or i is not in
-    nbr[j]; stored (min, max). Returns (edges int32 [E][2], weights [E])."""
+    """Edge list rule of the batched builder: for query i (in order) and slot s, j = nbr[i][s] is kept when i is not in nbr[j],
+    else when i is the pair's keeper (lower index if i + j even, higher if odd); stored (min, max).
+    Returns (edges int32 [E][2], weights [E])."""
     n, k = nbr.shape
     q_count = n - q_first if q_count is None else q_count
     e, w = [], []
@@ -221,7 +222,8 @@ def prm_edge_list(nbr: np.ndarray, dist: np.ndarray, q_first: int = 0, q_count: 
             j = int(nbr[i, s])
             if j < 0 or j == i:
                 continue
-            if j < i and i in nbr[j]:
+            mine = (i < j) if (i + j) % 2 == 0 else (i > j)
+            if not mine and i in nbr[j]:
                 continue
             e.append((min(i, j), max(i, j)))
             w.append(dist[i - q_first, s])

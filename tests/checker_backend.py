@@ -21,6 +21,15 @@ class CheckerBackend:
         out[:m] = rows[:m]
         return int(rows.shape[0])
 
+    def neighbors_part(self, states, k, part, parts, idx, dst):
+        n = states.shape[0]
+        per = -(-n // parts)
+        b, e = min(per * part, n), min(per * (part + 1), n)
+        if e > b:
+            i, d = self.neighbors(states, b, e - b, k)
+            idx[b:e] = i
+            dst[b:e] = d
+
     def neighbors(self, states, q_first, q_count, k):
         db = states.numpy().astype(np.float64)
         idx, dst = port.knn(db, db[q_first:q_first + q_count], k + 1, nthreads=self.nthreads)

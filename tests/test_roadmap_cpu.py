@@ -38,8 +38,12 @@ def test_edge_rule():
     nbr = np.array([[1, 2], [0, 2], [3, 1], [2, 0]], np.int64)   # 0<->1 mutual, 0->2 one-sided, 1<->2 mutual, 2<->3 mutual, 3->0 one-sided
     d = np.arange(8, dtype=np.float64).reshape(4, 2)
     e, w = port.prm_edge_list(nbr, d)
-    assert e.tolist() == [[0, 1], [0, 2], [1, 2], [2, 3], [0, 3]]
-    assert w.tolist() == [0.0, 1.0, 3.0, 4.0, 7.0]
+    # mutual pairs: {0,1} odd -> kept by 1; {1,2} odd -> kept by 2; {2,3} odd -> kept by 3; one-sided: 0->2 by 0, 3->0 by 3
+    assert e.tolist() == [[0, 2], [0, 1], [1, 2], [2, 3], [0, 3]]
+    assert w.tolist() == [1.0, 2.0, 5.0, 6.0, 7.0]
+    nbr2 = np.array([[2, 1], [0, 2], [0, 1]], np.int64)            # {0,2} even -> kept by 0; {0,1} odd -> by 1; {1,2} odd -> by 2
+    e2, _ = port.prm_edge_list(nbr2, np.zeros((3, 2)))
+    assert e2.tolist() == [[0, 2], [0, 1], [1, 2]]
 
 
 def _build(rank, world, port_file, n, k, seed, q):

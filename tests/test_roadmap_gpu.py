@@ -77,7 +77,7 @@ def _nccl_worker(rank, world, port_no, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     c = ompl_b200.Context(rank)
     env = synth.fill_env(ompl_b200.Environment(c), synth.cage_scene())
-    rm = RoadmapBuilder(EngineBackend(c, env, "panda")).build(30001, 16, 9)
+    rm = RoadmapBuilder(EngineBackend(c, env, "panda")).build(70001, 16, 9)
     q.put((rank, rm.states.cpu().numpy(), rm.edges.cpu().numpy(), rm.valid.cpu().numpy(), rm.weights.cpu().numpy()))
     dist.barrier()
     dist.destroy_process_group()
@@ -87,7 +87,7 @@ def _nccl_worker(rank, world, port_no, q):
 def test_two_gpu_nccl_roadmap_equals_single_gpu(ctx):
     import torch.multiprocessing as mp
     env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
-    one = ctx.prm_build("panda", env, 30001, 16, 9)
+    one = ctx.prm_build("panda", env, 70001, 16, 9)
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
     procs = [mpc.Process(target=_nccl_worker, args=(r, 2, 29611, q)) for r in range(2)]
