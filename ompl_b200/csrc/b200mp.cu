@@ -126,7 +126,7 @@ int build_grids(b200mp_env *e, SceneDesc *d) {
     if (!regular) return B200MP_OK;  // a cuboid with non-orthonormal axes has no simple bounding box: keep the full scan
     for (const auto &cls : boxes)
         if (cls.size() > 65535) return B200MP_OK;
-    const float reach[kGridLevels] = {0.0625f, 0.18f, 0.36f};
+    const float reach[kGridLevels] = {0.0625f, 0.11f, 0.18f, 0.36f};
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (const auto &cls : boxes)
         for (const auto &b : cls)

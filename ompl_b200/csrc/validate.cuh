@@ -41,7 +41,7 @@ struct CaptView {
 // that is conservative for it). In a sorted scene the reference's ordered scan stops only at obstacles that cannot
 // touch the sphere (min_distance >= max_extent), so "any listed obstacle has a negative test value" is the same
 // decision as the full scan, found with a few dozen tests instead of a thousand.
-constexpr int kGridLevels = 3;
+constexpr int kGridLevels = 4;
 constexpr int kShapeClasses = 5;  // spheres, capsules, z-capsules, cuboids, z-cuboids
 struct GridView {
     float ox, oy, oz, inv_h;
@@ -555,29 +555,30 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
                 const int ab = tb.link_begin[la], ae = tb.link_begin[la + 1];
                 const int bb = tb.link_begin[lb], be = tb.link_begin[lb + 1];
                 bool fhit = false;
+                // Fine spheres of link a one at a time. Each is first tested against link b's bounding sphere, inflated by
+                // 0.1 mm: the bounding sphere contains every fine sphere of b (to 1e-8 m, checked when the tables are
+                // generated), so a fine-fine contact implies this test is negative and skipping on a non-negative value
+                // cannot change a decision. Only the few spheres that pass are run against b's fine spheres.
 #pragma unroll 1
-                for (int j0 = bb; j0 < be; j0 += FT) {
-                    float px[FT], py[FT], pz[FT], pr[FT];
-#pragma unroll
-                    for (int t = 0; t < FT; ++t) {
-                        const float4 fl = tb.fine[min(j0 + t, be - 1)];
-                        frame_apply(F, fl.x, fl.y, fl.z, px[t], py[t], pz[t]);
-                        pr[t] = fl.w;  // idle slots (j0 + t >= be) are masked below
+                for (int i = ab; i < ae; ++i) {
+                    const float4 al = tb.fine[i];
+                    float qx, qy, qz;
+                    frame_apply(A, al.x, al.y, al.z, qx, qy, qz);
+                    const float xs0 = qx - bx, ys0 = qy - by, zs0 = qz - bz;
+                    const float rs0 = al.w + cb.w + 1.0e-4f;
+                    const bool cand = (fmaf(-rs0, rs0, fmaf(zs0, zs0, fmaf(ys0, ys0, xs0 * xs0))) < 0.0f) && need && !fhit;
+                    if (!__any_sync(kFull, cand)) continue;
+                    int acc = 0;
+#pragma unroll 2
+                    for (int j = bb; j < be; ++j) {
+                        const float4 fl = tb.fine[j];
+                        float px, py, pz;
+                        frame_apply(F, fl.x, fl.y, fl.z, px, py, pz);
+                        const float xs2 = qx - px, ys2 = qy - py, zs2 = qz - pz;
+                        const float rs2 = al.w + fl.w;
+                        acc |= __float_as_int(fmaf(-rs2, rs2, fmaf(zs2, zs2, fmaf(ys2, ys2, xs2 * xs2))));
                     }
-#pragma unroll 1
-                    for (int i = ab; i < ae; ++i) {
-                        const float4 al = tb.fine[i];
-                        float qx, qy, qz;
-                        frame_apply(A, al.x, al.y, al.z, qx, qy, qz);
-#pragma unroll
-                        for (int t = 0; t < FT; ++t) {
-                            const float xs2 = qx - px[t], ys2 = qy - py[t], zs2 = qz - pz[t];
-                            const float rs2 = al.w + pr[t];
-                            const float d2 = fmaf(-rs2, rs2, fmaf(zs2, zs2, fmaf(ys2, ys2, xs2 * xs2)));
-                            fhit |= (d2 < 0.0f) & (j0 + t < be);
-                        }
-                    }
-                    fhit &= need;
+                    fhit |= (acc < 0) && cand;
                     if (EDGE) {
                         if (__any_sync(kFull, fhit)) return !fhit;
                     } else {
