@@ -514,8 +514,9 @@ int b200mp_env_commit(b200mp_env *e) {
     d.blob_floats = static_cast<int>(blob.size());
     const size_t bytes = blob.size() * 4;
     // dynamic shared memory budget: opt-in maximum minus static use (barrier) and a margin
-    const size_t budget = static_cast<size_t>(e->ctx->max_smem_optin) - 1024;
-    if (bytes * 2 > budget && bytes > budget)
+    // and the per-thread bounding-sphere centres the kernels keep beside the scene
+    const size_t budget = static_cast<size_t>(e->ctx->max_smem_optin) - 1024 - std::max(lane_store_bytes<Panda>(), lane_store_bytes<Fetch>());
+    if (bytes > budget)
         return fail(B200MP_ERR_CAPACITY, "b200mp_env_commit: scene needs %zu bytes of shared memory, limit %zu", bytes, budget);
     env_free_device(e);
     B200_CUDA(cudaMalloc(&e->d_blob, std::max<size_t>(bytes, 16)));
@@ -540,7 +541,7 @@ namespace {
 template <class R>
 int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const float *d_q1, const int2 *d_pairs, int64_t m,
                    int resolution, uint8_t *d_valid, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4;
+    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>();
     auto kern = e->desc.n_grid > 0 ? validate_motions_kernel<R, false, true>
                                    : (e->desc.sorted ? validate_motions_kernel<R, false, false> : validate_motions_kernel<R, true, false>);
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -560,7 +561,7 @@ int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const 
 
 template <class R>
 int launch_states(b200mp_ctx *c, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4;
+    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>();
     auto kern = e->desc.n_grid > 0 ? validate_states_kernel<R, false, true>
                                    : (e->desc.sorted ? validate_states_kernel<R, false, false> : validate_states_kernel<R, true, false>);
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -418,12 +418,49 @@ __device__ __forceinline__ bool scan_pointclouds(const SceneDesc &d, const Tile<
 }
 
 // ------------------------------------------------------------------------------------------------ one state per lane
+// Per-thread scratch in shared memory: slot s of thread t lives at base[s * BT + t] (bank-conflict free). Slots
+// 3l .. 3l+2 hold the world-space centre of link l's bounding sphere.
+template <class R>
+__host__ __device__ constexpr int lane_slots() { return 3 * R::kLinks; }
+
+// Grid level of every robot sphere radius for this scene (computed once per block after staging).
+template <class R>
+struct SphereLevels {
+    signed char coarse[R::kLinks];
+    signed char fine[R::kFine];
+};
+
+template <class R>
+__device__ __forceinline__ void fill_levels(const SceneDesc &sd, SphereLevels<R> &lv) {
+    const typename R::Tables &tb = R::tables();
+    for (int i = threadIdx.x; i < R::kLinks; i += blockDim.x) lv.coarse[i] = static_cast<signed char>(grid_level(sd, tb.coarse[i].w));
+    for (int i = threadIdx.x; i < R::kFine; i += blockDim.x) lv.fine[i] = static_cast<signed char>(grid_level(sd, tb.fine[i].w));
+}
+
+// bring the streamed frame F (currently frame `have`, -1 = nothing) to frame k by walking the chain
+template <class R>
+__device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const float (&q)[R::kDim], const float (&sn)[R::kDim],
+                                           const float (&cs)[R::kDim]) {
+    if (have == k) return;
+    if (have < 0 || have > k) { frame_identity(F); have = 0; }
+#pragma unroll 1
+    for (int j = have + 1; j <= k; ++j) R::advance(j, F, q, sn, cs);
+    have = k;
+}
+
 // Returns true when this lane's state is collision free. `active` lanes take part; idle lanes only follow the
 // warp-uniform control flow. G = lanes per reference rake (8 for motions, 1 for single states).
 // EDGE: all lanes belong to one motion, so the first hit anywhere ends the whole warp's work.
-template <class R, int G, bool EDGE, bool MASKED, bool GRID>
-__device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, bool active) {
-    constexpr int FT = 4;  // fine spheres processed together per lane
+//
+// Phase A runs the forward kinematics once, base -> tip, fully unrolled, and parks the 11 (Panda) bounding-sphere
+// centres in shared memory. Phase B tests them against the scene tip -> base (the reference's order: distal links
+// collide first, so colliding states exit early); only when a rake has a coarse hit is the link's frame rebuilt (chain
+// walk from the cached sin / cos) and its fine spheres tested. Phase C runs the allowed self-collision pairs on the
+// stored centres (collision/validity.hh:13-44) and rebuilds frames only for pairs whose bounding spheres touch.
+template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT>
+__device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
+                            const SphereLevels<R> &lv, bool active) {
+    constexpr int FT = 4;  // fine spheres processed together per lane (ordered-scan path)
     constexpr int POLICY = EDGE ? kAnyHit : kUntilAllHit;
     const typename R::Tables &tb = R::tables();
     bool alive = active;  // false once this lane's state is known to collide (or lane idle)
@@ -431,70 +468,73 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
     float sn[R::kDim], cs[R::kDim];
     R::trig(q, sn, cs);
 
-    // ---------------- stage 1: environment vs robot. Links are visited tip -> base, the reference's own order
-    // (distal links collide first, so colliding states exit early); the frame of each group of links is rebuilt from
-    // the cached sin / cos by walking the chain from the base (a few dozen FMAs per step).
+    // ---------------- phase A
     Frame F;
+    R::fk_coarse(q, sn, cs, F, [&](int l, float x, float y, float z) {
+        slots[(3 * l + 0) * BT] = x;
+        slots[(3 * l + 1) * BT] = y;
+        slots[(3 * l + 2) * BT] = z;
+    });
+
+    // ---------------- phase B: environment vs robot
+    int have = R::kFrames - 1;  // frame held in F (warp-uniform): phase A leaves the tip frame, which the distal links need first
 #pragma unroll 1
-    for (int k = R::kFrames - 1; k >= 0; --k) {
-        if (tb.frame_link_begin[k] == tb.frame_link_begin[k + 1]) continue;
-        frame_identity(F);
-#pragma unroll 1
-        for (int j = 1; j <= k; ++j) R::advance(j, F, q, sn, cs);
-#pragma unroll 1
-        for (int l = tb.frame_link_begin[k + 1] - 1; l >= tb.frame_link_begin[k]; --l) {
-            // bounding sphere of the link
-            Tile<1> c;
-            const float4 cl = tb.coarse[l];
-            frame_apply(F, cl.x, cl.y, cl.z, c.x[0], c.y[0], c.z[0]);
-            c.r[0] = cl.w;
+    for (int l = R::kLinks - 1; l >= 0; --l) {
+        const float4 cl = tb.coarse[l];
+        Tile<1> c;
+        c.x[0] = slots[(3 * l + 0) * BT];
+        c.y[0] = slots[(3 * l + 1) * BT];
+        c.z[0] = slots[(3 * l + 2) * BT];
+        c.r[0] = cl.w;
+        const int clv = GRID ? lv.coarse[l] : -1;
+        bool chit;
+        if (GRID && clv >= 0) {
+            chit = grid_scan_scene<kUntilAllHit>(sd.grid[clv], sc, c.x[0], c.y[0], c.z[0], cl.w, alive);
+        } else {
             const float ext = alive ? sqrtf(fmaf(c.z[0], c.z[0], fmaf(c.y[0], c.y[0], c.x[0] * c.x[0]))) + cl.w : -INFINITY;
             c.ext[0] = group_max<G>(ext);
             if (!alive) { c.x[0] = kIdle; c.y[0] = kIdle; c.z[0] = kIdle; }  // idle lanes must never raise the sign bit
-            const int clv = GRID ? grid_level(sd, cl.w) : -1;
-            bool chit = (GRID && clv >= 0) ? grid_scan_scene<kUntilAllHit>(sd.grid[clv], sc, c.x[0], c.y[0], c.z[0], cl.w, alive)
-                                           : scan_scene<1, kUntilAllHit, MASKED>(sc, c, alive);
-            if (sd.n_pc > 0) chit |= scan_pointclouds<1>(sd, c, alive && !chit);
-            const bool need = group_any<G>(chit && alive) && alive;
-            if (!__any_sync(kFull, need)) continue;
-            // fine spheres of the link, FT at a time
-            const int fb = tb.link_begin[l], fe = tb.link_begin[l + 1];
-            bool fhit = false;
-            if (GRID) {
-                // one fine sphere per lane at a time, each against the short candidate list of its own cell
+            chit = scan_scene<1, kUntilAllHit, MASKED>(sc, c, alive);
+        }
+        if (sd.n_pc > 0) {
+            c.ext[0] = alive ? 0.0f : -INFINITY;
+            chit |= scan_pointclouds<1>(sd, c, alive && !chit);
+        }
+        const bool need = group_any<G>(chit && alive) && alive;
+        if (!__any_sync(kFull, need)) continue;
+        // fine spheres of the link
+        frame_seek<R>(F, have, tb.link_frame[l], q, sn, cs);
+        const int fb = tb.link_begin[l], fe = tb.link_begin[l + 1];
+        bool fhit = false;
+        if (GRID) {
+            // one fine sphere per lane at a time, each against the short candidate list of its own cell
 #pragma unroll 1
-                for (int f = fb; f < fe; ++f) {
-                    const float4 fl = tb.fine[f];
-                    const int flv = grid_level(sd, fl.w);
-                    const bool on = need && !fhit;
-                    bool h;
-                    if (flv >= 0) {
-                        float x, y, z;
-                        frame_apply(F, fl.x, fl.y, fl.z, x, y, z);
-                        h = grid_scan_scene<POLICY>(sd.grid[flv], sc, x, y, z, fl.w, on);
-                        if (sd.n_pc > 0) {
-                            Tile<1> s1;
-                            s1.x[0] = x; s1.y[0] = y; s1.z[0] = z; s1.r[0] = fl.w; s1.ext[0] = on ? 0.0f : -INFINITY;
-                            h |= scan_pointclouds<1>(sd, s1, on && !h);
-                        }
-                    } else {
-                        Tile<1> s1;
-                        frame_apply(F, fl.x, fl.y, fl.z, s1.x[0], s1.y[0], s1.z[0]);
-                        s1.r[0] = fl.w;
-                        const float e = on ? sqrtf(fmaf(s1.z[0], s1.z[0], fmaf(s1.y[0], s1.y[0], s1.x[0] * s1.x[0]))) + fl.w : -INFINITY;
-                        s1.ext[0] = group_max<G>(e);
-                        if (!on) { s1.ext[0] = -INFINITY; s1.x[0] = kIdle; s1.y[0] = kIdle; s1.z[0] = kIdle; }
-                        h = scan_scene<1, POLICY, MASKED>(sc, s1, on);
-                        if (sd.n_pc > 0) h |= scan_pointclouds<1>(sd, s1, on && !h);
-                    }
-                    fhit |= h && on;
-                    if (EDGE) {
-                        if (__any_sync(kFull, fhit)) return !fhit;
-                    } else {
-                        if (__all_sync(kFull, fhit || !need)) break;
-                    }
+            for (int f = fb; f < fe; ++f) {
+                const float4 fl = tb.fine[f];
+                const int flv = lv.fine[f];
+                const bool on = need && !fhit;
+                bool h;
+                Tile<1> s1;
+                frame_apply(F, fl.x, fl.y, fl.z, s1.x[0], s1.y[0], s1.z[0]);
+                s1.r[0] = fl.w;
+                if (flv >= 0) {
+                    h = grid_scan_scene<POLICY>(sd.grid[flv], sc, s1.x[0], s1.y[0], s1.z[0], fl.w, on);
+                    s1.ext[0] = on ? 0.0f : -INFINITY;
+                } else {
+                    const float e = on ? sqrtf(fmaf(s1.z[0], s1.z[0], fmaf(s1.y[0], s1.y[0], s1.x[0] * s1.x[0]))) + fl.w : -INFINITY;
+                    s1.ext[0] = group_max<G>(e);
+                    if (!on) { s1.ext[0] = -INFINITY; s1.x[0] = kIdle; s1.y[0] = kIdle; s1.z[0] = kIdle; }
+                    h = scan_scene<1, POLICY, MASKED>(sc, s1, on);
                 }
-            } else {
+                if (sd.n_pc > 0) h |= scan_pointclouds<1>(sd, s1, on && !h);
+                fhit |= h && on;
+                if (EDGE) {
+                    if (__any_sync(kFull, fhit)) return !fhit;
+                } else {
+                    if (__all_sync(kFull, fhit || !need)) break;
+                }
+            }
+        } else {
 #pragma unroll 1
             for (int f0 = fb; f0 < fe; f0 += FT) {
                 Tile<FT> s;
@@ -517,83 +557,65 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
                     if (__all_sync(kFull, fhit || !need)) break;
                 }
             }
-            }
-            if (fhit) alive = false;
-            if (!EDGE && !__any_sync(kFull, alive)) return false;
         }
+        if (fhit) alive = false;
+        if (!EDGE && !__any_sync(kFull, alive)) return false;
     }
 
-    // ---------------- stage 2: allowed self-collision pairs (collision/validity.hh:13-44), frames streamed again
-    Frame S[R::kSlots];
-#pragma unroll
-    for (int i = 0; i < R::kSlots; ++i) frame_identity(S[i]);
-    frame_identity(F);
+    // ---------------- phase C: allowed self-collision pairs on the stored centres; pairs are ordered by the later link's
+    // frame, so F only ever moves forward here
+    have = -1;
 #pragma unroll 1
-    for (int k = 0; k < R::kFrames; ++k) {
-        if (k > 0) R::advance(k, F, q, sn, cs);
+    for (int p = 0; p < R::kPairs; ++p) {
+        const int la = tb.pair_a[p], lb = tb.pair_b[p];
+        const float ra = tb.coarse[la].w, rb = tb.coarse[lb].w;
+        const float bx = slots[(3 * lb + 0) * BT], by = slots[(3 * lb + 1) * BT], bz = slots[(3 * lb + 2) * BT];
+        const float xs = slots[(3 * la + 0) * BT] - bx, ys = slots[(3 * la + 1) * BT] - by, zs = slots[(3 * la + 2) * BT] - bz;
+        const float rs = ra + rb;
+        const float d = fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs)));
+        const bool need = group_any<G>((d < 0.0f) && alive) && alive;
+        if (!__any_sync(kFull, need)) continue;
+        Frame A;
+        {
+            int ha = -1;
+            frame_seek<R>(A, ha, tb.link_frame[la], q, sn, cs);
+        }
+        frame_seek<R>(F, have, tb.link_frame[lb], q, sn, cs);
+        const int ab = tb.link_begin[la], ae = tb.link_begin[la + 1];
+        const int bb = tb.link_begin[lb], be = tb.link_begin[lb + 1];
+        bool fhit = false;
+        // Fine spheres of link a one at a time. Each is first tested against link b's bounding sphere, inflated by
+        // 0.1 mm: the bounding sphere contains every fine sphere of b (to 1e-8 m, checked when the tables are
+        // generated), so a fine-fine contact implies this test is negative and skipping on a non-negative value
+        // cannot change a decision. Only the few spheres that pass are run against b's fine spheres.
 #pragma unroll 1
-        for (int p = tb.pair_frame_begin[k]; p < tb.pair_frame_begin[k + 1]; ++p) {
-            const int la = tb.pair_a[p], lb = tb.pair_b[p], slot = tb.pair_slot[p];
-            Frame A;
-            if (slot == -2) frame_identity(A);
-            else if (slot == -1) A = F;
-            else {
-                A = S[0];
-#pragma unroll
-                for (int i = 1; i < R::kSlots; ++i) if (slot == i) A = S[i];
-            }
-            const float4 ca = tb.coarse[la], cb = tb.coarse[lb];
-            float ax, ay, az, bx, by, bz;
-            frame_apply(A, ca.x, ca.y, ca.z, ax, ay, az);
-            frame_apply(F, cb.x, cb.y, cb.z, bx, by, bz);
-            {
-                const float xs = ax - bx, ys = ay - by, zs = az - bz;
-                const float rs = ca.w + cb.w;
-                const float d = fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs)));
-                const bool need = group_any<G>((d < 0.0f) && alive) && alive;
-                if (!__any_sync(kFull, need)) continue;
-                const int ab = tb.link_begin[la], ae = tb.link_begin[la + 1];
-                const int bb = tb.link_begin[lb], be = tb.link_begin[lb + 1];
-                bool fhit = false;
-                // Fine spheres of link a one at a time. Each is first tested against link b's bounding sphere, inflated by
-                // 0.1 mm: the bounding sphere contains every fine sphere of b (to 1e-8 m, checked when the tables are
-                // generated), so a fine-fine contact implies this test is negative and skipping on a non-negative value
-                // cannot change a decision. Only the few spheres that pass are run against b's fine spheres.
-#pragma unroll 1
-                for (int i = ab; i < ae; ++i) {
-                    const float4 al = tb.fine[i];
-                    float qx, qy, qz;
-                    frame_apply(A, al.x, al.y, al.z, qx, qy, qz);
-                    const float xs0 = qx - bx, ys0 = qy - by, zs0 = qz - bz;
-                    const float rs0 = al.w + cb.w + 1.0e-4f;
-                    const bool cand = (fmaf(-rs0, rs0, fmaf(zs0, zs0, fmaf(ys0, ys0, xs0 * xs0))) < 0.0f) && need && !fhit;
-                    if (!__any_sync(kFull, cand)) continue;
-                    int acc = 0;
+        for (int i = ab; i < ae; ++i) {
+            const float4 al = tb.fine[i];
+            float qx, qy, qz;
+            frame_apply(A, al.x, al.y, al.z, qx, qy, qz);
+            const float xs0 = qx - bx, ys0 = qy - by, zs0 = qz - bz;
+            const float rs0 = al.w + rb + 1.0e-4f;
+            const bool cand = (fmaf(-rs0, rs0, fmaf(zs0, zs0, fmaf(ys0, ys0, xs0 * xs0))) < 0.0f) && need && !fhit;
+            if (!__any_sync(kFull, cand)) continue;
+            int acc = 0;
 #pragma unroll 2
-                    for (int j = bb; j < be; ++j) {
-                        const float4 fl = tb.fine[j];
-                        float px, py, pz;
-                        frame_apply(F, fl.x, fl.y, fl.z, px, py, pz);
-                        const float xs2 = qx - px, ys2 = qy - py, zs2 = qz - pz;
-                        const float rs2 = al.w + fl.w;
-                        acc |= __float_as_int(fmaf(-rs2, rs2, fmaf(zs2, zs2, fmaf(ys2, ys2, xs2 * xs2))));
-                    }
-                    fhit |= (acc < 0) && cand;
-                    if (EDGE) {
-                        if (__any_sync(kFull, fhit)) return !fhit;
-                    } else {
-                        if (__all_sync(kFull, fhit || !need)) break;
-                    }
-                }
-                if (fhit) alive = false;
-                if (!EDGE && !__any_sync(kFull, alive)) return false;
+            for (int j = bb; j < be; ++j) {
+                const float4 fl = tb.fine[j];
+                float px, py, pz;
+                frame_apply(F, fl.x, fl.y, fl.z, px, py, pz);
+                const float xs2 = qx - px, ys2 = qy - py, zs2 = qz - pz;
+                const float rs2 = al.w + fl.w;
+                acc |= __float_as_int(fmaf(-rs2, rs2, fmaf(zs2, zs2, fmaf(ys2, ys2, xs2 * xs2))));
+            }
+            fhit |= (acc < 0) && cand;
+            if (EDGE) {
+                if (__any_sync(kFull, fhit)) return !fhit;
+            } else {
+                if (__all_sync(kFull, fhit || !need)) break;
             }
         }
-        const int sv = tb.save_slot[k];
-        if (sv >= 0) {
-#pragma unroll
-            for (int i = 0; i < R::kSlots; ++i) if (sv == i) S[i] = F;
-        }
+        if (fhit) alive = false;
+        if (!EDGE && !__any_sync(kFull, alive)) return false;
     }
     return alive;
 }
@@ -603,8 +625,14 @@ struct LaunchCounters {
     unsigned long long next;  // dynamic work queue head
 };
 
+// Threads per block and blocks per SM of the validation kernels. Shared memory per block = scene blob + 3 * links
+// floats per thread for the bounding-sphere centres.
 constexpr int kBlockThreads = 256;
+constexpr int kBlocksPerSM = 2;
 constexpr int kWarpsPerBlock = kBlockThreads / 32;
+
+template <class R>
+__host__ __device__ constexpr size_t lane_store_bytes() { return static_cast<size_t>(lane_slots<R>()) * kBlockThreads * sizeof(float); }
 
 // horizontal sum in the reference's order (external/vamp/src/impl/vamp/vector/avx.hh:442-452): lanes padded to 8
 template <int DIM>
@@ -620,13 +648,16 @@ __device__ __forceinline__ float vamp_l2_norm(const float (&v)[DIM]) {
 
 // One warp per motion; motions are taken from a global queue (edge cost varies by 100x with early exit).
 template <class R, bool MASKED, bool GRID>
-__global__ void __launch_bounds__(kBlockThreads, 2)
+__global__ void __launch_bounds__(kBlockThreads, kBlocksPerSM)
 validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float *__restrict__ q1, const int2 *__restrict__ pairs,
                         long long m, int resolution, uint8_t *__restrict__ valid, LaunchCounters *cnt) {
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long bar;
+    __shared__ SphereLevels<R> lv;
+    fill_levels<R>(sd, lv);
     stage_scene(smem, sd.blob, sd.blob_floats, &bar);
     const Scene sc = scene_view(sd, smem);
+    float *slots = smem + sd.blob_floats + threadIdx.x;
     constexpr int D = R::kDim;
     const int lane = threadIdx.x & 31;
     const int rake_in_pass = lane >> 3;
@@ -669,7 +700,7 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
         bool ok = true;
         for (int base = 0; base < n; base += 4) {
             const bool active = (base + rake_in_pass) < n;
-            const bool good = check_state<R, 8, true, MASKED, GRID>(q, sd, sc, active);
+            const bool good = check_state<R, 8, true, MASKED, GRID, kBlockThreads>(q, sd, sc, slots, lv, active);
             if (__any_sync(kFull, active && !good)) { ok = false; break; }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -684,12 +715,15 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
 // One lane per state: VampStateValidityChecker::isValid = validate_motion<Robot, rake, 1>(q, q), i.e. one fkcc on
 // 8 identical lanes (src/ompl/vamp/VampStateValidityChecker.h:37-41) -> group size 1 here.
 template <class R, bool MASKED, bool GRID>
-__global__ void __launch_bounds__(kBlockThreads, 2)
+__global__ void __launch_bounds__(kBlockThreads, kBlocksPerSM)
 validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, uint8_t *__restrict__ valid, LaunchCounters *cnt) {
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long bar;
+    __shared__ SphereLevels<R> lv;
+    fill_levels<R>(sd, lv);
     stage_scene(smem, sd.blob, sd.blob_floats, &bar);
     const Scene sc = scene_view(sd, smem);
+    float *slots = smem + sd.blob_floats + threadIdx.x;
     constexpr int D = R::kDim;
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -704,7 +738,7 @@ validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, 
 #pragma unroll
         for (int j = 0; j < D; ++j) q[j] = active ? __ldg(qs + i * D + j) : 0.0f;
         // validate_vector with start == goal: block = q + 0 * percents
-        const bool good = check_state<R, 1, false, MASKED, GRID>(q, sd, sc, active);
+        const bool good = check_state<R, 1, false, MASKED, GRID, kBlockThreads>(q, sd, sc, slots, lv, active);
         if (active) valid[i] = good ? 1 : 0;
     }
 }

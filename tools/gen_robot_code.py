@@ -190,6 +190,7 @@ def gen_cuda(model: dict) -> str:
     w(f"    short frame_link_begin[{nfr + 1}];  // links living on frame k = [frame_link_begin[k], frame_link_begin[k+1])")
     w(f"    short pair_frame_begin[{nfr + 1}];  // pairs whose later link lives on frame k")
     w(f"    short save_slot[{nfr}];             // slot frame k is saved to for later pairs, or -1")
+    w(f"    short link_frame[{nl}];             // frame link l lives on")
     w("};")
     w("")
     w(f"__constant__ {cname}Tables k{cname}Tables = {{")
@@ -203,6 +204,7 @@ def gen_cuda(model: dict) -> str:
     w("    {" + ", ".join(str(v) for v in frame_link_begin) + "},")
     w("    {" + ", ".join(str(v) for v in pair_frame_begin) + "},")
     w("    {" + ", ".join(str(v) for v in save_slot) + "},")
+    w("    {" + ", ".join(str(r["frame"]) for r in link_rows) + "},")
     w("};")
     w("")
     w(f"struct {cname} {{")
@@ -234,6 +236,10 @@ def gen_cuda(model: dict) -> str:
     w("        constexpr bool v[kDim] = {" + ", ".join("true" if fr["type"] in ("revolute", "continuous") else "false" for fr in sorted(frames[1:], key=lambda f: f["q_index"])) + "};")
     w("        return v[j];")
     w("    }")
+    w("    // one base -> tip pass: st(l, x, y, z) receives the world-space centre of every link's bounding sphere, tip the last frame")
+    w("    // (same arithmetic as frame_apply on the streamed frames; zero coefficients dropped, which leaves the values unchanged)")
+    w("    template <class St>")
+    w("    __device__ static __forceinline__ void fk_coarse(const float (&q)[kDim], const float (&sn)[kDim], const float (&cs)[kDim], Frame &tip, St st);")
     w("    // step the streaming frame from k-1 to k (k >= 1); uniform switch, static joint indices")
     w("    __device__ static __forceinline__ void advance(int k, Frame &F, const float (&q)[kDim], const float (&sn)[kDim], const float (&cs)[kDim]);")
     w("};")
@@ -249,6 +255,36 @@ def gen_cuda(model: dict) -> str:
             w("    " + ln)
         w("}")
         w("")
+    def apply_expr(fname, row, c):
+        acc = f"{fname}.t[{row}]"
+        for j in (2, 1, 0):
+            cj = float(np.float32(c[j]))
+            if cj != 0.0:
+                acc = f"fmaf({fname}.r[{3 * row + j}], {f32(cj)}, {acc})"
+        return acc
+
+    w("template <class St>")
+    w(f"__device__ __forceinline__ void {cname}::fk_coarse(const float (&q)[kDim], const float (&sn)[kDim], const float (&cs)[kDim], Frame &tip, St st) {{")
+    w("    (void)q; (void)sn; (void)cs;")
+    w("    Frame F0;")
+    w("    frame_identity(F0);")
+    for fr in frames:
+        k = fr["id"]
+        if k > 0:
+            qi = fr["q_index"]
+            w(f"    Frame F{k};")
+            w(f"    frame<{k}>(F{k - 1}, q[{qi}], sn[{qi}], cs[{qi}], F{k});")
+        for li, r in enumerate(link_rows):
+            if r["frame"] != k:
+                continue
+            c = r["coarse"]["c"]
+            if k == 0:
+                w(f"    st({li}, {f32(c[0])}, {f32(c[1])}, {f32(c[2])});")
+            else:
+                w(f"    st({li}, {apply_expr(f'F{k}', 0, c)}, {apply_expr(f'F{k}', 1, c)}, {apply_expr(f'F{k}', 2, c)});")
+    w(f"    tip = F{len(frames) - 1};")
+    w("}")
+    w("")
     w(f"__device__ __forceinline__ void {cname}::advance(int k, Frame &F, const float (&q)[kDim], const float (&sn)[kDim], const float (&cs)[kDim]) {{")
     w("    const Frame P = F;")
     w("    switch (k) {")
