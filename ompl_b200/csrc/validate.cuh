@@ -311,12 +311,19 @@ __device__ __forceinline__ int grid_level(const SceneDesc &d, float r) {
     return lv;
 }
 
+// Exit test of a grid walk, evaluated every 8 candidates. any_mode (warp-uniform): stop as soon as any lane has a hit;
+// otherwise stop once every participating lane has a hit. One vote either way: any(hit) = !all(!hit).
+__device__ __forceinline__ bool grid_should_stop(bool hit, bool on, bool any_mode) {
+    const bool a = __all_sync(kFull, any_mode ? !hit : (hit || !on));
+    return a != any_mode;
+}
+
 // One shape class: every lane walks the candidate list of its own cell; record `n` (the first padding record) stands in
-// once a lane's list is exhausted, so the loop body needs no predication. One warp vote per 8 candidates.
-template <class Test, int POLICY>
+// once a lane's list is exhausted, so the loop body needs no predication.
+template <class Test>
 __device__ __forceinline__ int grid_scan_class(const unsigned *__restrict__ start, const unsigned short *__restrict__ ids, int cell,
                                                const float4 *__restrict__ obs, int n, float x, float y, float z, float r, float rsq,
-                                               bool on, int acc) {
+                                               bool on, bool any_mode, int acc) {
     unsigned b = 0, cnt = 0;
     if (on) {
         b = __ldg(start + cell);
@@ -329,33 +336,32 @@ __device__ __forceinline__ int grid_scan_class(const unsigned *__restrict__ star
         const int id1 = (i + 1 < cnt) ? static_cast<int>(__ldg(ids + b + i + 1)) : n;
         acc |= __float_as_int(Test::test(obs + id0 * Test::kRec, x, y, z, r, rsq));
         acc |= __float_as_int(Test::test(obs + id1 * Test::kRec, x, y, z, r, rsq));
-        if ((i & 6u) == 6u && scan_should_stop<POLICY>(acc < 0, on)) break;
+        if ((i & 6u) == 6u && grid_should_stop(acc < 0, on, any_mode)) break;
     }
     return acc;
 }
 
-template <int POLICY>
-__device__ __forceinline__ bool grid_scan_scene(const GridView &g, const Scene &sc, float x, float y, float z, float r, bool on) {
+__device__ __forceinline__ bool grid_scan_scene(const GridView &g, const Scene &sc, float x, float y, float z, float r, bool on, bool any_mode) {
     const int cell = grid_cell(g, x, y, z);
     const float rsq = r * r;
     int acc = 0;
     if (sc.n_sph > 0) {
-        acc = grid_scan_class<SphereTest, POLICY>(g.start[0], g.ids[0], cell, sc.sph, sc.n_sph, x, y, z, r, rsq, on, acc);
-        if (scan_should_stop<POLICY>(acc < 0, on)) return acc < 0;
+        acc = grid_scan_class<SphereTest>(g.start[0], g.ids[0], cell, sc.sph, sc.n_sph, x, y, z, r, rsq, on, any_mode, acc);
+        if (grid_should_stop(acc < 0, on, any_mode)) return acc < 0;
     }
     if (sc.n_cap > 0) {
-        acc = grid_scan_class<CapsuleTest, POLICY>(g.start[1], g.ids[1], cell, sc.cap, sc.n_cap, x, y, z, r, rsq, on, acc);
-        if (scan_should_stop<POLICY>(acc < 0, on)) return acc < 0;
+        acc = grid_scan_class<CapsuleTest>(g.start[1], g.ids[1], cell, sc.cap, sc.n_cap, x, y, z, r, rsq, on, any_mode, acc);
+        if (grid_should_stop(acc < 0, on, any_mode)) return acc < 0;
     }
     if (sc.n_zcap > 0) {
-        acc = grid_scan_class<ZCapsuleTest, POLICY>(g.start[2], g.ids[2], cell, sc.zcap, sc.n_zcap, x, y, z, r, rsq, on, acc);
-        if (scan_should_stop<POLICY>(acc < 0, on)) return acc < 0;
+        acc = grid_scan_class<ZCapsuleTest>(g.start[2], g.ids[2], cell, sc.zcap, sc.n_zcap, x, y, z, r, rsq, on, any_mode, acc);
+        if (grid_should_stop(acc < 0, on, any_mode)) return acc < 0;
     }
     if (sc.n_cub > 0) {
-        acc = grid_scan_class<CuboidTest, POLICY>(g.start[3], g.ids[3], cell, sc.cub, sc.n_cub, x, y, z, r, rsq, on, acc);
-        if (scan_should_stop<POLICY>(acc < 0, on)) return acc < 0;
+        acc = grid_scan_class<CuboidTest>(g.start[3], g.ids[3], cell, sc.cub, sc.n_cub, x, y, z, r, rsq, on, any_mode, acc);
+        if (grid_should_stop(acc < 0, on, any_mode)) return acc < 0;
     }
-    if (sc.n_zcub > 0) acc = grid_scan_class<ZCuboidTest, POLICY>(g.start[4], g.ids[4], cell, sc.zcub, sc.n_zcub, x, y, z, r, rsq, on, acc);
+    if (sc.n_zcub > 0) acc = grid_scan_class<ZCuboidTest>(g.start[4], g.ids[4], cell, sc.zcub, sc.n_zcub, x, y, z, r, rsq, on, any_mode, acc);
     return acc < 0;
 }
 
@@ -419,9 +425,17 @@ __device__ __forceinline__ bool scan_pointclouds(const SceneDesc &d, const Tile<
 
 // ------------------------------------------------------------------------------------------------ one state per lane
 // Per-thread scratch in shared memory: slot s of thread t lives at base[s * BT + t] (bank-conflict free). Slots
-// 3l .. 3l+2 hold the world-space centre of link l's bounding sphere.
+// 3l .. 3l+2 hold the world-space centre of link l's bounding sphere, then sin[dim] and cos[dim] of the joint angles.
 template <class R>
-__host__ __device__ constexpr int lane_slots() { return 3 * R::kLinks; }
+__host__ __device__ constexpr int lane_slots() { return 3 * R::kLinks + 2 * R::kDim; }
+template <class R>
+__host__ __device__ constexpr int trig_slot() { return 3 * R::kLinks; }
+template <class R>
+__host__ __device__ constexpr unsigned revolute_mask() {
+    unsigned m = 0;
+    for (int j = 0; j < R::kDim; ++j) m |= R::joint_revolute(j) ? (1u << j) : 0u;
+    return m;
+}
 
 // Grid level of every robot sphere radius for this scene (computed once per block after staging).
 template <class R>
@@ -437,134 +451,56 @@ __device__ __forceinline__ void fill_levels(const SceneDesc &sd, SphereLevels<R>
     for (int i = threadIdx.x; i < R::kFine; i += blockDim.x) lv.fine[i] = static_cast<signed char>(grid_level(sd, tb.fine[i].w));
 }
 
+// sin / cos of every joint angle with the reference's polynomials, left in the thread's shared-memory slots. The 2 * dim
+// evaluations run as one rolled loop (the code footprint of the kernel matters more than the few LDS / STS).
+template <class R, int BT>
+__device__ __forceinline__ void trig_to_slots(const float (&q)[R::kDim], float *__restrict__ slots) {
+    constexpr int D = R::kDim, T0 = trig_slot<R>();
+    constexpr float PI = 3.14159265359;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        // cos(x) = sin(wrap(x + pi/2)) with the reference's float constants (vector/interface.hh:451-459)
+        const float v = q[j] + static_cast<float>(PI / 2.);
+        slots[(T0 + j) * BT] = q[j];
+        slots[(T0 + D + j) * BT] = v - ((v >= PI) ? static_cast<float>(2 * PI) : 0.0f);
+    }
+#pragma unroll 1
+    for (int i = 0; i < 2 * D; ++i) {
+        const int j = i < D ? i : i - D;
+        float r = vamp_sin(slots[(T0 + i) * BT]);
+        if (!((revolute_mask<R>() >> j) & 1u)) r = i < D ? 0.0f : 1.0f;  // prismatic joints: the frame code uses q itself
+        slots[(T0 + i) * BT] = r;
+    }
+}
+
+template <class R, int BT>
+__device__ __forceinline__ void trig_from_slots(const float *__restrict__ slots, float (&sn)[R::kDim], float (&cs)[R::kDim]) {
+#pragma unroll
+    for (int j = 0; j < R::kDim; ++j) {
+        sn[j] = slots[(trig_slot<R>() + j) * BT];
+        cs[j] = slots[(trig_slot<R>() + R::kDim + j) * BT];
+    }
+}
+
 // bring the streamed frame F (currently frame `have`, -1 = nothing) to frame k by walking the chain
-template <class R>
-__device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const float (&q)[R::kDim], const float (&sn)[R::kDim],
-                                           const float (&cs)[R::kDim]) {
+template <class R, int BT>
+__device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const float (&q)[R::kDim], const float *__restrict__ slots) {
     if (have == k) return;
     if (have < 0 || have > k) { frame_identity(F); have = 0; }
+    float sn[R::kDim], cs[R::kDim];
+    trig_from_slots<R, BT>(slots, sn, cs);
 #pragma unroll 1
     for (int j = have + 1; j <= k; ++j) R::advance(j, F, q, sn, cs);
     have = k;
 }
 
-// Returns true when this lane's state is collision free. `active` lanes take part; idle lanes only follow the
-// warp-uniform control flow. G = lanes per reference rake (8 for motions, 1 for single states).
-// EDGE: all lanes belong to one motion, so the first hit anywhere ends the whole warp's work.
-//
-// Phase A runs the forward kinematics once, base -> tip, fully unrolled, and parks the 11 (Panda) bounding-sphere
-// centres in shared memory. Phase B tests them against the scene tip -> base (the reference's order: distal links
-// collide first, so colliding states exit early); only when a rake has a coarse hit is the link's frame rebuilt (chain
-// walk from the cached sin / cos) and its fine spheres tested. Phase C runs the allowed self-collision pairs on the
-// stored centres (collision/validity.hh:13-44) and rebuilds frames only for pairs whose bounding spheres touch.
-template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT>
-__device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
-                            const SphereLevels<R> &lv, bool active) {
-    constexpr int FT = 4;  // fine spheres processed together per lane (ordered-scan path)
-    constexpr int POLICY = EDGE ? kAnyHit : kUntilAllHit;
+// Allowed self-collision pairs on the stored centres (collision/validity.hh:13-44); frames are rebuilt only for pairs
+// whose bounding spheres touch. Updates `alive`; returns true when the caller should return `result` immediately.
+template <class R, int G, bool EDGE, int BT>
+__device__ __forceinline__ bool self_collision(const float (&q)[R::kDim], const float *__restrict__ slots, bool &alive, bool &result) {
     const typename R::Tables &tb = R::tables();
-    bool alive = active;  // false once this lane's state is known to collide (or lane idle)
-
-    float sn[R::kDim], cs[R::kDim];
-    R::trig(q, sn, cs);
-
-    // ---------------- phase A
     Frame F;
-    R::fk_coarse(q, sn, cs, F, [&](int l, float x, float y, float z) {
-        slots[(3 * l + 0) * BT] = x;
-        slots[(3 * l + 1) * BT] = y;
-        slots[(3 * l + 2) * BT] = z;
-    });
-
-    // ---------------- phase B: environment vs robot
-    int have = R::kFrames - 1;  // frame held in F (warp-uniform): phase A leaves the tip frame, which the distal links need first
-#pragma unroll 1
-    for (int l = R::kLinks - 1; l >= 0; --l) {
-        const float4 cl = tb.coarse[l];
-        Tile<1> c;
-        c.x[0] = slots[(3 * l + 0) * BT];
-        c.y[0] = slots[(3 * l + 1) * BT];
-        c.z[0] = slots[(3 * l + 2) * BT];
-        c.r[0] = cl.w;
-        const int clv = GRID ? lv.coarse[l] : -1;
-        bool chit;
-        if (GRID && clv >= 0) {
-            chit = grid_scan_scene<kUntilAllHit>(sd.grid[clv], sc, c.x[0], c.y[0], c.z[0], cl.w, alive);
-        } else {
-            const float ext = alive ? sqrtf(fmaf(c.z[0], c.z[0], fmaf(c.y[0], c.y[0], c.x[0] * c.x[0]))) + cl.w : -INFINITY;
-            c.ext[0] = group_max<G>(ext);
-            if (!alive) { c.x[0] = kIdle; c.y[0] = kIdle; c.z[0] = kIdle; }  // idle lanes must never raise the sign bit
-            chit = scan_scene<1, kUntilAllHit, MASKED>(sc, c, alive);
-        }
-        if (sd.n_pc > 0) {
-            c.ext[0] = alive ? 0.0f : -INFINITY;
-            chit |= scan_pointclouds<1>(sd, c, alive && !chit);
-        }
-        const bool need = group_any<G>(chit && alive) && alive;
-        if (!__any_sync(kFull, need)) continue;
-        // fine spheres of the link
-        frame_seek<R>(F, have, tb.link_frame[l], q, sn, cs);
-        const int fb = tb.link_begin[l], fe = tb.link_begin[l + 1];
-        bool fhit = false;
-        if (GRID) {
-            // one fine sphere per lane at a time, each against the short candidate list of its own cell
-#pragma unroll 1
-            for (int f = fb; f < fe; ++f) {
-                const float4 fl = tb.fine[f];
-                const int flv = lv.fine[f];
-                const bool on = need && !fhit;
-                bool h;
-                Tile<1> s1;
-                frame_apply(F, fl.x, fl.y, fl.z, s1.x[0], s1.y[0], s1.z[0]);
-                s1.r[0] = fl.w;
-                if (flv >= 0) {
-                    h = grid_scan_scene<POLICY>(sd.grid[flv], sc, s1.x[0], s1.y[0], s1.z[0], fl.w, on);
-                    s1.ext[0] = on ? 0.0f : -INFINITY;
-                } else {
-                    const float e = on ? sqrtf(fmaf(s1.z[0], s1.z[0], fmaf(s1.y[0], s1.y[0], s1.x[0] * s1.x[0]))) + fl.w : -INFINITY;
-                    s1.ext[0] = group_max<G>(e);
-                    if (!on) { s1.ext[0] = -INFINITY; s1.x[0] = kIdle; s1.y[0] = kIdle; s1.z[0] = kIdle; }
-                    h = scan_scene<1, POLICY, MASKED>(sc, s1, on);
-                }
-                if (sd.n_pc > 0) h |= scan_pointclouds<1>(sd, s1, on && !h);
-                fhit |= h && on;
-                if (EDGE) {
-                    if (__any_sync(kFull, fhit)) return !fhit;
-                } else {
-                    if (__all_sync(kFull, fhit || !need)) break;
-                }
-            }
-        } else {
-#pragma unroll 1
-            for (int f0 = fb; f0 < fe; f0 += FT) {
-                Tile<FT> s;
-#pragma unroll
-                for (int t = 0; t < FT; ++t) {
-                    const int fi = min(f0 + t, fe - 1);
-                    const float4 fl = tb.fine[fi];
-                    frame_apply(F, fl.x, fl.y, fl.z, s.x[t], s.y[t], s.z[t]);
-                    s.r[t] = fl.w;
-                    const bool on = need && (f0 + t < fe);
-                    const float e = on ? sqrtf(fmaf(s.z[t], s.z[t], fmaf(s.y[t], s.y[t], s.x[t] * s.x[t]))) + fl.w : -INFINITY;
-                    s.ext[t] = group_max<G>(e);
-                    if (!on) { s.ext[t] = -INFINITY; s.x[t] = kIdle; s.y[t] = kIdle; s.z[t] = kIdle; }
-                }
-                fhit |= scan_scene<FT, POLICY, MASKED>(sc, s, need && !fhit);
-                if (sd.n_pc > 0) fhit |= scan_pointclouds<FT>(sd, s, need && !fhit);
-                if (EDGE) {
-                    if (__any_sync(kFull, fhit)) return !fhit;
-                } else {
-                    if (__all_sync(kFull, fhit || !need)) break;
-                }
-            }
-        }
-        if (fhit) alive = false;
-        if (!EDGE && !__any_sync(kFull, alive)) return false;
-    }
-
-    // ---------------- phase C: allowed self-collision pairs on the stored centres; pairs are ordered by the later link's
-    // frame, so F only ever moves forward here
-    have = -1;
+    int have = -1;
 #pragma unroll 1
     for (int p = 0; p < R::kPairs; ++p) {
         const int la = tb.pair_a[p], lb = tb.pair_b[p];
@@ -575,12 +511,14 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
         const float d = fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs)));
         const bool need = group_any<G>((d < 0.0f) && alive) && alive;
         if (!__any_sync(kFull, need)) continue;
+        // frames of both links through the one chain walker: first link a's (kept in A), then link b's (pairs are ordered by
+        // the later link's frame, so F mostly moves forward)
         Frame A;
-        {
-            int ha = -1;
-            frame_seek<R>(A, ha, tb.link_frame[la], q, sn, cs);
+#pragma unroll 1
+        for (int w = 0; w < 2; ++w) {
+            frame_seek<R, BT>(F, have, tb.link_frame[w == 0 ? la : lb], q, slots);
+            if (w == 0) A = F;
         }
-        frame_seek<R>(F, have, tb.link_frame[lb], q, sn, cs);
         const int ab = tb.link_begin[la], ae = tb.link_begin[la + 1];
         const int bb = tb.link_begin[lb], be = tb.link_begin[lb + 1];
         bool fhit = false;
@@ -609,6 +547,83 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
             }
             fhit |= (acc < 0) && cand;
             if (EDGE) {
+                if (__any_sync(kFull, fhit)) { result = !fhit; return true; }
+            } else {
+                if (__all_sync(kFull, fhit || !need)) break;
+            }
+        }
+        if (fhit) alive = false;
+        if (!EDGE && !__any_sync(kFull, alive)) { result = false; return true; }
+    }
+    return false;
+}
+
+// phase A: trig into the slots, one unrolled base -> tip FK pass that parks the bounding-sphere centres and leaves the tip frame
+template <class R, int BT>
+__device__ __forceinline__ void fk_to_slots(const float (&q)[R::kDim], float *__restrict__ slots, Frame &tip) {
+    trig_to_slots<R, BT>(q, slots);
+    float sn[R::kDim], cs[R::kDim];
+    trig_from_slots<R, BT>(slots, sn, cs);
+    R::fk_coarse(q, sn, cs, tip, [&](int l, float x, float y, float z) {
+        slots[(3 * l + 0) * BT] = x;
+        slots[(3 * l + 1) * BT] = y;
+        slots[(3 * l + 2) * BT] = z;
+    });
+}
+
+// Returns true when this lane's state is collision free. `active` lanes take part; idle lanes only follow the
+// warp-uniform control flow. G = lanes per reference rake (8 for motions, 1 for single states).
+// EDGE: all lanes belong to one motion, so the first hit anywhere ends the whole warp's work.
+//
+// Phase A runs the forward kinematics once, base -> tip, and parks the bounding-sphere centres in shared memory.
+// Phase B tests them against the scene tip -> base (the reference's order: distal links collide first, so colliding
+// states exit early); only when a rake has a coarse hit is the link's frame rebuilt (chain walk from the cached
+// sin / cos) and its fine spheres tested. Phase C: self_collision().
+// This is the ordered-scan variant (scenes without a candidate grid: small or unsorted).
+template <class R, int G, bool EDGE, bool MASKED, int BT>
+__device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots, bool active) {
+    constexpr int FT = 4;  // fine spheres processed together per lane
+    constexpr int POLICY = EDGE ? kAnyHit : kUntilAllHit;
+    const typename R::Tables &tb = R::tables();
+    bool alive = active;  // false once this lane's state is known to collide (or lane idle)
+    Frame F;
+    fk_to_slots<R, BT>(q, slots, F);
+    int have = R::kFrames - 1;  // frame held in F (warp-uniform)
+#pragma unroll 1
+    for (int l = R::kLinks - 1; l >= 0; --l) {
+        const float4 cl = tb.coarse[l];
+        Tile<1> c;
+        c.x[0] = slots[(3 * l + 0) * BT];
+        c.y[0] = slots[(3 * l + 1) * BT];
+        c.z[0] = slots[(3 * l + 2) * BT];
+        c.r[0] = cl.w;
+        const float ext = alive ? sqrtf(fmaf(c.z[0], c.z[0], fmaf(c.y[0], c.y[0], c.x[0] * c.x[0]))) + cl.w : -INFINITY;
+        c.ext[0] = group_max<G>(ext);
+        if (!alive) { c.x[0] = kIdle; c.y[0] = kIdle; c.z[0] = kIdle; }  // idle lanes must never raise the sign bit
+        bool chit = scan_scene<1, kUntilAllHit, MASKED>(sc, c, alive);
+        if (sd.n_pc > 0) chit |= scan_pointclouds<1>(sd, c, alive && !chit);
+        const bool need = group_any<G>(chit && alive) && alive;
+        if (!__any_sync(kFull, need)) continue;
+        frame_seek<R, BT>(F, have, tb.link_frame[l], q, slots);
+        const int fb = tb.link_begin[l], fe = tb.link_begin[l + 1];
+        bool fhit = false;
+#pragma unroll 1
+        for (int f0 = fb; f0 < fe; f0 += FT) {
+            Tile<FT> s;
+#pragma unroll
+            for (int t = 0; t < FT; ++t) {
+                const int fi = min(f0 + t, fe - 1);
+                const float4 fl = tb.fine[fi];
+                frame_apply(F, fl.x, fl.y, fl.z, s.x[t], s.y[t], s.z[t]);
+                s.r[t] = fl.w;
+                const bool on = need && (f0 + t < fe);
+                const float e = on ? sqrtf(fmaf(s.z[t], s.z[t], fmaf(s.y[t], s.y[t], s.x[t] * s.x[t]))) + fl.w : -INFINITY;
+                s.ext[t] = group_max<G>(e);
+                if (!on) { s.ext[t] = -INFINITY; s.x[t] = kIdle; s.y[t] = kIdle; s.z[t] = kIdle; }
+            }
+            fhit |= scan_scene<FT, POLICY, MASKED>(sc, s, need && !fhit);
+            if (sd.n_pc > 0) fhit |= scan_pointclouds<FT>(sd, s, need && !fhit);
+            if (EDGE) {
                 if (__any_sync(kFull, fhit)) return !fhit;
             } else {
                 if (__all_sync(kFull, fhit || !need)) break;
@@ -617,7 +632,116 @@ __device__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, cons
         if (fhit) alive = false;
         if (!EDGE && !__any_sync(kFull, alive)) return false;
     }
+    bool result = false;
+    if (self_collision<R, G, EDGE, BT>(q, slots, alive, result)) return result;
     return alive;
+}
+
+// Rare fall-backs of the grid variant, kept out of line so that they do not sit between the hot loops in the instruction
+// cache: robot spheres larger than the widest grid reach take the ordered scan; point clouds.
+template <int G>
+__device__ __noinline__ bool ordered_scan_one(const Scene *scp, float x, float y, float z, float r, bool on, bool any_mode) {
+    const Scene sc = *scp;
+    Tile<1> s1;
+    s1.x[0] = x; s1.y[0] = y; s1.z[0] = z; s1.r[0] = r;
+    const float e = on ? sqrtf(fmaf(z, z, fmaf(y, y, x * x))) + r : -INFINITY;
+    s1.ext[0] = group_max<G>(e);
+    if (!on) { s1.x[0] = kIdle; s1.y[0] = kIdle; s1.z[0] = kIdle; }
+    return any_mode ? scan_scene<1, kAnyHit, false>(sc, s1, on) : scan_scene<1, kUntilAllHit, false>(sc, s1, on);
+}
+
+__device__ __noinline__ bool pointclouds_one(const CaptView *pcs, int n_pc, float x, float y, float z, float r, bool on) {
+    bool hit = false;
+    for (int p = 0; p < n_pc; ++p)
+        if (on && !hit) hit = capt_collides(pcs[p], x, y, z, r);
+    return hit;
+}
+
+// Block-shared copies of what the out-of-line fall-backs need (taking the address of a kernel parameter or of a register
+// struct would force a stack copy): the staged scene view and the point-cloud views.
+struct SharedViews {
+    Scene sc;
+    CaptView pc[kMaxPointClouds];
+};
+__device__ __forceinline__ void fill_views(const SceneDesc &sd, const Scene &sc, SharedViews &sv) {
+    if (threadIdx.x == 0) {
+        sv.sc = sc;
+        for (int p = 0; p < sd.n_pc; ++p) sv.pc[p] = sd.pc[p];
+    }
+}
+
+// Candidate-grid variant (sorted scenes with a grid). Phase B is one loop over "sphere tasks" -- a link's bounding sphere,
+// or, while a link is being refined, its next fine sphere -- so that the grid walk exists once in the instruction stream.
+template <class R, int G, bool EDGE, int BT>
+__device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
+                                 const SphereLevels<R> &lv, const SharedViews &sv, bool active) {
+    const typename R::Tables &tb = R::tables();
+    bool alive = active;
+    Frame F;
+    fk_to_slots<R, BT>(q, slots, F);
+    int have = R::kFrames - 1;
+    int l = R::kLinks - 1;   // next link whose bounding sphere is to be tested
+    int f = 0, fe = 0;       // fine spheres [f, fe) of the link being refined (f < fe <=> refining)
+    bool need = false, fhit = false;
+#pragma unroll 1
+    for (;;) {
+        const bool fine = f < fe;  // warp-uniform
+        float x, y, z, r;
+        int lvl;
+        bool on;
+        if (!fine) {
+            if (l < 0) break;
+            x = slots[(3 * l + 0) * BT];
+            y = slots[(3 * l + 1) * BT];
+            z = slots[(3 * l + 2) * BT];
+            r = tb.coarse[l].w;
+            lvl = lv.coarse[l];
+            on = alive;
+        } else {
+            const float4 fl = tb.fine[f];
+            frame_apply(F, fl.x, fl.y, fl.z, x, y, z);
+            r = fl.w;
+            lvl = lv.fine[f];
+            on = need && !fhit;
+        }
+        const bool any_mode = EDGE && fine;  // fine hit of an edge: the motion is dead, stop at once
+        bool h;
+        if (lvl >= 0) h = grid_scan_scene(sd.grid[lvl], sc, x, y, z, r, on, any_mode);
+        else h = ordered_scan_one<G>(&sv.sc, x, y, z, r, on, any_mode);
+        if (sd.n_pc > 0) h |= pointclouds_one(sv.pc, sd.n_pc, x, y, z, r, on && !h);
+        if (!fine) {
+            need = group_any<G>(h && alive) && alive;
+            if (__any_sync(kFull, need)) {
+                frame_seek<R, BT>(F, have, tb.link_frame[l], q, slots);
+                f = tb.link_begin[l];
+                fe = tb.link_begin[l + 1];
+                fhit = false;
+            }
+            --l;
+        } else {
+            fhit |= h && on;
+            ++f;
+            if (EDGE) {
+                if (__any_sync(kFull, fhit)) return !fhit;
+            } else {
+                if (__all_sync(kFull, fhit || !need)) f = fe;
+            }
+            if (f >= fe) {
+                if (fhit) alive = false;
+                if (!EDGE && !__any_sync(kFull, alive)) return false;
+            }
+        }
+    }
+    bool result = false;
+    if (self_collision<R, G, EDGE, BT>(q, slots, alive, result)) return result;
+    return alive;
+}
+
+template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT>
+__device__ __forceinline__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
+                                            const SphereLevels<R> &lv, const SharedViews &sv, bool active) {
+    if (GRID) return check_state_grid<R, G, EDGE, BT>(q, sd, sc, slots, lv, sv, active);
+    return check_state_ordered<R, G, EDGE, MASKED, BT>(q, sd, sc, slots, active);
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -658,6 +782,9 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
     stage_scene(smem, sd.blob, sd.blob_floats, &bar);
     const Scene sc = scene_view(sd, smem);
     float *slots = smem + sd.blob_floats + threadIdx.x;
+    __shared__ SharedViews sv;
+    fill_views(sd, sc, sv);
+    __syncthreads();
     constexpr int D = R::kDim;
     const int lane = threadIdx.x & 31;
     const int rake_in_pass = lane >> 3;
@@ -700,7 +827,7 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
         bool ok = true;
         for (int base = 0; base < n; base += 4) {
             const bool active = (base + rake_in_pass) < n;
-            const bool good = check_state<R, 8, true, MASKED, GRID, kBlockThreads>(q, sd, sc, slots, lv, active);
+            const bool good = check_state<R, 8, true, MASKED, GRID, kBlockThreads>(q, sd, sc, slots, lv, sv, active);
             if (__any_sync(kFull, active && !good)) { ok = false; break; }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -724,6 +851,9 @@ validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, 
     stage_scene(smem, sd.blob, sd.blob_floats, &bar);
     const Scene sc = scene_view(sd, smem);
     float *slots = smem + sd.blob_floats + threadIdx.x;
+    __shared__ SharedViews sv;
+    fill_views(sd, sc, sv);
+    __syncthreads();
     constexpr int D = R::kDim;
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -738,7 +868,7 @@ validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, 
 #pragma unroll
         for (int j = 0; j < D; ++j) q[j] = active ? __ldg(qs + i * D + j) : 0.0f;
         // validate_vector with start == goal: block = q + 0 * percents
-        const bool good = check_state<R, 1, false, MASKED, GRID, kBlockThreads>(q, sd, sc, slots, lv, active);
+        const bool good = check_state<R, 1, false, MASKED, GRID, kBlockThreads>(q, sd, sc, slots, lv, sv, active);
         if (active) valid[i] = good ? 1 : 0;
     }
 }
