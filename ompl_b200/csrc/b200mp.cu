@@ -515,7 +515,7 @@ int b200mp_env_commit(b200mp_env *e) {
     const size_t bytes = blob.size() * 4;
     // dynamic shared memory budget: opt-in maximum minus static use (barrier) and a margin
     // and the per-thread bounding-sphere centres the kernels keep beside the scene
-    const size_t budget = static_cast<size_t>(e->ctx->max_smem_optin) - 1024 - std::max(lane_store_bytes<Panda>(), lane_store_bytes<Fetch>());
+    const size_t budget = static_cast<size_t>(e->ctx->max_smem_optin) - 1024 - std::max(lane_store_bytes<Panda>(kStateThreads), lane_store_bytes<Fetch>(kStateThreads));
     if (bytes > budget)
         return fail(B200MP_ERR_CAPACITY, "b200mp_env_commit: scene needs %zu bytes of shared memory, limit %zu", bytes, budget);
     env_free_device(e);
@@ -541,18 +541,18 @@ namespace {
 template <class R>
 int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const float *d_q1, const int2 *d_pairs, int64_t m,
                    int resolution, uint8_t *d_valid, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>();
+    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>(kMotionThreads);
     auto kern = e->desc.n_grid > 0 ? validate_motions_kernel<R, false, true>
                                    : (e->desc.sorted ? validate_motions_kernel<R, false, false> : validate_motions_kernel<R, true, false>);
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMotionThreads, smem));
     if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_motions: kernel does not fit on an SM with %zu B of scene", smem);
     const long long warps_needed = m;
-    long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + (kMotionThreads / 32) - 1) / (kMotionThreads / 32));
     blocks = std::max<long long>(blocks, 1);
     B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), kBlockThreads, smem, st>>>(e->desc, d_q0, d_q1, d_pairs, m, resolution, d_valid,
+    kern<<<static_cast<unsigned>(blocks), kMotionThreads, smem, st>>>(e->desc, d_q0, d_q1, d_pairs, m, resolution, d_valid,
                                                                      static_cast<LaunchCounters *>(c->d_counters));
     B200_CUDA(cudaGetLastError());
     c->launches.fetch_add(1);
@@ -561,18 +561,18 @@ int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const 
 
 template <class R>
 int launch_states(b200mp_ctx *c, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>();
+    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>(kStateThreads);
     auto kern = e->desc.n_grid > 0 ? validate_states_kernel<R, false, true>
                                    : (e->desc.sorted ? validate_states_kernel<R, false, false> : validate_states_kernel<R, true, false>);
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStateThreads, smem));
     if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_states: kernel does not fit on an SM with %zu B of scene", smem);
     const long long warps_needed = (m + 31) / 32;
-    long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + (kStateThreads / 32) - 1) / (kStateThreads / 32));
     blocks = std::max<long long>(blocks, 1);
     B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), kBlockThreads, smem, st>>>(e->desc, d_q, m, d_valid, static_cast<LaunchCounters *>(c->d_counters));
+    kern<<<static_cast<unsigned>(blocks), kStateThreads, smem, st>>>(e->desc, d_q, m, d_valid, static_cast<LaunchCounters *>(c->d_counters));
     B200_CUDA(cudaGetLastError());
     c->launches.fetch_add(1);
     return B200MP_OK;
