@@ -297,7 +297,9 @@ __global__ void knn_all_distances_kernel(const double *__restrict__ pts, const f
 // with a rigorous error bound, fp64 re-evaluation of survivors in the reference's operation order). Pruning uses lower
 // bounds only, so the result is the same exact (distance, id)-ordered top-k as the exhaustive scan.
 constexpr int kCellTile = 512;
-constexpr int kCellThreads = 128;  // queries per block of the cell kernel
+constexpr int kCellThreads = 128;  // threads per block of the cell kernel
+constexpr int kCellQPT = 2;        // queries per thread
+constexpr int kCellQueries = kCellThreads * kCellQPT;  // queries per block
 constexpr int kRoundCells = kCellThreads;
 
 __global__ void knn_gather_pivots_kernel(const float *__restrict__ feat, long long n, int P, int fw, float *__restrict__ pivots) {
@@ -399,10 +401,10 @@ __global__ void knn_permute_kernel(const float4 *__restrict__ feat, const double
     orig[p] = static_cast<int>(i);
 }
 
-// blocks needed per query cell: ceil(#queries in the cell / kCellThreads)
+// blocks needed per query cell: ceil(#queries in the cell / kCellQueries)
 __global__ void knn_cell_blocks_kernel(const int *__restrict__ q_start, int P, int *__restrict__ nblk, int parts, int part) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < P) nblk[c] = (c % parts == part) ? (q_start[c + 1] - q_start[c] + kCellThreads - 1) / kCellThreads : 0;
+    if (c < P) nblk[c] = (c % parts == part) ? (q_start[c + 1] - q_start[c] + kCellQueries - 1) / kCellQueries : 0;
 }
 
 __global__ void knn_query_order_kernel(const int *__restrict__ cell, const int *__restrict__ pos, long long nq, int *__restrict__ order,
@@ -441,6 +443,9 @@ __global__ void knn_cell_bounds_kernel(const float *__restrict__ feat_s, const i
     }
 }
 
+// Each thread owns kCellQPT queries (every broadcast candidate read from shared memory feeds 2 x 4 FFMAs per float4); the
+// queries' top-k lists live in their slots of the `partial` output (global memory, touched only by the rare survivors),
+// so shared memory holds nothing but the two candidate tiles.
 template <int NV>
 __global__ void __launch_bounds__(kCellThreads)
 knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ pts_s, const int *__restrict__ orig, const int *__restrict__ cell_start,
@@ -448,6 +453,7 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
                  const int *__restrict__ q_order, const int *__restrict__ q_start, const int *__restrict__ blk_start, long long nq, const long long *__restrict__ self_ids,
                  long long self_base, int use_self, int kk, float err_scale, float cmax, Partial *__restrict__ partial,
                  unsigned long long *__restrict__ rows_visited) {
+    constexpr int QPT = kCellQPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long bars[2];
     __shared__ int s_job_row[2], s_job_cnt[2];
@@ -457,12 +463,10 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
     __shared__ float s_wlo[kCellThreads / 32][24], s_whi[kCellThreads / 32][24], s_qlo[24], s_qhi[24];
     __shared__ float s_wr[kCellThreads / 32];
     __shared__ float s_rblk;
-    float4 *tiles = reinterpret_cast<float4 *>(smem_raw);                                           // [2][kCellTile][NV]
-    double *ld2 = reinterpret_cast<double *>(smem_raw + 2 * kCellTile * NV * sizeof(float4));      // [kk][threads]
-    int *lidx = reinterpret_cast<int *>(ld2 + static_cast<size_t>(kk) * kCellThreads);
+    float4 *tiles = reinterpret_cast<float4 *>(smem_raw);  // [2][kCellTile][NV]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // block -> (query cell, chunk of kCellThreads queries of that cell): all queries of a block live in one cell, so the
+    // block -> (query cell, chunk of kCellQueries queries of that cell): all queries of a block live in one cell, so the
     // block's query box is (part of) that cell's box
     if (static_cast<int>(blockIdx.x) >= blk_start[P]) return;
     int own;
@@ -474,39 +478,50 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
         }
         own = lo_c;  // blk_start[own] <= blockIdx.x < blk_start[own + 1]: cells without blocks can never satisfy this
     }
-    const long long qs = static_cast<long long>(q_start[own]) + static_cast<long long>(blockIdx.x - blk_start[own]) * kCellThreads + tid;
-    const bool has_q = qs < q_start[own + 1];
-    const long long qi = has_q ? q_order[qs] : 0;
-
-    float m2q[4 * NV];
-    float qn = 0.f;
+    bool has_q[QPT];
+    long long qi[QPT], self[QPT];
+    float m2q[QPT][4 * NV], qn[QPT], err[QPT], thr[QPT];
+    double worst[QPT];
+    int worst_idx[QPT], worst_slot[QPT];
 #pragma unroll
-    for (int j = 0; j < 4 * NV; ++j) m2q[j] = 0.f;
-    double qd[4 * NV - 1];
+    for (int t = 0; t < QPT; ++t) {
+        const long long qs = static_cast<long long>(q_start[own]) + static_cast<long long>(blockIdx.x - blk_start[own]) * kCellQueries +
+                             t * kCellThreads + tid;
+        has_q[t] = qs < q_start[own + 1];
+        qi[t] = has_q[t] ? q_order[qs] : 0;
+        qn[t] = 0.f;
+        // (the fp64 query is not kept in registers: the rare exact re-evaluations read it back through L1)
 #pragma unroll
-    for (int j = 0; j < 4 * NV - 1; ++j) {
-        qd[j] = (has_q && j < dim) ? q64[qi * dim + j] : 0.0;
-        const float qf = static_cast<float>(qd[j]);
-        m2q[j] = -2.0f * qf;
-        qn = fmaf(qf, qf, qn);
+        for (int j = 0; j < 4 * NV - 1; ++j) {
+            const float qf = (has_q[t] && j < dim) ? static_cast<float>(q64[qi[t] * dim + j]) : 0.f;
+            m2q[t][j] = -2.0f * qf;
+            qn[t] = fmaf(qf, qf, qn[t]);
+        }
+        m2q[t][4 * NV - 1] = 1.0f;
+        self[t] = !use_self ? -1 : (self_ids ? (has_q[t] ? self_ids[qi[t]] : -1) : self_base + qi[t]);
+        const float qnorm = sqrtf(qn[t]);
+        err[t] = err_scale * (qnorm + cmax) * (qnorm + cmax);
+        if (has_q[t]) {
+            Partial *lst = partial + qi[t] * kk;
+            for (int s = 0; s < kk; ++s) {
+                Partial e;
+                e.d2 = INFINITY; e.idx = -1; e.pad = 0;
+                lst[s] = e;
+            }
+        }
+        worst[t] = INFINITY;
+        worst_idx[t] = 0x7fffffff;
+        worst_slot[t] = 0;
+        thr[t] = has_q[t] ? INFINITY : -INFINITY;
     }
-    m2q[4 * NV - 1] = 1.0f;
-    const long long self = !use_self ? -1 : (self_ids ? (has_q ? self_ids[qi] : -1) : self_base + qi);
-    const float qnorm = sqrtf(qn);
-    const float err = err_scale * (qnorm + cmax) * (qnorm + cmax);
-
-    for (int s = 0; s < kk; ++s) {
-        ld2[s * kCellThreads + tid] = INFINITY;
-        lidx[s * kCellThreads + tid] = -1;
-    }
-    double worst = INFINITY;
-    int worst_idx = 0x7fffffff, worst_slot = 0;
-    float thr = has_q ? INFINITY : -INFINITY;
 
     // ---- bounding box of the block's queries (fp32 values of the queries, widened like the cell boxes)
 #pragma unroll
     for (int j = 0; j < 4 * NV - 1; ++j) {
-        float mn = has_q ? -0.5f * m2q[j] : INFINITY, mx = has_q ? -0.5f * m2q[j] : -INFINITY;
+        float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < QPT; ++t)
+            if (has_q[t]) { mn = fminf(mn, -0.5f * m2q[t][j]); mx = fmaxf(mx, -0.5f * m2q[t][j]); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, o));
@@ -549,6 +564,33 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
         bulk_g2s(tiles + static_cast<size_t>(slot) * kCellTile * NV, feat_s + static_cast<long long>(gb) * NV, bytes, &bars[slot]);
         gb += cnt;
     };
+    // exact re-evaluation of a filter survivor (database row r) for query slot t, the reference's arithmetic
+    // (RealVectorStateSpace.cpp:230-242), and insertion into that query's list
+    auto survivor = [&](int t, long long r) {
+        const int id = orig[r];
+        if (id == self[t]) return;
+        double d2 = 0.0;
+        for (int j2 = 0; j2 < dim; ++j2) {
+            const double diff = pts_s[r * dim + j2] - q64[qi[t] * dim + j2];
+            d2 = __dadd_rn(d2, __dmul_rn(diff, diff));  // no FMA contraction: bit-identical to the reference's x86-64 doubles
+        }
+        if (d2 < worst[t] || (d2 == worst[t] && id < worst_idx[t])) {
+            Partial *lst = partial + qi[t] * kk;
+            Partial e;
+            e.d2 = d2; e.idx = id; e.pad = 0;
+            lst[worst_slot[t]] = e;
+            // new worst = lexicographic max of (d2, idx) over the list
+            worst[t] = -1.0;
+            worst_idx[t] = -1;
+            for (int s2 = 0; s2 < kk; ++s2) {
+                const Partial v = lst[s2];
+                const int key = v.idx < 0 ? 0x7fffffff : v.idx;
+                if (v.d2 > worst[t] || (v.d2 == worst[t] && key > worst_idx[t])) { worst[t] = v.d2; worst_idx[t] = key; worst_slot[t] = s2; }
+            }
+            // s_exact = d2 - |q|^2 ; pass while s_approx < worst - qn + err (rounded up)
+            thr[t] = (worst[t] == INFINITY) ? INFINITY : __double2float_ru(worst[t] - static_cast<double>(qn[t])) + err[t];
+        }
+    };
     unsigned long long visited = 0;  // rows streamed by this block (thread 0), for the pruning statistics
     auto run_list = [&]() {
         if (tid == 0) {
@@ -565,49 +607,33 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
             mbar_wait(&bars[slot], (it >> 1) & 1);
             const float4 *tile = tiles + static_cast<size_t>(slot) * kCellTile * NV;
             for (int c0 = 0; c0 < cnt; c0 += 4) {
-                float sv[4];
+                float sv[QPT][4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const float4 *row = tile + static_cast<size_t>(min(c0 + u, cnt - 1)) * NV;
-                    float acc = 0.f;
+                    // rows past cnt (same buffer, stale or unwritten) may be read: whatever they yield is dropped below by index
+                    const float4 *row = tile + (c0 + u) * NV;
+#pragma unroll
+                    for (int t = 0; t < QPT; ++t) sv[t][u] = 0.f;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
                         const float4 c = row[v];
-                        acc = fmaf(m2q[4 * v + 0], c.x, acc);
-                        acc = fmaf(m2q[4 * v + 1], c.y, acc);
-                        acc = fmaf(m2q[4 * v + 2], c.z, acc);
-                        acc = fmaf(m2q[4 * v + 3], c.w, acc);
-                    }
-                    sv[u] = acc;
-                }
-                const bool any = (sv[0] < thr) | (sv[1] < thr) | (sv[2] < thr) | (sv[3] < thr);
-                if (any) {
-#pragma unroll 1
-                    for (int u = 0; u < 4; ++u) {
-                        if (!(sv[u] < thr) || c0 + u >= cnt) continue;
-                        const long long r = row0 + c0 + u;
-                        const int id = orig[r];
-                        if (id == self) continue;
-                        double d2 = 0.0;
 #pragma unroll
-                        for (int j2 = 0; j2 < 4 * NV - 1; ++j2) {
-                            if (j2 < dim) {
-                                const double diff = pts_s[r * dim + j2] - qd[j2];
-                                d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
-                            }
+                        for (int t = 0; t < QPT; ++t) {
+                            sv[t][u] = fmaf(m2q[t][4 * v + 0], c.x, sv[t][u]);
+                            sv[t][u] = fmaf(m2q[t][4 * v + 1], c.y, sv[t][u]);
+                            sv[t][u] = fmaf(m2q[t][4 * v + 2], c.z, sv[t][u]);
+                            sv[t][u] = fmaf(m2q[t][4 * v + 3], c.w, sv[t][u]);
                         }
-                        if (d2 < worst || (d2 == worst && id < worst_idx)) {
-                            ld2[worst_slot * kCellThreads + tid] = d2;
-                            lidx[worst_slot * kCellThreads + tid] = id;
-                            worst = -1.0;
-                            worst_idx = -1;
-                            for (int s2 = 0; s2 < kk; ++s2) {
-                                const double v = ld2[s2 * kCellThreads + tid];
-                                const int vi = lidx[s2 * kCellThreads + tid];
-                                const int key = vi < 0 ? 0x7fffffff : vi;
-                                if (v > worst || (v == worst && key > worst_idx)) { worst = v; worst_idx = key; worst_slot = s2; }
-                            }
-                            thr = (worst == INFINITY) ? INFINITY : __double2float_ru(worst - static_cast<double>(qn)) + err;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < QPT; ++t) {
+                    const bool any = (sv[t][0] < thr[t]) | (sv[t][1] < thr[t]) | (sv[t][2] < thr[t]) | (sv[t][3] < thr[t]);
+                    if (any) {
+#pragma unroll 1
+                        for (int u = 0; u < 4; ++u) {
+                            if (!(sv[t][u] < thr[t]) || c0 + u >= cnt) continue;
+                            survivor(t, static_cast<long long>(row0) + c0 + u);
                         }
                     }
                 }
@@ -619,7 +645,10 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
     };
     // block-wide maximum of the queries' squared k-th distances (rounded up)
     auto refresh_bound = [&]() {
-        float r2 = !has_q ? -INFINITY : (worst == INFINITY ? INFINITY : __double2float_ru(worst) * 1.000001f);
+        float r2 = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < QPT; ++t)
+            if (has_q[t]) r2 = fmaxf(r2, worst[t] == INFINITY ? INFINITY : __double2float_ru(worst[t]) * 1.000001f);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(kFullMask, r2, o));
         if (lane == 0) s_wr[wid] = r2;
@@ -640,7 +669,7 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
         run_list();
     }
     refresh_bound();
-    // ---- every other cell, 256 at a time: one thread tests one cell's box against the block's query box. Two sweeps: first
+    // ---- every other cell, kRoundCells at a time: one thread tests one cell's box against the block's query box. Two sweeps: first
     // the cells whose box overlaps the query box (they hold almost all true neighbours, so afterwards the k-th distances
     // are nearly final), then the remaining cells that lie within the block's worst k-th distance.
     for (int sweep = 0; sweep < 2; ++sweep) {
@@ -671,16 +700,6 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
         }
     }
     if (tid == 0 && rows_visited) atomicAdd(rows_visited, visited);
-    if (has_q) {
-        Partial *out = partial + qi * kk;
-        for (int s = 0; s < kk; ++s) {
-            Partial p;
-            p.d2 = ld2[s * kCellThreads + tid];
-            p.idx = lidx[s * kCellThreads + tid];
-            p.pad = 0;
-            out[s] = p;
-        }
-    }
 }
 
 
@@ -1050,12 +1069,12 @@ int knn_build_index(b200mp_knn *k, cudaStream_t st) {
 template <int NV>
 int launch_cells(b200mp_knn *k, const double *d_q, const int *q_order, const int *q_start, const int *blk_start, long long nq,
                  const long long *d_self, long long self_base, int use_self, int kk, Partial *d_partial, cudaStream_t st) {
-    const size_t smem = 2 * kCellTile * NV * sizeof(float4) + static_cast<size_t>(kk) * kCellThreads * (sizeof(double) + sizeof(int));
+    const size_t smem = 2 * kCellTile * NV * sizeof(float4);
     auto kern = knn_cells_kernel<NV>;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const float err_scale = 4.0f * (4 * NV + 2) * 5.96e-8f;
-    // upper bound on the number of blocks (sum over cells of ceil(queries / kCellThreads)); surplus blocks exit at once
-    const unsigned grid = static_cast<unsigned>(nq / kCellThreads + k->index_P + 1);
+    // upper bound on the number of blocks (sum over cells of ceil(queries / kCellQueries)); surplus blocks exit at once
+    const unsigned grid = static_cast<unsigned>(nq / kCellQueries + k->index_P + 1);
     kern<<<grid, kCellThreads, smem, st>>>(k->ix_feat, k->ix_pts, k->ix_orig, k->ix_start, k->ix_lo, k->ix_hi, k->index_P, k->dim, d_q, q_order,
                                            q_start, blk_start, nq, d_self, self_base, use_self, kk, err_scale, k->cmax, d_partial,
                                            k->d_rows_visited);
