@@ -96,6 +96,14 @@ int b200mp_capt_build(const float *xyz, int64_t n, float r_min, float r_max, flo
 void b200mp_capt_destroy(b200mp_capt *capt);
 int b200mp_capt_sizes(const b200mp_capt *capt, int64_t *sizes);
 int b200mp_capt_export(const b200mp_capt *capt, float *tests, float *aabbs, uint32_t *aff_starts, float *aff, float *top);
+/* vamp::collision::filter_pointcloud (external/vamp/src/impl/vamp/collision/filter.hh:176-274; Python entry
+ * vamp.filter_pointcloud, bindings/environment.cc:168-190) on the device: cull to the range ball around `origin` and the
+ * workspace box (when cull != 0), then six Morton-curve passes that drop every point within min_dist of the last point
+ * kept. xyz[n][3] and out_xyz[>= n + 1][3] are host buffers; *out_n receives the number of points written (the reference
+ * can emit point 0 one extra time, hence n + 1). Points with equal curve codes keep their previous relative order (the
+ * reference's unstable sort leaves that order unspecified). */
+int b200mp_filter_pointcloud(b200mp_ctx *ctx, const float *xyz, int64_t n, float min_dist, float max_range, const float *origin,
+                             const float *ws_min, const float *ws_max, int cull, float *out_xyz, int64_t *out_n);
 /* Sort every shape list by min_distance (Environment::sort). Obstacles are otherwise tested in insertion
  * order with the reference's ordered-scan-with-break semantics. */
 int b200mp_env_sort(b200mp_env *env);

@@ -137,7 +137,8 @@ knn_tiled_kernel(const float4 *__restrict__ feat, const double *__restrict__ pts
             float sv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float4 *row = tile + static_cast<size_t>(min(c0 + u, cnt - 1)) * NV;
+                // rows past cnt (same buffer, stale or unwritten) may be read: whatever they yield is dropped below by index
+                const float4 *row = tile + (c0 + u) * NV;
                 float acc = 0.f;
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {

@@ -60,6 +60,7 @@ def load_library():
     L.b200mp_env_add_pointcloud.argtypes = [_vp, _vp, _i64, C.c_float, C.c_float, C.c_float]
     L.b200mp_capt_build.argtypes = [_vp, _i64, C.c_float, C.c_float, C.c_float, C.POINTER(_vp)]
     L.b200mp_capt_destroy.argtypes = [_vp]
+    L.b200mp_filter_pointcloud.argtypes = [_vp, _vp, _i64, C.c_float, C.c_float, _vp, _vp, _vp, C.c_int, _vp, _vp]
     L.b200mp_capt_sizes.argtypes = [_vp, _vp]
     L.b200mp_capt_export.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
     L.b200mp_env_sort.argtypes = [_vp]
@@ -191,6 +192,16 @@ class Context:
         return out.value
 
     # ---- host-buffer entry points (what the OMPL adapters call) ----
+    def filter_pointcloud(self, xyz, min_dist: float, max_range: float, origin, ws_min, ws_max, cull: bool = True) -> np.ndarray:
+        """vamp.filter_pointcloud on the device (b200mp_filter_pointcloud); returns the kept points [m][3] in the reference's order."""
+        pts = _host(np.asarray(xyz).reshape(-1, 3), np.float32)
+        o, lo, hi = (_host(np.asarray(v).reshape(3), np.float32) for v in (origin, ws_min, ws_max))
+        out = np.empty((pts.shape[0] + 1, 3), np.float32)
+        m = C.c_int64(0)
+        _check(self._L.b200mp_filter_pointcloud(self._h, pts.ctypes.data, pts.shape[0], float(min_dist), float(max_range), o.ctypes.data,
+                                                lo.ctypes.data, hi.ctypes.data, int(bool(cull)), out.ctypes.data, C.byref(m)))
+        return out[:m.value].copy()
+
     def validate_states(self, robot: str, env: "Environment", q) -> np.ndarray:
         q = np.asarray(q)
         dim = robot_info(robot)["dim"]

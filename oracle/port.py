@@ -54,6 +54,8 @@ def lib():
                          _i64p, _f64p, C.c_int]
     L.or_knn_radius.argtypes = [_f64p, C.c_int64, _f64p, C.c_int, C.c_double, C.c_int, C.c_double, _i64p, _f64p, C.c_int64]
     L.or_knn_radius.restype = C.c_int64
+    L.orf_filter_pointcloud.argtypes = [_f32p, C.c_int64, C.c_float, C.c_float, _f32p, _f32p, _f32p, C.c_int, _f32p, C.c_int64]
+    L.orf_filter_pointcloud.restype = C.c_int64
     _lib = L
     return L
 
@@ -228,3 +230,12 @@ def prm_edge_list(nbr: np.ndarray, dist: np.ndarray, q_first: int = 0, q_count: 
             e.append((min(i, j), max(i, j)))
             w.append(dist[i - q_first, s])
     return np.array(e, np.int32).reshape(-1, 2), np.array(w, np.float64)
+
+
+def filter_pointcloud(xyz, min_dist, max_range, origin, ws_min, ws_max, cull=True) -> np.ndarray:
+    """Restatement of vamp::collision::filter_pointcloud (oracle_filter.cpp; collision/filter.hh:176-274)."""
+    xyz = _f32(xyz).reshape(-1, 3)
+    out = np.empty((len(xyz) + 1, 3), np.float32)
+    n = lib().orf_filter_pointcloud(xyz, len(xyz), float(min_dist), float(max_range), _f32(origin), _f32(ws_min), _f32(ws_max),
+                                    int(bool(cull)), out, len(out))
+    return out[:n].copy()

@@ -151,3 +151,24 @@ extern "C"
 
     int refv_hardware_threads() { return static_cast<int>(std::thread::hardware_concurrency()); }
 }
+
+// ---- point-cloud filter (collision/filter.hh:176-274), unmodified; returns the number of points kept, writes at most cap
+#include <vamp/collision/filter.hh>
+extern "C" std::int64_t refv_filter_pointcloud(const float *xyz, std::int64_t n, float min_dist, float max_range, const float *origin,
+                                               const float *ws_min, const float *ws_max, int cull, float *out, std::int64_t cap)
+{
+    std::vector<vc::Point> pts(static_cast<std::size_t>(n));
+    for (std::int64_t i = 0; i < n; ++i)
+    {
+        pts[i] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+    }
+    const auto kept = vc::filter_pointcloud(pts, min_dist, max_range, vc::Point{origin[0], origin[1], origin[2]},
+                                            vc::Point{ws_min[0], ws_min[1], ws_min[2]}, vc::Point{ws_max[0], ws_max[1], ws_max[2]}, cull != 0);
+    for (std::size_t i = 0; i < kept.size() && static_cast<std::int64_t>(i) < cap; ++i)
+    {
+        out[3 * i] = kept[i][0];
+        out[3 * i + 1] = kept[i][1];
+        out[3 * i + 2] = kept[i][2];
+    }
+    return static_cast<std::int64_t>(kept.size());
+}

@@ -47,6 +47,8 @@ def lib():
     L.refv_capt_sizes.argtypes = [C.c_void_p, C.c_int, _i64p]
     L.refv_capt_export.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _u32p, _f32p, _f32p, _f32p]
     L.refv_capt_collides.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int64, _u8p]
+    L.refv_filter_pointcloud.argtypes = [_f32p, C.c_int64, C.c_float, C.c_float, _f32p, _f32p, _f32p, C.c_int, _f32p, C.c_int64]
+    L.refv_filter_pointcloud.restype = C.c_int64
     for r in ("panda", "fetch"):
         getattr(L, f"refv_{r}_bounds").argtypes = [_f32p, _f32p]
         getattr(L, f"refv_{r}_validate_motions").argtypes = [
@@ -170,3 +172,12 @@ def sphere_fk(robot: str, q) -> np.ndarray:
 
 def hardware_threads() -> int:
     return int(lib().refv_hardware_threads())
+
+
+def filter_pointcloud(xyz, min_dist, max_range, origin, ws_min, ws_max, cull=True) -> np.ndarray:
+    """vamp::collision::filter_pointcloud (collision/filter.hh:176-274), compiled as is."""
+    xyz = _f32(xyz).reshape(-1, 3)
+    out = np.empty((len(xyz) + 1, 3), np.float32)
+    n = lib().refv_filter_pointcloud(xyz, len(xyz), float(min_dist), float(max_range), _f32(origin), _f32(ws_min), _f32(ws_max),
+                                     int(bool(cull)), out, len(out))
+    return out[:n].copy()
