@@ -12,6 +12,7 @@
 
 #include "../../include/b200mp.h"
 #include "validate.cuh"
+#include "capt_order.cuh"
 #include "robots/panda_gen.cuh"
 #include "robots/fetch_gen.cuh"
 #include "host_common.hpp"
@@ -42,6 +43,7 @@ struct HCuboid { float c[3], a1[3], a2[3], a3[3], h[3], min_d; };
 struct DeviceCapt {
     float *tests = nullptr, *aabbs = nullptr, *aff = nullptr;
     uint32_t *aff_starts = nullptr;
+    unsigned short *pref = nullptr;
     CaptView view{};
 };
 
@@ -317,6 +319,7 @@ void b200mp_env_destroy(b200mp_env *e) {
         cudaFree(p.aabbs);
         cudaFree(p.aff);
         cudaFree(p.aff_starts);
+        cudaFree(p.pref);
     }
     delete e;
 }
@@ -398,10 +401,26 @@ int b200mp_env_add_capt(b200mp_env *e, int nlog2, const float *tests, const floa
     B200_CUDA(cudaMemcpy(d.aabbs, aabbs, nl * 6 * 4, cudaMemcpyHostToDevice));
     B200_CUDA(cudaMemcpy(d.aff_starts, aff_starts, (nl + 1) * 4, cudaMemcpyHostToDevice));
     if (n_aff8) B200_CUDA(cudaMemcpy(d.aff, aff, 3 * n_aff8 * 8 * 4, cudaMemcpyHostToDevice));
+    if (n_aff8 > 0) {
+        // device copy: lists ordered by distance from the leaf's cell + prefix table (capt_order.cuh)
+        float *boxes = nullptr, *sorted = nullptr;
+        B200_CUDA(cudaMalloc(&boxes, nl * 6 * 4));
+        B200_CUDA(cudaMalloc(&sorted, static_cast<size_t>(3) * n_aff8 * 8 * 4));
+        B200_CUDA(cudaMalloc(&d.pref, nl * kCaptBuckets * sizeof(unsigned short)));
+        capt_cell_boxes_kernel<<<static_cast<unsigned>((nl + 255) / 256), 256>>>(d.tests, nlog2, static_cast<unsigned>(nl), boxes);
+        capt_order_leaf_kernel<<<static_cast<unsigned>(nl), 256>>>(d.aff, sorted, n_aff8, d.aff_starts, boxes, d.pref);
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaDeviceSynchronize());
+        e->ctx->launches.fetch_add(2);
+        cudaFree(boxes);
+        cudaFree(d.aff);
+        d.aff = sorted;
+    }
     d.view.tests = d.tests;
     d.view.aabbs = d.aabbs;
     d.view.aff_starts = d.aff_starts;
     d.view.aff = d.aff;
+    d.view.pref = d.pref;
     d.view.n_aff8 = n_aff8;
     std::memcpy(d.view.top, top, 24);
     d.view.r_point = r_point;

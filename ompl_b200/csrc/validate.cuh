@@ -27,7 +27,8 @@ struct CaptView {
     const float *tests;
     const float *aabbs;           // [leaf][6]
     const uint32_t *aff_starts;   // [leaves + 1], units of 8-point vectors
-    const float *aff;             // [3][n_aff8 * 8]
+    const float *aff;             // [3][n_aff8 * 8]; on the device every leaf's list is ordered by distance from the leaf's cell
+    const unsigned short *pref;   // [leaf][kCaptBuckets]: records of the list within capt_reach(k) of the cell (0xffff: whole list), or null
     long long n_aff8;
     float top[6];
     float r_point;
@@ -373,51 +374,97 @@ __device__ __forceinline__ float aabb_distsq(const float *bb, float x, float y, 
     return d0 * d0 + d1 * d1 + d2 * d2;
 }
 
-// One sphere against one tree (collision/capt.hh:366-407 / :425-506): top AABB reject, nlog2 dependent loads down
-// the implicit tree, leaf AABB reject, then the leaf's affordance list; hit <=> distsq <= (r + r_point)^2.
-__device__ __forceinline__ bool capt_collides(const CaptView &t, float x, float y, float z, float r) {
-    r += t.r_point;
-    const float rsq = r * r;
-    if (aabb_distsq(t.top, x, y, z) > rsq) return false;
-    unsigned idx = 0;
-    float c0 = x, c1 = y, c2 = z;
-    for (int i = 0; i < t.nlog2; ++i) {
-        idx = 2u * idx + 1u + (c0 >= __ldg(t.tests + idx) ? 1u : 0u);
-        const float tmp = c0; c0 = c1; c1 = c2; c2 = tmp;  // cycle x, y, z
-    }
-    const unsigned leaf = idx - static_cast<unsigned>(t.n_tests);
-    const float *bb = t.aabbs + 6u * leaf;
-    float lb[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) lb[k] = __ldg(bb + k);
-    if (aabb_distsq(lb, x, y, z) > rsq) return false;
-    const unsigned beg = __ldg(t.aff_starts + leaf), end = __ldg(t.aff_starts + leaf + 1);
-    const float *ax = t.aff, *ay = t.aff + t.n_aff8 * 8, *az = t.aff + 2 * t.n_aff8 * 8;
-    for (unsigned i = beg * 8u; i < end * 8u; i += 4u) {
-        const float4 px = __ldg(reinterpret_cast<const float4 *>(ax + i));
-        const float4 py = __ldg(reinterpret_cast<const float4 *>(ay + i));
-        const float4 pz = __ldg(reinterpret_cast<const float4 *>(az + i));
-        float dx = px.x - x, dy = py.x - y, dz = pz.x - z;
-        bool h = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= rsq;
-        dx = px.y - x; dy = py.y - y; dz = pz.y - z;
-        h |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= rsq;
-        dx = px.z - x; dy = py.z - y; dz = pz.z - z;
-        h |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= rsq;
-        dx = px.w - x; dy = py.w - y; dz = pz.w - z;
-        h |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= rsq;
-        if (h) return true;
-    }
-    return false;
+// A leaf's affordance list holds every point within r_max + r_point of the leaf's cell (capt.hh:123-285). A query sphere
+// whose centre lies in the cell can only touch points no farther from the cell than its own radius, so the device copy of
+// the tree keeps each list ordered by distance from the cell and a small table of prefix lengths for a ladder of radii:
+// a fine sphere of 3 cm then tests a few dozen points instead of the ~1000 the list holds for the 24 cm bounding spheres.
+// Same decisions as the full scan (the skipped points cannot be within reach).
+constexpr int kCaptBuckets = 8;
+__host__ __device__ constexpr float capt_reach(int k) {
+    float v = 0.015f;
+    for (int i = 0; i < k; ++i) v *= 1.5f;
+    return v;
 }
 
-template <int T>
+// One sphere per lane against one tree (collision/capt.hh:366-407 / :425-506). Per lane: top AABB reject, nlog2 dependent
+// loads down the implicit tree, leaf AABB reject. The lists of the lanes that are left are then scanned by the whole warp,
+// one list at a time with coalesced loads (lane j takes points j, j + 32, ...); hit <=> distsq <= (r + r_point)^2.
+// Must be called by all 32 lanes; r is warp-uniform. any_mode: stop at the first lane found in collision.
+__device__ __forceinline__ bool capt_collides_warp(const CaptView &t, float x, float y, float z, float r, bool on, bool any_mode) {
+    r += t.r_point;
+    const float rsq = r * r;
+    int bucket = kCaptBuckets;
+    const float reach = r * 1.0001f + 1.0e-6f;  // slack for the rounding of the stored cell distances
+#pragma unroll
+    for (int k = kCaptBuckets - 1; k >= 0; --k)
+        if (reach <= capt_reach(k)) bucket = k;
+    bool pend = on && !(aabb_distsq(t.top, x, y, z) > rsq);
+    unsigned pb = 0, pe = 0;
+    if (pend) {
+        unsigned idx = 0;
+        float c0 = x, c1 = y, c2 = z;
+        for (int i = 0; i < t.nlog2; ++i) {
+            idx = 2u * idx + 1u + (c0 >= __ldg(t.tests + idx) ? 1u : 0u);
+            const float tmp = c0; c0 = c1; c1 = c2; c2 = tmp;  // cycle x, y, z
+        }
+        const unsigned leaf = idx - static_cast<unsigned>(t.n_tests);
+        const float *bb = t.aabbs + 6u * leaf;
+        float lb[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) lb[k] = __ldg(bb + k);
+        if (aabb_distsq(lb, x, y, z) > rsq) {
+            pend = false;
+        } else {
+            const unsigned beg = __ldg(t.aff_starts + leaf);
+            unsigned n = __ldg(t.aff_starts + leaf + 1) - beg;
+            if (t.pref != nullptr && bucket < kCaptBuckets) {
+                const unsigned pf = __ldg(t.pref + static_cast<size_t>(leaf) * kCaptBuckets + bucket);
+                if (pf != 0xffffu) n = min(n, pf);
+            }
+            pb = beg * 8u;
+            pe = pb + n * 8u;
+            pend = n > 0;
+        }
+    }
+    const float *ax = t.aff, *ay = t.aff + t.n_aff8 * 8, *az = t.aff + 2 * t.n_aff8 * 8;
+    const unsigned lane = threadIdx.x & 31u;
+    bool hit = false;
+    unsigned todo = __ballot_sync(kFull, pend);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float qx = __shfl_sync(kFull, x, src), qy = __shfl_sync(kFull, y, src), qz = __shfl_sync(kFull, z, src);
+        const unsigned sb = __shfl_sync(kFull, pb, src), se = __shfl_sync(kFull, pe, src);
+        bool found = false;
+#pragma unroll 1
+        for (unsigned base = sb; base < se; base += 128u) {
+            bool h = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned i = base + 32u * u + lane;
+                if (i < se) {
+                    const float dx = __ldg(ax + i) - qx, dy = __ldg(ay + i) - qy, dz = __ldg(az + i) - qz;
+                    h |= fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= rsq;
+                }
+            }
+            if (__any_sync(kFull, h)) { found = true; break; }
+        }
+        if (static_cast<int>(lane) == src) hit = found;
+        if (any_mode && found) break;
+    }
+    return hit;
+}
+
+template <int T, int POLICY>
 __device__ __forceinline__ bool scan_pointclouds(const SceneDesc &d, const Tile<T> &s, bool participating) {
     bool hit = false;
     for (int p = 0; p < d.n_pc; ++p) {
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             // idle slots carry ext = -inf
-            if (participating && s.ext[t] > -1e30f && !hit) hit = capt_collides(d.pc[p], s.x[t], s.y[t], s.z[t], s.r[t]);
+            const bool on = participating && s.ext[t] > -1e30f && !hit;
+            if (POLICY == kAnyHit && __any_sync(kFull, hit)) return hit;
+            hit |= capt_collides_warp(d.pc[p], s.x[t], s.y[t], s.z[t], s.r[t], on, POLICY == kAnyHit);
         }
     }
     return hit;
@@ -601,7 +648,7 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
         c.ext[0] = group_max<G>(ext);
         if (!alive) { c.x[0] = kIdle; c.y[0] = kIdle; c.z[0] = kIdle; }  // idle lanes must never raise the sign bit
         bool chit = scan_scene<1, kUntilAllHit, MASKED>(sc, c, alive);
-        if (sd.n_pc > 0) chit |= scan_pointclouds<1>(sd, c, alive && !chit);
+        if (sd.n_pc > 0) chit |= scan_pointclouds<1, kUntilAllHit>(sd, c, alive && !chit);
         const bool need = group_any<G>(chit && alive) && alive;
         if (!__any_sync(kFull, need)) continue;
         frame_seek<R, BT>(F, have, tb.link_frame[l], q, slots);
@@ -622,7 +669,7 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
                 if (!on) { s.ext[t] = -INFINITY; s.x[t] = kIdle; s.y[t] = kIdle; s.z[t] = kIdle; }
             }
             fhit |= scan_scene<FT, POLICY, MASKED>(sc, s, need && !fhit);
-            if (sd.n_pc > 0) fhit |= scan_pointclouds<FT>(sd, s, need && !fhit);
+            if (sd.n_pc > 0) fhit |= scan_pointclouds<FT, POLICY>(sd, s, need && !fhit);
             if (EDGE) {
                 if (__any_sync(kFull, fhit)) return !fhit;
             } else {
@@ -650,10 +697,9 @@ __device__ __noinline__ bool ordered_scan_one(const Scene *scp, float x, float y
     return any_mode ? scan_scene<1, kAnyHit, false>(sc, s1, on) : scan_scene<1, kUntilAllHit, false>(sc, s1, on);
 }
 
-__device__ __noinline__ bool pointclouds_one(const CaptView *pcs, int n_pc, float x, float y, float z, float r, bool on) {
+__device__ __noinline__ bool pointclouds_one(const CaptView *pcs, int n_pc, float x, float y, float z, float r, bool on, bool any_mode) {
     bool hit = false;
-    for (int p = 0; p < n_pc; ++p)
-        if (on && !hit) hit = capt_collides(pcs[p], x, y, z, r);
+    for (int p = 0; p < n_pc; ++p) hit |= capt_collides_warp(pcs[p], x, y, z, r, on && !hit, any_mode);
     return hit;
 }
 
@@ -708,7 +754,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
         bool h;
         if (lvl >= 0) h = grid_scan_scene(sd.grid[lvl], sc, x, y, z, r, on, any_mode);
         else h = ordered_scan_one<G>(&sv.sc, x, y, z, r, on, any_mode);
-        if (sd.n_pc > 0) h |= pointclouds_one(sv.pc, sd.n_pc, x, y, z, r, on && !h);
+        if (sd.n_pc > 0) h |= pointclouds_one(sv.pc, sd.n_pc, x, y, z, r, on && !h, any_mode);
         if (!fine) {
             need = group_any<G>(h && alive) && alive;
             if (__any_sync(kFull, need)) {

@@ -1,0 +1,182 @@
+#!/usr/bin/env python3
+"""GPU-box probe of BASELINE configs 4 and 5: one JSON line per config with device-timed throughput, the CPU
+checker timed beside it on a bounded sample (all host threads, count stated) and the parity counts of that sample.
+  C4  Fetch 8-DOF motion validation against a bookshelf-style cloud: 2^20 surface points -> filter_pointcloud
+      (min_dist = Fetch min radius 0.012, range 1.5 around (0, 0, 0.4)) -> point-cloud tree (r_min 0.012, r_max 0.24,
+      r_point 0.0025) -> 2^20 motions x 64 states
+  C5  20-link planar chain in the horn environment: 2^20 uniform states (validity), chain-metric kNN (k = 16) over
+      2^17 valid states, DiscreteMotionValidator over the kNN edges
+usage: configs_probe.py [--c4-motions N] [--c5-knn N]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ompl_b200  # noqa: E402
+from ompl_b200 import synth  # noqa: E402
+from oracle import chain as ochain  # noqa: E402
+from oracle import port  # noqa: E402
+
+try:
+    from oracle import refvamp
+    HAVE_REF = refvamp.available()
+except Exception:
+    HAVE_REF = False
+
+CORES = os.cpu_count() or 1
+
+
+def dev_time(fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def c4(ctx, n_motions):
+    o = np.array([0, 0, 0.4], np.float32)
+    radii = (0.012, 0.24, 0.0025)
+    pts = synth.shelf_cloud(1 << 20, seed=7)
+    t_filter_gpu = dev_time(lambda: ctx.filter_pointcloud(pts, radii[0], 1.5, o, o - 1.5, o + 1.5, True))
+    kept = ctx.filter_pointcloud(pts, radii[0], 1.5, o, o - 1.5, o + 1.5, True)
+    t0 = time.perf_counter()
+    want = port.filter_pointcloud(pts, radii[0], 1.5, o, o - 1.5, o + 1.5, True)
+    t_filter_cpu = time.perf_counter() - t0
+    t_filter_ref = None
+    if HAVE_REF:
+        t0 = time.perf_counter()
+        ref_kept = refvamp.filter_pointcloud(pts, radii[0], 1.5, o, o - 1.5, o + 1.5, True)
+        t_filter_ref = time.perf_counter() - t0
+    env = ompl_b200.Environment(ctx)
+    t0 = time.perf_counter()
+    env.add_pointcloud(kept, *radii)
+    env.commit()
+    t_build = time.perf_counter() - t0
+    q0, q1 = synth.fixed_length_edges("fetch", n_motions, 4321)
+    d0, d1 = torch.from_numpy(q0).cuda(), torch.from_numpy(q1).cuda()
+    out = torch.zeros(n_motions, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()
+
+    def run():
+        ctx.validate_motions_ptr("fetch", env, d0.data_ptr(), d1.data_ptr(), n_motions, out.data_ptr(), stream=stream.cuda_stream)
+        stream.synchronize()
+    t_val = dev_time(run)
+    got = out.cpu().numpy()
+    # all-valid sub-workload: no early exit hides work
+    vi = np.nonzero(got == 1)[0]
+    line = {"config": "C4 Fetch + 2^20-point cloud (filtered, CAPT)", "cloud_points": int(len(pts)), "filtered_points": int(len(kept)),
+            "filter_equals_cpu_restatement": bool(kept.shape == want.shape and (kept == want).all()),
+            "ms_filter_gpu": t_filter_gpu * 1e3, "ms_filter_cpu_restatement_1thread": t_filter_cpu * 1e3,
+            "ms_filter_reference_1thread": None if t_filter_ref is None else t_filter_ref * 1e3,
+            "filtered_points_reference": int(len(ref_kept)) if HAVE_REF else None,
+            "ms_tree_build_host": t_build * 1e3, "motions": n_motions, "states_per_motion": 64,
+            "ms_validate": t_val * 1e3, "edges_per_s": n_motions / t_val, "valid_fraction": float(got.mean())}
+    if len(vi) > 0:
+        rep = np.resize(vi, 1 << 16)
+        e0, e1 = torch.from_numpy(q0[rep]).cuda(), torch.from_numpy(q1[rep]).cuda()
+        o2 = torch.zeros(len(rep), dtype=torch.uint8, device="cuda")
+
+        def run2():
+            ctx.validate_motions_ptr("fetch", env, e0.data_ptr(), e1.data_ptr(), len(rep), o2.data_ptr(), stream=stream.cuda_stream)
+            stream.synchronize()
+        t2 = dev_time(run2)
+        line.update({"all_valid_unique": int(len(vi)), "ms_all_valid_2^16": t2 * 1e3, "all_valid_states_per_s": len(rep) * 64 / t2})
+    # CPU checker on a bounded sample, same tree arrays (engine-built == reference-built, tests/test_capt_cpu.py)
+    sample = min(n_motions, 1 << 15)
+    if HAVE_REF:
+        ce = refvamp.RefEnvironment()
+        ce.add_pointcloud(kept, *radii)
+        ce.finalize() if hasattr(ce, "finalize") else None
+        kind = "reference"
+    else:
+        ce = port.PortEnvironment()
+        ce.add_capt(ompl_b200.capt_build(kept, *radii))
+        kind = "port"
+    ce.validate_motions("fetch", q0[:1024], q1[:1024], nthreads=CORES)
+    t0 = time.perf_counter()
+    cv = ce.validate_motions("fetch", q0[:sample], q1[:sample], nthreads=CORES)
+    t_cpu = time.perf_counter() - t0
+    line["cpu_baseline"] = {"value": sample / t_cpu, "unit": "edges/s", "cores": CORES, "kind": kind, "sample": f"first {sample} motions",
+                            "decisions_differing_from_gpu": int((cv != got[:sample]).sum())}
+    print(json.dumps(line), flush=True)
+
+
+def c5(ctx, n_knn):
+    n = 20
+    L = 1.0 / n
+    env = ompl_b200.horn_environment(n, np.log(n) / n)
+    kc = ompl_b200.KinematicChain(ctx, n, L, env)
+    P = ochain.RefChain(n, L, env) if ochain.ref_available() else ochain.PortChain(n, L, env)
+    kind = "reference" if ochain.ref_available() else "port"
+    rng = np.random.default_rng(5)
+    # uniform states are almost never valid for a 20-link chain (self intersection); mix in scaled-down states as the
+    # reference's benchmark effectively explores (demos/KinematicChainBenchmark.cpp starts from the straight chain)
+    q = rng.uniform(-np.pi, np.pi, (1 << 20, n)) * rng.uniform(0.0, 0.35, (1 << 20, 1))
+    dq = torch.from_numpy(q).cuda()
+    dv = torch.zeros(len(q), dtype=torch.uint8, device="cuda")
+    t_states = dev_time(lambda: kc.validate_states_ptr(dq.data_ptr(), len(q), dv.data_ptr()))
+    valid = dv.cpu().numpy()
+    sample = 1 << 15
+    t0 = time.perf_counter()
+    cv = P.validate_states(q[:sample])
+    t_cpu_states = time.perf_counter() - t0
+    line = {"config": "C5 20-link planar chain, horn environment", "states": int(len(q)), "ms_validate_states": t_states * 1e3,
+            "states_per_s": len(q) / t_states, "valid_fraction": float(valid.mean()),
+            "cpu_states": {"value": sample / t_cpu_states, "unit": "states/s", "cores": 1, "kind": kind, "sample": f"first {sample} states",
+                           "decisions_differing_from_gpu": int((cv != valid[:sample]).sum())}}
+    ok = q[valid == 1][:n_knn]
+    nn = ompl_b200.NearestNeighbors(ctx, n, metric=1, link_length=L)
+    nn.add(ok)
+    k = 16
+    t0 = time.perf_counter()
+    idx, dist, cnt = nn.nearest_k(ok, k, self_ids=np.arange(len(ok)))
+    t_knn = time.perf_counter() - t0
+    qs = 256
+    t0 = time.perf_counter()
+    ridx, rdist = port.knn(ok, ok[:qs], k, metric=1, param=L, exclude_self=True, nthreads=CORES)
+    t_cpu_knn = time.perf_counter() - t0
+    line.update({"knn_states": int(len(ok)), "k": k, "ms_knn_e2e_host_buffers": t_knn * 1e3, "knn_queries_per_s": len(ok) / t_knn,
+                 "cpu_knn": {"value": qs / t_cpu_knn, "unit": "queries/s", "cores": CORES, "kind": "port", "sample": f"first {qs} queries",
+                             "max_rel_dist_err": float(np.max(np.abs(dist[:qs] - rdist) / np.maximum(rdist, 1e-300))),
+                             "index_rows_differing": int((idx[:qs] != ridx).any(axis=1).sum())}})
+    # edges of the roadmap under DiscreteMotionValidator semantics
+    ii = np.repeat(np.arange(len(ok)), k)
+    jj = idx.reshape(-1)
+    keep = (jj >= 0) & (ii < jj)
+    a, b = ok[ii[keep]], ok[jj[keep]]
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dm = torch.zeros(len(a), dtype=torch.uint8, device="cuda")
+    t_mot = dev_time(lambda: kc.check_motions_ptr(da.data_ptr(), db.data_ptr(), len(a), dm.data_ptr()))
+    mv = dm.cpu().numpy()
+    ms = 1 << 13
+    t0 = time.perf_counter()
+    cm, _, _ = P.check_motions(a[:ms], b[:ms], 0)
+    t_cpu_mot = time.perf_counter() - t0
+    line.update({"edges": int(len(a)), "ms_check_motions": t_mot * 1e3, "edges_per_s": len(a) / t_mot, "valid_edge_fraction": float(mv.mean()),
+                 "cpu_motions": {"value": ms / t_cpu_mot, "unit": "edges/s", "cores": 1, "kind": kind, "sample": f"first {ms} edges",
+                                 "decisions_differing_from_gpu": int((cm != mv[:ms]).sum())}})
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--c4-motions", type=int, default=1 << 20)
+    ap.add_argument("--c5-knn", type=int, default=1 << 17)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    ctx = ompl_b200.Context(0)
+    if args.only in ("", "c4"):
+        c4(ctx, args.c4_motions)
+    if args.only in ("", "c5"):
+        c5(ctx, args.c5_knn)
