@@ -56,7 +56,7 @@ enum {
     B200MP_ERR_EMPTY = 6       /* "No elements found in nearest neighbors data structure" */
 };
 
-enum { B200MP_ROBOT_PANDA = 0, B200MP_ROBOT_FETCH = 1 };
+enum { B200MP_ROBOT_PANDA = 0, B200MP_ROBOT_FETCH = 1, B200MP_ROBOT_UR5 = 2, B200MP_ROBOT_BAXTER = 3 };
 enum { B200MP_METRIC_L2 = 0, B200MP_METRIC_CHAIN = 1 };
 
 int b200mp_version(void);

@@ -65,6 +65,19 @@ namespace ompl::b200
         static constexpr int resolution = 32;
     };
 
+    struct UR5  // robots/ur5.hh:14-18
+    {
+        static constexpr int id = B200MP_ROBOT_UR5;
+        static constexpr std::size_t dimension = 6;
+        static constexpr int resolution = 32;
+    };
+    struct Baxter  // robots/baxter.hh:14-18 (both arms: 14 joints, resolution 64)
+    {
+        static constexpr int id = B200MP_ROBOT_BAXTER;
+        static constexpr std::size_t dimension = 14;
+        static constexpr int resolution = 64;
+    };
+
     /// One engine context per GPU. Shared by validators, environments and nearest-neighbour containers.
     class Engine
     {

@@ -15,6 +15,8 @@
 #include "capt_order.cuh"
 #include "robots/panda_gen.cuh"
 #include "robots/fetch_gen.cuh"
+#include "robots/ur5_gen.cuh"
+#include "robots/baxter_gen.cuh"
 #include "host_common.hpp"
 
 using namespace b200mp;
@@ -289,6 +291,8 @@ int b200mp_robot_info(int robot, int *dim, int *n_spheres, int *resolution, floa
     switch (robot) {
         case B200MP_ROBOT_PANDA: fill(Panda{}); return B200MP_OK;
         case B200MP_ROBOT_FETCH: fill(Fetch{}); return B200MP_OK;
+        case B200MP_ROBOT_UR5: fill(Ur5{}); return B200MP_OK;
+        case B200MP_ROBOT_BAXTER: fill(Baxter{}); return B200MP_OK;
         default: return fail(B200MP_ERR_INVALID, "b200mp_robot_info: unknown robot %d", robot);
     }
 }
@@ -534,7 +538,9 @@ int b200mp_env_commit(b200mp_env *e) {
     const size_t bytes = blob.size() * 4;
     // dynamic shared memory budget: opt-in maximum minus static use (barrier) and a margin
     // and the per-thread bounding-sphere centres the kernels keep beside the scene
-    const size_t budget = static_cast<size_t>(e->ctx->max_smem_optin) - 1024 - std::max(lane_store_bytes<Panda>(kStateThreads), lane_store_bytes<Fetch>(kStateThreads));
+    // (checked here for the leanest robot; a launch for a robot whose slots do not fit beside this scene fails with B200MP_ERR_CAPACITY)
+    const size_t budget = static_cast<size_t>(e->ctx->max_smem_optin) - 1024 -
+                          std::min({lane_store_bytes<Panda>(kStateThreads), lane_store_bytes<Fetch>(kStateThreads), lane_store_bytes<Ur5>(kStateThreads)});
     if (bytes > budget)
         return fail(B200MP_ERR_CAPACITY, "b200mp_env_commit: scene needs %zu bytes of shared memory, limit %zu", bytes, budget);
     env_free_device(e);
@@ -560,18 +566,18 @@ namespace {
 template <class R>
 int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const float *d_q1, const int2 *d_pairs, int64_t m,
                    int resolution, uint8_t *d_valid, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>(kMotionThreads);
+    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>(motion_threads<R>());
     auto kern = e->desc.n_grid > 0 ? validate_motions_kernel<R, false, true>
                                    : (e->desc.sorted ? validate_motions_kernel<R, false, false> : validate_motions_kernel<R, true, false>);
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMotionThreads, smem));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, motion_threads<R>(), smem));
     if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_motions: kernel does not fit on an SM with %zu B of scene", smem);
     const long long warps_needed = m;
-    long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + (kMotionThreads / 32) - 1) / (kMotionThreads / 32));
+    long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + (motion_threads<R>() / 32) - 1) / (motion_threads<R>() / 32));
     blocks = std::max<long long>(blocks, 1);
     B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), kMotionThreads, smem, st>>>(e->desc, d_q0, d_q1, d_pairs, m, resolution, d_valid,
+    kern<<<static_cast<unsigned>(blocks), motion_threads<R>(), smem, st>>>(e->desc, d_q0, d_q1, d_pairs, m, resolution, d_valid,
                                                                      static_cast<LaunchCounters *>(c->d_counters));
     B200_CUDA(cudaGetLastError());
     c->launches.fetch_add(1);
@@ -701,6 +707,8 @@ int b200mp_validate_motions_device(b200mp_ctx *c, int robot, const b200mp_env *e
     switch (robot) {
         case B200MP_ROBOT_PANDA: return launch_motions<Panda>(c, e, d_q0, d_q1, nullptr, m, resolution ? resolution : Panda::kResolution, d_valid, st);
         case B200MP_ROBOT_FETCH: return launch_motions<Fetch>(c, e, d_q0, d_q1, nullptr, m, resolution ? resolution : Fetch::kResolution, d_valid, st);
+        case B200MP_ROBOT_UR5: return launch_motions<Ur5>(c, e, d_q0, d_q1, nullptr, m, resolution ? resolution : Ur5::kResolution, d_valid, st);
+        case B200MP_ROBOT_BAXTER: return launch_motions<Baxter>(c, e, d_q0, d_q1, nullptr, m, resolution ? resolution : Baxter::kResolution, d_valid, st);
         default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
     }
 }
@@ -718,6 +726,8 @@ int b200mp_validate_edges_device(b200mp_ctx *c, int robot, const b200mp_env *e, 
     switch (robot) {
         case B200MP_ROBOT_PANDA: return launch_motions<Panda>(c, e, d_states, d_states, pairs, m, resolution ? resolution : Panda::kResolution, d_valid, st);
         case B200MP_ROBOT_FETCH: return launch_motions<Fetch>(c, e, d_states, d_states, pairs, m, resolution ? resolution : Fetch::kResolution, d_valid, st);
+        case B200MP_ROBOT_UR5: return launch_motions<Ur5>(c, e, d_states, d_states, pairs, m, resolution ? resolution : Ur5::kResolution, d_valid, st);
+        case B200MP_ROBOT_BAXTER: return launch_motions<Baxter>(c, e, d_states, d_states, pairs, m, resolution ? resolution : Baxter::kResolution, d_valid, st);
         default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
     }
 }
@@ -732,6 +742,8 @@ int b200mp_validate_states_device(b200mp_ctx *c, int robot, const b200mp_env *e,
     switch (robot) {
         case B200MP_ROBOT_PANDA: return launch_states<Panda>(c, e, d_q, m, d_valid, st);
         case B200MP_ROBOT_FETCH: return launch_states<Fetch>(c, e, d_q, m, d_valid, st);
+        case B200MP_ROBOT_UR5: return launch_states<Ur5>(c, e, d_q, m, d_valid, st);
+        case B200MP_ROBOT_BAXTER: return launch_states<Baxter>(c, e, d_q, m, d_valid, st);
         default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
     }
 }

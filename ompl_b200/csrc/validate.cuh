@@ -529,15 +529,18 @@ __device__ __forceinline__ void trig_from_slots(const float *__restrict__ slots,
     }
 }
 
-// bring the streamed frame F (currently frame `have`, -1 = nothing) to frame k by walking the chain
+// bring the streamed frame F (currently frame `have`, -1 = nothing) to frame k by walking k's chain (arm): either on
+// from `have` when that is an earlier frame of the same chain, or from the world frame at the chain's first joint
 template <class R, int BT>
 __device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const float (&q)[R::kDim], const float *__restrict__ slots) {
     if (have == k) return;
-    if (have < 0 || have > k) { frame_identity(F); have = 0; }
+    const int first = R::tables().frame_branch[k];
+    int from = have + 1;
+    if (have < first || have > k) { frame_identity(F); from = first; }
     float sn[R::kDim], cs[R::kDim];
     trig_from_slots<R, BT>(slots, sn, cs);
 #pragma unroll 1
-    for (int j = have + 1; j <= k; ++j) R::advance(j, F, q, sn, cs);
+    for (int j = from; j <= k; ++j) R::advance(j, F, q, sn, cs);
     have = k;
 }
 
@@ -797,8 +800,13 @@ struct LaunchCounters {
 
 // Threads per block / blocks per SM of the validation kernels (measured on C2: the motion kernel gains ~4 % from 20 warps
 // at 96 registers, the state kernel prefers 16 warps at 128). Shared memory per block = scene blob + lane_slots floats per thread.
-constexpr int kMotionThreads = 640, kMotionBlocksPerSM = 1;
+constexpr int kMotionBlocksPerSM = 1;
 constexpr int kStateThreads = 256, kStateBlocksPerSM = 2;
+// the motion kernel's block: as many warps as keep the per-thread slots within ~160 KB (Baxter: 33 links + 14 joints)
+template <class R>
+__host__ __device__ constexpr int motion_threads() {
+    return lane_slots<R>() * 640 * 4 <= 160 * 1024 ? 640 : (lane_slots<R>() * 384 * 4 <= 160 * 1024 ? 384 : 256);
+}
 
 template <class R>
 __host__ __device__ constexpr size_t lane_store_bytes(int threads) { return static_cast<size_t>(lane_slots<R>()) * threads * sizeof(float); }
@@ -817,7 +825,7 @@ __device__ __forceinline__ float vamp_l2_norm(const float (&v)[DIM]) {
 
 // One warp per motion; motions are taken from a global queue (edge cost varies by 100x with early exit).
 template <class R, bool MASKED, bool GRID>
-__global__ void __launch_bounds__(kMotionThreads, kMotionBlocksPerSM)
+__global__ void __launch_bounds__(motion_threads<R>(), kMotionBlocksPerSM)
 validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float *__restrict__ q1, const int2 *__restrict__ pairs,
                         long long m, int resolution, uint8_t *__restrict__ valid, LaunchCounters *cnt) {
     extern __shared__ __align__(16) float smem[];
@@ -872,7 +880,7 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
         bool ok = true;
         for (int base = 0; base < n; base += 4) {
             const bool active = (base + rake_in_pass) < n;
-            const bool good = check_state<R, 8, true, MASKED, GRID, kMotionThreads>(q, sd, sc, slots, lv, sv, active);
+            const bool good = check_state<R, 8, true, MASKED, GRID, motion_threads<R>()>(q, sd, sc, slots, lv, sv, active);
             if (__any_sync(kFull, active && !good)) { ok = false; break; }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {

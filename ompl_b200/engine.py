@@ -7,7 +7,7 @@ import os
 
 import numpy as np
 
-ROBOTS = {"panda": 0, "fetch": 1}
+ROBOTS = {"panda": 0, "fetch": 1, "ur5": 2, "baxter": 3}
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 

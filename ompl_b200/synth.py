@@ -14,6 +14,19 @@ FETCH_LO = np.array([0.0, -1.6056, -1.221, -3.14159, -2.251, -3.14159, -2.16, -3
 FETCH_HI = (FETCH_LO + np.array([0.38615, 3.2112, 2.739, 6.28318, 4.502, 6.28318, 4.32, 6.28318], np.float32)).astype(np.float32)
 BOUNDS = {"panda": (PANDA_LO, PANDA_HI), "fetch": (FETCH_LO, FETCH_HI)}
 
+
+def _bounds_from_model(robot: str):
+    """lo = s_a, hi = s_a + s_m in float32, from the robot model the CUDA tables are generated from (ompl_b200/robots/*.json)."""
+    import json
+    import os
+    m = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "robots", robot + ".json")))
+    lo = np.asarray(m["s_a"], np.float32)
+    return lo, (lo + np.asarray(m["s_m"], np.float32)).astype(np.float32)
+
+
+for _r in ("ur5", "baxter"):
+    BOUNDS[_r] = _bounds_from_model(_r)
+
 CAGE_CENTRES = np.array([
     (0.55, 0, 0.25), (0.35, 0.35, 0.25), (0, 0.55, 0.25), (-0.55, 0, 0.25), (-0.35, -0.35, 0.25),
     (0, -0.55, 0.25), (0.35, -0.35, 0.25), (0.35, 0.35, 0.8), (0, 0.55, 0.8), (-0.35, 0.35, 0.8),

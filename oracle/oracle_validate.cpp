@@ -352,7 +352,7 @@ namespace
     }
 
     constexpr int kMaxFrames = 16;
-    constexpr int kMaxLinks = 32;
+    constexpr int kMaxLinks = 48;
     constexpr int kMaxFine = 160;
 
     // Robot::fkcc<rake> on `lanes` configurations (robots/panda.hh:5226-10263): true = all lanes collision free.
@@ -575,6 +575,8 @@ namespace
         {
             case 0: return &panda_robot;
             case 1: return &fetch_robot;
+            case 2: return &ur5_robot;
+            case 3: return &baxter_robot;
             default: return nullptr;
         }
     }

@@ -1,0 +1,37 @@
+// TEST INFRASTRUCTURE ONLY -- see ref_vamp_impl.hh. Instantiates the reference for vamp::robots::Baxter.
+#include "ref_vamp_impl.hh"
+#include <vamp/robots/baxter.hh>
+
+using Robot = vamp::robots::Baxter;
+
+extern "C"
+{
+    int refv_baxter_dimension() { return static_cast<int>(Robot::dimension); }
+    int refv_baxter_n_spheres() { return static_cast<int>(Robot::n_spheres); }
+    int refv_baxter_resolution() { return static_cast<int>(Robot::resolution); }
+
+    // lo[d], hi[d]: the bounds the OMPL bridge derives by scaling 0 and 1 (src/ompl/vamp/VampStateSpace.h:10-36)
+    void refv_baxter_bounds(float *lo, float *hi)
+    {
+        std::array<float, Robot::Configuration::num_scalars> z{}, o{};
+        o.fill(1.0F);
+        Robot::Configuration a(z), b(o);
+        Robot::scale_configuration(a);
+        Robot::scale_configuration(b);
+        const auto za = a.to_array();
+        const auto oa = b.to_array();
+        for (std::size_t i = 0; i < Robot::dimension; ++i)
+        {
+            lo[i] = za[i];
+            hi[i] = oa[i];
+        }
+    }
+
+    int refv_baxter_validate_motions(
+        void *env, const float *q0, const float *q1, std::int64_t m, int resolution, std::uint8_t *out, int nthreads)
+    {
+        return refv::validate_motions<Robot>(static_cast<refv::Env *>(env), q0, q1, m, resolution, out, nthreads);
+    }
+
+    int refv_baxter_sphere_fk(const float *q, std::int64_t m, float *out) { return refv::sphere_fk<Robot>(q, m, out); }
+}

@@ -49,7 +49,7 @@ def lib():
     L.refv_capt_collides.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int64, _u8p]
     L.refv_filter_pointcloud.argtypes = [_f32p, C.c_int64, C.c_float, C.c_float, _f32p, _f32p, _f32p, C.c_int, _f32p, C.c_int64]
     L.refv_filter_pointcloud.restype = C.c_int64
-    for r in ("panda", "fetch"):
+    for r in ("panda", "fetch", "ur5", "baxter"):
         getattr(L, f"refv_{r}_bounds").argtypes = [_f32p, _f32p]
         getattr(L, f"refv_{r}_validate_motions").argtypes = [
             C.c_void_p, _f32p, _f32p, C.c_int64, C.c_int, _u8p, C.c_int]

@@ -109,6 +109,13 @@ def main():
         cloud_case("fetch_cloud", "fetch", (0.012, 0.24, 0.0025), 1500,
                    synth.clutter_scene(11, 20, 20, rho_lo=0.6, rho_hi=1.4, z_lo=0.2, z_hi=1.6), 1500, 800, 505)
         return
+    if "--more-robots" in sys.argv:  # UR5 (6-DOF chain) and Baxter (two 7-DOF arms, resolution 64); written without touching the older files
+        validation_case("ur5_clutter", "ur5", synth.clutter_scene(12, 60, 60, n_capsules=20, n_zcuboids=20, n_zcapsules=20), True, 2000, 1000, 606)
+        validation_case("baxter_clutter", "baxter", synth.clutter_scene(13, 10, 10, n_capsules=4, n_zcuboids=4, n_zcapsules=4), True, 2000, 1000, 707)
+        for robot in ("ur5", "baxter"):
+            q = synth.uniform_states(robot, 256, 55)
+            np.savez_compressed(os.path.join(HERE, f"{robot}_sphere_fk.npz"), q=q, spheres=refvamp.sphere_fk(robot, q))
+        return
     validation_case("panda_cage", "panda", synth.cage_scene(), True, 3000, 1500, 101)
     validation_case("panda_clutter", "panda",
                     synth.clutter_scene(7, 120, 120, n_capsules=40, n_zcuboids=40, n_zcapsules=40), True, 3000, 1500, 202)

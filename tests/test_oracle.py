@@ -10,7 +10,7 @@ from oracle import port
 from tests.util import assert_validity_parity, load_golden
 from tests.conftest import have_reference_build
 
-CASES = ["panda_cage", "panda_clutter", "panda_clutter_unsorted", "fetch_clutter"]
+CASES = ["panda_cage", "panda_clutter", "panda_clutter_unsorted", "fetch_clutter", "ur5_clutter", "baxter_clutter"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -33,7 +33,7 @@ def test_demo_known_answers():
     assert list(env.validate_motions("panda", [synth.CAGE_START], [synth.CAGE_GOAL])) == [0]
 
 
-@pytest.mark.parametrize("robot", ["panda", "fetch"])
+@pytest.mark.parametrize("robot", ["panda", "fetch", "ur5", "baxter"])
 def test_port_sphere_fk_matches_reference_trace(robot):
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{robot}_sphere_fk.npz"))
     got = port.sphere_fk(robot, z["q"])

@@ -11,7 +11,7 @@ from tests.util import assert_validity_parity, load_golden
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["panda_cage", "panda_clutter", "panda_clutter_unsorted", "fetch_clutter"]
+CASES = ["panda_cage", "panda_clutter", "panda_clutter_unsorted", "fetch_clutter", "ur5_clutter", "baxter_clutter"]
 
 
 def clr_states(pe, robot, q):
@@ -45,6 +45,8 @@ def test_demo_known_answers(ctx):
     ("panda", dict(seed=31, n_spheres=300, n_cuboids=300, n_capsules=60, n_zcuboids=60, n_zcapsules=60)),
     ("fetch", dict(seed=32, n_spheres=80, n_cuboids=80, n_capsules=20, n_zcuboids=20, n_zcapsules=20, rho_lo=0.6, rho_hi=1.4,
                    z_lo=0.2, z_hi=1.6)),
+    ("ur5", dict(seed=33, n_spheres=200, n_cuboids=200, n_capsules=30, n_zcuboids=30, n_zcapsules=30)),
+    ("baxter", dict(seed=5, n_spheres=6, n_cuboids=6, n_capsules=4)),
 ])
 def test_seeded_parity_vs_oracle(ctx, robot, scene_kw):
     scene = synth.clutter_scene(**scene_kw)
@@ -186,6 +188,8 @@ def test_linearity_properties_full_size(ctx):
     ("panda", dict(seed=1234, n_spheres=500, n_cuboids=500)),
     ("fetch", dict(seed=42, n_spheres=150, n_cuboids=150, n_capsules=30, n_zcuboids=30, n_zcapsules=30, rho_lo=0.5, rho_hi=1.6,
                    z_lo=0.0, z_hi=1.8)),
+    ("ur5", dict(seed=43, n_spheres=300, n_cuboids=300)),
+    ("baxter", dict(seed=5, n_spheres=15, n_cuboids=15, n_capsules=4)),
 ])
 def test_grid_culling_makes_the_same_decisions_as_the_ordered_scan(ctx, robot, scene_kw):
     """Sorted scenes are validated through candidate grids; the plain ordered scan (grid off) is the reference semantics."""

@@ -18,6 +18,7 @@ import os
 
 import numpy as np
 
+ROBOT_IDS = {"panda": 0, "fetch": 1, "ur5": 2, "baxter": 3}
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(HERE, ".."))
 EPS = 1e-9
@@ -156,8 +157,11 @@ def gen_cuda(model: dict) -> str:
         pairs.append((a, b))
     pairs.sort(key=lambda p: (link_rows[p[1]]["frame"], link_rows[p[0]]["frame"], p))
     nfr = len(frames)
+    # frames form chains hanging off the world frame (one per arm); frame_branch[k] = first frame of k's chain
+    frame_branch = [0] * nfr
     for fr in frames[1:]:
-        assert fr["parent"] == fr["id"] - 1, "frames must form a chain (tree robots need a saved-parent slot)"
+        assert fr["parent"] in (0, fr["id"] - 1), "every frame must continue the previous chain or start a new one at the world frame"
+        frame_branch[fr["id"]] = fr["id"] if fr["parent"] == 0 else frame_branch[fr["parent"]]
     frame_link_begin = [next((i for i, r in enumerate(link_rows) if r["frame"] >= k), len(link_rows)) for k in range(nfr)] + [len(link_rows)]
     pair_frame_begin = [next((i for i, p in enumerate(pairs) if link_rows[p[1]]["frame"] >= k), len(pairs)) for k in range(nfr)] + [len(pairs)]
     a_frames = sorted({link_rows[a]["frame"] for a, _ in pairs} - {0})
@@ -191,6 +195,7 @@ def gen_cuda(model: dict) -> str:
     w(f"    short pair_frame_begin[{nfr + 1}];  // pairs whose later link lives on frame k")
     w(f"    short save_slot[{nfr}];             // slot frame k is saved to for later pairs, or -1")
     w(f"    short link_frame[{nl}];             // frame link l lives on")
+    w(f"    short frame_branch[{nfr}];          // first frame of the chain (arm) frame k belongs to; its parent is the world frame")
     w("};")
     w("")
     w(f"__constant__ {cname}Tables k{cname}Tables = {{")
@@ -205,6 +210,7 @@ def gen_cuda(model: dict) -> str:
     w("    {" + ", ".join(str(v) for v in pair_frame_begin) + "},")
     w("    {" + ", ".join(str(v) for v in save_slot) + "},")
     w("    {" + ", ".join(str(r["frame"]) for r in link_rows) + "},")
+    w("    {" + ", ".join(str(v) for v in frame_branch) + "},")
     w("};")
     w("")
     w(f"struct {cname} {{")
@@ -215,7 +221,7 @@ def gen_cuda(model: dict) -> str:
     w(f"    static constexpr int kPairs = {npairs};")
     w(f"    static constexpr int kResolution = {model['resolution']};")
     w(f"    static constexpr int kSlots = {max(1, len(a_frames))};   // saved frames needed by the self-collision stage")
-    w(f"    static constexpr int kRobotId = {0 if name == 'panda' else 1 if name == 'fetch' else 9};")
+    w(f"    static constexpr int kRobotId = {ROBOT_IDS[name]};")
     w("    static constexpr float kLo[kDim] = {" + ", ".join(f32(v) for v in lo) + "};")
     w("    static constexpr float kHi[kDim] = {" + ", ".join(f32(v) for v in hi) + "};")
     w(f"    using Tables = {cname}Tables;")
@@ -273,7 +279,7 @@ def gen_cuda(model: dict) -> str:
         if k > 0:
             qi = fr["q_index"]
             w(f"    Frame F{k};")
-            w(f"    frame<{k}>(F{k - 1}, q[{qi}], sn[{qi}], cs[{qi}], F{k});")
+            w(f"    frame<{k}>(F{fr['parent']}, q[{qi}], sn[{qi}], cs[{qi}], F{k});")
         for li, r in enumerate(link_rows):
             if r["frame"] != k:
                 continue
@@ -351,7 +357,7 @@ def gen_oracle_tables(models: list) -> str:
 
 if __name__ == "__main__":
     models = []
-    for r in ("panda", "fetch"):
+    for r in ROBOT_IDS:
         p = os.path.join(ROOT, "ompl_b200", "robots", f"{r}.json")
         if not os.path.exists(p):
             continue
