@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -247,6 +248,9 @@ int b200mp_create(int device, b200mp_ctx **out) {
     }
     B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     B200_CUDA(cudaMalloc(&c->d_counters, sizeof(LaunchCounters)));
+    c->small_cap = size_t(256) << 10;
+    B200_CUDA(cudaHostAlloc(&c->h_small, c->small_cap, cudaHostAllocMapped));
+    B200_CUDA(cudaHostGetDevicePointer(&c->d_small, c->h_small, 0));
     *out = c;
     return B200MP_OK;
 }
@@ -257,6 +261,7 @@ void b200mp_destroy(b200mp_ctx *c) {
     cudaStreamSynchronize(c->stream);
     c->scratch.release();
     cudaFree(c->d_counters);
+    if (c->h_small) cudaFreeHost(c->h_small);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -563,15 +568,33 @@ int b200mp_env_commit(b200mp_env *e) {
 // ---------------------------------------------------------------------------------------------------- launches
 namespace {
 
+// resident blocks per SM of a kernel at a given dynamic shared-memory size; the opt-in attribute and the occupancy query
+// are made once per (kernel, size) and remembered (they cost more than a small launch)
+int blocks_per_sm(const void *kern, int threads, size_t smem, int *per_sm) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, size_t>, int> cache;
+    static std::map<const void *, size_t> opted;  // largest dynamic size each kernel has been opted in for (only ever raised)
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({kern, smem});
+    if (it != cache.end()) { *per_sm = it->second; return B200MP_OK; }
+    if (smem > opted[kern]) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        opted[kern] = smem;
+    }
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, threads, smem));
+    cache[{kern, smem}] = *per_sm;
+    return B200MP_OK;
+}
+
 template <class R>
 int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const float *d_q1, const int2 *d_pairs, int64_t m,
                    int resolution, uint8_t *d_valid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>(motion_threads<R>());
+    int rc_occ = 0;
     auto kern = e->desc.n_grid > 0 ? validate_motions_kernel<R, false, true>
                                    : (e->desc.sorted ? validate_motions_kernel<R, false, false> : validate_motions_kernel<R, true, false>);
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, motion_threads<R>(), smem));
+    if ((rc_occ = blocks_per_sm(reinterpret_cast<const void *>(kern), motion_threads<R>(), smem, &per_sm))) return rc_occ;
     if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_motions: kernel does not fit on an SM with %zu B of scene", smem);
     const long long warps_needed = m;
     long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + (motion_threads<R>() / 32) - 1) / (motion_threads<R>() / 32));
@@ -587,11 +610,11 @@ int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const 
 template <class R>
 int launch_states(b200mp_ctx *c, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>(kStateThreads);
+    int rc_occ = 0;
     auto kern = e->desc.n_grid > 0 ? validate_states_kernel<R, false, true>
                                    : (e->desc.sorted ? validate_states_kernel<R, false, false> : validate_states_kernel<R, true, false>);
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kStateThreads, smem));
+    if ((rc_occ = blocks_per_sm(reinterpret_cast<const void *>(kern), kStateThreads, smem, &per_sm))) return rc_occ;
     if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_states: kernel does not fit on an SM with %zu B of scene", smem);
     const long long warps_needed = (m + 31) / 32;
     long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + (kStateThreads / 32) - 1) / (kStateThreads / 32));
@@ -618,13 +641,10 @@ int upload_states(b200mp_ctx *c, const T *h, int64_t count, float *d, cudaStream
         B200_CUDA(cudaMemcpyAsync(d, h, count * sizeof(float), cudaMemcpyHostToDevice, st));
         return B200MP_OK;
     }
-    float *stage = nullptr;
-    B200_CUDA(cudaMallocHost(&stage, std::max<int64_t>(count, 1) * sizeof(float)));
+    std::vector<float> stage(static_cast<size_t>(std::max<int64_t>(count, 1)));
     for (int64_t i = 0; i < count; ++i) stage[i] = static_cast<float>(h[i]);  // ompl_to_vamp: static_cast<float>(values[i])
-    cudaError_t err = cudaMemcpyAsync(d, stage, count * sizeof(float), cudaMemcpyHostToDevice, st);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
-    cudaFreeHost(stage);
-    B200_CUDA(err);
+    B200_CUDA(cudaMemcpyAsync(d, stage.data(), count * sizeof(float), cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaStreamSynchronize(st));  // the staging vector dies with this scope
     return B200MP_OK;
 }
 
@@ -641,6 +661,18 @@ int validate_motions_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T
     std::lock_guard<std::mutex> lk(c->mu);
     B200_CUDA(cudaSetDevice(c->device));
     const size_t qbytes = static_cast<size_t>(m) * dim * sizeof(float);
+    if (2 * qbytes + static_cast<size_t>(m) + 64 <= c->small_cap) {
+        // few motions (a planner's single checkMotion): inputs converted straight into the mapped buffer, result read from it
+        float *h0 = static_cast<float *>(c->h_small), *h1 = h0 + static_cast<size_t>(m) * dim;
+        for (int64_t i = 0; i < m * dim; ++i) { h0[i] = static_cast<float>(q0[i]); h1[i] = static_cast<float>(q1[i]); }
+        const float *d0 = static_cast<const float *>(c->d_small);
+        uint8_t *dv = reinterpret_cast<uint8_t *>(c->d_small) + 2 * qbytes;
+        rc = b200mp_validate_motions_device(c, robot, e, d0, d0 + static_cast<size_t>(m) * dim, m, resolution, dv, c->stream);
+        if (rc) return rc;
+        B200_CUDA(cudaStreamSynchronize(c->stream));
+        std::memcpy(valid, static_cast<const uint8_t *>(c->h_small) + 2 * qbytes, static_cast<size_t>(m));
+        return B200MP_OK;
+    }
     rc = c->scratch.reserve(2 * qbytes + static_cast<size_t>(m) + 256);
     if (rc) return rc;
     float *d_q0 = reinterpret_cast<float *>(c->scratch.ptr);
@@ -666,6 +698,16 @@ int validate_states_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T 
     std::lock_guard<std::mutex> lk(c->mu);
     B200_CUDA(cudaSetDevice(c->device));
     const size_t qbytes = static_cast<size_t>(m) * dim * sizeof(float);
+    if (qbytes + static_cast<size_t>(m) + 64 <= c->small_cap) {
+        float *h0 = static_cast<float *>(c->h_small);
+        for (int64_t i = 0; i < m * dim; ++i) h0[i] = static_cast<float>(q[i]);
+        uint8_t *dv = reinterpret_cast<uint8_t *>(c->d_small) + qbytes;
+        rc = b200mp_validate_states_device(c, robot, e, static_cast<const float *>(c->d_small), m, dv, c->stream);
+        if (rc) return rc;
+        B200_CUDA(cudaStreamSynchronize(c->stream));
+        std::memcpy(valid, static_cast<const uint8_t *>(c->h_small) + qbytes, static_cast<size_t>(m));
+        return B200MP_OK;
+    }
     rc = c->scratch.reserve(qbytes + static_cast<size_t>(m) + 256);
     if (rc) return rc;
     float *d_q = reinterpret_cast<float *>(c->scratch.ptr);

@@ -53,6 +53,11 @@ struct b200mp_ctx {
     int cc_major = 0;
     cudaStream_t stream = nullptr;
     void *d_counters = nullptr;
+    // small-call path (one checkMotion / isValid at a time, the way OMPL planners call): a mapped pinned buffer the kernels
+    // read and write directly, so a call is one memset + one launch + one synchronise
+    void *h_small = nullptr;   // host address
+    void *d_small = nullptr;   // the same memory as the device sees it
+    size_t small_cap = 0;
     b200mp::Scratch scratch;
     std::mutex mu;
     std::atomic<long long> launches{0};

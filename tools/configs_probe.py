@@ -44,6 +44,42 @@ def dev_time(fn, reps=3):
     return best
 
 
+def c1(ctx, n_seeds):
+    """Single-query RRT-Connect in the 14-sphere cage: every checkMotion is one C-ABI call (one motion, fp64 states)."""
+    from tests.rrtconnect import solve
+    env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
+    if HAVE_REF:
+        ce, kind = synth.fill_env(refvamp.RefEnvironment(), synth.cage_scene()), "reference"
+    else:
+        ce, kind = synth.fill_env(port.PortEnvironment(), synth.cage_scene()), "port"
+    lo, hi = synth.BOUNDS["panda"]
+    gpu = lambda a, b: ctx.validate_motions("panda", env, np.asarray(a, np.float64)[None], np.asarray(b, np.float64)[None])[0]  # noqa: E731
+    cpu = lambda a, b: ce.validate_motions("panda", a[None].astype(np.float32), b[None].astype(np.float32))[0]  # noqa: E731
+    tg, tc, calls, same, solved = [], [], 0, 0, 0
+    for seed in range(1, n_seeds + 1):
+        t0 = time.perf_counter()
+        p1, log1, _ = solve(synth.CAGE_START, synth.CAGE_GOAL, lo, hi, gpu, seed)
+        t1 = time.perf_counter()
+        p2, log2, _ = solve(synth.CAGE_START, synth.CAGE_GOAL, lo, hi, cpu, seed)
+        t2 = time.perf_counter()
+        tg.append(t1 - t0)
+        tc.append(t2 - t1)
+        calls += len(log1)
+        same += int(log1 == log2)
+        solved += int(p1 is not None)
+    a, b = synth.CAGE_START.astype(np.float64), synth.CAGE_GOAL.astype(np.float64)
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        gpu(a, b)
+    lat = (time.perf_counter() - t0) / 2000
+    print(json.dumps({"config": "C1 Panda RRT-Connect single query, 14-sphere cage (python harness tests/rrtconnect.py, linear NN)",
+                      "seeds": n_seeds, "solved": solved, "runs_with_identical_decision_sequence": same, "checkMotion_calls": calls,
+                      "solve_ms_engine_median": float(np.median(tg) * 1e3), "solve_ms_cpu_checker_median": float(np.median(tc) * 1e3),
+                      "cpu_checker": kind, "us_per_checkMotion_through_c_abi": lat * 1e6,
+                      "note": "one motion per call: launch + synchronise latency dominates; single-query planners are 'replicas only' (SURVEY 8e), "
+                              "the batched entry points are what the GPU is for"}), flush=True)
+
+
 def c4(ctx, n_motions):
     o = np.array([0, 0, 0.4], np.float32)
     radii = (0.012, 0.24, 0.0025)
@@ -173,9 +209,12 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--c4-motions", type=int, default=1 << 20)
     ap.add_argument("--c5-knn", type=int, default=1 << 17)
+    ap.add_argument("--c1-seeds", type=int, default=20)
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     ctx = ompl_b200.Context(0)
+    if args.only in ("", "c1"):
+        c1(ctx, args.c1_seeds)
     if args.only in ("", "c4"):
         c4(ctx, args.c4_motions)
     if args.only in ("", "c5"):
