@@ -120,10 +120,25 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"first {sample} of the 2^20 motions per step, all host threads (dynamic chunks)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=claim_stdout(), flush=True)
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version at init), so the real
+    stdout is set aside for the result line and file descriptor 1 is pointed at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -309,7 +324,7 @@ def main():
                 dt = time.perf_counter() - t0
                 line["roadmap"]["cpu_knn"] = {"queries_per_s_at_2^18": nq / dt, "cores": cores, "kind": "port",
                                               "sample": f"{nq} queries against 2^18 states (cost is linear in the database size)"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=claim_stdout(), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

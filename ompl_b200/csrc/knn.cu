@@ -13,6 +13,7 @@
 // blockIdx.y; a second kernel merges the partial lists per query with a warp-shuffle arg-min selection.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -303,45 +304,119 @@ constexpr int kCellQPT = 2;        // queries per thread
 constexpr int kCellQueries = kCellThreads * kCellQPT;  // queries per block
 constexpr int kRoundCells = kCellThreads;
 
-__global__ void knn_gather_pivots_kernel(const float *__restrict__ feat, long long n, int P, int fw, float *__restrict__ pivots) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P * fw) return;
-    const int p = t / fw, j = t - p * fw;
-    pivots[t] = feat[((static_cast<long long>(p) * n) / P) * fw + j];
-}
+// ---- partition: a balanced k-d tree of depth L = log2(P) built level by level on the device. Every level splits all of its
+// nodes along one dimension (the one whose current cell extent is largest) at the approximate median of the node's rows:
+// a 256-bin histogram over the node's extent along that dimension, split at the upper edge of the bin where the count
+// passes one half. Leaves are axis-aligned boxes with ~n / P rows each; the pruning boxes are then taken from the rows
+// themselves (knn_cell_bounds_kernel), so they are at least as tight as the leaves. Any partition gives the same result
+// (pruning uses lower bounds only); this one is what makes the boxes small: the Voronoi cells of random pivots used before
+// have bounding boxes so fat in 7-D that every block visited every cell.
+constexpr int kKdBins = 256;
+constexpr int kKdMaxDim = 24;
 
-// nearest pivot (fp32, any tie-break: the partition only has to be a partition)
-template <int NV>
-__global__ void __launch_bounds__(kKnnThreads)
-knn_assign_kernel(const float4 *__restrict__ rows, long long n, const float4 *__restrict__ pivots, int P, int *__restrict__ cell) {
-    __shared__ float4 tile[256 * NV];
-    const long long i = static_cast<long long>(blockIdx.x) * kKnnThreads + threadIdx.x;
-    float m2q[4 * NV];
+__device__ __forceinline__ unsigned kd_fkey(float f) {  // order-preserving float -> uint
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float kd_unfkey(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+// ext[2 * j] = min key, ext[2 * j + 1] = max key of coordinate j over the rows
+__global__ void knn_kd_extent_kernel(const float *__restrict__ rows, long long n, int fw, int dim, unsigned *__restrict__ ext) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (int j = 0; j < dim; ++j) {
+        unsigned lo = 0xffffffffu, hi = 0u;
+        if (i < n) {
+            const float v = rows[i * fw + j];
+            if (isfinite(v)) { lo = kd_fkey(v); hi = lo; }
+        }
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        const float4 r = i < n ? rows[i * NV + v] : make_float4(0.f, 0.f, 0.f, 0.f);
-        m2q[4 * v] = -2.f * r.x; m2q[4 * v + 1] = -2.f * r.y; m2q[4 * v + 2] = -2.f * r.z; m2q[4 * v + 3] = -2.f * r.w;
-    }
-    m2q[4 * NV - 1] = 1.0f;
-    float best = INFINITY;
-    int arg = 0;
-    for (int p0 = 0; p0 < P; p0 += 256) {
-        const int cnt = min(256, P - p0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < cnt * NV; t += kKnnThreads) tile[t] = pivots[static_cast<long long>(p0) * NV + t];
-        __syncthreads();
-        for (int c = 0; c < cnt; ++c) {
-            float acc = 0.f;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const float4 pv = tile[c * NV + v];
-                acc = fmaf(m2q[4 * v], pv.x, acc); acc = fmaf(m2q[4 * v + 1], pv.y, acc);
-                acc = fmaf(m2q[4 * v + 2], pv.z, acc); acc = fmaf(m2q[4 * v + 3], pv.w, acc);
-            }
-            if (acc < best) { best = acc; arg = p0 + c; }
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(kFullMask, lo, o));
+            hi = max(hi, __shfl_xor_sync(kFullMask, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0 && lo <= hi) {
+            atomicMin(ext + 2 * j, lo);
+            atomicMax(ext + 2 * j + 1, hi);
         }
     }
-    if (i < n) cell[i] = arg;
+}
+
+// one thread: split dimension of every level (greedy: the dimension whose cell extent is currently largest) and the root box
+__global__ void knn_kd_plan_kernel(const unsigned *__restrict__ ext, int dim, int L, int *__restrict__ dims, float *__restrict__ root_box) {
+    float w[kKdMaxDim];
+    for (int j = 0; j < dim; ++j) {
+        const float lo = kd_unfkey(ext[2 * j]), hi = kd_unfkey(ext[2 * j + 1]);
+        root_box[2 * j] = lo;
+        root_box[2 * j + 1] = hi;
+        w[j] = hi - lo;
+    }
+    for (int l = 0; l < L; ++l) {
+        int best = 0;
+        for (int j = 1; j < dim; ++j)
+            if (w[j] > w[best]) best = j;
+        dims[l] = best;
+        w[best] *= 0.5f;
+    }
+}
+
+// histogram of level l: node[i] is the row's node inside the level (0 .. 2^l - 1); boxes[node][2 * dim] are the level's cells
+__global__ void knn_kd_hist_kernel(const float *__restrict__ rows, long long n, int fw, int dim, const int *__restrict__ node, const int *__restrict__ dims,
+                                   int l, const float *__restrict__ boxes, unsigned *__restrict__ hist) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nd = node[i], d = dims[l];
+    const float lo = boxes[(static_cast<size_t>(nd) * dim + d) * 2], hi = boxes[(static_cast<size_t>(nd) * dim + d) * 2 + 1];
+    const float x = rows[i * fw + d];
+    int bin = 0;
+    if (hi > lo) bin = min(max(static_cast<int>((x - lo) / (hi - lo) * kKdBins), 0), kKdBins - 1);
+    atomicAdd(hist + static_cast<size_t>(nd) * kKdBins + bin, 1u);
+}
+
+// one thread per node of level l: split value + the two child boxes (level l + 1)
+__global__ void knn_kd_split_kernel(const unsigned *__restrict__ hist, int l, int dim, const int *__restrict__ dims, const float *__restrict__ boxes,
+                                    float *__restrict__ child_boxes, float *__restrict__ splits) {
+    const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nd >= (1 << l)) return;
+    const int d = dims[l];
+    const unsigned *h = hist + static_cast<size_t>(nd) * kKdBins;
+    unsigned total = 0;
+    for (int b = 0; b < kKdBins; ++b) total += h[b];
+    const float lo = boxes[(static_cast<size_t>(nd) * dim + d) * 2], hi = boxes[(static_cast<size_t>(nd) * dim + d) * 2 + 1];
+    int cut = kKdBins / 2;
+    if (total > 0) {
+        unsigned acc = 0;
+        for (int b = 0; b < kKdBins; ++b) {
+            acc += h[b];
+            if (2u * acc >= total) { cut = b + 1; break; }
+        }
+    }
+    const float split = hi > lo ? lo + (hi - lo) * (static_cast<float>(cut) / kKdBins) : lo;
+    splits[(1 << l) - 1 + nd] = split;
+    for (int j = 0; j < dim; ++j) {
+        const float bl = boxes[(static_cast<size_t>(nd) * dim + j) * 2], bh = boxes[(static_cast<size_t>(nd) * dim + j) * 2 + 1];
+        float *c0 = child_boxes + (static_cast<size_t>(2 * nd) * dim + j) * 2, *c1 = child_boxes + (static_cast<size_t>(2 * nd + 1) * dim + j) * 2;
+        c0[0] = bl; c0[1] = j == d ? split : bh;
+        c1[0] = j == d ? split : bl; c1[1] = bh;
+    }
+}
+
+// node[i] <- child of node[i] at level l (right when x >= split)
+__global__ void knn_kd_descend_kernel(const float *__restrict__ rows, long long n, int fw, int *__restrict__ node, const int *__restrict__ dims, int l,
+                                      const float *__restrict__ splits) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nd = node[i];
+    node[i] = 2 * nd + (rows[i * fw + dims[l]] >= splits[(1 << l) - 1 + nd] ? 1 : 0);
+}
+
+// leaf of every row (queries, or the database itself): L comparisons down the split planes
+__global__ void knn_kd_assign_kernel(const float *__restrict__ rows, long long n, int fw, int L, const int *__restrict__ dims,
+                                     const float *__restrict__ splits, int *__restrict__ cell) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int nd = 0;
+    for (int l = 0; l < L; ++l) nd = 2 * nd + (rows[i * fw + dims[l]] >= splits[(1 << l) - 1 + nd] ? 1 : 0);
+    cell[i] = nd;
 }
 
 __global__ void knn_cell_count_kernel(const int *__restrict__ cell, long long n, int *__restrict__ counts) {
@@ -457,7 +532,7 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
     constexpr int QPT = kCellQPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long bars[2];
-    __shared__ int s_job_row[2], s_job_cnt[2];
+    __shared__ int s_job_row[2], s_job_cnt[2], s_job_cell[2];
     __shared__ int s_list[kRoundCells];
     __shared__ int s_nlist;
     __shared__ int s_wcnt[kCellThreads / 32];
@@ -548,18 +623,20 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
 
     // stream the listed cells through shared memory, double buffered. Thread 0 walks the list (cell -> tiles of at most
     // kCellTile rows), announces each tile in the 2-entry ring s_job_* and issues its bulk copy one tile ahead.
-    int gl = 0, gb = 0, ge = 0;  // generator state, meaningful in thread 0 only
+    int gl = 0, gb = 0, ge = 0, gcell = 0;  // generator state, meaningful in thread 0 only
     auto next_job = [&](int slot_it) {
         const int slot = slot_it & 1;
         while (gb >= ge) {
             if (gl >= s_nlist) { s_job_cnt[slot] = 0; return; }
             const int c = s_list[gl++];
+            gcell = c;
             gb = cell_start[c];
             ge = cell_start[c + 1];
         }
         const int cnt = min(kCellTile, ge - gb);
         s_job_row[slot] = gb;
         s_job_cnt[slot] = cnt;
+        s_job_cell[slot] = gcell;
         const uint32_t bytes = static_cast<uint32_t>(cnt) * NV * sizeof(float4);
         mbar_expect_tx(&bars[slot], bytes);
         bulk_g2s(tiles + static_cast<size_t>(slot) * kCellTile * NV, feat_s + static_cast<long long>(gb) * NV, bytes, &bars[slot]);
@@ -604,10 +681,30 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
             const int cnt = s_job_cnt[slot];
             if (cnt == 0) break;
             const int row0 = s_job_row[slot];
+            const int tcell = s_job_cell[slot];
             if (tid == 0) { next_job(it + 1); visited += cnt; }
+            // per-warp pruning: the block streams every cell some warp may need, but a warp whose own queries cannot be reached
+            // from this cell (box-to-box lower bound beyond the warp's worst k-th distance) skips the arithmetic. One query with
+            // few close neighbours then costs its own warp, not the block.
+            float gap2 = 0.f;
+            if (lane < dim) {
+                const float wl = s_wlo[wid][lane], wh = s_whi[wid][lane];
+                const float g = fmaxf(fmaxf(clo[tcell * 24 + lane] - (wh + (fabsf(wh) * 4e-7f + 1e-30f)), (wl - (fabsf(wl) * 4e-7f + 1e-30f)) - chi[tcell * 24 + lane]), 0.f);
+                gap2 = g * g;
+            }
+            float wr2 = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < QPT; ++t)
+                if (has_q[t]) wr2 = fmaxf(wr2, worst[t] == INFINITY ? INFINITY : __double2float_ru(worst[t]) * 1.000001f);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                gap2 += __shfl_xor_sync(kFullMask, gap2, o);
+                wr2 = fmaxf(wr2, __shfl_xor_sync(kFullMask, wr2, o));
+            }
+            const bool warp_skip = !(gap2 * 0.99999f <= wr2);  // also true for warps without queries (wr2 = -inf)
             mbar_wait(&bars[slot], (it >> 1) & 1);
             const float4 *tile = tiles + static_cast<size_t>(slot) * kCellTile * NV;
-            for (int c0 = 0; c0 < cnt; c0 += 4) {
+            for (int c0 = 0; c0 < (warp_skip ? 0 : cnt); c0 += 4) {
                 float sv[QPT][4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -862,7 +959,9 @@ struct b200mp_knn {
     float4 *ix_feat = nullptr;
     double *ix_pts = nullptr;
     int *ix_orig = nullptr, *ix_start = nullptr;
-    float *ix_lo = nullptr, *ix_hi = nullptr, *ix_pivots = nullptr;
+    float *ix_lo = nullptr, *ix_hi = nullptr, *ix_splits = nullptr;
+    int *ix_dims = nullptr;
+    int index_L = 0;
     unsigned long long *d_rows_visited = nullptr;  // candidate rows streamed by the cell kernel since creation
 };
 
@@ -990,18 +1089,9 @@ namespace {
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
-template <int NV>
-void launch_assign(const float4 *rows, long long n, const float4 *pivots, int P, int *cell, cudaStream_t st) {
-    knn_assign_kernel<NV><<<static_cast<unsigned>((n + kKnnThreads - 1) / kKnnThreads), kKnnThreads, 0, st>>>(rows, n, pivots, P, cell);
-}
-
+// leaf (cell) of every feature row under the index's split planes
 int knn_assign(b200mp_knn *k, const float *rows, long long n, int *cell, cudaStream_t st) {
-    const float4 *r4 = reinterpret_cast<const float4 *>(rows), *p4 = reinterpret_cast<const float4 *>(k->ix_pivots);
-    switch (k->nv) {
-        case 2: launch_assign<2>(r4, n, p4, k->index_P, cell, st); break;
-        case 3: launch_assign<3>(r4, n, p4, k->index_P, cell, st); break;
-        default: launch_assign<6>(r4, n, p4, k->index_P, cell, st); break;
-    }
+    knn_kd_assign_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(rows, n, k->nv * 4, k->index_L, k->ix_dims, k->ix_splits, cell);
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(1);
     return B200MP_OK;
@@ -1022,18 +1112,21 @@ int knn_cell_sort(b200mp_knn *k, const int *cell, long long n, int *counts, int 
 
 int knn_build_index(b200mp_knn *k, cudaStream_t st) {
     const long long n = k->n;
-    const int fw = k->nv * 4;
-    int P = 64;
-    while (P < 16384 && static_cast<long long>(P) * 128 < n) P *= 2;
+    const int fw = k->nv * 4, dim = k->dim;
+    int P = 64, L = 6;
+    const long long rows_per_cell = getenv("B200MP_KNN_CELL_ROWS") ? atoll(getenv("B200MP_KNN_CELL_ROWS")) : kCellQueries;
+    while (P < 65536 && static_cast<long long>(P) * rows_per_cell < n) { P *= 2; ++L; }
     k->index_P = P;
+    k->index_L = L;
     size_t off = 0;
     const size_t o_feat = off; off += align256(static_cast<size_t>(n) * fw * sizeof(float));
-    const size_t o_pts = off;  off += align256(static_cast<size_t>(n) * k->dim * sizeof(double));
+    const size_t o_pts = off;  off += align256(static_cast<size_t>(n) * dim * sizeof(double));
     const size_t o_orig = off; off += align256(static_cast<size_t>(n) * sizeof(int));
     const size_t o_start = off; off += align256(static_cast<size_t>(P + 1) * sizeof(int));
     const size_t o_lo = off; off += align256(static_cast<size_t>(P) * 24 * sizeof(float));
     const size_t o_hi = off; off += align256(static_cast<size_t>(P) * 24 * sizeof(float));
-    const size_t o_piv = off; off += align256(static_cast<size_t>(P) * fw * sizeof(float));
+    const size_t o_split = off; off += align256(static_cast<size_t>(P) * sizeof(float));
+    const size_t o_dims = off; off += align256(static_cast<size_t>(L + 1) * sizeof(int));
     int rc = k->index_mem.reserve(off);
     if (rc) return rc;
     char *m = k->index_mem.ptr;
@@ -1043,21 +1136,47 @@ int knn_build_index(b200mp_knn *k, cudaStream_t st) {
     k->ix_start = reinterpret_cast<int *>(m + o_start);
     k->ix_lo = reinterpret_cast<float *>(m + o_lo);
     k->ix_hi = reinterpret_cast<float *>(m + o_hi);
-    k->ix_pivots = reinterpret_cast<float *>(m + o_piv);
-    // temporaries: cell[n] | pos[n] | counts[P] | cursor[P]
-    rc = k->index_tmp.reserve(align256(static_cast<size_t>(n) * 4) * 2 + align256(static_cast<size_t>(P) * 4) * 2);
+    k->ix_splits = reinterpret_cast<float *>(m + o_split);
+    k->ix_dims = reinterpret_cast<int *>(m + o_dims);
+    // temporaries: cell[n] | pos[n] | counts[P] | cursor[P] | hist[P / 2][bins] | boxes A, B [P][2 dim] | extent[2 dim]
+    const size_t a_n = align256(static_cast<size_t>(n) * 4), a_p = align256(static_cast<size_t>(P) * 4);
+    const size_t a_hist = align256(static_cast<size_t>(P / 2) * kKdBins * 4), a_box = align256(static_cast<size_t>(P) * 2 * dim * 4);
+    rc = k->index_tmp.reserve(2 * a_n + 2 * a_p + a_hist + 2 * a_box + 256);
     if (rc) return rc;
-    int *cell = reinterpret_cast<int *>(k->index_tmp.ptr);
-    int *pos = reinterpret_cast<int *>(k->index_tmp.ptr + align256(static_cast<size_t>(n) * 4));
-    int *counts = reinterpret_cast<int *>(k->index_tmp.ptr + 2 * align256(static_cast<size_t>(n) * 4));
-    int *cursor = counts + align256(static_cast<size_t>(P) * 4) / 4;
-    knn_gather_pivots_kernel<<<(P * fw + 255) / 256, 256, 0, st>>>(k->d_feat, n, P, fw, k->ix_pivots);
+    char *t = k->index_tmp.ptr;
+    int *cell = reinterpret_cast<int *>(t);
+    int *pos = reinterpret_cast<int *>(t + a_n);
+    int *counts = reinterpret_cast<int *>(t + 2 * a_n);
+    int *cursor = reinterpret_cast<int *>(t + 2 * a_n + a_p);
+    unsigned *hist = reinterpret_cast<unsigned *>(t + 2 * a_n + 2 * a_p);
+    float *box_a = reinterpret_cast<float *>(t + 2 * a_n + 2 * a_p + a_hist);
+    float *box_b = reinterpret_cast<float *>(t + 2 * a_n + 2 * a_p + a_hist + a_box);
+    unsigned *ext = reinterpret_cast<unsigned *>(t + 2 * a_n + 2 * a_p + a_hist + 2 * a_box);
+    const unsigned nb = static_cast<unsigned>((n + 255) / 256);
+    // ---- split planes, level by level (cell[] doubles as the per-row node index while the tree grows)
+    {
+        unsigned init[2 * kKdMaxDim];
+        for (int j = 0; j < kKdMaxDim; ++j) { init[2 * j] = 0xffffffffu; init[2 * j + 1] = 0u; }
+        B200_CUDA(cudaMemcpyAsync(ext, init, sizeof(unsigned) * 2 * dim, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaStreamSynchronize(st));  // `init` is on the stack
+    }
+    knn_kd_extent_kernel<<<nb, 256, 0, st>>>(k->d_feat, n, fw, dim, ext);
+    knn_kd_plan_kernel<<<1, 1, 0, st>>>(ext, dim, L, k->ix_dims, box_a);
+    B200_CUDA(cudaMemsetAsync(cell, 0, static_cast<size_t>(n) * 4, st));
+    long long launches = 2;
+    for (int l = 0; l < L; ++l) {
+        B200_CUDA(cudaMemsetAsync(hist, 0, (static_cast<size_t>(1) << l) * kKdBins * 4, st));
+        knn_kd_hist_kernel<<<nb, 256, 0, st>>>(k->d_feat, n, fw, dim, cell, k->ix_dims, l, box_a, hist);
+        knn_kd_split_kernel<<<((1 << l) + 63) / 64, 64, 0, st>>>(hist, l, dim, k->ix_dims, box_a, box_b, k->ix_splits);
+        knn_kd_descend_kernel<<<nb, 256, 0, st>>>(k->d_feat, n, fw, cell, k->ix_dims, l, k->ix_splits);
+        std::swap(box_a, box_b);
+        launches += 3;
+    }
     B200_CUDA(cudaGetLastError());
-    k->ctx->launches.fetch_add(1);
-    if ((rc = knn_assign(k, k->d_feat, n, cell, st))) return rc;
+    k->ctx->launches.fetch_add(launches);
     if ((rc = knn_cell_sort(k, cell, n, counts, k->ix_start, cursor, pos, st))) return rc;
-    knn_permute_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(k->d_feat), k->d_pts, pos, n, k->dim,
-                                                                             k->nv, k->ix_feat, k->ix_pts, k->ix_orig);
+    knn_permute_kernel<<<nb, 256, 0, st>>>(reinterpret_cast<const float4 *>(k->d_feat), k->d_pts, pos, n, k->dim, k->nv, k->ix_feat, k->ix_pts,
+                                           k->ix_orig);
     knn_cell_bounds_kernel<<<(P * 32 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float *>(k->ix_feat), k->ix_start, P, fw, k->dim, k->ix_lo,
                                                                  k->ix_hi);
     B200_CUDA(cudaGetLastError());
