@@ -262,6 +262,8 @@ void b200mp_destroy(b200mp_ctx *c) {
     c->scratch.release();
     cudaFree(c->d_counters);
     if (c->h_small) cudaFreeHost(c->h_small);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -678,6 +680,41 @@ int validate_motions_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T
     float *d_q0 = reinterpret_cast<float *>(c->scratch.ptr);
     float *d_q1 = reinterpret_cast<float *>(c->scratch.ptr + qbytes);
     uint8_t *d_valid = reinterpret_cast<uint8_t *>(c->scratch.ptr + 2 * qbytes);
+    constexpr int64_t kChunk = int64_t(1) << 18;
+    if (std::is_same<T, float>::value && m >= 2 * kChunk) {
+        // large fp32 batches: chunks of 2^18 motions, the upload of chunk i + 1 and the download of chunk i - 1 overlap the
+        // kernel of chunk i (three streams, one event pair per chunk; overlap needs pinned caller buffers, pageable ones just serialise)
+        if (!c->h2d_stream) B200_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        if (!c->d2h_stream) B200_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        const int n_chunks = static_cast<int>((m + kChunk - 1) / kChunk);
+        std::vector<cudaEvent_t> up(n_chunks), done(n_chunks);
+        for (int i = 0; i < n_chunks; ++i) {
+            B200_CUDA(cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming));
+            B200_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        int err = B200MP_OK;
+        for (int i = 0; i < n_chunks && !err; ++i) {
+            const int64_t first = i * kChunk, cnt = std::min<int64_t>(kChunk, m - first);
+            const size_t off = static_cast<size_t>(first) * dim, bytes = static_cast<size_t>(cnt) * dim * sizeof(float);
+            cudaError_t ce = cudaMemcpyAsync(d_q0 + off, reinterpret_cast<const float *>(q0) + off, bytes, cudaMemcpyHostToDevice, c->h2d_stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_q1 + off, reinterpret_cast<const float *>(q1) + off, bytes, cudaMemcpyHostToDevice, c->h2d_stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(up[i], c->h2d_stream);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(c->stream, up[i], 0);
+            if (ce != cudaSuccess) { err = fail(B200MP_ERR_CUDA, "b200mp_validate_motions: upload failed: %s", cudaGetErrorString(ce)); break; }
+            err = b200mp_validate_motions_device(c, robot, e, d_q0 + off, d_q1 + off, cnt, resolution, d_valid + first, c->stream);
+            if (err) break;
+            ce = cudaEventRecord(done[i], c->stream);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(c->d2h_stream, done[i], 0);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(valid + first, d_valid + first, static_cast<size_t>(cnt), cudaMemcpyDeviceToHost, c->d2h_stream);
+            if (ce != cudaSuccess) err = fail(B200MP_ERR_CUDA, "b200mp_validate_motions: download failed: %s", cudaGetErrorString(ce));
+        }
+        cudaStreamSynchronize(c->h2d_stream);
+        cudaStreamSynchronize(c->stream);
+        cudaError_t ce = cudaStreamSynchronize(c->d2h_stream);
+        for (int i = 0; i < n_chunks; ++i) { cudaEventDestroy(up[i]); cudaEventDestroy(done[i]); }
+        if (!err && ce != cudaSuccess) err = fail(B200MP_ERR_CUDA, "b200mp_validate_motions: %s", cudaGetErrorString(ce));
+        return err;
+    }
     if ((rc = upload_states(c, q0, m * dim, d_q0, c->stream))) return rc;
     if ((rc = upload_states(c, q1, m * dim, d_q1, c->stream))) return rc;
     rc = b200mp_validate_motions_device(c, robot, e, d_q0, d_q1, m, resolution, d_valid, c->stream);

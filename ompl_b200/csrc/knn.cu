@@ -528,7 +528,7 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
                  const float *__restrict__ clo, const float *__restrict__ chi, int P, int dim, const double *__restrict__ q64,
                  const int *__restrict__ q_order, const int *__restrict__ q_start, const int *__restrict__ blk_start, long long nq, const long long *__restrict__ self_ids,
                  long long self_base, int use_self, int kk, float err_scale, float cmax, Partial *__restrict__ partial,
-                 unsigned long long *__restrict__ rows_visited) {
+                 unsigned long long *__restrict__ rows_visited, int stat_pairs) {
     constexpr int QPT = kCellQPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long bars[2];
@@ -702,6 +702,10 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
                 wr2 = fmaxf(wr2, __shfl_xor_sync(kFullMask, wr2, o));
             }
             const bool warp_skip = !(gap2 * 0.99999f <= wr2);  // also true for warps without queries (wr2 = -inf)
+            if (stat_pairs && !warp_skip) {
+                const unsigned nqw = __popc(__ballot_sync(kFullMask, has_q[0])) + __popc(__ballot_sync(kFullMask, has_q[QPT - 1]));
+                if (lane == 0) atomicAdd(rows_visited, static_cast<unsigned long long>(cnt) * nqw);
+            }
             mbar_wait(&bars[slot], (it >> 1) & 1);
             const float4 *tile = tiles + static_cast<size_t>(slot) * kCellTile * NV;
             for (int c0 = 0; c0 < (warp_skip ? 0 : cnt); c0 += 4) {
@@ -775,12 +779,13 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
             const int c = base + tid;
             bool pass = false;
             if (c < P && (c < own_lo || c > own_hi)) {
+                // block-level test (per-warp boxes were measured: queries of a cell are not ordered in space, so a warp's box is
+                // the block's box and listing per warp only adds tests); empty cells have gap = +inf and never pass
                 float d2 = 0.f;
                 for (int j = 0; j < dim; ++j) {
                     const float gap = fmaxf(fmaxf(clo[c * 24 + j] - s_qhi[j], s_qlo[j] - chi[c * 24 + j]), 0.f);
                     d2 = fmaf(gap, gap, d2);
                 }
-                // empty cells have gap = +inf: they never overlap and are harmless if listed
                 pass = sweep == 0 ? (d2 == 0.f) : (d2 > 0.f && d2 * 0.99999f <= s_rblk);
             }
             const unsigned bal = __ballot_sync(kFullMask, pass);
@@ -797,7 +802,7 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
             }
         }
     }
-    if (tid == 0 && rows_visited) atomicAdd(rows_visited, visited);
+    if (tid == 0 && rows_visited && !stat_pairs) atomicAdd(rows_visited, visited);
 }
 
 
@@ -1197,7 +1202,7 @@ int launch_cells(b200mp_knn *k, const double *d_q, const int *q_order, const int
     const unsigned grid = static_cast<unsigned>(nq / kCellQueries + k->index_P + 1);
     kern<<<grid, kCellThreads, smem, st>>>(k->ix_feat, k->ix_pts, k->ix_orig, k->ix_start, k->ix_lo, k->ix_hi, k->index_P, k->dim, d_q, q_order,
                                            q_start, blk_start, nq, d_self, self_base, use_self, kk, err_scale, k->cmax, d_partial,
-                                           k->d_rows_visited);
+                                           k->d_rows_visited, getenv("B200MP_KNN_STAT_PAIRS") ? 1 : 0);
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(1);
     return B200MP_OK;
