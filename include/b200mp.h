@@ -96,6 +96,11 @@ int b200mp_capt_build(const float *xyz, int64_t n, float r_min, float r_max, flo
 void b200mp_capt_destroy(b200mp_capt *capt);
 int b200mp_capt_sizes(const b200mp_capt *capt, int64_t *sizes);
 int b200mp_capt_export(const b200mp_capt *capt, float *tests, float *aabbs, uint32_t *aff_starts, float *aff, float *top);
+/* vamp::collision::factory::heightfield::flat (collision/factory.hh:363-386; shape collision/shapes.hh:250-312, test
+ * collision/sphere_heightfield.hh:9-30): centre, cell scale, nx x ny cells, heights[ny][nx] row-major (host buffer, copied).
+ * Tested after the z-aligned cuboids and before the point clouds, without pruning, like the reference (validity.hh:132-138). */
+int b200mp_env_add_heightfield(b200mp_env *env, float cx, float cy, float cz, float sx, float sy, float sz, int64_t nx, int64_t ny,
+                               const float *heights);
 /* vamp::collision::filter_pointcloud (external/vamp/src/impl/vamp/collision/filter.hh:176-274; Python entry
  * vamp.filter_pointcloud, bindings/environment.cc:168-190) on the device: cull to the range ball around `origin` and the
  * workspace box (when cull != 0), then six Morton-curve passes that drop every point within min_dist of the last point

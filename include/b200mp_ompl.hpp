@@ -181,6 +181,17 @@ namespace ompl::b200
         {
             check(b200mp_env_add_pointcloud(env_, xyz, static_cast<int64_t>(n), r_min, r_max, r_point), "addPointcloud");
         }
+
+        /// factory::heightfield::array(center, scale, {nx, ny}, data)  (factory.hh:405-421): heights[ny][nx] row-major
+        void addHeightfield(const std::array<float, 3> &c, const std::array<float, 3> &scale, std::size_t nx, std::size_t ny,
+                            const std::vector<float> &heights)
+        {
+            if (heights.size() != nx * ny)
+                throw ompl::Exception("b200mp::Environment::addHeightfield", "heights must hold nx * ny values");
+            check(b200mp_env_add_heightfield(env_, c[0], c[1], c[2], scale[0], scale[1], scale[2], static_cast<int64_t>(nx),
+                                             static_cast<int64_t>(ny), heights.data()),
+                  "addHeightfield");
+        }
         void sort()
         {
             check(b200mp_env_sort(env_), "sort");

@@ -61,6 +61,7 @@ struct b200mp_env {
     std::vector<HCapsule> capsules, zcapsules;
     std::vector<HCuboid> cuboids, zcuboids;
     std::vector<DeviceCapt> pcs;
+    std::vector<HeightFieldView> hfs;  // data pointers are device allocations owned by the environment
     float *d_blob = nullptr;
     void *d_grid = nullptr;
     bool use_grid = true;
@@ -332,6 +333,7 @@ void b200mp_env_destroy(b200mp_env *e) {
         cudaFree(p.aff_starts);
         cudaFree(p.pref);
     }
+    for (auto &h : e->hfs) cudaFree(const_cast<float *>(h.data));
     delete e;
 }
 
@@ -390,6 +392,27 @@ int b200mp_env_add_capsules(b200mp_env *e, const float *c, int n, int z_aligned)
         h.min_d = std::sqrt(xn * xn + yn * yn + zn * zn);
         (z_aligned ? e->zcapsules : e->capsules).push_back(h);
     }
+    e->committed = false;
+    return B200MP_OK;
+}
+
+int b200mp_env_add_heightfield(b200mp_env *e, float cx, float cy, float cz, float sx, float sy, float sz, int64_t nx, int64_t ny,
+                               const float *heights) {
+    if (!e || !heights || nx < 1 || ny < 1 || nx * ny > (int64_t(1) << 30) || !(sx != 0.f) || !(sy != 0.f) || !(sz != 0.f))
+        return fail(B200MP_ERR_INVALID, "b200mp_env_add_heightfield: bad argument");
+    if (e->hfs.size() >= kMaxHeightFields) return fail(B200MP_ERR_CAPACITY, "b200mp_env_add_heightfield: at most %d height fields", kMaxHeightFields);
+    B200_CUDA(cudaSetDevice(e->ctx->device));
+    HeightFieldView h{};
+    h.x = cx; h.y = cy; h.z = cz;
+    h.xs = 1.F / sx; h.ys = 1.F / sy; h.zs = 1.F / sz;  // factory::heightfield::flat stores reciprocals (factory.hh:376-385)
+    h.xd = static_cast<float>(nx); h.yd = static_cast<float>(ny);
+    h.xd2 = static_cast<float>(nx / 2); h.yd2 = static_cast<float>(ny / 2);
+    h.n = static_cast<unsigned>(nx * ny);
+    float *d = nullptr;
+    B200_CUDA(cudaMalloc(&d, static_cast<size_t>(nx * ny) * sizeof(float)));
+    B200_CUDA(cudaMemcpy(d, heights, static_cast<size_t>(nx * ny) * sizeof(float), cudaMemcpyHostToDevice));
+    h.data = d;
+    e->hfs.push_back(h);
     e->committed = false;
     return B200MP_OK;
 }
@@ -558,6 +581,8 @@ int b200mp_env_commit(b200mp_env *e) {
         const int grc = build_grids(e, &d);
         if (grc) return grc;
     }
+    d.n_hf = static_cast<int>(e->hfs.size());
+    for (int i = 0; i < d.n_hf; ++i) d.hf[i] = e->hfs[i];
     d.n_pc = static_cast<int>(e->pcs.size());
     for (int i = 0; i < d.n_pc; ++i) d.pc[i] = e->pcs[i].view;
     e->desc = d;

@@ -21,6 +21,16 @@ namespace b200mp {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxPointClouds = 4;
+constexpr int kMaxHeightFields = 2;
+
+// Height field (external/vamp/src/impl/vamp/collision/shapes.hh:250-312): centre, RECIPROCAL scales, cell counts (as floats,
+// the reference does this arithmetic in float), heights row-major in global memory.
+struct HeightFieldView {
+    float x, y, z, xs, ys, zs;
+    float xd, yd, xd2, yd2;
+    const float *data;
+    unsigned n;
+};
 
 // Point-cloud tree in global memory (arrays as external/vamp/src/impl/vamp/collision/capt.hh:571-613 stores them).
 struct CaptView {
@@ -65,6 +75,8 @@ struct SceneDesc {
     int sorted;  // 1 when every class is in non-decreasing min_distance order (prefix masks are then redundant)
     int n_pc;
     CaptView pc[kMaxPointClouds];
+    int n_hf;
+    HeightFieldView hf[kMaxHeightFields];
     int n_grid;  // 0: no grid (unsorted or small scene) -> ordered scans
     GridView grid[kGridLevels];
 };
@@ -470,6 +482,23 @@ __device__ __forceinline__ bool scan_pointclouds(const SceneDesc &d, const Tile<
     return hit;
 }
 
+// ------------------------------------------------------------------------------------------------ height fields
+// collision/sphere_heightfield.hh:9-30: the cell under the sphere's centre (index clamped to [0, xd] x [0, yd] as the reference
+// does; a read past the array, undefined there, takes the last element here); collision <=> z - r below the scaled height.
+__device__ __forceinline__ bool heightfields_hit(const SceneDesc &sd, float x, float y, float z, float r) {
+    bool hit = false;
+    for (int i = 0; i < sd.n_hf; ++i) {
+        const HeightFieldView &a = sd.hf[i];
+        const float xo = a.x - x, yo = a.y - y;
+        const float xs = floorf(fminf(fmaxf(fmaf(a.xs, xo, a.xd2), 0.f), a.xd));
+        const float ys = floorf(fminf(fmaxf(fmaf(a.ys, yo, a.yd2), 0.f), a.yd));
+        const unsigned idx = min(static_cast<unsigned>(max(__float2int_rn(fmaf(ys, a.xd, xs)), 0)), a.n - 1u);
+        const float zhs = fmaf(a.zs, __ldg(a.data + idx), a.z);
+        hit |= ((z - r) - zhs) < 0.0f;
+    }
+    return hit;
+}
+
 // ------------------------------------------------------------------------------------------------ one state per lane
 // Per-thread scratch in shared memory: slot s of thread t lives at base[s * BT + t] (bank-conflict free). Slots
 // 3l .. 3l+2 hold the world-space centre of link l's bounding sphere, then sin[dim] and cos[dim] of the joint angles.
@@ -651,6 +680,7 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
         c.ext[0] = group_max<G>(ext);
         if (!alive) { c.x[0] = kIdle; c.y[0] = kIdle; c.z[0] = kIdle; }  // idle lanes must never raise the sign bit
         bool chit = scan_scene<1, kUntilAllHit, MASKED>(sc, c, alive);
+        if (sd.n_hf > 0 && alive && !chit) chit = heightfields_hit(sd, c.x[0], c.y[0], c.z[0], cl.w);
         if (sd.n_pc > 0) chit |= scan_pointclouds<1, kUntilAllHit>(sd, c, alive && !chit);
         const bool need = group_any<G>(chit && alive) && alive;
         if (!__any_sync(kFull, need)) continue;
@@ -672,6 +702,11 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
                 if (!on) { s.ext[t] = -INFINITY; s.x[t] = kIdle; s.y[t] = kIdle; s.z[t] = kIdle; }
             }
             fhit |= scan_scene<FT, POLICY, MASKED>(sc, s, need && !fhit);
+            if (sd.n_hf > 0) {
+#pragma unroll
+                for (int t = 0; t < FT; ++t)
+                    if (need && !fhit && s.ext[t] > -1e30f) fhit = heightfields_hit(sd, s.x[t], s.y[t], s.z[t], s.r[t]);
+            }
             if (sd.n_pc > 0) fhit |= scan_pointclouds<FT, POLICY>(sd, s, need && !fhit);
             if (EDGE) {
                 if (__any_sync(kFull, fhit)) return !fhit;
@@ -757,6 +792,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
         bool h;
         if (lvl >= 0) h = grid_scan_scene(sd.grid[lvl], sc, x, y, z, r, on, any_mode);
         else h = ordered_scan_one<G>(&sv.sc, x, y, z, r, on, any_mode);
+        if (sd.n_hf > 0 && on && !h) h = heightfields_hit(sd, x, y, z, r);
         if (sd.n_pc > 0) h |= pointclouds_one(sv.pc, sd.n_pc, x, y, z, r, on && !h, any_mode);
         if (!fine) {
             need = group_any<G>(h && alive) && alive;

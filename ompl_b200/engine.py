@@ -57,6 +57,7 @@ def load_library():
     L.b200mp_env_add_cuboids.argtypes = [_vp, _vp, C.c_int, C.c_int]
     L.b200mp_env_add_capsules.argtypes = [_vp, _vp, C.c_int, C.c_int]
     L.b200mp_env_add_capt.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, C.c_float, C.c_float, C.c_float]
+    L.b200mp_env_add_heightfield.argtypes = [_vp] + [C.c_float] * 6 + [_i64, _i64, _vp]
     L.b200mp_env_add_pointcloud.argtypes = [_vp, _vp, _i64, C.c_float, C.c_float, C.c_float]
     L.b200mp_capt_build.argtypes = [_vp, _i64, C.c_float, C.c_float, C.c_float, C.POINTER(_vp)]
     L.b200mp_capt_destroy.argtypes = [_vp]
@@ -314,6 +315,12 @@ class Environment:
     def add_capsules(self, c7, z_aligned: bool = False):
         a = _host(c7, np.float32).reshape(-1, 7)
         _check(self._L.b200mp_env_add_capsules(self._h, a.ctypes.data, a.shape[0], int(z_aligned)))
+
+    def add_heightfield(self, centre, scale, heights):
+        """factory::heightfield::flat: heights[ny][nx] row-major, cell size `scale`, centred at `centre`."""
+        h = _host(np.asarray(heights), np.float32)
+        _check(self._L.b200mp_env_add_heightfield(self._h, *[float(v) for v in centre], *[float(v) for v in scale], h.shape[1], h.shape[0],
+                                                  h.ctypes.data))
 
     def add_capt(self, t: dict):
         tests = _host(t["tests"], np.float32)

@@ -118,6 +118,8 @@ def fill_env(env, scene: dict, sort: bool = True, grid: bool | None = None):
         env.add_cuboids(scene["cuboids"], z_aligned=False)
     if "z_cuboids" in scene and len(scene["z_cuboids"]):
         env.add_cuboids(scene["z_cuboids"], z_aligned=True)
+    if "heightfield" in scene:
+        env.add_heightfield(scene["heightfield_centre"], scene["heightfield_scale"], scene["heightfield"])
     if sort:
         env.sort()
     if hasattr(env, "finalize"):
@@ -201,3 +203,13 @@ def shelf_cloud(n: int, seed: int = 7, robot: str = "fetch") -> np.ndarray:
         p[ax] = c[ax] + sg * h[ax]
         pts[i] = p
     return pts.astype(np.float32)
+
+
+def terrain(seed: int = 4, nx: int = 64, ny: int = 48, size: float = 4.0, z0: float = -0.6) -> dict:
+    """A rolling height field (heights 0 .. 0.55 m above z0) covering size x size metres around the robot, as scene-dict
+    entries for fill_env (factory::heightfield::flat arguments: centre, cell scale, heights[ny][nx])."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    h = (0.25 + 0.25 * np.sin(xx / 5.0) * np.cos(yy / 4.0) + 0.05 * rng.uniform(size=(ny, nx))).astype(np.float32)
+    return {"heightfield": h, "heightfield_centre": np.array([0.1, -0.05, z0], np.float32),
+            "heightfield_scale": np.array([size / nx, size / ny, 1.0], np.float32)}

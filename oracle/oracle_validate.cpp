@@ -97,11 +97,20 @@ namespace
         float r_min, r_max, r_point;
     };
 
+    // shapes.hh:250-312; xs, ys, zs are the RECIPROCAL scales (factory.hh:363-386)
+    struct HeightField
+    {
+        float x, y, z, xs, ys, zs;
+        std::size_t xd, yd, xd2, yd2;
+        std::vector<float> data;
+    };
+
     struct Env
     {
         std::vector<Sphere> spheres;
         std::vector<Capsule> capsules, zcapsules;
         std::vector<Cuboid> cuboids, zcuboids;
+        std::vector<HeightField> hfs;
         std::vector<Capt> pcs;
     };
 
@@ -243,6 +252,21 @@ namespace
         return false;
     }
 
+    // sphere_heightfield.hh:9-30: value < 0 (sign bit) <=> collision. The cell index is clamped to [0, xd] x [0, yd] -- one past the
+    // last column / row, exactly as the reference does; reads beyond the array (sphere past the far edge) are undefined there and
+    // clamped to the last element here.
+    inline float t_heightfield(const HeightField &a, float x, float y, float z, float r)
+    {
+        const float xo = a.x - x, yo = a.y - y;
+        const float xs = std::floor(clampf(std::fmaf(a.xs, xo, static_cast<float>(a.xd2)), 0.F, static_cast<float>(a.xd)));
+        const float ys = std::floor(clampf(std::fmaf(a.ys, yo, static_cast<float>(a.yd2)), 0.F, static_cast<float>(a.yd)));
+        const float index = std::fmaf(ys, static_cast<float>(a.xd), xs);
+        std::size_t i = static_cast<std::size_t>(std::lrintf(index));
+        if (i >= a.data.size()) i = a.data.size() - 1;
+        const float zhs = std::fmaf(a.zs, a.data[i], a.z);
+        return (z - r) - zhs;
+    }
+
     inline bool sphere_env(const Env &e, const float *sx, const float *sy, const float *sz, float sr, int lanes, Counters *cnt)
     {
         float ext[kRake];
@@ -262,6 +286,16 @@ namespace
             return true;
         if (scan_class(e.zcuboids, ext, lanes, 22, cnt, [&](const Cuboid &o, int l) { return t_zcuboid(o, sx[l], sy[l], sz[l], rsq); }))
             return true;
+        for (const auto &hf : e.hfs)  // validity.hh:132-138 (no pruning: min_distance is 0)
+        {
+            for (int l = 0; l < lanes; ++l)
+            {
+                if (t_heightfield(hf, sx[l], sy[l], sz[l], sr) < 0.0f)
+                {
+                    return true;
+                }
+            }
+        }
         for (const auto &pc : e.pcs)
         {
             for (int l = 0; l < lanes; ++l)
@@ -524,6 +558,7 @@ namespace
         };
         for (const auto &c : e.cuboids) cub(c);
         for (const auto &c : e.zcuboids) cub(c);
+        for (const auto &hf : e.hfs) best = std::min(best, static_cast<double>(t_heightfield(hf, static_cast<float>(x), static_cast<float>(y), static_cast<float>(z), static_cast<float>(r))));
         for (const auto &t : e.pcs)
         {
             const std::size_t n8 = t.n_aff8;
@@ -658,6 +693,18 @@ extern "C"
         s.min_d = std::sqrt(xn * xn + yn * yn + zn * zn);
         auto &env = *static_cast<Env *>(e);
         (z_aligned ? env.zcapsules : env.capsules).push_back(s);
+    }
+
+    // factory::heightfield::flat (factory.hh:363-386): centre, scale (stored as reciprocals), cells, row-major heights
+    void or_env_add_heightfield(void *e, float cx, float cy, float cz, float sx, float sy, float sz, std::int64_t nx, std::int64_t ny, const float *data)
+    {
+        HeightField h;
+        h.x = cx; h.y = cy; h.z = cz;
+        h.xs = 1.F / sx; h.ys = 1.F / sy; h.zs = 1.F / sz;
+        h.xd = static_cast<std::size_t>(nx); h.yd = static_cast<std::size_t>(ny);
+        h.xd2 = h.xd / 2; h.yd2 = h.yd / 2;
+        h.data.assign(data, data + nx * ny);
+        static_cast<Env *>(e)->hfs.push_back(std::move(h));
     }
 
     // attach a point-cloud tree given as flat arrays (layout of refv_capt_export / b200mp_env_add_capt)

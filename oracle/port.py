@@ -40,6 +40,7 @@ def lib():
     L.or_env_add_sphere.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
     L.or_env_add_cuboid.argtypes = [C.c_void_p, _f32p, C.c_int]
     L.or_env_add_capsule.argtypes = [C.c_void_p, _f32p, C.c_int]
+    L.or_env_add_heightfield.argtypes = [C.c_void_p] + [C.c_float] * 6 + [C.c_int64, C.c_int64, _f32p]
     L.or_env_add_capt.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _u32p, _f32p, C.c_int64, _f32p,
                                   C.c_float, C.c_float, C.c_float]
     L.or_env_sort.argtypes = [C.c_void_p]
@@ -117,6 +118,11 @@ class PortEnvironment:
     def add_capsules(self, c7, z_aligned=False):
         for c in _f32(c7).reshape(-1, 7):
             self._L.or_env_add_capsule(self._h, np.ascontiguousarray(c), int(z_aligned))
+
+    def add_heightfield(self, centre, scale, heights):
+        """factory::heightfield::flat(centre, scale, heights.shape[1] x heights.shape[0] cells, row-major heights)"""
+        h = _f32(heights)
+        self._L.or_env_add_heightfield(self._h, *[float(v) for v in centre], *[float(v) for v in scale], h.shape[1], h.shape[0], h.reshape(-1))
 
     def add_capt(self, t: dict):
         aff = np.ascontiguousarray(t["aff"], np.float32)

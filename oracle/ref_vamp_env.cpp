@@ -41,6 +41,15 @@ extern "C"
         static_cast<Env *>(e)->f.pointclouds.emplace_back(pts, r_min, r_max, r_point);
     }
 
+    void refv_env_add_heightfield(void *e, float cx, float cy, float cz, float sx, float sy, float sz, std::int64_t nx, std::int64_t ny, const float *data)
+    {
+        std::vector<float> d(data, data + nx * ny);
+        // factory::heightfield::flat (factory.hh:363-386; that header needs real Eigen, so its one constructor call is made here):
+        // the shape stores the reciprocal scales
+        static_cast<Env *>(e)->f.heightfields.emplace_back(
+            vc::HeightField<float>(cx, cy, cz, 1.F / sx, 1.F / sy, 1.F / sz, static_cast<std::size_t>(nx), static_cast<std::size_t>(ny), d));
+    }
+
     void refv_env_sort(void *e) { static_cast<Env *>(e)->f.sort(); }
 
     void refv_env_finalize(void *e)

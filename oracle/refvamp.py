@@ -39,6 +39,7 @@ def lib():
     L.refv_env_add_sphere.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
     L.refv_env_add_cuboid.argtypes = [C.c_void_p, _f32p, C.c_int]
     L.refv_env_add_capsule.argtypes = [C.c_void_p, _f32p, C.c_int]
+    L.refv_env_add_heightfield.argtypes = [C.c_void_p] + [C.c_float] * 6 + [C.c_int64, C.c_int64, _f32p]
     L.refv_env_add_pointcloud.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_float, C.c_float, C.c_float]
     L.refv_env_sort.argtypes = [C.c_void_p]
     L.refv_env_finalize.argtypes = [C.c_void_p]
@@ -89,6 +90,11 @@ class RefEnvironment:
     def add_capsules(self, c7, z_aligned=False):
         for c in _f32(c7).reshape(-1, 7):
             self._L.refv_env_add_capsule(self._h, np.ascontiguousarray(c), int(z_aligned))
+        self._final = False
+
+    def add_heightfield(self, centre, scale, heights):
+        h = _f32(heights)
+        self._L.refv_env_add_heightfield(self._h, *[float(v) for v in centre], *[float(v) for v in scale], h.shape[1], h.shape[0], h.reshape(-1))
         self._final = False
 
     def add_pointcloud(self, xyz, r_min, r_max, r_point):

@@ -109,6 +109,12 @@ def main():
         cloud_case("fetch_cloud", "fetch", (0.012, 0.24, 0.0025), 1500,
                    synth.clutter_scene(11, 20, 20, rho_lo=0.6, rho_hi=1.4, z_lo=0.2, z_hi=1.6), 1500, 800, 505)
         return
+    if "--heightfield" in sys.argv:  # terrain under Panda, alone and together with primitives (validity.hh:132-138)
+        validation_case("panda_terrain", "panda", synth.terrain(), True, 3000, 1500, 808)
+        sc = synth.clutter_scene(14, 40, 40, n_capsules=10)
+        sc.update(synth.terrain(seed=5))
+        validation_case("fetch_terrain_clutter", "fetch", sc, True, 2000, 1000, 909)
+        return
     if "--more-robots" in sys.argv:  # UR5 (6-DOF chain) and Baxter (two 7-DOF arms, resolution 64); written without touching the older files
         validation_case("ur5_clutter", "ur5", synth.clutter_scene(12, 60, 60, n_capsules=20, n_zcuboids=20, n_zcapsules=20), True, 2000, 1000, 606)
         validation_case("baxter_clutter", "baxter", synth.clutter_scene(13, 10, 10, n_capsules=4, n_zcuboids=4, n_zcapsules=4), True, 2000, 1000, 707)

@@ -10,7 +10,7 @@ from oracle import port
 from tests.util import assert_validity_parity, load_golden
 from tests.conftest import have_reference_build
 
-CASES = ["panda_cage", "panda_clutter", "panda_clutter_unsorted", "fetch_clutter", "ur5_clutter", "baxter_clutter"]
+CASES = ["panda_cage", "panda_clutter", "panda_clutter_unsorted", "fetch_clutter", "ur5_clutter", "baxter_clutter", "panda_terrain", "fetch_terrain_clutter"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -11,7 +11,7 @@ from tests.util import assert_validity_parity, load_golden
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["panda_cage", "panda_clutter", "panda_clutter_unsorted", "fetch_clutter", "ur5_clutter", "baxter_clutter"]
+CASES = ["panda_cage", "panda_clutter", "panda_clutter_unsorted", "fetch_clutter", "ur5_clutter", "baxter_clutter", "panda_terrain", "fetch_terrain_clutter"]
 
 
 def clr_states(pe, robot, q):

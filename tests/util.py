@@ -5,7 +5,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-SCENE_KEYS = ("spheres", "capsules", "z_capsules", "cuboids", "z_cuboids")
+SCENE_KEYS = ("spheres", "capsules", "z_capsules", "cuboids", "z_cuboids", "heightfield", "heightfield_centre", "heightfield_scale")
 
 
 def load_golden(name):
