@@ -74,10 +74,11 @@ class EngineBackend:
     def neighbors_part(self, states: torch.Tensor, k: int, part: int, parts: int, idx: torch.Tensor, dst: torch.Tensor):
         """Fill the rows of this rank's share of ALL queries (every state against the whole set, self excluded) into the
         [n][k] tables idx / dst; rows of other shares stay untouched (b200mp_knn_query_part_device_f32)."""
-        if self._knn is not None:
-            self._knn.close()
         n = states.shape[0]
-        self._knn = NearestNeighbors(self.ctx, self.dim)
+        if self._knn is None:
+            self._knn = NearestNeighbors(self.ctx, self.dim)   # kept across builds: its device buffers are grow-only
+        else:
+            self._knn.clear()
         self._knn.add_device_f32(states.data_ptr(), n, self.max_norm, self._stream())
         self._knn.query_part_device_f32(states.data_ptr(), n, k, idx.data_ptr(), dst.data_ptr(), part, parts, self_base=0, exclude_self=True,
                                         stream=self._stream())

@@ -208,7 +208,7 @@ def prm_candidates(robot: str, seed: int, first: int, count: int) -> np.ndarray:
     c = np.arange(first, first + count, dtype=np.uint64)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
     words = []
-    for sub in range(2):
+    for sub in range((dim + 3) // 4):
         ctr = np.stack([c & np.uint64(0xFFFFFFFF), c >> np.uint64(32), np.full(count, sub, np.uint64), np.zeros(count, np.uint64)], axis=1)
         words.append(philox4x32_10(ctr, key))
     w = np.concatenate(words, axis=1)[:, :dim]
