@@ -299,10 +299,10 @@ __global__ void knn_all_distances_kernel(const double *__restrict__ pts, const f
 // with a rigorous error bound, fp64 re-evaluation of survivors in the reference's operation order). Pruning uses lower
 // bounds only, so the result is the same exact (distance, id)-ordered top-k as the exhaustive scan.
 constexpr int kCellTile = 512;
-constexpr int kCellThreads = 128;  // threads per block of the cell kernel
-constexpr int kCellQPT = 2;        // queries per thread
-constexpr int kCellQueries = kCellThreads * kCellQPT;  // queries per block
-constexpr int kRoundCells = kCellThreads;
+constexpr int kCellQueries = 256;  // queries per block of the cell kernel
+// The kernel is built for two shapes: 128 threads x 2 queries (each candidate read feeds 8 FFMAs: best when the GPU is full of
+// blocks) and 256 threads x 1 query (twice the warps per block, half the work per warp and tile: a block finishes sooner, which is
+// what counts when a rank of a multi-GPU build has fewer blocks than the GPU has block slots).
 
 // ---- partition: a balanced k-d tree of depth L = log2(P) built level by level on the device. Every level splits all of its
 // nodes along one dimension (the one whose current cell extent is largest) at the approximate median of the node's rows:
@@ -519,17 +519,17 @@ __global__ void knn_cell_bounds_kernel(const float *__restrict__ feat_s, const i
     }
 }
 
-// Each thread owns kCellQPT queries (every broadcast candidate read from shared memory feeds 2 x 4 FFMAs per float4); the
+// Each thread owns QPT queries (with 2, every broadcast candidate read from shared memory feeds 2 x 4 FFMAs per float4); the
 // queries' top-k lists live in their slots of the `partial` output (global memory, touched only by the rare survivors),
 // so shared memory holds nothing but the two candidate tiles.
-template <int NV>
-__global__ void __launch_bounds__(kCellThreads)
+template <int NV, int QPT>
+__global__ void __launch_bounds__(kCellQueries / QPT)
 knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ pts_s, const int *__restrict__ orig, const int *__restrict__ cell_start,
                  const float *__restrict__ clo, const float *__restrict__ chi, int P, int dim, const double *__restrict__ q64,
                  const int *__restrict__ q_order, const int *__restrict__ q_start, const int *__restrict__ blk_start, long long nq, const long long *__restrict__ self_ids,
                  long long self_base, int use_self, int kk, float err_scale, float cmax, Partial *__restrict__ partial,
                  unsigned long long *__restrict__ rows_visited, int stat_pairs) {
-    constexpr int QPT = kCellQPT;
+    constexpr int kCellThreads = kCellQueries / QPT, kRoundCells = kCellThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long bars[2];
     __shared__ int s_job_row[2], s_job_cnt[2], s_job_cell[2];
@@ -1193,14 +1193,18 @@ int knn_build_index(b200mp_knn *k, cudaStream_t st) {
 
 template <int NV>
 int launch_cells(b200mp_knn *k, const double *d_q, const int *q_order, const int *q_start, const int *blk_start, long long nq,
-                 const long long *d_self, long long self_base, int use_self, int kk, Partial *d_partial, cudaStream_t st) {
+                 const long long *d_self, long long self_base, int use_self, int kk, Partial *d_partial, cudaStream_t st, int n_parts) {
     const size_t smem = 2 * kCellTile * NV * sizeof(float4);
-    auto kern = knn_cells_kernel<NV>;
+    // few blocks for this GPU (a rank's share of a multi-GPU build, or a small batch): the 256-thread shape
+    const long long slots = static_cast<long long>(k->ctx->sm_count) * 5;
+    const bool wide = (nq / kCellQueries) / std::max(n_parts, 1) < 2 * slots;
+    auto kern = wide ? knn_cells_kernel<NV, 1> : knn_cells_kernel<NV, 2>;
+    const int threads = wide ? kCellQueries : kCellQueries / 2;
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const float err_scale = 4.0f * (4 * NV + 2) * 5.96e-8f;
     // upper bound on the number of blocks (sum over cells of ceil(queries / kCellQueries)); surplus blocks exit at once
     const unsigned grid = static_cast<unsigned>(nq / kCellQueries + k->index_P + 1);
-    kern<<<grid, kCellThreads, smem, st>>>(k->ix_feat, k->ix_pts, k->ix_orig, k->ix_start, k->ix_lo, k->ix_hi, k->index_P, k->dim, d_q, q_order,
+    kern<<<grid, threads, smem, st>>>(k->ix_feat, k->ix_pts, k->ix_orig, k->ix_start, k->ix_lo, k->ix_hi, k->index_P, k->dim, d_q, q_order,
                                            q_start, blk_start, nq, d_self, self_base, use_self, kk, err_scale, k->cmax, d_partial,
                                            k->d_rows_visited, getenv("B200MP_KNN_STAT_PAIRS") ? 1 : 0);
     B200_CUDA(cudaGetLastError());
@@ -1249,9 +1253,9 @@ int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, co
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(3);
     switch (k->nv) {
-        case 2: rc = launch_cells<2>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st); break;
-        case 3: rc = launch_cells<3>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st); break;
-        default: rc = launch_cells<6>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st); break;
+        case 2: rc = launch_cells<2>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st, parts); break;
+        case 3: rc = launch_cells<3>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st, parts); break;
+        default: rc = launch_cells<6>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st, parts); break;
     }
     if (rc) return rc;
     knn_merge_kernel<<<static_cast<unsigned>((nq * 32 + 255) / 256), 256, 0, st>>>(partial, nq, kq, kq, d_idx, d_dist, d_counts, 1,
