@@ -90,6 +90,14 @@ int b200mp_env_add_capt(b200mp_env *env, int nlog2, const float *tests, const fl
 /* Build the tree from raw points on the host exactly as the reference's constructor does
  * (vamp::collision::CAPT(points, r_min, r_max, r_point), collision/capt.hh:294-365) and attach it. xyz[n][3]. */
 int b200mp_env_add_pointcloud(b200mp_env *env, const float *xyz, int64_t n, float r_min, float r_max, float r_point);
+/* The tree built on the device instead (n <= 2^17 points, i.e. a filtered cloud): histogram-median split planes and one block
+ * per leaf gathering its list. Same structure and query as the reference's tree, not the same arrays. Every leaf lists ALL
+ * points a sphere of radius <= r_max centred in its cell can touch, so the query is exact (equal to brute force over the
+ * points). The reference's own build can drop such a point while handing candidates down its recursion (reproduced by
+ * b200mp_env_add_pointcloud, whose arrays equal the reference's), so this tree accepts no state the reference-identical tree
+ * rejects, and rejects a few it accepts (0.02 % of random Fetch states in tests/test_capt_gpu.py). Use the host build when
+ * decisions must equal the reference's bit for bit. */
+int b200mp_env_add_pointcloud_device(b200mp_env *env, const float *xyz, int64_t n, float r_min, float r_max, float r_point);
 /* The same build as a standalone host object (no GPU needed), e.g. to export the arrays.
  * sizes[4] = nlog2, n_tests, n_leaves, n_aff8. Any output pointer of b200mp_capt_export may be NULL. */
 int b200mp_capt_build(const float *xyz, int64_t n, float r_min, float r_max, float r_point, b200mp_capt **out);

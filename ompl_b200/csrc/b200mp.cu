@@ -14,6 +14,7 @@
 #include "../../include/b200mp.h"
 #include "validate.cuh"
 #include "capt_order.cuh"
+#include "capt_gpu_build.cuh"
 #include "robots/panda_gen.cuh"
 #include "robots/fetch_gen.cuh"
 #include "robots/ur5_gen.cuh"
@@ -417,24 +418,10 @@ int b200mp_env_add_heightfield(b200mp_env *e, float cx, float cy, float cz, floa
     return B200MP_OK;
 }
 
-int b200mp_env_add_capt(b200mp_env *e, int nlog2, const float *tests, const float *aabbs, const uint32_t *aff_starts,
-                        const float *aff, int64_t n_aff8, const float *top, float r_min, float r_max, float r_point) {
-    (void)r_min;
-    (void)r_max;
-    if (!e || (!tests && nlog2 > 0) || !aabbs || !aff_starts || !aff || !top || nlog2 < 0 || nlog2 > 30 || n_aff8 < 0)
-        return fail(B200MP_ERR_INVALID, "b200mp_env_add_capt: bad argument");
-    if (e->pcs.size() >= kMaxPointClouds) return fail(B200MP_ERR_CAPACITY, "b200mp_env_add_capt: at most %d point clouds", kMaxPointClouds);
-    B200_CUDA(cudaSetDevice(e->ctx->device));
+// d.tests / d.aabbs / d.aff_starts / d.aff are device arrays in the reference's layout (ownership passes to the environment):
+// order every leaf's list by distance from its cell, build the prefix table, attach
+static int env_attach_capt(b200mp_env *e, DeviceCapt d, int nlog2, int64_t n_aff8, const float *top, float r_point) {
     const size_t nl = size_t(1) << nlog2, nt = nl - 1;
-    DeviceCapt d;
-    B200_CUDA(cudaMalloc(&d.tests, std::max<size_t>(nt, 1) * 4));
-    B200_CUDA(cudaMalloc(&d.aabbs, nl * 6 * 4));
-    B200_CUDA(cudaMalloc(&d.aff_starts, (nl + 1) * 4));
-    B200_CUDA(cudaMalloc(&d.aff, std::max<size_t>(3 * n_aff8 * 8, 4) * 4));
-    if (nt) B200_CUDA(cudaMemcpy(d.tests, tests, nt * 4, cudaMemcpyHostToDevice));
-    B200_CUDA(cudaMemcpy(d.aabbs, aabbs, nl * 6 * 4, cudaMemcpyHostToDevice));
-    B200_CUDA(cudaMemcpy(d.aff_starts, aff_starts, (nl + 1) * 4, cudaMemcpyHostToDevice));
-    if (n_aff8) B200_CUDA(cudaMemcpy(d.aff, aff, 3 * n_aff8 * 8 * 4, cudaMemcpyHostToDevice));
     if (n_aff8 > 0) {
         // device copy: lists ordered by distance from the leaf's cell + prefix table (capt_order.cuh)
         float *boxes = nullptr, *sorted = nullptr;
@@ -463,6 +450,91 @@ int b200mp_env_add_capt(b200mp_env *e, int nlog2, const float *tests, const floa
     e->pcs.push_back(d);
     e->committed = false;
     return B200MP_OK;
+}
+
+int b200mp_env_add_capt(b200mp_env *e, int nlog2, const float *tests, const float *aabbs, const uint32_t *aff_starts,
+                        const float *aff, int64_t n_aff8, const float *top, float r_min, float r_max, float r_point) {
+    (void)r_min;
+    (void)r_max;
+    if (!e || (!tests && nlog2 > 0) || !aabbs || !aff_starts || !aff || !top || nlog2 < 0 || nlog2 > 30 || n_aff8 < 0)
+        return fail(B200MP_ERR_INVALID, "b200mp_env_add_capt: bad argument");
+    if (e->pcs.size() >= kMaxPointClouds) return fail(B200MP_ERR_CAPACITY, "b200mp_env_add_capt: at most %d point clouds", kMaxPointClouds);
+    B200_CUDA(cudaSetDevice(e->ctx->device));
+    const size_t nl = size_t(1) << nlog2, nt = nl - 1;
+    DeviceCapt d;
+    B200_CUDA(cudaMalloc(&d.tests, std::max<size_t>(nt, 1) * 4));
+    B200_CUDA(cudaMalloc(&d.aabbs, nl * 6 * 4));
+    B200_CUDA(cudaMalloc(&d.aff_starts, (nl + 1) * 4));
+    B200_CUDA(cudaMalloc(&d.aff, std::max<size_t>(3 * n_aff8 * 8, 4) * 4));
+    if (nt) B200_CUDA(cudaMemcpy(d.tests, tests, nt * 4, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(d.aabbs, aabbs, nl * 6 * 4, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMemcpy(d.aff_starts, aff_starts, (nl + 1) * 4, cudaMemcpyHostToDevice));
+    if (n_aff8) B200_CUDA(cudaMemcpy(d.aff, aff, 3 * n_aff8 * 8 * 4, cudaMemcpyHostToDevice));
+    return env_attach_capt(e, d, nlog2, n_aff8, top, r_point);
+}
+
+int b200mp_env_add_pointcloud_device(b200mp_env *e, const float *xyz, int64_t n, float r_min, float r_max, float r_point) {
+    (void)r_min;
+    if (!e || n < 1 || !xyz || !(r_max > 0.f) || !(r_point >= 0.f))
+        return fail(B200MP_ERR_INVALID, "b200mp_env_add_pointcloud_device: bad argument");
+    if (n > (int64_t(1) << 17))
+        return fail(B200MP_ERR_CAPACITY, "b200mp_env_add_pointcloud_device: at most 2^17 points (filter the cloud first, or use the host build)");
+    if (e->pcs.size() >= kMaxPointClouds) return fail(B200MP_ERR_CAPACITY, "b200mp_env_add_pointcloud_device: at most %d point clouds", kMaxPointClouds);
+    B200_CUDA(cudaSetDevice(e->ctx->device));
+    int nlog2 = 0;
+    while ((int64_t(1) << nlog2) < n) ++nlog2;
+    const size_t nl = size_t(1) << nlog2, nt = nl - 1;
+    const unsigned nb = static_cast<unsigned>((n + 255) / 256);
+    float *d_xyz = nullptr, *box_a = nullptr, *box_b = nullptr, *cells = nullptr, *d_top = nullptr;
+    int *node = nullptr;
+    unsigned *hist = nullptr, *ext = nullptr;
+    uint32_t *counts8 = nullptr;
+    DeviceCapt d;
+    B200_CUDA(cudaMalloc(&d_xyz, static_cast<size_t>(n) * 12));
+    B200_CUDA(cudaMemcpy(d_xyz, xyz, static_cast<size_t>(n) * 12, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaMalloc(&node, static_cast<size_t>(n) * 4));
+    B200_CUDA(cudaMemset(node, 0, static_cast<size_t>(n) * 4));
+    B200_CUDA(cudaMalloc(&box_a, nl * 6 * 4));
+    B200_CUDA(cudaMalloc(&box_b, nl * 6 * 4));
+    B200_CUDA(cudaMalloc(&cells, nl * 6 * 4));
+    B200_CUDA(cudaMalloc(&hist, std::max<size_t>(nl / 2, 1) * kCgBins * 4));
+    B200_CUDA(cudaMalloc(&ext, 6 * 4));
+    B200_CUDA(cudaMalloc(&d_top, 6 * 4));
+    B200_CUDA(cudaMalloc(&counts8, nl * 4));
+    B200_CUDA(cudaMalloc(&d.tests, std::max<size_t>(nt, 1) * 4));
+    B200_CUDA(cudaMalloc(&d.aabbs, nl * 6 * 4));
+    B200_CUDA(cudaMalloc(&d.aff_starts, (nl + 1) * 4));
+    const unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    B200_CUDA(cudaMemcpy(ext, init, sizeof(init), cudaMemcpyHostToDevice));
+    cg_extent_kernel<<<nb, 256>>>(d_xyz, n, ext);
+    cg_root_kernel<<<1, 32>>>(ext, box_a, d_top);
+    long long launches = 2;
+    for (int l = 0; l < nlog2; ++l) {
+        const int axis = l % 3;
+        B200_CUDA(cudaMemset(hist, 0, (static_cast<size_t>(1) << l) * kCgBins * 4));
+        cg_hist_kernel<<<nb, 256>>>(d_xyz, n, node, axis, box_a, hist);
+        cg_split_kernel<<<((1 << l) + 63) / 64, 64>>>(hist, l, axis, box_a, box_b, d.tests);
+        cg_descend_kernel<<<nb, 256>>>(d_xyz, n, node, l, axis, d.tests);
+        std::swap(box_a, box_b);
+        launches += 3;
+    }
+    // the cells the QUERY sees: cut out by the planes alone, unbounded at the rim (a sphere centre can be anywhere)
+    capt_cell_boxes_kernel<<<static_cast<unsigned>((nl + 255) / 256), 256>>>(d.tests, nlog2, static_cast<unsigned>(nl), cells);
+    const float reach = (r_max + r_point) * 1.00001f + 1.0e-6f;
+    cg_lists_kernel<false><<<static_cast<unsigned>(nl), 128>>>(d_xyz, static_cast<int>(n), cells, reach * reach, counts8, nullptr, nullptr, 0, nullptr);
+    cg_scan_kernel<<<1, 1024>>>(counts8, static_cast<unsigned>(nl), d.aff_starts);
+    uint32_t total8 = 0;
+    B200_CUDA(cudaMemcpy(&total8, d.aff_starts + nl, 4, cudaMemcpyDeviceToHost));
+    const int64_t n_aff8 = total8;
+    B200_CUDA(cudaMalloc(&d.aff, std::max<size_t>(static_cast<size_t>(3) * n_aff8 * 8, 4) * 4));
+    cg_lists_kernel<true><<<static_cast<unsigned>(nl), 128>>>(d_xyz, static_cast<int>(n), cells, reach * reach, nullptr, d.aff_starts, d.aff, n_aff8, d.aabbs);
+    float top[6];
+    B200_CUDA(cudaMemcpy(top, d_top, sizeof(top), cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaDeviceSynchronize());
+    e->ctx->launches.fetch_add(launches + 4);
+    cudaFree(d_xyz); cudaFree(node); cudaFree(box_a); cudaFree(box_b); cudaFree(cells); cudaFree(hist); cudaFree(ext); cudaFree(d_top); cudaFree(counts8);
+    return env_attach_capt(e, d, nlog2, n_aff8, top, r_point);
 }
 
 int b200mp_env_set_grid(b200mp_env *e, int enable) {

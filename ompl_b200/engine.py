@@ -59,6 +59,7 @@ def load_library():
     L.b200mp_env_add_capt.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, C.c_float, C.c_float, C.c_float]
     L.b200mp_env_add_heightfield.argtypes = [_vp] + [C.c_float] * 6 + [_i64, _i64, _vp]
     L.b200mp_env_add_pointcloud.argtypes = [_vp, _vp, _i64, C.c_float, C.c_float, C.c_float]
+    L.b200mp_env_add_pointcloud_device.argtypes = [_vp, _vp, _i64, C.c_float, C.c_float, C.c_float]
     L.b200mp_capt_build.argtypes = [_vp, _i64, C.c_float, C.c_float, C.c_float, C.POINTER(_vp)]
     L.b200mp_capt_destroy.argtypes = [_vp]
     L.b200mp_filter_pointcloud.argtypes = [_vp, _vp, _i64, C.c_float, C.c_float, _vp, _vp, _vp, C.c_int, _vp, _vp]
@@ -336,6 +337,11 @@ class Environment:
         """vamp::collision::CAPT(points, r_min, r_max, r_point), built on the host by the engine."""
         a = _host(xyz, np.float32).reshape(-1, 3)
         _check(self._L.b200mp_env_add_pointcloud(self._h, a.ctypes.data, a.shape[0], r_min, r_max, r_point))
+
+    def add_pointcloud_device(self, xyz, r_min: float, r_max: float, r_point: float):
+        """The same tree structure built on the GPU (b200mp_env_add_pointcloud_device; at most 2^17 points)."""
+        a = _host(xyz, np.float32).reshape(-1, 3)
+        _check(self._L.b200mp_env_add_pointcloud_device(self._h, a.ctypes.data, a.shape[0], r_min, r_max, r_point))
 
     def set_grid(self, enable: bool):
         """Candidate-grid culling of sorted scenes on/off (b200mp_env_set_grid); takes effect at the next commit()."""

@@ -99,6 +99,13 @@ def c4(ctx, n_motions):
     env.add_pointcloud(kept, *radii)
     env.commit()
     t_build = time.perf_counter() - t0
+    env_dev = ompl_b200.Environment(ctx)
+    env_dev.add_pointcloud_device(kept[:64], *radii)   # warm-up (kernel load)
+    env_dev = ompl_b200.Environment(ctx)
+    t0 = time.perf_counter()
+    env_dev.add_pointcloud_device(kept, *radii)
+    env_dev.commit()
+    t_build_dev = time.perf_counter() - t0
     q0, q1 = synth.fixed_length_edges("fetch", n_motions, 4321)
     d0, d1 = torch.from_numpy(q0).cuda(), torch.from_numpy(q1).cuda()
     out = torch.zeros(n_motions, dtype=torch.uint8, device="cuda")
@@ -116,7 +123,7 @@ def c4(ctx, n_motions):
             "ms_filter_gpu": t_filter_gpu * 1e3, "ms_filter_cpu_restatement_1thread": t_filter_cpu * 1e3,
             "ms_filter_reference_1thread": None if t_filter_ref is None else t_filter_ref * 1e3,
             "filtered_points_reference": int(len(ref_kept)) if HAVE_REF else None,
-            "ms_tree_build_host": t_build * 1e3, "motions": n_motions, "states_per_motion": 64,
+            "ms_tree_build_host": t_build * 1e3, "ms_tree_build_device": t_build_dev * 1e3, "motions": n_motions, "states_per_motion": 64,
             "ms_validate": t_val * 1e3, "edges_per_s": n_motions / t_val, "valid_fraction": float(got.mean())}
     if len(vi) > 0:
         rep = np.resize(vi, 1 << 16)
@@ -128,6 +135,12 @@ def c4(ctx, n_motions):
             stream.synchronize()
         t2 = dev_time(run2)
         line.update({"all_valid_unique": int(len(vi)), "ms_all_valid_2^16": t2 * 1e3, "all_valid_states_per_s": len(rep) * 64 / t2})
+    ov = torch.zeros(n_motions, dtype=torch.uint8, device="cuda")
+    ctx.validate_motions_ptr("fetch", env_dev, d0.data_ptr(), d1.data_ptr(), n_motions, ov.data_ptr(), stream=stream.cuda_stream)
+    stream.synchronize()
+    gd = ov.cpu().numpy()
+    line["device_built_tree"] = {"decisions_differing_from_host_built": int((gd != got).sum()),
+                                 "accepted_but_rejected_by_host_built": int(((gd == 1) & (got == 0)).sum())}
     # CPU checker on a bounded sample, same tree arrays (engine-built == reference-built, tests/test_capt_cpu.py)
     sample = min(n_motions, 1 << 15)
     if HAVE_REF:
