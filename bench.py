@@ -283,16 +283,17 @@ def main():
         assert bool(av.all()), "all-valid sub-workload must validate as valid"
         w_ref = w_ref_edge * len(rep) / (ms_av * 1e-3) / 1e12
         # executed flops per launch of exactly this workload, counted by ncu (profiles/validate_flops.json)
-        w_exec_launch, src = None, None
+        w_exec_launch, src, traffic = None, None, None
         try:
             with open(os.path.join(ROOT, "profiles", "validate_flops.json")) as f:
                 pj = json.load(f)
             if pj.get("motions") == len(rep) and pj.get("unique_valid") == int(len(valid_idx)):
                 w_exec_launch, src = float(pj["flops_per_launch"]), pj.get("source")
+                traffic = pj.get("dram_bytes")  # dram__bytes_read.sum + dram__bytes_write.sum of the same launch (ncu)
         except Exception:
             pass
         achieved = (w_exec_launch / (ms_av * 1e-3) / 1e12) if w_exec_launch else w_ref
-        line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                             "kernel": "validate_motions_kernel<Panda, sorted, grid>",
                             "achieved_is": ("executed FP32 flops (ncu-counted FFMA x2 + FADD + FMUL per launch of this workload: " + str(src) + ")")
                             if w_exec_launch else "W_ref (no ncu flop count for this workload found)",
