@@ -234,7 +234,7 @@ def main():
     if args.roadmap_n > 0:
         from ompl_b200.roadmap import EngineBackend, RoadmapBuilder
         builder = RoadmapBuilder(EngineBackend(ctx, env, "panda"))
-        w = builder.build(args.roadmap_n, 16, 7)   # warm-up at full size with another seed (grow-only buffers, memory pool, NCCL channels)
+        w = builder.build(args.roadmap_n, 16, 42)  # warm-up = the timed build itself, like the warm-up steps above (grow-only buffers, memory pool, NCCL channels)
         del w
         barrier()
         l0 = ctx.launch_count
@@ -249,7 +249,7 @@ def main():
         for k, v in zip(keys, t.tolist()):
             st[k] = v
         roadmap = {"workload": f"PRM roadmap: {args.roadmap_n} valid Panda samples, k=16 (self excluded), undirected de-duplicated edges, "
-                               "resolution 32, C2 scene; one full-size warm-up build (seed 7) precedes the timed build (seed 42)", "n_gpus": world, "scaling": "strong",
+                               "resolution 32, C2 scene; one identical warm-up build precedes the timed build", "n_gpus": world, "scaling": "strong",
                    "build_ms": st["ms_total"], **st}
         del rm
 
