@@ -182,6 +182,12 @@ namespace ompl::b200
             check(b200mp_env_add_pointcloud(env_, xyz, static_cast<int64_t>(n), r_min, r_max, r_point), "addPointcloud");
         }
 
+        /// The same tree structure built on the GPU (exact variant, at most 2^17 points; see b200mp_env_add_pointcloud_device)
+        void addPointcloudDevice(const float *xyz, std::size_t n, float r_min, float r_max, float r_point)
+        {
+            check(b200mp_env_add_pointcloud_device(env_, xyz, static_cast<int64_t>(n), r_min, r_max, r_point), "addPointcloudDevice");
+        }
+
         /// factory::heightfield::array(center, scale, {nx, ny}, data)  (factory.hh:405-421): heights[ny][nx] row-major
         void addHeightfield(const std::array<float, 3> &c, const std::array<float, 3> &scale, std::size_t nx, std::size_t ny,
                             const std::vector<float> &heights)
@@ -248,6 +254,22 @@ namespace ompl::b200
     }  // namespace detail
 
     /// isValid(state) == validate_motion<Robot, rake, 1>(q, q, env) of the reference bridge. Thread safe.
+
+    /// vamp::collision::filter_pointcloud(pc, min_dist, max_range, origin, workspace_min, workspace_max, cull)
+    /// (collision/filter.hh:176-274) on the device; points as x, y, z triples.
+    inline std::vector<float> filterPointcloud(const EnginePtr &engine, const std::vector<float> &xyz, float min_dist, float max_range,
+                                               const std::array<float, 3> &origin, const std::array<float, 3> &ws_min,
+                                               const std::array<float, 3> &ws_max, bool cull)
+    {
+        const std::size_t n = xyz.size() / 3;
+        std::vector<float> out(3 * (n + 1));
+        int64_t m = 0;
+        check(b200mp_filter_pointcloud(engine->get(), xyz.data(), static_cast<int64_t>(n), min_dist, max_range, origin.data(), ws_min.data(),
+                                       ws_max.data(), cull ? 1 : 0, out.data(), &m),
+              "filterPointcloud");
+        out.resize(3 * static_cast<std::size_t>(m));
+        return out;
+    }
     template <typename Robot>
     class B200StateValidityChecker : public ob::StateValidityChecker
     {
