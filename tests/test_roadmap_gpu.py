@@ -38,6 +38,24 @@ def test_prm_build_matches_checker(ctx, scene, n, k, seed):
     assert st["n_candidates"] >= n
 
 
+@pytest.mark.parametrize("robot,scene_kw,n,k", [
+    ("ur5", dict(seed=51, n_spheres=100, n_cuboids=100), 1200, 8),        # 6 joints
+    ("fetch", dict(seed=52, n_spheres=40, n_cuboids=40, rho_lo=0.6, rho_hi=1.4, z_lo=0.2, z_hi=1.6), 1000, 8),   # 8 joints: both Philox blocks full
+    ("baxter", dict(seed=5, n_spheres=6, n_cuboids=6, n_capsules=4), 600, 6),   # 14 joints: four Philox blocks per candidate
+])
+def test_prm_build_other_robots(ctx, robot, scene_kw, n, k):
+    sc = synth.clutter_scene(**scene_kw)
+    env = synth.fill_env(ompl_b200.Environment(ctx), sc)
+    pe = synth.fill_env(port.PortEnvironment(), sc)
+    got = ctx.prm_build(robot, env, n, k, 77)
+    want = RoadmapBuilder(CheckerBackend(pe, robot, nthreads=8)).build(n, k, 77)
+    np.testing.assert_array_equal(got["states"], want.states.numpy())
+    np.testing.assert_array_equal(got["edges"], want.edges.numpy())
+    np.testing.assert_array_equal(got["weights"], want.weights.numpy())
+    s, e = got["states"], got["edges"]
+    assert_validity_parity(got["valid"], want.valid.numpy(), lambda b: pe.edge_min_clearance(robot, s[e[b, 0]], s[e[b, 1]]), "roadmap edges")
+
+
 def test_builder_with_engine_backend_equals_prm_build(ctx):
     sc = _scene("cage")
     env = synth.fill_env(ompl_b200.Environment(ctx), sc)
