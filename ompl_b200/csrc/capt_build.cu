@@ -17,7 +17,10 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <atomic>
+#include <cstdlib>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200mp.h"
@@ -50,26 +53,45 @@ inline float cell_distsq(const Cell &c, const float *p) {
     return d0 * d0 + d1 * d1 + d2 * d2;
 }
 
+// One contiguous run of leaves (a whole tree, or the subtree a worker thread builds): the same arrays as b200mp_capt, with
+// aff_starts relative to the run.
+struct LeafRun {
+    std::vector<float> aabbs, ax, ay, az;
+    std::vector<uint32_t> starts;  // per leaf: records (of 8 points) listed so far in this run, AFTER the leaf
+    float top[6] = {kInf, kInf, kInf, -kInf, -kInf, -kInf};
+};
+
+struct Task {
+    uint32_t begin, count, node;
+    std::vector<uint32_t> cand;
+    Cell cell;
+    int axis;
+};
+
 struct Builder {
     const std::vector<float> &pts;  // [n2][3]
-    std::vector<uint32_t> order;
-    b200mp_capt &out;
+    std::vector<uint32_t> &order;   // shared; every subtree sorts its own segment
+    std::vector<float> &tests;      // shared; every node is written once
     float slab, afford_sq, inner_sq;
+    LeafRun *out = nullptr;         // where leaves go (one run per worker task)
+    int task_depth = -1;            // >= 0: subtrees rooted at this depth are queued instead of built
+    std::vector<Task> *tasks = nullptr;
 
     const float *p(uint32_t id) const { return pts.data() + 3 * static_cast<size_t>(id); }
 
     void leaf(uint32_t at, const std::vector<uint32_t> &cand, const Cell &cell) {
+        LeafRun &o = *out;
         const float *rep = p(order[at]);
         float bb[6] = {rep[0], rep[1], rep[2], rep[0], rep[1], rep[2]};
         if (std::isfinite(rep[0])) {
             for (int k = 0; k < 3; ++k) {
-                out.top[k] = std::min(out.top[k], rep[k]);
-                out.top[3 + k] = std::max(out.top[3 + k], rep[k]);
+                o.top[k] = std::min(o.top[k], rep[k]);
+                o.top[3 + k] = std::max(o.top[3 + k], rep[k]);
             }
             size_t listed = 1;
-            out.ax.push_back(rep[0]);
-            out.ay.push_back(rep[1]);
-            out.az.push_back(rep[2]);
+            o.ax.push_back(rep[0]);
+            o.ay.push_back(rep[1]);
+            o.az.push_back(rep[2]);
             // a cell that lies inside the ball of radius r_min + r_point around its own point needs nothing else:
             // every admissible query centred in the cell already hits that point
             const float e0 = std::max(rep[0] - cell.lo[0], cell.hi[0] - rep[0]);
@@ -83,33 +105,37 @@ struct Builder {
                             bb[k] = std::min(bb[k], q[k]);
                             bb[3 + k] = std::max(bb[3 + k], q[k]);
                         }
-                        out.ax.push_back(q[0]);
-                        out.ay.push_back(q[1]);
-                        out.az.push_back(q[2]);
+                        o.ax.push_back(q[0]);
+                        o.ay.push_back(q[1]);
+                        o.az.push_back(q[2]);
                         ++listed;
                     }
                 }
             }
             for (; listed % 8; ++listed) {  // padding that can never satisfy distsq <= r^2
-                out.ax.push_back(kInf);
-                out.ay.push_back(kInf);
-                out.az.push_back(kInf);
+                o.ax.push_back(kInf);
+                o.ay.push_back(kInf);
+                o.az.push_back(kInf);
             }
         }
-        out.aabbs.insert(out.aabbs.end(), bb, bb + 6);
-        out.aff_starts.push_back(static_cast<uint32_t>(out.ax.size() / 8));
+        o.aabbs.insert(o.aabbs.end(), bb, bb + 6);
+        o.starts.push_back(static_cast<uint32_t>(o.ax.size() / 8));
     }
 
-    void split(uint32_t begin, uint32_t count, uint32_t node, std::vector<uint32_t> cand, const Cell &cell, int axis) {
+    void split(uint32_t begin, uint32_t count, uint32_t node, std::vector<uint32_t> cand, const Cell &cell, int axis, int depth) {
         if (count == 1) {
             leaf(begin, cand, cell);
+            return;
+        }
+        if (depth == task_depth) {  // hand the subtree to a worker (tasks stay in left-to-right order)
+            tasks->push_back(Task{begin, count, node, std::move(cand), cell, axis});
             return;
         }
         std::sort(order.begin() + begin, order.begin() + begin + count,
                   [this, axis](uint32_t a, uint32_t b) { return p(a)[axis] < p(b)[axis]; });
         const uint32_t half = count / 2, mid = begin + half, end = begin + count;
         const float plane = static_cast<float>((p(order[mid - 1])[axis] + p(order[mid])[axis]) / 2.0);
-        out.tests[node] = plane;
+        tests[node] = plane;
         Cell lo_cell = cell, hi_cell = cell;
         lo_cell.hi[axis] = plane;
         hi_cell.lo[axis] = plane;
@@ -136,8 +162,8 @@ struct Builder {
         }
         cand = std::vector<uint32_t>();  // release before descending
         const int next = (axis + 1) % 3;
-        split(begin, half, 2 * node + 1, std::move(lo_cand), lo_cell, next);
-        split(mid, half, 2 * node + 2, std::move(hi_cand), hi_cell, next);
+        split(begin, half, 2 * node + 1, std::move(lo_cand), lo_cell, next, depth + 1);
+        split(mid, half, 2 * node + 2, std::move(hi_cand), hi_cell, next, depth + 1);
     }
 };
 
@@ -165,14 +191,63 @@ int b200mp_capt_build(const float *xyz, int64_t n, float r_min, float r_max, flo
     t->aff_starts.reserve(n2 + 1);
     t->aff_starts.push_back(0);
     const float reach = r_max + r_point;
-    Builder b{pts, std::vector<uint32_t>(n2), *t, r_max, reach * reach, (r_min + r_point) * (r_min + r_point)};
-    std::iota(b.order.begin(), b.order.end(), 0u);
+    std::vector<uint32_t> order(n2);
+    std::iota(order.begin(), order.end(), 0u);
     Cell root;
     for (int k = 0; k < 3; ++k) {
         root.lo[k] = -kInf;
         root.hi[k] = kInf;
     }
-    b.split(0, static_cast<uint32_t>(n2), 0, {}, root, 0);
+    // The top kTaskDepth levels are split on this thread; the 2^kTaskDepth subtrees below are independent (disjoint segments of
+    // `order`, disjoint nodes of `tests`, own leaf runs) and are built by worker threads, then concatenated in order -- the
+    // arrays are those of the serial recursion.
+    constexpr int kTaskDepth = 5;
+    std::vector<Task> tasks;
+    LeafRun serial;
+    Builder top{pts, order, t->tests, r_max, reach * reach, (r_min + r_point) * (r_min + r_point)};
+    top.out = &serial;
+    if (t->nlog2 > kTaskDepth + 2 && !getenv("B200MP_CAPT_SERIAL")) {
+        top.task_depth = kTaskDepth;
+        top.tasks = &tasks;
+    }
+    top.split(0, static_cast<uint32_t>(n2), 0, {}, root, 0, 0);
+    std::vector<LeafRun> runs(tasks.size());
+    if (!tasks.empty()) {
+        const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= tasks.size()) return;
+                Builder b{pts, order, t->tests, r_max, reach * reach, (r_min + r_point) * (r_min + r_point)};
+                b.out = &runs[i];
+                Task &k = tasks[i];
+                b.split(k.begin, k.count, k.node, std::move(k.cand), k.cell, k.axis, kTaskDepth + 1);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned w = 1; w < hw; ++w) pool.emplace_back(work);
+        work();
+        for (auto &th : pool) th.join();
+    } else {
+        runs.push_back(std::move(serial));
+    }
+    size_t n_rec = 0, n_leaf = 0;
+    for (const auto &r : runs) { n_rec += r.ax.size(); n_leaf += r.starts.size(); }
+    t->ax.reserve(n_rec); t->ay.reserve(n_rec); t->az.reserve(n_rec);
+    t->aabbs.reserve(6 * n_leaf);
+    for (const auto &r : runs) {
+        const uint32_t base = static_cast<uint32_t>(t->ax.size() / 8);
+        t->ax.insert(t->ax.end(), r.ax.begin(), r.ax.end());
+        t->ay.insert(t->ay.end(), r.ay.begin(), r.ay.end());
+        t->az.insert(t->az.end(), r.az.begin(), r.az.end());
+        t->aabbs.insert(t->aabbs.end(), r.aabbs.begin(), r.aabbs.end());
+        for (const uint32_t sre : r.starts) t->aff_starts.push_back(base + sre);
+        for (int k = 0; k < 3; ++k) {
+            t->top[k] = std::min(t->top[k], r.top[k]);
+            t->top[3 + k] = std::max(t->top[3 + k], r.top[3 + k]);
+        }
+    }
     *out = t;
     return B200MP_OK;
 }
