@@ -272,6 +272,25 @@ def main():
         pe = synth.fill_env(port.PortEnvironment(), scene)
         valid_idx = np.nonzero(dv.cpu().numpy() == 1)[0]
         peak = ctx.fp32_peak_tflops(4096)
+        if roadmap is not None:
+            # kNN phase against both bounds SURVEY 8(d) names: FP32 issue on the exhaustive pair count (pruning makes this exceed
+            # the peak) and the algorithmic bytes B_min = N d_pad 4 + Nq d_pad 4 + Nq k 16 against the measured HBM copy bandwidth
+            n_r, k_r, d_pad = roadmap["n_states"], 16, 8
+            hbm = None
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    hbm = float(json.load(f)["hbm_gbs"])
+            except Exception:
+                pass
+            t_knn = roadmap["ms_knn"] * 1e-3
+            flops = 2.0 * d_pad * n_r * n_r
+            b_min = n_r * d_pad * 4.0 * 2 + n_r * k_r * 16.0
+            roadmap["knn_roofline"] = {"exhaustive_pair_tflops": flops / t_knn / 1e12, "fp32_peak_tflops": peak,
+                                       "frac_of_fp32_peak": flops / t_knn / 1e12 / peak, "b_min_bytes": b_min,
+                                       "b_min_gbs": b_min / t_knn / 1e9, "hbm_peak_gbs": hbm,
+                                       "frac_of_hbm": (b_min / t_knn / 1e9 / hbm) if hbm else None,
+                                       "note": "exact kNN with k-d pruning: ~15 % of the N^2 pairs are evaluated (B200MP_KNN_STAT_PAIRS=1), "
+                                               "the database (32 MiB) is L2 resident; the phase includes index build and query grouping"}
         samp = valid_idx[:512]
         _, fl = pe.validate_motions("panda", q0[samp], q1[samp], nthreads=os.cpu_count() or 1, want_flops=True)
         w_ref_edge = float(fl.mean())     # flops the reference's sequential semantics execute per valid motion (oracle walker)
