@@ -19,6 +19,9 @@
 #include "b200mp_ompl.hpp"
 #include <ompl/datastructures/NearestNeighborsLinear.h>
 
+#include <atomic>
+#include <thread>
+
 namespace ob = ompl::base;
 namespace b2 = ompl::b200;
 using RVState = ob::RealVectorStateSpace::StateType;
@@ -104,6 +107,84 @@ static void test_validators(const b2::EnginePtr &eng)
     bool threw = false;
     try { bad.isValid(&start.s); } catch (const ompl::Exception &) { threw = true; }
     EXPECT(threw);
+}
+
+// "must be thread safe" (StateValidityChecker.h:87-89, MotionValidator.h:60-63): four planner threads share one validator pair
+static void test_thread_safety(const b2::EnginePtr &eng)
+{
+    auto env = std::make_shared<b2::Environment>(eng);
+    for (int i = 0; i < 40; ++i)
+        env->addSphere({0.35F + 0.02F * static_cast<float>(i % 9), 0.1F * static_cast<float>(i % 7) - 0.3F, 0.1F + 0.03F * static_cast<float>(i)}, 0.06F);
+    env->sort();
+    env->commit();
+    ob::SpaceInformation *si = nullptr;
+    b2::B200StateValidityChecker<b2::Panda> svc(si, env);
+    b2::B200MotionValidator<b2::Panda> mv(si, env);
+    std::array<double, 7> lo, hi;
+    b2::getRobotBounds<b2::Panda>(lo, hi);
+    std::mt19937_64 rng(11);
+    std::vector<std::unique_ptr<OwnedState>> st;
+    for (int i = 0; i < 256; ++i)
+    {
+        std::vector<double> q(7);
+        for (int j = 0; j < 7; ++j) q[j] = std::uniform_real_distribution<double>(lo[j], hi[j])(rng);
+        st.emplace_back(new OwnedState(q));
+    }
+    std::vector<int> want_s(256), want_m(256);
+    for (int i = 0; i < 256; ++i)
+    {
+        want_s[i] = svc.isValid(&st[i]->s) ? 1 : 0;
+        want_m[i] = mv.checkMotion(&st[i]->s, &st[(i + 1) % 256]->s) ? 1 : 0;
+    }
+    std::atomic<int> bad{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < 4; ++t)
+        pool.emplace_back([&, t]() {
+            for (int rep = 0; rep < 3; ++rep)
+                for (int i = t; i < 256; i += 4)
+                {
+                    if ((svc.isValid(&st[i]->s) ? 1 : 0) != want_s[i]) ++bad;
+                    if ((mv.checkMotion(&st[i]->s, &st[(i + 1) % 256]->s) ? 1 : 0) != want_m[i]) ++bad;
+                }
+        });
+    for (auto &th : pool) th.join();
+    EXPECT(bad.load() == 0);
+}
+
+// the other robots, a height field, the point-cloud filter and both tree builds through the adapters
+static void test_more_shapes_and_robots(const b2::EnginePtr &eng)
+{
+    ob::SpaceInformation *si = nullptr;
+    // terrain 32 x 32 cells of 0.125 m, 0.5 m below the base: the straight-up UR5 is free, one folded down into it is not
+    std::vector<float> h(32 * 32, 0.1F);
+    auto env = std::make_shared<b2::Environment>(eng);
+    env->addHeightfield({0.F, 0.F, -0.5F}, {0.125F, 0.125F, 1.F}, 32, 32, h);
+    env->commit();
+    b2::B200StateValidityChecker<b2::UR5> ur5(si, env);
+    OwnedState up({0., -1.5708, 0., 0., 0., 0.}), down({0., 0.9, 0.9, 0., 0., 0.});
+    EXPECT(ur5.isValid(&up.s));
+    EXPECT(!ur5.isValid(&down.s));
+    b2::B200StateValidityChecker<b2::Baxter> baxter(si, env);
+    OwnedState zero14(std::vector<double>(14, 0.0));
+    (void)baxter.isValid(&zero14.s);  // 14 joints, two arms: must run (the decision is covered by the Python parity tests)
+
+    // cloud: a wall of points at x = 0.6; filter it, build the tree both ways, the Panda stretched into it collides either way
+    std::vector<float> wall;
+    for (int i = 0; i < 60; ++i)
+        for (int j = 0; j < 60; ++j) { wall.push_back(0.6F); wall.push_back(-0.3F + 0.01F * static_cast<float>(i)); wall.push_back(0.2F + 0.01F * static_cast<float>(j)); }
+    const auto kept = b2::filterPointcloud(eng, wall, 0.015F, 1.5F, {0.F, 0.F, 0.4F}, {-1.5F, -1.5F, -1.1F}, {1.5F, 1.5F, 1.9F}, true);
+    EXPECT(!kept.empty() && kept.size() < wall.size() && kept.size() % 3 == 0);
+    OwnedState home({0., -0.785, 0., -2.356, 0., 1.571, 0.785}), reach({0., 1.2, 0., -0.6, 0., 1.9, 0.785});
+    for (int device_build = 0; device_build < 2; ++device_build)
+    {
+        auto e2 = std::make_shared<b2::Environment>(eng);
+        if (device_build) e2->addPointcloudDevice(kept.data(), kept.size() / 3, 0.012F, 0.18F, 0.0025F);
+        else e2->addPointcloud(kept.data(), kept.size() / 3, 0.012F, 0.18F, 0.0025F);
+        e2->commit();
+        b2::B200StateValidityChecker<b2::Panda> panda(si, e2);
+        EXPECT(panda.isValid(&home.s));
+        EXPECT(!panda.isValid(&reach.s));
+    }
 }
 
 static void test_nearest_neighbors(const b2::EnginePtr &eng, std::size_t dim, int n, int k)
@@ -244,6 +325,8 @@ int main(int argc, char **argv)
     {
         auto eng = std::make_shared<b2::Engine>(0);
         test_validators(eng);
+        test_thread_safety(eng);
+        test_more_shapes_and_robots(eng);
         test_nearest_neighbors(eng, 7, 1000, 10);
         test_nearest_neighbors(eng, 3, 60, 30);
         test_nearest_neighbors(eng, 20, 300, 10);

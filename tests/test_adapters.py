@@ -24,7 +24,7 @@ def compile_adapter_test(flavour: str) -> str:
         return out
     inc = [f"-I{ROOT}/include", f"-I{ROOT}/tests/ompl_shim"]
     inc += [f"-I{REF_SRC}"] if flavour == "genuine" else [f"-I{ROOT}/tests/ompl_mock"]
-    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", *inc,
+    cmd = ["g++", "-std=c++17", "-O1", "-pthread", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", *inc,
            '-DB200MP_OMPL_STATE_HEADER="b200_mock_real_vector_state.h"', src, "-o", out,
            f"-L{ROOT}/ompl_b200", "-lb200mp", f"-Wl,-rpath,{ROOT}/ompl_b200", "-Wl,-rpath,$ORIGIN/../../../ompl_b200"]
     subprocess.run(cmd, check=True)
