@@ -1033,7 +1033,11 @@ int launch_tiled(b200mp_knn *k, const double *d_q, long long nq, const long long
                  Partial *d_partial, int splits, cudaStream_t st) {
     const size_t smem = 2 * kTile * NV * sizeof(float4) + static_cast<size_t>(kk) * kKnnThreads * (sizeof(double) + sizeof(int));
     auto kern = knn_tiled_kernel<NV>;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    static size_t opted = 0;  // largest dynamic size this kernel has been opted in for (one attribute call per growth, not per query)
+    if (smem > opted) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        opted = smem;
+    }
     dim3 grid(static_cast<unsigned>((nq + kKnnThreads - 1) / kKnnThreads), static_cast<unsigned>(splits));
     // |approx - exact| of an fp32 dot product of <= 4*NV terms plus the stored norm: (4*NV + 2) ulp-level terms, x4 margin
     const float err_scale = 4.0f * (4 * NV + 2) * 5.96e-8f;
@@ -1583,6 +1587,24 @@ int b200mp_knn_query(b200mp_knn *k, const double *q, int64_t nq, int kq, const i
     const size_t db = static_cast<size_t>(nq) * kq * sizeof(double);
     const size_t sb = self_ids ? static_cast<size_t>(nq) * sizeof(int64_t) : 0;
     const size_t cb = static_cast<size_t>(nq) * sizeof(int);
+    if (qb + ib + db + sb + cb + 64 <= k->ctx->small_cap && nq <= 64) {
+        // a planner's single nearest / nearestK: query written into the mapped pinned buffer, results read back from it --
+        // no copies to enqueue, the kernels address the host memory directly
+        char *h = static_cast<char *>(k->ctx->h_small), *d = static_cast<char *>(k->ctx->d_small);
+        size_t o_q = 0, o_i = qb, o_d = qb + ib, o_s = qb + ib + db, o_c = qb + ib + db + sb;
+        o_c = (o_c + 7) / 8 * 8;
+        std::memcpy(h + o_q, q, qb);
+        if (self_ids) std::memcpy(h + o_s, self_ids, sb);
+        int rc2 = b200mp_knn_query_device(k, reinterpret_cast<const double *>(d + o_q), nq, kq, self_ids ? reinterpret_cast<const int64_t *>(d + o_s) : nullptr, 0,
+                                          self_ids ? 1 : 0, reinterpret_cast<int64_t *>(d + o_i), reinterpret_cast<double *>(d + o_d),
+                                          reinterpret_cast<int *>(d + o_c), st);
+        if (rc2) return rc2;
+        B200_CUDA(cudaStreamSynchronize(st));
+        std::memcpy(idx, h + o_i, ib);
+        std::memcpy(dist, h + o_d, db);
+        if (counts) std::memcpy(counts, h + o_c, cb);
+        return B200MP_OK;
+    }
     int rc = k->ctx->scratch.reserve(qb + ib + db + sb + cb + 1024);
     if (rc) return rc;
     char *p = k->ctx->scratch.ptr;
