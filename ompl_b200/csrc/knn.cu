@@ -140,14 +140,15 @@ knn_tiled_kernel(const float4 *__restrict__ feat, const double *__restrict__ pts
             for (int u = 0; u < 4; ++u) {
                 // rows past cnt (same buffer, stale or unwritten) may be read: whatever they yield is dropped below by index
                 const float4 *row = tile + (c0 + u) * NV;
-                float acc = 0.f;
+                float acc = 0.f;  // s = |c|^2 - 2 q.c: the stored norm starts the sum
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
-                    const float4 c = row[v];
-                    acc = fmaf(m2q[4 * v + 0], c.x, acc);
-                    acc = fmaf(m2q[4 * v + 1], c.y, acc);
-                    acc = fmaf(m2q[4 * v + 2], c.z, acc);
-                    acc = fmaf(m2q[4 * v + 3], c.w, acc);
+                    const float4 c = row[NV - 1 - v];
+                    if (v == 0) acc = c.w;
+                    else acc = fmaf(m2q[4 * (NV - 1 - v) + 3], c.w, acc);
+                    acc = fmaf(m2q[4 * (NV - 1 - v) + 0], c.x, acc);
+                    acc = fmaf(m2q[4 * (NV - 1 - v) + 1], c.y, acc);
+                    acc = fmaf(m2q[4 * (NV - 1 - v) + 2], c.z, acc);
                 }
                 sv[u] = acc;
             }
@@ -714,17 +715,17 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
                 for (int u = 0; u < 4; ++u) {
                     // rows past cnt (same buffer, stale or unwritten) may be read: whatever they yield is dropped below by index
                     const float4 *row = tile + (c0 + u) * NV;
-#pragma unroll
-                    for (int t = 0; t < QPT; ++t) sv[t][u] = 0.f;
+                    // s = |c|^2 - 2 q.c: the stored norm (last float of the row) starts the sum, 4 NV - 1 FFMAs follow
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-                        const float4 c = row[v];
+                        const float4 c = row[NV - 1 - v];  // last float4 first: it carries |c|^2
 #pragma unroll
                         for (int t = 0; t < QPT; ++t) {
-                            sv[t][u] = fmaf(m2q[t][4 * v + 0], c.x, sv[t][u]);
-                            sv[t][u] = fmaf(m2q[t][4 * v + 1], c.y, sv[t][u]);
-                            sv[t][u] = fmaf(m2q[t][4 * v + 2], c.z, sv[t][u]);
-                            sv[t][u] = fmaf(m2q[t][4 * v + 3], c.w, sv[t][u]);
+                            if (v == 0) sv[t][u] = c.w;
+                            else sv[t][u] = fmaf(m2q[t][4 * (NV - 1 - v) + 3], c.w, sv[t][u]);
+                            sv[t][u] = fmaf(m2q[t][4 * (NV - 1 - v) + 0], c.x, sv[t][u]);
+                            sv[t][u] = fmaf(m2q[t][4 * (NV - 1 - v) + 1], c.y, sv[t][u]);
+                            sv[t][u] = fmaf(m2q[t][4 * (NV - 1 - v) + 2], c.z, sv[t][u]);
                         }
                     }
                 }
