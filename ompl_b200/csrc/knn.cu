@@ -531,6 +531,7 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
                  long long self_base, int use_self, int kk, float err_scale, float cmax, Partial *__restrict__ partial,
                  unsigned long long *__restrict__ rows_visited, int stat_pairs) {
     constexpr int kCellThreads = kCellQueries / QPT, kRoundCells = kCellThreads;
+    constexpr int kGroup = 8;  // candidate rows per filter group (the tile buffers have kGroup spare rows for the tail)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long bars[2];
     __shared__ int s_job_row[2], s_job_cnt[2], s_job_cell[2];
@@ -640,7 +641,7 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
         s_job_cell[slot] = gcell;
         const uint32_t bytes = static_cast<uint32_t>(cnt) * NV * sizeof(float4);
         mbar_expect_tx(&bars[slot], bytes);
-        bulk_g2s(tiles + static_cast<size_t>(slot) * kCellTile * NV, feat_s + static_cast<long long>(gb) * NV, bytes, &bars[slot]);
+        bulk_g2s(tiles + static_cast<size_t>(slot) * (kCellTile + 8) * NV, feat_s + static_cast<long long>(gb) * NV, bytes, &bars[slot]);
         gb += cnt;
     };
     // exact re-evaluation of a filter survivor (database row r) for query slot t, the reference's arithmetic
@@ -708,11 +709,11 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
                 if (lane == 0) atomicAdd(rows_visited, static_cast<unsigned long long>(cnt) * nqw);
             }
             mbar_wait(&bars[slot], (it >> 1) & 1);
-            const float4 *tile = tiles + static_cast<size_t>(slot) * kCellTile * NV;
-            for (int c0 = 0; c0 < (warp_skip ? 0 : cnt); c0 += 4) {
-                float sv[QPT][4];
+            const float4 *tile = tiles + static_cast<size_t>(slot) * (kCellTile + 8) * NV;
+            for (int c0 = 0; c0 < (warp_skip ? 0 : cnt); c0 += kGroup) {
+                float sv[QPT][kGroup];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kGroup; ++u) {
                     // rows past cnt (same buffer, stale or unwritten) may be read: whatever they yield is dropped below by index
                     const float4 *row = tile + (c0 + u) * NV;
                     // s = |c|^2 - 2 q.c: the stored norm (last float of the row) starts the sum, 4 NV - 1 FFMAs follow
@@ -731,10 +732,12 @@ knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
                 }
 #pragma unroll
                 for (int t = 0; t < QPT; ++t) {
-                    const bool any = (sv[t][0] < thr[t]) | (sv[t][1] < thr[t]) | (sv[t][2] < thr[t]) | (sv[t][3] < thr[t]);
+                    bool any = false;
+#pragma unroll
+                    for (int u = 0; u < kGroup; ++u) any |= sv[t][u] < thr[t];
                     if (any) {
 #pragma unroll 1
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < kGroup; ++u) {
                             if (!(sv[t][u] < thr[t]) || c0 + u >= cnt) continue;
                             survivor(t, static_cast<long long>(row0) + c0 + u);
                         }
@@ -1199,7 +1202,7 @@ int knn_build_index(b200mp_knn *k, cudaStream_t st) {
 template <int NV>
 int launch_cells(b200mp_knn *k, const double *d_q, const int *q_order, const int *q_start, const int *blk_start, long long nq,
                  const long long *d_self, long long self_base, int use_self, int kk, Partial *d_partial, cudaStream_t st, int n_parts) {
-    const size_t smem = 2 * kCellTile * NV * sizeof(float4);
+    const size_t smem = 2 * (kCellTile + 8) * NV * sizeof(float4);
     // few blocks for this GPU (a rank's share of a multi-GPU build, or a small batch): the 256-thread shape
     const long long slots = static_cast<long long>(k->ctx->sm_count) * 5;
     const bool wide = (nq / kCellQueries) / std::max(n_parts, 1) < 2 * slots;
