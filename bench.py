@@ -123,6 +123,49 @@ def run_reference(args):
     print(json.dumps(line), file=claim_stdout(), flush=True)
 
 
+def roadmap_parity(states, edges, valid, nbr, dst, scene, cores, knn_queries=4096, max_edges=0):
+    """North-star parity of a built roadmap against the compiled reference (oracle/_ref), on the host cores:
+    every edge through the unmodified vamp::planning::validate_motion<Panda, 8, 32> (validate.hh:69-77) and a spread sample of
+    queries through the unmodified NearestNeighborsLinear::nearestK (NearestNeighborsLinear.h:119-132). Differing edge decisions are
+    classified by the restatement's minimum clearance (the reference cannot report one): inside / outside the 1e-5 m band."""
+    from ompl_b200 import synth
+    from oracle import port, refnn, refvamp
+    out = {"checker": "oracle/_ref (unmodified reference), %d host threads" % cores}
+    e = edges if not max_edges else edges[:max_edges]
+    v = valid[:len(e)]
+    env = synth.fill_env(refvamp.RefEnvironment(), scene)
+    q0, q1 = np.ascontiguousarray(states[e[:, 0]]), np.ascontiguousarray(states[e[:, 1]])
+    t0 = time.perf_counter()
+    want = env.validate_motions("panda", q0, q1, nthreads=cores)
+    dt = time.perf_counter() - t0
+    bad = np.nonzero(want != v)[0]
+    in_band = 0
+    if bad.size:
+        pe = synth.fill_env(port.PortEnvironment(), scene)
+        clr = pe.edge_min_clearance("panda", q0[bad], q1[bad], nthreads=cores)
+        in_band = int((np.abs(clr) < 1e-5).sum())
+    out.update(edges_compared=int(len(e)), differ=int(bad.size), differ_in_1e5_band=in_band, differ_outside=int(bad.size - in_band),
+               reference_valid_edges=int(want.sum()), reference_edges_per_s=len(e) / dt)
+    del q0, q1
+    # kNN sample
+    n, k = nbr.shape
+    ids = np.unique(np.linspace(0, n - 1, min(knn_queries, n)).astype(np.int64))
+    db = states.astype(np.float64)
+    t0 = time.perf_counter()
+    ri, rd = refnn.nearest_k(db, db[ids], k, nthreads=cores, exclude_ids=ids)
+    dtk = time.perf_counter() - t0
+    gi, gd = nbr[ids], dst[ids]
+    same_order = (gi == ri).all(axis=1)
+    same_set = np.array([set(a) == set(b) for a, b in zip(gi, ri)])
+    rel = np.abs(gd - rd) / np.maximum(rd, 1e-300)
+    # a row whose id sets differ counts as tie-only when its sorted distances still agree to 1e-6 relative (equidistant alternatives)
+    tie_only = (~same_set) & (rel.max(axis=1) < 1e-6)
+    out.update(knn_queries=int(len(ids)), identical_sets=int(same_set.sum()), identical_order=int(same_order.sum()),
+               tie_only=int(tie_only.sum()), differ_sets_not_tie=int((~same_set & ~tie_only).sum()), max_rel_dist_err=float(rel.max()),
+               reference_knn_queries_per_s=len(ids) / dtk)
+    return out
+
+
 _JSON_OUT = None
 
 
@@ -146,6 +189,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--roadmap-n", type=int, default=1 << 20, help="samples of the PRM roadmap build (0 = skip)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the reference check of the built roadmap (all edges + kNN sample, ~1 min of CPU)")
+    ap.add_argument("--parity-edges", type=int, default=0, help="check only the first N roadmap edges against the reference (0 = all)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -230,7 +275,7 @@ def main():
     sampler.join(timeout=2)
 
     # ---- roadmap build (all ranks): BASELINE config 3, same scene
-    roadmap = None
+    roadmap, rm_host = None, None
     if args.roadmap_n > 0:
         from ompl_b200.roadmap import EngineBackend, RoadmapBuilder
         builder = RoadmapBuilder(EngineBackend(ctx, env, "panda"))
@@ -241,58 +286,41 @@ def main():
         rm = builder.build(args.roadmap_n, 16, 42)
         barrier()
         st = dict(rm.stats)
-        st["gpu_launches"] = int(ctx.launch_count - l0)
         keys = ["ms_sample", "ms_knn", "ms_edges", "ms_validate", "ms_gather", "ms_total"]
         t = torch.tensor([st[k] for k in keys], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         for k, v in zip(keys, t.tolist()):
-            st[k] = v
-        roadmap = {"workload": f"PRM roadmap: {args.roadmap_n} valid Panda samples, k=16 (self excluded), undirected de-duplicated edges, "
-                               "resolution 32, C2 scene; one identical warm-up build precedes the timed build", "n_gpus": world, "scaling": "strong",
-                   "build_ms": st["ms_total"], **st}
+            st[k] = round(v, 3)
+        roadmap = {"workload": f"{args.roadmap_n} valid Panda samples, k=16, C2 scene, 1 warm-up build", "n_gpus": world, "scaling": "strong",
+                   "build_ms": st["ms_total"], "gpu_launches": int(ctx.launch_count - l0)}
+        roadmap.update({k: st[k] for k in ("n_states", "n_candidates", "n_edges", "n_valid_edges", "ms_sample", "ms_knn", "ms_edges",
+                                           "ms_validate", "ms_gather")})
+        if rank == 0 and not args.no_parity:
+            rm_host = tuple(x.cpu().numpy() for x in (rm.states, rm.edges, rm.valid, rm.neighbors, rm.neighbor_dist))
         del rm
 
+    if world > 1:
+        dist.destroy_process_group()  # nothing below is collective: rank 0 alone finishes the report
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "dtype": "f32", "data": "synthetic", "gpu_launches": int(launches), "valid_fraction": valid_frac,
+            "states_per_sec_upper": value * 64, "roadmap_build_ms": roadmap["build_ms"] if roadmap else None,
+            "config": workload_config(world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(q0.nbytes + q1.nbytes), "d2h_bytes_per_step": int(M_EDGES)},
-            "gpu_launches": int(launches), "clocks": sampler.summary(), "valid_fraction": valid_frac,
-            "states_per_sec_upper": value * 64}
-    if roadmap is not None:
-        line["roadmap"] = roadmap
+            "clocks": sampler.summary()}
+    cores = os.cpu_count() or 1
     if world == 1:
         # ---- roofline of the validation kernel on the all-valid sub-workload (no early exit hides work) + CPU baseline
         from oracle import port
         pe = synth.fill_env(port.PortEnvironment(), scene)
         valid_idx = np.nonzero(dv.cpu().numpy() == 1)[0]
         peak = ctx.fp32_peak_tflops(4096)
-        if roadmap is not None:
-            # kNN phase against both bounds SURVEY 8(d) names: FP32 issue on the exhaustive pair count (pruning makes this exceed
-            # the peak) and the algorithmic bytes B_min = N d_pad 4 + Nq d_pad 4 + Nq k 16 against the measured HBM copy bandwidth
-            n_r, k_r, d_pad = roadmap["n_states"], 16, 8
-            hbm = None
-            try:
-                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                    hbm = float(json.load(f)["hbm_gbs"])
-            except Exception:
-                pass
-            t_knn = roadmap["ms_knn"] * 1e-3
-            flops = 2.0 * d_pad * n_r * n_r
-            b_min = n_r * d_pad * 4.0 * 2 + n_r * k_r * 16.0
-            roadmap["knn_roofline"] = {"exhaustive_pair_tflops": flops / t_knn / 1e12, "fp32_peak_tflops": peak,
-                                       "frac_of_fp32_peak": flops / t_knn / 1e12 / peak, "b_min_bytes": b_min,
-                                       "b_min_gbs": b_min / t_knn / 1e9, "hbm_peak_gbs": hbm,
-                                       "frac_of_hbm": (b_min / t_knn / 1e9 / hbm) if hbm else None,
-                                       "note": "exact kNN with k-d pruning: ~15 % of the N^2 pairs are evaluated (B200MP_KNN_STAT_PAIRS=1), "
-                                               "the database (32 MiB) is L2 resident; the phase includes index build and query grouping"}
         samp = valid_idx[:512]
-        _, fl = pe.validate_motions("panda", q0[samp], q1[samp], nthreads=os.cpu_count() or 1, want_flops=True)
+        _, fl = pe.validate_motions("panda", q0[samp], q1[samp], nthreads=cores, want_flops=True)
         w_ref_edge = float(fl.mean())     # flops the reference's sequential semantics execute per valid motion (oracle walker)
         rep = np.resize(valid_idx, 1 << 17)
         a0, a1 = torch.from_numpy(q0[rep]).to(dev), torch.from_numpy(q1[rep]).to(dev)
@@ -304,30 +332,18 @@ def main():
         assert bool(av.all()), "all-valid sub-workload must validate as valid"
         w_ref = w_ref_edge * len(rep) / (ms_av * 1e-3) / 1e12
         # executed flops per launch of exactly this workload, counted by ncu (profiles/validate_flops.json)
-        w_exec_launch, src, traffic = None, None, None
-        try:
-            with open(os.path.join(ROOT, "profiles", "validate_flops.json")) as f:
-                pj = json.load(f)
-            if pj.get("motions") == len(rep) and pj.get("unique_valid") == int(len(valid_idx)):
-                w_exec_launch, src = float(pj["flops_per_launch"]), pj.get("source")
-                traffic = pj.get("dram_bytes")  # dram__bytes_read.sum + dram__bytes_write.sum of the same launch (ncu)
-        except Exception:
-            pass
+        w_exec_launch, src, traffic = flops_record(len(rep), int(len(valid_idx)))
         achieved = (w_exec_launch / (ms_av * 1e-3) / 1e12) if w_exec_launch else w_ref
         line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                             "kernel": "validate_motions_kernel<Panda, sorted, grid>",
-                            "achieved_is": ("executed FP32 flops (ncu-counted FFMA x2 + FADD + FMUL per launch of this workload: " + str(src) + ")")
-                            if w_exec_launch else "W_ref (no ncu flop count for this workload found)",
-                            "w_ref_tflops": w_ref, "w_ref_frac": w_ref / peak, "w_ref_flops_per_edge": w_ref_edge,
-                            "note": "W_ref = flops the reference's sequential scan semantics execute for the same motions (oracle-counted); the "
-                                    "grid-culled kernel reaches the same decisions with far fewer tests, so W_ref/time may exceed the FP32 peak",
-                            "workload": f"all-valid sub-workload: {len(valid_idx)} valid motions of the batch tiled to 2^17",
+                            "achieved_is": ("executed FP32 flops/launch (ncu FFMA x2 + FADD + FMUL, " + str(src) + ")")
+                            if w_exec_launch else "W_ref (no ncu flop count matching this build found)",
+                            "w_ref_tflops": w_ref, "w_ref_flops_per_edge": w_ref_edge,
+                            "workload": f"all-valid: {len(valid_idx)} valid motions of the batch tiled to 2^17",
                             "ms_per_launch": ms_av, "states_per_sec": len(rep) * 64 / (ms_av * 1e-3),
-                            "peak_source": "measured: b200mp_fp32_peak FFMA microbenchmark on this GPU (MEASURED_PEAKS.json has no FP32 "
-                                           "entry; nominal 148*128*2*1.965 GHz = 74.4)"}
+                            "peak_source": "b200mp_fp32_peak FFMA microbenchmark on this GPU (nominal 148*128*2*1.965 GHz = 74.4)"}
         if not args.no_cpu_baseline:
             chk, kind = checker_env(scene)
-            cores = os.cpu_count() or 1
             sample = 1 << 18
             chk.validate_motions("panda", q0[:8192], q1[:8192], nthreads=cores)
             t0 = time.perf_counter()
@@ -335,20 +351,48 @@ def main():
             dt = time.perf_counter() - t0
             got = dv.cpu().numpy()[:sample]
             mism = int((got != want).sum())
+            # the same reference on the all-valid sub-workload the roofline is quoted on (no early exit on either arm)
+            nv = min(len(valid_idx), 4096)
+            t0 = time.perf_counter()
+            wv = chk.validate_motions("panda", q0[valid_idx[:nv]], q1[valid_idx[:nv]], nthreads=cores)
+            dtv = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": kind,
-                                    "sample": f"first 2^18 of the 2^20 motions, all host threads; {mism} decisions differ from the GPU"}
-            if roadmap is not None:
-                # CPU figure for the roadmap's kNN phase: the reference-faithful exhaustive search on a bounded query sample
-                nq = 512
-                states = synth.uniform_states("panda", 1 << 18, 5).astype(np.float64)
-                t0 = time.perf_counter()
-                port.knn(states, states[:nq], 16, nthreads=cores)
-                dt = time.perf_counter() - t0
-                line["roadmap"]["cpu_knn"] = {"queries_per_s_at_2^18": nq / dt, "cores": cores, "kind": "port",
-                                              "sample": f"{nq} queries against 2^18 states (cost is linear in the database size)"}
+                                    "sample": f"first 2^18 of the 2^20 motions, all host threads; {mism} decisions differ from the GPU",
+                                    "all_valid_edges_per_s": nv / dtv, "all_valid_sample": f"{nv} valid motions, {int((wv != 1).sum())} differ"}
+    if roadmap is not None:
+        if rm_host is not None:
+            from oracle import refvamp, refnn
+            if refvamp.available() and refnn.available():
+                roadmap["parity"] = roadmap_parity(*rm_host, scene, cores, max_edges=args.parity_edges)
+                line["roadmap_parity_differ_outside"] = roadmap["parity"]["differ_outside"]
+            else:
+                roadmap["parity"] = {"skipped": "oracle/_ref not built"}
+        line["roadmap"] = roadmap  # last: the driver keeps the tail of the line
     print(json.dumps(line), file=claim_stdout(), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def flops_record(motions, unique_valid):
+    """(flops per launch, source, dram bytes) of the all-valid launch from profiles/validate_flops.json -- only if that ncu count was
+    taken on the kernel code of THIS build (sha256 of the validation kernel sources recorded next to it), else (None, None, None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "validate_flops.json")) as f:
+            pj = json.load(f)
+        if pj.get("motions") == motions and pj.get("unique_valid") == unique_valid and pj.get("kernel_sha256") == kernel_hash():
+            return float(pj["flops_per_launch"]), pj.get("source"), pj.get("dram_bytes")
+    except Exception:
+        pass
+    return None, None, None
+
+
+def kernel_hash():
+    """sha256 over the sources the validation kernels are compiled from (a changed kernel invalidates recorded ncu counts)."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "ompl_b200", "csrc")
+    for rel in ("validate.cuh", "robot_common.cuh", "robots/panda_gen.cuh"):
+        with open(os.path.join(csrc, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
 if __name__ == "__main__":

@@ -7,6 +7,8 @@
 #include <mutex>
 #include <string>
 #include <map>
+#include <memory>
+#include <tuple>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -235,7 +237,9 @@ int b200mp_create(int device, b200mp_ctx **out) {
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     }
     if (device < 0 || device >= n) return fail(B200MP_ERR_INVALID, "b200mp_create: device %d out of range [0,%d)", device, n);
-    auto *c = new b200mp_ctx();
+    struct Destroy { void operator()(b200mp_ctx *p) const { b200mp_destroy(p); } };
+    std::unique_ptr<b200mp_ctx, Destroy> guard(new b200mp_ctx());  // a failing step below releases what was created so far
+    b200mp_ctx *c = guard.get();
     c->device = device;
     B200_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop{};
@@ -244,29 +248,29 @@ int b200mp_create(int device, b200mp_ctx **out) {
     c->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
     c->cc_major = prop.major;
     if (prop.major < 10) {
-        delete c;
         return fail(B200MP_ERR_NO_DEVICE, "b200mp_create: device %d is sm_%d%d; kernels are built for sm_100a only", device,
                     prop.major, prop.minor);
     }
     B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    B200_CUDA(cudaMalloc(&c->d_counters, sizeof(LaunchCounters)));
+    B200_CUDA(cudaMalloc(&c->d_counters, sizeof(LaunchCounters) * kCounterRing * kCounterStride));
     c->small_cap = size_t(256) << 10;
     B200_CUDA(cudaHostAlloc(&c->h_small, c->small_cap, cudaHostAllocMapped));
     B200_CUDA(cudaHostGetDevicePointer(&c->d_small, c->h_small, 0));
-    *out = c;
+    *out = guard.release();
     return B200MP_OK;
 }
 
 void b200mp_destroy(b200mp_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     c->scratch.release();
-    cudaFree(c->d_counters);
+    if (c->d_counters) cudaFree(c->d_counters);
     if (c->h_small) cudaFreeHost(c->h_small);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
-    cudaStreamDestroy(c->stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
     delete c;
 }
 
@@ -668,21 +672,27 @@ int b200mp_env_commit(b200mp_env *e) {
 namespace {
 
 // resident blocks per SM of a kernel at a given dynamic shared-memory size; the opt-in attribute and the occupancy query
-// are made once per (kernel, size) and remembered (they cost more than a small launch)
-int blocks_per_sm(const void *kern, int threads, size_t smem, int *per_sm) {
+// are made once per (device, kernel, size) and remembered (they cost more than a small launch). Both are per-device state.
+int blocks_per_sm(int device, const void *kern, int threads, size_t smem, int *per_sm) {
     static std::mutex mu;
-    static std::map<std::pair<const void *, size_t>, int> cache;
-    static std::map<const void *, size_t> opted;  // largest dynamic size each kernel has been opted in for (only ever raised)
+    static std::map<std::tuple<int, const void *, size_t>, int> cache;
+    static std::map<std::pair<int, const void *>, size_t> opted;  // largest dynamic size each kernel has been opted in for (only ever raised)
     std::lock_guard<std::mutex> lk(mu);
-    auto it = cache.find({kern, smem});
+    auto it = cache.find({device, kern, smem});
     if (it != cache.end()) { *per_sm = it->second; return B200MP_OK; }
-    if (smem > opted[kern]) {
+    if (smem > opted[{device, kern}]) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        opted[kern] = smem;
+        opted[{device, kern}] = smem;
     }
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, threads, smem));
-    cache[{kern, smem}] = *per_sm;
+    cache[{device, kern, smem}] = *per_sm;
     return B200MP_OK;
+}
+
+// Every launch gets its own work-queue head from a ring in the context, zeroed on the launch stream just before the kernel, so
+// launches in flight on different streams (the _device entry points take any caller stream) never share or reset each other's queue.
+LaunchCounters *next_counter(b200mp_ctx *c) {
+    return static_cast<LaunchCounters *>(c->d_counters) + (c->counter_next.fetch_add(1) % kCounterRing) * kCounterStride;  // own 128-byte line
 }
 
 template <class R>
@@ -693,14 +703,14 @@ int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const 
     auto kern = e->desc.n_grid > 0 ? validate_motions_kernel<R, false, true>
                                    : (e->desc.sorted ? validate_motions_kernel<R, false, false> : validate_motions_kernel<R, true, false>);
     int per_sm = 0;
-    if ((rc_occ = blocks_per_sm(reinterpret_cast<const void *>(kern), motion_threads<R>(), smem, &per_sm))) return rc_occ;
+    if ((rc_occ = blocks_per_sm(c->device, reinterpret_cast<const void *>(kern), motion_threads<R>(), smem, &per_sm))) return rc_occ;
     if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_motions: kernel does not fit on an SM with %zu B of scene", smem);
     const long long warps_needed = m;
     long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + (motion_threads<R>() / 32) - 1) / (motion_threads<R>() / 32));
     blocks = std::max<long long>(blocks, 1);
-    B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), motion_threads<R>(), smem, st>>>(e->desc, d_q0, d_q1, d_pairs, m, resolution, d_valid,
-                                                                     static_cast<LaunchCounters *>(c->d_counters));
+    LaunchCounters *cnt = next_counter(c);
+    B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(LaunchCounters), st));
+    kern<<<static_cast<unsigned>(blocks), motion_threads<R>(), smem, st>>>(e->desc, d_q0, d_q1, d_pairs, m, resolution, d_valid, cnt);
     B200_CUDA(cudaGetLastError());
     c->launches.fetch_add(1);
     return B200MP_OK;
@@ -713,13 +723,14 @@ int launch_states(b200mp_ctx *c, const b200mp_env *e, const float *d_q, int64_t 
     auto kern = e->desc.n_grid > 0 ? validate_states_kernel<R, false, true>
                                    : (e->desc.sorted ? validate_states_kernel<R, false, false> : validate_states_kernel<R, true, false>);
     int per_sm = 0;
-    if ((rc_occ = blocks_per_sm(reinterpret_cast<const void *>(kern), kStateThreads, smem, &per_sm))) return rc_occ;
+    if ((rc_occ = blocks_per_sm(c->device, reinterpret_cast<const void *>(kern), kStateThreads, smem, &per_sm))) return rc_occ;
     if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_states: kernel does not fit on an SM with %zu B of scene", smem);
     const long long warps_needed = (m + 31) / 32;
     long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + (kStateThreads / 32) - 1) / (kStateThreads / 32));
     blocks = std::max<long long>(blocks, 1);
-    B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), kStateThreads, smem, st>>>(e->desc, d_q, m, d_valid, static_cast<LaunchCounters *>(c->d_counters));
+    LaunchCounters *cnt = next_counter(c);
+    B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(LaunchCounters), st));
+    kern<<<static_cast<unsigned>(blocks), kStateThreads, smem, st>>>(e->desc, d_q, m, d_valid, cnt);
     B200_CUDA(cudaGetLastError());
     c->launches.fetch_add(1);
     return B200MP_OK;

@@ -12,6 +12,8 @@
 
 namespace b200mp {
 
+constexpr unsigned kCounterRing = 256, kCounterStride = 16;
+
 int fail(int code, const char *fmt, ...);
 
 #define B200_CUDA(expr)                                                                                         \
@@ -52,7 +54,8 @@ struct b200mp_ctx {
     int max_smem_optin = 0;
     int cc_major = 0;
     cudaStream_t stream = nullptr;
-    void *d_counters = nullptr;
+    void *d_counters = nullptr;                // ring of kCounterRing work-queue heads, one per launch in flight
+    std::atomic<unsigned> counter_next{0};
     // small-call path (one checkMotion / isValid at a time, the way OMPL planners call): a mapped pinned buffer the kernels
     // read and write directly, so a call is one memset + one launch + one synchronise
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy streams of the chunked host entry points (created on first use)

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -1037,10 +1038,15 @@ int launch_tiled(b200mp_knn *k, const double *d_q, long long nq, const long long
                  Partial *d_partial, int splits, cudaStream_t st) {
     const size_t smem = 2 * kTile * NV * sizeof(float4) + static_cast<size_t>(kk) * kKnnThreads * (sizeof(double) + sizeof(int));
     auto kern = knn_tiled_kernel<NV>;
-    static size_t opted = 0;  // largest dynamic size this kernel has been opted in for (one attribute call per growth, not per query)
-    if (smem > opted) {
-        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        opted = smem;
+    // largest dynamic size this kernel has been opted in for ON THIS DEVICE (one attribute call per growth, not per query)
+    static std::mutex opt_mu;
+    static std::map<int, size_t> opted;
+    {
+        std::lock_guard<std::mutex> lk(opt_mu);
+        if (smem > opted[k->ctx->device]) {
+            B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            opted[k->ctx->device] = smem;
+        }
     }
     dim3 grid(static_cast<unsigned>((nq + kKnnThreads - 1) / kKnnThreads), static_cast<unsigned>(splits));
     // |approx - exact| of an fp32 dot product of <= 4*NV terms plus the stored norm: (4*NV + 2) ulp-level terms, x4 margin
@@ -1416,9 +1422,9 @@ int64_t b200mp_knn_size(const b200mp_knn *k) { return k ? k->n - k->n_removed : 
 
 int b200mp_knn_add(b200mp_knn *k, const double *pts, int64_t n, int64_t *first_id) {
     if (!k || (n > 0 && !pts) || n < 0) return fail(B200MP_ERR_INVALID, "b200mp_knn_add: bad argument");
+    std::lock_guard<std::mutex> lk(k->ctx->mu);
     if (first_id) *first_id = k->n;
     if (n == 0) return B200MP_OK;
-    std::lock_guard<std::mutex> lk(k->ctx->mu);
     B200_CUDA(cudaSetDevice(k->ctx->device));
     int rc = knn_reserve(k, k->n + n);
     if (rc) return rc;
@@ -1426,7 +1432,7 @@ int b200mp_knn_add(b200mp_knn *k, const double *pts, int64_t n, int64_t *first_i
                               k->ctx->stream));
     if ((rc = knn_build_features(k, k->n, n, k->ctx->stream))) return rc;
     k->h_pts.insert(k->h_pts.end(), pts, pts + n * k->dim);
-    k->alive.insert(k->alive.end(), static_cast<size_t>(n), 1);
+    k->alive.resize(static_cast<size_t>(k->n + n), 1);
     for (int64_t i = 0; i < n; ++i) {
         double s = 0;
         for (int j = 0; j < k->dim; ++j) s += pts[i * k->dim + j] * pts[i * k->dim + j];
@@ -1451,14 +1457,14 @@ int b200mp_knn_add_device_f32(b200mp_knn *k, const float *d_pts, int64_t n, floa
     if ((rc = knn_build_features(k, k->n, n, st))) return rc;
     k->cmax = std::max(k->cmax, max_norm * 1.0001f);
     k->h_pts.clear();  // host mirror not maintained for device-resident databases
-    k->alive.clear();
     k->n += n;
+    k->alive.resize(static_cast<size_t>(k->n), 1);  // liveness stays indexed by global id
     return B200MP_OK;
 }
 
 int b200mp_knn_remove(b200mp_knn *k, int64_t id) {
     if (!k) return fail(B200MP_ERR_INVALID, "b200mp_knn_remove: NULL");
-    if (id < 0 || id >= k->n || k->alive.empty() || !k->alive[id]) return fail(B200MP_ERR_INVALID, "b200mp_knn_remove: id %lld not present", (long long)id);
+    if (id < 0 || id >= k->n || static_cast<size_t>(id) >= k->alive.size() || !k->alive[id]) return fail(B200MP_ERR_INVALID, "b200mp_knn_remove: id %lld not present", (long long)id);
     std::lock_guard<std::mutex> lk(k->ctx->mu);
     B200_CUDA(cudaSetDevice(k->ctx->device));
     if (k->metric == B200MP_METRIC_CHAIN) {

@@ -38,6 +38,8 @@ class Roadmap:
     valid: torch.Tensor     # [E] uint8
     weights: torch.Tensor   # [E] float64 = edge length (PRM's motionCost for path-length objectives)
     stats: dict = field(default_factory=dict)
+    neighbors: torch.Tensor | None = None       # [n][k] int64: the kNN table the edges were derived from (-1 = none)
+    neighbor_dist: torch.Tensor | None = None   # [n][k] float64, ascending
 
     def to_planner_data(self):
         """Vertices and valid edges in the form ompl::base::PlannerData takes (addVertex / addEdge with weight), ready for
@@ -199,4 +201,4 @@ class RoadmapBuilder:
         stats = dict(n_states=n, n_candidates=drawn, n_edges=int(edges.shape[0]), n_valid_edges=int(valid.sum().item()), world=G,
                      sample_rounds=rounds, ms_sample=ms[0], ms_knn=ms[1], ms_edges=ms[2], ms_validate=ms[3], ms_gather=ms[4],
                      ms_total=sum(ms), local_edges=int(e_loc.shape[0]))
-        return Roadmap(states, edges, valid, weights, stats)
+        return Roadmap(states, edges, valid, weights, stats, nbr, dst)

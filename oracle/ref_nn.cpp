@@ -2,8 +2,10 @@
 // (/root/reference/src/ompl/datastructures/NearestNeighborsLinear.h) behind a C wrapper, driven exactly as
 // OMPL's planners drive it: _T = unsigned long vertex id, distance through a std::function that looks the
 // states up on the side (PRM.h:345-348) and evaluates RealVectorStateSpace::distance semantics.
+#include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <thread>
 #include <vector>
 
 #include <ompl/datastructures/NearestNeighborsLinear.h>
@@ -61,6 +63,35 @@ extern "C"
             dist[t] = h->nn.getDistanceFunction()(nbh[t], static_cast<unsigned long>(h->n));
         }
         return static_cast<std::int64_t>(nbh.size());
+    }
+
+    // nq independent nearestK queries on `nthreads` host threads; every thread drives its OWN container instance (the reference
+    // container is not thread safe and the query lives in a side slot). idx / dist are [nq][k], padded with -1 / +inf.
+    void refnn_nearest_k_batch(const double *db, std::int64_t n, int dim, const double *q, std::int64_t nq, int k, std::int64_t *idx,
+                               double *dist, int nthreads)
+    {
+        std::atomic<std::int64_t> next{0};
+        auto work = [&]()
+        {
+            void *h = refnn_create(db, n, dim);
+            for (;;)
+            {
+                const std::int64_t i = next.fetch_add(1);
+                if (i >= nq)
+                    break;
+                const std::int64_t c = refnn_nearest_k(h, q + i * dim, k, idx + i * k, dist + i * k);
+                for (std::int64_t t = c; t < k; ++t)
+                {
+                    idx[i * k + t] = -1;
+                    dist[i * k + t] = INFINITY;
+                }
+            }
+            refnn_destroy(h);
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
     }
 
     std::int64_t refnn_nearest_r(void *p, const double *q, double radius, std::int64_t *idx, double *dist, std::int64_t cap)

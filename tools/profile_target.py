@@ -40,4 +40,5 @@ assert va.all()
 if "--no-roadmap" not in sys.argv:
     r = ctx.prm_build("panda", env, 1 << 18, 16, 42, want_weights=False)
     print(json.dumps(r["stats"]))
-print(json.dumps({"motions": int(len(rep)), "unique_valid": int(len(valid_idx)), "mixed_valid_fraction": float(v.mean())}))
+print(json.dumps({"motions": int(len(rep)), "unique_valid": int(len(valid_idx)), "mixed_valid_fraction": float(v.mean()),
+                  "kernel_sha256": bench.kernel_hash()}))
