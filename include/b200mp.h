@@ -160,13 +160,18 @@ int b200mp_knn_create(b200mp_ctx *ctx, int dim, int metric, b200mp_knn **out);
 int b200mp_knn_create_chain(b200mp_ctx *ctx, int n_links, double link_length, b200mp_knn **out);
 void b200mp_knn_destroy(b200mp_knn *knn);
 int b200mp_knn_clear(b200mp_knn *knn);
-/* Batches of >= 4096 queries against >= 32768 points are answered through a cell index (Voronoi cells of strided pivots
- * with bounding boxes, queries sorted by cell, exact pruning by box distance; same results as the exhaustive kernel).
+/* Batches of >= 4096 queries against >= 32768 points are answered through a cell index: a balanced k-d partition of the
+ * database built on the device (leaves of ~64 rows stored contiguously, with tight bounding boxes for the leaves and for
+ * their 16- and 256-leaf subtrees), queries grouped by leaf, and an exact search that visits only the leaves within a
+ * query's current k-th distance (lower bounds only, so the results are those of the exhaustive kernel).
  * enable = 0 forces the exhaustive tiled kernel (A/B measurements, tests). Default: enabled. */
 int b200mp_knn_set_index(b200mp_knn *knn, int enable);
-/* Pruning statistics: candidate rows streamed per query block by the cell-index kernel, summed since creation
- * (x block size = pair evaluations; the exhaustive kernel evaluates size x queries). */
+/* Pruning statistics of the cell-index search, summed since creation and collected only while the environment variable
+ * B200MP_KNN_STAT_PAIRS is set: b200mp_knn_rows_visited = (query, candidate row) pairs evaluated (the exhaustive kernel
+ * evaluates size x queries); b200mp_knn_search_stats fills out[4] = pairs evaluated, exact fp64 re-evaluations, list
+ * insertions, (query batch, leaf) visits. */
 int64_t b200mp_knn_rows_visited(b200mp_knn *knn);
+int b200mp_knn_search_stats(b200mp_knn *knn, int64_t *out);
 int64_t b200mp_knn_size(const b200mp_knn *knn);
 /* pts[n][dim] host doubles; *first_id (may be NULL) receives the id of pts[0]. */
 int b200mp_knn_add(b200mp_knn *knn, const double *pts, int64_t n, int64_t *first_id);
@@ -185,7 +190,8 @@ int b200mp_knn_query_device(b200mp_knn *knn, const double *d_q, int64_t nq, int 
 int b200mp_knn_query_device_f32(b200mp_knn *knn, const float *d_q, int64_t nq, int k, int64_t self_base, int exclude_self,
                                 int64_t *d_idx, double *d_dist, int *d_counts, void *stream);
 /* Multi-GPU query sharing: computes the rows of part `part` of `n_parts` disjoint subsets that together cover the nq
- * queries (whole index cells per part when the cell index is used, contiguous blocks otherwise) and leaves all other
+ * queries (whole index leaves per part, contiguous in k-d order and balanced by query count, when the cell index is used;
+ * contiguous blocks otherwise) and leaves all other
  * rows of d_idx / d_dist untouched, so that tables pre-filled with -1 / +inf combine across ranks with an element-wise
  * max / min reduction. Every rank must hold the same database. */
 int b200mp_knn_query_part_device_f32(b200mp_knn *knn, const float *d_q, int64_t nq, int k, int64_t self_base, int exclude_self, int part,

@@ -205,12 +205,12 @@ knn_tiled_kernel(const float4 *__restrict__ feat, const double *__restrict__ pts
 // finds the smallest entry strictly greater than the last one emitted (entries are unique by idx) with a lane-local
 // scan followed by a warp-shuffle arg-min, so nothing has to be retired or sorted in memory. dist = sqrt(d2).
 __global__ void knn_merge_kernel(const Partial *__restrict__ partial, long long nq, int n_cand, int k, long long *__restrict__ idx,
-                                 double *__restrict__ dist, int *__restrict__ counts, int take_sqrt, const int *__restrict__ qcell = nullptr,
+                                 double *__restrict__ dist, int *__restrict__ counts, int take_sqrt, const int *__restrict__ qpart = nullptr,
                                  int parts = 1, int part = 0) {
     const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= nq) return;
-    if (qcell != nullptr && qcell[w] % parts != part) return;  // row belongs to another part: left untouched
+    if (qpart != nullptr && qpart[w] != part) return;  // row belongs to another part: left untouched
     const Partial *p = partial + w * n_cand;
     constexpr int kPer = 8;  // first 256 candidates live in registers; any further ones are re-read each round
     double d[kPer];
@@ -292,20 +292,10 @@ __global__ void knn_all_distances_kernel(const double *__restrict__ pts, const f
 
 
 // ================================================================================================ cell index
-// Exact search with spatial pruning for large batches (roadmap construction: every state queries the whole set).
-// The database is partitioned into P cells (the Voronoi regions of P database points taken at a regular stride), stored
-// cell by cell, each with an axis-aligned bounding box. Queries are sorted by their own cell so a block's 256 queries are
-// neighbours in space; the block first searches the cells its queries live in, which gives every query a finite k-th
-// distance, and then visits only the cells whose box lies within the block's current worst k-th distance of the
-// block's query box, streaming each visited cell through shared memory exactly like the brute-force kernel (fp32 filter
-// with a rigorous error bound, fp64 re-evaluation of survivors in the reference's operation order). Pruning uses lower
-// bounds only, so the result is the same exact (distance, id)-ordered top-k as the exhaustive scan.
-constexpr int kCellTile = 512;
-constexpr int kCellQueries = 256;  // queries per block of the cell kernel
-// The kernel is built for two shapes: 128 threads x 2 queries (each candidate read feeds 8 FFMAs: best when the GPU is full of
-// blocks) and 256 threads x 1 query (twice the warps per block, half the work per warp and tile: a block finishes sooner, which is
-// what counts when a rank of a multi-GPU build has fewer blocks than the GPU has block slots).
-
+// Exact search with spatial pruning for large batches (roadmap construction: every state queries the whole set): a balanced k-d
+// partition of the database built on the device, rows stored leaf by leaf, tight boxes per leaf; the search itself is the
+// query-major kernel further down. Pruning uses lower bounds only, so the result is the same exact (distance, id)-ordered top-k
+// as the exhaustive scan.
 // ---- partition: a balanced k-d tree of depth L = log2(P) built level by level on the device. Every level splits all of its
 // nodes along one dimension (the one whose current cell extent is largest) at the approximate median of the node's rows:
 // a 256-bin histogram over the node's extent along that dimension, split at the upper edge of the bin where the count
@@ -479,12 +469,6 @@ __global__ void knn_permute_kernel(const float4 *__restrict__ feat, const double
     orig[p] = static_cast<int>(i);
 }
 
-// blocks needed per query cell: ceil(#queries in the cell / kCellQueries)
-__global__ void knn_cell_blocks_kernel(const int *__restrict__ q_start, int P, int *__restrict__ nblk, int parts, int part) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < P) nblk[c] = (c % parts == part) ? (q_start[c + 1] - q_start[c] + kCellQueries - 1) / kCellQueries : 0;
-}
-
 __global__ void knn_query_order_kernel(const int *__restrict__ cell, const int *__restrict__ pos, long long nq, int *__restrict__ order,
                                        int *__restrict__ cell_sorted) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -515,299 +499,413 @@ __global__ void knn_cell_bounds_kernel(const float *__restrict__ feat_s, const i
         }
         if (lane == 0) {
             const bool empty = mn > mx;  // no live rows: a box at infinite distance from everything
-            lo[c * 24 + j] = empty ? INFINITY : mn - (fabsf(mn) * 4e-7f + 1e-30f);
-            hi[c * 24 + j] = empty ? -INFINITY : mx + (fabsf(mx) * 4e-7f + 1e-30f);
+            // (1e-6 relative: 4e-7 for the fp32 rounding of the rows, the rest for the fp32 rounding of a query tested against the box)
+            lo[c * 24 + j] = empty ? INFINITY : mn - (fabsf(mn) * 1e-6f + 1e-30f);
+            hi[c * 24 + j] = empty ? -INFINITY : mx + (fabsf(mx) * 1e-6f + 1e-30f);
         }
     }
 }
 
-// Each thread owns QPT queries (with 2, every broadcast candidate read from shared memory feeds 2 x 4 FFMAs per float4); the
-// queries' top-k lists live in their slots of the `partial` output (global memory, touched only by the rare survivors),
-// so shared memory holds nothing but the two candidate tiles.
-template <int NV, int QPT>
-__global__ void __launch_bounds__(kCellQueries / QPT)
-knn_cells_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ pts_s, const int *__restrict__ orig, const int *__restrict__ cell_start,
-                 const float *__restrict__ clo, const float *__restrict__ chi, int P, int dim, const double *__restrict__ q64,
-                 const int *__restrict__ q_order, const int *__restrict__ q_start, const int *__restrict__ blk_start, long long nq, const long long *__restrict__ self_ids,
-                 long long self_base, int use_self, int kk, float err_scale, float cmax, Partial *__restrict__ partial,
-                 unsigned long long *__restrict__ rows_visited, int stat_pairs) {
-    constexpr int kCellThreads = kCellQueries / QPT, kRoundCells = kCellThreads;
-    constexpr int kGroup = 8;  // candidate rows per filter group (the tile buffers have kGroup spare rows for the tail)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned long long bars[2];
-    __shared__ int s_job_row[2], s_job_cnt[2], s_job_cell[2];
-    __shared__ int s_list[kRoundCells];
-    __shared__ int s_nlist;
-    __shared__ int s_wcnt[kCellThreads / 32];
-    __shared__ float s_wlo[kCellThreads / 32][24], s_whi[kCellThreads / 32][24], s_qlo[24], s_qhi[24];
-    __shared__ float s_wr[kCellThreads / 32];
-    __shared__ float s_rblk;
-    float4 *tiles = reinterpret_cast<float4 *>(smem_raw);  // [2][kCellTile][NV]
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // block -> (query cell, chunk of kCellQueries queries of that cell): all queries of a block live in one cell, so the
-    // block's query box is (part of) that cell's box
-    if (static_cast<int>(blockIdx.x) >= blk_start[P]) return;
-    int own;
-    {
-        int lo_c = 0, hi_c = P;  // the cell c with blk_start[c] <= blockIdx.x < blk_start[c + 1] (cells without blocks are skipped)
-        while (hi_c - lo_c > 1) {
-            const int mid = (lo_c + hi_c) >> 1;
-            if (blk_start[mid] <= static_cast<int>(blockIdx.x)) lo_c = mid; else hi_c = mid;
-        }
-        own = lo_c;  // blk_start[own] <= blockIdx.x < blk_start[own + 1]: cells without blocks can never satisfy this
-    }
-    bool has_q[QPT];
-    long long qi[QPT], self[QPT];
-    float m2q[QPT][4 * NV], qn[QPT], err[QPT], thr[QPT];
-    double worst[QPT];
-    int worst_idx[QPT], worst_slot[QPT];
-#pragma unroll
-    for (int t = 0; t < QPT; ++t) {
-        const long long qs = static_cast<long long>(q_start[own]) + static_cast<long long>(blockIdx.x - blk_start[own]) * kCellQueries +
-                             t * kCellThreads + tid;
-        has_q[t] = qs < q_start[own + 1];
-        qi[t] = has_q[t] ? q_order[qs] : 0;
-        qn[t] = 0.f;
-        // (the fp64 query is not kept in registers: the rare exact re-evaluations read it back through L1)
-#pragma unroll
-        for (int j = 0; j < 4 * NV - 1; ++j) {
-            const float qf = (has_q[t] && j < dim) ? static_cast<float>(q64[qi[t] * dim + j]) : 0.f;
-            m2q[t][j] = -2.0f * qf;
-            qn[t] = fmaf(qf, qf, qn[t]);
-        }
-        m2q[t][4 * NV - 1] = 1.0f;
-        self[t] = !use_self ? -1 : (self_ids ? (has_q[t] ? self_ids[qi[t]] : -1) : self_base + qi[t]);
-        const float qnorm = sqrtf(qn[t]);
-        err[t] = err_scale * (qnorm + cmax) * (qnorm + cmax);
-        if (has_q[t]) {
-            Partial *lst = partial + qi[t] * kk;
-            for (int s = 0; s < kk; ++s) {
-                Partial e;
-                e.d2 = INFINITY; e.idx = -1; e.pad = 0;
-                lst[s] = e;
-            }
-        }
-        worst[t] = INFINITY;
-        worst_idx[t] = 0x7fffffff;
-        worst_slot[t] = 0;
-        thr[t] = has_q[t] ? INFINITY : -INFINITY;
-    }
+// ================================================================================================ query-major cell search
+// Box-to-box pruning (above) is weak in 7-D: 2^14 leaves are only ~4 cells per dimension, every leaf TOUCHES ~3^7 others, so a
+// block (or warp) of queries that shares one bound and one box still evaluates 8-15 % of all pairs, while a single query's ball
+// reaches a few dozen leaves. Here the unit of work is a batch of QB queries adjacent in k-d order, worked on by ONE WARP with the
+// roles of the lanes turned around:
+//   * search: lanes span CELLS. Three levels of boxes (256-leaf subtrees, 16-leaf subtrees, leaves; consecutive in heap order) are
+//     tested 32 at a time: the upper levels against the batch's box, the leaves against each query POINT (point-to-box distance vs
+//     that query's current k-th distance);
+//   * evaluation: lanes span candidate ROWS of a visited leaf (coalesced LDG.128 of the k-d ordered feature rows), every row is
+//     filtered against the QB queries (fp32, rigorous error bound, as in the kernels above); survivors are re-evaluated by their lane
+//     in the reference's fp64 operation order;
+//   * the k-list of a query is spread over the lanes (entry i in lane i & 31); the worst entry is kept warp-uniform and found again
+//     after an insertion with three warp reductions (REDUX) on the bit pattern of the non-negative doubles;
+//   * nearest first: ring s visits the leaves whose smallest point gap^2 lies in (tau_{s-1}, tau_s]; ring 0 is the queries' own
+//     leaves, later rings grow geometrically while the bounds shrink.
+// Results are written sorted, straight to the caller's tables (no partial lists, no merge kernel). Work per query is proportional
+// to the leaves its own ball reaches, so pairs evaluated fall from 14.5 % of N^2 to well under 1 %.
+constexpr int kSuper = 16;           // leaves per super-cell
+constexpr int kMega = 256;           // leaves per mega-cell
+constexpr int kPointThreads = 256;
+constexpr int kF2Cap = 32 * kSuper;  // super-cells of one round of 32 mega-cells
 
-    // ---- bounding box of the block's queries (fp32 values of the queries, widened like the cell boxes)
-#pragma unroll
-    for (int j = 0; j < 4 * NV - 1; ++j) {
-        float mn = INFINITY, mx = -INFINITY;
-#pragma unroll
-        for (int t = 0; t < QPT; ++t)
-            if (has_q[t]) { mn = fminf(mn, -0.5f * m2q[t][j]); mx = fmaxf(mx, -0.5f * m2q[t][j]); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, o));
-            mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+// box4[(c * 2 + 0) * NV + v] = lower corner, [(c * 2 + 1) * NV + v] = upper corner of leaf c, padded coordinates 0; sbox4 / mbox4 the
+// same for the unions over groups of kSuper / kMega leaves. Empty boxes are (+inf, -inf).
+__global__ void knn_pack_boxes_kernel(const float *__restrict__ lo, const float *__restrict__ hi, int P, int dim, int fw, int group, int write_leaves,
+                                      float *__restrict__ box, float *__restrict__ gbox) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (group, coordinate)
+    const int G = (P + group - 1) / group;
+    if (i >= G * fw) return;
+    const int s = i / fw, j = i % fw;
+    float slo = INFINITY, shi = -INFINITY;
+    for (int t = 0; t < group; ++t) {
+        const int c = s * group + t;
+        if (c >= P) break;
+        const float l = j < dim ? lo[c * 24 + j] : 0.f, h = j < dim ? hi[c * 24 + j] : 0.f;
+        if (write_leaves) {
+            box[(static_cast<size_t>(c) * 2 + 0) * fw + j] = l;
+            box[(static_cast<size_t>(c) * 2 + 1) * fw + j] = h;
         }
-        if (lane == 0) { s_wlo[wid][j] = mn; s_whi[wid][j] = mx; }
+        slo = fminf(slo, l);
+        shi = fmaxf(shi, h);
     }
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid < 4 * NV - 1) {
-        float mn = INFINITY, mx = -INFINITY;
-        for (int w = 0; w < kCellThreads / 32; ++w) { mn = fminf(mn, s_wlo[w][tid]); mx = fmaxf(mx, s_whi[w][tid]); }
-        s_qlo[tid] = mn - (fabsf(mn) * 4e-7f + 1e-30f);
-        s_qhi[tid] = mx + (fabsf(mx) * 4e-7f + 1e-30f);
-    }
-    const int own_lo = own, own_hi = own;
-    int it = 0;  // tile jobs issued so far: buffer = it & 1, mbarrier parity = (it >> 1) & 1
-    __syncthreads();
+    gbox[(static_cast<size_t>(s) * 2 + 0) * fw + j] = slo;
+    gbox[(static_cast<size_t>(s) * 2 + 1) * fw + j] = shi;
+}
 
-    // stream the listed cells through shared memory, double buffered. Thread 0 walks the list (cell -> tiles of at most
-    // kCellTile rows), announces each tile in the 2-entry ring s_job_* and issues its bulk copy one tile ahead.
-    int gl = 0, gb = 0, ge = 0, gcell = 0;  // generator state, meaningful in thread 0 only
-    auto next_job = [&](int slot_it) {
-        const int slot = slot_it & 1;
-        while (gb >= ge) {
-            if (gl >= s_nlist) { s_job_cnt[slot] = 0; return; }
-            const int c = s_list[gl++];
-            gcell = c;
-            gb = cell_start[c];
-            ge = cell_start[c + 1];
+// Share of part `part` of `parts` in the k-d ordered queries: whole leaves, contiguous, balanced by query count. Depends only on the
+// leaves' query counts, so every GPU holding the same database and the same queries computes the same shares.
+__device__ __forceinline__ void knn_part_range(const int *__restrict__ q_start, int P, long long nq, int parts, int part, int *lo, int *hi) {
+    auto first_leaf_at = [&](long long target) {  // first leaf whose queries start at or after `target`
+        int a = 0, b = P;
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (q_start[mid] < target) a = mid + 1; else b = mid;
         }
-        const int cnt = min(kCellTile, ge - gb);
-        s_job_row[slot] = gb;
-        s_job_cnt[slot] = cnt;
-        s_job_cell[slot] = gcell;
-        const uint32_t bytes = static_cast<uint32_t>(cnt) * NV * sizeof(float4);
-        mbar_expect_tx(&bars[slot], bytes);
-        bulk_g2s(tiles + static_cast<size_t>(slot) * (kCellTile + 8) * NV, feat_s + static_cast<long long>(gb) * NV, bytes, &bars[slot]);
-        gb += cnt;
+        return a;
     };
-    // exact re-evaluation of a filter survivor (database row r) for query slot t, the reference's arithmetic
-    // (RealVectorStateSpace.cpp:230-242), and insertion into that query's list
-    auto survivor = [&](int t, long long r) {
-        const int id = orig[r];
-        if (id == self[t]) return;
-        double d2 = 0.0;
-        for (int j2 = 0; j2 < dim; ++j2) {
-            const double diff = pts_s[r * dim + j2] - q64[qi[t] * dim + j2];
-            d2 = __dadd_rn(d2, __dmul_rn(diff, diff));  // no FMA contraction: bit-identical to the reference's x86-64 doubles
-        }
-        if (d2 < worst[t] || (d2 == worst[t] && id < worst_idx[t])) {
-            Partial *lst = partial + qi[t] * kk;
-            Partial e;
-            e.d2 = d2; e.idx = id; e.pad = 0;
-            lst[worst_slot[t]] = e;
-            // new worst = lexicographic max of (d2, idx) over the list
-            worst[t] = -1.0;
-            worst_idx[t] = -1;
-            for (int s2 = 0; s2 < kk; ++s2) {
-                const Partial v = lst[s2];
-                const int key = v.idx < 0 ? 0x7fffffff : v.idx;
-                if (v.d2 > worst[t] || (v.d2 == worst[t] && key > worst_idx[t])) { worst[t] = v.d2; worst_idx[t] = key; worst_slot[t] = s2; }
-            }
-            // s_exact = d2 - |q|^2 ; pass while s_approx < worst - qn + err (rounded up)
-            thr[t] = (worst[t] == INFINITY) ? INFINITY : __double2float_ru(worst[t] - static_cast<double>(qn[t])) + err[t];
-        }
-    };
-    unsigned long long visited = 0;  // rows streamed by this block (thread 0), for the pruning statistics
-    auto run_list = [&]() {
-        if (tid == 0) {
-            gl = 0; gb = 0; ge = 0;
-            next_job(it);
-        }
-        __syncthreads();
-        for (;;) {
-            const int slot = it & 1;
-            const int cnt = s_job_cnt[slot];
-            if (cnt == 0) break;
-            const int row0 = s_job_row[slot];
-            const int tcell = s_job_cell[slot];
-            if (tid == 0) { next_job(it + 1); visited += cnt; }
-            // per-warp pruning: the block streams every cell some warp may need, but a warp whose own queries cannot be reached
-            // from this cell (box-to-box lower bound beyond the warp's worst k-th distance) skips the arithmetic. One query with
-            // few close neighbours then costs its own warp, not the block.
-            float gap2 = 0.f;
-            if (lane < dim) {
-                const float wl = s_wlo[wid][lane], wh = s_whi[wid][lane];
-                const float g = fmaxf(fmaxf(clo[tcell * 24 + lane] - (wh + (fabsf(wh) * 4e-7f + 1e-30f)), (wl - (fabsf(wl) * 4e-7f + 1e-30f)) - chi[tcell * 24 + lane]), 0.f);
-                gap2 = g * g;
-            }
-            float wr2 = -INFINITY;
+    *lo = part == 0 ? 0 : q_start[first_leaf_at(nq * part / parts)];
+    *hi = part == parts - 1 ? static_cast<int>(nq) : q_start[first_leaf_at(nq * (part + 1) / parts)];
+}
+
+// KPL list entries per lane (k <= 32 KPL); QB queries per batch
+template <int NV, int QB, int KPL, int MINB>
+__global__ void __launch_bounds__(kPointThreads, MINB)
+knn_point_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ pts_s, const int *__restrict__ orig, const int *__restrict__ cell_start,
+                 const float4 *__restrict__ box4, const float4 *__restrict__ sbox4, const float4 *__restrict__ mbox4, int P, int dim,
+                 const double *__restrict__ q64, const int *__restrict__ q_order, const int *__restrict__ q_cell, const int *__restrict__ q_start,
+                 long long nq, const long long *__restrict__ self_ids, long long self_base, int use_self, int kk, float err_scale, float cmax,
+                 float tau0_frac, float tau_growth, int parts, int part, int chunk, long long *__restrict__ out_idx, double *__restrict__ out_dist,
+                 int *__restrict__ out_counts, unsigned long long *__restrict__ work_head, unsigned long long *__restrict__ stats) {
+    constexpr int W = kPointThreads / 32;
+    constexpr int FW = 4 * NV;
+    __shared__ unsigned short s_f2[W][kF2Cap];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int S = (P + kSuper - 1) / kSuper, M = (P + kMega - 1) / kMega;
+    int p_lo = 0, p_hi = static_cast<int>(nq);
+    if (parts > 1) knn_part_range(q_start, P, nq, parts, part, &p_lo, &p_hi);
+    unsigned long long st_rows = 0, st_exact = 0, st_ins = 0, st_cells = 0;
+
+    for (;;) {
+        unsigned long long w0 = 0;
+        if (lane == 0) w0 = atomicAdd(work_head, static_cast<unsigned long long>(chunk));
+        w0 = __shfl_sync(kFullMask, w0, 0);
+        if (static_cast<long long>(w0) >= p_hi - p_lo) break;
+        const int c_end = static_cast<int>(min(static_cast<long long>(p_hi), static_cast<long long>(p_lo) + static_cast<long long>(w0) + chunk));
+        for (int p0 = p_lo + static_cast<int>(w0); p0 < c_end; p0 += QB) {
+            // ---- the batch: QB queries adjacent in k-d order (all lanes hold all of them)
+            bool has_q[QB];
+            long long qi[QB];
+            int self[QB], own[QB];
+            float m2q[QB][FW], qn[QB], err[QB], thr[QB], rw2[QB];  // query b's coordinates are -0.5 * m2q[b][.] (exact)
+            double wd2[QB];            // worst entry of the list: value, key, holder (warp-uniform)
+            int wkey[QB], wlane[QB], wslot[QB];
+            double ld2[QB][KPL];       // this lane's entries of the QB lists
+            int lid[QB][KPL];          // id, -1 = empty, -2 = beyond k (never the worst, never reported)
+            float blo[FW], bhi[FW];    // box of the batch (upper levels of the search)
 #pragma unroll
-            for (int t = 0; t < QPT; ++t)
-                if (has_q[t]) wr2 = fmaxf(wr2, worst[t] == INFINITY ? INFINITY : __double2float_ru(worst[t]) * 1.000001f);
+            for (int j = 0; j < FW; ++j) { blo[j] = INFINITY; bhi[j] = -INFINITY; }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                gap2 += __shfl_xor_sync(kFullMask, gap2, o);
-                wr2 = fmaxf(wr2, __shfl_xor_sync(kFullMask, wr2, o));
-            }
-            const bool warp_skip = !(gap2 * 0.99999f <= wr2);  // also true for warps without queries (wr2 = -inf)
-            if (stat_pairs && !warp_skip) {
-                const unsigned nqw = __popc(__ballot_sync(kFullMask, has_q[0])) + __popc(__ballot_sync(kFullMask, has_q[QPT - 1]));
-                if (lane == 0) atomicAdd(rows_visited, static_cast<unsigned long long>(cnt) * nqw);
-            }
-            mbar_wait(&bars[slot], (it >> 1) & 1);
-            const float4 *tile = tiles + static_cast<size_t>(slot) * (kCellTile + 8) * NV;
-            for (int c0 = 0; c0 < (warp_skip ? 0 : cnt); c0 += kGroup) {
-                float sv[QPT][kGroup];
+            for (int b = 0; b < QB; ++b) {
+                has_q[b] = p0 + b < c_end;
+                qi[b] = q_order[has_q[b] ? p0 + b : p0];
+                own[b] = q_cell[has_q[b] ? p0 + b : p0];
+                qn[b] = 0.f;
 #pragma unroll
-                for (int u = 0; u < kGroup; ++u) {
-                    // rows past cnt (same buffer, stale or unwritten) may be read: whatever they yield is dropped below by index
-                    const float4 *row = tile + (c0 + u) * NV;
-                    // s = |c|^2 - 2 q.c: the stored norm (last float of the row) starts the sum, 4 NV - 1 FFMAs follow
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        const float4 c = row[NV - 1 - v];  // last float4 first: it carries |c|^2
-#pragma unroll
-                        for (int t = 0; t < QPT; ++t) {
-                            if (v == 0) sv[t][u] = c.w;
-                            else sv[t][u] = fmaf(m2q[t][4 * (NV - 1 - v) + 3], c.w, sv[t][u]);
-                            sv[t][u] = fmaf(m2q[t][4 * (NV - 1 - v) + 0], c.x, sv[t][u]);
-                            sv[t][u] = fmaf(m2q[t][4 * (NV - 1 - v) + 1], c.y, sv[t][u]);
-                            sv[t][u] = fmaf(m2q[t][4 * (NV - 1 - v) + 2], c.z, sv[t][u]);
-                        }
-                    }
+                for (int j = 0; j < FW - 1; ++j) {
+                    const float v = j < dim ? static_cast<float>(q64[qi[b] * dim + j]) : 0.f;
+                    m2q[b][j] = -2.0f * v;
+                    qn[b] = fmaf(v, v, qn[b]);
+                    blo[j] = fminf(blo[j], v);
+                    bhi[j] = fmaxf(bhi[j], v);
                 }
+                m2q[b][FW - 1] = 1.0f;  // picks up |c|^2 stored in the last slot
+                const long long sf = !use_self ? -1 : (self_ids ? self_ids[qi[b]] : self_base + qi[b]);
+                self[b] = static_cast<int>(sf);
+                const float qnorm = sqrtf(qn[b]);
+                err[b] = err_scale * (qnorm + cmax) * (qnorm + cmax);
+                thr[b] = has_q[b] ? INFINITY : -INFINITY;
+                rw2[b] = has_q[b] ? INFINITY : -INFINITY;
 #pragma unroll
-                for (int t = 0; t < QPT; ++t) {
+                for (int e = 0; e < KPL; ++e) {
+                    const bool real = e * 32 + lane < kk;
+                    ld2[b][e] = real ? INFINITY : 0.0;
+                    lid[b][e] = real ? -1 : -2;
+                }
+                wd2[b] = INFINITY;
+                wkey[b] = 0x7fffffff;
+                wlane[b] = 0;
+                wslot[b] = 0;
+            }
+#pragma unroll
+            for (int j = 0; j < FW; ++j) {  // widened like the cell boxes: the box also bounds the exact fp64 queries
+                blo[j] = j < FW - 1 ? blo[j] - (fabsf(blo[j]) * 4e-7f + 1e-30f) : 0.f;
+                bhi[j] = j < FW - 1 ? bhi[j] + (fabsf(bhi[j]) * 4e-7f + 1e-30f) : 0.f;
+            }
+            // squared distance from the batch's box to a box (upper levels) / from query b to a box (leaves)
+            auto box_gap2 = [&](const float4 *__restrict__ bx) -> float {
+                float g2 = 0.f;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 lo = __ldg(bx + v), hi = __ldg(bx + NV + v);
+                    float g;
+                    g = fmaxf(fmaxf(lo.x - bhi[4 * v + 0], blo[4 * v + 0] - hi.x), 0.f); g2 = fmaf(g, g, g2);
+                    g = fmaxf(fmaxf(lo.y - bhi[4 * v + 1], blo[4 * v + 1] - hi.y), 0.f); g2 = fmaf(g, g, g2);
+                    g = fmaxf(fmaxf(lo.z - bhi[4 * v + 2], blo[4 * v + 2] - hi.z), 0.f); g2 = fmaf(g, g, g2);
+                    if (v < NV - 1) { g = fmaxf(fmaxf(lo.w - bhi[4 * v + 3], blo[4 * v + 3] - hi.w), 0.f); g2 = fmaf(g, g, g2); }
+                }
+                return g2;
+            };
+            // list update after the bound of query b changed
+            auto refresh = [&](int b) {
+                thr[b] = (wd2[b] == INFINITY) ? INFINITY : __double2float_ru(wd2[b] - static_cast<double>(qn[b])) + err[b];
+                rw2[b] = (wd2[b] == INFINITY) ? INFINITY : __double2float_ru(wd2[b]) * 1.000001f;
+            };
+            // lexicographic maximum of (d2, key) over the list of query b: three reductions on the bits of the non-negative doubles
+            auto find_worst = [&](int b) {
+                unsigned hi_u = 0, lo_u = 0, key_u = 0;
+                int slot = 0;
+#pragma unroll
+                for (int e = 0; e < KPL; ++e) {
+                    const unsigned h = static_cast<unsigned>(__double2hiint(ld2[b][e])), l = static_cast<unsigned>(__double2loint(ld2[b][e]));
+                    // keys: real id + 1; empty = above every id (distinct per entry); beyond-k entries = 0 (with d2 = 0: the minimum)
+                    const unsigned ky = lid[b][e] >= 0 ? static_cast<unsigned>(lid[b][e]) + 1u
+                                                       : (lid[b][e] == -1 ? 0xffffffffu - static_cast<unsigned>(e * 32 + lane) : 0u);
+                    if (h > hi_u || (h == hi_u && (l > lo_u || (l == lo_u && ky >= key_u)))) { hi_u = h; lo_u = l; key_u = ky; slot = e; }
+                }
+                const unsigned mh = __reduce_max_sync(kFullMask, hi_u);
+                bool cand = hi_u == mh;
+                const unsigned ml = __reduce_max_sync(kFullMask, cand ? lo_u : 0u);
+                cand = cand && lo_u == ml;
+                const unsigned mk = __reduce_max_sync(kFullMask, cand ? key_u : 0u);
+                const unsigned who = __ballot_sync(kFullMask, cand && key_u == mk);
+                wlane[b] = __ffs(who) - 1;
+                wslot[b] = __shfl_sync(kFullMask, slot, wlane[b]);
+                wd2[b] = __hiloint2double(static_cast<int>(mh), static_cast<int>(ml));
+                wkey[b] = mk >= 0x80000000u ? 0x7fffffff : static_cast<int>(mk) - 1;  // an empty entry ranks above every id
+                refresh(b);
+            };
+            // rows [rb, re) of the k-d ordered database against the batch, 64 at a time (two per lane, all loads issued first)
+            auto eval_rows = [&](int rb, int re) {
+                for (int r0 = rb; r0 < re; r0 += 64) {
+                    int r[2];
+                    bool in[2];
+                    float4 c[2][NV];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        r[h] = r0 + 32 * h + lane;
+                        in[h] = r[h] < re;
+                        const float4 *row = feat_s + static_cast<long long>(in[h] ? r[h] : re - 1) * NV;
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) c[h][v] = __ldg(row + v);
+                    }
+                    bool pass[2][QB];
                     bool any = false;
 #pragma unroll
-                    for (int u = 0; u < kGroup; ++u) any |= sv[t][u] < thr[t];
-                    if (any) {
-#pragma unroll 1
-                        for (int u = 0; u < kGroup; ++u) {
-                            if (!(sv[t][u] < thr[t]) || c0 + u >= cnt) continue;
-                            survivor(t, static_cast<long long>(row0) + c0 + u);
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int b = 0; b < QB; ++b) {
+                            float sv = c[h][NV - 1].w;  // s = |c|^2 - 2 q.c: the stored norm starts the sum
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) {
+                                sv = fmaf(m2q[b][4 * v + 0], c[h][v].x, sv);
+                                sv = fmaf(m2q[b][4 * v + 1], c[h][v].y, sv);
+                                sv = fmaf(m2q[b][4 * v + 2], c[h][v].z, sv);
+                                if (v < NV - 1) sv = fmaf(m2q[b][4 * v + 3], c[h][v].w, sv);
+                            }
+                            pass[h][b] = in[h] && sv < thr[b];
+                            any |= pass[h][b];
+                        }
+                    }
+                    if (!__any_sync(kFullMask, any)) continue;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        bool anyh = false;
+#pragma unroll
+                        for (int b = 0; b < QB; ++b) anyh |= pass[h][b];
+                        if (!__any_sync(kFullMask, anyh)) continue;
+                        const int rr = r[h];
+                        const int id = anyh ? __ldg(orig + rr) : -1;
+#pragma unroll
+                        for (int b = 0; b < QB; ++b) {
+                            bool cand = pass[h][b];
+                            if (!__any_sync(kFullMask, cand)) continue;
+                            // exact distance, the reference's arithmetic (RealVectorStateSpace.cpp:230-242), by the lane that holds the row
+                            double d2 = 0.0;
+                            if (cand && id != self[b]) {
+                                for (int j = 0; j < dim; ++j) {
+                                    const double diff = pts_s[static_cast<long long>(rr) * dim + j] - q64[qi[b] * dim + j];
+                                    d2 = __dadd_rn(d2, __dmul_rn(diff, diff));  // no FMA contraction: bit-identical to the reference's x86-64 doubles
+                                }
+                            } else {
+                                cand = false;
+                            }
+                            if (stats) st_exact += __popc(__ballot_sync(kFullMask, cand));
+                            for (;;) {  // insert the candidates one at a time, each against the bound the previous one left
+                                const bool better = cand && (d2 < wd2[b] || (d2 == wd2[b] && id < wkey[b]));
+                                const unsigned m = __ballot_sync(kFullMask, better);
+                                if (!m) break;
+                                const int src = __ffs(m) - 1;
+                                const double nd = __shfl_sync(kFullMask, d2, src);
+                                const int ni = __shfl_sync(kFullMask, id, src);
+                                if (lane == wlane[b]) {
+#pragma unroll
+                                    for (int e = 0; e < KPL; ++e)
+                                        if (e == wslot[b]) { ld2[b][e] = nd; lid[b][e] = ni; }
+                                }
+                                if (lane == src) cand = false;
+                                find_worst(b);
+                                if (stats) ++st_ins;
+                            }
                         }
                     }
                 }
+                if (stats) { st_rows += static_cast<unsigned long long>(re - rb) * QB; ++st_cells; }
+            };
+            // ---- ring 0: the leaves the queries fall into
+#pragma unroll
+            for (int b = 0; b < QB; ++b) {
+                bool first = has_q[b];
+#pragma unroll
+                for (int b2 = 0; b2 < b; ++b2) first = first && !(has_q[b2] && own[b2] == own[b]);
+                if (first) eval_rows(__ldg(cell_start + own[b]), __ldg(cell_start + own[b] + 1));
             }
-            __syncthreads();
-            ++it;
-        }
-        __syncthreads();
-    };
-    // block-wide maximum of the queries' squared k-th distances (rounded up)
-    auto refresh_bound = [&]() {
-        float r2 = -INFINITY;
+            // ---- rings: leaves whose smallest point gap^2 lies in (tau_prev, tau], nearest first
+            auto sweep = [&](float tau_prev, float tau) {
+                float rmax = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < QPT; ++t)
-            if (has_q[t]) r2 = fmaxf(r2, worst[t] == INFINITY ? INFINITY : __double2float_ru(worst[t]) * 1.000001f);
+                for (int b = 0; b < QB; ++b) rmax = fmaxf(rmax, rw2[b]);
+                for (int mb = 0; mb < M; mb += 32) {
+                    const int mg = mb + lane;
+                    const float g = mg < M ? box_gap2(mbox4 + static_cast<size_t>(mg) * 2 * NV) : INFINITY;
+                    unsigned mm = __ballot_sync(kFullMask, g <= tau && g * 0.99999f <= rmax);
+                    int nf2 = 0;
+                    while (mm) {  // super-cells of two passing mega-cells at a time, one lane each
+                        const int m1 = mb + __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        int m2 = -1;
+                        if (mm) { m2 = mb + __ffs(mm) - 1; mm &= mm - 1; }
+                        const int mym = lane < 16 ? m1 : m2;
+                        const int sc = mym * (kMega / kSuper) + (lane & 15);
+                        const float sg = (mym >= 0 && sc < S) ? box_gap2(sbox4 + static_cast<size_t>(sc) * 2 * NV) : INFINITY;
+                        const bool ok = sg <= tau && sg * 0.99999f <= rmax;
+                        const unsigned sm = __ballot_sync(kFullMask, ok);
+                        if (ok) s_f2[wid][nf2 + __popc(sm & ((1u << lane) - 1u))] = static_cast<unsigned short>(sc);
+                        nf2 += __popc(sm);
+                    }
+                    __syncwarp();
+                    for (int i = 0; i < nf2; i += 2) {  // leaves of two passing super-cells at a time, one lane each
+                        const int s1 = s_f2[wid][i], s2 = i + 1 < nf2 ? static_cast<int>(s_f2[wid][i + 1]) : -1;
+                        const int mys = lane < 16 ? s1 : s2;
+                        const int c = mys * kSuper + (lane & 15);
+                        bool take = false;
+                        int rb = 0, re = 0;
+                        if (mys >= 0 && c < P) {
+                            rb = __ldg(cell_start + c);  // row range of the leaf, fetched by its lane alongside the box
+                            re = __ldg(cell_start + c + 1);
+                            const float4 *bx = box4 + static_cast<size_t>(c) * 2 * NV;
+                            float4 lo[NV], hi[NV];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(kFullMask, r2, o));
-        if (lane == 0) s_wr[wid] = r2;
-        __syncthreads();
-        if (tid == 0) {
-            float m = -INFINITY;
-            for (int w = 0; w < kCellThreads / 32; ++w) m = fmaxf(m, s_wr[w]);
-            s_rblk = m;
-        }
-        __syncthreads();
-    };
-    // ---- the cells the block's own queries live in (contiguous in cell order)
-    for (int c0 = own_lo; c0 <= own_hi; c0 += kRoundCells) {
-        if (tid == 0) s_nlist = min(kRoundCells, own_hi - c0 + 1);
-        __syncthreads();
-        if (tid < s_nlist) s_list[tid] = c0 + tid;
-        __syncthreads();
-        run_list();
-    }
-    refresh_bound();
-    // ---- every other cell, kRoundCells at a time: one thread tests one cell's box against the block's query box. Two sweeps: first
-    // the cells whose box overlaps the query box (they hold almost all true neighbours, so afterwards the k-th distances
-    // are nearly final), then the remaining cells that lie within the block's worst k-th distance.
-    for (int sweep = 0; sweep < 2; ++sweep) {
-        for (int base = 0; base < P; base += kRoundCells) {
-            const int c = base + tid;
-            bool pass = false;
-            if (c < P && (c < own_lo || c > own_hi)) {
-                // block-level test (per-warp boxes were measured: queries of a cell are not ordered in space, so a warp's box is
-                // the block's box and listing per warp only adds tests); empty cells have gap = +inf and never pass
-                float d2 = 0.f;
-                for (int j = 0; j < dim; ++j) {
-                    const float gap = fmaxf(fmaxf(clo[c * 24 + j] - s_qhi[j], s_qlo[j] - chi[c * 24 + j]), 0.f);
-                    d2 = fmaf(gap, gap, d2);
+                            for (int v = 0; v < NV; ++v) { lo[v] = __ldg(bx + v); hi[v] = __ldg(bx + NV + v); }
+                            float gmin = INFINITY;
+                            bool reach = false;
+#pragma unroll
+                            for (int b = 0; b < QB; ++b) {
+                                float g2 = 0.f;
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) {
+                                    const float qc0 = -0.5f * m2q[b][4 * v + 0], qc1 = -0.5f * m2q[b][4 * v + 1], qc2 = -0.5f * m2q[b][4 * v + 2];
+                                    const float qc3 = v < NV - 1 ? -0.5f * m2q[b][4 * v + 3] : 0.f;
+                                    float d;
+                                    d = fmaxf(fmaxf(lo[v].x - qc0, qc0 - hi[v].x), 0.f); g2 = fmaf(d, d, g2);
+                                    d = fmaxf(fmaxf(lo[v].y - qc1, qc1 - hi[v].y), 0.f); g2 = fmaf(d, d, g2);
+                                    d = fmaxf(fmaxf(lo[v].z - qc2, qc2 - hi[v].z), 0.f); g2 = fmaf(d, d, g2);
+                                    if (v < NV - 1) { d = fmaxf(fmaxf(lo[v].w - qc3, qc3 - hi[v].w), 0.f); g2 = fmaf(d, d, g2); }
+                                }
+                                if (has_q[b]) {
+                                    gmin = fminf(gmin, g2);
+                                    // 0.9999: the fp32 gap of the fp32-rounded query stays below the true gap of the fp64 query
+                                    reach = reach || g2 * 0.9999f <= rw2[b];
+                                    take = take || c == own[b];
+                                }
+                            }
+                            take = !take && reach && gmin > tau_prev && gmin <= tau;  // own leaves were ring 0
+                        }
+                        unsigned cm = __ballot_sync(kFullMask, take);
+                        while (cm) {
+                            const int l = __ffs(cm) - 1;
+                            cm &= cm - 1;
+                            eval_rows(__shfl_sync(kFullMask, rb, l), __shfl_sync(kFullMask, re, l));
+                        }
+                    }
+                    __syncwarp();
                 }
-                pass = sweep == 0 ? (d2 == 0.f) : (d2 > 0.f && d2 * 0.99999f <= s_rblk);
+            };
+            // first radius when the own leaves hold fewer than k rows (no finite bound yet): diagonal of the own leaf's box, at least
+            float seed_tau = 1e-12f;
+            {
+                const float4 *bx = box4 + static_cast<size_t>(own[0]) * 2 * NV;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const float4 lo = __ldg(bx + v), hi = __ldg(bx + NV + v);
+                    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z, dw = v < NV - 1 ? hi.w - lo.w : 0.f;
+                    if (dx > 0.f && dx < INFINITY) seed_tau = fmaf(dx, dx, seed_tau);
+                    if (dy > 0.f && dy < INFINITY) seed_tau = fmaf(dy, dy, seed_tau);
+                    if (dz > 0.f && dz < INFINITY) seed_tau = fmaf(dz, dz, seed_tau);
+                    if (dw > 0.f && dw < INFINITY) seed_tau = fmaf(dw, dw, seed_tau);
+                }
             }
-            const unsigned bal = __ballot_sync(kFullMask, pass);
-            if (lane == 0) s_wcnt[wid] = __popc(bal);
-            __syncthreads();
-            int off = 0;
-            for (int w = 0; w < wid; ++w) off += s_wcnt[w];
-            if (pass) s_list[off + __popc(bal & ((1u << lane) - 1u))] = c;
-            if (tid == kCellThreads - 1) s_nlist = off + __popc(bal);
-            __syncthreads();
-            if (s_nlist > 0) {
-                run_list();
-                refresh_bound();
+            float tau_prev = -1.f, tau = 0.f;
+            for (int it = 0;; ++it) {
+                float rmax = -INFINITY;
+#pragma unroll
+                for (int b = 0; b < QB; ++b) rmax = fmaxf(rmax, rw2[b]);
+                if (it > 0 && tau * 0.9999f >= rmax) break;  // every leaf within the final bounds has been visited
+                tau_prev = it == 0 ? -1.f : tau;
+                tau = it == 0 ? (rmax < INFINITY ? tau0_frac * rmax : seed_tau) : tau * tau_growth;
+                if (it > 48) tau = INFINITY;
+                sweep(tau_prev, tau);
+            }
+            // ---- sorted output: rank of every entry = number of entries before it in (d2, id) order
+#pragma unroll
+            for (int b = 0; b < QB; ++b) {
+                if (!has_q[b]) continue;
+                int rank[KPL];
+                unsigned mykey[KPL];
+#pragma unroll
+                for (int e = 0; e < KPL; ++e) {
+                    rank[e] = 0;
+                    mykey[e] = lid[b][e] >= 0 ? static_cast<unsigned>(lid[b][e]) : 0xffffffffu - static_cast<unsigned>(e * 32 + lane);
+                }
+                for (int s2 = 0; s2 < kk; ++s2) {
+                    double od = 0.0;
+                    unsigned ok = 0;
+#pragma unroll
+                    for (int e = 0; e < KPL; ++e)
+                        if (e == s2 / 32) { od = __shfl_sync(kFullMask, ld2[b][e], s2 & 31); ok = __shfl_sync(kFullMask, mykey[e], s2 & 31); }
+#pragma unroll
+                    for (int e = 0; e < KPL; ++e) rank[e] += (od < ld2[b][e] || (od == ld2[b][e] && ok < mykey[e])) ? 1 : 0;
+                }
+                int found = 0;
+#pragma unroll
+                for (int e = 0; e < KPL; ++e) {
+                    const bool real = lid[b][e] != -2;
+                    if (real) {
+                        out_idx[qi[b] * kk + rank[e]] = lid[b][e];
+                        out_dist[qi[b] * kk + rank[e]] = lid[b][e] >= 0 ? sqrt(ld2[b][e]) : INFINITY;
+                    }
+                    found += __popc(__ballot_sync(kFullMask, real && lid[b][e] >= 0));
+                }
+                if (out_counts && lane == 0) out_counts[qi[b]] = found;
             }
         }
     }
-    if (tid == 0 && rows_visited && !stat_pairs) atomicAdd(rows_visited, visited);
+    if (stats && lane == 0) {
+        atomicAdd(stats + 0, st_rows);
+        atomicAdd(stats + 1, st_exact);
+        atomicAdd(stats + 2, st_ins);
+        atomicAdd(stats + 3, st_cells);
+    }
 }
 
 
@@ -970,6 +1068,8 @@ struct b200mp_knn {
     double *ix_pts = nullptr;
     int *ix_orig = nullptr, *ix_start = nullptr;
     float *ix_lo = nullptr, *ix_hi = nullptr, *ix_splits = nullptr;
+    float4 *ix_box = nullptr, *ix_sbox = nullptr, *ix_mbox = nullptr;  // packed boxes of the leaves and of their 16- and 256-leaf subtrees
+    unsigned long long *d_point_ctl = nullptr;  // [0] work-queue head, [1..4] statistics of the query-major search
     int *ix_dims = nullptr;
     int index_L = 0;
     unsigned long long *d_rows_visited = nullptr;  // candidate rows streamed by the cell kernel since creation
@@ -1108,6 +1208,17 @@ namespace {
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
+// development switches (A/B measurements): B200MP_KNN_QPT = queries per batch of the search, B200MP_KNN_CELL_ROWS = rows per leaf
+inline int knn_warp_qpt() {  // queries per batch of the query-major search
+    const char *e = getenv("B200MP_KNN_QPT");
+    const int v = e ? atoi(e) : 1;
+    return (v == 2 || v == 4) ? v : 1;
+}
+inline float knn_env_float(const char *name, float dflt) {
+    const char *e = getenv(name);
+    return e ? static_cast<float>(atof(e)) : dflt;
+}
+
 // leaf (cell) of every feature row under the index's split planes
 int knn_assign(b200mp_knn *k, const float *rows, long long n, int *cell, cudaStream_t st) {
     knn_kd_assign_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(rows, n, k->nv * 4, k->index_L, k->ix_dims, k->ix_splits, cell);
@@ -1133,7 +1244,7 @@ int knn_build_index(b200mp_knn *k, cudaStream_t st) {
     const long long n = k->n;
     const int fw = k->nv * 4, dim = k->dim;
     int P = 64, L = 6;
-    const long long rows_per_cell = getenv("B200MP_KNN_CELL_ROWS") ? atoll(getenv("B200MP_KNN_CELL_ROWS")) : kCellQueries;
+    const long long rows_per_cell = getenv("B200MP_KNN_CELL_ROWS") ? atoll(getenv("B200MP_KNN_CELL_ROWS")) : 64;
     while (P < 65536 && static_cast<long long>(P) * rows_per_cell < n) { P *= 2; ++L; }
     k->index_P = P;
     k->index_L = L;
@@ -1146,6 +1257,9 @@ int knn_build_index(b200mp_knn *k, cudaStream_t st) {
     const size_t o_hi = off; off += align256(static_cast<size_t>(P) * 24 * sizeof(float));
     const size_t o_split = off; off += align256(static_cast<size_t>(P) * sizeof(float));
     const size_t o_dims = off; off += align256(static_cast<size_t>(L + 1) * sizeof(int));
+    const size_t o_box = off; off += align256(static_cast<size_t>(P) * 2 * fw * sizeof(float));
+    const size_t o_sbox = off; off += align256(static_cast<size_t>(P / kSuper) * 2 * fw * sizeof(float));
+    const size_t o_mbox = off; off += align256(static_cast<size_t>((P + kMega - 1) / kMega) * 2 * fw * sizeof(float));
     int rc = k->index_mem.reserve(off);
     if (rc) return rc;
     char *m = k->index_mem.ptr;
@@ -1157,6 +1271,9 @@ int knn_build_index(b200mp_knn *k, cudaStream_t st) {
     k->ix_hi = reinterpret_cast<float *>(m + o_hi);
     k->ix_splits = reinterpret_cast<float *>(m + o_split);
     k->ix_dims = reinterpret_cast<int *>(m + o_dims);
+    k->ix_box = reinterpret_cast<float4 *>(m + o_box);
+    k->ix_sbox = reinterpret_cast<float4 *>(m + o_sbox);
+    k->ix_mbox = reinterpret_cast<float4 *>(m + o_mbox);
     // temporaries: cell[n] | pos[n] | counts[P] | cursor[P] | hist[P / 2][bins] | boxes A, B [P][2 dim] | extent[2 dim]
     const size_t a_n = align256(static_cast<size_t>(n) * 4), a_p = align256(static_cast<size_t>(P) * 4);
     const size_t a_hist = align256(static_cast<size_t>(P / 2) * kKdBins * 4), a_box = align256(static_cast<size_t>(P) * 2 * dim * 4);
@@ -1198,32 +1315,51 @@ int knn_build_index(b200mp_knn *k, cudaStream_t st) {
                                            k->ix_orig);
     knn_cell_bounds_kernel<<<(P * 32 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float *>(k->ix_feat), k->ix_start, P, fw, k->dim, k->ix_lo,
                                                                  k->ix_hi);
+    knn_pack_boxes_kernel<<<(P / kSuper * fw + 255) / 256, 256, 0, st>>>(k->ix_lo, k->ix_hi, P, k->dim, fw, kSuper, 1, reinterpret_cast<float *>(k->ix_box),
+                                                                        reinterpret_cast<float *>(k->ix_sbox));
+    knn_pack_boxes_kernel<<<((P + kMega - 1) / kMega * fw + 255) / 256, 256, 0, st>>>(k->ix_lo, k->ix_hi, P, k->dim, fw, kMega, 0, nullptr,
+                                                                                     reinterpret_cast<float *>(k->ix_mbox));
     B200_CUDA(cudaGetLastError());
-    k->ctx->launches.fetch_add(2);
+    k->ctx->launches.fetch_add(4);
     k->index_valid = true;
     k->index_n = n;
     return B200MP_OK;
 }
 
-template <int NV>
-int launch_cells(b200mp_knn *k, const double *d_q, const int *q_order, const int *q_start, const int *blk_start, long long nq,
-                 const long long *d_self, long long self_base, int use_self, int kk, Partial *d_partial, cudaStream_t st, int n_parts) {
-    const size_t smem = 2 * (kCellTile + 8) * NV * sizeof(float4);
-    // few blocks for this GPU (a rank's share of a multi-GPU build, or a small batch): the 256-thread shape
-    const long long slots = static_cast<long long>(k->ctx->sm_count) * 5;
-    const bool wide = (nq / kCellQueries) / std::max(n_parts, 1) < 2 * slots;
-    auto kern = wide ? knn_cells_kernel<NV, 1> : knn_cells_kernel<NV, 2>;
-    const int threads = wide ? kCellQueries : kCellQueries / 2;
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+template <int NV, int QB, int KPL, int MINB>
+int launch_point(b200mp_knn *k, const double *d_q, const int *q_order, const int *q_cell, const int *q_start, long long nq, const long long *d_self,
+                 long long self_base, int use_self, int kk, long long *d_idx, double *d_dist, int *d_counts, cudaStream_t st, int parts, int part) {
+    auto kern = knn_point_kernel<NV, QB, KPL, MINB>;
+    int per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPointThreads, 0));
     const float err_scale = 4.0f * (4 * NV + 2) * 5.96e-8f;
-    // upper bound on the number of blocks (sum over cells of ceil(queries / kCellQueries)); surplus blocks exit at once
-    const unsigned grid = static_cast<unsigned>(nq / kCellQueries + k->index_P + 1);
-    kern<<<grid, threads, smem, st>>>(k->ix_feat, k->ix_pts, k->ix_orig, k->ix_start, k->ix_lo, k->ix_hi, k->index_P, k->dim, d_q, q_order,
-                                           q_start, blk_start, nq, d_self, self_base, use_self, kk, err_scale, k->cmax, d_partial,
-                                           k->d_rows_visited, getenv("B200MP_KNN_STAT_PAIRS") ? 1 : 0);
+    const int chunk = std::max(QB, getenv("B200MP_KNN_CHUNK") ? atoi(getenv("B200MP_KNN_CHUNK")) : 8) / QB * QB;
+    const long long warps_needed = (nq / std::max(parts, 1) + chunk - 1) / chunk + 1;
+    const long long blocks = std::max<long long>(1, std::min<long long>(static_cast<long long>(k->ctx->sm_count) * std::max(per_sm, 1),
+                                                                         (warps_needed + kPointThreads / 32 - 1) / (kPointThreads / 32)));
+    const bool want_stats = getenv("B200MP_KNN_STAT_PAIRS") != nullptr;
+    B200_CUDA(cudaMemsetAsync(k->d_point_ctl, 0, sizeof(unsigned long long), st));  // the work-queue head; statistics accumulate
+    kern<<<static_cast<unsigned>(blocks), kPointThreads, 0, st>>>(
+        k->ix_feat, k->ix_pts, k->ix_orig, k->ix_start, k->ix_box, k->ix_sbox, k->ix_mbox, k->index_P, k->dim, d_q, q_order, q_cell, q_start, nq, d_self,
+        self_base, use_self, kk, err_scale, k->cmax, knn_env_float("B200MP_KNN_TAU0", 0.3f), knn_env_float("B200MP_KNN_TAUG", 2.0f), parts, part, chunk,
+        d_idx, d_dist, d_counts, k->d_point_ctl, want_stats ? k->d_point_ctl + 1 : nullptr);
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(1);
     return B200MP_OK;
+}
+
+template <int NV>
+int launch_point_nv(b200mp_knn *k, int qb, const double *d_q, const int *q_order, const int *q_cell, const int *q_start, long long nq,
+                    const long long *d_self, long long self_base, int use_self, int kk, long long *d_idx, double *d_dist, int *d_counts, cudaStream_t st,
+                    int parts, int part) {
+#define B200_POINT(QB_, KPL_, MINB_) launch_point<NV, QB_, KPL_, MINB_>(k, d_q, q_order, q_cell, q_start, nq, d_self, self_base, use_self, kk, d_idx, d_dist, d_counts, st, parts, part)
+    const int minb = getenv("B200MP_KNN_MINB") ? atoi(getenv("B200MP_KNN_MINB")) : 4;
+    if (kk <= 32) {
+        if (qb == 1) return minb == 2 ? B200_POINT(1, 1, 2) : (minb == 3 ? B200_POINT(1, 1, 3) : B200_POINT(1, 1, 4));
+        return qb == 4 ? B200_POINT(4, 1, 1) : B200_POINT(2, 1, 2);
+    }
+    return qb == 1 ? B200_POINT(1, 2, 3) : B200_POINT(2, 2, 2);
+#undef B200_POINT
 }
 
 // large query batches against a large database: cell-pruned exact search
@@ -1233,7 +1369,7 @@ int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, co
     if (!k->index_valid || k->index_n != k->n)
         if ((rc = knn_build_index(k, st))) return rc;
     const int fw = k->nv * 4, P = k->index_P;
-    // temporaries: qfeat[nq][fw] | cell[nq] | pos[nq] | order[nq] | cell_sorted[nq] | counts[P] | start[P+1] | cursor[P] | partial[nq][kq]
+    // temporaries: qfeat[nq][fw] | cell[nq] | pos[nq] | order[nq] | cell_sorted[nq] | counts[P] | start[P+1] | cursor[P]
     const size_t a_q = align256(static_cast<size_t>(nq) * 4);
     size_t off = 0;
     const size_t o_feat = off; off += align256(static_cast<size_t>(nq) * fw * sizeof(float));
@@ -1244,17 +1380,12 @@ int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, co
     const size_t o_counts = off; off += align256(static_cast<size_t>(P) * 4);
     const size_t o_start = off; off += align256(static_cast<size_t>(P + 1) * 4);
     const size_t o_cursor = off; off += align256(static_cast<size_t>(P) * 4);
-    const size_t o_nblk = off; off += align256(static_cast<size_t>(P) * 4);
-    const size_t o_bstart = off; off += align256(static_cast<size_t>(P + 1) * 4);
-    const size_t o_partial = off; off += align256(static_cast<size_t>(nq) * kq * sizeof(Partial));
     if ((rc = k->scratch.reserve(off))) return rc;
     char *m = k->scratch.ptr;
     float *qfeat = reinterpret_cast<float *>(m + o_feat);
     int *cell = reinterpret_cast<int *>(m + o_cell), *pos = reinterpret_cast<int *>(m + o_pos);
     int *order = reinterpret_cast<int *>(m + o_order), *csort = reinterpret_cast<int *>(m + o_csort);
     int *counts = reinterpret_cast<int *>(m + o_counts), *start = reinterpret_cast<int *>(m + o_start), *cursor = reinterpret_cast<int *>(m + o_cursor);
-    int *nblk = reinterpret_cast<int *>(m + o_nblk), *bstart = reinterpret_cast<int *>(m + o_bstart);
-    Partial *partial = reinterpret_cast<Partial *>(m + o_partial);
     const unsigned qblocks = static_cast<unsigned>((nq + 255) / 256);
     knn_features_kernel<<<qblocks, 256, 0, st>>>(d_q, 0, nq, k->dim, fw, qfeat);
     B200_CUDA(cudaGetLastError());
@@ -1262,21 +1393,14 @@ int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, co
     if ((rc = knn_assign(k, qfeat, nq, cell, st))) return rc;
     if ((rc = knn_cell_sort(k, cell, nq, counts, start, cursor, pos, st))) return rc;
     knn_query_order_kernel<<<qblocks, 256, 0, st>>>(cell, pos, nq, order, csort);
-    knn_cell_blocks_kernel<<<(P + 255) / 256, 256, 0, st>>>(start, P, nblk, parts, part);
-    knn_cell_scan_kernel<<<1, 1024, 0, st>>>(nblk, P, bstart, cursor);
-    B200_CUDA(cudaGetLastError());
-    k->ctx->launches.fetch_add(3);
+    // query-major search: writes the sorted rows of its part's queries itself
+    const int qb = knn_warp_qpt();
     switch (k->nv) {
-        case 2: rc = launch_cells<2>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st, parts); break;
-        case 3: rc = launch_cells<3>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st, parts); break;
-        default: rc = launch_cells<6>(k, d_q, order, start, bstart, nq, d_self, self_base, use_self, kq, partial, st, parts); break;
+        case 2: rc = launch_point_nv<2>(k, qb, d_q, order, csort, start, nq, d_self, self_base, use_self, kq, d_idx, d_dist, d_counts, st, parts, part); break;
+        case 3: rc = launch_point_nv<3>(k, qb, d_q, order, csort, start, nq, d_self, self_base, use_self, kq, d_idx, d_dist, d_counts, st, parts, part); break;
+        default: rc = launch_point_nv<6>(k, qb, d_q, order, csort, start, nq, d_self, self_base, use_self, kq, d_idx, d_dist, d_counts, st, parts, part); break;
     }
-    if (rc) return rc;
-    knn_merge_kernel<<<static_cast<unsigned>((nq * 32 + 255) / 256), 256, 0, st>>>(partial, nq, kq, kq, d_idx, d_dist, d_counts, 1,
-                                                                                     parts > 1 ? cell : nullptr, parts, part);
-    B200_CUDA(cudaGetLastError());
-    k->ctx->launches.fetch_add(1);
-    return B200MP_OK;
+    return rc;
 }
 
 }  // namespace
@@ -1341,8 +1465,11 @@ int b200mp_knn_create(b200mp_ctx *ctx, int dim, int metric, b200mp_knn **out) {
     k->metric = metric;
     k->nv = dim <= 7 ? 2 : (dim <= 11 ? 3 : 6);
     if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&k->d_rows_visited, sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(k->d_rows_visited, 0, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMemset(k->d_rows_visited, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&k->d_point_ctl, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(k->d_point_ctl, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) {
         cudaGetLastError();
+        if (k->d_rows_visited) cudaFree(k->d_rows_visited);
         delete k;
         return fail(B200MP_ERR_CUDA, "b200mp_knn_create: device allocation failed");
     }
@@ -1385,6 +1512,7 @@ void b200mp_knn_destroy(b200mp_knn *k) {
     k->index_mem.release();
     k->index_tmp.release();
     if (k->d_rows_visited) cudaFree(k->d_rows_visited);
+    if (k->d_point_ctl) cudaFree(k->d_point_ctl);
     delete k;
 }
 
@@ -1400,7 +1528,19 @@ int64_t b200mp_knn_rows_visited(b200mp_knn *k) {
     cudaSetDevice(k->ctx->device);
     cudaStreamSynchronize(k->ctx->stream);
     if (cudaMemcpy(&v, k->d_rows_visited, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    return static_cast<int64_t>(v);
+    unsigned long long p = 0;
+    if (k->d_point_ctl && cudaMemcpy(&p, k->d_point_ctl + 1, sizeof(p), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return static_cast<int64_t>(v + p);
+}
+
+int b200mp_knn_search_stats(b200mp_knn *k, int64_t *out) {
+    if (!k || !out) return fail(B200MP_ERR_INVALID, "b200mp_knn_search_stats: NULL argument");
+    unsigned long long v[4] = {0, 0, 0, 0};
+    B200_CUDA(cudaSetDevice(k->ctx->device));
+    B200_CUDA(cudaStreamSynchronize(k->ctx->stream));
+    if (k->d_point_ctl) B200_CUDA(cudaMemcpy(v, k->d_point_ctl + 1, sizeof(v), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) out[i] = static_cast<int64_t>(v[i]);
+    return B200MP_OK;
 }
 
 int b200mp_knn_clear(b200mp_knn *k) {

@@ -104,6 +104,7 @@ def load_library():
     L.b200mp_knn_set_index.argtypes = [_vp, C.c_int]
     L.b200mp_knn_rows_visited.argtypes = [_vp]
     L.b200mp_knn_rows_visited.restype = _i64
+    L.b200mp_knn_search_stats.argtypes = [_vp, _vp]
     L.b200mp_knn_size.argtypes = [_vp]
     L.b200mp_knn_size.restype = _i64
     L.b200mp_knn_add.argtypes = [_vp, _vp, _i64, C.POINTER(_i64)]
@@ -395,6 +396,12 @@ class NearestNeighbors:
 
     def rows_visited(self) -> int:
         return int(self._L.b200mp_knn_rows_visited(self._h))
+
+    def search_stats(self) -> dict:
+        """Counters of the cell-index search (collected only while B200MP_KNN_STAT_PAIRS is set)."""
+        out = np.zeros(4, np.int64)
+        _check(self._L.b200mp_knn_search_stats(self._h, out.ctypes.data))
+        return dict(pairs=int(out[0]), exact=int(out[1]), insertions=int(out[2]), leaf_visits=int(out[3]))
 
     def set_index(self, enable: bool):
         """Cell-index pruning for large batches on/off (b200mp_knn_set_index)."""
