@@ -123,7 +123,7 @@ def run_reference(args):
     print(json.dumps(line), file=claim_stdout(), flush=True)
 
 
-def roadmap_parity(states, edges, valid, nbr, dst, scene, cores, knn_queries=4096, max_edges=0):
+def roadmap_parity(states, edges, valid, nbr, scene, cores, knn_queries=4096, max_edges=0):
     """North-star parity of a built roadmap against the compiled reference (oracle/_ref), on the host cores:
     every edge through the unmodified vamp::planning::validate_motion<Panda, 8, 32> (validate.hh:69-77) and a spread sample of
     queries through the unmodified NearestNeighborsLinear::nearestK (NearestNeighborsLinear.h:119-132). Differing edge decisions are
@@ -154,7 +154,12 @@ def roadmap_parity(states, edges, valid, nbr, dst, scene, cores, knn_queries=409
     t0 = time.perf_counter()
     ri, rd = refnn.nearest_k(db, db[ids], k, nthreads=cores, exclude_ids=ids)
     dtk = time.perf_counter() - t0
-    gi, gd = nbr[ids], dst[ids]
+    gi = nbr[ids].astype(np.int64)
+    gd2 = np.zeros(gi.shape)  # distances of the reported neighbours, accumulated in the reference's order (RealVectorStateSpace.cpp:230-242)
+    for j in range(db.shape[1]):
+        diff = db[gi, j] - db[ids, j][:, None]
+        gd2 += diff * diff
+    gd = np.sqrt(gd2)
     same_order = (gi == ri).all(axis=1)
     same_set = np.array([set(a) == set(b) for a, b in zip(gi, ri)])
     rel = np.abs(gd - rd) / np.maximum(rd, 1e-300)
@@ -274,31 +279,40 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # ---- roadmap build (all ranks): BASELINE config 3, same scene
+    # ---- roadmap build (all ranks): BASELINE config 3, same scene, through the C library's collective entry point
+    # (b200mp_prm_build_multi: NCCL exchanges inside the library; torch.distributed only carries the NCCL unique id)
     roadmap, rm_host = None, None
     if args.roadmap_n > 0:
-        from ompl_b200.roadmap import EngineBackend, RoadmapBuilder
-        builder = RoadmapBuilder(EngineBackend(ctx, env, "panda"))
-        w = builder.build(args.roadmap_n, 16, 42)  # warm-up = the timed build itself, like the warm-up steps above (grow-only buffers, memory pool, NCCL channels)
-        del w
+        from ompl_b200.roadmap import build_roadmap, make_comm
+        comm = make_comm(ctx)
+        build_roadmap(comm, env, "panda", args.roadmap_n, 16, 42, want_arrays=False)  # warm-up = the timed build itself (grow-only buffers, memory pool, NCCL channels)
         barrier()
         l0 = ctx.launch_count
-        rm = builder.build(args.roadmap_n, 16, 42)
+        rm = build_roadmap(comm, env, "panda", args.roadmap_n, 16, 42, want_arrays=False)
         barrier()
         st = dict(rm.stats)
+        launches_rm = int(ctx.launch_count - l0)
         keys = ["ms_sample", "ms_knn", "ms_edges", "ms_validate", "ms_gather", "ms_total"]
         t = torch.tensor([st[k] for k in keys], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         for k, v in zip(keys, t.tolist()):
             st[k] = round(v, 3)
-        roadmap = {"workload": f"{args.roadmap_n} valid Panda samples, k=16, C2 scene, 1 warm-up build", "n_gpus": world, "scaling": "strong",
-                   "build_ms": st["ms_total"], "gpu_launches": int(ctx.launch_count - l0)}
+        # the same build once more, end to end: wall clock around the C call, the whole roadmap copied to rank 0's host memory
+        barrier()
+        t0 = time.perf_counter()
+        rm = build_roadmap(comm, env, "panda", args.roadmap_n, 16, 42, want_arrays=(rank == 0), want_neighbors=(rank == 0))
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        assert rm.stats["n_edges"] == st["n_edges"] and rm.stats["n_valid_edges"] == st["n_valid_edges"], "roadmap builds disagree"
+        roadmap = {"workload": f"{args.roadmap_n} valid Panda samples, k=16, C2 scene, b200mp_prm_build_multi, 1 warm-up build", "n_gpus": world,
+                   "scaling": "strong", "build_ms": st["ms_total"], "build_e2e_ms": round(e2e_ms, 3), "gpu_launches": launches_rm}
         roadmap.update({k: st[k] for k in ("n_states", "n_candidates", "n_edges", "n_valid_edges", "ms_sample", "ms_knn", "ms_edges",
                                            "ms_validate", "ms_gather")})
         if rank == 0 and not args.no_parity:
-            rm_host = tuple(x.cpu().numpy() for x in (rm.states, rm.edges, rm.valid, rm.neighbors, rm.neighbor_dist))
+            rm_host = tuple(x.numpy() for x in (rm.states, rm.edges, rm.valid, rm.neighbors))
         del rm
+        comm.close()
 
     if world > 1:
         dist.destroy_process_group()  # nothing below is collective: rank 0 alone finishes the report

@@ -38,13 +38,14 @@
 extern "C" {
 #endif
 
-#define B200MP_VERSION 1
+#define B200MP_VERSION 2
 
 typedef struct b200mp_ctx b200mp_ctx;
 typedef struct b200mp_env b200mp_env;
 typedef struct b200mp_knn b200mp_knn;
 typedef struct b200mp_capt b200mp_capt;
 typedef struct b200mp_chain b200mp_chain;
+typedef struct b200mp_comm b200mp_comm;
 
 enum {
     B200MP_OK = 0,
@@ -62,7 +63,7 @@ enum { B200MP_METRIC_L2 = 0, B200MP_METRIC_CHAIN = 1 };
 int b200mp_version(void);
 const char *b200mp_last_error(void);
 
-/* ---- context: one per GPU (one process per GPU in multi-GPU jobs) -------------------------------------------- */
+/* ---- context: one per GPU (several GPUs: one context each, grouped by b200mp_comm_*, see below) ----------------- */
 int b200mp_create(int device, b200mp_ctx **out);
 void b200mp_destroy(b200mp_ctx *ctx);
 int b200mp_device(const b200mp_ctx *ctx, int *device, int *sm_count);
@@ -196,6 +197,11 @@ int b200mp_knn_query_device_f32(b200mp_knn *knn, const float *d_q, int64_t nq, i
  * max / min reduction. Every rank must hold the same database. */
 int b200mp_knn_query_part_device_f32(b200mp_knn *knn, const float *d_q, int64_t nq, int k, int64_t self_base, int exclude_self, int part,
                                      int n_parts, int64_t *d_idx, double *d_dist, void *stream);
+/* The same sharing for roadmap construction: only the neighbour ids, as int32, into d_ids[nq][k] (rows of other parts untouched;
+ * a table pre-filled with -1 combines across GPUs with ONE element-wise max all-reduce of nq * k * 4 bytes). Always answered
+ * through the cell index, whatever the batch size. k <= 64. */
+int b200mp_knn_query_part_ids_device_f32(b200mp_knn *knn, const float *d_q, int64_t nq, int k, int64_t self_base, int exclude_self, int part,
+                                         int n_parts, int32_t *d_ids, void *stream);
 /* nearestR: all points with distance <= radius, ascending; *count = how many exist, at most cap are written.
  * radius = +inf gives the exhaustive sorted list used for nearestK with k >= size. */
 int b200mp_knn_radius(b200mp_knn *knn, const double *q, double radius, int64_t *idx, double *dist, int64_t cap, int64_t *count);
@@ -224,10 +230,16 @@ int b200mp_chain_check_motions_device(b200mp_chain *chain, const double *d_a, co
 /* ---- batched PRM roadmap construction ------------------------------------------------------------------------- */
 /* Replaces the per-milestone loop of ompl::geometric::PRM (growRoadmap / addMilestone,
  * src/ompl/geometric/planners/prm/src/PRM.cpp:240-270,570-604; KStrategy, ConnectionStrategy.h:78-82) by one pass
- * per phase over the whole batch: sample -> state validity -> kNN (self excluded) -> edge list -> edge validity. */
+ * per phase over the whole batch: sample -> state validity -> kNN (self excluded) -> edge list -> edge validity.
+ * NOT the graph stock PRM grows from the same states: addMilestone queries only the milestones inserted EARLIER (it asks
+ * before nn_->add(m), PRM.cpp:583,601), the batch connects every state to its k nearest among ALL n states and stores the
+ * union as undirected edges -- a denser, insertion-order independent k-NN graph (the s-PRM construction). Edge direction
+ * (older -> newer milestone) and the motion checks themselves are the reference's. */
 typedef struct b200mp_roadmap_stats {
     int64_t n_states, n_candidates, n_edges, n_valid_edges;
-    double ms_sample, ms_knn, ms_edges, ms_validate, ms_total; /* device time per phase (CUDA events) */
+    double ms_sample, ms_knn, ms_edges, ms_validate, ms_total; /* device time per phase on the calling rank (CUDA events) */
+    double ms_gather;                                          /* final exchange of the ranks' edge lists (0 on one GPU) */
+    int64_t n_local_edges;                                     /* edges this rank listed and validated */
 } b200mp_roadmap_stats;
 /* Phase 1. Candidates cand_first .. cand_first + cand_count - 1 of the sample stream of `seed` (candidate c is a pure
  * function of (seed, c): Philox4x32-10 -> uniform in the robot's joint box) are validated and the valid ones are
@@ -242,11 +254,36 @@ int b200mp_prm_sample_device(b200mp_ctx *ctx, int robot, const b200mp_env *env, 
  * (both may be NULL). Synchronises `stream`. */
 int b200mp_prm_edges_device(b200mp_ctx *ctx, const int64_t *d_nbr, const double *d_dist_local, int64_t n, int k, int64_t q_first,
                             int64_t q_count, int32_t *d_edges, double *d_weights, int64_t capacity, int64_t *n_edges, void *stream);
-/* All phases on one GPU (phase 2 = b200mp_knn_add_device_f32 + b200mp_knn_query_device_f32, phase 4 =
- * b200mp_validate_edges_device). Host outputs (any may be NULL): states[n][dim], edges[edge_capacity][2],
- * valid[edge_capacity], weights[edge_capacity]; n * k always suffices for edge_capacity. */
+/* All phases on one GPU. Host outputs (any may be NULL): states[n][dim], edges[edge_capacity][2], valid[edge_capacity],
+ * weights[edge_capacity] (edge length, the reference's double); n * k always suffices for edge_capacity. k <= 64. */
 int b200mp_prm_build(b200mp_ctx *ctx, int robot, const b200mp_env *env, uint64_t seed, int64_t n, int k, int resolution, float *states,
                      int32_t *edges, uint8_t *valid, double *weights, int64_t edge_capacity, b200mp_roadmap_stats *stats);
+
+/* ---- several GPUs of one node ------------------------------------------------------------------------------------- */
+/* A b200mp_comm is one rank of a group of GPUs: a context plus an NCCL communicator (libnccl.so.2 is loaded when the first
+ * group is made; without it these calls fail with B200MP_ERR_STATE, single-GPU use never needs it). Two ways to form a group:
+ *   one process per GPU (MPI / torchrun style): rank 0 calls b200mp_comm_unique_id, the bytes reach the other processes by any
+ *     means, every process calls b200mp_comm_create(ctx, id, rank, world);
+ *   one process, one thread per GPU: b200mp_comm_create_all(ctxs, n, comms) (ncclCommInitAll), each thread then drives its rank.
+ * b200mp_prm_build_multi is collective: every rank calls it with the same robot / seed / n / k / resolution and an environment
+ * holding the same scene on its own context (b200mp_env_clone copies one across contexts). Rank r samples and validates a
+ * contiguous slice of every round of the candidate stream (all-gather of the valid states), answers the nearest-neighbour
+ * queries of a share of the states (whole leaves of the k-d index; ONE int32 max all-reduce of n k 4 bytes merges the tables),
+ * lists and validates the edges of the states r B .. (r + 1) B - 1, B = ceil(n / world), and an all-gather leaves the whole
+ * roadmap on every rank. The result is identical for every world size, and equal to b200mp_prm_build's. `neighbors` receives the
+ * nearest-neighbour table the edges were derived from (ids ascending by (distance, id), self excluded). */
+#define B200MP_UNIQUE_ID_BYTES 128
+int b200mp_comm_unique_id(void *id, size_t bytes);
+int b200mp_comm_create(b200mp_ctx *ctx, const void *unique_id, int rank, int world, b200mp_comm **out);
+int b200mp_comm_create_all(b200mp_ctx *const *ctxs, int n, b200mp_comm **out /* [n] */);
+void b200mp_comm_destroy(b200mp_comm *comm);
+int b200mp_comm_rank(const b200mp_comm *comm, int *rank, int *world);
+int b200mp_prm_build_multi(b200mp_comm *comm, int robot, const b200mp_env *env, uint64_t seed, int64_t n, int k, int resolution,
+                           float *states, int32_t *edges, uint8_t *valid, double *weights, int32_t *neighbors /* [n][min(k, n - 1)], may be NULL */,
+                           int64_t edge_capacity, b200mp_roadmap_stats *stats);
+/* A copy of `src` (primitive shapes, grid setting; scenes with point clouds or height fields are refused with
+ * B200MP_ERR_CAPACITY) on another context, committed when `src` is. */
+int b200mp_env_clone(const b200mp_env *src, b200mp_ctx *dst_ctx, b200mp_env **out);
 
 /* FP32 FMA micro-benchmark used as the measured roofline denominator of the collision kernels:
  * runs `iters` dependent-chain FFMA blocks on every SM and returns achieved TFLOP/s. */

@@ -264,6 +264,7 @@ void b200mp_destroy(b200mp_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->self_comm) b200mp_comm_destroy(static_cast<b200mp_comm *>(c->self_comm));
     c->scratch.release();
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->h_small) cudaFreeHost(c->h_small);
@@ -539,6 +540,27 @@ int b200mp_env_add_pointcloud_device(b200mp_env *e, const float *xyz, int64_t n,
     e->ctx->launches.fetch_add(launches + 4);
     cudaFree(d_xyz); cudaFree(node); cudaFree(box_a); cudaFree(box_b); cudaFree(cells); cudaFree(hist); cudaFree(ext); cudaFree(d_top); cudaFree(counts8);
     return env_attach_capt(e, d, nlog2, n_aff8, top, r_point);
+}
+
+int b200mp_env_clone(const b200mp_env *src, b200mp_ctx *dst_ctx, b200mp_env **out) {
+    if (!src || !dst_ctx || !out) return fail(B200MP_ERR_INVALID, "b200mp_env_clone: NULL argument");
+    *out = nullptr;
+    if (!src->pcs.empty() || !src->hfs.empty())
+        return fail(B200MP_ERR_CAPACITY, "b200mp_env_clone: scenes with point clouds or height fields own device arrays and are not cloned");
+    auto *e = new b200mp_env();
+    e->ctx = dst_ctx;
+    e->spheres = src->spheres;
+    e->capsules = src->capsules;
+    e->zcapsules = src->zcapsules;
+    e->cuboids = src->cuboids;
+    e->zcuboids = src->zcuboids;
+    e->use_grid = src->use_grid;
+    if (src->committed) {
+        const int rc = b200mp_env_commit(e);
+        if (rc) { b200mp_env_destroy(e); return rc; }
+    }
+    *out = e;
+    return B200MP_OK;
 }
 
 int b200mp_env_set_grid(b200mp_env *e, int enable) {

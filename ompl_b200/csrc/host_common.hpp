@@ -64,5 +64,7 @@ struct b200mp_ctx {
     size_t small_cap = 0;
     b200mp::Scratch scratch;
     std::mutex mu;
+    std::mutex build_mu;        // one roadmap build at a time per context
+    void *self_comm = nullptr;  // group of one used by b200mp_prm_build (a b200mp_comm, created on first use)
     std::atomic<long long> launches{0};
 };

@@ -576,7 +576,7 @@ knn_point_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
                  const double *__restrict__ q64, const int *__restrict__ q_order, const int *__restrict__ q_cell, const int *__restrict__ q_start,
                  long long nq, const long long *__restrict__ self_ids, long long self_base, int use_self, int kk, float err_scale, float cmax,
                  float tau0_frac, float tau_growth, int parts, int part, int chunk, long long *__restrict__ out_idx, double *__restrict__ out_dist,
-                 int *__restrict__ out_counts, unsigned long long *__restrict__ work_head, unsigned long long *__restrict__ stats) {
+                 int *__restrict__ out_idx32, int *__restrict__ out_counts, unsigned long long *__restrict__ work_head, unsigned long long *__restrict__ stats) {
     constexpr int W = kPointThreads / 32;
     constexpr int FW = 4 * NV;
     __shared__ unsigned short s_f2[W][kF2Cap];
@@ -891,8 +891,9 @@ knn_point_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
                 for (int e = 0; e < KPL; ++e) {
                     const bool real = lid[b][e] != -2;
                     if (real) {
-                        out_idx[qi[b] * kk + rank[e]] = lid[b][e];
-                        out_dist[qi[b] * kk + rank[e]] = lid[b][e] >= 0 ? sqrt(ld2[b][e]) : INFINITY;
+                        if (out_idx) out_idx[qi[b] * kk + rank[e]] = lid[b][e];
+                        if (out_dist) out_dist[qi[b] * kk + rank[e]] = lid[b][e] >= 0 ? sqrt(ld2[b][e]) : INFINITY;
+                        if (out_idx32) out_idx32[qi[b] * kk + rank[e]] = lid[b][e];
                     }
                     found += __popc(__ballot_sync(kFullMask, real && lid[b][e] >= 0));
                 }
@@ -1328,7 +1329,7 @@ int knn_build_index(b200mp_knn *k, cudaStream_t st) {
 
 template <int NV, int QB, int KPL, int MINB>
 int launch_point(b200mp_knn *k, const double *d_q, const int *q_order, const int *q_cell, const int *q_start, long long nq, const long long *d_self,
-                 long long self_base, int use_self, int kk, long long *d_idx, double *d_dist, int *d_counts, cudaStream_t st, int parts, int part) {
+                 long long self_base, int use_self, int kk, long long *d_idx, double *d_dist, int *d_idx32, int *d_counts, cudaStream_t st, int parts, int part) {
     auto kern = knn_point_kernel<NV, QB, KPL, MINB>;
     int per_sm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPointThreads, 0));
@@ -1342,7 +1343,7 @@ int launch_point(b200mp_knn *k, const double *d_q, const int *q_order, const int
     kern<<<static_cast<unsigned>(blocks), kPointThreads, 0, st>>>(
         k->ix_feat, k->ix_pts, k->ix_orig, k->ix_start, k->ix_box, k->ix_sbox, k->ix_mbox, k->index_P, k->dim, d_q, q_order, q_cell, q_start, nq, d_self,
         self_base, use_self, kk, err_scale, k->cmax, knn_env_float("B200MP_KNN_TAU0", 0.3f), knn_env_float("B200MP_KNN_TAUG", 2.0f), parts, part, chunk,
-        d_idx, d_dist, d_counts, k->d_point_ctl, want_stats ? k->d_point_ctl + 1 : nullptr);
+        d_idx, d_dist, d_idx32, d_counts, k->d_point_ctl, want_stats ? k->d_point_ctl + 1 : nullptr);
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(1);
     return B200MP_OK;
@@ -1350,9 +1351,9 @@ int launch_point(b200mp_knn *k, const double *d_q, const int *q_order, const int
 
 template <int NV>
 int launch_point_nv(b200mp_knn *k, int qb, const double *d_q, const int *q_order, const int *q_cell, const int *q_start, long long nq,
-                    const long long *d_self, long long self_base, int use_self, int kk, long long *d_idx, double *d_dist, int *d_counts, cudaStream_t st,
-                    int parts, int part) {
-#define B200_POINT(QB_, KPL_, MINB_) launch_point<NV, QB_, KPL_, MINB_>(k, d_q, q_order, q_cell, q_start, nq, d_self, self_base, use_self, kk, d_idx, d_dist, d_counts, st, parts, part)
+                    const long long *d_self, long long self_base, int use_self, int kk, long long *d_idx, double *d_dist, int *d_idx32, int *d_counts,
+                    cudaStream_t st, int parts, int part) {
+#define B200_POINT(QB_, KPL_, MINB_) launch_point<NV, QB_, KPL_, MINB_>(k, d_q, q_order, q_cell, q_start, nq, d_self, self_base, use_self, kk, d_idx, d_dist, d_idx32, d_counts, st, parts, part)
     const int minb = getenv("B200MP_KNN_MINB") ? atoi(getenv("B200MP_KNN_MINB")) : 4;
     if (kk <= 32) {
         if (qb == 1) return minb == 2 ? B200_POINT(1, 1, 2) : (minb == 3 ? B200_POINT(1, 1, 3) : B200_POINT(1, 1, 4));
@@ -1364,7 +1365,7 @@ int launch_point_nv(b200mp_knn *k, int qb, const double *d_q, const int *q_order
 
 // large query batches against a large database: cell-pruned exact search
 int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, const long long *d_self, long long self_base, int use_self,
-                      long long *d_idx, double *d_dist, int *d_counts, cudaStream_t st, int parts = 1, int part = 0) {
+                      long long *d_idx, double *d_dist, int *d_counts, cudaStream_t st, int parts = 1, int part = 0, int *d_idx32 = nullptr) {
     int rc;
     if (!k->index_valid || k->index_n != k->n)
         if ((rc = knn_build_index(k, st))) return rc;
@@ -1396,9 +1397,9 @@ int knn_query_indexed(b200mp_knn *k, const double *d_q, long long nq, int kq, co
     // query-major search: writes the sorted rows of its part's queries itself
     const int qb = knn_warp_qpt();
     switch (k->nv) {
-        case 2: rc = launch_point_nv<2>(k, qb, d_q, order, csort, start, nq, d_self, self_base, use_self, kq, d_idx, d_dist, d_counts, st, parts, part); break;
-        case 3: rc = launch_point_nv<3>(k, qb, d_q, order, csort, start, nq, d_self, self_base, use_self, kq, d_idx, d_dist, d_counts, st, parts, part); break;
-        default: rc = launch_point_nv<6>(k, qb, d_q, order, csort, start, nq, d_self, self_base, use_self, kq, d_idx, d_dist, d_counts, st, parts, part); break;
+        case 2: rc = launch_point_nv<2>(k, qb, d_q, order, csort, start, nq, d_self, self_base, use_self, kq, d_idx, d_dist, d_idx32, d_counts, st, parts, part); break;
+        case 3: rc = launch_point_nv<3>(k, qb, d_q, order, csort, start, nq, d_self, self_base, use_self, kq, d_idx, d_dist, d_idx32, d_counts, st, parts, part); break;
+        default: rc = launch_point_nv<6>(k, qb, d_q, order, csort, start, nq, d_self, self_base, use_self, kq, d_idx, d_dist, d_idx32, d_counts, st, parts, part); break;
     }
     return rc;
 }
@@ -1704,6 +1705,25 @@ int b200mp_knn_query_part_device_f32(b200mp_knn *k, const float *d_q, int64_t nq
     k->ctx->launches.fetch_add(1);
     // queries are shared out by the index cell they fall into (cell c -> part c mod n_parts): every part works on whole cells
     return knn_query_indexed(k, d_q64, nq, kq, nullptr, self_base, exclude_self, reinterpret_cast<long long *>(d_idx), d_dist, nullptr, st, n_parts, part);
+}
+
+int b200mp_knn_query_part_ids_device_f32(b200mp_knn *k, const float *d_q, int64_t nq, int kq, int64_t self_base, int exclude_self, int part, int n_parts,
+                                         int32_t *d_ids, void *stream) {
+    if (!k || nq < 0 || kq < 1 || n_parts < 1 || part < 0 || part >= n_parts || (nq > 0 && (!d_q || !d_ids)))
+        return fail(B200MP_ERR_INVALID, "b200mp_knn_query_part_ids_device_f32: bad argument");
+    if (nq == 0) return B200MP_OK;
+    if (kq > 64) return fail(B200MP_ERR_CAPACITY, "b200mp_knn_query_part_ids_device_f32: k %d > 64", kq);
+    if (k->metric != B200MP_METRIC_L2 || k->n > 0x7fffffffLL) return fail(B200MP_ERR_INVALID, "b200mp_knn_query_part_ids_device_f32: L2 containers only");
+    B200_CUDA(cudaSetDevice(k->ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : k->ctx->stream;
+    const long long cnt = static_cast<long long>(nq) * k->dim;
+    int rc = k->qscratch.reserve(static_cast<size_t>(cnt) * sizeof(double));
+    if (rc) return rc;
+    double *d_q64 = reinterpret_cast<double *>(k->qscratch.ptr);
+    knn_f32_to_f64_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(d_q, cnt, d_q64);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(1);
+    return knn_query_indexed(k, d_q64, nq, kq, nullptr, self_base, exclude_self, nullptr, nullptr, nullptr, st, n_parts, part, d_ids);
 }
 
 int b200mp_knn_query(b200mp_knn *k, const double *q, int64_t nq, int kq, const int64_t *self_ids, int64_t *idx, double *dist, int *counts) {

@@ -19,7 +19,7 @@ class RoadmapStats(C.Structure):
     """b200mp_roadmap_stats (include/b200mp.h)."""
     _fields_ = [("n_states", _i64), ("n_candidates", _i64), ("n_edges", _i64), ("n_valid_edges", _i64),
                 ("ms_sample", C.c_double), ("ms_knn", C.c_double), ("ms_edges", C.c_double), ("ms_validate", C.c_double),
-                ("ms_total", C.c_double)]
+                ("ms_total", C.c_double), ("ms_gather", C.c_double), ("n_local_edges", _i64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -81,6 +81,15 @@ def load_library():
     L.b200mp_prm_edges_device.argtypes = [_vp, _vp, _vp, _i64, C.c_int, _i64, _i64, _vp, _vp, _i64, C.POINTER(_i64), _vp]
     L.b200mp_prm_build.argtypes = [_vp, C.c_int, _vp, C.c_uint64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _i64,
                                    C.POINTER(RoadmapStats)]
+    L.b200mp_comm_unique_id.argtypes = [_vp, C.c_size_t]
+    L.b200mp_comm_create.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]
+    L.b200mp_comm_create_all.argtypes = [_vp, C.c_int, _vp]
+    L.b200mp_comm_destroy.argtypes = [_vp]
+    L.b200mp_comm_rank.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.b200mp_prm_build_multi.argtypes = [_vp, C.c_int, _vp, C.c_uint64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64,
+                                         C.POINTER(RoadmapStats)]
+    L.b200mp_env_clone.argtypes = [_vp, _vp, C.POINTER(_vp)]
+    L.b200mp_knn_query_part_ids_device_f32.argtypes = [_vp, _vp, _i64, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.b200mp_knn_query_device_f32.argtypes = [_vp, _vp, _i64, C.c_int, _i64, C.c_int, _vp, _vp, _vp, _vp]
     L.b200mp_knn_query_part_device_f32.argtypes = [_vp, _vp, _i64, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
     L.b200mp_chain_horn_environment.argtypes = [C.c_int, C.c_double, _vp, C.POINTER(C.c_int)]
@@ -284,6 +293,62 @@ class Context:
                     weights=weights[:e].copy() if want_weights else None, stats=st.as_dict())
 
 
+UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """b200mp_comm_unique_id: made by rank 0, handed to the other ranks by any means (torch.distributed, MPI, a file)."""
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    _check(load_library().b200mp_comm_unique_id(buf, UNIQUE_ID_BYTES))
+    return buf.raw
+
+
+class Comm:
+    """One rank of a group of GPUs (b200mp_comm): the context of this process's GPU + an NCCL communicator."""
+
+    def __init__(self, ctx: Context, unique_id: bytes | None, rank: int, world: int):
+        self._L = load_library()
+        self._ctx = ctx
+        h = _vp()
+        idbuf = C.create_string_buffer(unique_id, UNIQUE_ID_BYTES) if unique_id is not None else None
+        _check(self._L.b200mp_comm_create(ctx._h, idbuf, rank, world, C.byref(h)))
+        self._h = h
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._L.b200mp_comm_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def prm_build(self, robot: str, env: "Environment", n: int, k: int, seed: int, resolution: int = 0, want_arrays: bool = True,
+                  want_weights: bool = True, want_neighbors: bool = False):
+        """Collective roadmap build (b200mp_prm_build_multi); every rank receives the whole roadmap when want_arrays."""
+        dim = robot_info(robot)["dim"]
+        cap = n * k
+        st = RoadmapStats()
+        if not want_arrays:
+            _check(self._L.b200mp_prm_build_multi(self._h, ROBOTS[robot], env._h, seed, n, k, resolution, None, None, None, None, None, cap,
+                                                  C.byref(st)))
+            return dict(stats=st.as_dict())
+        states = np.empty((n, dim), np.float32)
+        edges = np.empty((cap, 2), np.int32)
+        valid = np.empty(cap, np.uint8)
+        weights = np.empty(cap, np.float64) if want_weights else None
+        nbr = np.empty((n, min(k, n - 1)), np.int32) if want_neighbors and n > 1 else None
+        _check(self._L.b200mp_prm_build_multi(self._h, ROBOTS[robot], env._h, seed, n, k, resolution, states.ctypes.data, edges.ctypes.data,
+                                              valid.ctypes.data, weights.ctypes.data if want_weights else None,
+                                              nbr.ctypes.data if nbr is not None else None, cap, C.byref(st)))
+        e = int(st.n_edges)
+        return dict(states=states, edges=edges[:e].copy(), valid=valid[:e].copy(),
+                    weights=weights[:e].copy() if want_weights else None, neighbors=nbr, stats=st.as_dict())
+
+
 class Environment:
     """Mirror of vamp::collision::Environment<float> (collision/environment.hh:14-85): shape lists per class,
     `sort()` by min_distance, then `commit()` uploads the scene to the GPU."""
@@ -455,6 +520,11 @@ class NearestNeighbors:
                          exclude_self: bool = False, counts_ptr: int = 0, stream: int = 0):
         _check(self._L.b200mp_knn_query_device_f32(self._h, q_ptr, nq, k, self_base, int(exclude_self), idx_ptr, dist_ptr,
                                                    counts_ptr or None, stream or None))
+
+    def query_part_ids_device_f32(self, q_ptr: int, nq: int, k: int, ids_ptr: int, part: int, n_parts: int, self_base: int = 0,
+                                  exclude_self: bool = False, stream: int = 0):
+        _check(self._L.b200mp_knn_query_part_ids_device_f32(self._h, q_ptr, nq, k, self_base, int(exclude_self), part, n_parts, ids_ptr,
+                                                            stream or None))
 
     def query_part_device_f32(self, q_ptr: int, nq: int, k: int, idx_ptr: int, dist_ptr: int, part: int, n_parts: int, self_base: int = 0,
                               exclude_self: bool = False, stream: int = 0):

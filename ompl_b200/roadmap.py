@@ -28,7 +28,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .engine import Context, Environment, NearestNeighbors, robot_info
+from .engine import Comm, Context, Environment, NearestNeighbors, comm_unique_id, robot_info
 
 
 @dataclass
@@ -49,8 +49,33 @@ class Roadmap:
                     weights=self.weights[keep].cpu().numpy())
 
 
+def make_comm(ctx: Context, group=None) -> Comm:
+    """This process's rank of the GPU group behind b200mp_prm_build_multi: rank 0 makes the NCCL unique id, torch.distributed (any
+    backend) carries its 128 bytes to the other processes, every process joins with b200mp_comm_create. Without an initialised
+    process group the group has one member and no NCCL is involved."""
+    rank, world = _world(group)
+    if world == 1:
+        return Comm(ctx, None, 0, 1)
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return Comm(ctx, box[0], rank, world)
+
+
+def build_roadmap(comm: Comm, env: Environment, robot: str, n: int, k: int, seed: int, resolution: int = 0, want_arrays: bool = True,
+                  want_neighbors: bool = False) -> "Roadmap":
+    """The whole build inside the C library (b200mp_prm_build_multi): collective over the ranks of `comm`, NCCL exchanges included.
+    Returns host tensors (every rank holds the whole roadmap) or, with want_arrays = False, only the statistics."""
+    r = comm.prm_build(robot, env, n, k, seed, resolution, want_arrays=want_arrays, want_neighbors=want_neighbors)
+    st = dict(r["stats"], world=comm.world)
+    if not want_arrays:
+        return Roadmap(None, None, None, None, st)
+    nb = torch.from_numpy(r["neighbors"]) if r.get("neighbors") is not None else None
+    return Roadmap(torch.from_numpy(r["states"]), torch.from_numpy(r["edges"]), torch.from_numpy(r["valid"]), torch.from_numpy(r["weights"]), st, nb)
+
+
 class EngineBackend:
-    """The four roadmap phases on one GPU through the C ABI."""
+    """The four roadmap phases on one GPU through the C ABI (the torch.distributed front-end of RoadmapBuilder; the C library's own
+    collective build is build_roadmap above)."""
 
     def __init__(self, ctx: Context, env: Environment, robot: str):
         self.ctx, self.env, self.robot = ctx, env, robot

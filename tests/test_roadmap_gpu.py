@@ -120,3 +120,103 @@ def test_two_gpu_nccl_roadmap_equals_single_gpu(ctx):
         np.testing.assert_array_equal(o[2], one["edges"])
         np.testing.assert_array_equal(o[3], one["valid"])
         np.testing.assert_array_equal(o[4], one["weights"])
+
+
+# ---- the C library's own collective build (b200mp_prm_build_multi): NCCL inside the library ------------------------------------
+def _cabi_worker(rank, world, uid_q, out_q, n, k, seed):
+    c = ompl_b200.Context(rank)
+    env = synth.fill_env(ompl_b200.Environment(c), synth.cage_scene())
+    uid = uid_q.get(timeout=120)
+    comm = ompl_b200.Comm(c, uid, rank, world)
+    r = comm.prm_build("panda", env, n, k, seed, want_neighbors=True)
+    out_q.put((rank, r["states"], r["edges"], r["valid"], r["weights"], r["neighbors"], r["stats"]))
+    comm.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_c_abi_roadmap_equals_single_gpu(ctx):
+    """One process per GPU, the NCCL unique id handed over a queue: the roadmap equals b200mp_prm_build's on every rank."""
+    import torch.multiprocessing as mp
+    n, k, seed = 70001, 16, 9
+    env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
+    one = ctx.prm_build("panda", env, n, k, seed)
+    mpc = mp.get_context("spawn")
+    uid_q, out_q = mpc.Queue(), mpc.Queue()
+    uid = ompl_b200.comm_unique_id()
+    procs = [mpc.Process(target=_cabi_worker, args=(r, 2, uid_q, out_q, n, k, seed)) for r in range(2)]
+    for p in procs:
+        p.start()
+        uid_q.put(uid)
+    outs = [out_q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for o in outs:
+        np.testing.assert_array_equal(o[1], one["states"])
+        np.testing.assert_array_equal(o[2], one["edges"])
+        np.testing.assert_array_equal(o[3], one["valid"])
+        np.testing.assert_array_equal(o[4], one["weights"])
+        assert o[6]["n_local_edges"] < o[6]["n_edges"]
+    np.testing.assert_array_equal(outs[0][5], outs[1][5])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_single_process_threads(ctx):
+    """One process, one thread per GPU (b200mp_comm_create_all = ncclCommInitAll, environment cloned across contexts)."""
+    import ctypes as C
+    import threading
+    from ompl_b200 import engine
+    L = engine.load_library()
+    n, k, seed = 30011, 12, 5
+    env0 = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
+    one = ctx.prm_build("panda", env0, n, k, seed)
+    c1 = ompl_b200.Context(1)
+    h_env1 = C.c_void_p()
+    engine._check(L.b200mp_env_clone(env0._h, c1._h, C.byref(h_env1)))
+    ctxs = (C.c_void_p * 2)(ctx._h, c1._h)
+    comms = (C.c_void_p * 2)()
+    engine._check(L.b200mp_comm_create_all(ctxs, 2, comms))
+    envs = [env0._h, h_env1]
+    res = [None, None]
+
+    def run(r):
+        cap = n * k
+        st = engine.RoadmapStats()
+        states = np.empty((n, 7), np.float32)
+        edges = np.empty((cap, 2), np.int32)
+        valid = np.empty(cap, np.uint8)
+        w = np.empty(cap, np.float64)
+        rc = L.b200mp_prm_build_multi(comms[r], 0, envs[r], seed, n, k, 0, states.ctypes.data, edges.ctypes.data, valid.ctypes.data, w.ctypes.data,
+                                      None, cap, C.byref(st))
+        res[r] = (rc, states, edges[:st.n_edges], valid[:st.n_edges], w[:st.n_edges])
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    for r in range(2):
+        assert res[r] is not None and res[r][0] == 0
+        np.testing.assert_array_equal(res[r][1], one["states"])
+        np.testing.assert_array_equal(res[r][2], one["edges"])
+        np.testing.assert_array_equal(res[r][3], one["valid"])
+        np.testing.assert_array_equal(res[r][4], one["weights"])
+    for r in range(2):
+        L.b200mp_comm_destroy(comms[r])
+    L.b200mp_env_destroy(h_env1)
+    c1.close()
+
+
+def test_comm_of_one_needs_no_nccl(ctx):
+    env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
+    comm = ompl_b200.Comm(ctx, None, 0, 1)
+    a = comm.prm_build("panda", env, 5000, 8, 3, want_neighbors=True)
+    b = ctx.prm_build("panda", env, 5000, 8, 3)
+    for key in ("states", "edges", "valid", "weights"):
+        np.testing.assert_array_equal(a[key], b[key])
+    # the neighbour table behind the edges: ids ascending by distance, self excluded, equal to the container's own answer
+    nn = ompl_b200.NearestNeighbors(ctx, 7)
+    nn.add(a["states"].astype(np.float64))
+    idx, _, _ = nn.nearest_k(a["states"][:256].astype(np.float64), 8, self_ids=np.arange(256))
+    np.testing.assert_array_equal(a["neighbors"][:256], idx.astype(np.int32))
+    comm.close()
