@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -14,7 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/b200mp.h"
-#include "validate.cuh"
+#include "validate_launch.cuh"
 #include "capt_order.cuh"
 #include "capt_gpu_build.cuh"
 #include "robots/panda_gen.cuh"
@@ -37,6 +38,36 @@ int fail(int code, const char *fmt, ...) {
     g_last_error = buf;
     return code;
 }
+
+// resident blocks per SM of a kernel at a given dynamic shared-memory size; the opt-in attribute and the occupancy query
+// are made once per (device, kernel, size) and remembered (they cost more than a small launch). Both are per-device state.
+int blocks_per_sm(int device, const void *kern, int threads, size_t smem, int *per_sm) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void *, size_t>, int> cache;
+    static std::map<std::pair<int, const void *>, size_t> opted;  // largest dynamic size each kernel has been opted in for (only ever raised)
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({device, kern, smem});
+    if (it != cache.end()) { *per_sm = it->second; return B200MP_OK; }
+    if (smem > opted[{device, kern}]) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        opted[{device, kern}] = smem;
+    }
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, threads, smem));
+    cache[{device, kern, smem}] = *per_sm;
+    return B200MP_OK;
+}
+
+// Every launch gets its own work-queue head from a ring in the context, zeroed on the launch stream just before the kernel, so
+// launches in flight on different streams (the _device entry points take any caller stream) never share or reset each other's queue.
+LaunchCounters *next_counter(b200mp_ctx *c) {
+    return static_cast<LaunchCounters *>(c->d_counters) + (c->counter_next.fetch_add(1) % kCounterRing) * kCounterStride;  // own 128-byte line
+}
+
+
+B200MP_EXTERN_ROBOT(Panda)
+B200MP_EXTERN_ROBOT(Fetch)
+B200MP_EXTERN_ROBOT(Ur5)
+B200MP_EXTERN_ROBOT(Baxter)
 }  // namespace b200mp
 
 // ---------------------------------------------------------------------------------------------------- environment
@@ -693,71 +724,6 @@ int b200mp_env_commit(b200mp_env *e) {
 // ---------------------------------------------------------------------------------------------------- launches
 namespace {
 
-// resident blocks per SM of a kernel at a given dynamic shared-memory size; the opt-in attribute and the occupancy query
-// are made once per (device, kernel, size) and remembered (they cost more than a small launch). Both are per-device state.
-int blocks_per_sm(int device, const void *kern, int threads, size_t smem, int *per_sm) {
-    static std::mutex mu;
-    static std::map<std::tuple<int, const void *, size_t>, int> cache;
-    static std::map<std::pair<int, const void *>, size_t> opted;  // largest dynamic size each kernel has been opted in for (only ever raised)
-    std::lock_guard<std::mutex> lk(mu);
-    auto it = cache.find({device, kern, smem});
-    if (it != cache.end()) { *per_sm = it->second; return B200MP_OK; }
-    if (smem > opted[{device, kern}]) {
-        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        opted[{device, kern}] = smem;
-    }
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, threads, smem));
-    cache[{device, kern, smem}] = *per_sm;
-    return B200MP_OK;
-}
-
-// Every launch gets its own work-queue head from a ring in the context, zeroed on the launch stream just before the kernel, so
-// launches in flight on different streams (the _device entry points take any caller stream) never share or reset each other's queue.
-LaunchCounters *next_counter(b200mp_ctx *c) {
-    return static_cast<LaunchCounters *>(c->d_counters) + (c->counter_next.fetch_add(1) % kCounterRing) * kCounterStride;  // own 128-byte line
-}
-
-template <class R>
-int launch_motions(b200mp_ctx *c, const b200mp_env *e, const float *d_q0, const float *d_q1, const int2 *d_pairs, int64_t m,
-                   int resolution, uint8_t *d_valid, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>(motion_threads<R>());
-    int rc_occ = 0;
-    auto kern = e->desc.n_grid > 0 ? validate_motions_kernel<R, false, true>
-                                   : (e->desc.sorted ? validate_motions_kernel<R, false, false> : validate_motions_kernel<R, true, false>);
-    int per_sm = 0;
-    if ((rc_occ = blocks_per_sm(c->device, reinterpret_cast<const void *>(kern), motion_threads<R>(), smem, &per_sm))) return rc_occ;
-    if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_motions: kernel does not fit on an SM with %zu B of scene", smem);
-    const long long warps_needed = m;
-    long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + (motion_threads<R>() / 32) - 1) / (motion_threads<R>() / 32));
-    blocks = std::max<long long>(blocks, 1);
-    LaunchCounters *cnt = next_counter(c);
-    B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), motion_threads<R>(), smem, st>>>(e->desc, d_q0, d_q1, d_pairs, m, resolution, d_valid, cnt);
-    B200_CUDA(cudaGetLastError());
-    c->launches.fetch_add(1);
-    return B200MP_OK;
-}
-
-template <class R>
-int launch_states(b200mp_ctx *c, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st) {
-    const size_t smem = static_cast<size_t>(e->desc.blob_floats) * 4 + lane_store_bytes<R>(kStateThreads);
-    int rc_occ = 0;
-    auto kern = e->desc.n_grid > 0 ? validate_states_kernel<R, false, true>
-                                   : (e->desc.sorted ? validate_states_kernel<R, false, false> : validate_states_kernel<R, true, false>);
-    int per_sm = 0;
-    if ((rc_occ = blocks_per_sm(c->device, reinterpret_cast<const void *>(kern), kStateThreads, smem, &per_sm))) return rc_occ;
-    if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_states: kernel does not fit on an SM with %zu B of scene", smem);
-    const long long warps_needed = (m + 31) / 32;
-    long long blocks = std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + (kStateThreads / 32) - 1) / (kStateThreads / 32));
-    blocks = std::max<long long>(blocks, 1);
-    LaunchCounters *cnt = next_counter(c);
-    B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), kStateThreads, smem, st>>>(e->desc, d_q, m, d_valid, cnt);
-    B200_CUDA(cudaGetLastError());
-    c->launches.fetch_add(1);
-    return B200MP_OK;
-}
-
 int check_common(const char *who, b200mp_ctx *c, const b200mp_env *e, const void *a, const void *out, int64_t m) {
     if (!c || !e) return fail(B200MP_ERR_INVALID, "%s: NULL handle", who);
     if (e->ctx != c) return fail(B200MP_ERR_INVALID, "%s: environment belongs to another context", who);
@@ -914,10 +880,10 @@ int b200mp_validate_motions_device(b200mp_ctx *c, int robot, const b200mp_env *e
     B200_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     switch (robot) {
-        case B200MP_ROBOT_PANDA: return launch_motions<Panda>(c, e, d_q0, d_q1, nullptr, m, resolution ? resolution : Panda::kResolution, d_valid, st);
-        case B200MP_ROBOT_FETCH: return launch_motions<Fetch>(c, e, d_q0, d_q1, nullptr, m, resolution ? resolution : Fetch::kResolution, d_valid, st);
-        case B200MP_ROBOT_UR5: return launch_motions<Ur5>(c, e, d_q0, d_q1, nullptr, m, resolution ? resolution : Ur5::kResolution, d_valid, st);
-        case B200MP_ROBOT_BAXTER: return launch_motions<Baxter>(c, e, d_q0, d_q1, nullptr, m, resolution ? resolution : Baxter::kResolution, d_valid, st);
+        case B200MP_ROBOT_PANDA: return launch_motions<Panda>(c, e->desc, d_q0, d_q1, nullptr, m, resolution ? resolution : Panda::kResolution, d_valid, st);
+        case B200MP_ROBOT_FETCH: return launch_motions<Fetch>(c, e->desc, d_q0, d_q1, nullptr, m, resolution ? resolution : Fetch::kResolution, d_valid, st);
+        case B200MP_ROBOT_UR5: return launch_motions<Ur5>(c, e->desc, d_q0, d_q1, nullptr, m, resolution ? resolution : Ur5::kResolution, d_valid, st);
+        case B200MP_ROBOT_BAXTER: return launch_motions<Baxter>(c, e->desc, d_q0, d_q1, nullptr, m, resolution ? resolution : Baxter::kResolution, d_valid, st);
         default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
     }
 }
@@ -932,13 +898,20 @@ int b200mp_validate_edges_device(b200mp_ctx *c, int robot, const b200mp_env *e, 
     B200_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     const int2 *pairs = reinterpret_cast<const int2 *>(d_edges);
+    // roadmap edges are a few rakes long: batches go through the bucketed path (rakes of different edges share a warp pass)
+    static const bool packed_ok = !(getenv("B200MP_EDGES_PACKED") && atoi(getenv("B200MP_EDGES_PACKED")) == 0);
+    const bool packed = packed_ok && m >= 1024;
+#define B200_EDGES(R)                                                                                                               \
+    (packed ? launch_motions_bucketed<R>(c, e->desc, d_states, d_states, pairs, m, resolution ? resolution : R::kResolution, d_valid, st) \
+            : launch_motions<R>(c, e->desc, d_states, d_states, pairs, m, resolution ? resolution : R::kResolution, d_valid, st))
     switch (robot) {
-        case B200MP_ROBOT_PANDA: return launch_motions<Panda>(c, e, d_states, d_states, pairs, m, resolution ? resolution : Panda::kResolution, d_valid, st);
-        case B200MP_ROBOT_FETCH: return launch_motions<Fetch>(c, e, d_states, d_states, pairs, m, resolution ? resolution : Fetch::kResolution, d_valid, st);
-        case B200MP_ROBOT_UR5: return launch_motions<Ur5>(c, e, d_states, d_states, pairs, m, resolution ? resolution : Ur5::kResolution, d_valid, st);
-        case B200MP_ROBOT_BAXTER: return launch_motions<Baxter>(c, e, d_states, d_states, pairs, m, resolution ? resolution : Baxter::kResolution, d_valid, st);
+        case B200MP_ROBOT_PANDA: return B200_EDGES(Panda);
+        case B200MP_ROBOT_FETCH: return B200_EDGES(Fetch);
+        case B200MP_ROBOT_UR5: return B200_EDGES(Ur5);
+        case B200MP_ROBOT_BAXTER: return B200_EDGES(Baxter);
         default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
     }
+#undef B200_EDGES
 }
 
 int b200mp_validate_states_device(b200mp_ctx *c, int robot, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid,
@@ -949,10 +922,10 @@ int b200mp_validate_states_device(b200mp_ctx *c, int robot, const b200mp_env *e,
     B200_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     switch (robot) {
-        case B200MP_ROBOT_PANDA: return launch_states<Panda>(c, e, d_q, m, d_valid, st);
-        case B200MP_ROBOT_FETCH: return launch_states<Fetch>(c, e, d_q, m, d_valid, st);
-        case B200MP_ROBOT_UR5: return launch_states<Ur5>(c, e, d_q, m, d_valid, st);
-        case B200MP_ROBOT_BAXTER: return launch_states<Baxter>(c, e, d_q, m, d_valid, st);
+        case B200MP_ROBOT_PANDA: return launch_states<Panda>(c, e->desc, d_q, m, d_valid, st);
+        case B200MP_ROBOT_FETCH: return launch_states<Fetch>(c, e->desc, d_q, m, d_valid, st);
+        case B200MP_ROBOT_UR5: return launch_states<Ur5>(c, e->desc, d_q, m, d_valid, st);
+        case B200MP_ROBOT_BAXTER: return launch_states<Baxter>(c, e->desc, d_q, m, d_valid, st);
         default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
     }
 }

@@ -575,8 +575,10 @@ __device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const flo
 
 // Allowed self-collision pairs on the stored centres (collision/validity.hh:13-44); frames are rebuilt only for pairs
 // whose bounding spheres touch. Updates `alive`; returns true when the caller should return `result` immediately.
-template <class R, int G, bool EDGE, int BT>
-__device__ __forceinline__ bool self_collision(const float (&q)[R::kDim], const float *__restrict__ slots, bool &alive, bool &result) {
+// KILL (lane-per-state form only): lanes are grouped into motions by `kill` (the lanes that belong to the same motion as this
+// one); a hit in any of them ends the work of all of them.
+template <class R, int G, bool EDGE, bool KILL, int BT>
+__device__ __forceinline__ bool self_collision(const float (&q)[R::kDim], const float *__restrict__ slots, bool &alive, bool &result, unsigned kill) {
     const typename R::Tables &tb = R::tables();
     Frame F;
     int have = -1;
@@ -628,6 +630,7 @@ __device__ __forceinline__ bool self_collision(const float (&q)[R::kDim], const 
             if (EDGE) {
                 if (__any_sync(kFull, fhit)) { result = !fhit; return true; }
             } else {
+                if (KILL) fhit = (__ballot_sync(kFull, fhit) & kill) != 0u;
                 if (__all_sync(kFull, fhit || !need)) break;
             }
         }
@@ -659,8 +662,9 @@ __device__ __forceinline__ void fk_to_slots(const float (&q)[R::kDim], float *__
 // states exit early); only when a rake has a coarse hit is the link's frame rebuilt (chain walk from the cached
 // sin / cos) and its fine spheres tested. Phase C: self_collision().
 // This is the ordered-scan variant (scenes without a candidate grid: small or unsorted).
-template <class R, int G, bool EDGE, bool MASKED, int BT>
-__device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots, bool active) {
+template <class R, int G, bool EDGE, bool KILL, bool MASKED, int BT>
+__device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots, bool active,
+                                    unsigned kill) {
     constexpr int FT = 4;  // fine spheres processed together per lane
     constexpr int POLICY = EDGE ? kAnyHit : kUntilAllHit;
     const typename R::Tables &tb = R::tables();
@@ -711,6 +715,7 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
             if (EDGE) {
                 if (__any_sync(kFull, fhit)) return !fhit;
             } else {
+                if (KILL) fhit = (__ballot_sync(kFull, fhit) & kill) != 0u;
                 if (__all_sync(kFull, fhit || !need)) break;
             }
         }
@@ -718,7 +723,7 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
         if (!EDGE && !__any_sync(kFull, alive)) return false;
     }
     bool result = false;
-    if (self_collision<R, G, EDGE, BT>(q, slots, alive, result)) return result;
+    if (self_collision<R, G, EDGE, KILL, BT>(q, slots, alive, result, kill)) return result;
     return alive;
 }
 
@@ -735,7 +740,7 @@ __device__ __noinline__ bool ordered_scan_one(const Scene *scp, float x, float y
     return any_mode ? scan_scene<1, kAnyHit, false>(sc, s1, on) : scan_scene<1, kUntilAllHit, false>(sc, s1, on);
 }
 
-__device__ __noinline__ bool pointclouds_one(const CaptView *pcs, int n_pc, float x, float y, float z, float r, bool on, bool any_mode) {
+static __device__ __noinline__ bool pointclouds_one(const CaptView *pcs, int n_pc, float x, float y, float z, float r, bool on, bool any_mode) {
     bool hit = false;
     for (int p = 0; p < n_pc; ++p) hit |= capt_collides_warp(pcs[p], x, y, z, r, on && !hit, any_mode);
     return hit;
@@ -756,9 +761,9 @@ __device__ __forceinline__ void fill_views(const SceneDesc &sd, const Scene &sc,
 
 // Candidate-grid variant (sorted scenes with a grid). Phase B is one loop over "sphere tasks" -- a link's bounding sphere,
 // or, while a link is being refined, its next fine sphere -- so that the grid walk exists once in the instruction stream.
-template <class R, int G, bool EDGE, int BT>
+template <class R, int G, bool EDGE, bool KILL, int BT>
 __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
-                                 const SphereLevels<R> &lv, const SharedViews &sv, bool active) {
+                                 const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill) {
     const typename R::Tables &tb = R::tables();
     bool alive = active;
     Frame F;
@@ -809,6 +814,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
             if (EDGE) {
                 if (__any_sync(kFull, fhit)) return !fhit;
             } else {
+                if (KILL) fhit = (__ballot_sync(kFull, fhit) & kill) != 0u;
                 if (__all_sync(kFull, fhit || !need)) f = fe;
             }
             if (f >= fe) {
@@ -818,20 +824,34 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
         }
     }
     bool result = false;
-    if (self_collision<R, G, EDGE, BT>(q, slots, alive, result)) return result;
+    if (self_collision<R, G, EDGE, KILL, BT>(q, slots, alive, result, kill)) return result;
     return alive;
 }
 
-template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT>
+template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT, bool KILL = false>
 __device__ __forceinline__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
-                                            const SphereLevels<R> &lv, const SharedViews &sv, bool active) {
-    if (GRID) return check_state_grid<R, G, EDGE, BT>(q, sd, sc, slots, lv, sv, active);
-    return check_state_ordered<R, G, EDGE, MASKED, BT>(q, sd, sc, slots, active);
+                                            const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill = 0u) {
+    if (GRID) return check_state_grid<R, G, EDGE, KILL, BT>(q, sd, sc, slots, lv, sv, active, kill);
+    return check_state_ordered<R, G, EDGE, KILL, MASKED, BT>(q, sd, sc, slots, active, kill);
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
 struct LaunchCounters {
     unsigned long long next;  // dynamic work queue head
+};
+
+// Work description of a bucketed batch of motions (written on the device by the pre-pass below, read by the two kernels that follow
+// it): the motions are grouped by their number of rakes n = max(ceil(|q1 - q0| / 8 * resolution), 1).
+//   bucket b = 1 .. 4: motions with exactly b rakes -> validate_rakes_kernel packs their rakes four to a warp pass
+//   bucket 5         : longer motions               -> validate_motions_kernel, one warp per motion, passes in sequence with early exit
+constexpr int kRakeBuckets = 6;  // index 0 unused
+struct BucketPlan {
+    unsigned cnt[kRakeBuckets];       // motions per bucket
+    unsigned off[kRakeBuckets];       // start of each bucket in the list
+    unsigned cursor[kRakeBuckets];    // fill positions of the scatter pass
+    unsigned pass_end[kRakeBuckets];  // warp passes up to and including bucket b (b <= 4)
+    unsigned long long next_pass;     // work queue head of validate_rakes_kernel
+    LaunchCounters long_queue;        // work queue head of validate_motions_kernel over bucket 5
 };
 
 // Threads per block / blocks per SM of the validation kernels (measured on C2: the motion kernel gains ~4 % from 20 warps
@@ -860,10 +880,12 @@ __device__ __forceinline__ float vamp_l2_norm(const float (&v)[DIM]) {
 }
 
 // One warp per motion; motions are taken from a global queue (edge cost varies by 100x with early exit).
+// `list` / `plan` (both or neither): the motions to check are list[plan->off[5] .. + plan->cnt[5]) instead of 0 .. m - 1.
 template <class R, bool MASKED, bool GRID>
 __global__ void __launch_bounds__(motion_threads<R>(), kMotionBlocksPerSM)
 validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float *__restrict__ q1, const int2 *__restrict__ pairs,
-                        long long m, int resolution, uint8_t *__restrict__ valid, LaunchCounters *cnt) {
+                        long long m, int resolution, uint8_t *__restrict__ valid, LaunchCounters *cnt, const unsigned *__restrict__ list,
+                        const BucketPlan *__restrict__ plan) {
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long bar;
     __shared__ SphereLevels<R> lv;
@@ -878,12 +900,18 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
     const int lane = threadIdx.x & 31;
     const int rake_in_pass = lane >> 3;
     const float pct = static_cast<float>((lane & 7) + 1) / 8.0f;
+    if (plan != nullptr) {
+        m = plan->cnt[kRakeBuckets - 1];
+        list += plan->off[kRakeBuckets - 1];
+        if (m == 0) return;
+    }
 
     for (;;) {
         unsigned long long e = 0;
         if (lane == 0) e = atomicAdd(&cnt->next, 1ull);
         e = __shfl_sync(kFull, e, 0);
         if (e >= static_cast<unsigned long long>(m)) break;
+        if (list != nullptr) e = __ldg(list + e);
 
         float a[D], v[D], q[D], back[D];
         // roadmap edges address their end points in one state table (pairs != nullptr: q0 == q1 == the table)
@@ -925,6 +953,190 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
             }
         }
         if (lane == 0) valid[e] = ok ? 1 : 0;
+    }
+}
+
+// ---- short motions: rakes of different motions share a warp pass ----------------------------------------------------------------
+// A roadmap edge is 2-3 rakes long (its length is a k-th neighbour distance), so the warp-per-motion kernel above runs with half to
+// three quarters of its lanes. Here a warp pass takes four RAKES from the bucket's task list -- task t of bucket b is rake t % b of
+// motion t / b -- whatever motions they belong to. States, arithmetic and decisions are those of the kernel above (start + v * pct,
+// then `rake` sequential back-steps). A fine hit ends the work of every lane of the same motion in the warp (KILL mask); rakes of
+// that motion running in other warps finish on their own, later passes skip it (valid[e] is already 0).
+// valid[] must be 1 on entry (the pre-pass sets it); a pass only ever writes 0.
+template <class R, bool MASKED, bool GRID>
+__global__ void __launch_bounds__(motion_threads<R>(), kMotionBlocksPerSM)
+validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *__restrict__ q1, const int2 *__restrict__ pairs,
+                      uint8_t *__restrict__ valid, const unsigned *__restrict__ list, BucketPlan *__restrict__ plan) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ unsigned long long bar;
+    __shared__ SphereLevels<R> lv;
+    const unsigned total = plan->pass_end[kRakeBuckets - 2];
+    if (total == 0) return;
+    fill_levels<R>(sd, lv);
+    stage_scene(smem, sd.blob, sd.blob_floats, &bar);
+    const Scene sc = scene_view(sd, smem);
+    float *slots = smem + sd.blob_floats + threadIdx.x;
+    __shared__ SharedViews sv;
+    fill_views(sd, sc, sv);
+    __syncthreads();
+    constexpr int D = R::kDim;
+    const int lane = threadIdx.x & 31;
+    const int group = lane >> 3;
+    const float pct = static_cast<float>((lane & 7) + 1) / 8.0f;
+    for (;;) {
+        unsigned long long p64 = 0;
+        if (lane == 0) p64 = atomicAdd(&plan->next_pass, 1ull);
+        p64 = __shfl_sync(kFull, p64, 0);
+        if (p64 >= total) break;
+        const unsigned p = static_cast<unsigned>(p64);
+        int b = 1;
+        while (p >= plan->pass_end[b]) ++b;  // (warp-uniform; at most three steps)
+        const unsigned t = 4u * (p - plan->pass_end[b - 1]) + static_cast<unsigned>(group);
+        const unsigned ei = t / static_cast<unsigned>(b);
+        const int rake = static_cast<int>(t - ei * static_cast<unsigned>(b));
+        bool active = ei < plan->cnt[b];
+        const unsigned e = active ? __ldg(list + plan->off[b] + ei) : 0xffffffffu;
+        if (active && valid[e] == 0) active = false;  // another pass already found this motion in collision
+        float a[D], v[D], q[D], back[D];
+        unsigned long long ia = e, ib = e;
+        if (active && pairs != nullptr) {
+            const int2 pr = __ldg(pairs + e);
+            ia = static_cast<unsigned long long>(pr.x);
+            ib = static_cast<unsigned long long>(pr.y);
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            a[j] = active ? __ldg(q0 + ia * D + j) : 0.0f;
+            v[j] = active ? __ldg(q1 + ib * D + j) - a[j] : 0.0f;
+        }
+        // n = max(ceil(dist / rake * resolution), 1)  (planning/validate.hh:41) = b: the pre-pass computed it with the motion kernel's expression
+        const float denom = static_cast<float>(8 * b);
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            q[j] = fmaf(v[j], pct, a[j]);  // block = start + vector * percents
+            back[j] = v[j] / denom;        // backstep = vector / (rake * n)
+        }
+        for (int r = 0; r < rake; ++r) {   // sequential back-steps, exactly as the reference accumulates them
+#pragma unroll
+            for (int j = 0; j < D; ++j) q[j] = q[j] - back[j];
+        }
+        // lanes of the same motion in this warp
+        unsigned kill = 0u;
+#pragma unroll
+        for (int g2 = 0; g2 < 4; ++g2) {
+            const unsigned eg = __shfl_sync(kFull, e, 8 * g2);
+            const bool ag = __shfl_sync(kFull, active ? 1 : 0, 8 * g2) != 0;
+            if (ag && eg == e) kill |= 0xffu << (8 * g2);
+        }
+        if (!__any_sync(kFull, active)) continue;
+        const bool good = check_state<R, 8, false, MASKED, GRID, motion_threads<R>(), true>(q, sd, sc, slots, lv, sv, active, kill);
+        const bool bad = group_any<8>(active && !good);
+        if (bad && (lane & 7) == 0) valid[e] = 0;
+    }
+}
+
+// Pre-pass of a bucketed batch: number of rakes of every motion -> bucket key; per-bucket counts (whole batch and per block);
+// valid[] = 1. The list is then filled in a STABLE order: consecutive motions of a bucket stay consecutive, so the rakes that share
+// a warp pass belong to neighbouring motions of the batch (roadmap edges of one milestone: nearby states, the same links near the
+// same obstacles), which is what keeps the lock-step lanes of a pass doing the same work.
+template <class R>
+__global__ void __launch_bounds__(256)
+bucket_count_kernel(const float *__restrict__ q0, const float *__restrict__ q1, const int2 *__restrict__ pairs, long long m, int resolution,
+                    unsigned char *__restrict__ keys, uint8_t *__restrict__ valid, unsigned *__restrict__ blk_cnt, BucketPlan *__restrict__ plan) {
+    constexpr int D = R::kDim;
+    __shared__ unsigned s_cnt[8];
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < m) {
+        long long ia = e, ib = e;
+        if (pairs != nullptr) {
+            const int2 pr = __ldg(pairs + e);
+            ia = pr.x;
+            ib = pr.y;
+        }
+        float v[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) v[j] = __ldg(q1 + ib * D + j) - __ldg(q0 + ia * D + j);
+        const float dist = vamp_l2_norm<D>(v);
+        const float nf = fmaxf(ceilf(dist / 8.0f * static_cast<float>(resolution)), 1.0f);
+        const int key = nf <= 4.0f ? static_cast<int>(nf) : kRakeBuckets - 1;  // (NaN lengths go to the long bucket as well)
+        keys[e] = static_cast<unsigned char>(key);
+        valid[e] = 1;
+        atomicAdd(&s_cnt[key], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        blk_cnt[static_cast<size_t>(blockIdx.x) * 8 + threadIdx.x] = s_cnt[threadIdx.x];
+        if (threadIdx.x < kRakeBuckets && s_cnt[threadIdx.x]) atomicAdd(&plan->cnt[threadIdx.x], s_cnt[threadIdx.x]);
+    }
+}
+
+// one block: bucket offsets and pass counts; blk_cnt[block][key] -> exclusive prefix over the blocks (in place)
+static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__restrict__ plan, unsigned *__restrict__ blk_cnt, int nb) {
+    __shared__ unsigned s_part[1024][kRakeBuckets];
+    const int t = threadIdx.x;
+    const int chunk = (nb + 1023) / 1024, b0 = t * chunk, b1 = min(nb, b0 + chunk);
+    unsigned sum[kRakeBuckets];
+#pragma unroll
+    for (int k = 0; k < kRakeBuckets; ++k) sum[k] = 0;
+    for (int i = b0; i < b1; ++i)
+#pragma unroll
+        for (int k = 0; k < kRakeBuckets; ++k) sum[k] += blk_cnt[static_cast<size_t>(i) * 8 + k];
+#pragma unroll
+    for (int k = 0; k < kRakeBuckets; ++k) s_part[t][k] = sum[k];
+    __syncthreads();
+    if (t < kRakeBuckets) {  // one thread per key: running sum over the 1024 partials (tiny)
+        unsigned run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            const unsigned v = s_part[i][t];
+            s_part[i][t] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kRakeBuckets; ++k) sum[k] = s_part[t][k];
+    for (int i = b0; i < b1; ++i)
+#pragma unroll
+        for (int k = 0; k < kRakeBuckets; ++k) {
+            const unsigned v = blk_cnt[static_cast<size_t>(i) * 8 + k];
+            blk_cnt[static_cast<size_t>(i) * 8 + k] = sum[k];
+            sum[k] += v;
+        }
+    if (t == 0) {
+        unsigned off = 0, passes = 0;
+        plan->off[0] = 0; plan->cursor[0] = 0; plan->pass_end[0] = 0;
+        for (int b = 1; b < kRakeBuckets; ++b) {
+            plan->off[b] = off;
+            plan->cursor[b] = 0;
+            off += plan->cnt[b];
+            if (b < kRakeBuckets - 1) passes += (plan->cnt[b] * static_cast<unsigned>(b) + 3u) / 4u;
+            plan->pass_end[b] = passes;
+        }
+        plan->next_pass = 0;
+        plan->long_queue.next = 0;
+    }
+}
+
+static __global__ void __launch_bounds__(256) bucket_scatter_kernel(const unsigned char *__restrict__ keys, long long m, const unsigned *__restrict__ blk_base,
+                                                                    unsigned *__restrict__ list, const BucketPlan *__restrict__ plan) {
+    __shared__ unsigned s_w[8][8];  // [warp][key]: motions of that key in the warp
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int key = e < m ? keys[e] : 0;
+    unsigned rank = 0;
+#pragma unroll
+    for (int k = 1; k < kRakeBuckets; ++k) {
+        const unsigned mask = __ballot_sync(kFull, key == k);
+        if (key == k) rank = __popc(mask & ((1u << lane) - 1u));
+        if (lane == 0) s_w[w][k] = __popc(mask);
+    }
+    __syncthreads();
+    if (key != 0) {
+        unsigned base = blk_base[static_cast<size_t>(blockIdx.x) * 8 + key];
+        for (int w2 = 0; w2 < w; ++w2) base += s_w[w2][key];
+        list[plan->off[key] + base + rank] = static_cast<unsigned>(e);
     }
 }
 

@@ -1,0 +1,110 @@
+// Host-side launches of the validation kernels, one explicit instantiation per robot (validate_<robot>.cu) so that the robots
+// compile in parallel. b200mp.cu declares them `extern template`.
+#pragma once
+#include <algorithm>
+
+#include "validate.cuh"
+#include "host_common.hpp"
+
+namespace b200mp {
+
+// resident blocks per SM of a kernel at a given dynamic shared-memory size (cached per device; defined in b200mp.cu)
+int blocks_per_sm(int device, const void *kern, int threads, size_t smem, int *per_sm);
+// this launch's own work-queue head from the context's ring (defined in b200mp.cu)
+LaunchCounters *next_counter(b200mp_ctx *c);
+
+template <class R, bool RAKES>
+inline auto pick_motion_kernel(const SceneDesc &d) {
+    if constexpr (RAKES)
+        return d.n_grid > 0 ? validate_rakes_kernel<R, false, true> : (d.sorted ? validate_rakes_kernel<R, false, false> : validate_rakes_kernel<R, true, false>);
+    else
+        return d.n_grid > 0 ? validate_motions_kernel<R, false, true>
+                            : (d.sorted ? validate_motions_kernel<R, false, false> : validate_motions_kernel<R, true, false>);
+}
+
+template <class R>
+int launch_motions(b200mp_ctx *c, const SceneDesc &desc, const float *d_q0, const float *d_q1, const int2 *d_pairs, int64_t m, int resolution,
+                   uint8_t *d_valid, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(desc.blob_floats) * 4 + lane_store_bytes<R>(motion_threads<R>());
+    auto kern = pick_motion_kernel<R, false>(desc);
+    int per_sm = 0, rc = 0;
+    if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(kern), motion_threads<R>(), smem, &per_sm))) return rc;
+    if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_motions: kernel does not fit on an SM with %zu B of scene", smem);
+    const long long wpb = motion_threads<R>() / 32;
+    const long long blocks = std::max<long long>(1, std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (m + wpb - 1) / wpb));
+    LaunchCounters *cnt = next_counter(c);
+    B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(LaunchCounters), st));
+    kern<<<static_cast<unsigned>(blocks), motion_threads<R>(), smem, st>>>(desc, d_q0, d_q1, d_pairs, m, resolution, d_valid, cnt, nullptr, nullptr);
+    B200_CUDA(cudaGetLastError());
+    c->launches.fetch_add(1);
+    return B200MP_OK;
+}
+
+// Motions grouped by their number of rakes first (pre-pass on the device, no host round trip): the short ones (<= 4 rakes, e.g.
+// roadmap edges) go through validate_rakes_kernel, four rakes of any motions per warp pass, the rest through validate_motions_kernel.
+template <class R>
+int launch_motions_bucketed(b200mp_ctx *c, const SceneDesc &desc, const float *d_q0, const float *d_q1, const int2 *d_pairs, int64_t m,
+                            int resolution, uint8_t *d_valid, cudaStream_t st) {
+    if (m > 0xfffffff0LL) return fail(B200MP_ERR_CAPACITY, "validate (bucketed): at most 2^32 - 16 motions per call");
+    const size_t smem = static_cast<size_t>(desc.blob_floats) * 4 + lane_store_bytes<R>(motion_threads<R>());
+    auto k_rakes = pick_motion_kernel<R, true>(desc);
+    auto k_long = pick_motion_kernel<R, false>(desc);
+    int per_rakes = 0, per_long = 0, rc = 0;
+    if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(k_rakes), motion_threads<R>(), smem, &per_rakes))) return rc;
+    if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(k_long), motion_threads<R>(), smem, &per_long))) return rc;
+    if (per_rakes < 1 || per_long < 1) return fail(B200MP_ERR_CAPACITY, "validate (bucketed): kernel does not fit on an SM with %zu B of scene", smem);
+    // stream-ordered temporaries: keys[m] | list[m] | per-block counts[nb][8] | plan
+    const unsigned nb = static_cast<unsigned>((m + 255) / 256);
+    const size_t o_list = (static_cast<size_t>(m) + 255) / 256 * 256, o_blk = o_list + (static_cast<size_t>(m) * 4 + 255) / 256 * 256;
+    const size_t o_plan = o_blk + static_cast<size_t>(nb) * 8 * 4;
+    char *tmp = nullptr;
+    B200_CUDA(cudaMallocAsync(&tmp, o_plan + sizeof(BucketPlan), st));
+    unsigned char *keys = reinterpret_cast<unsigned char *>(tmp);
+    unsigned *list = reinterpret_cast<unsigned *>(tmp + o_list);
+    unsigned *blk = reinterpret_cast<unsigned *>(tmp + o_blk);
+    BucketPlan *plan = reinterpret_cast<BucketPlan *>(tmp + o_plan);
+    cudaMemsetAsync(plan, 0, sizeof(BucketPlan), st);
+    bucket_count_kernel<R><<<nb, 256, 0, st>>>(d_q0, d_q1, d_pairs, m, resolution, keys, d_valid, blk, plan);
+    bucket_plan_kernel<<<1, 1024, 0, st>>>(plan, blk, static_cast<int>(nb));
+    bucket_scatter_kernel<<<nb, 256, 0, st>>>(keys, m, blk, list, plan);
+    const long long wpb = motion_threads<R>() / 32;
+    const long long cap = std::max<long long>(1, (m + wpb - 1) / wpb);
+    const unsigned b_rakes = static_cast<unsigned>(std::min<long long>(static_cast<long long>(c->sm_count) * per_rakes, cap));
+    const unsigned b_long = static_cast<unsigned>(std::min<long long>(static_cast<long long>(c->sm_count) * per_long, cap));
+    k_rakes<<<b_rakes, motion_threads<R>(), smem, st>>>(desc, d_q0, d_q1, d_pairs, d_valid, list, plan);
+    k_long<<<b_long, motion_threads<R>(), smem, st>>>(desc, d_q0, d_q1, d_pairs, m, resolution, d_valid, &plan->long_queue, list, plan);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(tmp, st);
+    if (e != cudaSuccess) return fail(B200MP_ERR_CUDA, "validate (bucketed) launch failed: %s", cudaGetErrorString(e));
+    c->launches.fetch_add(5);
+    return B200MP_OK;
+}
+
+template <class R>
+int launch_states(b200mp_ctx *c, const SceneDesc &desc, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(desc.blob_floats) * 4 + lane_store_bytes<R>(kStateThreads);
+    auto kern = desc.n_grid > 0 ? validate_states_kernel<R, false, true>
+                                : (desc.sorted ? validate_states_kernel<R, false, false> : validate_states_kernel<R, true, false>);
+    int per_sm = 0, rc = 0;
+    if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(kern), kStateThreads, smem, &per_sm))) return rc;
+    if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_states: kernel does not fit on an SM with %zu B of scene", smem);
+    const long long warps_needed = (m + 31) / 32, wpb = kStateThreads / 32;
+    const long long blocks = std::max<long long>(1, std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + wpb - 1) / wpb));
+    LaunchCounters *cnt = next_counter(c);
+    B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(LaunchCounters), st));
+    kern<<<static_cast<unsigned>(blocks), kStateThreads, smem, st>>>(desc, d_q, m, d_valid, cnt);
+    B200_CUDA(cudaGetLastError());
+    c->launches.fetch_add(1);
+    return B200MP_OK;
+}
+
+#define B200MP_INSTANTIATE_ROBOT(R)                                                                                                        \
+    template int launch_motions<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t);          \
+    template int launch_motions_bucketed<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t); \
+    template int launch_states<R>(b200mp_ctx *, const SceneDesc &, const float *, int64_t, uint8_t *, cudaStream_t);
+#define B200MP_EXTERN_ROBOT(R)                                                                                                                    \
+    extern template int launch_motions<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t);          \
+    extern template int launch_motions_bucketed<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t); \
+    extern template int launch_states<R>(b200mp_ctx *, const SceneDesc &, const float *, int64_t, uint8_t *, cudaStream_t);
+
+}  // namespace b200mp
