@@ -8,6 +8,13 @@
 //   ompl::b200::getRobotBounds<Robot>()          <->  ompl::vamp::getRobotBounds<Robot>()          src/ompl/vamp/VampStateSpace.h:10-36
 //   ompl::b200::NearestNeighborsB200<_T>         <->  ompl::NearestNeighbors<_T> backends          src/ompl/datastructures/NearestNeighbors.h:46-115
 //                                                     (Linear semantics: NearestNeighborsLinear.h:65-142)
+//   ompl::b200::KinematicChain                   <->  KinematicChainSpace + createHornEnvironment  demos/KinematicChain.h:88-191,279-315
+//   ompl::b200::B200ChainValidityChecker         <->  KinematicChainValidityChecker                demos/KinematicChain.h:193-276
+//   ompl::b200::B200DiscreteMotionValidator      <->  ompl::base::DiscreteMotionValidator          src/ompl/base/src/DiscreteMotionValidator.cpp:48-145
+//   batched call sites (extensions, no planner changes needed to adopt them one loop at a time):
+//     checkMotionsFrom / rewireBatch             the k edges PRM::addMilestone checks (PRM.cpp:585-598) and the parent / rewire loops of
+//                                                RRT* (src/ompl/geometric/planners/rrt/src/RRTstar.cpp:346,372,431) in one launch
+//     shortcutBatch                              candidate shortcuts of PathSimplifier (src/ompl/geometric/src/PathSimplifier.cpp:103-232)
 // The classes derive from the real OMPL base classes, so planners install them through the usual calls
 // (SpaceInformation::setStateValidityChecker / setMotionValidator, src/ompl/base/SpaceInformation.h:146-172;
 // Planner::setNearestNeighbors<NearestNeighborsB200>(), PRM.h:254-265, RRTConnect.h:106-115, RRTstar.h:141-149).
@@ -207,6 +214,13 @@ namespace ompl::b200
         {
             check(b200mp_env_commit(env_), "commit");
         }
+        /// A copy of this scene on another engine (another GPU), committed when this one is (b200mp_env_clone; primitive shapes only).
+        std::shared_ptr<Environment> cloneTo(EnginePtr engine) const
+        {
+            b200mp_env *e = nullptr;
+            check(b200mp_env_clone(env_, engine->get(), &e), "cloneTo");
+            return std::shared_ptr<Environment>(new Environment(std::move(engine), e));
+        }
         b200mp_env *get() const
         {
             return env_;
@@ -217,6 +231,9 @@ namespace ompl::b200
         }
 
     private:
+        Environment(EnginePtr engine, b200mp_env *adopted) : engine_(std::move(engine)), env_(adopted)
+        {
+        }
         static void cuboidRecord(const std::array<float, 3> &c, const std::array<float, 3> &e, const std::array<float, 3> &h, float *rec)
         {
             // R = Rz(e[2]) * Ry(e[1]) * Rx(e[0]); axes are the columns (factory.hh:26-62)
@@ -344,8 +361,205 @@ namespace ompl::b200
                   "checkMotions");
         }
 
+        /// out[i] = checkMotion(from, to[i]): the k candidate edges of a new PRM milestone (PRM::addMilestone checks
+        /// neighbour -> milestone one call at a time, PRM.cpp:585-598; pass reverse = true for that direction).
+        void checkMotionsFrom(const ob::State *from, const ob::State *const *to, std::size_t n, std::uint8_t *out, bool reverse = false) const
+        {
+            std::vector<const ob::State *> rep(n, from);
+            if (reverse)
+                checkMotions(to, rep.data(), n, out);
+            else
+                checkMotions(rep.data(), to, n, out);
+        }
+
+        /// RRT*'s neighbourhood in one launch (RRTstar.cpp:346-431): toNew[i] = checkMotion(nbh[i], newState) -- the parent candidates --
+        /// and fromNew[i] = checkMotion(newState, nbh[i]) -- the rewiring candidates. Either output may be null.
+        void rewireBatch(const ob::State *newState, const ob::State *const *nbh, std::size_t n, std::uint8_t *toNew, std::uint8_t *fromNew) const
+        {
+            const std::size_t m = (toNew ? n : 0) + (fromNew ? n : 0);
+            if (m == 0)
+                return;
+            std::vector<const ob::State *> a, b;
+            a.reserve(m);
+            b.reserve(m);
+            if (toNew)
+                for (std::size_t i = 0; i < n; ++i) { a.push_back(nbh[i]); b.push_back(newState); }
+            if (fromNew)
+                for (std::size_t i = 0; i < n; ++i) { a.push_back(newState); b.push_back(nbh[i]); }
+            std::vector<std::uint8_t> out(m);
+            checkMotions(a.data(), b.data(), m, out.data());
+            if (toNew)
+                std::copy_n(out.data(), n, toNew);
+            if (fromNew)
+                std::copy_n(out.data() + (toNew ? n : 0), n, fromNew);
+        }
+
+        /// PathSimplifier's shortcut candidates in one launch (PathSimplifier.cpp:103-232 tries them one checkMotion at a time):
+        /// out[c] = checkMotion(path[pairs[c].first], path[pairs[c].second]).
+        void shortcutBatch(const std::vector<const ob::State *> &path, const std::vector<std::pair<std::size_t, std::size_t>> &pairs,
+                           std::uint8_t *out) const
+        {
+            std::vector<const ob::State *> a, b;
+            a.reserve(pairs.size());
+            b.reserve(pairs.size());
+            for (const auto &pr : pairs) { a.push_back(path.at(pr.first)); b.push_back(path.at(pr.second)); }
+            if (!pairs.empty())
+                checkMotions(a.data(), b.data(), pairs.size(), out);
+        }
+
     private:
         EnvironmentPtr env_;
+    };
+
+    /// The planar kinematic chain of demos/KinematicChain.h on the GPU: n_links revolute joints (a RealVectorStateSpace of angles),
+    /// link length, environment segments; KinematicChainSpace::distance / interpolate and the longest valid segment
+    /// (lvsFraction = StateSpace::getLongestValidSegmentFraction(), OMPL's default 0.01, of the maximum extent).
+    class KinematicChain
+    {
+    public:
+        KinematicChain(EnginePtr engine, unsigned int links, double linkLength, const std::vector<std::array<double, 4>> &segments,
+                       double lvsFraction = 0.01)
+          : engine_(std::move(engine)), links_(links), linkLength_(linkLength)
+        {
+            std::vector<double> seg;
+            for (const auto &s : segments)
+                seg.insert(seg.end(), s.begin(), s.end());
+            check(b200mp_chain_create(engine_->get(), static_cast<int>(links), linkLength, seg.empty() ? nullptr : seg.data(),
+                                      static_cast<int>(segments.size()), lvsFraction, &chain_),
+                  "KinematicChain");
+        }
+        ~KinematicChain()
+        {
+            b200mp_chain_destroy(chain_);
+        }
+        KinematicChain(const KinematicChain &) = delete;
+        KinematicChain &operator=(const KinematicChain &) = delete;
+
+        /// createHornEnvironment(d, eps) (demos/KinematicChain.h:279-315)
+        static std::vector<std::array<double, 4>> hornEnvironment(unsigned int d, double eps)
+        {
+            int n = 0;
+            check(b200mp_chain_horn_environment(static_cast<int>(d), eps, nullptr, &n), "hornEnvironment");
+            std::vector<double> flat(4 * static_cast<std::size_t>(n));
+            check(b200mp_chain_horn_environment(static_cast<int>(d), eps, flat.data(), &n), "hornEnvironment");
+            std::vector<std::array<double, 4>> out(n);
+            for (int i = 0; i < n; ++i)
+                std::copy_n(flat.data() + 4 * i, 4, out[i].begin());
+            return out;
+        }
+        /// KinematicChainSpace::distance (demos/KinematicChain.h:105-121)
+        double distance(const ob::State *a, const ob::State *b) const
+        {
+            double d = 0;
+            check(b200mp_chain_distance(chain_, detail::values(a), detail::values(b), 1, &d), "chain distance");
+            return d;
+        }
+        /// KinematicChainSpace::interpolate (demos/KinematicChain.h:150-176)
+        void interpolate(const ob::State *from, const ob::State *to, double t, ob::State *state) const
+        {
+            check(b200mp_chain_interpolate(chain_, detail::values(from), detail::values(to), &t, 1,
+                                           state->as<ob::RealVectorStateSpace::StateType>()->values),
+                  "chain interpolate");
+        }
+        unsigned int links() const { return links_; }
+        double linkLength() const { return linkLength_; }
+        b200mp_chain *get() const { return chain_; }
+        const EnginePtr &engine() const { return engine_; }
+
+    private:
+        EnginePtr engine_;
+        b200mp_chain *chain_{nullptr};
+        unsigned int links_;
+        double linkLength_;
+    };
+    using KinematicChainPtr = std::shared_ptr<KinematicChain>;
+
+    /// KinematicChainValidityChecker::isValid (demos/KinematicChain.h:193-276): no self intersection, no intersection with the environment.
+    class B200ChainValidityChecker : public ob::StateValidityChecker
+    {
+    public:
+        B200ChainValidityChecker(ob::SpaceInformation *si, KinematicChainPtr chain) : ob::StateValidityChecker(si), chain_(std::move(chain))
+        {
+        }
+        B200ChainValidityChecker(const ob::SpaceInformationPtr &si, KinematicChainPtr chain)
+          : ob::StateValidityChecker(si), chain_(std::move(chain))
+        {
+        }
+        bool isValid(const ob::State *state) const override
+        {
+            std::uint8_t ok = 0;
+            check(b200mp_chain_validate_states(chain_->get(), detail::values(state), 1, &ok), "chain isValid");
+            return ok != 0;
+        }
+        void isValidBatch(const ob::State *const *states, std::size_t n, std::uint8_t *out) const
+        {
+            std::vector<double> q;
+            detail::gather(states, n, chain_->links(), q);
+            check(b200mp_chain_validate_states(chain_->get(), q.data(), static_cast<int64_t>(n), out), "chain isValidBatch");
+        }
+
+    private:
+        KinematicChainPtr chain_;
+    };
+
+    /// ompl::base::DiscreteMotionValidator over the chain (src/ompl/base/src/DiscreteMotionValidator.cpp): the first form checks the end
+    /// state, then the interior states in bisection order (:93-145); the second walks them in order and reports the last valid
+    /// parameter, interpolating lastValid.first when it is given (:48-91). Both maintain valid_ / invalid_ as the reference does.
+    /// One kernel launch per call: every discrete state of the motion is tested at once (the decision, lastValid.second and the counters
+    /// do not depend on the order the states are visited in).
+    class B200DiscreteMotionValidator : public ob::MotionValidator
+    {
+    public:
+        B200DiscreteMotionValidator(ob::SpaceInformation *si, KinematicChainPtr chain) : ob::MotionValidator(si), chain_(std::move(chain))
+        {
+        }
+        B200DiscreteMotionValidator(const ob::SpaceInformationPtr &si, KinematicChainPtr chain)
+          : ob::MotionValidator(si), chain_(std::move(chain))
+        {
+        }
+        bool checkMotion(const ob::State *s1, const ob::State *s2) const override
+        {
+            std::uint8_t ok = 0;
+            check(b200mp_chain_check_motions(chain_->get(), detail::values(s1), detail::values(s2), 1, &ok, nullptr, nullptr), "chain checkMotion");
+            count(ok != 0);
+            return ok != 0;
+        }
+        bool checkMotion(const ob::State *s1, const ob::State *s2, std::pair<ob::State *, double> &lastValid) const override
+        {
+            std::uint8_t ok = 0;
+            double t = -1.0;
+            check(b200mp_chain_check_motions(chain_->get(), detail::values(s1), detail::values(s2), 1, &ok, &t, nullptr), "chain checkMotion");
+            if (!ok)
+            {
+                lastValid.second = t;
+                if (lastValid.first != nullptr)
+                    chain_->interpolate(s1, s2, t, lastValid.first);
+            }
+            count(ok != 0);
+            return ok != 0;
+        }
+        /// Batch extension: out[i] = checkMotion(s1[i], s2[i]); counters advance as n single calls would.
+        void checkMotions(const ob::State *const *s1, const ob::State *const *s2, std::size_t n, std::uint8_t *out) const
+        {
+            std::vector<double> a, b;
+            detail::gather(s1, n, chain_->links(), a);
+            detail::gather(s2, n, chain_->links(), b);
+            check(b200mp_chain_check_motions(chain_->get(), a.data(), b.data(), static_cast<int64_t>(n), out, nullptr, nullptr), "chain checkMotions");
+            for (std::size_t i = 0; i < n; ++i)
+                count(out[i] != 0);
+        }
+
+    private:
+        void count(bool ok) const
+        {
+            std::lock_guard<std::mutex> lk(mu_);  // "must be thread safe" (MotionValidator.h:60-63); the reference's plain ++ is not
+            if (ok)
+                ++valid_;
+            else
+                ++invalid_;
+        }
+        KinematicChainPtr chain_;
+        mutable std::mutex mu_;
     };
 
     /// GPU nearest-neighbour container with the NearestNeighbors<_T> contract. OMPL hands a backend only opaque
@@ -378,6 +592,18 @@ namespace ompl::b200
             dim_ = dim;
             coords_ = std::move(coords);
             check(b200mp_knn_create(engine_->get(), static_cast<int>(dim), B200MP_METRIC_L2, &knn_), "knn_create");
+        }
+
+        /// The same container under KinematicChainSpace::distance (demos/KinematicChain.h:105-121) instead of the Euclidean metric:
+        /// elements are chains of `links` joint angles with the given link length.
+        void bindChain(std::size_t links, double linkLength, CoordFunction coords, EnginePtr engine = nullptr)
+        {
+            if (knn_)
+                throw ompl::Exception("NearestNeighborsB200", "bind() called twice");
+            engine_ = engine ? std::move(engine) : Engine::shared(0);
+            dim_ = links;
+            coords_ = std::move(coords);
+            check(b200mp_knn_create_chain(engine_->get(), static_cast<int>(links), linkLength, &knn_), "knn_create_chain");
         }
 
         bool reportsSortedResults() const override
@@ -529,8 +755,9 @@ namespace ompl::b200
             {
                 const double want = this->distFun_(q, nbh[i]);
                 if (std::fabs(want - dist_[i]) > 1e-9 * std::max(1.0, std::fabs(want)))
-                    throw ompl::Exception("NearestNeighborsB200", "the planner's distance function is not the Euclidean "
-                                                                  "RealVectorStateSpace metric evaluated on the GPU");
+                    throw ompl::Exception("NearestNeighborsB200", "the planner's distance function is not the metric evaluated on the GPU "
+                                                                  "(RealVectorStateSpace::distance after bind, KinematicChainSpace::distance "
+                                                                  "after bindChain)");
             }
             verified_ = true;
         }

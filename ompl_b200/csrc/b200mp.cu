@@ -199,7 +199,7 @@ int build_grids(b200mp_env *e, SceneDesc *d) {
             Piece &p = pieces[l * kShapeClasses + t];
             const auto &cls = boxes[t];
             if (cls.empty()) continue;
-            const float grow = reach[l] * 1.0001f + 1e-4f;  // slack covers rounding in the device-side tests
+            const float grow = reach[l] * 1.0001f + 3e-4f;  // slack covers kHitMargin (bounding spheres are inflated by 0.1 mm) and rounding in the device-side tests
             p.start.assign(cells + 1, 0u);
             std::vector<int> rng(cls.size() * 6);
             for (size_t i = 0; i < cls.size(); ++i) {

@@ -378,6 +378,87 @@ __device__ __forceinline__ bool grid_scan_scene(const GridView &g, const Scene &
     return acc < 0;
 }
 
+// Coarse walk that REMEMBERS what it touches. A link's fine spheres lie inside its bounding sphere (to 1e-8 m, checked when the
+// tables are generated), so a fine sphere can only touch obstacles the bounding sphere touches: the walk tests every candidate of
+// the cell against the bounding sphere inflated by kHitMargin (far above any rounding) and lists the hits -- (class << 16) | record
+// -- in the lane's shared-memory slots; the fine spheres are then tested against that short list directly, without grid walks of
+// their own. A bounding sphere within kHitMargin of an obstacle counts as a coarse hit here where the reference's exact test may
+// not; the fine tests it triggers are exact and cannot hit unless a fine sphere really intersects, so decisions are unchanged.
+// Returns the number of hits, kHitCap + 1 meaning "more than fit": the caller then falls back to per-sphere walks.
+constexpr float kHitMargin = 1.0e-4f;
+constexpr int kHitCap = 6;  // list entries per lane
+
+template <class Test, int BT>
+__device__ __forceinline__ int grid_collect_class(const unsigned *__restrict__ start, const unsigned short *__restrict__ ids, int cell,
+                                                  const float4 *__restrict__ obs, int n, int cls, float x, float y, float z, float r, float rsq,
+                                                  bool on, float *__restrict__ hits, int cnt) {
+    unsigned b = 0, c = 0;
+    if (on) {
+        b = __ldg(start + cell);
+        c = __ldg(start + cell + 1) - b;
+    }
+    const unsigned wmax = __reduce_max_sync(kFull, c);
+#pragma unroll 1
+    for (unsigned i = 0; i < wmax; i += 2) {
+        const int id0 = (i < c) ? static_cast<int>(__ldg(ids + b + i)) : n;
+        const int id1 = (i + 1 < c) ? static_cast<int>(__ldg(ids + b + i + 1)) : n;
+        const float v0 = Test::test(obs + id0 * Test::kRec, x, y, z, r, rsq);
+        const float v1 = Test::test(obs + id1 * Test::kRec, x, y, z, r, rsq);
+        if (v0 < 0.0f) {  // (record n, the far-away stand-in of exhausted lists, never hits)
+            if (cnt < kHitCap) hits[cnt * BT] = __int_as_float((cls << 16) | id0);
+            cnt = min(cnt + 1, kHitCap + 1);
+        }
+        if (v1 < 0.0f) {
+            if (cnt < kHitCap) hits[cnt * BT] = __int_as_float((cls << 16) | id1);
+            cnt = min(cnt + 1, kHitCap + 1);
+        }
+    }
+    return cnt;
+}
+
+template <int BT>
+__device__ __forceinline__ int grid_collect_scene(const GridView &g, const Scene &sc, float x, float y, float z, float r, bool on,
+                                                  float *__restrict__ hits) {
+    const int cell = grid_cell(g, x, y, z);
+    r += kHitMargin;
+    const float rsq = r * r;
+    int cnt = 0;
+    if (sc.n_sph > 0) cnt = grid_collect_class<SphereTest, BT>(g.start[0], g.ids[0], cell, sc.sph, sc.n_sph, 0, x, y, z, r, rsq, on, hits, cnt);
+    if (sc.n_cap > 0) cnt = grid_collect_class<CapsuleTest, BT>(g.start[1], g.ids[1], cell, sc.cap, sc.n_cap, 1, x, y, z, r, rsq, on, hits, cnt);
+    if (sc.n_zcap > 0) cnt = grid_collect_class<ZCapsuleTest, BT>(g.start[2], g.ids[2], cell, sc.zcap, sc.n_zcap, 2, x, y, z, r, rsq, on, hits, cnt);
+    if (sc.n_cub > 0) cnt = grid_collect_class<CuboidTest, BT>(g.start[3], g.ids[3], cell, sc.cub, sc.n_cub, 3, x, y, z, r, rsq, on, hits, cnt);
+    if (sc.n_zcub > 0) cnt = grid_collect_class<ZCuboidTest, BT>(g.start[4], g.ids[4], cell, sc.zcub, sc.n_zcub, 4, x, y, z, r, rsq, on, hits, cnt);
+    return cnt;
+}
+
+// one fine sphere against the lane's list of obstacles (cnt <= kHitCap entries); any_mode as in grid_should_stop
+template <int BT>
+__device__ __forceinline__ bool hits_scan(const Scene &sc, const float *__restrict__ hits, int cnt, float x, float y, float z, float r, bool on,
+                                          bool any_mode) {
+    const float rsq = r * r;
+    const int mine = on ? cnt : 0;
+    const int hmax = __reduce_max_sync(kFull, mine);
+    int acc = 0;
+#pragma unroll 1
+    for (int h = 0; h < hmax; ++h) {
+        if (h < mine) {
+            const int ent = __float_as_int(hits[h * BT]);
+            const int id = ent & 0xffff;
+            float v;
+            switch (ent >> 16) {
+                case 0: v = SphereTest::test(sc.sph + id * SphereTest::kRec, x, y, z, r, rsq); break;
+                case 1: v = CapsuleTest::test(sc.cap + id * CapsuleTest::kRec, x, y, z, r, rsq); break;
+                case 2: v = ZCapsuleTest::test(sc.zcap + id * ZCapsuleTest::kRec, x, y, z, r, rsq); break;
+                case 3: v = CuboidTest::test(sc.cub + id * CuboidTest::kRec, x, y, z, r, rsq); break;
+                default: v = ZCuboidTest::test(sc.zcub + id * ZCuboidTest::kRec, x, y, z, r, rsq); break;
+            }
+            acc |= __float_as_int(v);
+        }
+        if (any_mode && __any_sync(kFull, acc < 0)) break;
+    }
+    return acc < 0;
+}
+
 // ------------------------------------------------------------------------------------------------ point clouds
 __device__ __forceinline__ float aabb_distsq(const float *bb, float x, float y, float z) {
     const float d0 = x - fminf(fmaxf(x, bb[0]), bb[3]);
@@ -502,10 +583,13 @@ __device__ __forceinline__ bool heightfields_hit(const SceneDesc &sd, float x, f
 // ------------------------------------------------------------------------------------------------ one state per lane
 // Per-thread scratch in shared memory: slot s of thread t lives at base[s * BT + t] (bank-conflict free). Slots
 // 3l .. 3l+2 hold the world-space centre of link l's bounding sphere, then sin[dim] and cos[dim] of the joint angles.
+// ... followed by kHitCap slots listing the obstacles the current link's bounding sphere touches (see grid_collect_scene).
 template <class R>
-__host__ __device__ constexpr int lane_slots() { return 3 * R::kLinks + 2 * R::kDim; }
+__host__ __device__ constexpr int lane_slots() { return 3 * R::kLinks + 2 * R::kDim + kHitCap; }
 template <class R>
 __host__ __device__ constexpr int trig_slot() { return 3 * R::kLinks; }
+template <class R>
+__host__ __device__ constexpr int hit_slot() { return 3 * R::kLinks + 2 * R::kDim; }
 template <class R>
 __host__ __device__ constexpr unsigned revolute_mask() {
     unsigned m = 0;
@@ -772,6 +856,8 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
     int l = R::kLinks - 1;   // next link whose bounding sphere is to be tested
     int f = 0, fe = 0;       // fine spheres [f, fe) of the link being refined (f < fe <=> refining)
     bool need = false, fhit = false;
+    float *hit_list = slots + hit_slot<R>() * BT;  // obstacles the current link's bounding sphere touches
+    int hits = 0;
 #pragma unroll 1
     for (;;) {
         const bool fine = f < fe;  // warp-uniform
@@ -795,8 +881,22 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
         }
         const bool any_mode = EDGE && fine;  // fine hit of an edge: the motion is dead, stop at once
         bool h;
-        if (lvl >= 0) h = grid_scan_scene(sd.grid[lvl], sc, x, y, z, r, on, any_mode);
-        else h = ordered_scan_one<G>(&sv.sc, x, y, z, r, on, any_mode);
+        if (!fine) {
+            // bounding sphere: list what it touches (hits > 0 <=> coarse hit); radii beyond the widest grid reach take the ordered scan
+            if (lvl >= 0) {
+                hits = grid_collect_scene<BT>(sd.grid[lvl], sc, x, y, z, r, on, hit_list);
+                h = hits > 0;
+            } else {
+                h = ordered_scan_one<G>(&sv.sc, x, y, z, r, on, false);
+                hits = kHitCap + 1;
+            }
+        } else if (__any_sync(kFull, on && hits > kHitCap)) {
+            // some lane's list overflowed (or was never made): this fine sphere walks the grid itself, as the bounding sphere did
+            if (lvl >= 0) h = grid_scan_scene(sd.grid[lvl], sc, x, y, z, r, on, any_mode);
+            else h = ordered_scan_one<G>(&sv.sc, x, y, z, r, on, any_mode);
+        } else {
+            h = hits_scan<BT>(sc, hit_list, hits, x, y, z, r, on, any_mode);
+        }
         if (sd.n_hf > 0 && on && !h) h = heightfields_hit(sd, x, y, z, r);
         if (sd.n_pc > 0) h |= pointclouds_one(sv.pc, sd.n_pc, x, y, z, r, on && !h, any_mode);
         if (!fine) {

@@ -5,7 +5,11 @@
 //     of single calls with the batch extensions;
 //   * NearestNeighborsB200<State *>: the body of tests/datastructures/nearestneighbors.cpp:stateSpaceTest against
 //     NearestNeighborsLinear (distances equal within 1e-6), nearestR(inf), k > size, remove down to empty, and the
-//     "No elements found" exception.
+//     "No elements found" exception; randomAccessPatternTest (:205-280: rounds of add / nearestK / nearestR / remove);
+//   * the planar chain (config 5): validity checker, DiscreteMotionValidator (both forms, counters, lastValid) and the
+//     container under the chain metric, through the OMPL base classes;
+//   * batched call sites (rewireBatch, checkMotionsFrom, shortcutBatch) against single calls;
+//   * roadmap hand-off: buildRoadmap -> PlannerData -> the loop of PRM(const PlannerData &) (PRM.cpp:96-156), file round trip, GraphML.
 // Usage: adapter_test            -> runs everything on GPU 0 (exit 0 on success)
 //        adapter_test --no-gpu   -> expects engine construction to fail with ompl::Exception (no CPU fallback)
 #include <cmath>
@@ -17,7 +21,13 @@
 #include <vector>
 
 #include "b200mp_ompl.hpp"
+#include "b200mp_ompl_roadmap.hpp"
 #include <ompl/datastructures/NearestNeighborsLinear.h>
+
+#include <map>
+#include <numeric>
+#include <sstream>
+#include <unordered_set>
 
 #include <atomic>
 #include <thread>
@@ -305,6 +315,315 @@ static void test_metric_guard(const b2::EnginePtr &eng)
     EXPECT(threw);
 }
 
+
+// tests/datastructures/nearestneighbors.cpp:205-280 (randomAccessPatternTest), with the reference's sizes scaled down
+// (n = 200 states -> 40 rounds of 10 adds, 10 queries with k in [1, 30] and r in [0, 3], then each stored state removed with p = 1/2)
+static void test_random_access_pattern(const b2::EnginePtr &eng, std::size_t dim)
+{
+    std::mt19937_64 rng(77 + dim);
+    std::uniform_real_distribution<double> coord(-3, 3), u01(0, 1);
+    const int m = 40, n = 10, maxk = 30;
+    const double eps = 1e-6;
+    std::vector<std::unique_ptr<OwnedState>> store;
+    auto fresh = [&]() {
+        std::vector<double> q(dim);
+        for (auto &x : q) x = coord(rng);
+        store.emplace_back(new OwnedState(q));
+        return static_cast<ob::State *>(&store.back()->s);
+    };
+    b2::NearestNeighborsB200<ob::State *> nn;
+    nn.bind(dim, [](ob::State *const &s) { return static_cast<const double *>(s->as<RVState>()->values); }, eng);
+    ompl::NearestNeighbors<ob::State *> &proximity = nn;
+    ompl::NearestNeighborsLinear<ob::State *> linear;
+    auto df = [dim](ob::State *const &x, ob::State *const &y) { return l2(x, y, dim); };
+    proximity.setDistanceFunction(df);
+    linear.setDistanceFunction(df);
+    std::unordered_set<ob::State *> states;
+    std::vector<ob::State *> nghbr, truth;
+    for (int i = 0; i < m; ++i)
+    {
+        for (int j = 0; j < n; ++j)
+        {
+            ob::State *s = fresh();
+            states.insert(s);
+            proximity.add(s);
+            linear.add(s);
+        }
+        for (int j = 0; j < n; ++j)
+        {
+            ob::State *s = fresh();
+            const int k = 1 + static_cast<int>(u01(rng) * maxk) % maxk;
+            linear.nearestK(s, k, truth);
+            proximity.nearestK(s, k, nghbr);
+            EXPECT(nghbr.size() == truth.size());
+            for (std::size_t p = 0; p < std::min(nghbr.size(), truth.size()); ++p) EXPECT(std::fabs(l2(s, truth[p], dim) - l2(s, nghbr[p], dim)) < eps);
+            const double r = 3.0 * u01(rng);
+            linear.nearestR(s, r, truth);
+            proximity.nearestR(s, r, nghbr);
+            EXPECT(nghbr.size() == truth.size());
+            for (std::size_t p = 0; p < std::min(nghbr.size(), truth.size()); ++p) EXPECT(std::fabs(l2(s, truth[p], dim) - l2(s, nghbr[p], dim)) < eps);
+        }
+        for (auto it = states.begin(); it != states.end();)
+        {
+            if (u01(rng) < .5)
+            {
+                const std::size_t szLinear = linear.size(), sz = proximity.size();
+                linear.remove(*it);
+                const bool removed = proximity.remove(*it);
+                it = states.erase(it);
+                EXPECT(removed);
+                EXPECT(proximity.size() == sz - 1);
+                EXPECT(sz == szLinear);
+                EXPECT(proximity.size() == states.size());
+                proximity.list(nghbr);
+                linear.list(truth);
+                EXPECT(nghbr.size() == truth.size());
+            }
+            else
+                ++it;
+        }
+    }
+}
+
+// config 5 through the OMPL interfaces: 20-link chain in the horn environment of demos/KinematicChainBenchmark.cpp:48-49
+static void test_chain_adapters(const b2::EnginePtr &eng)
+{
+    const unsigned int links = 20;
+    const double len = 1.0 / links;
+    auto chain = std::make_shared<b2::KinematicChain>(eng, links, len, b2::KinematicChain::hornEnvironment(links, std::log(static_cast<double>(links)) / links));
+    ob::SpaceInformation *si = nullptr;
+    std::shared_ptr<ob::StateValidityChecker> svc = std::make_shared<b2::B200ChainValidityChecker>(si, chain);
+    std::shared_ptr<ob::MotionValidator> mv = std::make_shared<b2::B200DiscreteMotionValidator>(si, chain);
+    auto *svc_b = dynamic_cast<b2::B200ChainValidityChecker *>(svc.get());
+    auto *mv_b = dynamic_cast<b2::B200DiscreteMotionValidator *>(mv.get());
+
+    // known answers, taken from the compiled reference (oracle/_ref/libref_chain.so = demos/KinematicChain.h): the chain stretched
+    // along +x runs into the horn, the same chain pointing up (first joint at pi/2) is free
+    OwnedState straight(std::vector<double>(links, 0.0));
+    std::vector<double> upq(links, 0.0);
+    upq[0] = 1.5708;
+    OwnedState up(upq);
+    EXPECT(!svc->isValid(&straight.s));
+    EXPECT(svc->isValid(&up.s));
+
+    std::mt19937_64 rng(3);
+    std::uniform_real_distribution<double> first(1.5708 - 1.0, 1.5708 + 1.0), small(-0.35, 0.35);
+    std::vector<std::unique_ptr<OwnedState>> st;
+    for (int i = 0; i < 300; ++i)
+    {
+        std::vector<double> q(links);
+        for (auto &x : q) x = small(rng);  // gently curved chains around the upright pose: about half of them are valid
+        q[0] = first(rng);
+        st.emplace_back(new OwnedState(q));
+    }
+    std::vector<const ob::State *> a, b;
+    for (int i = 0; i < 300; ++i) { a.push_back(&st[i]->s); b.push_back(&st[(i * 7 + 3) % 300]->s); }
+    std::vector<std::uint8_t> sv(300), mvb(300);
+    svc_b->isValidBatch(a.data(), a.size(), sv.data());
+    int nvalid = std::accumulate(sv.begin(), sv.end(), 0);
+    EXPECT(nvalid > 20 && nvalid < 290);
+    mv_b->checkMotions(a.data(), b.data(), a.size(), mvb.data());
+    const unsigned int v0 = mv->getValidMotionCount(), i0 = mv->getInvalidMotionCount();
+    EXPECT(v0 + i0 == 300);
+    EXPECT(static_cast<int>(v0) == std::accumulate(mvb.begin(), mvb.end(), 0));
+    OwnedState scratch(std::vector<double>(links, 0.0));
+    int checked = 0;
+    for (int i = 0; i < 300; i += 5)
+    {
+        EXPECT(svc->isValid(a[i]) == (sv[i] != 0));
+        if (!sv[i]) continue;  // checkMotion assumes a valid start (MotionValidator.h:72-77)
+        const bool ok = mv->checkMotion(a[i], b[i]);
+        EXPECT(ok == (mvb[i] != 0));
+        std::pair<ob::State *, double> last(&scratch.s, -7.0);
+        const bool ok2 = mv->checkMotion(a[i], b[i], last);
+        EXPECT(ok2 == ok);
+        if (!ok)
+        {
+            // lastValid.second = (j - 1) / nd of the first invalid state j; the state handed back is the interpolation at that parameter
+            // and, the start being valid, it is itself valid (DiscreteMotionValidator.cpp:60-71)
+            EXPECT(last.second >= 0.0 && last.second < 1.0);
+            OwnedState want(std::vector<double>(links, 0.0));
+            chain->interpolate(a[i], b[i], last.second, &want.s);
+            for (unsigned int j = 0; j < links; ++j) EXPECT(scratch.v[j] == want.v[j]);
+            EXPECT(svc->isValid(&scratch.s));
+        }
+        else
+            EXPECT(last.second == -7.0);  // untouched on success, like the reference
+        ++checked;
+    }
+    EXPECT(checked > 10);
+    EXPECT(mv->getValidMotionCount() + mv->getInvalidMotionCount() == 300 + 2u * static_cast<unsigned>(checked));
+
+    // nearest neighbours under KinematicChainSpace::distance, against NearestNeighborsLinear with the same metric
+    b2::NearestNeighborsB200<ob::State *> nn;
+    auto df = [&chain](ob::State *const &x, ob::State *const &y) { return chain->distance(x, y); };
+    nn.setDistanceFunction(df);
+    nn.bindChain(links, len, [](ob::State *const &s) { return static_cast<const double *>(s->as<RVState>()->values); }, eng);
+    ompl::NearestNeighborsLinear<ob::State *> linear;
+    linear.setDistanceFunction(df);
+    std::vector<ob::State *> all;
+    for (auto &p : st) all.push_back(&p->s);
+    nn.add(all);
+    linear.add(all);
+    std::vector<ob::State *> got, want;
+    for (int i = 0; i < 300; i += 17)
+    {
+        nn.nearestK(all[i], 10, got);
+        linear.nearestK(all[i], 10, want);
+        EXPECT(got.size() == want.size());
+        for (std::size_t t = 0; t < std::min(got.size(), want.size()); ++t) EXPECT(std::fabs(df(all[i], got[t]) - df(all[i], want[t])) < 1e-9);
+    }
+    // the guard still rejects a functor that is not the bound metric
+    b2::NearestNeighborsB200<ob::State *> wrong;
+    wrong.setDistanceFunction([](ob::State *const &x, ob::State *const &y) { return l2(x, y, 20); });
+    wrong.bindChain(links, len, [](ob::State *const &s) { return static_cast<const double *>(s->as<RVState>()->values); }, eng);
+    wrong.add(all);
+    bool threw = false;
+    try { wrong.nearestK(all[0], 3, got); } catch (const ompl::Exception &) { threw = true; }
+    EXPECT(threw);
+}
+
+// batched call sites of PRM::addMilestone, RRT* and PathSimplifier against the single calls they replace
+static void test_batched_call_sites(const b2::EnginePtr &eng)
+{
+    auto env = std::make_shared<b2::Environment>(eng);
+    const float cage[14][3] = {{0.55, 0, 0.25}, {0.35, 0.35, 0.25}, {0, 0.55, 0.25}, {-0.55, 0, 0.25}, {-0.35, -0.35, 0.25},
+                               {0, -0.55, 0.25}, {0.35, -0.35, 0.25}, {0.35, 0.35, 0.8}, {0, 0.55, 0.8}, {-0.35, 0.35, 0.8},
+                               {-0.55, 0, 0.8}, {-0.35, -0.35, 0.8}, {0, -0.55, 0.8}, {0.35, -0.35, 0.8}};
+    for (const auto &p : cage) env->addSphere({p[0], p[1], p[2]}, 0.2F);
+    env->sort();
+    env->commit();
+    ob::SpaceInformation *si = nullptr;
+    b2::B200MotionValidator<b2::Panda> mv(si, env);
+    std::array<double, 7> lo, hi;
+    b2::getRobotBounds<b2::Panda>(lo, hi);
+    std::mt19937_64 rng(21);
+    std::vector<std::unique_ptr<OwnedState>> st;
+    OwnedState centre({0., -0.785, 0., -2.356, 0., 1.571, 0.785});
+    for (int i = 0; i < 48; ++i)
+    {
+        std::vector<double> q(7);
+        for (int j = 0; j < 7; ++j) q[j] = std::min(hi[j], std::max(lo[j], centre.v[j] + std::uniform_real_distribution<double>(-1.2, 1.2)(rng)));
+        st.emplace_back(new OwnedState(q));
+    }
+    std::vector<const ob::State *> nbh;
+    for (auto &p : st) nbh.push_back(&p->s);
+    std::vector<std::uint8_t> to(48), from(48), fwd(48), rev(48);
+    mv.rewireBatch(&centre.s, nbh.data(), nbh.size(), to.data(), from.data());
+    mv.checkMotionsFrom(&centre.s, nbh.data(), nbh.size(), fwd.data());
+    mv.checkMotionsFrom(&centre.s, nbh.data(), nbh.size(), rev.data(), true);
+    int nv = 0;
+    for (int i = 0; i < 48; ++i)
+    {
+        EXPECT((to[i] != 0) == mv.checkMotion(nbh[i], &centre.s));
+        EXPECT((from[i] != 0) == mv.checkMotion(&centre.s, nbh[i]));
+        EXPECT(fwd[i] == from[i] && rev[i] == to[i]);
+        nv += to[i];
+    }
+    EXPECT(nv > 0 && nv < 48);
+    std::vector<std::uint8_t> only(48);
+    mv.rewireBatch(&centre.s, nbh.data(), nbh.size(), nullptr, only.data());
+    EXPECT(only == from);
+    // shortcuts over a path of 12 way points
+    std::vector<const ob::State *> path(nbh.begin(), nbh.begin() + 12);
+    std::vector<std::pair<std::size_t, std::size_t>> pairs;
+    for (std::size_t i = 0; i < 12; ++i)
+        for (std::size_t j = i + 2; j < 12; j += 3) pairs.emplace_back(i, j);
+    std::vector<std::uint8_t> sc(pairs.size());
+    mv.shortcutBatch(path, pairs, sc.data());
+    for (std::size_t c = 0; c < pairs.size(); ++c) EXPECT((sc[c] != 0) == mv.checkMotion(path[pairs[c].first], path[pairs[c].second]));
+}
+
+// GPU-built roadmap -> ompl::base::PlannerData -> the loop of PRM(const PlannerData &) (PRM.cpp:96-156), restated over the same calls
+static void test_roadmap_handoff(const b2::EnginePtr &eng)
+{
+    auto env = std::make_shared<b2::Environment>(eng);
+    const float c[14][3] = {{0.55, 0, 0.25}, {0.35, 0.35, 0.25}, {0, 0.55, 0.25}, {-0.55, 0, 0.25}, {-0.35, -0.35, 0.25},
+                            {0, -0.55, 0.25}, {0.35, -0.35, 0.25}, {0.35, 0.35, 0.8}, {0, 0.55, 0.8}, {-0.35, 0.35, 0.8},
+                            {-0.55, 0, 0.8}, {-0.35, -0.35, 0.8}, {0, -0.55, 0.8}, {0.35, -0.35, 0.8}};
+    for (const auto &p : c) env->addSphere({p[0], p[1], p[2]}, 0.2F);
+    env->sort();
+    env->commit();
+    const std::size_t n = 6000;
+    const int k = 10;
+    const b2::Roadmap rm = b2::buildRoadmap<b2::Panda>(env, 42, n, k);
+    EXPECT(rm.numStates() == n && rm.dim == 7);
+    EXPECT(rm.numEdges() >= n * k / 2 && rm.numEdges() <= n * k);
+    EXPECT(static_cast<std::size_t>(rm.stats.n_valid_edges) == static_cast<std::size_t>(std::accumulate(rm.valid.begin(), rm.valid.end(), 0)));
+
+    b2::RoadmapStates states(rm);
+    ob::PlannerData data;
+    const std::size_t added = b2::toPlannerData(rm, states, data);
+    EXPECT(added == static_cast<std::size_t>(rm.stats.n_valid_edges));
+    EXPECT(data.numVertices() == n && data.numEdges() == added);
+
+    // PRM(const PlannerData &): every vertex cloned, every edge read with its weight, components united
+    std::vector<std::vector<double>> cloned(data.numVertices());
+    std::vector<unsigned int> parent(data.numVertices());
+    std::iota(parent.begin(), parent.end(), 0u);
+    auto find = [&](unsigned int x) { while (parent[x] != x) x = parent[x] = parent[parent[x]]; return x; };
+    std::size_t graph_edges = 0;
+    double weight_err = 0;
+    for (unsigned int v = 0; v < data.numVertices(); ++v)
+    {
+        const double *q = data.getVertex(v).getState()->as<RVState>()->values;
+        cloned[v].assign(q, q + 7);
+    }
+    for (unsigned int v = 0; v < data.numVertices(); ++v)
+    {
+        std::vector<unsigned int> nb;
+        data.getEdges(v, nb);
+        for (unsigned int w : nb)
+        {
+            ob::Cost cost;
+            EXPECT(data.getEdgeWeight(v, w, &cost));
+            double d = 0;
+            for (int j = 0; j < 7; ++j) d += (cloned[v][j] - cloned[w][j]) * (cloned[v][j] - cloned[w][j]);
+            weight_err = std::max(weight_err, std::fabs(std::sqrt(d) - cost.value()));
+            parent[find(v)] = find(w);
+            ++graph_edges;
+        }
+    }
+    EXPECT(graph_edges == added);
+    EXPECT(weight_err < 1e-12);
+    for (std::size_t i = 0; i < n; i += 997)
+        for (int j = 0; j < 7; ++j) EXPECT(cloned[i][j] == static_cast<double>(rm.states[i * 7 + j]));
+    std::map<unsigned int, std::size_t> comp;
+    for (unsigned int v = 0; v < data.numVertices(); ++v) ++comp[find(v)];
+    std::size_t biggest = 0;
+    for (const auto &kv : comp) biggest = std::max(biggest, kv.second);
+    EXPECT(biggest > n / 2);  // a connected roadmap of the cage's free space
+
+    // file round trip and GraphML
+    const std::string path = "/tmp/b200mp_adapter_test_roadmap.b2rm";
+    b2::saveRoadmap(path, rm);
+    const b2::Roadmap back = b2::loadRoadmap(path);
+    EXPECT(back == rm);
+    EXPECT(back.stats.n_valid_edges == rm.stats.n_valid_edges);
+    std::remove(path.c_str());
+    bool threw = false;
+    try { b2::loadRoadmap("/tmp/b200mp_no_such_file.b2rm"); } catch (const ompl::Exception &) { threw = true; }
+    EXPECT(threw);
+    std::ostringstream xml;
+    b2::writeGraphML(xml, rm);
+    const std::string doc = xml.str();
+    std::size_t nodes = 0, edges = 0;
+    for (std::size_t p = doc.find("<node id="); p != std::string::npos; p = doc.find("<node id=", p + 1)) ++nodes;
+    for (std::size_t p = doc.find("<edge id="); p != std::string::npos; p = doc.find("<edge id=", p + 1)) ++edges;
+    EXPECT(nodes == n && edges == added);
+    EXPECT(doc.find("attr.name=\"coords\"") != std::string::npos && doc.find("attr.name=\"weight\"") != std::string::npos);
+
+    // several GPUs when the box has them: same roadmap, one thread per GPU
+    std::shared_ptr<b2::Engine> eng1;
+    try { eng1 = std::make_shared<b2::Engine>(1); } catch (const ompl::Exception &) {}
+    if (eng1)
+    {
+        const b2::Roadmap two = b2::buildRoadmapMulti<b2::Panda>({env, env->cloneTo(eng1)}, 42, n, k);
+        EXPECT(two == rm);
+        std::printf("buildRoadmapMulti on 2 GPUs: identical roadmap (%zu edges)\n", two.numEdges());
+    }
+}
+
 int main(int argc, char **argv)
 {
     if (argc > 1 && std::strcmp(argv[1], "--no-gpu") == 0)
@@ -331,6 +650,11 @@ int main(int argc, char **argv)
         test_nearest_neighbors(eng, 3, 60, 30);
         test_nearest_neighbors(eng, 20, 300, 10);
         test_metric_guard(eng);
+        test_random_access_pattern(eng, 3);
+        test_random_access_pattern(eng, 7);
+        test_chain_adapters(eng);
+        test_batched_call_sites(eng);
+        test_roadmap_handoff(eng);
     }
     catch (const std::exception &e)
     {

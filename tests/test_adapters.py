@@ -19,13 +19,14 @@ def compile_adapter_test(flavour: str) -> str:
     os.makedirs(BUILD, exist_ok=True)
     out = os.path.join(BUILD, f"adapter_test_{flavour}")
     src = os.path.join(ROOT, "tests", "cpp", "adapter_test.cpp")
-    hdr = os.path.join(ROOT, "include", "b200mp_ompl.hpp")
-    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "include", h) for h in os.listdir(os.path.join(ROOT, "include"))]
+    hdrs += [os.path.join(ROOT, "tests", "ompl_shim", h) for h in os.listdir(os.path.join(ROOT, "tests", "ompl_shim")) if h.endswith(".h")]
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(p) for p in [src] + hdrs):
         return out
     inc = [f"-I{ROOT}/include", f"-I{ROOT}/tests/ompl_shim"]
     inc += [f"-I{REF_SRC}"] if flavour == "genuine" else [f"-I{ROOT}/tests/ompl_mock"]
     cmd = ["g++", "-std=c++17", "-O1", "-pthread", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", *inc,
-           '-DB200MP_OMPL_STATE_HEADER="b200_mock_real_vector_state.h"', src, "-o", out,
+           '-DB200MP_OMPL_STATE_HEADER="b200_mock_real_vector_state.h"', '-DB200MP_OMPL_PLANNERDATA_HEADER="b200_mock_planner_data.h"', src, "-o", out,
            f"-L{ROOT}/ompl_b200", "-lb200mp", f"-Wl,-rpath,{ROOT}/ompl_b200", "-Wl,-rpath,$ORIGIN/../../../ompl_b200"]
     subprocess.run(cmd, check=True)
     return out

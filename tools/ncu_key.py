@@ -1,22 +1,24 @@
 #!/usr/bin/env python3
-"""Key metrics of every launch in an ncu report. usage: ncu_key.py <report.ncu-rep>"""
-import csv, io, subprocess, sys
-txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+"""Key metrics of one launch of an ncu report. usage: ncu_key.py <report.ncu-rep> [launch index]"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_lsu.sum", "sm__inst_executed_pipe_xu.sum",
+        "smsp__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_uniform.sum",
+        "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "smsp__cycles_active.avg", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__average_warp_latency_per_inst_issued.ratio"]
+rep = sys.argv[1]
+idx = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
-hdr, units, data = rows[0], rows[1], rows[2:]
-want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
-        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
-        "smsp__thread_inst_executed_per_inst_executed.ratio"]
-want += [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
-for w in want:
-    if w in hdr:
-        i = hdr.index(w)
-        vals = [r[i] for r in data]
-        try:
-            if max(float(v.replace(",", "")) for v in vals) < 0.05 and "stalled" in w:
-                continue
-        except ValueError:
-            pass
-        print(f"{w.replace('smsp__average_warps_issue_stalled_', 'stall ').replace('_per_issue_active.ratio', '')} [{units[i]}]: " + "  ".join(vals))
+h, v = rows[0], rows[2 + idx]
+for i, name in enumerate(h):
+    if name in KEYS or "issue_stalled" in name and "per_issue_active" in name or name == "Kernel Name":
+        print(f"{name:95s} {v[i][:90]}")
