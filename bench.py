@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--roadmap-n", type=int, default=1 << 20, help="samples of the PRM roadmap build (0 = skip)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the compact config 4 / config 5 blocks")
     ap.add_argument("--no-parity", action="store_true", help="skip the reference check of the built roadmap (all edges + kNN sample, ~1 min of CPU)")
     ap.add_argument("--parity-edges", type=int, default=0, help="check only the first N roadmap edges against the reference (0 = all)")
     args = ap.parse_args()
@@ -346,8 +347,27 @@ def main():
         assert bool(av.all()), "all-valid sub-workload must validate as valid"
         w_ref = w_ref_edge * len(rep) / (ms_av * 1e-3) / 1e12
         # executed flops per launch of exactly this workload, counted by ncu (profiles/validate_flops.json)
-        w_exec_launch, src, traffic = flops_record(len(rep), int(len(valid_idx)))
+        rec = flops_record(len(rep), int(len(valid_idx)))
+        w_exec_launch, src, traffic = (float(rec["flops_per_launch"]), rec.get("source"), rec.get("dram_bytes")) if rec else (None, None, None)
         achieved = (w_exec_launch / (ms_av * 1e-3) / 1e12) if w_exec_launch else w_ref
+        # the dense variant SURVEY 8(d) asks for beside it: the same motions through the ordered scan (sorted scene, candidate grid off),
+        # i.e. every bounding sphere against every obstacle the reference's scan reaches
+        env_dense = synth.fill_env(ompl_b200.Environment(ctx), scene, sort=True, grid=False)
+        dense_ms = []
+        for _ in range(3):
+            evd = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
+                evd[0].record(stream)
+                ctx.validate_motions_ptr("panda", env_dense, a0.data_ptr(), a1.data_ptr(), len(rep), av.data_ptr(), stream=stream.cuda_stream)
+                evd[1].record(stream)
+            stream.synchronize()
+            dense_ms.append(evd[0].elapsed_time(evd[1]))
+        assert bool(av.all()), "dense variant must agree on the all-valid sub-workload"
+        ms_dense = float(np.median(dense_ms[1:]))
+        dflops = float(rec["dense"]["flops_per_launch"]) if rec and rec.get("dense") else None
+        dense_t = (dflops if dflops else w_ref_edge * len(rep)) / (ms_dense * 1e-3) / 1e12
+        del env_dense
         line["roofline"] = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                             "kernel": "validate_motions_kernel<Panda, sorted, grid>",
                             "achieved_is": ("executed FP32 flops/launch (ncu FFMA x2 + FADD + FMUL, " + str(src) + ")")
@@ -355,6 +375,9 @@ def main():
                             "w_ref_tflops": w_ref, "w_ref_flops_per_edge": w_ref_edge,
                             "workload": f"all-valid: {len(valid_idx)} valid motions of the batch tiled to 2^17",
                             "ms_per_launch": ms_av, "states_per_sec": len(rep) * 64 / (ms_av * 1e-3),
+                            "dense": {"kernel": "validate_motions_kernel<Panda, sorted, ordered scan>", "ms_per_launch": ms_dense,
+                                      "achieved": dense_t, "frac": dense_t / peak, "states_per_sec": len(rep) * 64 / (ms_dense * 1e-3),
+                                      "achieved_is": "executed FP32 flops (ncu)" if dflops else "W_ref (oracle-counted reference flops; no ncu count for this build)"},
                             "peak_source": "b200mp_fp32_peak FFMA microbenchmark on this GPU (nominal 148*128*2*1.965 GHz = 74.4)"}
         if not args.no_cpu_baseline:
             chk, kind = checker_env(scene)
@@ -373,12 +396,30 @@ def main():
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"first 2^18 of the 2^20 motions, all host threads; {mism} decisions differ from the GPU",
                                     "all_valid_edges_per_s": nv / dtv, "all_valid_sample": f"{nv} valid motions, {int((wv != 1).sum())} differ"}
+    if world == 1 and not args.no_configs:
+        # ---- BASELINE configs 4 and 5, compact (tools/configs_probe.py holds the full probes): throughput, CPU checker beside it, mismatches
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import configs_probe
+        c4 = configs_probe.c4(ctx, 1 << 20)
+        line["c4"] = {"workload": "Fetch, 2^20 motions x 64 states vs 2^20-point shelf cloud (filtered -> point-cloud tree)",
+                      "edges_per_s": c4["edges_per_s"], "all_valid_states_per_s": c4.get("all_valid_states_per_s"), "ms_filter_gpu": c4["ms_filter_gpu"],
+                      "ms_filter_reference_1thread": c4["ms_filter_reference_1thread"], "filtered_points": c4["filtered_points"],
+                      "filtered_points_reference": c4["filtered_points_reference"], "cpu_baseline": c4["cpu_baseline"],
+                      "reference_on_own_filter": c4.get("reference_pipeline_on_reference_filtered_cloud")}
+        c5 = configs_probe.c5(ctx, 1 << 16)
+        line["c5"] = {"workload": "20-link planar chain, horn environment: 2^20 states, chain-metric kNN k=16 over 2^16 valid states, its edges",
+                      "states_per_s": c5["states_per_s"], "cpu_states": c5["cpu_states"], "knn_queries_per_s": c5["knn_queries_per_s"],
+                      "cpu_knn": c5["cpu_knn"], "edges_per_s": c5["edges_per_s"], "cpu_motions": c5["cpu_motions"]}
     if roadmap is not None:
         if rm_host is not None:
             from oracle import refvamp, refnn
             if refvamp.available() and refnn.available():
                 roadmap["parity"] = roadmap_parity(*rm_host, scene, cores, max_edges=args.parity_edges)
                 line["roadmap_parity_differ_outside"] = roadmap["parity"]["differ_outside"]
+                roadmap["cpu_knn"] = {"value": roadmap["parity"].pop("reference_knn_queries_per_s"), "unit": "queries/s at 2^20 states", "cores": cores,
+                                      "kind": "reference", "sample": f"{roadmap['parity']['knn_queries']} queries, NearestNeighborsLinear via std::function"}
+                roadmap["cpu_edges"] = {"value": roadmap["parity"].pop("reference_edges_per_s"), "unit": "edges/s", "cores": cores, "kind": "reference",
+                                        "sample": "all roadmap edges"}
             else:
                 roadmap["parity"] = {"skipped": "oracle/_ref not built"}
         line["roadmap"] = roadmap  # last: the driver keeps the tail of the line
@@ -386,16 +427,16 @@ def main():
 
 
 def flops_record(motions, unique_valid):
-    """(flops per launch, source, dram bytes) of the all-valid launch from profiles/validate_flops.json -- only if that ncu count was
-    taken on the kernel code of THIS build (sha256 of the validation kernel sources recorded next to it), else (None, None, None)."""
+    """The ncu flop counts of the all-valid launches (profiles/validate_flops.json) -- only if they were taken on the kernel code of
+    THIS build (sha256 of the validation kernel sources recorded next to them) and on this workload, else None."""
     try:
         with open(os.path.join(ROOT, "profiles", "validate_flops.json")) as f:
             pj = json.load(f)
         if pj.get("motions") == motions and pj.get("unique_valid") == unique_valid and pj.get("kernel_sha256") == kernel_hash():
-            return float(pj["flops_per_launch"]), pj.get("source"), pj.get("dram_bytes")
+            return pj
     except Exception:
         pass
-    return None, None, None
+    return None
 
 
 def kernel_hash():

@@ -158,7 +158,16 @@ def c4(ctx, n_motions):
     t_cpu = time.perf_counter() - t0
     line["cpu_baseline"] = {"value": sample / t_cpu, "unit": "edges/s", "cores": CORES, "kind": kind, "sample": f"first {sample} motions",
                             "decisions_differing_from_gpu": int((cv != got[:sample]).sum())}
-    print(json.dumps(line), flush=True)
+    if HAVE_REF:
+        # the whole reference pipeline on its OWN filter output (its unstable sort leaves another order among equal curve codes, so it
+        # keeps a slightly different subset of the cloud): how many decisions that changes
+        cr = refvamp.RefEnvironment()
+        cr.add_pointcloud(ref_kept, *radii)
+        rv = cr.validate_motions("fetch", q0[:sample], q1[:sample], nthreads=CORES)
+        line["reference_pipeline_on_reference_filtered_cloud"] = {"filtered_points": int(len(ref_kept)), "sample": sample,
+                                                                  "decisions_differing_from_gpu": int((rv != got[:sample]).sum()),
+                                                                  "gpu_valid_reference_invalid": int(((got[:sample] == 1) & (rv == 0)).sum())}
+    return line
 
 
 def c5(ctx, n_knn):
@@ -215,7 +224,7 @@ def c5(ctx, n_knn):
     line.update({"edges": int(len(a)), "ms_check_motions": t_mot * 1e3, "edges_per_s": len(a) / t_mot, "valid_edge_fraction": float(mv.mean()),
                  "cpu_motions": {"value": ms / t_cpu_mot, "unit": "edges/s", "cores": 1, "kind": kind, "sample": f"first {ms} edges",
                                  "decisions_differing_from_gpu": int((cm != mv[:ms]).sum())}})
-    print(json.dumps(line), flush=True)
+    return line
 
 
 if __name__ == "__main__":
@@ -229,6 +238,6 @@ if __name__ == "__main__":
     if args.only in ("", "c1"):
         c1(ctx, args.c1_seeds)
     if args.only in ("", "c4"):
-        c4(ctx, args.c4_motions)
+        print(json.dumps(c4(ctx, args.c4_motions)), flush=True)
     if args.only in ("", "c5"):
-        c5(ctx, args.c5_knn)
+        print(json.dumps(c5(ctx, args.c5_knn)), flush=True)

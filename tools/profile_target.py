@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """ncu target (GPU box): the bench's own workloads as a short, fixed launch sequence.
-  validate_motions launches: #0 warm-up (2^14 mixed), #1 C2 mixed 2^20 (the bench step), #2 C2 all-valid 2^17 (the roofline launch)
+  validate_motions launches: #0 warm-up (2^14 mixed), #1 C2 mixed 2^20 (the bench step), #2 C2 all-valid 2^17 (the roofline launch),
+                             #3 the same all-valid motions through the ordered scan (candidate grid off: the dense variant)
   then one single-GPU roadmap build (n = 2^18, k = 16): sample / validate_states / compaction / kNN index + cells / edges / validate
 Prints the facts profiles/validate_flops.json is keyed on (motions, unique_valid)."""
 import json
@@ -37,6 +38,9 @@ valid_idx = np.nonzero(v == 1)[0]
 rep = np.resize(valid_idx, 1 << 17)
 va = run(env, q0[rep], q1[rep])
 assert va.all()
+env_dense = synth.fill_env(ompl_b200.Environment(ctx), scene, sort=True, grid=False)
+vd = run(env_dense, q0[rep], q1[rep])
+assert vd.all()
 if "--no-roadmap" not in sys.argv:
     r = ctx.prm_build("panda", env, 1 << 18, 16, 42, want_weights=False)
     print(json.dumps(r["stats"]))

@@ -50,6 +50,13 @@ def flops(path, facts_path):
     out.update(flops_per_launch=2 * ffma + fadd + fmul, ffma=ffma, fadd=fadd, fmul=fmul, duration_ns_under_ncu=m.get("gpu__time_duration.sum"),
                dram_bytes=m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0),
                source="ncu smsp__sass_thread_inst_executed_op_{ffma,fadd,fmul}_pred_on.sum, tools/profile_target.py launch #2")
+    if len(ids) > 3:  # launch #3: the same motions through the ordered scan (dense variant)
+        d = by_id[ids[3]]
+        out["dense"] = dict(flops_per_launch=2 * d["smsp__sass_thread_inst_executed_op_ffma_pred_on.sum"] +
+                            d["smsp__sass_thread_inst_executed_op_fadd_pred_on.sum"] + d["smsp__sass_thread_inst_executed_op_fmul_pred_on.sum"],
+                            duration_ns_under_ncu=d.get("gpu__time_duration.sum"),
+                            dram_bytes=d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0),
+                            inst_executed=d.get("smsp__inst_executed.sum"), inst_fma_pipe=d.get("sm__inst_executed_pipe_fma.sum"))
     mixed = by_id[ids[1]]
     out["mixed_launch"] = dict(flops=2 * mixed["smsp__sass_thread_inst_executed_op_ffma_pred_on.sum"] +
                                mixed["smsp__sass_thread_inst_executed_op_fadd_pred_on.sum"] + mixed["smsp__sass_thread_inst_executed_op_fmul_pred_on.sum"],
