@@ -199,7 +199,9 @@ int b200mp_knn_query_part_device_f32(b200mp_knn *knn, const float *d_q, int64_t 
                                      int n_parts, int64_t *d_idx, double *d_dist, void *stream);
 /* The same sharing for roadmap construction: only the neighbour ids, as int32, into d_ids[nq][k] (rows of other parts untouched;
  * a table pre-filled with -1 combines across GPUs with ONE element-wise max all-reduce of nq * k * 4 bytes). Always answered
- * through the cell index, whatever the batch size. k <= 64. */
+ * through the cell index, whatever the batch size. k <= 64. exclude_self = 2 selects the CAUSAL query of incremental PRM: query i
+ * sees only the points with ids below self_base + i (what nn_->nearestK returns when milestone i is inserted, PRM.cpp:583,601);
+ * rows of early queries hold fewer than k ids, padded with -1. */
 int b200mp_knn_query_part_ids_device_f32(b200mp_knn *knn, const float *d_q, int64_t nq, int k, int64_t self_base, int exclude_self, int part,
                                          int n_parts, int32_t *d_ids, void *stream);
 /* nearestR: all points with distance <= radius, ascending; *count = how many exist, at most cap are written.
@@ -278,9 +280,14 @@ int b200mp_comm_create(b200mp_ctx *ctx, const void *unique_id, int rank, int wor
 int b200mp_comm_create_all(b200mp_ctx *const *ctxs, int n, b200mp_comm **out /* [n] */);
 void b200mp_comm_destroy(b200mp_comm *comm);
 int b200mp_comm_rank(const b200mp_comm *comm, int *rank, int *world);
-int b200mp_prm_build_multi(b200mp_comm *comm, int robot, const b200mp_env *env, uint64_t seed, int64_t n, int k, int resolution,
+int b200mp_prm_build_multi(b200mp_comm *comm, int robot, const b200mp_env *env, uint64_t seed, int64_t n, int k, int resolution, int flags,
                            float *states, int32_t *edges, uint8_t *valid, double *weights, int32_t *neighbors /* [n][min(k, n - 1)], may be NULL */,
                            int64_t edge_capacity, b200mp_roadmap_stats *stats);
+/* flags of b200mp_prm_build_multi. B200MP_PRM_INCREMENTAL: the graph stock PRM grows when the states are inserted in index order --
+ * state i is connected to its k nearest among the states 0 .. i - 1 only (KStrategy queried before nn_->add, PRM.cpp:583,601), every
+ * such pair is an edge (no symmetric union), checked neighbour -> new milestone like PRM::addMilestone (PRM.cpp:585-598). Slower than
+ * the default (early states have few candidates, so their searches reach far), meant for graph-for-graph comparison with stock OMPL. */
+enum { B200MP_PRM_INCREMENTAL = 1 };
 /* A copy of `src` (primitive shapes, grid setting; scenes with point clouds or height fields are refused with
  * B200MP_ERR_CAPACITY) on another context, committed when `src` is. */
 int b200mp_env_clone(const b200mp_env *src, b200mp_ctx *dst_ctx, b200mp_env **out);

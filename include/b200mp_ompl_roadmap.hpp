@@ -87,11 +87,12 @@ namespace ompl::b200
     }
 
     /// The same roadmap built by several GPUs of this node, one thread per GPU (b200mp_comm_create_all + b200mp_prm_build_multi; NCCL
-    /// inside the library). envs[r] holds the scene on GPU r's engine (Environment::cloneTo copies one across engines). The result is
-    /// identical to buildRoadmap's for any number of GPUs.
+    /// inside the library). envs[r] holds the scene on GPU r's engine (Environment::cloneTo copies one across engines); one environment
+    /// is the single-GPU case. The result is identical to buildRoadmap's for any number of GPUs. incremental: the graph stock PRM grows
+    /// from the same states inserted in index order (B200MP_PRM_INCREMENTAL), for graph-for-graph comparison with ompl::geometric::PRM.
     template <typename Robot>
     inline Roadmap buildRoadmapMulti(const std::vector<EnvironmentPtr> &envs, std::uint64_t seed, std::size_t n, int k, int resolution = 0,
-                                     bool wantNeighbors = false)
+                                     bool wantNeighbors = false, bool incremental = false)
     {
         const int g = static_cast<int>(envs.size());
         if (g < 1)
@@ -112,7 +113,7 @@ namespace ompl::b200
                 const bool root = r == 0;
                 b200mp_roadmap_stats st{};
                 rc[r] = b200mp_prm_build_multi(comms[r], Robot::id, envs[r]->get(), seed, static_cast<std::int64_t>(n), k, resolution,
-                                               root ? out.states.data() : nullptr, root ? out.edges.data() : nullptr,
+                                               incremental ? B200MP_PRM_INCREMENTAL : 0, root ? out.states.data() : nullptr, root ? out.edges.data() : nullptr,
                                                root ? out.valid.data() : nullptr, root ? out.weights.data() : nullptr,
                                                root && wantNeighbors ? out.neighbors.data() : nullptr, static_cast<std::int64_t>(out.valid.size()),
                                                &st);

@@ -726,13 +726,14 @@ knn_point_kernel(const float4 *__restrict__ feat_s, const double *__restrict__ p
                         if (!__any_sync(kFullMask, anyh)) continue;
                         const int rr = r[h];
                         const int id = anyh ? __ldg(orig + rr) : -1;
+                        const bool causal = use_self == 2;  // only points inserted before the query (ids below its own)
 #pragma unroll
                         for (int b = 0; b < QB; ++b) {
                             bool cand = pass[h][b];
                             if (!__any_sync(kFullMask, cand)) continue;
                             // exact distance, the reference's arithmetic (RealVectorStateSpace.cpp:230-242), by the lane that holds the row
                             double d2 = 0.0;
-                            if (cand && id != self[b]) {
+                            if (cand && (causal ? id < self[b] : id != self[b])) {
                                 for (int j = 0; j < dim; ++j) {
                                     const double diff = pts_s[static_cast<long long>(rr) * dim + j] - q64[qi[b] * dim + j];
                                     d2 = __dadd_rn(d2, __dmul_rn(diff, diff));  // no FMA contraction: bit-identical to the reference's x86-64 doubles

@@ -86,7 +86,7 @@ def load_library():
     L.b200mp_comm_create_all.argtypes = [_vp, C.c_int, _vp]
     L.b200mp_comm_destroy.argtypes = [_vp]
     L.b200mp_comm_rank.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    L.b200mp_prm_build_multi.argtypes = [_vp, C.c_int, _vp, C.c_uint64, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64,
+    L.b200mp_prm_build_multi.argtypes = [_vp, C.c_int, _vp, C.c_uint64, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64,
                                          C.POINTER(RoadmapStats)]
     L.b200mp_env_clone.argtypes = [_vp, _vp, C.POINTER(_vp)]
     L.b200mp_knn_query_part_ids_device_f32.argtypes = [_vp, _vp, _i64, C.c_int, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp]
@@ -327,13 +327,15 @@ class Comm:
             pass
 
     def prm_build(self, robot: str, env: "Environment", n: int, k: int, seed: int, resolution: int = 0, want_arrays: bool = True,
-                  want_weights: bool = True, want_neighbors: bool = False):
-        """Collective roadmap build (b200mp_prm_build_multi); every rank receives the whole roadmap when want_arrays."""
+                  want_weights: bool = True, want_neighbors: bool = False, incremental: bool = False):
+        """Collective roadmap build (b200mp_prm_build_multi); every rank receives the whole roadmap when want_arrays.
+        incremental: B200MP_PRM_INCREMENTAL -- state i is connected to its k nearest among states 0 .. i - 1 only, stock PRM's graph."""
         dim = robot_info(robot)["dim"]
         cap = n * k
         st = RoadmapStats()
+        flags = 1 if incremental else 0
         if not want_arrays:
-            _check(self._L.b200mp_prm_build_multi(self._h, ROBOTS[robot], env._h, seed, n, k, resolution, None, None, None, None, None, cap,
+            _check(self._L.b200mp_prm_build_multi(self._h, ROBOTS[robot], env._h, seed, n, k, resolution, flags, None, None, None, None, None, cap,
                                                   C.byref(st)))
             return dict(stats=st.as_dict())
         states = np.empty((n, dim), np.float32)
@@ -341,7 +343,7 @@ class Comm:
         valid = np.empty(cap, np.uint8)
         weights = np.empty(cap, np.float64) if want_weights else None
         nbr = np.empty((n, min(k, n - 1)), np.int32) if want_neighbors and n > 1 else None
-        _check(self._L.b200mp_prm_build_multi(self._h, ROBOTS[robot], env._h, seed, n, k, resolution, states.ctypes.data, edges.ctypes.data,
+        _check(self._L.b200mp_prm_build_multi(self._h, ROBOTS[robot], env._h, seed, n, k, resolution, flags, states.ctypes.data, edges.ctypes.data,
                                               valid.ctypes.data, weights.ctypes.data if want_weights else None,
                                               nbr.ctypes.data if nbr is not None else None, cap, C.byref(st)))
         e = int(st.n_edges)

@@ -186,7 +186,7 @@ def test_two_gpu_single_process_threads(ctx):
         edges = np.empty((cap, 2), np.int32)
         valid = np.empty(cap, np.uint8)
         w = np.empty(cap, np.float64)
-        rc = L.b200mp_prm_build_multi(comms[r], 0, envs[r], seed, n, k, 0, states.ctypes.data, edges.ctypes.data, valid.ctypes.data, w.ctypes.data,
+        rc = L.b200mp_prm_build_multi(comms[r], 0, envs[r], seed, n, k, 0, 0, states.ctypes.data, edges.ctypes.data, valid.ctypes.data, w.ctypes.data,
                                       None, cap, C.byref(st))
         res[r] = (rc, states, edges[:st.n_edges], valid[:st.n_edges], w[:st.n_edges])
 
@@ -219,4 +219,31 @@ def test_comm_of_one_needs_no_nccl(ctx):
     nn.add(a["states"].astype(np.float64))
     idx, _, _ = nn.nearest_k(a["states"][:256].astype(np.float64), 8, self_ids=np.arange(256))
     np.testing.assert_array_equal(a["neighbors"][:256], idx.astype(np.int32))
+    comm.close()
+
+
+def test_incremental_mode_is_stock_prm_graph(ctx):
+    """B200MP_PRM_INCREMENTAL: state i is connected to its k nearest among 0 .. i - 1 (PRM::addMilestone with KStrategy queried before
+    nn_->add, PRM.cpp:583-601): edge set equal to a brute-force restatement of that loop, validity equal to the motion entry point."""
+    env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
+    n, k = 3000, 10
+    comm = ompl_b200.Comm(ctx, None, 0, 1)
+    r = comm.prm_build("panda", env, n, k, 7, want_neighbors=True, incremental=True)
+    base = ctx.prm_build("panda", env, n, k, 7)
+    np.testing.assert_array_equal(r["states"], base["states"])          # same milestones, only the connection rule differs
+    s = r["states"].astype(np.float64)
+    want_edges = []
+    for i in range(1, n):
+        d2 = np.zeros(i)
+        for j in range(7):
+            diff = s[:i, j] - s[i, j]
+            d2 += diff * diff
+        order = np.lexsort((np.arange(i), d2))[:k]
+        np.testing.assert_array_equal(r["neighbors"][i, :len(order)], order)
+        assert (r["neighbors"][i, len(order):] == -1).all()
+        want_edges += [(int(j), i) for j in order]
+    assert (r["neighbors"][0] == -1).all()
+    np.testing.assert_array_equal(r["edges"], np.array(want_edges, np.int32))
+    e = r["edges"]
+    np.testing.assert_array_equal(r["valid"], ctx.validate_motions("panda", env, r["states"][e[:, 0]], r["states"][e[:, 1]]))
     comm.close()
