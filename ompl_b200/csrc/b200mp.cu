@@ -299,6 +299,7 @@ void b200mp_destroy(b200mp_ctx *c) {
     c->scratch.release();
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->h_small) cudaFreeHost(c->h_small);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -776,12 +777,23 @@ int validate_motions_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T
     float *d_q0 = reinterpret_cast<float *>(c->scratch.ptr);
     float *d_q1 = reinterpret_cast<float *>(c->scratch.ptr + qbytes);
     uint8_t *d_valid = reinterpret_cast<uint8_t *>(c->scratch.ptr + 2 * qbytes);
-    constexpr int64_t kChunk = int64_t(1) << 18;
-    if (std::is_same<T, float>::value && m >= 2 * kChunk) {
-        // large fp32 batches: chunks of 2^18 motions, the upload of chunk i + 1 and the download of chunk i - 1 overlap the
-        // kernel of chunk i (three streams, one event pair per chunk; overlap needs pinned caller buffers, pageable ones just serialise)
+    // Large batches go through in chunks: the upload of chunk i + 1 and the download of chunk i - 1 overlap the kernel of chunk i (three
+    // streams, one event pair per chunk). fp32 states are copied straight from the caller's buffers (the overlap needs them pinned,
+    // pageable ones just serialise); fp64 states (what OMPL stores) are cast chunk by chunk into a two-slot pinned staging ring, so the
+    // cast of chunk i + 1 on the host also overlaps the copies and the kernel of chunk i.
+    constexpr bool kIsFloat = std::is_same<T, float>::value;
+    constexpr int64_t kChunk = kIsFloat ? (int64_t(1) << 18) : (int64_t(1) << 16);
+    if (m >= 2 * kChunk) {
         if (!c->h2d_stream) B200_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
         if (!c->d2h_stream) B200_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        const size_t slot_floats = static_cast<size_t>(kChunk) * dim;  // one array of one slot
+        if (!kIsFloat && c->stage_cap < 4 * slot_floats * sizeof(float)) {
+            if (c->h_stage) cudaFreeHost(c->h_stage);
+            c->h_stage = nullptr;
+            c->stage_cap = 0;
+            B200_CUDA(cudaHostAlloc(&c->h_stage, 4 * slot_floats * sizeof(float), cudaHostAllocDefault));
+            c->stage_cap = 4 * slot_floats * sizeof(float);
+        }
         const int n_chunks = static_cast<int>((m + kChunk - 1) / kChunk);
         std::vector<cudaEvent_t> up(n_chunks), done(n_chunks);
         for (int i = 0; i < n_chunks; ++i) {
@@ -792,8 +804,20 @@ int validate_motions_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T
         for (int i = 0; i < n_chunks && !err; ++i) {
             const int64_t first = i * kChunk, cnt = std::min<int64_t>(kChunk, m - first);
             const size_t off = static_cast<size_t>(first) * dim, bytes = static_cast<size_t>(cnt) * dim * sizeof(float);
-            cudaError_t ce = cudaMemcpyAsync(d_q0 + off, reinterpret_cast<const float *>(q0) + off, bytes, cudaMemcpyHostToDevice, c->h2d_stream);
-            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_q1 + off, reinterpret_cast<const float *>(q1) + off, bytes, cudaMemcpyHostToDevice, c->h2d_stream);
+            const float *s0 = reinterpret_cast<const float *>(q0) + off, *s1 = reinterpret_cast<const float *>(q1) + off;
+            cudaError_t ce = cudaSuccess;
+            if (!kIsFloat) {
+                float *h0 = static_cast<float *>(c->h_stage) + static_cast<size_t>(i & 1) * 2 * slot_floats, *h1 = h0 + slot_floats;
+                if (i >= 2) ce = cudaEventSynchronize(up[i - 2]);  // the slot's previous contents have been uploaded
+                for (size_t t = 0; t < static_cast<size_t>(cnt) * dim; ++t) {  // ompl_to_vamp: static_cast<float>(values[i])
+                    h0[t] = static_cast<float>(q0[off + t]);
+                    h1[t] = static_cast<float>(q1[off + t]);
+                }
+                s0 = h0;
+                s1 = h1;
+            }
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_q0 + off, s0, bytes, cudaMemcpyHostToDevice, c->h2d_stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_q1 + off, s1, bytes, cudaMemcpyHostToDevice, c->h2d_stream);
             if (ce == cudaSuccess) ce = cudaEventRecord(up[i], c->h2d_stream);
             if (ce == cudaSuccess) ce = cudaStreamWaitEvent(c->stream, up[i], 0);
             if (ce != cudaSuccess) { err = fail(B200MP_ERR_CUDA, "b200mp_validate_motions: upload failed: %s", cudaGetErrorString(ce)); break; }

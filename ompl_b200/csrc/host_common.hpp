@@ -62,6 +62,8 @@ struct b200mp_ctx {
     void *h_small = nullptr;   // host address
     void *d_small = nullptr;   // the same memory as the device sees it
     size_t small_cap = 0;
+    void *h_stage = nullptr;   // pinned two-slot ring the chunked fp64 entry points cast into
+    size_t stage_cap = 0;
     b200mp::Scratch scratch;
     std::mutex mu;
     std::mutex build_mu;        // one roadmap build at a time per context

@@ -21,7 +21,8 @@ def compile_adapter_test(flavour: str) -> str:
     src = os.path.join(ROOT, "tests", "cpp", "adapter_test.cpp")
     hdrs = [os.path.join(ROOT, "include", h) for h in os.listdir(os.path.join(ROOT, "include"))]
     hdrs += [os.path.join(ROOT, "tests", "ompl_shim", h) for h in os.listdir(os.path.join(ROOT, "tests", "ompl_shim")) if h.endswith(".h")]
-    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(p) for p in [src] + hdrs):
+    lib = os.path.join(ROOT, "ompl_b200", "libb200mp.so")
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(p) for p in [src, lib] + hdrs):
         return out
     inc = [f"-I{ROOT}/include", f"-I{ROOT}/tests/ompl_shim"]
     inc += [f"-I{REF_SRC}"] if flavour == "genuine" else [f"-I{ROOT}/tests/ompl_mock"]
@@ -53,10 +54,10 @@ def test_adapters_on_gpu():
     ran = 0
     for flavour in ("genuine", "mock"):
         exe = os.path.join(BUILD, f"adapter_test_{flavour}")
-        if not os.path.exists(exe):
-            if flavour not in flavours():
-                continue
-            exe = compile_adapter_test(flavour)
+        if flavour in flavours():
+            exe = compile_adapter_test(flavour)  # (rebuilt when the headers or the test are newer than the binary)
+        elif not os.path.exists(exe):
+            continue
         r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "all passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
         ran += 1

@@ -140,6 +140,18 @@ def test_double_precision_entry_points(ctx):
                                   ctx.validate_motions("panda", env, q.astype(np.float32), q1.astype(np.float32)))
 
 
+def test_double_precision_large_batch_is_chunked(ctx):
+    """fp64 batches of >= 2^17 motions go through the chunked pipeline (host cast into a pinned ring overlapping copies and kernels):
+    same answers as the fp32 entry point, ragged last chunk included."""
+    env = synth.fill_env(ompl_b200.Environment(ctx), synth.clutter_scene(1234, 120, 120))
+    m = (1 << 17) + (1 << 16) + 77
+    q0, q1 = synth.fixed_length_edges("panda", m, 99, 0.3, 1.2)
+    want = ctx.validate_motions("panda", env, q0, q1)
+    got = ctx.validate_motions("panda", env, q0.astype(np.float64), q1.astype(np.float64))
+    np.testing.assert_array_equal(got, want)
+    assert 0 < want.sum() < m
+
+
 def test_device_pointer_entry_points(ctx):
     import torch
     scene = synth.clutter_scene(16, 60, 60)
