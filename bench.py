@@ -343,7 +343,7 @@ def main():
         device_pass(3, a0, a1, av, len(rep))
         l1 = ctx.launch_count
         ms_av = device_pass(args.steps, a0, a1, av, len(rep)) / args.steps
-        assert ctx.launch_count - l1 == args.steps
+        assert ctx.launch_count - l1 >= args.steps
         assert bool(av.all()), "all-valid sub-workload must validate as valid"
         w_ref = w_ref_edge * len(rep) / (ms_av * 1e-3) / 1e12
         # executed flops per launch of exactly this workload, counted by ncu (profiles/validate_flops.json)

@@ -283,6 +283,16 @@ int b200mp_create(int device, b200mp_ctx **out) {
                     prop.major, prop.minor);
     }
     B200_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        // stream-ordered temporaries (bucketed validation, roadmap phases) come from the device's default pool: keep what it has
+        // acquired across synchronisations instead of handing it back to the driver after every call
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     B200_CUDA(cudaMalloc(&c->d_counters, sizeof(LaunchCounters) * kCounterRing * kCounterStride));
     c->small_cap = size_t(256) << 10;
     B200_CUDA(cudaHostAlloc(&c->h_small, c->small_cap, cudaHostAllocMapped));
@@ -903,13 +913,20 @@ int b200mp_validate_motions_device(b200mp_ctx *c, int robot, const b200mp_env *e
     if (resolution < 0) return fail(B200MP_ERR_INVALID, "b200mp_validate_motions_device: negative resolution");
     B200_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    // batches are bucketed by length on the device: short motions share warp passes, long ones get a first look (validate_launch.cuh)
+    static const bool bucketed_ok = !(getenv("B200MP_MOTIONS_BUCKETED") && atoi(getenv("B200MP_MOTIONS_BUCKETED")) == 0);
+    const bool bucketed = bucketed_ok && m >= 4096;
+#define B200_MOTIONS(R)                                                                                                        \
+    (bucketed ? launch_motions_bucketed<R>(c, e->desc, d_q0, d_q1, nullptr, m, resolution ? resolution : R::kResolution, d_valid, st) \
+              : launch_motions<R>(c, e->desc, d_q0, d_q1, nullptr, m, resolution ? resolution : R::kResolution, d_valid, st))
     switch (robot) {
-        case B200MP_ROBOT_PANDA: return launch_motions<Panda>(c, e->desc, d_q0, d_q1, nullptr, m, resolution ? resolution : Panda::kResolution, d_valid, st);
-        case B200MP_ROBOT_FETCH: return launch_motions<Fetch>(c, e->desc, d_q0, d_q1, nullptr, m, resolution ? resolution : Fetch::kResolution, d_valid, st);
-        case B200MP_ROBOT_UR5: return launch_motions<Ur5>(c, e->desc, d_q0, d_q1, nullptr, m, resolution ? resolution : Ur5::kResolution, d_valid, st);
-        case B200MP_ROBOT_BAXTER: return launch_motions<Baxter>(c, e->desc, d_q0, d_q1, nullptr, m, resolution ? resolution : Baxter::kResolution, d_valid, st);
+        case B200MP_ROBOT_PANDA: return B200_MOTIONS(Panda);
+        case B200MP_ROBOT_FETCH: return B200_MOTIONS(Fetch);
+        case B200MP_ROBOT_UR5: return B200_MOTIONS(Ur5);
+        case B200MP_ROBOT_BAXTER: return B200_MOTIONS(Baxter);
         default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
     }
+#undef B200_MOTIONS
 }
 
 int b200mp_validate_edges_device(b200mp_ctx *c, int robot, const b200mp_env *e, const float *d_states, const int32_t *d_edges, int64_t m,

@@ -952,6 +952,11 @@ struct BucketPlan {
     unsigned pass_end[kRakeBuckets];  // warp passes up to and including bucket b (b <= 4)
     unsigned long long next_pass;     // work queue head of validate_rakes_kernel
     LaunchCounters long_queue;        // work queue head of validate_motions_kernel over bucket 5
+    // first look at the long motions (bucket 5): rake 0 of four motions per warp pass, see validate_rakes_kernel
+    unsigned pre_passes;              // ceil(cnt[5] / 4)
+    unsigned pre_sample;              // passes that always run; their outcome decides about the rest
+    unsigned pre_done, pre_killed, pre_tested;
+    unsigned pre_decision;            // 0 undecided, 1 run the remaining first-look passes, 2 skip them
 };
 
 // Threads per block / blocks per SM of the validation kernels (measured on C2: the motion kernel gains ~4 % from 20 warps
@@ -1011,7 +1016,10 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
         if (lane == 0) e = atomicAdd(&cnt->next, 1ull);
         e = __shfl_sync(kFull, e, 0);
         if (e >= static_cast<unsigned long long>(m)) break;
-        if (list != nullptr) e = __ldg(list + e);
+        if (list != nullptr) {
+            e = __ldg(list + e);
+            if (valid[e] == 0) continue;  // the first look (validate_rakes_kernel) already found it in collision
+        }
 
         float a[D], v[D], q[D], back[D];
         // roadmap edges address their end points in one state table (pairs != nullptr: q0 == q1 == the table)
@@ -1070,7 +1078,8 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long bar;
     __shared__ SphereLevels<R> lv;
-    const unsigned total = plan->pass_end[kRakeBuckets - 2];
+    const unsigned short_passes = plan->pass_end[kRakeBuckets - 2];
+    const unsigned total = short_passes + plan->pre_passes;
     if (total == 0) return;
     fill_levels<R>(sd, lv);
     stage_scene(smem, sd.blob, sd.blob_floats, &bar);
@@ -1089,11 +1098,32 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
         p64 = __shfl_sync(kFull, p64, 0);
         if (p64 >= total) break;
         const unsigned p = static_cast<unsigned>(p64);
+        // First look at the LONG motions (the passes after the short buckets): rake 0 -- eight states spread over the whole motion -- of
+        // four motions per pass. Where most motions are in collision (random end points) this settles them at a quarter of a warp pass
+        // each; validate_motions_kernel then skips what is already invalid. Where most survive it would only add work, so the first
+        // pre_sample passes always run and their kill rate decides whether the remaining ones do (decided on the device, no host round trip).
+        const bool first_look = p >= short_passes;
         int b = 1;
-        while (p >= plan->pass_end[b]) ++b;  // (warp-uniform; at most three steps)
-        const unsigned t = 4u * (p - plan->pass_end[b - 1]) + static_cast<unsigned>(group);
-        const unsigned ei = t / static_cast<unsigned>(b);
-        const int rake = static_cast<int>(t - ei * static_cast<unsigned>(b));
+        unsigned t;
+        if (first_look) {
+            const unsigned lp = p - short_passes;
+            if (lp >= plan->pre_sample) {
+                unsigned dec = 0;
+                if (lane == 0) {
+                    const volatile unsigned *flag = &plan->pre_decision;
+                    while ((dec = *flag) == 0u) __nanosleep(200);
+                }
+                dec = __shfl_sync(kFull, dec, 0);
+                if (dec == 2u) continue;
+            }
+            b = kRakeBuckets - 1;
+            t = 4u * lp + static_cast<unsigned>(group);
+        } else {
+            while (p >= plan->pass_end[b]) ++b;  // (warp-uniform; at most three steps)
+            t = 4u * (p - plan->pass_end[b - 1]) + static_cast<unsigned>(group);
+        }
+        const unsigned ei = first_look ? t : t / static_cast<unsigned>(b);
+        const int rake = first_look ? 0 : static_cast<int>(t - ei * static_cast<unsigned>(b));
         bool active = ei < plan->cnt[b];
         const unsigned e = active ? __ldg(list + plan->off[b] + ei) : 0xffffffffu;
         if (active && valid[e] == 0) active = false;  // another pass already found this motion in collision
@@ -1110,7 +1140,7 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
             v[j] = active ? __ldg(q1 + ib * D + j) - a[j] : 0.0f;
         }
         // n = max(ceil(dist / rake * resolution), 1)  (planning/validate.hh:41) = b: the pre-pass computed it with the motion kernel's expression
-        const float denom = static_cast<float>(8 * b);
+        const float denom = static_cast<float>(8 * b);  // (not used by a first look: rake 0 takes no back-step)
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             q[j] = fmaf(v[j], pct, a[j]);  // block = start + vector * percents
@@ -1128,10 +1158,27 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
             const bool ag = __shfl_sync(kFull, active ? 1 : 0, 8 * g2) != 0;
             if (ag && eg == e) kill |= 0xffu << (8 * g2);
         }
-        if (!__any_sync(kFull, active)) continue;
-        const bool good = check_state<R, 8, false, MASKED, GRID, motion_threads<R>(), true>(q, sd, sc, slots, lv, sv, active, kill);
-        const bool bad = group_any<8>(active && !good);
-        if (bad && (lane & 7) == 0) valid[e] = 0;
+        bool bad = false;
+        if (__any_sync(kFull, active)) {
+            const bool good = check_state<R, 8, false, MASKED, GRID, motion_threads<R>(), true>(q, sd, sc, slots, lv, sv, active, kill);
+            bad = group_any<8>(active && !good);
+            if (bad && (lane & 7) == 0) valid[e] = 0;
+        }
+        if (first_look && p - short_passes < plan->pre_sample) {
+            const unsigned tested = __popc(__ballot_sync(kFull, active && (lane & 7) == 0));
+            const unsigned killed = __popc(__ballot_sync(kFull, bad && (lane & 7) == 0));
+            if (lane == 0) {
+                atomicAdd(&plan->pre_tested, tested);
+                atomicAdd(&plan->pre_killed, killed);
+                __threadfence();
+                if (atomicAdd(&plan->pre_done, 1u) + 1u == plan->pre_sample) {
+                    // the sample is complete: go on with the first look only if it settles most motions
+                    const unsigned k = atomicAdd(&plan->pre_killed, 0u), n = atomicAdd(&plan->pre_tested, 0u);
+                    __threadfence();
+                    atomicExch(&plan->pre_decision, 2u * k > n ? 1u : 2u);
+                }
+            }
+        }
     }
 }
 
@@ -1173,7 +1220,7 @@ bucket_count_kernel(const float *__restrict__ q0, const float *__restrict__ q1, 
 }
 
 // one block: bucket offsets and pass counts; blk_cnt[block][key] -> exclusive prefix over the blocks (in place)
-static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__restrict__ plan, unsigned *__restrict__ blk_cnt, int nb) {
+static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__restrict__ plan, unsigned *__restrict__ blk_cnt, int nb, int first_look) {
     __shared__ unsigned s_part[1024][kRakeBuckets];
     const int t = threadIdx.x;
     const int chunk = (nb + 1023) / 1024, b0 = t * chunk, b1 = min(nb, b0 + chunk);
@@ -1186,11 +1233,20 @@ static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__
 #pragma unroll
     for (int k = 0; k < kRakeBuckets; ++k) s_part[t][k] = sum[k];
     __syncthreads();
-    if (t < kRakeBuckets) {  // one thread per key: running sum over the 1024 partials (tiny)
-        unsigned run = 0;
-        for (int i = 0; i < 1024; ++i) {
-            const unsigned v = s_part[i][t];
-            s_part[i][t] = run;
+    if (t < 32 * kRakeBuckets) {  // one warp per key: exclusive scan of the 1024 partials, 32 consecutive ones per lane
+        const int key = t >> 5, ln = t & 31;
+        unsigned mine = 0;
+        for (int i = 0; i < 32; ++i) mine += s_part[ln * 32 + i][key];
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned up = __shfl_up_sync(kFull, incl, o);
+            if (ln >= o) incl += up;
+        }
+        unsigned run = incl - mine;
+        for (int i = 0; i < 32; ++i) {
+            const unsigned v = s_part[ln * 32 + i][key];
+            s_part[ln * 32 + i][key] = run;
             run += v;
         }
     }
@@ -1216,6 +1272,13 @@ static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__
         }
         plan->next_pass = 0;
         plan->long_queue.next = 0;
+        const unsigned pre = first_look ? (plan->cnt[kRakeBuckets - 1] + 3u) / 4u : 0u;
+        plan->pre_passes = pre;
+        plan->pre_sample = pre <= 256u ? pre : max(256u, pre / 16u);
+        plan->pre_done = 0;
+        plan->pre_killed = 0;
+        plan->pre_tested = 0;
+        plan->pre_decision = pre == 0u ? 2u : 0u;
     }
 }
 

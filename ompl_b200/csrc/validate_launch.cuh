@@ -2,6 +2,7 @@
 // compile in parallel. b200mp.cu declares them `extern template`.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "validate.cuh"
 #include "host_common.hpp"
@@ -65,7 +66,8 @@ int launch_motions_bucketed(b200mp_ctx *c, const SceneDesc &desc, const float *d
     BucketPlan *plan = reinterpret_cast<BucketPlan *>(tmp + o_plan);
     cudaMemsetAsync(plan, 0, sizeof(BucketPlan), st);
     bucket_count_kernel<R><<<nb, 256, 0, st>>>(d_q0, d_q1, d_pairs, m, resolution, keys, d_valid, blk, plan);
-    bucket_plan_kernel<<<1, 1024, 0, st>>>(plan, blk, static_cast<int>(nb));
+    static const bool first_look = !(getenv("B200MP_FIRST_LOOK") && atoi(getenv("B200MP_FIRST_LOOK")) == 0);
+    bucket_plan_kernel<<<1, 1024, 0, st>>>(plan, blk, static_cast<int>(nb), first_look ? 1 : 0);
     bucket_scatter_kernel<<<nb, 256, 0, st>>>(keys, m, blk, list, plan);
     const long long wpb = motion_threads<R>() / 32;
     const long long cap = std::max<long long>(1, (m + wpb - 1) / wpb);
