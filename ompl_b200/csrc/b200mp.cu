@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <map>
 #include <memory>
 #include <tuple>
@@ -804,7 +805,14 @@ int validate_motions_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T
             B200_CUDA(cudaHostAlloc(&c->h_stage, 4 * slot_floats * sizeof(float), cudaHostAllocDefault));
             c->stage_cap = 4 * slot_floats * sizeof(float);
         }
-        const int n_chunks = static_cast<int>((m + kChunk - 1) / kChunk);
+        // chunk boundaries: the first chunk's upload is the only one nothing overlaps, every chunk costs a kernel sequence with its own
+        // tail, so few chunks win (measured on 2^20 C2 motions: 2^18 then doubling 4.87 ms, 2 x 2^19 4.86, 2^16 then doubling 5.34, one chunk 5.31)
+        std::vector<int64_t> bounds{0};
+        constexpr int64_t kMaxChunk = kIsFloat ? 2 * kChunk : kChunk;  // (fp64: a chunk must fit a slot of the staging ring)
+        const char *e0 = getenv("B200MP_CHUNK0"), *e1 = getenv("B200MP_CHUNKMAX");  // (development switches, fp32 only)
+        const int64_t first_sz = e0 && kIsFloat ? atoll(e0) : kChunk, max_sz = e1 && kIsFloat ? atoll(e1) : kMaxChunk;
+        for (int64_t sz = first_sz; bounds.back() < m; sz = std::min<int64_t>(2 * sz, max_sz)) bounds.push_back(std::min<int64_t>(m, bounds.back() + sz));
+        const int n_chunks = static_cast<int>(bounds.size()) - 1;
         std::vector<cudaEvent_t> up(n_chunks), done(n_chunks);
         for (int i = 0; i < n_chunks; ++i) {
             B200_CUDA(cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming));
@@ -812,17 +820,27 @@ int validate_motions_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T
         }
         int err = B200MP_OK;
         for (int i = 0; i < n_chunks && !err; ++i) {
-            const int64_t first = i * kChunk, cnt = std::min<int64_t>(kChunk, m - first);
+            const int64_t first = bounds[i], cnt = bounds[i + 1] - bounds[i];
             const size_t off = static_cast<size_t>(first) * dim, bytes = static_cast<size_t>(cnt) * dim * sizeof(float);
             const float *s0 = reinterpret_cast<const float *>(q0) + off, *s1 = reinterpret_cast<const float *>(q1) + off;
             cudaError_t ce = cudaSuccess;
             if (!kIsFloat) {
                 float *h0 = static_cast<float *>(c->h_stage) + static_cast<size_t>(i & 1) * 2 * slot_floats, *h1 = h0 + slot_floats;
                 if (i >= 2) ce = cudaEventSynchronize(up[i - 2]);  // the slot's previous contents have been uploaded
-                for (size_t t = 0; t < static_cast<size_t>(cnt) * dim; ++t) {  // ompl_to_vamp: static_cast<float>(values[i])
-                    h0[t] = static_cast<float>(q0[off + t]);
-                    h1[t] = static_cast<float>(q1[off + t]);
-                }
+                // ompl_to_vamp: static_cast<float>(values[i]); four host threads share the cast of a chunk (it would otherwise be the
+                // slowest stage of the pipeline)
+                const size_t total = static_cast<size_t>(cnt) * dim;
+                auto cast = [&](size_t b, size_t e2) {
+                    for (size_t t = b; t < e2; ++t) {
+                        h0[t] = static_cast<float>(q0[off + t]);
+                        h1[t] = static_cast<float>(q1[off + t]);
+                    }
+                };
+                constexpr size_t kCastThreads = 4;
+                std::thread helpers[kCastThreads - 1];
+                for (size_t w = 1; w < kCastThreads; ++w) helpers[w - 1] = std::thread(cast, total * w / kCastThreads, total * (w + 1) / kCastThreads);
+                cast(0, total / kCastThreads);
+                for (auto &th : helpers) th.join();
                 s0 = h0;
                 s1 = h1;
             }

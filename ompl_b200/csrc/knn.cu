@@ -1173,12 +1173,13 @@ __global__ void knn_chain_all_distances_kernel(const double *__restrict__ link64
     out[i] = dead[i] ? INFINITY : __dmul_rn(dist, link_len);
 }
 
-// exact distance of one query to every point, filtered by radius, sorted by (distance, id); caller holds ctx->mu
-int knn_radius_impl(b200mp_knn *k, const double *q, double radius, int64_t self, std::vector<std::pair<double, int64_t>> &sel) {
+// exact distance of one host query to every point (removed points: +inf) into the context's scratch buffer; caller holds ctx->mu
+int knn_all_distances(b200mp_knn *k, const double *q, double **d_all_out, size_t extra_bytes = 0) {
     B200_CUDA(cudaSetDevice(k->ctx->device));
     cudaStream_t st = k->ctx->stream;
-    int rc = k->ctx->scratch.reserve(static_cast<size_t>(k->n) * sizeof(double) + static_cast<size_t>(k->dim) * 3 * sizeof(double) +
-                                     static_cast<size_t>(k->nl) * 2 * sizeof(float) + 512);
+    const size_t head = (static_cast<size_t>(k->n) * sizeof(double) + static_cast<size_t>(k->dim) * 3 * sizeof(double) +
+                         static_cast<size_t>(k->nl) * 2 * sizeof(float) + 512 + 255) / 256 * 256;
+    int rc = k->ctx->scratch.reserve(head + extra_bytes);
     if (rc) return rc;
     double *d_all = reinterpret_cast<double *>(k->ctx->scratch.ptr);
     double *d_q = d_all + k->n;
@@ -1193,6 +1194,154 @@ int knn_radius_impl(b200mp_knn *k, const double *q, double radius, int64_t self,
     knn_all_distances_kernel<<<static_cast<unsigned>((k->n + 255) / 256), 256, 0, st>>>(k->d_pts, k->d_feat, k->nv * 4, k->n, k->dim, d_q, d_all);
     B200_CUDA(cudaGetLastError());
     k->ctx->launches.fetch_add(1);
+    *d_all_out = d_all;
+    return B200MP_OK;
+}
+
+// ---- large k on the device: radix select of the k-th smallest distance, then a sort of what lies at or below it -------------------
+// (RRT* asks nearestK with k = ceil(k_rrt log n), planners like PRM* with KStarStrategy grow k with the roadmap: past the list sizes of
+// the tiled / cell kernels a query used to copy all n distances to the host and sort them there)
+struct SelectState {
+    unsigned long long prefix;   // bits of the k-th smallest key fixed so far (from the top)
+    unsigned long long want;     // rank still to find among the keys that share the prefix
+    unsigned long long n_out;    // entries emitted by the compaction
+    unsigned hist[256];
+};
+
+__device__ __forceinline__ unsigned long long dist_key(double d) { return static_cast<unsigned long long>(__double_as_longlong(d)); }  // d >= 0 or +inf: order preserving
+
+__global__ void knn_select_init_kernel(SelectState *s, unsigned long long want, double *__restrict__ d_all, long long self) {
+    if (threadIdx.x == 0) { s->prefix = 0; s->want = want; s->n_out = 0; }
+    s->hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0 && self >= 0) d_all[self] = INFINITY;  // the excluded point can never be selected
+}
+
+// histogram of the byte at `shift` over the keys whose higher bits equal the prefix
+__global__ void __launch_bounds__(256) knn_select_hist_kernel(const double *__restrict__ d_all, long long n, int shift, SelectState *s) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long prefix = s->prefix;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const unsigned long long key = dist_key(d_all[i]);
+        if (shift == 56 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&h[(key >> shift) & 255ull], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&s->hist[threadIdx.x], h[threadIdx.x]);
+}
+
+// one thread: the byte in which the wanted rank falls; histogram cleared for the next pass
+__global__ void knn_select_step_kernel(SelectState *s, int shift) {
+    unsigned long long want = s->want, acc = 0;
+    int b = 0;
+    for (; b < 255; ++b) {
+        if (acc + s->hist[b] >= want) break;
+        acc += s->hist[b];
+    }
+    s->prefix |= static_cast<unsigned long long>(b) << shift;
+    s->want = want - acc;
+    for (int i = 0; i < 256; ++i) s->hist[i] = 0;
+}
+
+// everything at or below the k-th smallest key (ties included), as (key, id) pairs in arbitrary order
+__global__ void knn_select_compact_kernel(const double *__restrict__ d_all, long long n, SelectState *s, unsigned long long *__restrict__ keys,
+                                          int *__restrict__ ids, long long cap) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = dist_key(d_all[i]);
+    if (key <= s->prefix && key < 0x7ff0000000000000ull) {
+        const unsigned long long p = atomicAdd(&s->n_out, 1ull);
+        if (static_cast<long long>(p) < cap) { keys[p] = key; ids[p] = static_cast<int>(i); }
+    }
+}
+
+__global__ void knn_select_pad_kernel(unsigned long long *__restrict__ keys, int *__restrict__ ids, const SelectState *s, long long padded) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < padded && i >= static_cast<long long>(s->n_out)) { keys[i] = ~0ull; ids[i] = 0x7fffffff; }
+}
+
+// one compare-exchange stage of a bitonic network over (key, id) pairs, ascending by (key, id)
+__global__ void knn_bitonic_stage_kernel(unsigned long long *__restrict__ keys, int *__restrict__ ids, long long padded, long long kk, long long j) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= padded) return;
+    const long long l = i ^ j;
+    if (l <= i) return;
+    const unsigned long long a = keys[i], b = keys[l];
+    const int ia = ids[i], ib = ids[l];
+    const bool up = (i & kk) == 0;
+    const bool gt = a > b || (a == b && ia > ib);
+    if (gt == up) { keys[i] = b; keys[l] = a; ids[i] = ib; ids[l] = ia; }
+}
+
+__global__ void knn_select_emit_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ ids, const SelectState *s, int k,
+                                       long long *__restrict__ idx, double *__restrict__ dist, int *__restrict__ count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    const bool have = static_cast<unsigned long long>(t) < s->n_out;
+    idx[t] = have ? ids[t] : -1;
+    dist[t] = have ? __longlong_as_double(static_cast<long long>(keys[t])) : INFINITY;
+    if (t == 0 && count) *count = static_cast<int>(min(static_cast<unsigned long long>(k), s->n_out));
+}
+
+// k nearest of one host query, any k, selected and ordered on the device; results to host buffers. caller holds ctx->mu
+int knn_query_large_k(b200mp_knn *k, const double *q, int kq, int64_t self, int64_t *idx, double *dist, int *count) {
+    // scratch behind the distances: select state | keys[cap] | ids[cap] | idx[kq] | dist[kq] | count ; cap = padded (k + room for ties)
+    long long padded = 1;
+    while (padded < static_cast<long long>(kq) + 1024) padded *= 2;
+    padded = std::min<long long>(padded, 1LL << 31);
+    const size_t o_keys = 2048, o_ids = o_keys + static_cast<size_t>(padded) * 8, o_idx = o_ids + static_cast<size_t>(padded) * 4;
+    const size_t o_dist = o_idx + static_cast<size_t>(kq) * 8, o_cnt = o_dist + static_cast<size_t>(kq) * 8, extra = o_cnt + 64;
+    double *d_all = nullptr;
+    int rc = knn_all_distances(k, q, &d_all, extra);
+    if (rc) return rc;
+    cudaStream_t st = k->ctx->stream;
+    const size_t head = (static_cast<size_t>(k->n) * sizeof(double) + static_cast<size_t>(k->dim) * 3 * sizeof(double) +
+                         static_cast<size_t>(k->nl) * 2 * sizeof(float) + 512 + 255) / 256 * 256;
+    char *base = k->ctx->scratch.ptr + head;
+    SelectState *s = reinterpret_cast<SelectState *>(base);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(base + o_keys);
+    int *ids = reinterpret_cast<int *>(base + o_ids);
+    long long *d_idx = reinterpret_cast<long long *>(base + o_idx);
+    double *d_dist = reinterpret_cast<double *>(base + o_dist);
+    int *d_cnt = reinterpret_cast<int *>(base + o_cnt);
+    const long long n = k->n;
+    const unsigned sel_blocks = static_cast<unsigned>(std::min<long long>((n + 255) / 256, static_cast<long long>(k->ctx->sm_count) * 8));
+    const unsigned long long want = static_cast<unsigned long long>(std::min<long long>(kq, n));
+    knn_select_init_kernel<<<1, 256, 0, st>>>(s, want, d_all, self);
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        knn_select_hist_kernel<<<sel_blocks, 256, 0, st>>>(d_all, n, shift, s);
+        knn_select_step_kernel<<<1, 1, 0, st>>>(s, shift);
+    }
+    knn_select_compact_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(d_all, n, s, keys, ids, padded);
+    knn_select_pad_kernel<<<static_cast<unsigned>((padded + 255) / 256), 256, 0, st>>>(keys, ids, s, padded);
+    long long launches = 20;
+    for (long long kk2 = 2; kk2 <= padded; kk2 <<= 1)
+        for (long long j = kk2 >> 1; j > 0; j >>= 1) {
+            knn_bitonic_stage_kernel<<<static_cast<unsigned>((padded + 255) / 256), 256, 0, st>>>(keys, ids, padded, kk2, j);
+            ++launches;
+        }
+    knn_select_emit_kernel<<<(kq + 255) / 256, 256, 0, st>>>(keys, ids, s, kq, d_idx, d_dist, d_cnt);
+    B200_CUDA(cudaGetLastError());
+    k->ctx->launches.fetch_add(launches + 1);
+    B200_CUDA(cudaMemcpyAsync(idx, d_idx, static_cast<size_t>(kq) * 8, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(dist, d_dist, static_cast<size_t>(kq) * 8, cudaMemcpyDeviceToHost, st));
+    int h_cnt = 0;
+    B200_CUDA(cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+    unsigned long long n_out = 0;
+    B200_CUDA(cudaMemcpyAsync(&n_out, &s->n_out, sizeof(n_out), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    if (static_cast<long long>(n_out) > padded)  // more than 1024 points tie with the k-th distance: not reachable with real data
+        return fail(B200MP_ERR_CAPACITY, "knn (large k): %llu points at or below the k-th distance exceed the selection buffer", n_out);
+    if (count) *count = h_cnt;
+    return B200MP_OK;
+}
+
+// exact distance of one query to every point, filtered by radius, sorted by (distance, id); caller holds ctx->mu
+int knn_radius_impl(b200mp_knn *k, const double *q, double radius, int64_t self, std::vector<std::pair<double, int64_t>> &sel) {
+    double *d_all = nullptr;
+    int rc = knn_all_distances(k, q, &d_all);
+    if (rc) return rc;
+    cudaStream_t st = k->ctx->stream;
     std::vector<double> all(static_cast<size_t>(k->n));
     B200_CUDA(cudaMemcpyAsync(all.data(), d_all, static_cast<size_t>(k->n) * sizeof(double), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
@@ -1735,19 +1884,17 @@ int b200mp_knn_query(b200mp_knn *k, const double *q, int64_t nq, int kq, const i
     }
     std::lock_guard<std::mutex> lk(k->ctx->mu);
     if (kq > kMaxK) {
-        // large k (RRT* asks for k ~ k_rrt log n, often >= size): exhaustive sorted list per query
-        std::vector<std::pair<double, int64_t>> sel;
+        // large k (RRT* asks for k ~ k_rrt log n, k >= size means "everything, sorted"): per query all exact distances, then a radix
+        // select + sort on the device; only the k results cross to the host
         for (int64_t i = 0; i < nq; ++i) {
-            int rc = B200MP_OK;
-            sel.clear();
-            if (k->n > 0) rc = knn_radius_impl(k, q + i * k->dim, INFINITY, self_ids ? self_ids[i] : -1, sel);
-            if (rc) return rc;
-            const int64_t c = std::min<int64_t>(kq, static_cast<int64_t>(sel.size()));
-            for (int64_t t = 0; t < kq; ++t) {
-                idx[i * kq + t] = t < c ? sel[t].second : -1;
-                dist[i * kq + t] = t < c ? sel[t].first : INFINITY;
+            int c = 0;
+            if (k->n > 0) {
+                const int rc = knn_query_large_k(k, q + i * k->dim, kq, self_ids ? self_ids[i] : -1, idx + i * kq, dist + i * kq, &c);
+                if (rc) return rc;
+            } else {
+                for (int64_t t = 0; t < kq; ++t) { idx[i * kq + t] = -1; dist[i * kq + t] = INFINITY; }
             }
-            if (counts) counts[i] = static_cast<int>(c);
+            if (counts) counts[i] = c;
         }
         return B200MP_OK;
     }

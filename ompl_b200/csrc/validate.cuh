@@ -1100,19 +1100,18 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
         const unsigned p = static_cast<unsigned>(p64);
         // First look at the LONG motions (the passes after the short buckets): rake 0 -- eight states spread over the whole motion -- of
         // four motions per pass. Where most motions are in collision (random end points) this settles them at a quarter of a warp pass
-        // each; validate_motions_kernel then skips what is already invalid. Where most survive it would only add work, so the first
-        // pre_sample passes always run and their kill rate decides whether the remaining ones do (decided on the device, no host round trip).
+        // each; validate_motions_kernel then skips what is already invalid. Where most survive it would only add work, so the kill rate of
+        // the first pre_sample passes decides whether the first look goes on (decided on the device, no host round trip).
         const bool first_look = p >= short_passes;
         int b = 1;
         unsigned t;
         if (first_look) {
             const unsigned lp = p - short_passes;
             if (lp >= plan->pre_sample) {
+                // beyond the sample: run unless the verdict is already "skip" (no waiting for it: until the sample is complete the
+                // first look simply goes on, which costs at most a pass per warp where it turns out not to pay)
                 unsigned dec = 0;
-                if (lane == 0) {
-                    const volatile unsigned *flag = &plan->pre_decision;
-                    while ((dec = *flag) == 0u) __nanosleep(200);
-                }
+                if (lane == 0) dec = *reinterpret_cast<const volatile unsigned *>(&plan->pre_decision);
                 dec = __shfl_sync(kFull, dec, 0);
                 if (dec == 2u) continue;
             }
@@ -1274,7 +1273,7 @@ static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__
         plan->long_queue.next = 0;
         const unsigned pre = first_look ? (plan->cnt[kRakeBuckets - 1] + 3u) / 4u : 0u;
         plan->pre_passes = pre;
-        plan->pre_sample = pre <= 256u ? pre : max(256u, pre / 16u);
+        plan->pre_sample = pre <= 1024u ? pre : max(1024u, pre / 16u);
         plan->pre_done = 0;
         plan->pre_killed = 0;
         plan->pre_tested = 0;

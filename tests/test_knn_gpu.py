@@ -131,7 +131,7 @@ def test_single_query_large_database(ctx):
     idx, dist, _ = nn.nearest_k(q, 16)
     ridx, rdist = port.knn(db, q, 16, nthreads=8)
     np.testing.assert_array_equal(idx, ridx)
-    np.testing.assert_array_equal(dist, rdist)
+    np.testing.assert_allclose(dist, rdist, rtol=1e-12)  # (device sincos vs libm: last-bit differences in the link tables)
 
 
 @pytest.mark.parametrize("dim,n,nq,k,kind", [(7, 40000, 40000, 16, "self"), (8, 50000, 6000, 10, "uniform"), (14, 33000, 5000, 32, "uniform"),
@@ -172,3 +172,49 @@ def test_cell_index_equals_exhaustive_search(ctx, dim, n, nq, k, kind):
     nn.remove(victim)
     idx2, _, _ = nn.nearest_k(qs[:5000], k, self_ids=None if self_ids is None else self_ids[:5000])
     assert victim not in idx2
+
+
+@pytest.mark.parametrize("n,dim,k", [(100000, 7, 6000), (5000, 3, 4999), (3000, 6, 5000)])
+def test_large_k_is_selected_on_the_device(ctx, n, dim, k):
+    """k beyond the kernels' list sizes (RRT* / PRM* style k ~ log n, or "everything, sorted"): radix select + sort on the device.
+    Same answer as a full sort: ids ascending by (distance, id), distances the reference's doubles, missing entries -1 / +inf."""
+    rng = np.random.default_rng(n + k)
+    db = rng.uniform(-2, 2, (n, dim))
+    db[7] = db[3]                       # an exact duplicate: ties are ordered by id
+    nn = ompl_b200.NearestNeighbors(ctx, dim)
+    nn.add(db)
+    nn.remove(11)
+    q = rng.uniform(-2, 2, (2, dim))
+    q[1] = db[5]
+    before = ctx.launch_count
+    idx, dist, cnt = nn.nearest_k(q, k, self_ids=np.array([-1, 5]))
+    assert ctx.launch_count - before > 20   # the device path, not a host sort
+    for i in range(2):
+        d2 = np.zeros(n)
+        for j in range(dim):
+            diff = db[:, j] - q[i, j]
+            d2 += diff * diff
+        d = np.sqrt(d2)
+        d[11] = np.inf
+        if i == 1:
+            d[5] = np.inf
+        order = np.lexsort((np.arange(n), d))
+        live = int(np.isfinite(d).sum())
+        m = min(k, live)
+        assert cnt[i] == m
+        np.testing.assert_array_equal(idx[i, :m], order[:m])
+        np.testing.assert_array_equal(dist[i, :m], d[order[:m]])
+        assert (idx[i, m:] == -1).all() and np.isinf(dist[i, m:]).all()
+
+
+def test_large_k_chain_metric(ctx):
+    n, links = 4000, 20
+    rng = np.random.default_rng(1)
+    db = rng.uniform(-np.pi, np.pi, (n, links))
+    nn = ompl_b200.NearestNeighbors(ctx, links, metric=1, link_length=1.0 / links)
+    nn.add(db)
+    idx, dist, cnt = nn.nearest_k(db[:1], 1000)
+    ridx, rdist = port.knn(db, db[:1], 1000, metric=1, param=1.0 / links, nthreads=4)
+    assert cnt[0] == 1000
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_allclose(dist, rdist, rtol=1e-12)  # (device sincos vs libm: last-bit differences in the link tables)
