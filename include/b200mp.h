@@ -25,7 +25,8 @@
  * Conventions: every function returns B200MP_OK (0) or an error code; b200mp_last_error() gives the text for the
  * calling thread. Batch buffers are caller-owned, contiguous, row-major. "_device" variants take device pointers
  * that live on the context's GPU and an optional cudaStream_t passed as void* (NULL = the context's own stream);
- * they do not synchronise. Host variants are synchronous and thread-safe (calls on one context are serialised).
+ * they do not synchronise. Host variants are synchronous and thread-safe: small validation calls (a planner thread's single
+ * isValid / checkMotion) run concurrently on per-call lanes (own stream + mapped buffer), large ones are serialised per context.
  * There is no CPU fallback: without a CUDA device b200mp_create fails with B200MP_ERR_NO_DEVICE.
  */
 #ifndef B200MP_H

@@ -298,6 +298,11 @@ int b200mp_create(int device, b200mp_ctx **out) {
     c->small_cap = size_t(256) << 10;
     B200_CUDA(cudaHostAlloc(&c->h_small, c->small_cap, cudaHostAllocMapped));
     B200_CUDA(cudaHostGetDevicePointer(&c->d_small, c->h_small, 0));
+    for (auto &ln : c->lanes) {
+        B200_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        B200_CUDA(cudaHostAlloc(&ln.h, b200mp_ctx::kLaneBytes, cudaHostAllocMapped));
+        B200_CUDA(cudaHostGetDevicePointer(&ln.d, ln.h, 0));
+    }
     *out = guard.release();
     return B200MP_OK;
 }
@@ -311,6 +316,10 @@ void b200mp_destroy(b200mp_ctx *c) {
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->h_small) cudaFreeHost(c->h_small);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (auto &ln : c->lanes) {
+        if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
+        if (ln.h) cudaFreeHost(ln.h);
+    }
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -744,6 +753,19 @@ int check_common(const char *who, b200mp_ctx *c, const b200mp_env *e, const void
     return B200MP_OK;
 }
 
+// a free small-call lane, or nullptr when all are taken (the caller then goes through the context mutex like a large call)
+b200mp_small_lane *acquire_lane(b200mp_ctx *c) {
+    for (auto &ln : c->lanes) {
+        bool expected = false;
+        if (ln.busy.compare_exchange_strong(expected, true, std::memory_order_acquire)) return &ln;
+    }
+    return nullptr;
+}
+struct LaneGuard {
+    b200mp_small_lane *ln;
+    ~LaneGuard() { if (ln) ln->busy.store(false, std::memory_order_release); }
+};
+
 // host float -> device float (direct) or host double -> pinned float staging -> device
 template <typename T>
 int upload_states(b200mp_ctx *c, const T *h, int64_t count, float *d, cudaStream_t st) {
@@ -768,9 +790,26 @@ int validate_motions_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T
     rc = b200mp_robot_info(robot, &dim, nullptr, &res, nullptr, nullptr);
     if (rc) return rc;
     if (m == 0) return B200MP_OK;
+    const size_t qbytes = static_cast<size_t>(m) * dim * sizeof(float);
+    if (2 * qbytes + static_cast<size_t>(m) + 64 <= b200mp_ctx::kLaneBytes) {
+        // a planner's single checkMotion (or a handful): own lane, no context lock; inputs cast straight into the mapped buffer, result
+        // read back from it -- one launch and one stream synchronise per call
+        LaneGuard g{acquire_lane(c)};
+        if (g.ln) {
+            B200_CUDA(cudaSetDevice(c->device));
+            float *h0 = static_cast<float *>(g.ln->h), *h1 = h0 + static_cast<size_t>(m) * dim;
+            for (int64_t i = 0; i < m * dim; ++i) { h0[i] = static_cast<float>(q0[i]); h1[i] = static_cast<float>(q1[i]); }
+            const float *d0 = static_cast<const float *>(g.ln->d);
+            uint8_t *dv = reinterpret_cast<uint8_t *>(g.ln->d) + 2 * qbytes;
+            rc = b200mp_validate_motions_device(c, robot, e, d0, d0 + static_cast<size_t>(m) * dim, m, resolution, dv, g.ln->stream);
+            if (rc) return rc;
+            B200_CUDA(cudaStreamSynchronize(g.ln->stream));
+            std::memcpy(valid, static_cast<const uint8_t *>(g.ln->h) + 2 * qbytes, static_cast<size_t>(m));
+            return B200MP_OK;
+        }
+    }
     std::lock_guard<std::mutex> lk(c->mu);
     B200_CUDA(cudaSetDevice(c->device));
-    const size_t qbytes = static_cast<size_t>(m) * dim * sizeof(float);
     if (2 * qbytes + static_cast<size_t>(m) + 64 <= c->small_cap) {
         // few motions (a planner's single checkMotion): inputs converted straight into the mapped buffer, result read from it
         float *h0 = static_cast<float *>(c->h_small), *h1 = h0 + static_cast<size_t>(m) * dim;
@@ -880,9 +919,23 @@ int validate_states_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T 
     rc = b200mp_robot_info(robot, &dim, nullptr, nullptr, nullptr, nullptr);
     if (rc) return rc;
     if (m == 0) return B200MP_OK;
+    const size_t qbytes = static_cast<size_t>(m) * dim * sizeof(float);
+    if (qbytes + static_cast<size_t>(m) + 64 <= b200mp_ctx::kLaneBytes) {
+        LaneGuard g{acquire_lane(c)};  // a planner's single isValid: own lane, no context lock
+        if (g.ln) {
+            B200_CUDA(cudaSetDevice(c->device));
+            float *h0 = static_cast<float *>(g.ln->h);
+            for (int64_t i = 0; i < m * dim; ++i) h0[i] = static_cast<float>(q[i]);
+            uint8_t *dv = reinterpret_cast<uint8_t *>(g.ln->d) + qbytes;
+            rc = b200mp_validate_states_device(c, robot, e, static_cast<const float *>(g.ln->d), m, dv, g.ln->stream);
+            if (rc) return rc;
+            B200_CUDA(cudaStreamSynchronize(g.ln->stream));
+            std::memcpy(valid, static_cast<const uint8_t *>(g.ln->h) + qbytes, static_cast<size_t>(m));
+            return B200MP_OK;
+        }
+    }
     std::lock_guard<std::mutex> lk(c->mu);
     B200_CUDA(cudaSetDevice(c->device));
-    const size_t qbytes = static_cast<size_t>(m) * dim * sizeof(float);
     if (qbytes + static_cast<size_t>(m) + 64 <= c->small_cap) {
         float *h0 = static_cast<float *>(c->h_small);
         for (int64_t i = 0; i < m * dim; ++i) h0[i] = static_cast<float>(q[i]);

@@ -48,7 +48,19 @@ struct Scratch {
 
 }  // namespace b200mp
 
+// Small host calls (a planner thread's single isValid / checkMotion) do not queue behind the context mutex: each takes one of a few
+// "lanes" -- its own stream and its own mapped pinned buffer -- so several planner threads are in flight at once.
+struct b200mp_small_lane {
+    cudaStream_t stream = nullptr;
+    void *h = nullptr;  // host address of the mapped buffer
+    void *d = nullptr;  // the same memory as the device sees it
+    std::atomic<bool> busy{false};
+};
+
 struct b200mp_ctx {
+    static constexpr int kLanes = 8;
+    static constexpr size_t kLaneBytes = size_t(16) << 10;
+    b200mp_small_lane lanes[kLanes];
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
