@@ -153,6 +153,11 @@ int b200mp_validate_edges_device(b200mp_ctx *ctx, int robot, const b200mp_env *e
                                  int64_t m, int resolution, uint8_t *d_valid, void *stream);
 /* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
 int64_t b200mp_launch_count(const b200mp_ctx *ctx);
+/* Tuning switches (decisions never depend on them). B200MP_OPT_FIRST_LOOK (default 1): batches of long motions (>= 5 rakes) first get a
+ * look at rake 0 of four motions per warp pass, continued only while it settles most motions (see validate_rakes_kernel); 0 sends
+ * them straight to the warp-per-motion kernel (measurements of that kernel alone). */
+enum { B200MP_OPT_FIRST_LOOK = 1 };
+int b200mp_set_option(b200mp_ctx *ctx, int option, int value);
 
 /* ---- nearest neighbours ------------------------------------------------------------------------------------- */
 /* A container of `dim`-dimensional points with the NearestNeighbors<_T> contract. Points get consecutive ids in

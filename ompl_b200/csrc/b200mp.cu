@@ -343,6 +343,14 @@ int b200mp_synchronize(b200mp_ctx *c) {
 
 int64_t b200mp_launch_count(const b200mp_ctx *c) { return c ? c->launches.load() : -1; }
 
+int b200mp_set_option(b200mp_ctx *c, int option, int value) {
+    if (!c) return fail(B200MP_ERR_INVALID, "b200mp_set_option: ctx is NULL");
+    switch (option) {
+        case B200MP_OPT_FIRST_LOOK: c->first_look.store(value != 0 ? 1 : 0); return B200MP_OK;
+        default: return fail(B200MP_ERR_INVALID, "b200mp_set_option: unknown option %d", option);
+    }
+}
+
 int b200mp_robot_info(int robot, int *dim, int *n_spheres, int *resolution, float *lo, float *hi) {
     auto fill = [&](auto tag) {
         using R = decltype(tag);

@@ -81,4 +81,5 @@ struct b200mp_ctx {
     std::mutex build_mu;        // one roadmap build at a time per context
     void *self_comm = nullptr;  // group of one used by b200mp_prm_build (a b200mp_comm, created on first use)
     std::atomic<long long> launches{0};
+    std::atomic<int> first_look{1};  // B200MP_OPT_FIRST_LOOK
 };

@@ -835,12 +835,19 @@ static __device__ __noinline__ bool pointclouds_one(const CaptView *pcs, int n_p
 struct SharedViews {
     Scene sc;
     CaptView pc[kMaxPointClouds];
+    GridView grid[kGridLevels];
 };
 __device__ __forceinline__ void fill_views(const SceneDesc &sd, const Scene &sc, SharedViews &sv) {
     if (threadIdx.x == 0) {
         sv.sc = sc;
         for (int p = 0; p < sd.n_pc; ++p) sv.pc[p] = sd.pc[p];
+        for (int l = 0; l < sd.n_grid; ++l) sv.grid[l] = sd.grid[l];
     }
+}
+
+// the per-sphere grid walk as a rare fall-back of the hit-list path (a lane's list overflowed): out of line for the same reason
+static __device__ __noinline__ bool grid_scan_scene_cold(const GridView *g, const Scene *scp, float x, float y, float z, float r, bool on, bool any_mode) {
+    return grid_scan_scene(*g, *scp, x, y, z, r, on, any_mode);
 }
 
 // Candidate-grid variant (sorted scenes with a grid). Phase B is one loop over "sphere tasks" -- a link's bounding sphere,
@@ -892,7 +899,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
             }
         } else if (__any_sync(kFull, on && hits > kHitCap)) {
             // some lane's list overflowed (or was never made): this fine sphere walks the grid itself, as the bounding sphere did
-            if (lvl >= 0) h = grid_scan_scene(sd.grid[lvl], sc, x, y, z, r, on, any_mode);
+            if (lvl >= 0) h = grid_scan_scene_cold(&sv.grid[lvl], &sv.sc, x, y, z, r, on, any_mode);
             else h = ordered_scan_one<G>(&sv.sc, x, y, z, r, on, any_mode);
         } else {
             h = hits_scan<BT>(sc, hit_list, hits, x, y, z, r, on, any_mode);
@@ -950,7 +957,8 @@ struct BucketPlan {
     unsigned off[kRakeBuckets];       // start of each bucket in the list
     unsigned cursor[kRakeBuckets];    // fill positions of the scatter pass
     unsigned pass_end[kRakeBuckets];  // warp passes up to and including bucket b (b <= 4)
-    unsigned long long next_pass;     // work queue head of validate_rakes_kernel
+    unsigned long long next_pass;     // work queue head of validate_rakes_kernel (short buckets)
+    unsigned long long next_first;    // work queue head of its first-look instantiation
     LaunchCounters long_queue;        // work queue head of validate_motions_kernel over bucket 5
     // first look at the long motions (bucket 5): rake 0 of four motions per warp pass, see validate_rakes_kernel
     unsigned pre_passes;              // ceil(cnt[5] / 4)
@@ -1071,15 +1079,17 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
 // then `rake` sequential back-steps). A fine hit ends the work of every lane of the same motion in the warp (KILL mask); rakes of
 // that motion running in other warps finish on their own, later passes skip it (valid[e] is already 0).
 // valid[] must be 1 on entry (the pre-pass sets it); a pass only ever writes 0.
-template <class R, bool MASKED, bool GRID>
+// FIRST: the instantiation that runs the first-look passes over the long motions (below); the other one runs the short buckets.
+// (Two kernels rather than one loop with both kinds of pass: the short-bucket loop is the roadmap's hot loop and stays lean.)
+template <class R, bool MASKED, bool GRID, bool FIRST>
 __global__ void __launch_bounds__(motion_threads<R>(), kMotionBlocksPerSM)
 validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *__restrict__ q1, const int2 *__restrict__ pairs,
                       uint8_t *__restrict__ valid, const unsigned *__restrict__ list, BucketPlan *__restrict__ plan) {
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long bar;
     __shared__ SphereLevels<R> lv;
-    const unsigned short_passes = plan->pass_end[kRakeBuckets - 2];
-    const unsigned total = short_passes + plan->pre_passes;
+    const unsigned short_passes = FIRST ? 0u : plan->pass_end[kRakeBuckets - 2];
+    const unsigned total = FIRST ? plan->pre_passes : short_passes;
     if (total == 0) return;
     fill_levels<R>(sd, lv);
     stage_scene(smem, sd.blob, sd.blob_floats, &bar);
@@ -1094,7 +1104,7 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
     const float pct = static_cast<float>((lane & 7) + 1) / 8.0f;
     for (;;) {
         unsigned long long p64 = 0;
-        if (lane == 0) p64 = atomicAdd(&plan->next_pass, 1ull);
+        if (lane == 0) p64 = atomicAdd(FIRST ? &plan->next_first : &plan->next_pass, 1ull);
         p64 = __shfl_sync(kFull, p64, 0);
         if (p64 >= total) break;
         const unsigned p = static_cast<unsigned>(p64);
@@ -1102,16 +1112,22 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
         // four motions per pass. Where most motions are in collision (random end points) this settles them at a quarter of a warp pass
         // each; validate_motions_kernel then skips what is already invalid. Where most survive it would only add work, so the kill rate of
         // the first pre_sample passes decides whether the first look goes on (decided on the device, no host round trip).
-        const bool first_look = p >= short_passes;
+        constexpr bool first_look = FIRST;
         int b = 1;
         unsigned t;
         if (first_look) {
             const unsigned lp = p - short_passes;
             if (lp >= plan->pre_sample) {
-                // beyond the sample: run unless the verdict is already "skip" (no waiting for it: until the sample is complete the
-                // first look simply goes on, which costs at most a pass per warp where it turns out not to pay)
+                // beyond the sample: run unless the verdict is already "skip". A warp does not idle while the sample is being
+                // finished by others -- it takes one more pass on trust -- but no more than that: past one pass per warp of the grid
+                // it waits for the verdict (where passes are slow, e.g. ordered scans of a large scene, optimism would cost too much)
                 unsigned dec = 0;
-                if (lane == 0) dec = *reinterpret_cast<const volatile unsigned *>(&plan->pre_decision);
+                if (lane == 0) {
+                    const volatile unsigned *flag = &plan->pre_decision;
+                    dec = *flag;
+                    if (lp >= plan->pre_sample + gridDim.x * (blockDim.x >> 5))
+                        while ((dec = *flag) == 0u) __nanosleep(200);
+                }
                 dec = __shfl_sync(kFull, dec, 0);
                 if (dec == 2u) continue;
             }
@@ -1270,10 +1286,11 @@ static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__
             plan->pass_end[b] = passes;
         }
         plan->next_pass = 0;
+        plan->next_first = 0;
         plan->long_queue.next = 0;
         const unsigned pre = first_look ? (plan->cnt[kRakeBuckets - 1] + 3u) / 4u : 0u;
         plan->pre_passes = pre;
-        plan->pre_sample = pre <= 1024u ? pre : max(1024u, pre / 16u);
+        plan->pre_sample = pre <= 512u ? pre : min(max(512u, pre / 32u), 4096u);
         plan->pre_done = 0;
         plan->pre_killed = 0;
         plan->pre_tested = 0;

@@ -14,10 +14,14 @@ int blocks_per_sm(int device, const void *kern, int threads, size_t smem, int *p
 // this launch's own work-queue head from the context's ring (defined in b200mp.cu)
 LaunchCounters *next_counter(b200mp_ctx *c);
 
-template <class R, bool RAKES>
+template <class R, int KIND>  // 0: warp-per-motion kernel, 1: packed rakes of the short buckets, 2: first look at the long motions
 inline auto pick_motion_kernel(const SceneDesc &d) {
-    if constexpr (RAKES)
-        return d.n_grid > 0 ? validate_rakes_kernel<R, false, true> : (d.sorted ? validate_rakes_kernel<R, false, false> : validate_rakes_kernel<R, true, false>);
+    if constexpr (KIND == 1)
+        return d.n_grid > 0 ? validate_rakes_kernel<R, false, true, false>
+                            : (d.sorted ? validate_rakes_kernel<R, false, false, false> : validate_rakes_kernel<R, true, false, false>);
+    else if constexpr (KIND == 2)
+        return d.n_grid > 0 ? validate_rakes_kernel<R, false, true, true>
+                            : (d.sorted ? validate_rakes_kernel<R, false, false, true> : validate_rakes_kernel<R, true, false, true>);
     else
         return d.n_grid > 0 ? validate_motions_kernel<R, false, true>
                             : (d.sorted ? validate_motions_kernel<R, false, false> : validate_motions_kernel<R, true, false>);
@@ -27,7 +31,7 @@ template <class R>
 int launch_motions(b200mp_ctx *c, const SceneDesc &desc, const float *d_q0, const float *d_q1, const int2 *d_pairs, int64_t m, int resolution,
                    uint8_t *d_valid, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(desc.blob_floats) * 4 + lane_store_bytes<R>(motion_threads<R>());
-    auto kern = pick_motion_kernel<R, false>(desc);
+    auto kern = pick_motion_kernel<R, 0>(desc);
     int per_sm = 0, rc = 0;
     if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(kern), motion_threads<R>(), smem, &per_sm))) return rc;
     if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_motions: kernel does not fit on an SM with %zu B of scene", smem);
@@ -48,12 +52,14 @@ int launch_motions_bucketed(b200mp_ctx *c, const SceneDesc &desc, const float *d
                             int resolution, uint8_t *d_valid, cudaStream_t st) {
     if (m > 0xfffffff0LL) return fail(B200MP_ERR_CAPACITY, "validate (bucketed): at most 2^32 - 16 motions per call");
     const size_t smem = static_cast<size_t>(desc.blob_floats) * 4 + lane_store_bytes<R>(motion_threads<R>());
-    auto k_rakes = pick_motion_kernel<R, true>(desc);
-    auto k_long = pick_motion_kernel<R, false>(desc);
-    int per_rakes = 0, per_long = 0, rc = 0;
+    auto k_rakes = pick_motion_kernel<R, 1>(desc);
+    auto k_first = pick_motion_kernel<R, 2>(desc);
+    auto k_long = pick_motion_kernel<R, 0>(desc);
+    int per_rakes = 0, per_first = 0, per_long = 0, rc = 0;
     if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(k_rakes), motion_threads<R>(), smem, &per_rakes))) return rc;
+    if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(k_first), motion_threads<R>(), smem, &per_first))) return rc;
     if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(k_long), motion_threads<R>(), smem, &per_long))) return rc;
-    if (per_rakes < 1 || per_long < 1) return fail(B200MP_ERR_CAPACITY, "validate (bucketed): kernel does not fit on an SM with %zu B of scene", smem);
+    if (per_rakes < 1 || per_first < 1 || per_long < 1) return fail(B200MP_ERR_CAPACITY, "validate (bucketed): kernel does not fit on an SM with %zu B of scene", smem);
     // stream-ordered temporaries: keys[m] | list[m] | per-block counts[nb][8] | plan
     const unsigned nb = static_cast<unsigned>((m + 255) / 256);
     const size_t o_list = (static_cast<size_t>(m) + 255) / 256 * 256, o_blk = o_list + (static_cast<size_t>(m) * 4 + 255) / 256 * 256;
@@ -66,19 +72,22 @@ int launch_motions_bucketed(b200mp_ctx *c, const SceneDesc &desc, const float *d
     BucketPlan *plan = reinterpret_cast<BucketPlan *>(tmp + o_plan);
     cudaMemsetAsync(plan, 0, sizeof(BucketPlan), st);
     bucket_count_kernel<R><<<nb, 256, 0, st>>>(d_q0, d_q1, d_pairs, m, resolution, keys, d_valid, blk, plan);
-    static const bool first_look = !(getenv("B200MP_FIRST_LOOK") && atoi(getenv("B200MP_FIRST_LOOK")) == 0);
+    static const bool first_look_env = !(getenv("B200MP_FIRST_LOOK") && atoi(getenv("B200MP_FIRST_LOOK")) == 0);
+    const bool first_look = first_look_env && c->first_look.load() != 0;
     bucket_plan_kernel<<<1, 1024, 0, st>>>(plan, blk, static_cast<int>(nb), first_look ? 1 : 0);
     bucket_scatter_kernel<<<nb, 256, 0, st>>>(keys, m, blk, list, plan);
     const long long wpb = motion_threads<R>() / 32;
     const long long cap = std::max<long long>(1, (m + wpb - 1) / wpb);
     const unsigned b_rakes = static_cast<unsigned>(std::min<long long>(static_cast<long long>(c->sm_count) * per_rakes, cap));
     const unsigned b_long = static_cast<unsigned>(std::min<long long>(static_cast<long long>(c->sm_count) * per_long, cap));
+    const unsigned b_first = static_cast<unsigned>(std::min<long long>(static_cast<long long>(c->sm_count) * per_first, cap));
     k_rakes<<<b_rakes, motion_threads<R>(), smem, st>>>(desc, d_q0, d_q1, d_pairs, d_valid, list, plan);
+    if (first_look) k_first<<<b_first, motion_threads<R>(), smem, st>>>(desc, d_q0, d_q1, d_pairs, d_valid, list, plan);
     k_long<<<b_long, motion_threads<R>(), smem, st>>>(desc, d_q0, d_q1, d_pairs, m, resolution, d_valid, &plan->long_queue, list, plan);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(tmp, st);
     if (e != cudaSuccess) return fail(B200MP_ERR_CUDA, "validate (bucketed) launch failed: %s", cudaGetErrorString(e));
-    c->launches.fetch_add(5);
+    c->launches.fetch_add(first_look ? 6 : 5);
     return B200MP_OK;
 }
 

@@ -103,6 +103,7 @@ def load_library():
     L.b200mp_chain_check_motions.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp, _vp]
     L.b200mp_chain_validate_states_device.argtypes = [_vp, _vp, _i64, _vp, _vp]
     L.b200mp_chain_check_motions_device.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]
+    L.b200mp_set_option.argtypes = [_vp, C.c_int, C.c_int]
     L.b200mp_launch_count.argtypes = [_vp]
     L.b200mp_launch_count.restype = _i64
     L.b200mp_fp32_peak.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
@@ -197,6 +198,10 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._L.b200mp_launch_count(self._h))
+
+    def set_option(self, option: int, value: int):
+        """b200mp_set_option; option 1 = B200MP_OPT_FIRST_LOOK."""
+        _check(self._L.b200mp_set_option(self._h, option, value))
 
     def fp32_peak_tflops(self, iters: int = 4096) -> float:
         out = C.c_double()

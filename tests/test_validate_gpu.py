@@ -165,7 +165,7 @@ def test_device_pointer_entry_points(ctx):
     before = ctx.launch_count
     ctx.validate_motions_ptr("panda", env, d0.data_ptr(), d1.data_ptr(), len(q0), out.data_ptr(), stream=st.cuda_stream)
     st.synchronize()
-    assert ctx.launch_count - before in (1, 5)  # one kernel, or the bucketed sequence (count, plan, scatter, rakes, motions)
+    assert ctx.launch_count - before in (1, 5, 6)  # one kernel, or the bucketed sequence (count, plan, scatter, rakes, [first look,] motions)
     np.testing.assert_array_equal(out.cpu().numpy(), want)
 
 
