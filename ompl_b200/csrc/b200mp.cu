@@ -1034,6 +1034,24 @@ int b200mp_validate_edges_device(b200mp_ctx *c, int robot, const b200mp_env *e, 
 #undef B200_EDGES
 }
 
+}  // extern "C"
+
+namespace b200mp {
+// states visited in the order of d_order (may be null); results in the states' own slots. Used by the roadmap sampler.
+int validate_states_ordered(b200mp_ctx *c, int robot, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid, const unsigned *d_order,
+                            cudaStream_t st) {
+    switch (robot) {
+        case B200MP_ROBOT_PANDA: return launch_states<Panda>(c, e->desc, d_q, m, d_valid, st, d_order);
+        case B200MP_ROBOT_FETCH: return launch_states<Fetch>(c, e->desc, d_q, m, d_valid, st, d_order);
+        case B200MP_ROBOT_UR5: return launch_states<Ur5>(c, e->desc, d_q, m, d_valid, st, d_order);
+        case B200MP_ROBOT_BAXTER: return launch_states<Baxter>(c, e->desc, d_q, m, d_valid, st, d_order);
+        default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
+    }
+}
+}  // namespace b200mp
+
+extern "C" {
+
 int b200mp_validate_states_device(b200mp_ctx *c, int robot, const b200mp_env *e, const float *d_q, int64_t m, uint8_t *d_valid,
                                   void *stream) {
     int rc = check_common("b200mp_validate_states_device", c, e, d_q, d_valid, m);
@@ -1041,13 +1059,7 @@ int b200mp_validate_states_device(b200mp_ctx *c, int robot, const b200mp_env *e,
     if (m == 0) return B200MP_OK;
     B200_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
-    switch (robot) {
-        case B200MP_ROBOT_PANDA: return launch_states<Panda>(c, e->desc, d_q, m, d_valid, st);
-        case B200MP_ROBOT_FETCH: return launch_states<Fetch>(c, e->desc, d_q, m, d_valid, st);
-        case B200MP_ROBOT_UR5: return launch_states<Ur5>(c, e->desc, d_q, m, d_valid, st);
-        case B200MP_ROBOT_BAXTER: return launch_states<Baxter>(c, e->desc, d_q, m, d_valid, st);
-        default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
-    }
+    return validate_states_ordered(c, robot, e, d_q, m, d_valid, nullptr, st);
 }
 
 int b200mp_validate_motions(b200mp_ctx *c, int robot, const b200mp_env *e, const float *q0, const float *q1, int64_t m, int resolution,

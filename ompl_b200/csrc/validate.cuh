@@ -1323,7 +1323,8 @@ static __global__ void __launch_bounds__(256) bucket_scatter_kernel(const unsign
 // 8 identical lanes (src/ompl/vamp/VampStateValidityChecker.h:37-41) -> group size 1 here.
 template <class R, bool MASKED, bool GRID>
 __global__ void __launch_bounds__(kStateThreads, kStateBlocksPerSM)
-validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, uint8_t *__restrict__ valid, LaunchCounters *cnt) {
+validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, uint8_t *__restrict__ valid, LaunchCounters *cnt,
+                       const unsigned *__restrict__ order) {
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long bar;
     __shared__ SphereLevels<R> lv;
@@ -1342,8 +1343,10 @@ validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, 
         w = __shfl_sync(kFull, w, 0);
         const long long first = static_cast<long long>(w) * 32;
         if (first >= m) break;
-        const long long i = first + lane;
-        const bool active = i < m;
+        const bool active = first + lane < m;
+        // `order` (optional): the states are visited in this order (a warp's 32 states then come from one bucket of similar
+        // configurations, see prm_sample_async) -- results still go to the states' own slots
+        const long long i = active ? (order != nullptr ? static_cast<long long>(__ldg(order + first + lane)) : first + lane) : 0;
         float q[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) q[j] = active ? __ldg(qs + i * D + j) : 0.0f;

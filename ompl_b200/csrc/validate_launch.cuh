@@ -92,7 +92,7 @@ int launch_motions_bucketed(b200mp_ctx *c, const SceneDesc &desc, const float *d
 }
 
 template <class R>
-int launch_states(b200mp_ctx *c, const SceneDesc &desc, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st) {
+int launch_states(b200mp_ctx *c, const SceneDesc &desc, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st, const unsigned *d_order) {
     const size_t smem = static_cast<size_t>(desc.blob_floats) * 4 + lane_store_bytes<R>(kStateThreads);
     auto kern = desc.n_grid > 0 ? validate_states_kernel<R, false, true>
                                 : (desc.sorted ? validate_states_kernel<R, false, false> : validate_states_kernel<R, true, false>);
@@ -103,7 +103,7 @@ int launch_states(b200mp_ctx *c, const SceneDesc &desc, const float *d_q, int64_
     const long long blocks = std::max<long long>(1, std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + wpb - 1) / wpb));
     LaunchCounters *cnt = next_counter(c);
     B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), kStateThreads, smem, st>>>(desc, d_q, m, d_valid, cnt);
+    kern<<<static_cast<unsigned>(blocks), kStateThreads, smem, st>>>(desc, d_q, m, d_valid, cnt, d_order);
     B200_CUDA(cudaGetLastError());
     c->launches.fetch_add(1);
     return B200MP_OK;
@@ -112,10 +112,10 @@ int launch_states(b200mp_ctx *c, const SceneDesc &desc, const float *d_q, int64_
 #define B200MP_INSTANTIATE_ROBOT(R)                                                                                                        \
     template int launch_motions<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t);          \
     template int launch_motions_bucketed<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t); \
-    template int launch_states<R>(b200mp_ctx *, const SceneDesc &, const float *, int64_t, uint8_t *, cudaStream_t);
+    template int launch_states<R>(b200mp_ctx *, const SceneDesc &, const float *, int64_t, uint8_t *, cudaStream_t, const unsigned *);
 #define B200MP_EXTERN_ROBOT(R)                                                                                                                    \
     extern template int launch_motions<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t);          \
     extern template int launch_motions_bucketed<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t); \
-    extern template int launch_states<R>(b200mp_ctx *, const SceneDesc &, const float *, int64_t, uint8_t *, cudaStream_t);
+    extern template int launch_states<R>(b200mp_ctx *, const SceneDesc &, const float *, int64_t, uint8_t *, cudaStream_t, const unsigned *);
 
 }  // namespace b200mp
