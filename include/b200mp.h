@@ -11,6 +11,8 @@
  *                             (= validate_motion<Robot, 8, Robot::resolution>)  external/vamp/src/impl/vamp/planning/validate.hh:23-77
  *   b200mp_env_*              vamp::collision::Environment<float> + sort()       external/vamp/src/impl/vamp/collision/environment.hh:14-85
  *                             and the shape constructors' min_distance           external/vamp/src/impl/vamp/collision/shapes.hh:52-67,165-189,236-239
+ *   b200mp_env_set_attachment vamp::collision::Attachment, Robot::fkcc_attach   external/vamp/src/impl/vamp/collision/attachments.hh:13-56,
+ *                                                                                external/vamp/src/impl/vamp/robots/panda.hh:10264-15469
  *   b200mp_env_add_capt       vamp::collision::CAPT (prebuilt tree arrays)       external/vamp/src/impl/vamp/collision/capt.hh:61-618
  *   b200mp_env_add_pointcloud vamp::collision::CAPT::CAPT / subdivide            external/vamp/src/impl/vamp/collision/capt.hh:104-365
  *   b200mp_robot_info         Robot::dimension / resolution / joint bounds       src/ompl/vamp/VampStateSpace.h:10-36
@@ -119,6 +121,14 @@ int b200mp_env_add_heightfield(b200mp_env *env, float cx, float cy, float cz, fl
  * reference's unstable sort leaves that order unspecified). */
 int b200mp_filter_pointcloud(b200mp_ctx *ctx, const float *xyz, int64_t n, float min_dist, float max_range, const float *origin,
                              const float *ws_min, const float *ws_max, int cull, float *out_xyz, int64_t *out_n);
+/* vamp::collision::Attachment + Environment::attachments (collision/attachments.hh:13-56, environment.hh:25,87-93): spheres
+ * rigidly fixed to the robot's end effector (a grasped object). tf[12] = row-major 3x4 [R | t], the pose of the attachment
+ * relative to the end-effector frame (Robot::eefk); xyzr[n][4] = its spheres in the attachment's own frame. While an attachment
+ * is set every validation call runs Robot::fkcc_attach instead of fkcc (planning/validate.hh:43,58): the robot's own tests, then
+ * the posed attachment against the environment and against the links the robot's table lists (robots/panda.hh:15308-15466).
+ * n = 0 removes it. May be called before or after b200mp_env_commit (no re-commit needed); not while a validation call on this
+ * environment is in flight on another thread. */
+int b200mp_env_set_attachment(b200mp_env *env, const float *tf, const float *xyzr, int n);
 /* Sort every shape list by min_distance (Environment::sort). Obstacles are otherwise tested in insertion
  * order with the reference's ordered-scan-with-break semantics. */
 int b200mp_env_sort(b200mp_env *env);

@@ -195,6 +195,20 @@ namespace ompl::b200
             check(b200mp_env_add_pointcloud_device(env_, xyz, static_cast<int64_t>(n), r_min, r_max, r_point), "addPointcloudDevice");
         }
 
+        /// Environment::attachments.emplace(Attachment<float>(tf)) + spheres (collision/attachments.hh:13-56): a grasped object, rigidly
+        /// fixed to the end effector at the pose tf (row-major 3x4 [R | t] relative to Robot::eefk); xyzr = its spheres in its own
+        /// frame. Validation then behaves like Robot::fkcc_attach. May be called after commit().
+        void setAttachment(const std::array<float, 12> &tf, const std::vector<std::array<float, 4>> &xyzr)
+        {
+            check(b200mp_env_set_attachment(env_, tf.data(), xyzr.empty() ? nullptr : xyzr[0].data(), static_cast<int>(xyzr.size())),
+                  "setAttachment");
+        }
+        /// environment.attachments.reset()
+        void clearAttachment()
+        {
+            check(b200mp_env_set_attachment(env_, nullptr, nullptr, 0), "clearAttachment");
+        }
+
         /// factory::heightfield::array(center, scale, {nx, ny}, data)  (factory.hh:405-421): heights[ny][nx] row-major
         void addHeightfield(const std::array<float, 3> &c, const std::array<float, 3> &scale, std::size_t nx, std::size_t ny,
                             const std::vector<float> &heights)

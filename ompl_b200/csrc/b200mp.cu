@@ -99,6 +99,8 @@ struct b200mp_env {
     std::vector<HeightFieldView> hfs;  // data pointers are device allocations owned by the environment
     float *d_blob = nullptr;
     void *d_grid = nullptr;
+    std::vector<float> att;  // attachment: 12 floats of pose + 4 pad, then (x, y, z, r) per sphere; empty = none
+    float *d_att = nullptr;
     bool use_grid = true;
     SceneDesc desc{};
     bool committed = false;
@@ -400,7 +402,28 @@ void b200mp_env_destroy(b200mp_env *e) {
         cudaFree(p.pref);
     }
     for (auto &h : e->hfs) cudaFree(const_cast<float *>(h.data));
+    if (e->d_att) cudaFree(e->d_att);
     delete e;
+}
+
+// vamp::collision::Attachment (collision/attachments.hh:13-56) + Environment::attachments (environment.hh:25). May be called before
+// or after commit: the attachment lives in its own device buffer, so grasping / releasing an object does not re-upload the scene.
+int b200mp_env_set_attachment(b200mp_env *e, const float *tf, const float *xyzr, int n) {
+    if (!e || n < 0 || (n > 0 && (!tf || !xyzr))) return fail(B200MP_ERR_INVALID, "b200mp_env_set_attachment: bad argument");
+    B200_CUDA(cudaSetDevice(e->ctx->device));
+    if (e->d_att) B200_CUDA(cudaFree(e->d_att));  // (cudaFree waits for launches that still read it)
+    e->d_att = nullptr;
+    e->att.clear();
+    if (n > 0) {
+        e->att.assign(tf, tf + 12);
+        e->att.resize(16, 0.f);
+        e->att.insert(e->att.end(), xyzr, xyzr + static_cast<size_t>(n) * 4);
+        B200_CUDA(cudaMalloc(&e->d_att, e->att.size() * 4));
+        B200_CUDA(cudaMemcpy(e->d_att, e->att.data(), e->att.size() * 4, cudaMemcpyHostToDevice));
+    }
+    e->desc.att = e->d_att;
+    e->desc.n_att = n;
+    return B200MP_OK;
 }
 
 int b200mp_env_add_spheres(b200mp_env *e, const float *s, int n) {
@@ -615,6 +638,10 @@ int b200mp_env_clone(const b200mp_env *src, b200mp_ctx *dst_ctx, b200mp_env **ou
     e->cuboids = src->cuboids;
     e->zcuboids = src->zcuboids;
     e->use_grid = src->use_grid;
+    if (!src->att.empty()) {
+        const int rc = b200mp_env_set_attachment(e, src->att.data(), src->att.data() + 16, static_cast<int>((src->att.size() - 16) / 4));
+        if (rc) { b200mp_env_destroy(e); return rc; }
+    }
     if (src->committed) {
         const int rc = b200mp_env_commit(e);
         if (rc) { b200mp_env_destroy(e); return rc; }
@@ -743,6 +770,8 @@ int b200mp_env_commit(b200mp_env *e) {
     for (int i = 0; i < d.n_hf; ++i) d.hf[i] = e->hfs[i];
     d.n_pc = static_cast<int>(e->pcs.size());
     for (int i = 0; i < d.n_pc; ++i) d.pc[i] = e->pcs[i].view;
+    d.att = e->d_att;
+    d.n_att = e->att.empty() ? 0 : static_cast<int>((e->att.size() - 16) / 4);
     e->desc = d;
     e->committed = true;
     return B200MP_OK;

@@ -79,6 +79,10 @@ struct SceneDesc {
     HeightFieldView hf[kMaxHeightFields];
     int n_grid;  // 0: no grid (unsorted or small scene) -> ordered scans
     GridView grid[kGridLevels];
+    // Attachment (collision/attachments.hh): global memory, 16 floats = row-major 3x4 pose of the attachment relative to the robot's
+    // end-effector frame (+ 4 pad), then n_att records (x, y, z, r) in the attachment's own frame. n_att == 0: none.
+    const float *att;
+    int n_att;
 };
 
 // Pointers into the staged copy.
@@ -566,10 +570,10 @@ __device__ __forceinline__ bool scan_pointclouds(const SceneDesc &d, const Tile<
 // ------------------------------------------------------------------------------------------------ height fields
 // collision/sphere_heightfield.hh:9-30: the cell under the sphere's centre (index clamped to [0, xd] x [0, yd] as the reference
 // does; a read past the array, undefined there, takes the last element here); collision <=> z - r below the scaled height.
-__device__ __forceinline__ bool heightfields_hit(const SceneDesc &sd, float x, float y, float z, float r) {
+__device__ __forceinline__ bool heightfields_hit(const HeightFieldView *hf, int n_hf, float x, float y, float z, float r) {
     bool hit = false;
-    for (int i = 0; i < sd.n_hf; ++i) {
-        const HeightFieldView &a = sd.hf[i];
+    for (int i = 0; i < n_hf; ++i) {
+        const HeightFieldView &a = hf[i];
         const float xo = a.x - x, yo = a.y - y;
         const float xs = floorf(fminf(fmaxf(fmaf(a.xs, xo, a.xd2), 0.f), a.xd));
         const float ys = floorf(fminf(fmaxf(fmaf(a.ys, yo, a.yd2), 0.f), a.yd));
@@ -578,6 +582,9 @@ __device__ __forceinline__ bool heightfields_hit(const SceneDesc &sd, float x, f
         hit |= ((z - r) - zhs) < 0.0f;
     }
     return hit;
+}
+__device__ __forceinline__ bool heightfields_hit(const SceneDesc &sd, float x, float y, float z, float r) {
+    return heightfields_hit(sd.hf, sd.n_hf, x, y, z, r);
 }
 
 // ------------------------------------------------------------------------------------------------ one state per lane
@@ -836,13 +843,23 @@ struct SharedViews {
     Scene sc;
     CaptView pc[kMaxPointClouds];
     GridView grid[kGridLevels];
+    HeightFieldView hf[kMaxHeightFields];
+    int n_pc, n_grid, n_hf, n_att;
+    const float *att;
 };
 __device__ __forceinline__ void fill_views(const SceneDesc &sd, const Scene &sc, SharedViews &sv) {
     if (threadIdx.x == 0) {
         sv.sc = sc;
         for (int p = 0; p < sd.n_pc; ++p) sv.pc[p] = sd.pc[p];
         for (int l = 0; l < sd.n_grid; ++l) sv.grid[l] = sd.grid[l];
+        for (int h = 0; h < sd.n_hf; ++h) sv.hf[h] = sd.hf[h];
+        sv.n_pc = sd.n_pc; sv.n_grid = sd.n_grid; sv.n_hf = sd.n_hf; sv.n_att = sd.n_att;
+        sv.att = sd.att;
     }
+}
+
+__device__ __forceinline__ bool capt_any(const SharedViews &sv, float x, float y, float z, float r, bool on) {
+    return pointclouds_one(sv.pc, sv.n_pc, x, y, z, r, on, false);
 }
 
 // the per-sphere grid walk as a rare fall-back of the hit-list path (a lane's list overflowed): out of line for the same reason
@@ -935,11 +952,125 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
     return alive;
 }
 
+// ------------------------------------------------------------------------------------------------ attachments
+// Robot::fkcc_attach (robots/panda.hh:10264-15469): after the robot's own tests, the attachment -- spheres rigidly fixed to the end
+// effector, collision/attachments.hh:13-56 -- is posed at eefk(q) * tf and tested against the environment
+// (attachment_environment_collision, validity.hh:251-268) and against the links the robot's table lists
+// (attachment_sphere_collision, validity.hh:270-293: bounding sphere first, then the link's fine spheres). Rare path: out of
+// line, per-lane results, warp-uniform loops; the caller applies its exit policy to the returned flag.
+template <int G, bool MASKED, bool GRID>
+__device__ __forceinline__ bool env_sphere_hit(const SharedViews &sv, float x, float y, float z, float r, bool on) {
+    bool h;
+    int lvl = -1;
+    if (GRID) {
+        for (int l = kGridLevels - 1; l >= 0; --l)
+            if (l < sv.n_grid && r <= sv.grid[l].reach) lvl = l;
+    }
+    if (GRID && lvl >= 0) {
+        h = grid_scan_scene(sv.grid[lvl], sv.sc, x, y, z, r, on, false);
+    } else {
+        Tile<1> s1;
+        s1.x[0] = x; s1.y[0] = y; s1.z[0] = z; s1.r[0] = r;
+        const float e = on ? sqrtf(fmaf(z, z, fmaf(y, y, x * x))) + r : -INFINITY;
+        s1.ext[0] = group_max<G>(e);
+        if (!on) { s1.x[0] = kIdle; s1.y[0] = kIdle; s1.z[0] = kIdle; }
+        h = scan_scene<1, kUntilAllHit, MASKED>(sv.sc, s1, on);
+    }
+    if (sv.n_hf > 0 && on && !h) h = heightfields_hit(sv.hf, sv.n_hf, x, y, z, r);
+    if (sv.n_pc > 0) h |= capt_any(sv, x, y, z, r, on && !h);
+    return h && on;
+}
+
+template <class R, int G, bool MASKED, bool GRID, int BT>
+__device__ __noinline__ bool attachment_hit(const float *__restrict__ qv, const float *__restrict__ slots, const SharedViews *__restrict__ svp, bool alive) {
+    const SharedViews &sv = *svp;
+    const typename R::Tables &tb = R::tables();
+    float q[R::kDim];
+#pragma unroll
+    for (int j = 0; j < R::kDim; ++j) q[j] = qv[j];
+    // N = eefk(q) * tf: the end-effector frame is a constant transform away from one of the moving frames
+    Frame F, N;
+    int have = -1;
+    frame_seek<R, BT>(F, have, R::kEeFrame, q, slots);
+    {
+        Frame E;
+        R::ee_pose(F, E);
+        float t[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) t[i] = __ldg(sv.att + i);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) N.r[3 * r + c] = fmaf(E.r[3 * r + 2], t[8 + c], fmaf(E.r[3 * r + 1], t[4 + c], E.r[3 * r] * t[c]));
+            N.t[r] = fmaf(E.r[3 * r + 2], t[11], fmaf(E.r[3 * r + 1], t[7], fmaf(E.r[3 * r], t[3], E.t[r])));
+        }
+    }
+    const float4 *sph = reinterpret_cast<const float4 *>(sv.att + 16);
+    const int n = sv.n_att;
+    bool hit = false;
+    // attachment vs. environment
+    for (int i = 0; i < n; ++i) {
+        if (!__any_sync(kFull, alive && !hit)) break;
+        const float4 a = __ldg(sph + i);
+        float x, y, z;
+        frame_apply(N, a.x, a.y, a.z, x, y, z);
+        hit |= env_sphere_hit<G, MASKED, GRID>(sv, x, y, z, a.w, alive && !hit);
+    }
+    // attachment vs. the robot's links
+    have = -1;
+    for (int k = 0; k < R::kAttLinks; ++k) {
+        if (!__any_sync(kFull, alive && !hit)) break;
+        const int l = tb.att_links[k];
+        const float bx = slots[(3 * l + 0) * BT], by = slots[(3 * l + 1) * BT], bz = slots[(3 * l + 2) * BT];
+        const float rb = tb.coarse[l].w;
+        int acc = 0;
+        for (int i = 0; i < n; ++i) {
+            const float4 a = __ldg(sph + i);
+            float x, y, z;
+            frame_apply(N, a.x, a.y, a.z, x, y, z);
+            const float xs = bx - x, ys = by - y, zs = bz - z, rs = rb + a.w;
+            acc |= __float_as_int(fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs))));
+        }
+        const bool need = group_any<G>(acc < 0 && alive && !hit) && alive && !hit;
+        if (!__any_sync(kFull, need)) continue;
+        frame_seek<R, BT>(F, have, tb.link_frame[l], q, slots);
+        int facc = 0;
+        for (int f = tb.link_begin[l]; f < tb.link_begin[l + 1]; ++f) {
+            const float4 fl = tb.fine[f];
+            float px, py, pz;
+            frame_apply(F, fl.x, fl.y, fl.z, px, py, pz);
+            for (int i = 0; i < n; ++i) {
+                const float4 a = __ldg(sph + i);
+                float x, y, z;
+                frame_apply(N, a.x, a.y, a.z, x, y, z);
+                const float xs = px - x, ys = py - y, zs = pz - z, rs = fl.w + a.w;
+                facc |= __float_as_int(fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs))));
+            }
+        }
+        hit |= (facc < 0) && need;
+    }
+    return hit;
+}
+
 template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT, bool KILL = false>
 __device__ __forceinline__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
                                             const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill = 0u) {
-    if (GRID) return check_state_grid<R, G, EDGE, KILL, BT>(q, sd, sc, slots, lv, sv, active, kill);
-    return check_state_ordered<R, G, EDGE, KILL, MASKED, BT>(q, sd, sc, slots, active, kill);
+    bool good = GRID ? check_state_grid<R, G, EDGE, KILL, BT>(q, sd, sc, slots, lv, sv, active, kill)
+                     : check_state_ordered<R, G, EDGE, KILL, MASKED, BT>(q, sd, sc, slots, active, kill);
+    if (sd.n_att > 0) {
+        // (an EDGE pass that already has a hit is over: its caller drops the motion)
+        if (EDGE && __any_sync(kFull, active && !good)) return good;
+        const bool alive = active && good;
+        if (__any_sync(kFull, alive)) {
+            float qq[R::kDim];  // a copy the out-of-line call may take the address of (q itself stays in registers)
+#pragma unroll
+            for (int j = 0; j < R::kDim; ++j) qq[j] = q[j];
+            bool ahit = attachment_hit<R, G, MASKED, GRID, BT>(qq, slots, &sv, alive);
+            if (KILL) ahit = (__ballot_sync(kFull, ahit) & kill) != 0u;
+            good = good && !ahit;
+        }
+    }
+    return good;
 }
 
 // ------------------------------------------------------------------------------------------------ kernels

@@ -66,6 +66,7 @@ def load_library():
     L.b200mp_capt_sizes.argtypes = [_vp, _vp]
     L.b200mp_capt_export.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
     L.b200mp_env_sort.argtypes = [_vp]
+    L.b200mp_env_set_attachment.argtypes = [_vp, C.c_void_p, C.c_void_p, C.c_int]
     L.b200mp_env_set_grid.argtypes = [_vp, C.c_int]
     L.b200mp_env_commit.argtypes = [_vp]
     L.b200mp_env_min_distances.argtypes = [_vp, C.c_int, _vp]
@@ -415,6 +416,16 @@ class Environment:
         """The same tree structure built on the GPU (b200mp_env_add_pointcloud_device; at most 2^17 points)."""
         a = _host(xyz, np.float32).reshape(-1, 3)
         _check(self._L.b200mp_env_add_pointcloud_device(self._h, a.ctypes.data, a.shape[0], r_min, r_max, r_point))
+
+    def set_attachment(self, tf, xyzr):
+        """vamp::collision::Attachment (collision/attachments.hh:13-56): spheres xyzr[n][4] rigidly fixed to the end effector at the
+        pose tf (3x4 [R | t], relative to Robot::eefk). Validation then runs Robot::fkcc_attach. No re-commit needed."""
+        t = _host(np.asarray(tf, np.float32).reshape(-1)[:12].copy(), np.float32)
+        a = _host(xyzr, np.float32).reshape(-1, 4)
+        _check(self._L.b200mp_env_set_attachment(self._h, t.ctypes.data, a.ctypes.data, a.shape[0]))
+
+    def clear_attachment(self):
+        _check(self._L.b200mp_env_set_attachment(self._h, None, None, 0))
 
     def set_grid(self, enable: bool):
         """Candidate-grid culling of sorted scenes on/off (b200mp_env_set_grid); takes effect at the next commit()."""

@@ -112,6 +112,10 @@ namespace
         std::vector<Cuboid> cuboids, zcuboids;
         std::vector<HeightField> hfs;
         std::vector<Capt> pcs;
+        // collision/attachments.hh:13-56: pose relative to the end effector (row-major 3x4) + spheres in the attachment's frame
+        bool has_att = false;
+        float att_tf[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        std::vector<Sphere> att;
     };
 
     inline float dot3(float ax, float ay, float az, float bx, float by, float bz) { return ax * bx + ay * by + az * bz; }
@@ -385,7 +389,50 @@ namespace
         z = F.r[6] * lx + F.r[7] * ly + F.r[8] * lz + F.t[2];
     }
 
+    // Attachment::pose (attachments.hh:43-56) at Robot::eefk(q) = frame[ee_frame] * constant offset: n_tf = p_tf * tf, then
+    // n_tf * sphere centre. (x, y, z)[i] receive the world positions of the attachment's spheres.
+    inline void pose_attachment(const OrRobot &R, const Env &e, const Fr *F, float *x, float *y, float *z)
+    {
+        const Fr &P = F[R.ee_frame];
+        Fr E, N;
+        for (int i = 0; i < 3; ++i)
+        {
+            for (int j = 0; j < 3; ++j)
+            {
+                float acc = 0;
+                for (int k = 0; k < 3; ++k)
+                {
+                    if (std::fabs(R.ee_R[3 * k + j]) >= 1e-9) acc += P.r[3 * i + k] * static_cast<float>(R.ee_R[3 * k + j]);
+                }
+                E.r[3 * i + j] = acc;
+            }
+            float acc = P.t[i];
+            for (int k = 0; k < 3; ++k)
+            {
+                if (std::fabs(R.ee_t[k]) >= 1e-12) acc += P.r[3 * i + k] * static_cast<float>(R.ee_t[k]);
+            }
+            E.t[i] = acc;
+        }
+        const float *t = e.att_tf;
+        for (int i = 0; i < 3; ++i)
+        {
+            for (int j = 0; j < 3; ++j)
+            {
+                N.r[3 * i + j] = E.r[3 * i] * t[j] + E.r[3 * i + 1] * t[4 + j] + E.r[3 * i + 2] * t[8 + j];
+            }
+            N.t[i] = E.r[3 * i] * t[3] + E.r[3 * i + 1] * t[7] + E.r[3 * i + 2] * t[11] + E.t[i];
+        }
+        for (std::size_t s = 0; s < e.att.size(); ++s)
+        {
+            const Sphere &a = e.att[s];
+            x[s] = N.r[0] * a.x + N.r[1] * a.y + N.r[2] * a.z + N.t[0];
+            y[s] = N.r[3] * a.x + N.r[4] * a.y + N.r[5] * a.z + N.t[1];
+            z[s] = N.r[6] * a.x + N.r[7] * a.y + N.r[8] * a.z + N.t[2];
+        }
+    }
+
     constexpr int kMaxFrames = 16;
+    constexpr int kMaxAtt = 256;
     constexpr int kMaxLinks = 48;
     constexpr int kMaxFine = 160;
 
@@ -394,10 +441,23 @@ namespace
     {
         static thread_local float cx[kMaxLinks][kRake], cy[kMaxLinks][kRake], cz[kMaxLinks][kRake];
         static thread_local float fx[kMaxFine][kRake], fy[kMaxFine][kRake], fz[kMaxFine][kRake];
+        static thread_local float ax[kMaxAtt][kRake], ay[kMaxAtt][kRake], az[kMaxAtt][kRake];
+        const int n_att = e.has_att ? static_cast<int>(e.att.size()) : 0;
         Fr F[kMaxFrames];
         for (int l = 0; l < lanes; ++l)
         {
             fk_frames(R, q[l], F);
+            if (n_att > 0)
+            {
+                float tx[kMaxAtt], ty[kMaxAtt], tz[kMaxAtt];
+                pose_attachment(R, e, F, tx, ty, tz);
+                for (int s = 0; s < n_att; ++s)
+                {
+                    ax[s][l] = tx[s];
+                    ay[s][l] = ty[s];
+                    az[s][l] = tz[s];
+                }
+            }
             for (int k = 0; k < R.n_links; ++k)
             {
                 const OrLink &L = R.links[k];
@@ -452,6 +512,44 @@ namespace
                     {
                         if (pair_hit(fx[i], fy[i], fz[i], static_cast<float>(R.fine[i].r), fx[j], fy[j], fz[j],
                                      static_cast<float>(R.fine[j].r)))
+                        {
+                            return false;
+                        }
+                    }
+                }
+            }
+        }
+        if (n_att > 0)
+        {
+            // Robot::fkcc_attach (robots/panda.hh:15308-15466): attachment vs environment (validity.hh:251-268) ...
+            for (int s = 0; s < n_att; ++s)
+            {
+                if (sphere_env(e, ax[s], ay[s], az[s], e.att[s].r, lanes, cnt))
+                {
+                    return false;
+                }
+            }
+            // ... then vs the listed links: bounding sphere, then fine spheres (attachment_sphere_collision, validity.hh:270-293)
+            auto att_hit = [&](const float *sx, const float *sy, const float *sz, float sr)
+            {
+                for (int s = 0; s < n_att; ++s)
+                {
+                    if (pair_hit(sx, sy, sz, sr, ax[s], ay[s], az[s], e.att[s].r))
+                    {
+                        return true;
+                    }
+                }
+                return false;
+            };
+            for (int k = 0; k < R.n_att_links; ++k)
+            {
+                const int li = R.att_links[k];
+                const OrLink &L = R.links[li];
+                if (att_hit(cx[li], cy[li], cz[li], static_cast<float>(L.coarse.r)))
+                {
+                    for (int s = L.fine_begin; s < L.fine_end; ++s)
+                    {
+                        if (att_hit(fx[s], fy[s], fz[s], static_cast<float>(R.fine[s].r)))
                         {
                             return false;
                         }
@@ -601,6 +699,24 @@ namespace
                 }
             }
         }
+        if (e.has_att && !e.att.empty())
+        {
+            float tx[kMaxAtt], ty[kMaxAtt], tz[kMaxAtt];
+            pose_attachment(R, e, F, tx, ty, tz);
+            for (std::size_t s = 0; s < e.att.size(); ++s)
+            {
+                best = std::min(best, clearance_env(e, tx[s], ty[s], tz[s], e.att[s].r));
+                for (int k = 0; k < R.n_att_links; ++k)
+                {
+                    const OrLink &L = R.links[R.att_links[k]];
+                    for (int i = L.fine_begin; i < L.fine_end; ++i)
+                    {
+                        const double dx = px[i] - tx[s], dy = py[i] - ty[s], dz = pz[i] - tz[s];
+                        best = std::min(best, std::sqrt(dx * dx + dy * dy + dz * dz) - (static_cast<double>(static_cast<float>(R.fine[i].r)) + e.att[s].r));
+                    }
+                }
+            }
+        }
         return best;
     }
 
@@ -658,6 +774,20 @@ extern "C"
         Sphere s{x, y, z, r, 0};
         s.min_d = std::sqrt(x * x + y * y + z * z) - r;  // shapes.hh:236-239
         static_cast<Env *>(e)->spheres.push_back(s);
+    }
+
+    // tf: row-major 3x4 relative to the end effector; xyzr[n][4]; n == 0 removes the attachment (at most kMaxAtt spheres)
+    int or_env_set_attachment(void *e, const float *tf, const float *xyzr, std::int64_t n)
+    {
+        auto &env = *static_cast<Env *>(e);
+        env.att.clear();
+        env.has_att = false;
+        if (n <= 0) return 0;
+        if (n > kMaxAtt) return -1;
+        std::memcpy(env.att_tf, tf, sizeof(env.att_tf));
+        for (std::int64_t i = 0; i < n; ++i) env.att.push_back(Sphere{xyzr[4 * i], xyzr[4 * i + 1], xyzr[4 * i + 2], xyzr[4 * i + 3], 0});
+        env.has_att = true;
+        return 0;
     }
 
     void or_env_add_cuboid(void *e, const float *c, int z_aligned)
@@ -843,6 +973,34 @@ extern "C"
                     o[3] = static_cast<float>(R->fine[s].r);
                 }
             }
+        }
+        return 0;
+    }
+
+    // Robot::eefk (robots/panda.hh:15472-15552): out[m][12] = row-major 3x4 pose of the end effector (identity attachment posed there)
+    int or_eefk(int robot, const float *q, std::int64_t m, float *out)
+    {
+        const OrRobot *R = robot_by_id(robot);
+        if (!R) return -1;
+        Env e;
+        e.has_att = true;
+        e.att = {Sphere{0, 0, 0, 0, 0}, Sphere{1, 0, 0, 0, 0}, Sphere{0, 1, 0, 0, 0}, Sphere{0, 0, 1, 0, 0}};
+        Fr F[kMaxFrames];
+        for (std::int64_t i = 0; i < m; ++i)
+        {
+            fk_frames(*R, q + i * R->dim, F);
+            float x[4], y[4], z[4];
+            pose_attachment(*R, e, F, x, y, z);
+            float *o = out + i * 12;
+            for (int c = 0; c < 3; ++c)
+            {
+                o[c] = x[1 + c] - x[0];
+                o[4 + c] = y[1 + c] - y[0];
+                o[8 + c] = z[1 + c] - z[0];
+            }
+            o[3] = x[0];
+            o[7] = y[0];
+            o[11] = z[0];
         }
         return 0;
     }

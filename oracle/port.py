@@ -43,12 +43,14 @@ def lib():
     L.or_env_add_heightfield.argtypes = [C.c_void_p] + [C.c_float] * 6 + [C.c_int64, C.c_int64, _f32p]
     L.or_env_add_capt.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _u32p, _f32p, C.c_int64, _f32p,
                                   C.c_float, C.c_float, C.c_float]
+    L.or_env_set_attachment.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int64]
     L.or_env_sort.argtypes = [C.c_void_p]
     L.or_env_min_distances.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.or_env_min_distances.restype = C.c_int64
     L.or_validate_motions.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int64, C.c_int, _u8p, C.c_void_p, C.c_int]
     L.or_edge_min_clearance.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int64, C.c_int, _f64p, C.c_int]
     L.or_sphere_fk.argtypes = [C.c_int, _f32p, C.c_int64, _f32p]
+    L.or_eefk.argtypes = [C.c_int, _f32p, C.c_int64, _f32p]
     L.or_robot_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 4 + [_f32p, _f32p]
     L.or_trig.argtypes = [_f32p, C.c_int64, _f32p, _f32p]
     L.or_knn.argtypes = [_f64p, C.c_int64, _f64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
@@ -96,6 +98,14 @@ def sphere_fk(robot: str, q) -> np.ndarray:
     return out
 
 
+def eefk(robot: str, q) -> np.ndarray:
+    """[M][3][4] end-effector pose (Robot::eefk) from the restatement's frames."""
+    q = _f32(q)
+    out = np.zeros((q.shape[0], 3, 4), np.float32)
+    assert lib().or_eefk(ROBOT_ID[robot], q, q.shape[0], out.reshape(-1)) == 0
+    return out
+
+
 class PortEnvironment:
     def __init__(self):
         self._L = lib()
@@ -110,6 +120,14 @@ class PortEnvironment:
     def add_spheres(self, xyzr):
         for s in _f32(xyzr).reshape(-1, 4):
             self._L.or_env_add_sphere(self._h, *[float(v) for v in s])
+
+    def set_attachment(self, tf, xyzr):
+        """collision/attachments.hh:13-56 (see oracle_validate.cpp::pose_attachment); tf = 3x4 [R | t] relative to the end effector."""
+        xyzr = _f32(xyzr).reshape(-1, 4)
+        assert self._L.or_env_set_attachment(self._h, _f32(np.asarray(tf, np.float32).reshape(-1)[:12].copy()), xyzr, xyzr.shape[0]) == 0
+
+    def clear_attachment(self):
+        self._L.or_env_set_attachment(self._h, np.zeros(12, np.float32), np.zeros((0, 4), np.float32), 0)
 
     def add_cuboids(self, c15, z_aligned=False):
         for c in _f32(c15).reshape(-1, 15):

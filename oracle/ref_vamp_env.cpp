@@ -50,6 +50,33 @@ extern "C"
             vc::HeightField<float>(cx, cy, cz, 1.F / sx, 1.F / sy, 1.F / sz, static_cast<std::size_t>(nx), static_cast<std::size_t>(ny), d));
     }
 
+    // Attachment (collision/attachments.hh:13-56): tf = row-major 3x4 [R | t] of the attachment relative to the end effector,
+    // xyzr[n][4] its spheres in the attachment's frame. n == 0 removes it.
+    void refv_env_set_attachment(void *e, const float *tf, const float *xyzr, std::int64_t n)
+    {
+        auto &env = static_cast<Env *>(e)->f;
+        env.attachments.reset();
+        if (n <= 0)
+        {
+            return;
+        }
+        Eigen::Transform<float, 3, Eigen::Isometry> t;
+        for (int r = 0; r < 3; ++r)
+        {
+            for (int c = 0; c < 3; ++c)
+            {
+                t.linear()(r, c) = tf[4 * r + c];
+            }
+            t.translation()[r] = tf[4 * r + 3];
+        }
+        vc::Attachment<float> a(t);
+        for (std::int64_t i = 0; i < n; ++i)
+        {
+            a.spheres.emplace_back(vc::Sphere<float>(xyzr[4 * i], xyzr[4 * i + 1], xyzr[4 * i + 2], xyzr[4 * i + 3]));
+        }
+        env.attachments.emplace(a);
+    }
+
     void refv_env_sort(void *e) { static_cast<Env *>(e)->f.sort(); }
 
     void refv_env_finalize(void *e)

@@ -16,6 +16,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -87,17 +88,21 @@ namespace refv
         {
             nthreads = 1;
         }
-        auto body = [&](std::int64_t b, std::int64_t en)
+        // fkcc_attach re-poses the attachment inside the (const) environment (collision/attachments.hh:37-41, a `mutable`
+        // member): threads sharing one environment would race, so with an attachment every thread works on its own copy
+        const bool own_copy = e->v->attachments.has_value() && nthreads > 1;
+        auto body_on = [&](const EnvV &env, std::int64_t b, std::int64_t en)
         {
             if (resolution == 1)
             {
-                run_motions<Robot, 1>(*e->v, q0, q1, b, en, out);
+                run_motions<Robot, 1>(env, q0, q1, b, en, out);
             }
             else
             {
-                run_motions<Robot, Robot::resolution>(*e->v, q0, q1, b, en, out);
+                run_motions<Robot, Robot::resolution>(env, q0, q1, b, en, out);
             }
         };
+        auto body = [&](std::int64_t b, std::int64_t en) { body_on(*e->v, b, en); };
         if (resolution != 1 && resolution != 0 && resolution != static_cast<int>(Robot::resolution))
         {
             return -2;  // the reference fixes resolution at compile time
@@ -116,6 +121,12 @@ namespace refv
             pool.emplace_back(
                 [&]()
                 {
+                    std::unique_ptr<EnvV> mine;
+                    if (own_copy)
+                    {
+                        mine = std::make_unique<EnvV>(*e->v);
+                    }
+                    const EnvV &env = own_copy ? *mine : *e->v;
                     for (;;)
                     {
                         const std::int64_t b = next.fetch_add(chunk);
@@ -123,7 +134,7 @@ namespace refv
                         {
                             break;
                         }
-                        body(b, std::min(b + chunk, m));
+                        body_on(env, b, std::min(b + chunk, m));
                     }
                 });
         }
@@ -169,6 +180,30 @@ namespace refv
                     o[2] = zs[l];
                     o[3] = rs[l];
                 }
+            }
+        }
+        return 0;
+    }
+    // Robot::eefk (robots/panda.hh:15472-15552): the end-effector pose for scalar configurations
+    template <typename Robot>
+    inline int eefk(const float *q, std::int64_t m, float *out)
+    {
+        constexpr std::size_t d = Robot::dimension;
+        for (std::int64_t i = 0; i < m; ++i)
+        {
+            std::array<float, d> x;
+            for (std::size_t j = 0; j < d; ++j)
+            {
+                x[j] = q[i * d + j];
+            }
+            const auto tf = Robot::eefk(x);
+            for (int r = 0; r < 3; ++r)
+            {
+                for (int c = 0; c < 3; ++c)
+                {
+                    out[i * 12 + 4 * r + c] = tf.linear()(r, c);
+                }
+                out[i * 12 + 4 * r + 3] = tf.translation()[r];
             }
         }
         return 0;

@@ -34,4 +34,7 @@ extern "C"
     }
 
     int refv_panda_sphere_fk(const float *q, std::int64_t m, float *out) { return refv::sphere_fk<Robot>(q, m, out); }
+
+    // out[m][12] = row-major 3x4 [R | t] of Robot::eefk (the frame fkcc_attach poses attachments in)
+    int refv_panda_eefk(const float *q, std::int64_t m, float *out) { return refv::eefk<Robot>(q, m, out); }
 }

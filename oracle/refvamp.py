@@ -41,6 +41,7 @@ def lib():
     L.refv_env_add_capsule.argtypes = [C.c_void_p, _f32p, C.c_int]
     L.refv_env_add_heightfield.argtypes = [C.c_void_p] + [C.c_float] * 6 + [C.c_int64, C.c_int64, _f32p]
     L.refv_env_add_pointcloud.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_float, C.c_float, C.c_float]
+    L.refv_env_set_attachment.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int64]
     L.refv_env_sort.argtypes = [C.c_void_p]
     L.refv_env_finalize.argtypes = [C.c_void_p]
     L.refv_env_min_distances.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -55,6 +56,7 @@ def lib():
         getattr(L, f"refv_{r}_validate_motions").argtypes = [
             C.c_void_p, _f32p, _f32p, C.c_int64, C.c_int, _u8p, C.c_int]
         getattr(L, f"refv_{r}_sphere_fk").argtypes = [_f32p, C.c_int64, _f32p]
+        getattr(L, f"refv_{r}_eefk").argtypes = [_f32p, C.c_int64, _f32p]
     _lib = L
     return L
 
@@ -100,6 +102,17 @@ class RefEnvironment:
     def add_pointcloud(self, xyz, r_min, r_max, r_point):
         xyz = _f32(xyz).reshape(-1, 3)
         self._L.refv_env_add_pointcloud(self._h, xyz, xyz.shape[0], r_min, r_max, r_point)
+        self._final = False
+
+    def set_attachment(self, tf, xyzr):
+        """Attachment<float>(tf) + spheres (collision/attachments.hh:13-56); tf = 3x4 [R | t] relative to the end effector.
+        With an attachment validate_motion runs Robot::fkcc_attach (planning/validate.hh:43,58)."""
+        xyzr = _f32(xyzr).reshape(-1, 4)
+        self._L.refv_env_set_attachment(self._h, _f32(tf).reshape(-1)[:12].copy(), xyzr, xyzr.shape[0])
+        self._final = False
+
+    def clear_attachment(self):
+        self._L.refv_env_set_attachment(self._h, np.zeros(12, np.float32), np.zeros((0, 4), np.float32), 0)
         self._final = False
 
     def sort(self):
@@ -173,6 +186,14 @@ def sphere_fk(robot: str, q) -> np.ndarray:
     ns = int(getattr(L, f"refv_{robot}_n_spheres")())
     out = np.zeros((q.shape[0], ns, 4), np.float32)
     getattr(L, f"refv_{robot}_sphere_fk")(q, q.shape[0], out)
+    return out
+
+
+def eefk(robot: str, q) -> np.ndarray:
+    """Robot::eefk: [M][3][4] end-effector pose [R | t]."""
+    q = _f32(q)
+    out = np.zeros((q.shape[0], 3, 4), np.float32)
+    getattr(lib(), f"refv_{robot}_eefk")(q, q.shape[0], out.reshape(-1))
     return out
 
 

@@ -110,6 +110,17 @@ static void test_validators(const b2::EnginePtr &eng)
     for (auto v : sv) nvalid += v;
     EXPECT(nvalid > 10 && nvalid < 390);
 
+    // a grasped object (collision/attachments.hh): a 6 cm ball 5 cm beyond the hand leaves the start state valid,
+    // a 60 cm one reaches the cage; clearing it restores the bare robot. No re-commit.
+    const std::array<float, 12> tf = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0.05F};
+    env->setAttachment(tf, {{0.F, 0.F, 0.F, 0.03F}});
+    EXPECT(svc->isValid(&start.s));
+    env->setAttachment(tf, {{0.F, 0.F, 0.F, 0.03F}, {0.F, 0.F, 0.1F, 0.3F}});
+    EXPECT(!svc->isValid(&start.s));
+    EXPECT(!mv->checkMotion(&start.s, &start.s));
+    env->clearAttachment();
+    EXPECT(svc->isValid(&start.s));
+
     // an environment that was not committed is an error surfaced as ompl::Exception
     auto env2 = std::make_shared<b2::Environment>(eng);
     env2->addSphere({1, 0, 0}, 0.1F);

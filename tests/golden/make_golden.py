@@ -101,7 +101,54 @@ def chain_case():
     print(f"chain: states valid {sv.mean():.3f}, motions valid {v0.mean():.3f}, nd mean {nd.mean():.1f} max {nd.max()}")
 
 
+ATTACH_SCENES = dict(
+    panda=dict(seed=41, n_spheres=40, n_cuboids=40, n_capsules=8, n_zcuboids=8, n_zcapsules=8),
+    panda_unsorted=dict(seed=42, n_spheres=30, n_cuboids=30, n_capsules=6, n_zcuboids=6, n_zcapsules=6),
+    fetch=dict(seed=43, n_spheres=30, n_cuboids=30, n_capsules=6, n_zcuboids=6, n_zcapsules=6, rho_lo=0.6, rho_hi=1.4, z_lo=0.2, z_hi=1.6),
+    ur5=dict(seed=44, n_spheres=40, n_cuboids=40, n_capsules=8),
+    baxter=dict(seed=45, n_spheres=6, n_cuboids=6, n_capsules=3),
+)
+
+
+def attachment(seed):
+    """A grasped object: a rotated, offset pose relative to the end effector and a few spheres of mixed size."""
+    rng = np.random.default_rng(seed)
+    a, b = rng.uniform(-0.6, 0.6, 2)
+    rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+    tf = np.concatenate([rz @ rx, rng.uniform(-0.03, 0.03, (3, 1)) + np.array([[0], [0], [0.06]])], axis=1).astype(np.float32)
+    n = int(rng.integers(3, 9))
+    sph = np.concatenate([rng.uniform(-0.08, 0.08, (n, 2)), rng.uniform(0.0, 0.3, (n, 1)), rng.uniform(0.015, 0.07, (n, 1))], axis=1).astype(np.float32)
+    return tf, sph
+
+
+def attachment_cases():
+    """Robot::fkcc_attach of the unmodified reference (collision/attachments.hh, robots/<robot>.hh) through oracle/_ref, whose
+    Eigen stand-in (oracle/shim/Eigen) executes Transform * Transform and Transform * Vector3 with plain float arithmetic."""
+    out = {}
+    for tag, kw in ATTACH_SCENES.items():
+        robot = tag.split("_")[0]
+        scene = synth.clutter_scene(**kw)
+        is_sorted = not tag.endswith("unsorted")
+        env = synth.fill_env(refvamp.RefEnvironment(), scene, sort=is_sorted)
+        tf, sph = attachment(kw["seed"])
+        q = synth.uniform_states(robot, 3000, kw["seed"] + 1)
+        bare = env.validate_states(robot, q)
+        env.set_attachment(tf, sph)
+        sv = env.validate_states(robot, q)
+        starts = np.resize(q[sv == 1], (1200, q.shape[1]))
+        q0, q1 = synth.local_edges(robot, starts, kw["seed"] + 2, 0.05, 2.5)
+        mv = env.validate_motions(robot, q0, q1)
+        out.update({f"{tag}_tf": tf, f"{tag}_spheres": sph, f"{tag}_states": q, f"{tag}_states_valid_bare": bare, f"{tag}_states_valid": sv,
+                    f"{tag}_q0": q0, f"{tag}_q1": q1, f"{tag}_motions_valid": mv, f"{tag}_eefk": refvamp.eefk(robot, q[:64])})
+        print(f"attach {tag}: states valid {bare.mean():.3f} -> {sv.mean():.3f} with the attachment, motions valid {mv.mean():.3f}")
+    np.savez_compressed(os.path.join(HERE, "attach.npz"), **out)
+
+
 def main():
+    if "--attachments" in sys.argv:
+        attachment_cases()
+        return
     if "--chain" in sys.argv:
         chain_case()
         return

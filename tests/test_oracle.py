@@ -26,6 +26,35 @@ def test_port_matches_golden_validity(name):
     assert_validity_parity(mv, z["motions_valid"], lambda b: env.edge_min_clearance(robot, z["q0"][b], z["q1"][b]), name + " motions")
 
 
+ATTACH_CASES = ["panda", "panda_unsorted", "fetch", "ur5", "baxter"]
+
+
+def attach_scene(tag):
+    from tests.golden.make_golden import ATTACH_SCENES
+    return synth.clutter_scene(**ATTACH_SCENES[tag]), tag.split("_")[0], not tag.endswith("unsorted")
+
+
+@pytest.mark.parametrize("tag", ATTACH_CASES)
+def test_port_matches_golden_attachments(tag):
+    """Robot::fkcc_attach (collision/attachments.hh:13-56, robots/<robot>.hh): golden answers of the unmodified reference."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "attach.npz"))
+    scene, robot, is_sorted = attach_scene(tag)
+    env = synth.fill_env(port.PortEnvironment(), scene, sort=is_sorted)
+    q, q0, q1 = z[tag + "_states"], z[tag + "_q0"], z[tag + "_q1"]
+    clr_s = lambda b: env.edge_min_clearance(robot, q[b], q[b], resolution=1)
+    assert_validity_parity(env.validate_states(robot, q, nthreads=4), z[tag + "_states_valid_bare"], clr_s, tag + " bare states")
+    env.set_attachment(z[tag + "_tf"], z[tag + "_spheres"])
+    assert_validity_parity(env.validate_states(robot, q, nthreads=4), z[tag + "_states_valid"], clr_s, tag + " states")
+    assert (z[tag + "_states_valid"] <= z[tag + "_states_valid_bare"]).all() and (z[tag + "_states_valid"] < z[tag + "_states_valid_bare"]).any()
+    assert_validity_parity(env.validate_motions(robot, q0, q1, nthreads=4), z[tag + "_motions_valid"],
+                           lambda b: env.edge_min_clearance(robot, q0[b], q1[b]), tag + " motions")
+    # the end-effector frame the attachment is posed in
+    # (Robot::eefk is the reference's SCALAR trace: libm sin / cos, where fkcc_attach and the restatement use the 4.2e-6 polynomials)
+    assert np.abs(port.eefk(robot, q[:64]) - z[tag + "_eefk"]).max() < 3e-5
+    env.clear_attachment()
+    assert_validity_parity(env.validate_states(robot, q, nthreads=4), z[tag + "_states_valid_bare"], clr_s, tag + " cleared")
+
+
 def test_demo_known_answers():
     # demos/vamp/VAMPPlanning.cpp:43-47,87-88: start and goal are valid in the 14-sphere cage, the straight edge is not
     env = synth.fill_env(port.PortEnvironment(), synth.cage_scene())

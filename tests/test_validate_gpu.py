@@ -35,6 +35,60 @@ def test_golden_validity(ctx, name):
     assert_validity_parity(mv, z["motions_valid"], clr_motions(pe, robot, z["q0"], z["q1"]), name + " motions")
 
 
+@pytest.mark.parametrize("tag", ["panda", "panda_unsorted", "fetch", "ur5", "baxter"])
+@pytest.mark.parametrize("grid", [True, False])
+def test_golden_attachments(ctx, tag, grid):
+    """Robot::fkcc_attach: golden answers of the unmodified reference (tests/golden/attach.npz), set / replace / clear after commit."""
+    import os
+    from tests.golden.make_golden import ATTACH_SCENES
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "attach.npz"))
+    robot, is_sorted = tag.split("_")[0], not tag.endswith("unsorted")
+    if not is_sorted and grid:
+        pytest.skip("unsorted scenes have no grid")
+    scene = synth.clutter_scene(**ATTACH_SCENES[tag])
+    env = ompl_b200.Environment(ctx)
+    env.set_grid(grid)
+    synth.fill_env(env, scene, sort=is_sorted)
+    pe = synth.fill_env(port.PortEnvironment(), scene, sort=is_sorted)
+    q, q0, q1 = z[tag + "_states"], z[tag + "_q0"], z[tag + "_q1"]
+    assert_validity_parity(ctx.validate_states(robot, env, q), z[tag + "_states_valid_bare"], clr_states(pe, robot, q), tag + " bare")
+    env.set_attachment(z[tag + "_tf"], z[tag + "_spheres"])
+    pe.set_attachment(z[tag + "_tf"], z[tag + "_spheres"])
+    assert_validity_parity(ctx.validate_states(robot, env, q), z[tag + "_states_valid"], clr_states(pe, robot, q), tag + " states")
+    assert_validity_parity(ctx.validate_motions(robot, env, q0, q1), z[tag + "_motions_valid"], clr_motions(pe, robot, q0, q1), tag + " motions")
+    # the bucketed path (packed rakes, first look) sees the attachment as well: a batch large enough to take it
+    reps = 4096 // len(q0) + 1
+    big0, big1 = np.tile(q0, (reps, 1)), np.tile(q1, (reps, 1))
+    got = ctx.validate_motions(robot, env, big0, big1)
+    assert_validity_parity(got, np.tile(z[tag + "_motions_valid"], reps), clr_motions(pe, robot, big0, big1), tag + " bucketed motions")
+    env.clear_attachment()
+    pe.clear_attachment()
+    assert_validity_parity(ctx.validate_states(robot, env, q), z[tag + "_states_valid_bare"], clr_states(pe, robot, q), tag + " cleared")
+
+
+def test_attachment_seeded_vs_oracle_with_cloud_and_terrain(ctx):
+    """An attachment in a scene with a point cloud and a height field as well (every obstacle kind the attachment is tested against)."""
+    scene = synth.clutter_scene(14, 20, 20, n_capsules=6, rho_lo=0.6, rho_hi=1.4, z_lo=0.2, z_hi=1.6)
+    scene.update(synth.terrain(seed=5))
+    pts = synth.shelf_cloud(800, seed=3, robot="fetch")
+    env = ompl_b200.Environment(ctx)
+    pe = port.PortEnvironment()
+    env.add_pointcloud(pts, 0.012, 0.24, 0.0025)
+    pe.add_capt(ompl_b200.capt_build(pts, 0.012, 0.24, 0.0025))
+    synth.fill_env(env, scene)
+    synth.fill_env(pe, scene)
+    tf = np.array([[1, 0, 0, 0.0], [0, 1, 0, 0.0], [0, 0, 1, 0.1]], np.float32)
+    sph = np.array([[0, 0, 0, 0.06], [0, 0, 0.12, 0.05], [0.05, 0, 0.2, 0.03]], np.float32)
+    env.set_attachment(tf, sph)
+    pe.set_attachment(tf, sph)
+    q = synth.uniform_states("fetch", 8000, 23)
+    want = pe.validate_states("fetch", q, nthreads=8)
+    assert_validity_parity(ctx.validate_states("fetch", env, q), want, clr_states(pe, "fetch", q), "states")
+    q0, q1 = synth.local_edges("fetch", q[want == 1][:1500], 29, 0.05, 2.0)
+    want = pe.validate_motions("fetch", q0, q1, nthreads=8)
+    assert_validity_parity(ctx.validate_motions("fetch", env, q0, q1), want, clr_motions(pe, "fetch", q0, q1), "motions")
+
+
 def test_demo_known_answers(ctx):
     env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
     assert list(ctx.validate_states("panda", env, [synth.CAGE_START, synth.CAGE_GOAL])) == [1, 1]

@@ -35,11 +35,11 @@ REF = os.environ.get("OMPL_REF", "/root/reference")
 
 
 # ----------------------------------------------------------------------------- trace evaluation
-def load_fkcc_source(hh_path: str):
+def load_fkcc_source(hh_path: str, fn: str = "fkcc"):
     src = open(hh_path).read().split("\n")
     start = None
     for i, line in enumerate(src):
-        if "inline static bool fkcc(" in line:
+        if f"inline static bool {fn}(" in line:
             start = i
             break
     assert start is not None
@@ -333,11 +333,58 @@ def extract(robot: str):
     slack = min(l["coarse"]["r"] - (np.linalg.norm(np.asarray(f["c"]) - np.asarray(l["coarse"]["c"])) + f["r"])
                 for l in model_links for f in l["fine"])
 
-    model = dict(
-        name=robot, dimension=dim, n_fine=n_fine, resolution=resolution,
+    # ---- attachments (Robot::fkcc_attach): the end-effector frame the attachment is posed in and the links tested against it.
+    # The trace of fkcc_attach is evaluated like fkcc's; `set_attachment_pose(environment, to_isometry(&y[N]))` names the 12
+    # outputs holding the pose (translation, then the rotation column by column: vector/math.hh:39-51); it must be a constant
+    # transform away from one of the moving frames. "// Attachment vs. <link>" blocks list bounding sphere, then fine spheres.
+    abody = load_fkcc_source(hh, "fkcc_attach")
+    a_nv = int(re.search(r"FloatVector<rake, 1>, (\d+)> v;", "\n".join(abody)).group(1))
+    a_ny = int(re.search(r"FloatVector<rake, 1>, (\d+)> y;", "\n".join(abody)).group(1))
+    a_fk, a_rest = split_trace(abody)
+    ya = eval_trace(a_fk, qs, a_ny, a_nv)
+    assert np.abs(ya[:n_y] - y).max() < 1e-12, "fkcc_attach must lay out its spheres like fkcc"
+    ee_off = int(re.search(r"set_attachment_pose\(environment, to_isometry\(&y\[(\d+)\]\)\)", "\n".join(a_rest)).group(1))
+    ee_t = ya[ee_off:ee_off + 3].T                                        # [64, 3]
+    ee_r = ya[ee_off + 3:ee_off + 12].T.reshape(64, 3, 3).transpose(0, 2, 1)  # column-major -> [64][row][col]
+    ee = None
+    for idx in reversed(range(len(actuated))):
+        j = next(jj for jj in joints if jj["name"] == actuated[idx])
+        loc_r, loc_t = [], []
+        for m in range(64):
+            rf, tf_ = tfs[m][j["child"]]
+            loc_r.append(rf.T @ ee_r[m])
+            loc_t.append(rf.T @ (ee_t[m] - tf_))
+        loc_r, loc_t = np.asarray(loc_r), np.asarray(loc_t)
+        if loc_r.std(axis=0).max() < 1e-7 and loc_t.std(axis=0).max() < 1e-7:
+            ee = dict(frame=idx + 1, R=loc_r.mean(axis=0).tolist(), t=loc_t.mean(axis=0).tolist())
+            break
+    assert ee is not None, "end-effector pose is not rigidly attached to any moving frame"
+    att_links = []
+    cur = None
+    for line in a_rest:
+        mm = re.match(r"^//\s*Attachment vs\. ([A-Za-z0-9_]+)\s*$", line)
+        if mm:
+            cur = [mm.group(1), None, []]
+            att_links.append(cur)
+            continue
+        mm = re.search(r"attachment_sphere_collision<[^>]*>\(\s*environment,\s*y\[(\d+)\]", line)
+        if mm and cur is not None:
+            if cur[1] is None:
+                cur[1] = int(mm.group(1))
+            else:
+                cur[2].append(int(mm.group(1)))
+    att = []
+    for (lname, cy, fys) in att_links:
+        li = name_to_link[lname]
+        assert coarse_y[cy] == lname, (lname, cy)
+        assert sorted(fys) == sorted(4 * f["id"] for f in model_links[li]["fine"]), lname
+        att.append(li)
+    attachment = dict(ee_frame=ee["frame"], R=ee["R"], t=ee["t"], links=att, link_names=[a[0] for a in att_links])
+
+    model = dict(        name=robot, dimension=dim, n_fine=n_fine, resolution=resolution,
         s_a=s_a, s_m=s_m, joint_names=actuated,
         min_radius=const("min_radius"), max_radius=const("max_radius"),
-        frames=frames, links=model_links, self_pairs=pairs,
+        frames=frames, links=model_links, self_pairs=pairs, attachment=attachment,
         provenance=dict(urdf=os.path.relpath(urdf, REF), trace=os.path.relpath(hh, REF),
                         fine_match_max_err_m=float(worst), urdf_spheres_not_in_reference=unused,
                         min_bounding_slack_m=float(slack),

@@ -174,6 +174,8 @@ def gen_cuda(model: dict) -> str:
 
     lo = [float(np.float32(a)) for a in model["s_a"]]
     hi = [float(np.float32(np.float32(a) + np.float32(m))) for a, m in zip(model["s_a"], model["s_m"])]
+    att = model["attachment"]
+    att_links = sorted((new_index[a] for a in att["links"]), key=lambda i: (link_rows[i]["frame"], i))
 
     out = []
     w = out.append
@@ -196,6 +198,7 @@ def gen_cuda(model: dict) -> str:
     w(f"    short save_slot[{nfr}];             // slot frame k is saved to for later pairs, or -1")
     w(f"    short link_frame[{nl}];             // frame link l lives on")
     w(f"    short frame_branch[{nfr}];          // first frame of the chain (arm) frame k belongs to; its parent is the world frame")
+    w(f"    short att_links[{len(att_links)}];  // links tested against an attachment (Robot::fkcc_attach), in frame order")
     w("};")
     w("")
     w(f"__constant__ {cname}Tables k{cname}Tables = {{")
@@ -211,6 +214,7 @@ def gen_cuda(model: dict) -> str:
     w("    {" + ", ".join(str(v) for v in save_slot) + "},")
     w("    {" + ", ".join(str(r["frame"]) for r in link_rows) + "},")
     w("    {" + ", ".join(str(v) for v in frame_branch) + "},")
+    w("    {" + ", ".join(str(v) for v in att_links) + "},")
     w("};")
     w("")
     w(f"struct {cname} {{")
@@ -222,6 +226,8 @@ def gen_cuda(model: dict) -> str:
     w(f"    static constexpr int kResolution = {model['resolution']};")
     w(f"    static constexpr int kSlots = {max(1, len(a_frames))};   // saved frames needed by the self-collision stage")
     w(f"    static constexpr int kRobotId = {ROBOT_IDS[name]};")
+    w(f"    static constexpr int kAttLinks = {len(att_links)};   // links an attachment is tested against")
+    w(f"    static constexpr int kEeFrame = {att['ee_frame']};   // moving frame the end effector ({cname}::eefk) is rigidly attached to")
     w("    static constexpr float kLo[kDim] = {" + ", ".join(f32(v) for v in lo) + "};")
     w("    static constexpr float kHi[kDim] = {" + ", ".join(f32(v) for v in hi) + "};")
     w(f"    using Tables = {cname}Tables;")
@@ -246,6 +252,8 @@ def gen_cuda(model: dict) -> str:
     w("    // (same arithmetic as frame_apply on the streamed frames; zero coefficients dropped, which leaves the values unchanged)")
     w("    template <class St>")
     w("    __device__ static __forceinline__ void fk_coarse(const float (&q)[kDim], const float (&sn)[kDim], const float (&cs)[kDim], Frame &tip, St st);")
+    w("    // E = P * (constant end-effector offset), P = frame kEeFrame: the pose Robot::eefk returns, in which attachments are posed")
+    w("    __device__ static __forceinline__ void ee_pose(const Frame &P, Frame &E);")
     w("    // step the streaming frame from k-1 to k (k >= 1); uniform switch, static joint indices")
     w("    __device__ static __forceinline__ void advance(int k, Frame &F, const float (&q)[kDim], const float (&sn)[kDim], const float (&cs)[kDim]);")
     w("};")
@@ -261,6 +269,19 @@ def gen_cuda(model: dict) -> str:
             w("    " + ln)
         w("}")
         w("")
+    em = Emitter()
+    er = np.asarray(att["R"], dtype=np.float64)
+    et = np.asarray(att["t"], dtype=np.float64)
+    pr = [[f"P.r[{3 * i + j}]" for j in range(3)] for i in range(3)]
+    w(f"__device__ __forceinline__ void {cname}::ee_pose(const Frame &P, Frame &E) {{")
+    for i in range(3):
+        for j in range(3):
+            w(f"    E.r[{3 * i + j}] = {em.lit(em.sum([em.mul(pr[i][k], float(er[k][j])) for k in range(3)]))};")
+    for i in range(3):
+        w(f"    E.t[{i}] = {em.lit(em.add(em.sum([em.mul(pr[i][k], float(et[k])) for k in range(3)]), f'P.t[{i}]'))};")
+    w("}")
+    w("")
+
     def apply_expr(fname, row, c):
         acc = f"{fname}.t[{row}]"
         for j in (2, 1, 0):
@@ -317,7 +338,8 @@ def gen_oracle_tables(models: list) -> str:
     w("typedef struct { int frame; OrSphere coarse; int fine_begin, fine_end; } OrLink;")
     w("typedef struct { const char *name; int dim, n_frames, n_links, n_fine, n_pairs, resolution;")
     w("                 const OrFrame *frames; const OrLink *links; const OrSphere *fine; const int *fine_id; const int (*pairs)[2];")
-    w("                 const float *lo; const float *hi; } OrRobot;")
+    w("                 const float *lo; const float *hi;")
+    w("                 int ee_frame; const double *ee_R; const double *ee_t; int n_att_links; const int *att_links; } OrRobot;")
     for m in models:
         n = m["name"]
         frames = m["frames"]
@@ -350,8 +372,13 @@ def gen_oracle_tables(models: list) -> str:
         hi = [float(np.float32(np.float32(a) + np.float32(mm))) for a, mm in zip(m["s_a"], m["s_m"])]
         w(f"static const float {n}_lo[] = {{" + ", ".join(f32(v) for v in lo) + "};")
         w(f"static const float {n}_hi[] = {{" + ", ".join(f32(v) for v in hi) + "};")
+        at = m["attachment"]
+        w(f"static const double {n}_ee_R[] = {{" + ", ".join(repr(float(v)) for v in np.asarray(at["R"]).reshape(-1)) + "};")
+        w(f"static const double {n}_ee_t[] = {{" + ", ".join(repr(float(v)) for v in at["t"]) + "};")
+        w(f"static const int {n}_att_links[] = {{" + ", ".join(str(v) for v in at["links"]) + "};  /* reference order */")
         w(f"static const OrRobot {n}_robot = {{\"{n}\", {m['dimension']}, {len(frames)}, {len(m['links'])}, {len(fine)}, "
-          f"{len(m['self_pairs'])}, {m['resolution']}, {n}_frames, {n}_links, {n}_fine, {n}_fine_id, {n}_pairs, {n}_lo, {n}_hi}};")
+          f"{len(m['self_pairs'])}, {m['resolution']}, {n}_frames, {n}_links, {n}_fine, {n}_fine_id, {n}_pairs, {n}_lo, {n}_hi, "
+          f"{at['ee_frame']}, {n}_ee_R, {n}_ee_t, {len(at['links'])}, {n}_att_links}};")
     return "\n".join(out) + "\n"
 
 
