@@ -169,7 +169,10 @@ int build_grids(b200mp_env *e, SceneDesc *d) {
     if (!regular) return B200MP_OK;  // a cuboid with non-orthonormal axes has no simple bounding box: keep the full scan
     for (const auto &cls : boxes)
         if (cls.size() > 65535) return B200MP_OK;
-    const float reach[kGridLevels] = {0.0625f, 0.11f, 0.18f, 0.36f};
+    // reach ladder: x 1.12 per level from 2.5 cm, the last level 36 cm -- a robot sphere walks the level just above its radius, so the
+    // lists it sees hold little more than what it can actually touch
+    float reach[kGridLevels];
+    for (int l = 0; l < kGridLevels; ++l) reach[l] = l == kGridLevels - 1 ? 0.36f : 0.025f * std::pow(1.12f, static_cast<float>(l));
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (const auto &cls : boxes)
         for (const auto &b : cls)
@@ -193,7 +196,8 @@ int build_grids(b200mp_env *e, SceneDesc *d) {
         const int c = static_cast<int>(std::floor((v - lo[k]) * inv_h));
         return std::min(std::max(c, 0), n[k] - 1);
     };
-    // layout of the device buffer: for level, class: start[cells + 1] (u32) then ids (u16), 16-byte aligned pieces
+    // layout of the device buffer: for level, class: one word per cell ((first entry << 8) | entries), then the entries (u16 record
+    // indices); 16-byte aligned pieces
     struct Piece { size_t start_off, ids_off; std::vector<unsigned> start; std::vector<unsigned short> ids; };
     std::vector<Piece> pieces(kGridLevels * kShapeClasses);
     size_t bytes = 0;
@@ -203,27 +207,59 @@ int build_grids(b200mp_env *e, SceneDesc *d) {
             const auto &cls = boxes[t];
             if (cls.empty()) continue;
             const float grow = reach[l] * 1.0001f + 3e-4f;  // slack covers kHitMargin (bounding spheres are inflated by 0.1 mm) and rounding in the device-side tests
+            // A cell lists obstacle i when the obstacle can be within `grow` of SOME point of the cell: Euclidean distance between the
+            // cell's box (unbounded on the outer side of border cells, which stand in for everything beyond the grid) and the
+            // obstacle's bounding box -- for spheres the distance to the centre minus the radius. Candidate cells = the box range.
+            const bool is_sphere = t == 0;
+            auto gap = [&](int c, int k, float blo, float bhi) {  // distance along axis k between cell c and [blo, bhi]
+                const float clo = c == 0 ? -INFINITY : lo[k] + static_cast<float>(c) * h;
+                const float chi = c == n[k] - 1 ? INFINITY : lo[k] + static_cast<float>(c + 1) * h;
+                return std::max(0.0f, std::max(blo - chi, clo - bhi));
+            };
             p.start.assign(cells + 1, 0u);
             std::vector<int> rng(cls.size() * 6);
+            std::vector<std::pair<unsigned, unsigned short>> hits;  // (cell, obstacle)
             for (size_t i = 0; i < cls.size(); ++i) {
+                const Box &b = cls[i];
+                const float rad = is_sphere ? 0.5f * (b.hi[0] - b.lo[0]) : 0.0f;
+                float blo[3], bhi[3];
                 for (int k = 0; k < 3; ++k) {
-                    rng[6 * i + k] = cell_of(cls[i].lo[k] - grow, k);
-                    rng[6 * i + 3 + k] = cell_of(cls[i].hi[k] + grow, k);
+                    rng[6 * i + k] = cell_of(b.lo[k] - grow, k);
+                    rng[6 * i + 3 + k] = cell_of(b.hi[k] + grow, k);
+                    blo[k] = is_sphere ? 0.5f * (b.lo[k] + b.hi[k]) : b.lo[k];
+                    bhi[k] = is_sphere ? blo[k] : b.hi[k];
                 }
-                for (int z = rng[6 * i + 2]; z <= rng[6 * i + 5]; ++z)
-                    for (int y = rng[6 * i + 1]; y <= rng[6 * i + 4]; ++y)
-                        for (int x = rng[6 * i]; x <= rng[6 * i + 3]; ++x) ++p.start[(static_cast<size_t>(z) * n[1] + y) * n[0] + x + 1];
+                const float lim = (grow + rad) * 1.0001f + 1e-5f;
+                for (int z = rng[6 * i + 2]; z <= rng[6 * i + 5]; ++z) {
+                    const float gz = gap(z, 2, blo[2], bhi[2]);
+                    for (int y = rng[6 * i + 1]; y <= rng[6 * i + 4]; ++y) {
+                        const float gy = gap(y, 1, blo[1], bhi[1]);
+                        for (int x = rng[6 * i]; x <= rng[6 * i + 3]; ++x) {
+                            const float gx = gap(x, 0, blo[0], bhi[0]);
+                            if (gx * gx + gy * gy + gz * gz > lim * lim) continue;
+                            const unsigned cell = static_cast<unsigned>((static_cast<size_t>(z) * n[1] + y) * n[0] + x);
+                            ++p.start[cell + 1];
+                            hits.emplace_back(cell, static_cast<unsigned short>(i));
+                        }
+                    }
+                }
             }
-            for (size_t c = 0; c < cells; ++c) p.start[c + 1] += p.start[c];
-            p.ids.resize(p.start[cells]);
-            std::vector<unsigned> fill(p.start.begin(), p.start.end() - 1);
-            for (size_t i = 0; i < cls.size(); ++i)  // ascending record index inside every cell
-                for (int z = rng[6 * i + 2]; z <= rng[6 * i + 5]; ++z)
-                    for (int y = rng[6 * i + 1]; y <= rng[6 * i + 4]; ++y)
-                        for (int x = rng[6 * i]; x <= rng[6 * i + 3]; ++x)
-                            p.ids[fill[(static_cast<size_t>(z) * n[1] + y) * n[0] + x]++] = static_cast<unsigned short>(i);
+            // counts -> offsets; p.start becomes the per-cell word (first entry << 8) | entries
+            {
+                std::vector<unsigned> off(cells + 1, 0u);
+                for (size_t c = 0; c < cells; ++c) {
+                    if (p.start[c + 1] > 255u) return B200MP_OK;  // a cell this crowded: keep the ordered scan for the whole scene
+                    off[c + 1] = off[c] + p.start[c + 1];
+                }
+                if (off[cells] >= (1u << 24)) return B200MP_OK;
+                p.ids.resize(off[cells]);
+                std::vector<unsigned> fill(off.begin(), off.end() - 1);
+                for (const auto &hc : hits) p.ids[fill[hc.first]++] = hc.second;  // (obstacles were visited in ascending order: so is every cell's list)
+                for (size_t c = 0; c < cells; ++c) p.start[c] = (off[c] << 8) | (off[c + 1] - off[c]);
+                p.start.resize(cells);
+            }
             p.start_off = bytes;
-            bytes += ((cells + 1) * sizeof(unsigned) + 15) / 16 * 16;
+            bytes += (cells * sizeof(unsigned) + 15) / 16 * 16;
             p.ids_off = bytes;
             bytes += (p.ids.size() * sizeof(unsigned short) + 15) / 16 * 16 + 16;
         }
@@ -245,7 +281,7 @@ int build_grids(b200mp_env *e, SceneDesc *d) {
         g.reach = reach[l];
         for (int t = 0; t < kShapeClasses; ++t) {
             const Piece &p = pieces[l * kShapeClasses + t];
-            g.start[t] = p.start.empty() ? nullptr : reinterpret_cast<const unsigned *>(base + p.start_off);
+            g.cellw[t] = p.start.empty() ? nullptr : reinterpret_cast<const unsigned *>(base + p.start_off);
             g.ids[t] = p.start.empty() ? nullptr : reinterpret_cast<const unsigned short *>(base + p.ids_off);
         }
     }

@@ -9,6 +9,17 @@ struct Frame {
     float t[3];
 };
 
+// One step of a robot's state check (generated table `tasks`, run by check_state_grid in validate.cuh):
+//   kTaskFk    : bring the streamed frame to `frame`, park the bounding-sphere centres of links [a, b)
+//   kTaskEnv   : link a against the environment (bounding sphere; its fine spheres when that touches something)
+//   kTaskSelfA : self-collision pair (a, b): bounding spheres; when they touch, the frame of link a is saved ...
+//   kTaskSelfB : ... and, with link b's frame, a's fine spheres (outer loop) are tested against b's
+struct RobotTask {
+    signed char kind, frame;
+    short a, b;
+};
+enum { kTaskFk = 0, kTaskEnv = 1, kTaskSelfA = 2, kTaskSelfB = 3 };
+
 __device__ __forceinline__ void frame_identity(Frame &F) {
     F.r[0] = 1.f; F.r[1] = 0.f; F.r[2] = 0.f;
     F.r[3] = 0.f; F.r[4] = 1.f; F.r[5] = 0.f;

@@ -52,14 +52,15 @@ struct CaptView {
 // that is conservative for it). In a sorted scene the reference's ordered scan stops only at obstacles that cannot
 // touch the sphere (min_distance >= max_extent), so "any listed obstacle has a negative test value" is the same
 // decision as the full scan, found with a few dozen tests instead of a thousand.
-constexpr int kGridLevels = 4;
+constexpr int kGridLevels = 24;
 constexpr int kShapeClasses = 5;  // spheres, capsules, z-capsules, cuboids, z-cuboids
 struct GridView {
     float ox, oy, oz, inv_h;
     int nx, ny, nz;
     float reach;
-    const unsigned *start[kShapeClasses];        // CSR row starts [cells + 1]
-    const unsigned short *ids[kShapeClasses];    // record indices into the staged class arrays
+    // per cell one word (first list entry << 8) | entries; entries = u16 record indices into the staged class arrays
+    const unsigned *cellw[kShapeClasses];
+    const unsigned short *ids[kShapeClasses];
 };
 
 // Scene as one packed float blob (16-byte aligned sections). Offsets are in floats.
@@ -338,14 +339,11 @@ __device__ __forceinline__ bool grid_should_stop(bool hit, bool on, bool any_mod
 // One shape class: every lane walks the candidate list of its own cell; record `n` (the first padding record) stands in
 // once a lane's list is exhausted, so the loop body needs no predication.
 template <class Test>
-__device__ __forceinline__ int grid_scan_class(const unsigned *__restrict__ start, const unsigned short *__restrict__ ids, int cell,
+__device__ __forceinline__ int grid_scan_class(const unsigned *__restrict__ cellw, const unsigned short *__restrict__ ids, int cell,
                                                const float4 *__restrict__ obs, int n, float x, float y, float z, float r, float rsq,
                                                bool on, bool any_mode, int acc) {
-    unsigned b = 0, cnt = 0;
-    if (on) {
-        b = __ldg(start + cell);
-        cnt = __ldg(start + cell + 1) - b;
-    }
+    const unsigned w = on ? __ldg(cellw + cell) : 0u;
+    const unsigned cnt = w & 255u, b = w >> 8;
     const unsigned wmax = __reduce_max_sync(kFull, cnt);
 #pragma unroll 1
     for (unsigned i = 0; i < wmax; i += 2) {
@@ -363,22 +361,22 @@ __device__ __forceinline__ bool grid_scan_scene(const GridView &g, const Scene &
     const float rsq = r * r;
     int acc = 0;
     if (sc.n_sph > 0) {
-        acc = grid_scan_class<SphereTest>(g.start[0], g.ids[0], cell, sc.sph, sc.n_sph, x, y, z, r, rsq, on, any_mode, acc);
+        acc = grid_scan_class<SphereTest>(g.cellw[0], g.ids[0], cell, sc.sph, sc.n_sph, x, y, z, r, rsq, on, any_mode, acc);
         if (grid_should_stop(acc < 0, on, any_mode)) return acc < 0;
     }
     if (sc.n_cap > 0) {
-        acc = grid_scan_class<CapsuleTest>(g.start[1], g.ids[1], cell, sc.cap, sc.n_cap, x, y, z, r, rsq, on, any_mode, acc);
+        acc = grid_scan_class<CapsuleTest>(g.cellw[1], g.ids[1], cell, sc.cap, sc.n_cap, x, y, z, r, rsq, on, any_mode, acc);
         if (grid_should_stop(acc < 0, on, any_mode)) return acc < 0;
     }
     if (sc.n_zcap > 0) {
-        acc = grid_scan_class<ZCapsuleTest>(g.start[2], g.ids[2], cell, sc.zcap, sc.n_zcap, x, y, z, r, rsq, on, any_mode, acc);
+        acc = grid_scan_class<ZCapsuleTest>(g.cellw[2], g.ids[2], cell, sc.zcap, sc.n_zcap, x, y, z, r, rsq, on, any_mode, acc);
         if (grid_should_stop(acc < 0, on, any_mode)) return acc < 0;
     }
     if (sc.n_cub > 0) {
-        acc = grid_scan_class<CuboidTest>(g.start[3], g.ids[3], cell, sc.cub, sc.n_cub, x, y, z, r, rsq, on, any_mode, acc);
+        acc = grid_scan_class<CuboidTest>(g.cellw[3], g.ids[3], cell, sc.cub, sc.n_cub, x, y, z, r, rsq, on, any_mode, acc);
         if (grid_should_stop(acc < 0, on, any_mode)) return acc < 0;
     }
-    if (sc.n_zcub > 0) acc = grid_scan_class<ZCuboidTest>(g.start[4], g.ids[4], cell, sc.zcub, sc.n_zcub, x, y, z, r, rsq, on, any_mode, acc);
+    if (sc.n_zcub > 0) acc = grid_scan_class<ZCuboidTest>(g.cellw[4], g.ids[4], cell, sc.zcub, sc.n_zcub, x, y, z, r, rsq, on, any_mode, acc);
     return acc < 0;
 }
 
@@ -390,17 +388,14 @@ __device__ __forceinline__ bool grid_scan_scene(const GridView &g, const Scene &
 // not; the fine tests it triggers are exact and cannot hit unless a fine sphere really intersects, so decisions are unchanged.
 // Returns the number of hits, kHitCap + 1 meaning "more than fit": the caller then falls back to per-sphere walks.
 constexpr float kHitMargin = 1.0e-4f;
-constexpr int kHitCap = 6;  // list entries per lane
+constexpr int kHitCap = 8;  // list entries per lane
 
 template <class Test, int BT>
-__device__ __forceinline__ int grid_collect_class(const unsigned *__restrict__ start, const unsigned short *__restrict__ ids, int cell,
+__device__ __forceinline__ int grid_collect_class(const unsigned *__restrict__ cellw, const unsigned short *__restrict__ ids, int cell,
                                                   const float4 *__restrict__ obs, int n, int cls, float x, float y, float z, float r, float rsq,
                                                   bool on, float *__restrict__ hits, int cnt) {
-    unsigned b = 0, c = 0;
-    if (on) {
-        b = __ldg(start + cell);
-        c = __ldg(start + cell + 1) - b;
-    }
+    const unsigned w = on ? __ldg(cellw + cell) : 0u;
+    const unsigned c = w & 255u, b = w >> 8;
     const unsigned wmax = __reduce_max_sync(kFull, c);
 #pragma unroll 1
     for (unsigned i = 0; i < wmax; i += 2) {
@@ -427,40 +422,38 @@ __device__ __forceinline__ int grid_collect_scene(const GridView &g, const Scene
     r += kHitMargin;
     const float rsq = r * r;
     int cnt = 0;
-    if (sc.n_sph > 0) cnt = grid_collect_class<SphereTest, BT>(g.start[0], g.ids[0], cell, sc.sph, sc.n_sph, 0, x, y, z, r, rsq, on, hits, cnt);
-    if (sc.n_cap > 0) cnt = grid_collect_class<CapsuleTest, BT>(g.start[1], g.ids[1], cell, sc.cap, sc.n_cap, 1, x, y, z, r, rsq, on, hits, cnt);
-    if (sc.n_zcap > 0) cnt = grid_collect_class<ZCapsuleTest, BT>(g.start[2], g.ids[2], cell, sc.zcap, sc.n_zcap, 2, x, y, z, r, rsq, on, hits, cnt);
-    if (sc.n_cub > 0) cnt = grid_collect_class<CuboidTest, BT>(g.start[3], g.ids[3], cell, sc.cub, sc.n_cub, 3, x, y, z, r, rsq, on, hits, cnt);
-    if (sc.n_zcub > 0) cnt = grid_collect_class<ZCuboidTest, BT>(g.start[4], g.ids[4], cell, sc.zcub, sc.n_zcub, 4, x, y, z, r, rsq, on, hits, cnt);
+    if (sc.n_sph > 0) cnt = grid_collect_class<SphereTest, BT>(g.cellw[0], g.ids[0], cell, sc.sph, sc.n_sph, 0, x, y, z, r, rsq, on, hits, cnt);
+    if (sc.n_cap > 0) cnt = grid_collect_class<CapsuleTest, BT>(g.cellw[1], g.ids[1], cell, sc.cap, sc.n_cap, 1, x, y, z, r, rsq, on, hits, cnt);
+    if (sc.n_zcap > 0) cnt = grid_collect_class<ZCapsuleTest, BT>(g.cellw[2], g.ids[2], cell, sc.zcap, sc.n_zcap, 2, x, y, z, r, rsq, on, hits, cnt);
+    if (sc.n_cub > 0) cnt = grid_collect_class<CuboidTest, BT>(g.cellw[3], g.ids[3], cell, sc.cub, sc.n_cub, 3, x, y, z, r, rsq, on, hits, cnt);
+    if (sc.n_zcub > 0) cnt = grid_collect_class<ZCuboidTest, BT>(g.cellw[4], g.ids[4], cell, sc.zcub, sc.n_zcub, 4, x, y, z, r, rsq, on, hits, cnt);
     return cnt;
 }
 
-// one fine sphere against the lane's list of obstacles (cnt <= kHitCap entries); any_mode as in grid_should_stop
+// TWO fine spheres against the lane's list of obstacles (`mine` <= kHitCap entries, hmax = the warp's longest list): an obstacle's
+// record is read once for both. acc0 / acc1 collect the raw bits of the test values (sign bit <=> collision).
 template <int BT>
-__device__ __forceinline__ bool hits_scan(const Scene &sc, const float *__restrict__ hits, int cnt, float x, float y, float z, float r, bool on,
-                                          bool any_mode) {
-    const float rsq = r * r;
-    const int mine = on ? cnt : 0;
-    const int hmax = __reduce_max_sync(kFull, mine);
-    int acc = 0;
+__device__ __forceinline__ void hits_scan2(const Scene &sc, const float *__restrict__ hits, int mine, int hmax, float x0, float y0, float z0, float r0,
+                                           float x1, float y1, float z1, float r1, bool any_mode, int &acc0, int &acc1) {
+    const float rsq0 = r0 * r0, rsq1 = r1 * r1;
 #pragma unroll 1
     for (int h = 0; h < hmax; ++h) {
         if (h < mine) {
             const int ent = __float_as_int(hits[h * BT]);
             const int id = ent & 0xffff;
-            float v;
+            float v0, v1;
             switch (ent >> 16) {
-                case 0: v = SphereTest::test(sc.sph + id * SphereTest::kRec, x, y, z, r, rsq); break;
-                case 1: v = CapsuleTest::test(sc.cap + id * CapsuleTest::kRec, x, y, z, r, rsq); break;
-                case 2: v = ZCapsuleTest::test(sc.zcap + id * ZCapsuleTest::kRec, x, y, z, r, rsq); break;
-                case 3: v = CuboidTest::test(sc.cub + id * CuboidTest::kRec, x, y, z, r, rsq); break;
-                default: v = ZCuboidTest::test(sc.zcub + id * ZCuboidTest::kRec, x, y, z, r, rsq); break;
+                case 0: { const float4 *o = sc.sph + id * SphereTest::kRec; v0 = SphereTest::test(o, x0, y0, z0, r0, rsq0); v1 = SphereTest::test(o, x1, y1, z1, r1, rsq1); break; }
+                case 1: { const float4 *o = sc.cap + id * CapsuleTest::kRec; v0 = CapsuleTest::test(o, x0, y0, z0, r0, rsq0); v1 = CapsuleTest::test(o, x1, y1, z1, r1, rsq1); break; }
+                case 2: { const float4 *o = sc.zcap + id * ZCapsuleTest::kRec; v0 = ZCapsuleTest::test(o, x0, y0, z0, r0, rsq0); v1 = ZCapsuleTest::test(o, x1, y1, z1, r1, rsq1); break; }
+                case 3: { const float4 *o = sc.cub + id * CuboidTest::kRec; v0 = CuboidTest::test(o, x0, y0, z0, r0, rsq0); v1 = CuboidTest::test(o, x1, y1, z1, r1, rsq1); break; }
+                default: { const float4 *o = sc.zcub + id * ZCuboidTest::kRec; v0 = ZCuboidTest::test(o, x0, y0, z0, r0, rsq0); v1 = ZCuboidTest::test(o, x1, y1, z1, r1, rsq1); break; }
             }
-            acc |= __float_as_int(v);
+            acc0 |= __float_as_int(v0);
+            acc1 |= __float_as_int(v1);
         }
-        if (any_mode && __any_sync(kFull, acc < 0)) break;
+        if (any_mode && __any_sync(kFull, (acc0 | acc1) < 0)) break;
     }
-    return acc < 0;
 }
 
 // ------------------------------------------------------------------------------------------------ point clouds
@@ -591,8 +584,12 @@ __device__ __forceinline__ bool heightfields_hit(const SceneDesc &sd, float x, f
 // Per-thread scratch in shared memory: slot s of thread t lives at base[s * BT + t] (bank-conflict free). Slots
 // 3l .. 3l+2 hold the world-space centre of link l's bounding sphere, then sin[dim] and cos[dim] of the joint angles.
 // ... followed by kHitCap slots listing the obstacles the current link's bounding sphere touches (see grid_collect_scene).
+// ... followed by kScratchSlots slots: the hit list (kHitCap entries) while a link is tested against the environment, the saved frame
+// of the first link while a self-collision pair is refined.
+constexpr int kScratchSlots = 12;
+static_assert(kHitCap <= kScratchSlots, "the hit list lives in the scratch slots");
 template <class R>
-__host__ __device__ constexpr int lane_slots() { return 3 * R::kLinks + 2 * R::kDim + kHitCap; }
+__host__ __device__ constexpr int lane_slots() { return 3 * R::kLinks + 2 * R::kDim + kScratchSlots; }
 template <class R>
 __host__ __device__ constexpr int trig_slot() { return 3 * R::kLinks; }
 template <class R>
@@ -634,33 +631,30 @@ __device__ __forceinline__ void trig_to_slots(const float (&q)[R::kDim], float *
 #pragma unroll 1
     for (int i = 0; i < 2 * D; ++i) {
         const int j = i < D ? i : i - D;
-        float r = vamp_sin(slots[(T0 + i) * BT]);
-        if (!((revolute_mask<R>() >> j) & 1u)) r = i < D ? 0.0f : 1.0f;  // prismatic joints: the frame code uses q itself
+        const float q_of_slot = slots[(T0 + i) * BT];
+        float r = vamp_sin(q_of_slot);
+        if (!((revolute_mask<R>() >> j) & 1u)) r = i < D ? q_of_slot : 1.0f;  // prismatic joints: the frame code uses q itself (kept in the sin slot)
         slots[(T0 + i) * BT] = r;
     }
 }
 
+// one step of the streamed frame, k - 1 -> k, through the robot's single out-of-line copy of the frame code (R::step); the joint of
+// frame k is joint k - 1, its sin / cos (or, for a prismatic joint, its value) come from the thread's slots
 template <class R, int BT>
-__device__ __forceinline__ void trig_from_slots(const float *__restrict__ slots, float (&sn)[R::kDim], float (&cs)[R::kDim]) {
-#pragma unroll
-    for (int j = 0; j < R::kDim; ++j) {
-        sn[j] = slots[(trig_slot<R>() + j) * BT];
-        cs[j] = slots[(trig_slot<R>() + R::kDim + j) * BT];
-    }
+__device__ __forceinline__ void frame_step(Frame &F, int k, const float *__restrict__ slots) {
+    F = R::step(k, F, slots[(trig_slot<R>() + k - 1) * BT], slots[(trig_slot<R>() + R::kDim + k - 1) * BT]);
 }
 
 // bring the streamed frame F (currently frame `have`, -1 = nothing) to frame k by walking k's chain (arm): either on
 // from `have` when that is an earlier frame of the same chain, or from the world frame at the chain's first joint
 template <class R, int BT>
-__device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const float (&q)[R::kDim], const float *__restrict__ slots) {
+__device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const float *__restrict__ slots) {
     if (have == k) return;
     const int first = R::tables().frame_branch[k];
     int from = have + 1;
     if (have < first || have > k) { frame_identity(F); from = first; }
-    float sn[R::kDim], cs[R::kDim];
-    trig_from_slots<R, BT>(slots, sn, cs);
 #pragma unroll 1
-    for (int j = from; j <= k; ++j) R::advance(j, F, q, sn, cs);
+    for (int j = max(from, 1); j <= k; ++j) frame_step<R, BT>(F, j, slots);
     have = k;
 }
 
@@ -669,7 +663,7 @@ __device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const flo
 // KILL (lane-per-state form only): lanes are grouped into motions by `kill` (the lanes that belong to the same motion as this
 // one); a hit in any of them ends the work of all of them.
 template <class R, int G, bool EDGE, bool KILL, int BT>
-__device__ __forceinline__ bool self_collision(const float (&q)[R::kDim], const float *__restrict__ slots, bool &alive, bool &result, unsigned kill) {
+__device__ __forceinline__ bool self_collision(const float *__restrict__ slots, bool &alive, bool &result, unsigned kill) {
     const typename R::Tables &tb = R::tables();
     Frame F;
     int have = -1;
@@ -688,7 +682,7 @@ __device__ __forceinline__ bool self_collision(const float (&q)[R::kDim], const 
         Frame A;
 #pragma unroll 1
         for (int w = 0; w < 2; ++w) {
-            frame_seek<R, BT>(F, have, tb.link_frame[w == 0 ? la : lb], q, slots);
+            frame_seek<R, BT>(F, have, tb.link_frame[w == 0 ? la : lb], slots);
             if (w == 0) A = F;
         }
         const int ab = tb.link_begin[la], ae = tb.link_begin[la + 1];
@@ -731,17 +725,28 @@ __device__ __forceinline__ bool self_collision(const float (&q)[R::kDim], const 
     return false;
 }
 
-// phase A: trig into the slots, one unrolled base -> tip FK pass that parks the bounding-sphere centres and leaves the tip frame
+// phase A: trig into the slots, then one base -> tip pass over the frames that parks the bounding-sphere centres and leaves the last
+// frame in `tip`. The pass is a ROLLED loop over the same frame stepper the later frame rebuilds use (R::step, out of line), not the generated
+// straight-line R::fk_coarse: the values are the same (same operations in the same order), the instructions are shared -- the hot
+// code of these kernels has to fit the 32 KB instruction cache.
 template <class R, int BT>
 __device__ __forceinline__ void fk_to_slots(const float (&q)[R::kDim], float *__restrict__ slots, Frame &tip) {
+    const typename R::Tables &tb = R::tables();
     trig_to_slots<R, BT>(q, slots);
-    float sn[R::kDim], cs[R::kDim];
-    trig_from_slots<R, BT>(slots, sn, cs);
-    R::fk_coarse(q, sn, cs, tip, [&](int l, float x, float y, float z) {
-        slots[(3 * l + 0) * BT] = x;
-        slots[(3 * l + 1) * BT] = y;
-        slots[(3 * l + 2) * BT] = z;
-    });
+#pragma unroll 1
+    for (int k = 0; k < R::kFrames; ++k) {
+        if (tb.frame_branch[k] == k) frame_identity(tip);  // the world frame itself (k = 0) or the first frame of an arm
+        if (k > 0) frame_step<R, BT>(tip, k, slots);
+#pragma unroll 1
+        for (int l = tb.frame_link_begin[k]; l < tb.frame_link_begin[k + 1]; ++l) {
+            const float4 c = tb.coarse[l];
+            float x, y, z;
+            frame_apply(tip, c.x, c.y, c.z, x, y, z);
+            slots[(3 * l + 0) * BT] = x;
+            slots[(3 * l + 1) * BT] = y;
+            slots[(3 * l + 2) * BT] = z;
+        }
+    }
 }
 
 // Returns true when this lane's state is collision free. `active` lanes take part; idle lanes only follow the
@@ -779,7 +784,7 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
         if (sd.n_pc > 0) chit |= scan_pointclouds<1, kUntilAllHit>(sd, c, alive && !chit);
         const bool need = group_any<G>(chit && alive) && alive;
         if (!__any_sync(kFull, need)) continue;
-        frame_seek<R, BT>(F, have, tb.link_frame[l], q, slots);
+        frame_seek<R, BT>(F, have, tb.link_frame[l], slots);
         const int fb = tb.link_begin[l], fe = tb.link_begin[l + 1];
         bool fhit = false;
 #pragma unroll 1
@@ -814,7 +819,7 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
         if (!EDGE && !__any_sync(kFull, alive)) return false;
     }
     bool result = false;
-    if (self_collision<R, G, EDGE, KILL, BT>(q, slots, alive, result, kill)) return result;
+    if (self_collision<R, G, EDGE, KILL, BT>(slots, alive, result, kill)) return result;
     return alive;
 }
 
@@ -867,88 +872,174 @@ static __device__ __noinline__ bool grid_scan_scene_cold(const GridView *g, cons
     return grid_scan_scene(*g, *scp, x, y, z, r, on, any_mode);
 }
 
-// Candidate-grid variant (sorted scenes with a grid). Phase B is one loop over "sphere tasks" -- a link's bounding sphere,
-// or, while a link is being refined, its next fine sphere -- so that the grid walk exists once in the instruction stream.
+// Candidate-grid variant (sorted scenes with a grid): the whole state check as ONE loop over the robot's task table (RobotTask,
+// robot_common.cuh) -- the forward pass over the frames that parks the bounding-sphere centres, the links against the environment
+// tip -> base (the reference's order: distal links collide first), the allowed self-collision pairs. A task first decides whether it
+// needs its frame at all (a link: does the bounding sphere touch anything -- the candidate-list walk that also remembers WHAT it
+// touches; a pair: do the bounding spheres touch); the streamed frame is then brought to the task's frame at the ONE place this
+// function steps frames; then the fine spheres are tested (a link: two at a time against the remembered obstacles). One copy of the
+// frame code and of every loop: the hot code of these kernels has to fit the 32 KB instruction cache.
 template <class R, int G, bool EDGE, bool KILL, int BT>
 __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
                                  const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill) {
     const typename R::Tables &tb = R::tables();
     bool alive = active;
+    trig_to_slots<R, BT>(q, slots);
     Frame F;
-    fk_to_slots<R, BT>(q, slots, F);
-    int have = R::kFrames - 1;
-    int l = R::kLinks - 1;   // next link whose bounding sphere is to be tested
-    int f = 0, fe = 0;       // fine spheres [f, fe) of the link being refined (f < fe <=> refining)
-    bool need = false, fhit = false;
-    float *hit_list = slots + hit_slot<R>() * BT;  // obstacles the current link's bounding sphere touches
+    int have = -1;  // frame held in F (warp-uniform)
+    float *scratch = slots + hit_slot<R>() * BT;
+    bool need = false;  // lanes taking part in the fine tests of the current link / pair
     int hits = 0;
 #pragma unroll 1
-    for (;;) {
-        const bool fine = f < fe;  // warp-uniform
-        float x, y, z, r;
-        int lvl;
-        bool on;
-        if (!fine) {
-            if (l < 0) break;
-            x = slots[(3 * l + 0) * BT];
-            y = slots[(3 * l + 1) * BT];
-            z = slots[(3 * l + 2) * BT];
-            r = tb.coarse[l].w;
-            lvl = lv.coarse[l];
-            on = alive;
-        } else {
-            const float4 fl = tb.fine[f];
-            frame_apply(F, fl.x, fl.y, fl.z, x, y, z);
-            r = fl.w;
-            lvl = lv.fine[f];
-            on = need && !fhit;
-        }
-        const bool any_mode = EDGE && fine;  // fine hit of an edge: the motion is dead, stop at once
-        bool h;
-        if (!fine) {
+    for (int t = 0; t < R::kTasks; ++t) {
+        const RobotTask tk = tb.tasks[t];
+        const int kind = tk.kind;
+        if (kind == kTaskEnv) {
+            const int l = tk.a;
+            const float x = slots[(3 * l + 0) * BT], y = slots[(3 * l + 1) * BT], z = slots[(3 * l + 2) * BT];
+            const float r = tb.coarse[l].w;
+            const int lvl = lv.coarse[l];
             // bounding sphere: list what it touches (hits > 0 <=> coarse hit); radii beyond the widest grid reach take the ordered scan
+            bool h;
             if (lvl >= 0) {
-                hits = grid_collect_scene<BT>(sd.grid[lvl], sc, x, y, z, r, on, hit_list);
+                hits = grid_collect_scene<BT>(sd.grid[lvl], sc, x, y, z, r, alive, scratch);
                 h = hits > 0;
             } else {
-                h = ordered_scan_one<G>(&sv.sc, x, y, z, r, on, false);
+                h = ordered_scan_one<G>(&sv.sc, x, y, z, r, alive, false);
                 hits = kHitCap + 1;
             }
-        } else if (__any_sync(kFull, on && hits > kHitCap)) {
-            // some lane's list overflowed (or was never made): this fine sphere walks the grid itself, as the bounding sphere did
-            if (lvl >= 0) h = grid_scan_scene_cold(&sv.grid[lvl], &sv.sc, x, y, z, r, on, any_mode);
-            else h = ordered_scan_one<G>(&sv.sc, x, y, z, r, on, any_mode);
-        } else {
-            h = hits_scan<BT>(sc, hit_list, hits, x, y, z, r, on, any_mode);
+            bool other = false;  // touches something that is not in the list (height field, point cloud): tested per fine sphere
+            if (sd.n_hf > 0 && alive && !h) other = heightfields_hit(sd, x, y, z, r);
+            if (sd.n_pc > 0) other |= pointclouds_one(sv.pc, sd.n_pc, x, y, z, r, alive && !h && !other, false);
+            need = group_any<G>((h || other) && alive) && alive;
+            if (!__any_sync(kFull, need)) continue;
+        } else if (kind == kTaskSelfA) {
+            // allowed self-collision pair (collision/validity.hh:13-44): bounding spheres on the stored centres
+            const int la = tk.a, lb = tk.b;
+            const float xs = slots[(3 * la + 0) * BT] - slots[(3 * lb + 0) * BT], ys = slots[(3 * la + 1) * BT] - slots[(3 * lb + 1) * BT],
+                        zs = slots[(3 * la + 2) * BT] - slots[(3 * lb + 2) * BT];
+            const float rs = tb.coarse[la].w + tb.coarse[lb].w;
+            const float d = fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs)));
+            need = group_any<G>((d < 0.0f) && alive) && alive;
+            if (!__any_sync(kFull, need)) { ++t; continue; }  // (skips the pair's second half as well)
         }
-        if (sd.n_hf > 0 && on && !h) h = heightfields_hit(sd, x, y, z, r);
-        if (sd.n_pc > 0) h |= pointclouds_one(sv.pc, sd.n_pc, x, y, z, r, on && !h, any_mode);
-        if (!fine) {
-            need = group_any<G>(h && alive) && alive;
-            if (__any_sync(kFull, need)) {
-                frame_seek<R, BT>(F, have, tb.link_frame[l], q, slots);
-                f = tb.link_begin[l];
-                fe = tb.link_begin[l + 1];
-                fhit = false;
+        // ---- the one place frames are stepped: bring F to the task's frame by walking its chain (arm), either on from the frame held
+        // when that is an earlier frame of the same chain, or from the world frame at the chain's first joint
+        {
+            const int k = tk.frame;
+            if (have != k) {
+                const int first = tb.frame_branch[k];
+                int from = have + 1;
+                if (have < first || have > k) { frame_identity(F); from = first; }
+#pragma unroll 1
+                for (int j = max(from, 1); j <= k; ++j)
+                    F = R::step_inline(j, F, slots[(trig_slot<R>() + j - 1) * BT], slots[(trig_slot<R>() + R::kDim + j - 1) * BT]);
+                have = k;
             }
-            --l;
+        }
+        if (kind == kTaskFk) {
+#pragma unroll 1
+            for (int l = tk.a; l < tk.b; ++l) {
+                const float4 c = tb.coarse[l];
+                float x, y, z;
+                frame_apply(F, c.x, c.y, c.z, x, y, z);
+                slots[(3 * l + 0) * BT] = x;
+                slots[(3 * l + 1) * BT] = y;
+                slots[(3 * l + 2) * BT] = z;
+            }
+        } else if (kind == kTaskEnv) {
+            const int l = tk.a;
+            const int fe = tb.link_begin[l + 1];
+            // a list that overflowed (or was never made): the link's fine spheres walk the grid themselves, as the bounding sphere did
+            const bool walk = __any_sync(kFull, need && hits > kHitCap);
+            const int mine = need ? min(hits, kHitCap) : 0;
+            const int hmax = __reduce_max_sync(kFull, mine);
+            bool fhit = false;
+#pragma unroll 1
+            for (int f = tb.link_begin[l]; f < fe; f += 2) {
+                const float4 fa = tb.fine[f], fb = tb.fine[min(f + 1, fe - 1)];  // (an odd last sphere is tested twice)
+                float x0, y0, z0, x1, y1, z1;
+                frame_apply(F, fa.x, fa.y, fa.z, x0, y0, z0);
+                frame_apply(F, fb.x, fb.y, fb.z, x1, y1, z1);
+                const bool on = need && !fhit;
+                bool hh;
+                if (!walk) {
+                    int a0 = 0, a1 = 0;
+                    hits_scan2<BT>(sc, scratch, on ? mine : 0, hmax, x0, y0, z0, fa.w, x1, y1, z1, fb.w, EDGE, a0, a1);
+                    hh = (a0 | a1) < 0;
+                } else {
+                    const int l0 = lv.fine[f], l1 = lv.fine[min(f + 1, fe - 1)];
+                    hh = l0 >= 0 ? grid_scan_scene_cold(&sv.grid[l0], &sv.sc, x0, y0, z0, fa.w, on, EDGE) : ordered_scan_one<G>(&sv.sc, x0, y0, z0, fa.w, on, EDGE);
+                    const bool on1 = on && !hh;
+                    hh |= l1 >= 0 ? grid_scan_scene_cold(&sv.grid[l1], &sv.sc, x1, y1, z1, fb.w, on1, EDGE) : ordered_scan_one<G>(&sv.sc, x1, y1, z1, fb.w, on1, EDGE);
+                }
+                if (sd.n_hf > 0 && on && !hh) hh = heightfields_hit(sd, x0, y0, z0, fa.w) || heightfields_hit(sd, x1, y1, z1, fb.w);
+                if (sd.n_pc > 0) {
+                    hh |= pointclouds_one(sv.pc, sd.n_pc, x0, y0, z0, fa.w, on && !hh, EDGE);
+                    hh |= pointclouds_one(sv.pc, sd.n_pc, x1, y1, z1, fb.w, on && !hh, EDGE);
+                }
+                fhit |= hh && on;
+                if (EDGE) {
+                    if (__any_sync(kFull, fhit)) return !fhit;  // a fine hit of an edge: the motion is dead, stop at once
+                } else {
+                    if (KILL) fhit = (__ballot_sync(kFull, fhit) & kill) != 0u;
+                    if (__all_sync(kFull, fhit || !need)) break;
+                }
+            }
+            if (fhit) alive = false;
+            if (!EDGE && !__any_sync(kFull, alive)) return false;
+        } else if (kind == kTaskSelfA) {
+            // the frame of the pair's first link waits in the scratch slots while F moves on to the second link's frame
+#pragma unroll
+            for (int i = 0; i < 9; ++i) scratch[i * BT] = F.r[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) scratch[(9 + i) * BT] = F.t[i];
         } else {
-            fhit |= h && on;
-            ++f;
-            if (EDGE) {
-                if (__any_sync(kFull, fhit)) return !fhit;
-            } else {
-                if (KILL) fhit = (__ballot_sync(kFull, fhit) & kill) != 0u;
-                if (__all_sync(kFull, fhit || !need)) f = fe;
+            // Fine spheres of the first link (the one with fewer of them) one at a time. Each is first tested against the second
+            // link's bounding sphere, inflated by 0.1 mm: the bounding sphere contains every fine sphere of that link (to 1e-8 m,
+            // checked when the tables are generated), so a fine-fine contact implies this test is negative and skipping on a
+            // non-negative value cannot change a decision. Only the few spheres that pass are run against the other link's fine spheres.
+            const int la = tk.a, lb = tk.b;
+            Frame A;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) A.r[i] = scratch[i * BT];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) A.t[i] = scratch[(9 + i) * BT];
+            const float bx = slots[(3 * lb + 0) * BT], by = slots[(3 * lb + 1) * BT], bz = slots[(3 * lb + 2) * BT];
+            const float rb = tb.coarse[lb].w;
+            const int ae = tb.link_begin[la + 1], bb = tb.link_begin[lb], be = tb.link_begin[lb + 1];
+            bool fhit = false;
+#pragma unroll 1
+            for (int i = tb.link_begin[la]; i < ae; ++i) {
+                const float4 al = tb.fine[i];
+                float qx, qy, qz;
+                frame_apply(A, al.x, al.y, al.z, qx, qy, qz);
+                const float xs0 = qx - bx, ys0 = qy - by, zs0 = qz - bz;
+                const float rs0 = al.w + rb + 1.0e-4f;
+                const bool cand = (fmaf(-rs0, rs0, fmaf(zs0, zs0, fmaf(ys0, ys0, xs0 * xs0))) < 0.0f) && need && !fhit;
+                if (!__any_sync(kFull, cand)) continue;
+                int acc = 0;
+#pragma unroll 2
+                for (int j = bb; j < be; ++j) {
+                    const float4 fl = tb.fine[j];
+                    float px, py, pz;
+                    frame_apply(F, fl.x, fl.y, fl.z, px, py, pz);
+                    const float xs2 = qx - px, ys2 = qy - py, zs2 = qz - pz;
+                    const float rs2 = al.w + fl.w;
+                    acc |= __float_as_int(fmaf(-rs2, rs2, fmaf(zs2, zs2, fmaf(ys2, ys2, xs2 * xs2))));
+                }
+                fhit |= (acc < 0) && cand;
+                if (EDGE) {
+                    if (__any_sync(kFull, fhit)) return !fhit;
+                } else {
+                    if (KILL) fhit = (__ballot_sync(kFull, fhit) & kill) != 0u;
+                    if (__all_sync(kFull, fhit || !need)) break;
+                }
             }
-            if (f >= fe) {
-                if (fhit) alive = false;
-                if (!EDGE && !__any_sync(kFull, alive)) return false;
-            }
+            if (fhit) alive = false;
+            if (!EDGE && !__any_sync(kFull, alive)) return false;
         }
     }
-    bool result = false;
-    if (self_collision<R, G, EDGE, KILL, BT>(q, slots, alive, result, kill)) return result;
     return alive;
 }
 
@@ -982,16 +1073,13 @@ __device__ __forceinline__ bool env_sphere_hit(const SharedViews &sv, float x, f
 }
 
 template <class R, int G, bool MASKED, bool GRID, int BT>
-__device__ __noinline__ bool attachment_hit(const float *__restrict__ qv, const float *__restrict__ slots, const SharedViews *__restrict__ svp, bool alive) {
+__device__ __noinline__ bool attachment_hit(const float *__restrict__ slots, const SharedViews *__restrict__ svp, bool alive) {
     const SharedViews &sv = *svp;
     const typename R::Tables &tb = R::tables();
-    float q[R::kDim];
-#pragma unroll
-    for (int j = 0; j < R::kDim; ++j) q[j] = qv[j];
     // N = eefk(q) * tf: the end-effector frame is a constant transform away from one of the moving frames
     Frame F, N;
     int have = -1;
-    frame_seek<R, BT>(F, have, R::kEeFrame, q, slots);
+    frame_seek<R, BT>(F, have, R::kEeFrame, slots);
     {
         Frame E;
         R::ee_pose(F, E);
@@ -1033,7 +1121,7 @@ __device__ __noinline__ bool attachment_hit(const float *__restrict__ qv, const 
         }
         const bool need = group_any<G>(acc < 0 && alive && !hit) && alive && !hit;
         if (!__any_sync(kFull, need)) continue;
-        frame_seek<R, BT>(F, have, tb.link_frame[l], q, slots);
+        frame_seek<R, BT>(F, have, tb.link_frame[l], slots);
         int facc = 0;
         for (int f = tb.link_begin[l]; f < tb.link_begin[l + 1]; ++f) {
             const float4 fl = tb.fine[f];
@@ -1062,10 +1150,7 @@ __device__ __forceinline__ bool check_state(const float (&q)[R::kDim], const Sce
         if (EDGE && __any_sync(kFull, active && !good)) return good;
         const bool alive = active && good;
         if (__any_sync(kFull, alive)) {
-            float qq[R::kDim];  // a copy the out-of-line call may take the address of (q itself stays in registers)
-#pragma unroll
-            for (int j = 0; j < R::kDim; ++j) qq[j] = q[j];
-            bool ahit = attachment_hit<R, G, MASKED, GRID, BT>(qq, slots, &sv, alive);
+            bool ahit = attachment_hit<R, G, MASKED, GRID, BT>(slots, &sv, alive);
             if (KILL) ahit = (__ballot_sync(kFull, ahit) & kill) != 0u;
             good = good && !ahit;
         }

@@ -174,6 +174,16 @@ def gen_cuda(model: dict) -> str:
 
     lo = [float(np.float32(a)) for a in model["s_a"]]
     hi = [float(np.float32(np.float32(a) + np.float32(m))) for a, m in zip(model["s_a"], model["s_m"])]
+    # The state check as a task list, so that ONE loop (one copy of the frame code) runs all of it: the forward pass over the frames
+    # (bounding-sphere centres), the links against the environment tip -> base (the reference's order), the self-collision pairs
+    # (first the frame of the link whose fine spheres run in the outer loop -- the one with fewer spheres --, then the other's).
+    T_FK, T_ENV, T_SELF_A, T_SELF_B = 0, 1, 2, 3
+    tasks = [(T_FK, k, frame_link_begin[k], frame_link_begin[k + 1]) for k in range(nfr)]
+    tasks += [(T_ENV, link_rows[l]["frame"], l, 0) for l in range(len(link_rows) - 1, -1, -1)]
+    for a, b in pairs:
+        na, nb = link_rows[a]["end"] - link_rows[a]["begin"], link_rows[b]["end"] - link_rows[b]["begin"]
+        o, i = (a, b) if na <= nb else (b, a)
+        tasks += [(T_SELF_A, link_rows[o]["frame"], o, i), (T_SELF_B, link_rows[i]["frame"], o, i)]
     att = model["attachment"]
     att_links = sorted((new_index[a] for a in att["links"]), key=lambda i: (link_rows[i]["frame"], i))
 
@@ -199,6 +209,7 @@ def gen_cuda(model: dict) -> str:
     w(f"    short link_frame[{nl}];             // frame link l lives on")
     w(f"    short frame_branch[{nfr}];          // first frame of the chain (arm) frame k belongs to; its parent is the world frame")
     w(f"    short att_links[{len(att_links)}];  // links tested against an attachment (Robot::fkcc_attach), in frame order")
+    w(f"    RobotTask tasks[{len(tasks)}];       // the state check as one list of steps (see RobotTask in robot_common.cuh)")
     w("};")
     w("")
     w(f"__constant__ {cname}Tables k{cname}Tables = {{")
@@ -215,6 +226,7 @@ def gen_cuda(model: dict) -> str:
     w("    {" + ", ".join(str(r["frame"]) for r in link_rows) + "},")
     w("    {" + ", ".join(str(v) for v in frame_branch) + "},")
     w("    {" + ", ".join(str(v) for v in att_links) + "},")
+    w("    {" + ", ".join("{%d, %d, %d, %d}" % t for t in tasks) + "},")
     w("};")
     w("")
     w(f"struct {cname} {{")
@@ -226,6 +238,7 @@ def gen_cuda(model: dict) -> str:
     w(f"    static constexpr int kResolution = {model['resolution']};")
     w(f"    static constexpr int kSlots = {max(1, len(a_frames))};   // saved frames needed by the self-collision stage")
     w(f"    static constexpr int kRobotId = {ROBOT_IDS[name]};")
+    w(f"    static constexpr int kTasks = {len(tasks)};")
     w(f"    static constexpr int kAttLinks = {len(att_links)};   // links an attachment is tested against")
     w(f"    static constexpr int kEeFrame = {att['ee_frame']};   // moving frame the end effector ({cname}::eefk) is rigidly attached to")
     w("    static constexpr float kLo[kDim] = {" + ", ".join(f32(v) for v in lo) + "};")
@@ -256,6 +269,13 @@ def gen_cuda(model: dict) -> str:
     w("    __device__ static __forceinline__ void ee_pose(const Frame &P, Frame &E);")
     w("    // step the streaming frame from k-1 to k (k >= 1); uniform switch, static joint indices")
     w("    __device__ static __forceinline__ void advance(int k, Frame &F, const float (&q)[kDim], const float (&sn)[kDim], const float (&cs)[kDim]);")
+    w("    // The same step OUT OF LINE, frame in and out by value (registers): the one copy of the frame code every caller shares, so that")
+    w("    // the kernels' hot code fits the instruction cache. s, c = the joint's sin / cos; a prismatic joint passes its value q as s.")
+    w("    // (a template only for its linkage: the header is included by several translation units)")
+    w("    template <int = 0>")
+    w("    __device__ static __noinline__ Frame step(int k, Frame P, float s, float c);")
+    w("    // ... and inline, for the one place a kernel's task loop steps frames (validate.cuh: check_state_grid)")
+    w("    __device__ static __forceinline__ Frame step_inline(int k, const Frame &P, float s, float c);")
     w("};")
     w("")
     for fr in frames[1:]:
@@ -321,6 +341,19 @@ def gen_cuda(model: dict) -> str:
     w("        default: break;")
     w("    }")
     w("}")
+    w("")
+    w(f"__device__ __forceinline__ Frame {cname}::step_inline(int k, const Frame &P, float s, float c) {{")
+    w("    Frame F = P;")
+    w("    switch (k) {")
+    for fr in frames[1:]:
+        w(f"        case {fr['id']}: frame<{fr['id']}>(P, s, s, c, F); break;")
+    w("        default: break;")
+    w("    }")
+    w("    return F;")
+    w("}")
+    w("")
+    w("template <int>")
+    w(f"__device__ __noinline__ Frame {cname}::step(int k, Frame P, float s, float c) {{ return step_inline(k, P, s, c); }}")
     w("")
     w("}  // namespace b200mp")
     return "\n".join(out) + "\n", link_rows, fine_sorted, pairs
