@@ -872,6 +872,40 @@ static __device__ __noinline__ bool grid_scan_scene_cold(const GridView *g, cons
     return grid_scan_scene(*g, *scp, x, y, z, r, on, any_mode);
 }
 
+// Everything rare about a link's bounding sphere, out of line: height fields and point clouds (obstacles that are not in the hit list)
+static __device__ __noinline__ bool coarse_other_cold(const SharedViews *svp, float x, float y, float z, float r, bool on) {
+    const SharedViews &sv = *svp;
+    bool other = false;
+    if (sv.n_hf > 0 && on) other = heightfields_hit(sv.hf, sv.n_hf, x, y, z, r);
+    if (sv.n_pc > 0) other |= pointclouds_one(sv.pc, sv.n_pc, x, y, z, r, on && !other, false);
+    return other;
+}
+
+// Everything rare about a pair of fine spheres, out of line: lists that overflowed (the spheres walk the grid themselves, as the
+// bounding sphere did; lvl < 0: radius beyond the widest grid reach -> ordered scan), height fields, point clouds.
+template <int G, int BT>
+__device__ __noinline__ bool fine_pair_cold(const Scene *scp, const SharedViews *svp, const float *__restrict__ hit_list, int mine, int hmax, bool walk,
+                                            int l0, int l1, float x0, float y0, float z0, float r0, float x1, float y1, float z1, float r1, bool on,
+                                            bool any_mode) {
+    const SharedViews &sv = *svp;
+    bool hh;
+    if (!walk) {
+        int a0 = 0, a1 = 0;
+        hits_scan2<BT>(*scp, hit_list, on ? mine : 0, hmax, x0, y0, z0, r0, x1, y1, z1, r1, any_mode, a0, a1);
+        hh = (a0 | a1) < 0;
+    } else {
+        hh = l0 >= 0 ? grid_scan_scene(sv.grid[l0], sv.sc, x0, y0, z0, r0, on, any_mode) : ordered_scan_one<G>(&sv.sc, x0, y0, z0, r0, on, any_mode);
+        const bool on1 = on && !hh;
+        hh |= l1 >= 0 ? grid_scan_scene(sv.grid[l1], sv.sc, x1, y1, z1, r1, on1, any_mode) : ordered_scan_one<G>(&sv.sc, x1, y1, z1, r1, on1, any_mode);
+    }
+    if (sv.n_hf > 0 && on && !hh) hh = heightfields_hit(sv.hf, sv.n_hf, x0, y0, z0, r0) || heightfields_hit(sv.hf, sv.n_hf, x1, y1, z1, r1);
+    if (sv.n_pc > 0) {
+        hh |= pointclouds_one(sv.pc, sv.n_pc, x0, y0, z0, r0, on && !hh, any_mode);
+        hh |= pointclouds_one(sv.pc, sv.n_pc, x1, y1, z1, r1, on && !hh, any_mode);
+    }
+    return hh;
+}
+
 // Candidate-grid variant (sorted scenes with a grid): the whole state check as ONE loop over the robot's task table (RobotTask,
 // robot_common.cuh) -- the forward pass over the frames that parks the bounding-sphere centres, the links against the environment
 // tip -> base (the reference's order: distal links collide first), the allowed self-collision pairs. A task first decides whether it
@@ -908,10 +942,9 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
                 h = ordered_scan_one<G>(&sv.sc, x, y, z, r, alive, false);
                 hits = kHitCap + 1;
             }
-            bool other = false;  // touches something that is not in the list (height field, point cloud): tested per fine sphere
-            if (sd.n_hf > 0 && alive && !h) other = heightfields_hit(sd, x, y, z, r);
-            if (sd.n_pc > 0) other |= pointclouds_one(sv.pc, sd.n_pc, x, y, z, r, alive && !h && !other, false);
-            need = group_any<G>((h || other) && alive) && alive;
+            // touches something that is not in the list (height field, point cloud)? Those are tested per fine sphere
+            if (sd.n_hf > 0 || sd.n_pc > 0) h |= coarse_other_cold(&sv, x, y, z, r, alive && !h);
+            need = group_any<G>(h && alive) && alive;
             if (!__any_sync(kFull, need)) continue;
         } else if (kind == kTaskSelfA) {
             // allowed self-collision pair (collision/validity.hh:13-44): bounding spheres on the stored centres
@@ -952,6 +985,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
             const int fe = tb.link_begin[l + 1];
             // a list that overflowed (or was never made): the link's fine spheres walk the grid themselves, as the bounding sphere did
             const bool walk = __any_sync(kFull, need && hits > kHitCap);
+            const bool rare = walk || sd.n_hf > 0 || sd.n_pc > 0;  // (warp-uniform)
             const int mine = need ? min(hits, kHitCap) : 0;
             const int hmax = __reduce_max_sync(kFull, mine);
             bool fhit = false;
@@ -963,20 +997,13 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
                 frame_apply(F, fb.x, fb.y, fb.z, x1, y1, z1);
                 const bool on = need && !fhit;
                 bool hh;
-                if (!walk) {
+                if (!rare) {
                     int a0 = 0, a1 = 0;
                     hits_scan2<BT>(sc, scratch, on ? mine : 0, hmax, x0, y0, z0, fa.w, x1, y1, z1, fb.w, EDGE, a0, a1);
                     hh = (a0 | a1) < 0;
                 } else {
-                    const int l0 = lv.fine[f], l1 = lv.fine[min(f + 1, fe - 1)];
-                    hh = l0 >= 0 ? grid_scan_scene_cold(&sv.grid[l0], &sv.sc, x0, y0, z0, fa.w, on, EDGE) : ordered_scan_one<G>(&sv.sc, x0, y0, z0, fa.w, on, EDGE);
-                    const bool on1 = on && !hh;
-                    hh |= l1 >= 0 ? grid_scan_scene_cold(&sv.grid[l1], &sv.sc, x1, y1, z1, fb.w, on1, EDGE) : ordered_scan_one<G>(&sv.sc, x1, y1, z1, fb.w, on1, EDGE);
-                }
-                if (sd.n_hf > 0 && on && !hh) hh = heightfields_hit(sd, x0, y0, z0, fa.w) || heightfields_hit(sd, x1, y1, z1, fb.w);
-                if (sd.n_pc > 0) {
-                    hh |= pointclouds_one(sv.pc, sd.n_pc, x0, y0, z0, fa.w, on && !hh, EDGE);
-                    hh |= pointclouds_one(sv.pc, sd.n_pc, x1, y1, z1, fb.w, on && !hh, EDGE);
+                    hh = fine_pair_cold<G, BT>(&sv.sc, &sv, scratch, mine, hmax, walk, lv.fine[f], lv.fine[min(f + 1, fe - 1)], x0, y0, z0, fa.w, x1, y1, z1,
+                                               fb.w, on, EDGE);
                 }
                 fhit |= hh && on;
                 if (EDGE) {
