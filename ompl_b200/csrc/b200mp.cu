@@ -196,8 +196,8 @@ int build_grids(b200mp_env *e, SceneDesc *d) {
         const int c = static_cast<int>(std::floor((v - lo[k]) * inv_h));
         return std::min(std::max(c, 0), n[k] - 1);
     };
-    // layout of the device buffer: for level, class: one word per cell ((first entry << 8) | entries), then the entries (u16 record
-    // indices); 16-byte aligned pieces
+    // layout of the device buffer: for level, class: one 8-byte record per cell (count, where the list goes on, its first two
+    // entries), then the further entries of the longer lists (u16 record indices); 16-byte aligned pieces
     struct Piece { size_t start_off, ids_off; std::vector<unsigned> start; std::vector<unsigned short> ids; };
     std::vector<Piece> pieces(kGridLevels * kShapeClasses);
     size_t bytes = 0;
@@ -244,22 +244,34 @@ int build_grids(b200mp_env *e, SceneDesc *d) {
                     }
                 }
             }
-            // counts -> offsets; p.start becomes the per-cell word (first entry << 8) | entries
+            // counts -> the per-cell record: x = (position in `ids` of the list's THIRD entry << 8) | entries, y = the first two entries
+            // (the padding record's index where the list is shorter); `ids` holds entries 2, 3, ... of every list
             {
+                const unsigned pad = static_cast<unsigned>(cls.size());
                 std::vector<unsigned> off(cells + 1, 0u);
                 for (size_t c = 0; c < cells; ++c) {
                     if (p.start[c + 1] > 255u) return B200MP_OK;  // a cell this crowded: keep the ordered scan for the whole scene
-                    off[c + 1] = off[c] + p.start[c + 1];
+                    off[c + 1] = off[c] + (p.start[c + 1] > 2u ? p.start[c + 1] - 2u : 0u);
                 }
                 if (off[cells] >= (1u << 24)) return B200MP_OK;
-                p.ids.resize(off[cells]);
-                std::vector<unsigned> fill(off.begin(), off.end() - 1);
-                for (const auto &hc : hits) p.ids[fill[hc.first]++] = hc.second;  // (obstacles were visited in ascending order: so is every cell's list)
-                for (size_t c = 0; c < cells; ++c) p.start[c] = (off[c] << 8) | (off[c + 1] - off[c]);
-                p.start.resize(cells);
+                std::vector<unsigned> cnt(cells);
+                for (size_t c = 0; c < cells; ++c) cnt[c] = p.start[c + 1];
+                p.ids.assign(off[cells], 0);
+                p.start.assign(cells * 2, 0u);
+                for (size_t c = 0; c < cells; ++c) {
+                    p.start[2 * c] = (off[c] << 8) | cnt[c];  // (the device reads entry i >= 2 from ids[(x >> 8) + i - 2])
+                    p.start[2 * c + 1] = pad * 0x10001u;
+                }
+                std::vector<unsigned> seen(cells, 0u);
+                for (const auto &hc : hits) {  // (obstacles were visited in ascending order: so is every cell's list)
+                    const unsigned k = seen[hc.first]++;
+                    if (k == 0) p.start[2 * hc.first + 1] = (p.start[2 * hc.first + 1] & 0xffff0000u) | hc.second;
+                    else if (k == 1) p.start[2 * hc.first + 1] = (p.start[2 * hc.first + 1] & 0x0000ffffu) | (static_cast<unsigned>(hc.second) << 16);
+                    else p.ids[off[hc.first] + k - 2] = hc.second;
+                }
             }
             p.start_off = bytes;
-            bytes += (cells * sizeof(unsigned) + 15) / 16 * 16;
+            bytes += (cells * 2 * sizeof(unsigned) + 15) / 16 * 16;
             p.ids_off = bytes;
             bytes += (p.ids.size() * sizeof(unsigned short) + 15) / 16 * 16 + 16;
         }
@@ -281,7 +293,7 @@ int build_grids(b200mp_env *e, SceneDesc *d) {
         g.reach = reach[l];
         for (int t = 0; t < kShapeClasses; ++t) {
             const Piece &p = pieces[l * kShapeClasses + t];
-            g.cellw[t] = p.start.empty() ? nullptr : reinterpret_cast<const unsigned *>(base + p.start_off);
+            g.cellw[t] = p.start.empty() ? nullptr : reinterpret_cast<const uint2 *>(base + p.start_off);
             g.ids[t] = p.start.empty() ? nullptr : reinterpret_cast<const unsigned short *>(base + p.ids_off);
         }
     }

@@ -58,8 +58,10 @@ struct GridView {
     float ox, oy, oz, inv_h;
     int nx, ny, nz;
     float reach;
-    // per cell one word (first list entry << 8) | entries; entries = u16 record indices into the staged class arrays
-    const unsigned *cellw[kShapeClasses];
+    // per cell and class 8 bytes: x = (where the list goes on << 8) | entries, y = the first two entries (u16 record indices into the
+    // staged class arrays; the class's first padding record where the list is shorter) -- most lists end there, so one load answers
+    // a cell; entries 2, 3, ... of longer lists follow in `ids` from position x >> 8
+    const uint2 *cellw[kShapeClasses];
     const unsigned short *ids[kShapeClasses];
 };
 
@@ -339,16 +341,19 @@ __device__ __forceinline__ bool grid_should_stop(bool hit, bool on, bool any_mod
 // One shape class: every lane walks the candidate list of its own cell; record `n` (the first padding record) stands in
 // once a lane's list is exhausted, so the loop body needs no predication.
 template <class Test>
-__device__ __forceinline__ int grid_scan_class(const unsigned *__restrict__ cellw, const unsigned short *__restrict__ ids, int cell,
+__device__ __forceinline__ int grid_scan_class(const uint2 *__restrict__ cellw, const unsigned short *__restrict__ ids, int cell,
                                                const float4 *__restrict__ obs, int n, float x, float y, float z, float r, float rsq,
                                                bool on, bool any_mode, int acc) {
-    const unsigned w = on ? __ldg(cellw + cell) : 0u;
-    const unsigned cnt = w & 255u, b = w >> 8;
+    const uint2 w = on ? __ldg(cellw + cell) : make_uint2(0u, static_cast<unsigned>(n) * 0x10001u);
+    const unsigned cnt = w.x & 255u, b = w.x >> 8;  // (entry i >= 2 of the list sits at ids[b + i - 2])
     const unsigned wmax = __reduce_max_sync(kFull, cnt);
 #pragma unroll 1
     for (unsigned i = 0; i < wmax; i += 2) {
-        const int id0 = (i < cnt) ? static_cast<int>(__ldg(ids + b + i)) : n;
-        const int id1 = (i + 1 < cnt) ? static_cast<int>(__ldg(ids + b + i + 1)) : n;
+        int id0 = static_cast<int>(w.y & 0xffffu), id1 = static_cast<int>(w.y >> 16);
+        if (i > 0) {
+            id0 = (i < cnt) ? static_cast<int>(__ldg(ids + (b + i - 2u))) : n;
+            id1 = (i + 1 < cnt) ? static_cast<int>(__ldg(ids + (b + i - 1u))) : n;
+        }
         acc |= __float_as_int(Test::test(obs + id0 * Test::kRec, x, y, z, r, rsq));
         acc |= __float_as_int(Test::test(obs + id1 * Test::kRec, x, y, z, r, rsq));
         if ((i & 6u) == 6u && grid_should_stop(acc < 0, on, any_mode)) break;
@@ -391,16 +396,13 @@ constexpr float kHitMargin = 1.0e-4f;
 constexpr int kHitCap = 8;  // list entries per lane
 
 template <class Test, int BT>
-__device__ __forceinline__ int grid_collect_class(const unsigned *__restrict__ cellw, const unsigned short *__restrict__ ids, int cell,
-                                                  const float4 *__restrict__ obs, int n, int cls, float x, float y, float z, float r, float rsq,
-                                                  bool on, float *__restrict__ hits, int cnt) {
-    const unsigned w = on ? __ldg(cellw + cell) : 0u;
-    const unsigned c = w & 255u, b = w >> 8;
+__device__ __forceinline__ int grid_collect_class(uint2 w, const unsigned short *__restrict__ ids, const float4 *__restrict__ obs, int n, int cls,
+                                                  float x, float y, float z, float r, float rsq, float *__restrict__ hits, int cnt) {
+    const unsigned c = w.x & 255u, b = w.x >> 8;  // (entry i >= 2 of the list sits at ids[b + i - 2])
     const unsigned wmax = __reduce_max_sync(kFull, c);
+    int id0 = static_cast<int>(w.y & 0xffffu), id1 = static_cast<int>(w.y >> 16);  // the first two candidates came with the cell word
 #pragma unroll 1
     for (unsigned i = 0; i < wmax; i += 2) {
-        const int id0 = (i < c) ? static_cast<int>(__ldg(ids + b + i)) : n;
-        const int id1 = (i + 1 < c) ? static_cast<int>(__ldg(ids + b + i + 1)) : n;
         const float v0 = Test::test(obs + id0 * Test::kRec, x, y, z, r, rsq);
         const float v1 = Test::test(obs + id1 * Test::kRec, x, y, z, r, rsq);
         if (v0 < 0.0f) {  // (record n, the far-away stand-in of exhausted lists, never hits)
@@ -411,6 +413,8 @@ __device__ __forceinline__ int grid_collect_class(const unsigned *__restrict__ c
             if (cnt < kHitCap) hits[cnt * BT] = __int_as_float((cls << 16) | id1);
             cnt = min(cnt + 1, kHitCap + 1);
         }
+        id0 = (i + 2 < c) ? static_cast<int>(__ldg(ids + (b + i))) : n;
+        id1 = (i + 3 < c) ? static_cast<int>(__ldg(ids + (b + i + 1u))) : n;
     }
     return cnt;
 }
@@ -421,12 +425,20 @@ __device__ __forceinline__ int grid_collect_scene(const GridView &g, const Scene
     const int cell = grid_cell(g, x, y, z);
     r += kHitMargin;
     const float rsq = r * r;
+    // the cell words of every class first (independent loads in flight together), then class by class
+    uint2 w[kShapeClasses];
+    const int ns[kShapeClasses] = {sc.n_sph, sc.n_cap, sc.n_zcap, sc.n_cub, sc.n_zcub};
+#pragma unroll
+    for (int c = 0; c < kShapeClasses; ++c) {
+        w[c] = make_uint2(0u, static_cast<unsigned>(ns[c]) * 0x10001u);
+        if (ns[c] > 0 && on) w[c] = __ldg(g.cellw[c] + cell);
+    }
     int cnt = 0;
-    if (sc.n_sph > 0) cnt = grid_collect_class<SphereTest, BT>(g.cellw[0], g.ids[0], cell, sc.sph, sc.n_sph, 0, x, y, z, r, rsq, on, hits, cnt);
-    if (sc.n_cap > 0) cnt = grid_collect_class<CapsuleTest, BT>(g.cellw[1], g.ids[1], cell, sc.cap, sc.n_cap, 1, x, y, z, r, rsq, on, hits, cnt);
-    if (sc.n_zcap > 0) cnt = grid_collect_class<ZCapsuleTest, BT>(g.cellw[2], g.ids[2], cell, sc.zcap, sc.n_zcap, 2, x, y, z, r, rsq, on, hits, cnt);
-    if (sc.n_cub > 0) cnt = grid_collect_class<CuboidTest, BT>(g.cellw[3], g.ids[3], cell, sc.cub, sc.n_cub, 3, x, y, z, r, rsq, on, hits, cnt);
-    if (sc.n_zcub > 0) cnt = grid_collect_class<ZCuboidTest, BT>(g.cellw[4], g.ids[4], cell, sc.zcub, sc.n_zcub, 4, x, y, z, r, rsq, on, hits, cnt);
+    if (sc.n_sph > 0) cnt = grid_collect_class<SphereTest, BT>(w[0], g.ids[0], sc.sph, sc.n_sph, 0, x, y, z, r, rsq, hits, cnt);
+    if (sc.n_cap > 0) cnt = grid_collect_class<CapsuleTest, BT>(w[1], g.ids[1], sc.cap, sc.n_cap, 1, x, y, z, r, rsq, hits, cnt);
+    if (sc.n_zcap > 0) cnt = grid_collect_class<ZCapsuleTest, BT>(w[2], g.ids[2], sc.zcap, sc.n_zcap, 2, x, y, z, r, rsq, hits, cnt);
+    if (sc.n_cub > 0) cnt = grid_collect_class<CuboidTest, BT>(w[3], g.ids[3], sc.cub, sc.n_cub, 3, x, y, z, r, rsq, hits, cnt);
+    if (sc.n_zcub > 0) cnt = grid_collect_class<ZCuboidTest, BT>(w[4], g.ids[4], sc.zcub, sc.n_zcub, 4, x, y, z, r, rsq, hits, cnt);
     return cnt;
 }
 
@@ -1345,10 +1357,19 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
     const int lane = threadIdx.x & 31;
     const int group = lane >> 3;
     const float pct = static_cast<float>((lane & 7) + 1) / 8.0f;
+    // the short buckets take their passes four at a time from the queue (one atomic round trip per four passes; passes still run in
+    // increasing order inside a warp); the first look, whose sample / verdict logic counts single passes, one at a time
+    constexpr unsigned kTake = FIRST ? 1u : 4u;
+    unsigned long long next = 0;
+    unsigned left = 0;
     for (;;) {
-        unsigned long long p64 = 0;
-        if (lane == 0) p64 = atomicAdd(FIRST ? &plan->next_first : &plan->next_pass, 1ull);
-        p64 = __shfl_sync(kFull, p64, 0);
+        if (left == 0u) {
+            if (lane == 0) next = atomicAdd(FIRST ? &plan->next_first : &plan->next_pass, static_cast<unsigned long long>(kTake));
+            next = __shfl_sync(kFull, next, 0);
+            left = kTake;
+        }
+        const unsigned long long p64 = next++;
+        --left;
         if (p64 >= total) break;
         const unsigned p = static_cast<unsigned>(p64);
         // First look at the LONG motions (the passes after the short buckets): rake 0 -- eight states spread over the whole motion -- of
