@@ -1034,36 +1034,44 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
 #pragma unroll
             for (int i = 0; i < 3; ++i) scratch[(9 + i) * BT] = F.t[i];
         } else {
-            // Fine spheres of the first link (the one with fewer of them) one at a time. Each is first tested against the second
-            // link's bounding sphere, inflated by 0.1 mm: the bounding sphere contains every fine sphere of that link (to 1e-8 m,
-            // checked when the tables are generated), so a fine-fine contact implies this test is negative and skipping on a
-            // non-negative value cannot change a decision. Only the few spheres that pass are run against the other link's fine spheres.
+            // The pair's fine spheres, in the SECOND link's frame: with Rel = F^-1 * A the first link's spheres (the link with fewer of
+            // them; outer loop) are carried into that frame once, and the second link's spheres are then the table's frame-local
+            // constants -- a rigid transform keeps distances (to rounding, ~1e-7 m; the reference measures the same distances in the
+            // world frame). Each outer sphere is first tested against the second link's bounding sphere, inflated by 0.1 mm: the
+            // bounding sphere contains every fine sphere of that link (to 1e-8 m, checked when the tables are generated), so a fine-fine
+            // contact implies this test is negative and skipping on a non-negative value cannot change a decision.
             const int la = tk.a, lb = tk.b;
-            Frame A;
+            Frame Rel;
+            {
+                Frame A;
 #pragma unroll
-            for (int i = 0; i < 9; ++i) A.r[i] = scratch[i * BT];
+                for (int i = 0; i < 9; ++i) A.r[i] = scratch[i * BT];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) A.t[i] = scratch[(9 + i) * BT];
-            const float bx = slots[(3 * lb + 0) * BT], by = slots[(3 * lb + 1) * BT], bz = slots[(3 * lb + 2) * BT];
-            const float rb = tb.coarse[lb].w;
+                for (int i = 0; i < 3; ++i) A.t[i] = scratch[(9 + i) * BT] - F.t[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) Rel.r[3 * i + j] = fmaf(F.r[6 + i], A.r[6 + j], fmaf(F.r[3 + i], A.r[3 + j], F.r[i] * A.r[j]));
+                    Rel.t[i] = fmaf(F.r[6 + i], A.t[2], fmaf(F.r[3 + i], A.t[1], F.r[i] * A.t[0]));
+                }
+            }
+            const float4 cb = tb.coarse[lb];
             const int ae = tb.link_begin[la + 1], bb = tb.link_begin[lb], be = tb.link_begin[lb + 1];
             bool fhit = false;
 #pragma unroll 1
             for (int i = tb.link_begin[la]; i < ae; ++i) {
                 const float4 al = tb.fine[i];
                 float qx, qy, qz;
-                frame_apply(A, al.x, al.y, al.z, qx, qy, qz);
-                const float xs0 = qx - bx, ys0 = qy - by, zs0 = qz - bz;
-                const float rs0 = al.w + rb + 1.0e-4f;
+                frame_apply(Rel, al.x, al.y, al.z, qx, qy, qz);
+                const float xs0 = qx - cb.x, ys0 = qy - cb.y, zs0 = qz - cb.z;
+                const float rs0 = al.w + cb.w + 1.0e-4f;
                 const bool cand = (fmaf(-rs0, rs0, fmaf(zs0, zs0, fmaf(ys0, ys0, xs0 * xs0))) < 0.0f) && need && !fhit;
                 if (!__any_sync(kFull, cand)) continue;
                 int acc = 0;
 #pragma unroll 2
                 for (int j = bb; j < be; ++j) {
                     const float4 fl = tb.fine[j];
-                    float px, py, pz;
-                    frame_apply(F, fl.x, fl.y, fl.z, px, py, pz);
-                    const float xs2 = qx - px, ys2 = qy - py, zs2 = qz - pz;
+                    const float xs2 = qx - fl.x, ys2 = qy - fl.y, zs2 = qz - fl.z;
                     const float rs2 = al.w + fl.w;
                     acc |= __float_as_int(fmaf(-rs2, rs2, fmaf(zs2, zs2, fmaf(ys2, ys2, xs2 * xs2))));
                 }
