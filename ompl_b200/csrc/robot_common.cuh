@@ -14,9 +14,9 @@ struct Frame {
 //   kTaskEnv   : link a against the environment (bounding sphere; its fine spheres when that touches something)
 //   kTaskSelfA : self-collision pair (a, b): bounding spheres; when they touch, the frame of link a is saved ...
 //   kTaskSelfB : ... and, with link b's frame, a's fine spheres (outer loop) are tested against b's
+// (one 32-bit word: a single constant load per task)
 struct RobotTask {
-    signed char kind, frame;
-    short a, b;
+    unsigned kind : 2, frame : 6, a : 12, b : 12;
 };
 enum { kTaskFk = 0, kTaskEnv = 1, kTaskSelfA = 2, kTaskSelfB = 3 };
 

@@ -652,21 +652,24 @@ __device__ __forceinline__ void trig_to_slots(const float (&q)[R::kDim], float *
 
 // one step of the streamed frame, k - 1 -> k, through the robot's single out-of-line copy of the frame code (R::step); the joint of
 // frame k is joint k - 1, its sin / cos (or, for a prismatic joint, its value) come from the thread's slots
-template <class R, int BT>
+// INL: the inlined copy (the ordered-scan variant, whose hot loops are the obstacle scans: its three sites may each have one)
+template <class R, int BT, bool INL = false>
 __device__ __forceinline__ void frame_step(Frame &F, int k, const float *__restrict__ slots) {
-    F = R::step(k, F, slots[(trig_slot<R>() + k - 1) * BT], slots[(trig_slot<R>() + R::kDim + k - 1) * BT]);
+    const float s = slots[(trig_slot<R>() + k - 1) * BT], c = slots[(trig_slot<R>() + R::kDim + k - 1) * BT];
+    if (INL) F = R::step_inline(k, F, s, c);
+    else F = R::step(k, F, s, c);
 }
 
 // bring the streamed frame F (currently frame `have`, -1 = nothing) to frame k by walking k's chain (arm): either on
 // from `have` when that is an earlier frame of the same chain, or from the world frame at the chain's first joint
-template <class R, int BT>
+template <class R, int BT, bool INL = false>
 __device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const float *__restrict__ slots) {
     if (have == k) return;
     const int first = R::tables().frame_branch[k];
     int from = have + 1;
     if (have < first || have > k) { frame_identity(F); from = first; }
 #pragma unroll 1
-    for (int j = max(from, 1); j <= k; ++j) frame_step<R, BT>(F, j, slots);
+    for (int j = max(from, 1); j <= k; ++j) frame_step<R, BT, INL>(F, j, slots);
     have = k;
 }
 
@@ -694,7 +697,7 @@ __device__ __forceinline__ bool self_collision(const float *__restrict__ slots, 
         Frame A;
 #pragma unroll 1
         for (int w = 0; w < 2; ++w) {
-            frame_seek<R, BT>(F, have, tb.link_frame[w == 0 ? la : lb], slots);
+            frame_seek<R, BT, true>(F, have, tb.link_frame[w == 0 ? la : lb], slots);
             if (w == 0) A = F;
         }
         const int ab = tb.link_begin[la], ae = tb.link_begin[la + 1];
@@ -737,28 +740,24 @@ __device__ __forceinline__ bool self_collision(const float *__restrict__ slots, 
     return false;
 }
 
-// phase A: trig into the slots, then one base -> tip pass over the frames that parks the bounding-sphere centres and leaves the last
-// frame in `tip`. The pass is a ROLLED loop over the same frame stepper the later frame rebuilds use (R::step, out of line), not the generated
-// straight-line R::fk_coarse: the values are the same (same operations in the same order), the instructions are shared -- the hot
-// code of these kernels has to fit the 32 KB instruction cache.
+// phase A of the ordered-scan variant: trig into the slots, then one unrolled base -> tip pass that parks the bounding-sphere centres
+// and leaves the last frame in `tip` (the candidate-grid variant runs the same steps from its task table instead, check_state_grid)
 template <class R, int BT>
 __device__ __forceinline__ void fk_to_slots(const float (&q)[R::kDim], float *__restrict__ slots, Frame &tip) {
-    const typename R::Tables &tb = R::tables();
+    // (the ordered-scan variant: its hot loops are the obstacle scans, so the forward pass may be the generated straight-line code)
     trig_to_slots<R, BT>(q, slots);
-#pragma unroll 1
-    for (int k = 0; k < R::kFrames; ++k) {
-        if (tb.frame_branch[k] == k) frame_identity(tip);  // the world frame itself (k = 0) or the first frame of an arm
-        if (k > 0) frame_step<R, BT>(tip, k, slots);
-#pragma unroll 1
-        for (int l = tb.frame_link_begin[k]; l < tb.frame_link_begin[k + 1]; ++l) {
-            const float4 c = tb.coarse[l];
-            float x, y, z;
-            frame_apply(tip, c.x, c.y, c.z, x, y, z);
-            slots[(3 * l + 0) * BT] = x;
-            slots[(3 * l + 1) * BT] = y;
-            slots[(3 * l + 2) * BT] = z;
-        }
+    float sn[R::kDim], cs[R::kDim];
+#pragma unroll
+    for (int j = 0; j < R::kDim; ++j) {
+        sn[j] = slots[(trig_slot<R>() + j) * BT];
+        cs[j] = slots[(trig_slot<R>() + R::kDim + j) * BT];
     }
+    // (prismatic joints keep q in their sin slot; the generated frames read q itself)
+    R::fk_coarse(q, sn, cs, tip, [&](int l, float x, float y, float z) {
+        slots[(3 * l + 0) * BT] = x;
+        slots[(3 * l + 1) * BT] = y;
+        slots[(3 * l + 2) * BT] = z;
+    });
 }
 
 // Returns true when this lane's state is collision free. `active` lanes take part; idle lanes only follow the
@@ -796,7 +795,7 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
         if (sd.n_pc > 0) chit |= scan_pointclouds<1, kUntilAllHit>(sd, c, alive && !chit);
         const bool need = group_any<G>(chit && alive) && alive;
         if (!__any_sync(kFull, need)) continue;
-        frame_seek<R, BT>(F, have, tb.link_frame[l], slots);
+        frame_seek<R, BT, true>(F, have, tb.link_frame[l], slots);
         const int fb = tb.link_begin[l], fe = tb.link_begin[l + 1];
         bool fhit = false;
 #pragma unroll 1
@@ -939,7 +938,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
 #pragma unroll 1
     for (int t = 0; t < R::kTasks; ++t) {
         const RobotTask tk = tb.tasks[t];
-        const int kind = tk.kind;
+        const int kind = static_cast<int>(tk.kind);
         if (kind == kTaskEnv) {
             const int l = tk.a;
             const float x = slots[(3 * l + 0) * BT], y = slots[(3 * l + 1) * BT], z = slots[(3 * l + 2) * BT];
@@ -971,7 +970,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
         // ---- the one place frames are stepped: bring F to the task's frame by walking its chain (arm), either on from the frame held
         // when that is an earlier frame of the same chain, or from the world frame at the chain's first joint
         {
-            const int k = tk.frame;
+            const int k = static_cast<int>(tk.frame);
             if (have != k) {
                 const int first = tb.frame_branch[k];
                 int from = have + 1;
@@ -984,7 +983,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
         }
         if (kind == kTaskFk) {
 #pragma unroll 1
-            for (int l = tk.a; l < tk.b; ++l) {
+            for (int l = static_cast<int>(tk.a); l < static_cast<int>(tk.b); ++l) {
                 const float4 c = tb.coarse[l];
                 float x, y, z;
                 frame_apply(F, c.x, c.y, c.z, x, y, z);
