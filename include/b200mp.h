@@ -49,6 +49,7 @@ typedef struct b200mp_knn b200mp_knn;
 typedef struct b200mp_capt b200mp_capt;
 typedef struct b200mp_chain b200mp_chain;
 typedef struct b200mp_comm b200mp_comm;
+typedef struct b200mp_session b200mp_session;
 
 enum {
     B200MP_OK = 0,
@@ -163,6 +164,24 @@ int b200mp_validate_edges_device(b200mp_ctx *ctx, int robot, const b200mp_env *e
                                  int64_t m, int resolution, uint8_t *d_valid, void *stream);
 /* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
 int64_t b200mp_launch_count(const b200mp_ctx *ctx);
+/* ---- sessions: single calls without a launch ----------------------------------------------------------------
+ * A serial planner (RRT-Connect, BASELINE config 1) asks one VampMotionValidator::checkMotion / VampStateValidityChecker::isValid at a
+ * time (src/ompl/vamp/VampMotionValidator.h:37-52, VampStateValidityChecker.h:37-41); through b200mp_validate_motions that is one kernel
+ * launch and one stream synchronise per call (~30 us). A session keeps ONE small block resident on the GPU -- the scene staged in its
+ * shared memory -- polling a mailbox in mapped host memory: a call writes the two configurations and a sequence number and spins on the
+ * answer. Decisions are those of b200mp_validate_motions (same states, same tests). The kernel leaves by itself after 50 ms without
+ * a call (B200MP_SESSION_IDLE_MS) and is restarted by the next one, so an idle session holds no SM. A session is a snapshot of the
+ * committed environment at open time (re-open it after changing the scene or the attachment); calls on one session are serialised. */
+int b200mp_session_open(b200mp_ctx *ctx, int robot, const b200mp_env *env, b200mp_session **out);
+void b200mp_session_close(b200mp_session *session);
+/* q0, q1[dim]; resolution 0 = the robot's default. */
+int b200mp_session_check_motion(b200mp_session *session, const float *q0, const float *q1, int resolution, uint8_t *valid);
+int b200mp_session_check_motion_f64(b200mp_session *session, const double *q0, const double *q1, int resolution, uint8_t *valid);
+int b200mp_session_is_valid(b200mp_session *session, const float *q, uint8_t *valid);
+int b200mp_session_is_valid_f64(b200mp_session *session, const double *q, uint8_t *valid);
+/* calls answered so far, kernel (re)starts so far; either pointer may be NULL */
+int b200mp_session_stats(const b200mp_session *session, int64_t *calls, int64_t *launches);
+
 /* Tuning switches (decisions never depend on them). B200MP_OPT_FIRST_LOOK (default 1): batches of long motions (>= 5 rakes) first get a
  * look at rake 0 of four motions per warp pass, continued only while it settles most motions (see validate_rakes_kernel); 0 sends
  * them straight to the warp-per-motion kernel (measurements of that kernel alone). */

@@ -269,6 +269,30 @@ namespace ompl::b200
     };
     using EnvironmentPtr = std::shared_ptr<Environment>;
 
+    /// RAII handle of a b200mp_session (the resident single-call kernel, include/b200mp.h "sessions")
+    class Session
+    {
+    public:
+        Session(EnvironmentPtr env, int robot) : env_(std::move(env))
+        {
+            check(b200mp_session_open(env_->engine()->get(), robot, env_->get(), &s_), "Session");
+        }
+        ~Session()
+        {
+            b200mp_session_close(s_);
+        }
+        Session(const Session &) = delete;
+        Session &operator=(const Session &) = delete;
+        b200mp_session *get() const
+        {
+            return s_;
+        }
+
+    private:
+        EnvironmentPtr env_;
+        b200mp_session *s_ = nullptr;
+    };
+
     namespace detail
     {
         inline const double *values(const ob::State *s)
@@ -347,9 +371,25 @@ namespace ompl::b200
         {
         }
 
+        /// Serial planners (RRT-Connect ...): answer single checkMotion calls from a kernel that stays resident on the GPU
+        /// (b200mp_session_*: no launch and no synchronise per call). Same decisions. The session is a snapshot of the environment as
+        /// committed now; call again after changing the scene or the attachment. Calls from several threads are serialised.
+        void useSession(bool on = true)
+        {
+            session_.reset();
+            if (on)
+                session_ = std::make_shared<Session>(env_, Robot::id);
+        }
+
         bool checkMotion(const ob::State *s1, const ob::State *s2) const override
         {
             std::uint8_t ok = 0;
+            if (session_)
+            {
+                check(b200mp_session_check_motion_f64(session_->get(), detail::values(s1), detail::values(s2), Robot::resolution, &ok),
+                      "checkMotion (session)");
+                return ok != 0;
+            }
             check(b200mp_validate_motions_f64(env_->engine()->get(), Robot::id, env_->get(), detail::values(s1), detail::values(s2), 1,
                                               Robot::resolution, &ok),
                   "checkMotion");
@@ -423,6 +463,7 @@ namespace ompl::b200
 
     private:
         EnvironmentPtr env_;
+        std::shared_ptr<Session> session_;
     };
 
     /// The planar kinematic chain of demos/KinematicChain.h on the GPU: n_links revolute joints (a RealVectorStateSpace of angles),

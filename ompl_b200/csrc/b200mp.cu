@@ -1,5 +1,6 @@
 // b200mp C ABI implementation: contexts, environments, validation launches (see include/b200mp.h).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1083,6 +1084,153 @@ int b200mp_validate_motions_device(b200mp_ctx *c, int robot, const b200mp_env *e
         default: return fail(B200MP_ERR_INVALID, "unknown robot %d", robot);
     }
 #undef B200_MOTIONS
+}
+
+}  // extern "C"
+
+// ---- sessions: the resident single-call kernel (session.cuh) ---------------------------------------------------------------------
+struct b200mp_session {
+    b200mp_ctx *ctx = nullptr;
+    const b200mp_env *env = nullptr;
+    int robot = 0, dim = 0, resolution = 0;
+    cudaStream_t stream = nullptr;
+    b200mp::SessionMailbox *h = nullptr, *d = nullptr;  // the same mapped memory as the host / the device sees it
+    unsigned seq = 0;
+    unsigned long long idle_ns = 50ull * 1000 * 1000;
+    long long relaunches = 0;
+    std::mutex mu;
+};
+
+namespace {
+int session_launch(b200mp_session *s) {
+    volatile b200mp::SessionMailbox *mb = s->h;
+    mb->alive = 1u;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    const SceneDesc &desc = s->env->desc;
+    int rc = B200MP_ERR_INVALID;
+    switch (s->robot) {
+        case B200MP_ROBOT_PANDA: rc = launch_session<Panda>(s->ctx, desc, s->d, s->seq, s->idle_ns, s->stream); break;
+        case B200MP_ROBOT_FETCH: rc = launch_session<Fetch>(s->ctx, desc, s->d, s->seq, s->idle_ns, s->stream); break;
+        case B200MP_ROBOT_UR5: rc = launch_session<Ur5>(s->ctx, desc, s->d, s->seq, s->idle_ns, s->stream); break;
+        case B200MP_ROBOT_BAXTER: rc = launch_session<Baxter>(s->ctx, desc, s->d, s->seq, s->idle_ns, s->stream); break;
+        default: return fail(B200MP_ERR_INVALID, "b200mp_session: unknown robot %d", s->robot);
+    }
+    if (rc == B200MP_OK) ++s->relaunches;
+    return rc;
+}
+
+template <typename T>
+int session_check(b200mp_session *s, const T *q0, const T *q1, int resolution, uint8_t *valid) {
+    if (!s || !q0 || !q1 || !valid) return fail(B200MP_ERR_INVALID, "b200mp_session_check_motion: NULL argument");
+    if (resolution < 0) return fail(B200MP_ERR_INVALID, "b200mp_session_check_motion: negative resolution");
+    std::lock_guard<std::mutex> lk(s->mu);
+    volatile b200mp::SessionMailbox *mb = s->h;
+    if (mb->alive == 0u) {  // the kernel left after its idle time (or was never started): start it again
+        B200_CUDA(cudaSetDevice(s->ctx->device));
+        const int rc = session_launch(s);
+        if (rc) return rc;
+    }
+    for (int j = 0; j < s->dim; ++j) {
+        mb->q0[j] = static_cast<float>(q0[j]);  // ompl_to_vamp: static_cast<float>(values[i])
+        mb->q1[j] = static_cast<float>(q1[j]);
+    }
+    mb->resolution = resolution == 0 ? s->resolution : resolution;
+    mb->cmd = b200mp::kSessionMotion;
+    const unsigned want = ++s->seq;
+    std::atomic_thread_fence(std::memory_order_release);
+    mb->seq_req = want;
+    // spin on the answer; a kernel that left between our look at `alive` and the request is restarted once
+    const auto t0 = std::chrono::steady_clock::now();
+    bool restarted = false;
+    for (unsigned spins = 0;; ++spins) {
+        if (mb->seq_ack == want) break;
+        if ((spins & 1023u) == 1023u) {
+            if (mb->alive == 0u && !restarted && mb->seq_ack != want) {
+                B200_CUDA(cudaStreamSynchronize(s->stream));
+                if (mb->seq_ack == want) break;
+                --s->seq;  // the relaunched kernel starts from the sequence number before this request and sees it as new
+                const int rc = session_launch(s);
+                ++s->seq;
+                if (rc) return rc;
+                restarted = true;
+            }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) {
+                const cudaError_t ce = cudaStreamQuery(s->stream);
+                return fail(B200MP_ERR_CUDA, "b200mp_session_check_motion: no answer from the resident kernel (%s)",
+                            ce == cudaSuccess || ce == cudaErrorNotReady ? "timeout" : cudaGetErrorString(ce));
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    *valid = static_cast<uint8_t>(mb->result);
+    return B200MP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int b200mp_session_open(b200mp_ctx *c, int robot, const b200mp_env *e, b200mp_session **out) {
+    if (!out) return fail(B200MP_ERR_INVALID, "b200mp_session_open: out is NULL");
+    *out = nullptr;
+    float dummy = 0;
+    uint8_t dummy_out = 0;
+    int rc = check_common("b200mp_session_open", c, e, &dummy, &dummy_out, 1);
+    if (rc) return rc;
+    int dim = 0, res = 0;
+    if ((rc = b200mp_robot_info(robot, &dim, nullptr, &res, nullptr, nullptr))) return rc;
+    B200_CUDA(cudaSetDevice(c->device));
+    auto *s = new b200mp_session();
+    s->ctx = c;
+    s->env = e;
+    s->robot = robot;
+    s->dim = dim;
+    s->resolution = res;
+    if (const char *v = getenv("B200MP_SESSION_IDLE_MS")) s->idle_ns = static_cast<unsigned long long>(std::max(1, atoi(v))) * 1000ull * 1000ull;
+    cudaError_t ce = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaHostAlloc(reinterpret_cast<void **>(&s->h), sizeof(b200mp::SessionMailbox), cudaHostAllocMapped);
+    if (ce == cudaSuccess) ce = cudaHostGetDevicePointer(reinterpret_cast<void **>(&s->d), s->h, 0);
+    if (ce != cudaSuccess) {
+        b200mp_session_close(s);
+        return fail(B200MP_ERR_CUDA, "b200mp_session_open: %s", cudaGetErrorString(ce));
+    }
+    std::memset(s->h, 0, sizeof(b200mp::SessionMailbox));
+    if ((rc = session_launch(s))) { b200mp_session_close(s); return rc; }
+    *out = s;
+    return B200MP_OK;
+}
+
+void b200mp_session_close(b200mp_session *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    if (s->h && s->stream) {
+        volatile b200mp::SessionMailbox *mb = s->h;
+        if (mb->alive != 0u) {  // ask the kernel to leave (it would also do so by itself after its idle time)
+            mb->cmd = b200mp::kSessionQuit;
+            std::atomic_thread_fence(std::memory_order_release);
+            mb->seq_req = ++s->seq;
+        }
+        cudaStreamSynchronize(s->stream);
+    }
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->h) cudaFreeHost(s->h);
+    cudaGetLastError();
+    delete s;
+}
+
+int b200mp_session_check_motion(b200mp_session *s, const float *q0, const float *q1, int resolution, uint8_t *valid) {
+    return session_check<float>(s, q0, q1, resolution, valid);
+}
+int b200mp_session_check_motion_f64(b200mp_session *s, const double *q0, const double *q1, int resolution, uint8_t *valid) {
+    return session_check<double>(s, q0, q1, resolution, valid);
+}
+/* VampStateValidityChecker::isValid = validate_motion<Robot, rake, 1>(q, q) */
+int b200mp_session_is_valid(b200mp_session *s, const float *q, uint8_t *valid) { return session_check<float>(s, q, q, 1, valid); }
+int b200mp_session_is_valid_f64(b200mp_session *s, const double *q, uint8_t *valid) { return session_check<double>(s, q, q, 1, valid); }
+int b200mp_session_stats(const b200mp_session *s, int64_t *calls, int64_t *launches) {
+    if (!s) return fail(B200MP_ERR_INVALID, "b200mp_session_stats: session is NULL");
+    if (calls) *calls = s->seq;
+    if (launches) *launches = s->relaunches;
+    return B200MP_OK;
 }
 
 int b200mp_validate_edges_device(b200mp_ctx *c, int robot, const b200mp_env *e, const float *d_states, const int32_t *d_edges, int64_t m,

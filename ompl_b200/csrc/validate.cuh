@@ -677,13 +677,25 @@ __device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const flo
 // whose bounding spheres touch. Updates `alive`; returns true when the caller should return `result` immediately.
 // KILL (lane-per-state form only): lanes are grouped into motions by `kill` (the lanes that belong to the same motion as this
 // one); a hit in any of them ends the work of all of them.
-template <class R, int G, bool EDGE, bool KILL, int BT>
-__device__ __forceinline__ bool self_collision(const float *__restrict__ slots, bool &alive, bool &result, unsigned kill) {
+// SLICED (the resident single-call kernel, session.cuh): several warps check the SAME states, each a share of the links and pairs
+// (index % nslice == slice); a state is valid when every share says so. The unsliced kernels carry no trace of it (empty type).
+template <bool SLICED>
+struct Share {
+    __device__ __forceinline__ bool mine(unsigned) const { return true; }
+};
+template <>
+struct Share<true> {
+    int slice, nslice;
+    __device__ __forceinline__ bool mine(unsigned i) const { return static_cast<int>(i % static_cast<unsigned>(nslice)) == slice; }
+};
+template <class R, int G, bool EDGE, bool KILL, int BT, bool SLICED = false>
+__device__ __forceinline__ bool self_collision(const float *__restrict__ slots, bool &alive, bool &result, unsigned kill, Share<SLICED> share = {}) {
     const typename R::Tables &tb = R::tables();
     Frame F;
     int have = -1;
 #pragma unroll 1
     for (int p = 0; p < R::kPairs; ++p) {
+        if (!share.mine(static_cast<unsigned>(p))) continue;
         const int la = tb.pair_a[p], lb = tb.pair_b[p];
         const float ra = tb.coarse[la].w, rb = tb.coarse[lb].w;
         const float bx = slots[(3 * lb + 0) * BT], by = slots[(3 * lb + 1) * BT], bz = slots[(3 * lb + 2) * BT];
@@ -769,9 +781,9 @@ __device__ __forceinline__ void fk_to_slots(const float (&q)[R::kDim], float *__
 // states exit early); only when a rake has a coarse hit is the link's frame rebuilt (chain walk from the cached
 // sin / cos) and its fine spheres tested. Phase C: self_collision().
 // This is the ordered-scan variant (scenes without a candidate grid: small or unsorted).
-template <class R, int G, bool EDGE, bool KILL, bool MASKED, int BT>
+template <class R, int G, bool EDGE, bool KILL, bool MASKED, int BT, bool SLICED = false>
 __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots, bool active,
-                                    unsigned kill) {
+                                    unsigned kill, Share<SLICED> share = {}) {
     constexpr int FT = 4;  // fine spheres processed together per lane
     constexpr int POLICY = EDGE ? kAnyHit : kUntilAllHit;
     const typename R::Tables &tb = R::tables();
@@ -781,6 +793,7 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
     int have = R::kFrames - 1;  // frame held in F (warp-uniform)
 #pragma unroll 1
     for (int l = R::kLinks - 1; l >= 0; --l) {
+        if (!share.mine(static_cast<unsigned>(l))) continue;
         const float4 cl = tb.coarse[l];
         Tile<1> c;
         c.x[0] = slots[(3 * l + 0) * BT];
@@ -830,7 +843,7 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
         if (!EDGE && !__any_sync(kFull, alive)) return false;
     }
     bool result = false;
-    if (self_collision<R, G, EDGE, KILL, BT>(slots, alive, result, kill)) return result;
+    if (self_collision<R, G, EDGE, KILL, BT, SLICED>(slots, alive, result, kill, share)) return result;
     return alive;
 }
 
@@ -924,9 +937,9 @@ __device__ __noinline__ bool fine_pair_cold(const Scene *scp, const SharedViews 
 // touches; a pair: do the bounding spheres touch); the streamed frame is then brought to the task's frame at the ONE place this
 // function steps frames; then the fine spheres are tested (a link: two at a time against the remembered obstacles). One copy of the
 // frame code and of every loop: the hot code of these kernels has to fit the 32 KB instruction cache.
-template <class R, int G, bool EDGE, bool KILL, int BT>
+template <class R, int G, bool EDGE, bool KILL, int BT, bool SLICED = false>
 __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
-                                 const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill) {
+                                 const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill, Share<SLICED> share = {}) {
     const typename R::Tables &tb = R::tables();
     bool alive = active;
     trig_to_slots<R, BT>(q, slots);
@@ -939,6 +952,8 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
     for (int t = 0; t < R::kTasks; ++t) {
         const RobotTask tk = tb.tasks[t];
         const int kind = static_cast<int>(tk.kind);
+        // (a sliced check: this warp's share of the links and pairs; both halves of a pair fall to the same share)
+        if (SLICED && kind != kTaskFk && !share.mine(tk.a + 3u * (kind == kTaskEnv ? 0u : tk.b))) continue;
         if (kind == kTaskEnv) {
             const int l = tk.a;
             const float x = slots[(3 * l + 0) * BT], y = slots[(3 * l + 1) * BT], z = slots[(3 * l + 2) * BT];
@@ -1186,12 +1201,13 @@ __device__ __noinline__ bool attachment_hit(const float *__restrict__ slots, con
     return hit;
 }
 
-template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT, bool KILL = false>
+template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT, bool KILL = false, bool SLICED = false>
 __device__ __forceinline__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
-                                            const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill = 0u) {
-    bool good = GRID ? check_state_grid<R, G, EDGE, KILL, BT>(q, sd, sc, slots, lv, sv, active, kill)
-                     : check_state_ordered<R, G, EDGE, KILL, MASKED, BT>(q, sd, sc, slots, active, kill);
-    if (sd.n_att > 0) {
+                                            const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill = 0u,
+                                            Share<SLICED> share = {}) {
+    bool good = GRID ? check_state_grid<R, G, EDGE, KILL, BT, SLICED>(q, sd, sc, slots, lv, sv, active, kill, share)
+                     : check_state_ordered<R, G, EDGE, KILL, MASKED, BT, SLICED>(q, sd, sc, slots, active, kill, share);
+    if (sd.n_att > 0 && share.mine(0u)) {
         // (an EDGE pass that already has a hit is over: its caller drops the motion)
         if (EDGE && __any_sync(kFull, active && !good)) return good;
         const bool alive = active && good;

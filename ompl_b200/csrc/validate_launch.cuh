@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "validate.cuh"
+#include "session.cuh"
 #include "host_common.hpp"
 
 namespace b200mp {
@@ -109,13 +110,29 @@ int launch_states(b200mp_ctx *c, const SceneDesc &desc, const float *d_q, int64_
     return B200MP_OK;
 }
 
+// the resident single-call kernel (session.cuh) on `st`; returns once it is launched
+template <class R>
+int launch_session(b200mp_ctx *c, const SceneDesc &desc, SessionMailbox *d_mailbox, unsigned first_seq, unsigned long long idle_ns, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(desc.blob_floats) * 4 + lane_store_bytes<R>(kSessionThreads);
+    auto kern = desc.n_grid > 0 ? session_kernel<R, false, true> : (desc.sorted ? session_kernel<R, false, false> : session_kernel<R, true, false>);
+    int per_sm = 0, rc = 0;
+    if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(kern), kSessionThreads, smem, &per_sm))) return rc;
+    if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "session: kernel does not fit on an SM with %zu B of scene", smem);
+    kern<<<1, kSessionThreads, smem, st>>>(desc, d_mailbox, first_seq, idle_ns);
+    B200_CUDA(cudaGetLastError());
+    c->launches.fetch_add(1);
+    return B200MP_OK;
+}
+
 #define B200MP_INSTANTIATE_ROBOT(R)                                                                                                        \
     template int launch_motions<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t);          \
     template int launch_motions_bucketed<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t); \
-    template int launch_states<R>(b200mp_ctx *, const SceneDesc &, const float *, int64_t, uint8_t *, cudaStream_t, const unsigned *);
+    template int launch_states<R>(b200mp_ctx *, const SceneDesc &, const float *, int64_t, uint8_t *, cudaStream_t, const unsigned *);                          \
+    template int launch_session<R>(b200mp_ctx *, const SceneDesc &, SessionMailbox *, unsigned, unsigned long long, cudaStream_t);
 #define B200MP_EXTERN_ROBOT(R)                                                                                                                    \
     extern template int launch_motions<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t);          \
     extern template int launch_motions_bucketed<R>(b200mp_ctx *, const SceneDesc &, const float *, const float *, const int2 *, int64_t, int, uint8_t *, cudaStream_t); \
-    extern template int launch_states<R>(b200mp_ctx *, const SceneDesc &, const float *, int64_t, uint8_t *, cudaStream_t, const unsigned *);
+    extern template int launch_states<R>(b200mp_ctx *, const SceneDesc &, const float *, int64_t, uint8_t *, cudaStream_t, const unsigned *);                          \
+    extern template int launch_session<R>(b200mp_ctx *, const SceneDesc &, SessionMailbox *, unsigned, unsigned long long, cudaStream_t);
 
 }  // namespace b200mp

@@ -67,6 +67,14 @@ def load_library():
     L.b200mp_capt_export.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
     L.b200mp_env_sort.argtypes = [_vp]
     L.b200mp_env_set_attachment.argtypes = [_vp, C.c_void_p, C.c_void_p, C.c_int]
+    L.b200mp_session_open.argtypes = [_vp, C.c_int, _vp, C.POINTER(_vp)]
+    L.b200mp_session_close.argtypes = [_vp]
+    L.b200mp_session_close.restype = None
+    L.b200mp_session_check_motion.argtypes = [_vp, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.b200mp_session_check_motion_f64.argtypes = [_vp, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.b200mp_session_is_valid.argtypes = [_vp, C.c_void_p, C.c_void_p]
+    L.b200mp_session_is_valid_f64.argtypes = [_vp, C.c_void_p, C.c_void_p]
+    L.b200mp_session_stats.argtypes = [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.b200mp_env_set_grid.argtypes = [_vp, C.c_int]
     L.b200mp_env_commit.argtypes = [_vp]
     L.b200mp_env_min_distances.argtypes = [_vp, C.c_int, _vp]
@@ -355,6 +363,52 @@ class Comm:
         e = int(st.n_edges)
         return dict(states=states, edges=edges[:e].copy(), valid=valid[:e].copy(),
                     weights=weights[:e].copy() if want_weights else None, neighbors=nbr, stats=st.as_dict())
+
+
+class Session:
+    """The resident single-call kernel (b200mp_session_*): one checkMotion / isValid per call without a kernel launch."""
+
+    def __init__(self, ctx: "Context", robot: str, env: "Environment"):
+        self._L = load_library()
+        self._ctx, self._env = ctx, env
+        self._dim = robot_info(robot)["dim"]
+        h = _vp()
+        _check(self._L.b200mp_session_open(ctx._h, ROBOTS[robot], env._h, C.byref(h)))
+        self._h = h
+        self._out = np.zeros(1, np.uint8)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200mp_session_close(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check_motion(self, q0, q1, resolution: int = 0) -> bool:
+        a, b = np.ascontiguousarray(q0), np.ascontiguousarray(q1)
+        assert a.shape == (self._dim,) and b.shape == (self._dim,) and a.dtype == b.dtype
+        fn = self._L.b200mp_session_check_motion_f64 if a.dtype == np.float64 else self._L.b200mp_session_check_motion
+        if a.dtype not in (np.float32, np.float64):
+            a, b = a.astype(np.float32), b.astype(np.float32)
+        _check(fn(self._h, a.ctypes.data, b.ctypes.data, int(resolution), self._out.ctypes.data))
+        return bool(self._out[0])
+
+    def is_valid(self, q) -> bool:
+        a = np.ascontiguousarray(q)
+        fn = self._L.b200mp_session_is_valid_f64 if a.dtype == np.float64 else self._L.b200mp_session_is_valid
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float32)
+        _check(fn(self._h, a.ctypes.data, self._out.ctypes.data))
+        return bool(self._out[0])
+
+    def stats(self) -> dict:
+        c, l = C.c_int64(0), C.c_int64(0)
+        _check(self._L.b200mp_session_stats(self._h, C.byref(c), C.byref(l)))
+        return {"calls": c.value, "launches": l.value}
 
 
 class Environment:

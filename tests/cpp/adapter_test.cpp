@@ -121,6 +121,13 @@ static void test_validators(const b2::EnginePtr &eng)
     env->clearAttachment();
     EXPECT(svc->isValid(&start.s));
 
+    // single calls through the resident kernel (b200mp_session_*): same answers, no launch per call
+    mv_b->useSession(true);
+    EXPECT(!mv->checkMotion(&start.s, &goal.s));
+    EXPECT(mv->checkMotion(&start.s, &start.s));
+    for (int i = 0; i < 400; i += 3) EXPECT(mv->checkMotion(a[i], b[i]) == (mvb[i] != 0));
+    mv_b->useSession(false);
+
     // an environment that was not committed is an error surfaced as ompl::Exception
     auto env2 = std::make_shared<b2::Environment>(eng);
     env2->addSphere({1, 0, 0}, 0.1F);

@@ -38,3 +38,19 @@ def test_same_planner_run_with_engine_and_checker(ctx, seed):
     # every edge of the solution is valid for the checker, and the straight line is not (known answer of the demo)
     assert ce.validate_motions("panda", p1[:-1].astype(np.float32), p1[1:].astype(np.float32)).all()
     assert not cpu(synth.CAGE_START.astype(np.float64), synth.CAGE_GOAL.astype(np.float64))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_same_planner_run_through_the_resident_kernel(ctx, seed):
+    """The same run with every checkMotion answered by a b200mp_session (no launch per call): identical decisions again."""
+    env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
+    ce = checker()
+    lo, hi = synth.BOUNDS["panda"]
+    s = ompl_b200.Session(ctx, "panda", env)
+    gpu = lambda a, b: s.check_motion(np.asarray(a, np.float64), np.asarray(b, np.float64))  # noqa: E731
+    cpu = lambda a, b: ce.validate_motions("panda", a[None].astype(np.float32), b[None].astype(np.float32))[0]  # noqa: E731
+    p1, log1, it1 = solve(synth.CAGE_START, synth.CAGE_GOAL, lo, hi, gpu, seed)
+    p2, log2, it2 = solve(synth.CAGE_START, synth.CAGE_GOAL, lo, hi, cpu, seed)
+    assert p1 is not None and log1 == log2 and it1 == it2
+    np.testing.assert_array_equal(p1, p2)
+    s.close()
