@@ -1249,10 +1249,14 @@ struct BucketPlan {
 // at 96 registers, the state kernel prefers 16 warps at 128). Shared memory per block = scene blob + lane_slots floats per thread.
 constexpr int kMotionBlocksPerSM = 1;
 constexpr int kStateThreads = 256, kStateBlocksPerSM = 2;
+// (measured on the 2^20 roadmap, Panda: 640 threads at 96 registers 100 ms; 704 at 80 registers 126 ms -- spills --; 576 at 96: 107 ms)
+#ifndef B200MP_MOTION_THREADS
+#define B200MP_MOTION_THREADS 640
+#endif
 // the motion kernel's block: as many warps as keep the per-thread slots within ~160 KB (Baxter: 33 links + 14 joints)
 template <class R>
 __host__ __device__ constexpr int motion_threads() {
-    return lane_slots<R>() * 640 * 4 <= 160 * 1024 ? 640 : (lane_slots<R>() * 384 * 4 <= 160 * 1024 ? 384 : 256);
+    return lane_slots<R>() * B200MP_MOTION_THREADS * 4 <= 172 * 1024 ? B200MP_MOTION_THREADS : (lane_slots<R>() * 384 * 4 <= 160 * 1024 ? 384 : 256);
 }
 
 template <class R>
