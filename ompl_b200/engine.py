@@ -303,8 +303,7 @@ class Context:
         _check(self._L.b200mp_prm_build(self._h, ROBOTS[robot], env._h, seed, n, k, resolution, states.ctypes.data, edges.ctypes.data,
                                         valid.ctypes.data, weights.ctypes.data if want_weights else None, cap, C.byref(st)))
         e = int(st.n_edges)
-        return dict(states=states, edges=edges[:e].copy(), valid=valid[:e].copy(),
-                    weights=weights[:e].copy() if want_weights else None, stats=st.as_dict())
+        return dict(states=states, edges=edges[:e], valid=valid[:e], weights=weights[:e] if want_weights else None, stats=st.as_dict())
 
 
 UNIQUE_ID_BYTES = 128
@@ -361,8 +360,9 @@ class Comm:
                                               valid.ctypes.data, weights.ctypes.data if want_weights else None,
                                               nbr.ctypes.data if nbr is not None else None, cap, C.byref(st)))
         e = int(st.n_edges)
-        return dict(states=states, edges=edges[:e].copy(), valid=valid[:e].copy(),
-                    weights=weights[:e].copy() if want_weights else None, neighbors=nbr, stats=st.as_dict())
+        # (views of the capacity-sized buffers, not copies: ~180 MB at 2^20 x 16)
+        return dict(states=states, edges=edges[:e], valid=valid[:e],
+                    weights=weights[:e] if want_weights else None, neighbors=nbr, stats=st.as_dict())
 
 
 class Session:
