@@ -1259,6 +1259,12 @@ __host__ __device__ constexpr int motion_threads() {
     return lane_slots<R>() * B200MP_MOTION_THREADS * 4 <= 172 * 1024 ? B200MP_MOTION_THREADS : (lane_slots<R>() * 384 * 4 <= 160 * 1024 ? 384 : 256);
 }
 
+// the state kernel's block: one block of 20 warps where the robot's slots allow it, else two blocks of 8 warps
+template <class R>
+__host__ __device__ constexpr int state_threads() { return motion_threads<R>() == B200MP_MOTION_THREADS ? B200MP_MOTION_THREADS : kStateThreads; }
+template <class R>
+__host__ __device__ constexpr int state_blocks_per_sm() { return state_threads<R>() == kStateThreads ? kStateBlocksPerSM : 1; }
+
 template <class R>
 __host__ __device__ constexpr size_t lane_store_bytes(int threads) { return static_cast<size_t>(lane_slots<R>()) * threads * sizeof(float); }
 
@@ -1613,7 +1619,7 @@ static __global__ void __launch_bounds__(256) bucket_scatter_kernel(const unsign
 // One lane per state: VampStateValidityChecker::isValid = validate_motion<Robot, rake, 1>(q, q), i.e. one fkcc on
 // 8 identical lanes (src/ompl/vamp/VampStateValidityChecker.h:37-41) -> group size 1 here.
 template <class R, bool MASKED, bool GRID>
-__global__ void __launch_bounds__(kStateThreads, kStateBlocksPerSM)
+__global__ void __launch_bounds__(state_threads<R>(), state_blocks_per_sm<R>())
 validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, uint8_t *__restrict__ valid, LaunchCounters *cnt,
                        const unsigned *__restrict__ order) {
     extern __shared__ __align__(16) float smem[];
@@ -1642,7 +1648,7 @@ validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, 
 #pragma unroll
         for (int j = 0; j < D; ++j) q[j] = active ? __ldg(qs + i * D + j) : 0.0f;
         // validate_vector with start == goal: block = q + 0 * percents
-        const bool good = check_state<R, 1, false, MASKED, GRID, kStateThreads>(q, sd, sc, slots, lv, sv, active);
+        const bool good = check_state<R, 1, false, MASKED, GRID, state_threads<R>()>(q, sd, sc, slots, lv, sv, active);
         if (active) valid[i] = good ? 1 : 0;
     }
 }

@@ -94,17 +94,17 @@ int launch_motions_bucketed(b200mp_ctx *c, const SceneDesc &desc, const float *d
 
 template <class R>
 int launch_states(b200mp_ctx *c, const SceneDesc &desc, const float *d_q, int64_t m, uint8_t *d_valid, cudaStream_t st, const unsigned *d_order) {
-    const size_t smem = static_cast<size_t>(desc.blob_floats) * 4 + lane_store_bytes<R>(kStateThreads);
+    const size_t smem = static_cast<size_t>(desc.blob_floats) * 4 + lane_store_bytes<R>(state_threads<R>());
     auto kern = desc.n_grid > 0 ? validate_states_kernel<R, false, true>
                                 : (desc.sorted ? validate_states_kernel<R, false, false> : validate_states_kernel<R, true, false>);
     int per_sm = 0, rc = 0;
-    if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(kern), kStateThreads, smem, &per_sm))) return rc;
+    if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(kern), state_threads<R>(), smem, &per_sm))) return rc;
     if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_states: kernel does not fit on an SM with %zu B of scene", smem);
-    const long long warps_needed = (m + 31) / 32, wpb = kStateThreads / 32;
+    const long long warps_needed = (m + 31) / 32, wpb = state_threads<R>() / 32;
     const long long blocks = std::max<long long>(1, std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + wpb - 1) / wpb));
     LaunchCounters *cnt = next_counter(c);
     B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), kStateThreads, smem, st>>>(desc, d_q, m, d_valid, cnt, d_order);
+    kern<<<static_cast<unsigned>(blocks), state_threads<R>(), smem, st>>>(desc, d_q, m, d_valid, cnt, d_order);
     B200_CUDA(cudaGetLastError());
     c->launches.fetch_add(1);
     return B200MP_OK;
