@@ -407,7 +407,8 @@ def main():
                       "edges_per_s": c4["edges_per_s"], "all_valid_states_per_s": c4.get("all_valid_states_per_s"), "ms_filter_gpu": c4["ms_filter_gpu"],
                       "ms_filter_reference_1thread": c4["ms_filter_reference_1thread"], "filtered_points": c4["filtered_points"],
                       "filtered_points_reference": c4["filtered_points_reference"], "cpu_baseline": c4["cpu_baseline"],
-                      "reference_on_own_filter": c4.get("reference_pipeline_on_reference_filtered_cloud")}
+                      "reference_on_own_filter": c4.get("reference_pipeline_on_reference_filtered_cloud"),
+                      "reference_filter_stable_ties": c4.get("reference_filter_with_stable_ties")}
         c5 = configs_probe.c5(ctx, 1 << 16)
         line["c5"] = {"workload": "20-link planar chain, horn environment: 2^20 states, chain-metric kNN k=16 over 2^16 valid states, its edges",
                       "states_per_s": c5["states_per_s"], "cpu_states": c5["cpu_states"], "knn_queries_per_s": c5["knn_queries_per_s"],

@@ -190,6 +190,8 @@ extern "C"
 
 // ---- point-cloud filter (collision/filter.hh:176-274), unmodified; returns the number of points kept, writes at most cap
 #include <vamp/collision/filter.hh>
+// 1: equal curve codes keep their previous order (std::stable_sort in place of the absent pdqsort); 0: std::sort (default)
+extern "C" void refv_set_stable_sort(int on) { refv_sort_mode() = on ? 1 : 0; }
 extern "C" std::int64_t refv_filter_pointcloud(const float *xyz, std::int64_t n, float min_dist, float max_range, const float *origin,
                                                const float *ws_min, const float *ws_max, int cull, float *out, std::int64_t cap)
 {

@@ -51,6 +51,7 @@ def lib():
     L.refv_capt_collides.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int64, _u8p]
     L.refv_filter_pointcloud.argtypes = [_f32p, C.c_int64, C.c_float, C.c_float, _f32p, _f32p, _f32p, C.c_int, _f32p, C.c_int64]
     L.refv_filter_pointcloud.restype = C.c_int64
+    L.refv_set_stable_sort.argtypes = [C.c_int]
     for r in ("panda", "fetch", "ur5", "baxter"):
         getattr(L, f"refv_{r}_bounds").argtypes = [_f32p, _f32p]
         getattr(L, f"refv_{r}_validate_motions").argtypes = [
@@ -201,10 +202,13 @@ def hardware_threads() -> int:
     return int(lib().refv_hardware_threads())
 
 
-def filter_pointcloud(xyz, min_dist, max_range, origin, ws_min, ws_max, cull=True) -> np.ndarray:
-    """vamp::collision::filter_pointcloud (collision/filter.hh:176-274), compiled as is."""
+def filter_pointcloud(xyz, min_dist, max_range, origin, ws_min, ws_max, cull=True, stable_ties=False) -> np.ndarray:
+    """vamp::collision::filter_pointcloud (collision/filter.hh:176-274), compiled as is. Its sort (pdqsort, absent here) is std::sort, or
+    with stable_ties std::stable_sort: equal curve codes then keep their previous order."""
     xyz = _f32(xyz).reshape(-1, 3)
+    lib().refv_set_stable_sort(1 if stable_ties else 0)
     out = np.empty((len(xyz) + 1, 3), np.float32)
     n = lib().refv_filter_pointcloud(xyz, len(xyz), float(min_dist), float(max_range), _f32(origin), _f32(ws_min), _f32(ws_max),
                                      int(bool(cull)), out, len(out))
+    lib().refv_set_stable_sort(0)
     return out[:n].copy()

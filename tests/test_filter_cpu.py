@@ -73,3 +73,7 @@ def test_restatement_matches_compiled_reference_live():
     b = port.filter_pointcloud(pts, 0.012, 1.5, o, o - 1.5, o + 1.5, True)
     assert abs(len(a) - len(b)) < 0.005 * len(a)
     assert len(set(map(tuple, a)) & set(map(tuple, b))) > 0.85 * len(a)
+    # ... and tie order is ALL they differ by: the same reference code with its (absent) pdqsort replaced by a stable sort instead of
+    # std::sort gives the restatement's output point for point
+    c = refvamp.filter_pointcloud(pts, 0.012, 1.5, o, o - 1.5, o + 1.5, True, stable_ties=True)
+    np.testing.assert_array_equal(c, b)

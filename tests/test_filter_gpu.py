@@ -30,6 +30,20 @@ def test_dense_cloud_equals_restatement(ctx, n, min_dist, cull):
     np.testing.assert_array_equal(got, want)
 
 
+def test_dense_cloud_equals_compiled_reference_with_stable_ties(ctx):
+    """The unmodified reference, its absent pdqsort replaced by std::stable_sort (oracle/shim/pdqsort.h), on the C4 cloud: point for point
+    the engine's output. With std::sort in its place the outputs differ in the order of equal curve codes only (test_filter_cpu.py)."""
+    from tests.conftest import have_reference_build
+    if not have_reference_build():
+        pytest.skip("oracle/_ref not built")
+    from oracle import refvamp
+    pts = synth.shelf_cloud(1 << 20, seed=7)
+    o = np.array([0, 0, 0.4], np.float32)
+    got = ctx.filter_pointcloud(pts, 0.012, 1.5, o, o - 1.5, o + 1.5, True)
+    want = refvamp.filter_pointcloud(pts, 0.012, 1.5, o, o - 1.5, o + 1.5, True, stable_ties=True)
+    np.testing.assert_array_equal(got, want)
+
+
 def test_everything_culled_duplicates_and_empty(ctx):
     o = np.zeros(3, np.float32)
     far = np.full((100, 3), 5.0, np.float32)

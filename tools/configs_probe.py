@@ -167,6 +167,12 @@ def c4(ctx, n_motions):
         line["reference_pipeline_on_reference_filtered_cloud"] = {"filtered_points": int(len(ref_kept)), "sample": sample,
                                                                   "decisions_differing_from_gpu": int((rv != got[:sample]).sum()),
                                                                   "gpu_valid_reference_invalid": int(((got[:sample] == 1) & (rv == 0)).sum())}
+        # ... and the same reference code with its (absent) pdqsort replaced by a STABLE sort instead of std::sort: ties keep their
+        # previous order, which is the order the engine defines -- the outputs must then be equal point for point
+        o = np.array([0, 0, 0.4], np.float32)
+        st_kept = refvamp.filter_pointcloud(pts, 0.012, 1.5, o, o - 1.5, o + 1.5, True, stable_ties=True)
+        line["reference_filter_with_stable_ties"] = {"filtered_points": int(len(st_kept)),
+                                                     "equals_gpu_output": bool(st_kept.shape == kept.shape and (st_kept == kept).all())}
     return line
 
 
