@@ -381,6 +381,16 @@ def main():
                                       "achieved": dense_t, "frac": dense_t / peak, "states_per_sec": len(rep) * 64 / (ms_dense * 1e-3),
                                       "achieved_is": "executed FP32 flops (ncu)" if dflops else "W_ref (oracle-counted reference flops; no ncu count for this build)"},
                             "peak_source": "b200mp_fp32_peak FFMA microbenchmark on this GPU (nominal 148*128*2*1.965 GHz = 74.4)"}
+        # what actually bounds the grid variant: instruction issue. Executed warp instructions per launch (ncu smsp__inst_executed.sum, same
+        # record) / time against the issue slots of the chip (SMs x 4 schedulers x SM clock).
+        if rec and rec.get("inst_executed"):
+            sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+            slots = sm_count * 4 * 1.965e9
+            for name, tgt, ms_k, r_ in (("issue", line["roofline"], ms_av, rec), ("issue", line["roofline"]["dense"], ms_dense, rec.get("dense") or {})):
+                if r_.get("inst_executed"):
+                    rate = float(r_["inst_executed"]) / (ms_k * 1e-3)
+                    tgt[name] = {"warp_inst_per_launch": float(r_["inst_executed"]), "achieved_ginst_s": rate / 1e9, "peak_ginst_s": slots / 1e9,
+                                 "frac": rate / slots, "peak_is": f"{sm_count} SMs x 4 schedulers x 1.965 GHz"}
         if not args.no_cpu_baseline:
             chk, kind = checker_env(scene)
             sample = 1 << 18

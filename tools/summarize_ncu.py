@@ -49,6 +49,7 @@ def flops(path, facts_path):
     out = dict(facts)
     out.update(flops_per_launch=2 * ffma + fadd + fmul, ffma=ffma, fadd=fadd, fmul=fmul, duration_ns_under_ncu=m.get("gpu__time_duration.sum"),
                dram_bytes=m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0),
+               inst_executed=m.get("smsp__inst_executed.sum"), inst_fma_pipe=m.get("sm__inst_executed_pipe_fma.sum"),
                source="ncu smsp__sass_thread_inst_executed_op_{ffma,fadd,fmul}_pred_on.sum, tools/profile_target.py launch #2")
     if len(ids) > 3:  # launch #3: the same motions through the ordered scan (dense variant)
         d = by_id[ids[3]]
