@@ -312,14 +312,21 @@ __device__ __forceinline__ unsigned kd_fkey(float f) {  // order-preserving floa
 }
 __device__ __forceinline__ float kd_unfkey(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
-// ext[2 * j] = min key, ext[2 * j + 1] = max key of coordinate j over the rows
-__global__ void knn_kd_extent_kernel(const float *__restrict__ rows, long long n, int fw, int dim, unsigned *__restrict__ ext) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+__global__ void knn_kd_extent_init_kernel(unsigned *__restrict__ ext, int dim) {
+    const int j = threadIdx.x;
+    if (j < dim) { ext[2 * j] = 0xffffffffu; ext[2 * j + 1] = 0u; }
+}
+
+// ext[2 * j] = min key, ext[2 * j + 1] = max key of coordinate j over the rows (grid-stride; one pair of atomics per block and coordinate)
+__global__ void __launch_bounds__(256) knn_kd_extent_kernel(const float *__restrict__ rows, long long n, int fw, int dim, unsigned *__restrict__ ext) {
+    __shared__ unsigned s_lo[kKdMaxDim], s_hi[kKdMaxDim];
+    if (threadIdx.x < kKdMaxDim) { s_lo[threadIdx.x] = 0xffffffffu; s_hi[threadIdx.x] = 0u; }
+    __syncthreads();
     for (int j = 0; j < dim; ++j) {
         unsigned lo = 0xffffffffu, hi = 0u;
-        if (i < n) {
+        for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
             const float v = rows[i * fw + j];
-            if (isfinite(v)) { lo = kd_fkey(v); hi = lo; }
+            if (isfinite(v)) { const unsigned key = kd_fkey(v); lo = min(lo, key); hi = max(hi, key); }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -327,9 +334,14 @@ __global__ void knn_kd_extent_kernel(const float *__restrict__ rows, long long n
             hi = max(hi, __shfl_xor_sync(kFullMask, hi, o));
         }
         if ((threadIdx.x & 31) == 0 && lo <= hi) {
-            atomicMin(ext + 2 * j, lo);
-            atomicMax(ext + 2 * j + 1, hi);
+            atomicMin(&s_lo[j], lo);
+            atomicMax(&s_hi[j], hi);
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < dim && s_lo[threadIdx.x] <= s_hi[threadIdx.x]) {
+        atomicMin(ext + 2 * threadIdx.x, s_lo[threadIdx.x]);
+        atomicMax(ext + 2 * threadIdx.x + 1, s_hi[threadIdx.x]);
     }
 }
 
@@ -362,6 +374,30 @@ __global__ void knn_kd_hist_kernel(const float *__restrict__ rows, long long n, 
     int bin = 0;
     if (hi > lo) bin = min(max(static_cast<int>((x - lo) / (hi - lo) * kKdBins), 0), kKdBins - 1);
     atomicAdd(hist + static_cast<size_t>(nd) * kKdBins + bin, 1u);
+}
+
+// the same for the shallow levels (<= 32 nodes: the whole histogram fits shared memory): grid-stride blocks count in shared memory and
+// flush once -- a million rows hammering a few hundred global counters is what made these levels the slowest
+constexpr int kKdSmemLevels = 5;
+__global__ void __launch_bounds__(512) knn_kd_hist_smem_kernel(const float *__restrict__ rows, long long n, int fw, int dim, const int *__restrict__ node,
+                                                               const int *__restrict__ dims, int l, const float *__restrict__ boxes,
+                                                               unsigned *__restrict__ hist) {
+    __shared__ unsigned s_h[(1 << kKdSmemLevels) * kKdBins];
+    const int cells = (1 << l) * kKdBins;
+    for (int t = threadIdx.x; t < cells; t += blockDim.x) s_h[t] = 0u;
+    __syncthreads();
+    const int d = dims[l];
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int nd = node[i];
+        const float lo = boxes[(static_cast<size_t>(nd) * dim + d) * 2], hi = boxes[(static_cast<size_t>(nd) * dim + d) * 2 + 1];
+        const float x = rows[i * fw + d];
+        int bin = 0;
+        if (hi > lo) bin = min(max(static_cast<int>((x - lo) / (hi - lo) * kKdBins), 0), kKdBins - 1);
+        atomicAdd(&s_h[nd * kKdBins + bin], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < cells; t += blockDim.x)
+        if (s_h[t]) atomicAdd(hist + t, s_h[t]);
 }
 
 // one thread per node of level l: split value + the two child boxes (level l + 1)
@@ -1441,19 +1477,18 @@ int knn_build_index(b200mp_knn *k, cudaStream_t st) {
     unsigned *ext = reinterpret_cast<unsigned *>(t + 2 * a_n + 2 * a_p + a_hist + 2 * a_box);
     const unsigned nb = static_cast<unsigned>((n + 255) / 256);
     // ---- split planes, level by level (cell[] doubles as the per-row node index while the tree grows)
-    {
-        unsigned init[2 * kKdMaxDim];
-        for (int j = 0; j < kKdMaxDim; ++j) { init[2 * j] = 0xffffffffu; init[2 * j + 1] = 0u; }
-        B200_CUDA(cudaMemcpyAsync(ext, init, sizeof(unsigned) * 2 * dim, cudaMemcpyHostToDevice, st));
-        B200_CUDA(cudaStreamSynchronize(st));  // `init` is on the stack
-    }
-    knn_kd_extent_kernel<<<nb, 256, 0, st>>>(k->d_feat, n, fw, dim, ext);
+    const unsigned nb_stride = static_cast<unsigned>(std::min<long long>(nb, 4LL * k->ctx->sm_count));
+    knn_kd_extent_init_kernel<<<1, 32, 0, st>>>(ext, dim);  // (no host round trip: the build stays asynchronous)
+    knn_kd_extent_kernel<<<nb_stride, 256, 0, st>>>(k->d_feat, n, fw, dim, ext);
     knn_kd_plan_kernel<<<1, 1, 0, st>>>(ext, dim, L, k->ix_dims, box_a);
     B200_CUDA(cudaMemsetAsync(cell, 0, static_cast<size_t>(n) * 4, st));
     long long launches = 2;
     for (int l = 0; l < L; ++l) {
         B200_CUDA(cudaMemsetAsync(hist, 0, (static_cast<size_t>(1) << l) * kKdBins * 4, st));
-        knn_kd_hist_kernel<<<nb, 256, 0, st>>>(k->d_feat, n, fw, dim, cell, k->ix_dims, l, box_a, hist);
+        if (l <= kKdSmemLevels)
+            knn_kd_hist_smem_kernel<<<std::min<unsigned>((nb + 1) / 2, 2u * k->ctx->sm_count), 512, 0, st>>>(k->d_feat, n, fw, dim, cell, k->ix_dims, l, box_a, hist);
+        else
+            knn_kd_hist_kernel<<<nb, 256, 0, st>>>(k->d_feat, n, fw, dim, cell, k->ix_dims, l, box_a, hist);
         knn_kd_split_kernel<<<((1 << l) + 63) / 64, 64, 0, st>>>(hist, l, dim, k->ix_dims, box_a, box_b, k->ix_splits);
         knn_kd_descend_kernel<<<nb, 256, 0, st>>>(k->d_feat, n, fw, cell, k->ix_dims, l, k->ix_splits);
         std::swap(box_a, box_b);
