@@ -937,9 +937,12 @@ __device__ __noinline__ bool fine_pair_cold(const Scene *scp, const SharedViews 
 // touches; a pair: do the bounding spheres touch); the streamed frame is then brought to the task's frame at the ONE place this
 // function steps frames; then the fine spheres are tested (a link: two at a time against the remembered obstacles). One copy of the
 // frame code and of every loop: the hot code of these kernels has to fit the 32 KB instruction cache.
-template <class R, int G, bool EDGE, bool KILL, int BT, bool SLICED = false>
+// PRE: only the first part of the table -- the forward pass and the DISTAL half of the links against the environment. A state that
+// fails it is invalid; one that passes needs the whole check (see launch_states: large batches of unrelated states are sifted first).
+template <class R, int G, bool EDGE, bool KILL, int BT, bool SLICED = false, bool PRE = false>
 __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
                                  const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill, Share<SLICED> share = {}) {
+    constexpr int kTaskEnd = PRE ? R::kFrames + (R::kLinks + 1) / 2 : R::kTasks;
     const typename R::Tables &tb = R::tables();
     bool alive = active;
     trig_to_slots<R, BT>(q, slots);
@@ -949,7 +952,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
     bool need = false;  // lanes taking part in the fine tests of the current link / pair
     int hits = 0;
 #pragma unroll 1
-    for (int t = 0; t < R::kTasks; ++t) {
+    for (int t = 0; t < kTaskEnd; ++t) {
         const RobotTask tk = tb.tasks[t];
         const int kind = static_cast<int>(tk.kind);
         // (a sliced check: this warp's share of the links and pairs; both halves of a pair fall to the same share)
@@ -1201,13 +1204,14 @@ __device__ __noinline__ bool attachment_hit(const float *__restrict__ slots, con
     return hit;
 }
 
-template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT, bool KILL = false, bool SLICED = false>
+template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT, bool KILL = false, bool SLICED = false, bool PRE = false>
 __device__ __forceinline__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
                                             const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill = 0u,
                                             Share<SLICED> share = {}) {
-    bool good = GRID ? check_state_grid<R, G, EDGE, KILL, BT, SLICED>(q, sd, sc, slots, lv, sv, active, kill, share)
+    static_assert(!PRE || GRID, "the sifting pass exists for the candidate-grid variant only");
+    bool good = GRID ? check_state_grid<R, G, EDGE, KILL, BT, SLICED, PRE>(q, sd, sc, slots, lv, sv, active, kill, share)
                      : check_state_ordered<R, G, EDGE, KILL, MASKED, BT, SLICED>(q, sd, sc, slots, active, kill, share);
-    if (sd.n_att > 0 && share.mine(0u)) {
+    if (!PRE && sd.n_att > 0 && share.mine(0u)) {
         // (an EDGE pass that already has a hit is over: its caller drops the motion)
         if (EDGE && __any_sync(kFull, active && !good)) return good;
         const bool alive = active && good;
@@ -1618,10 +1622,14 @@ static __global__ void __launch_bounds__(256) bucket_scatter_kernel(const unsign
 
 // One lane per state: VampStateValidityChecker::isValid = validate_motion<Robot, rake, 1>(q, q), i.e. one fkcc on
 // 8 identical lanes (src/ompl/vamp/VampStateValidityChecker.h:37-41) -> group size 1 here.
-template <class R, bool MASKED, bool GRID>
+// PRE: the sifting pass (check_state_grid<..., PRE>). m_dev (optional): the number of states to visit, read on the device (the survivors
+// of a sifting pass are counted there).
+template <class R, bool MASKED, bool GRID, bool PRE = false>
 __global__ void __launch_bounds__(state_threads<R>(), state_blocks_per_sm<R>())
 validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, uint8_t *__restrict__ valid, LaunchCounters *cnt,
-                       const unsigned *__restrict__ order) {
+                       const unsigned *__restrict__ order, const unsigned *__restrict__ m_dev) {
+    if (m_dev != nullptr) m = static_cast<long long>(*m_dev);
+    if (m == 0) return;
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long bar;
     __shared__ SphereLevels<R> lv;
@@ -1648,9 +1656,34 @@ validate_states_kernel(SceneDesc sd, const float *__restrict__ qs, long long m, 
 #pragma unroll
         for (int j = 0; j < D; ++j) q[j] = active ? __ldg(qs + i * D + j) : 0.0f;
         // validate_vector with start == goal: block = q + 0 * percents
-        const bool good = check_state<R, 1, false, MASKED, GRID, state_threads<R>()>(q, sd, sc, slots, lv, sv, active);
+        const bool good = check_state<R, 1, false, MASKED, GRID, state_threads<R>(), false, false, PRE>(q, sd, sc, slots, lv, sv, active);
         if (active) valid[i] = good ? 1 : 0;
     }
+}
+
+// survivors of a sifting pass, in the order they were visited (block by block: neighbours stay neighbours, so the warps of the full
+// pass still hold similar configurations); out[0 .. *count)
+static __global__ void __launch_bounds__(256) sift_survivors_kernel(const uint8_t *__restrict__ flags, const unsigned *__restrict__ order, long long m,
+                                                                    unsigned *__restrict__ out, unsigned *__restrict__ count) {
+    __shared__ unsigned s_warp[8], s_base;
+    const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned id = 0;
+    bool keep = false;
+    if (p < m) {
+        id = order != nullptr ? __ldg(order + p) : static_cast<unsigned>(p);
+        keep = flags[id] != 0;
+    }
+    const unsigned b = __ballot_sync(kFull, keep);
+    if (lane == 0) s_warp[w] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int i = 0; i < 8; ++i) { const unsigned c = s_warp[i]; s_warp[i] = tot; tot += c; }
+        s_base = tot ? atomicAdd(count, tot) : 0u;
+    }
+    __syncthreads();
+    if (keep) out[s_base + s_warp[w] + __popc(b & ((1u << lane) - 1u))] = id;
 }
 
 }  // namespace b200mp

@@ -102,9 +102,36 @@ int launch_states(b200mp_ctx *c, const SceneDesc &desc, const float *d_q, int64_
     if (per_sm < 1) return fail(B200MP_ERR_CAPACITY, "validate_states: kernel does not fit on an SM with %zu B of scene", smem);
     const long long warps_needed = (m + 31) / 32, wpb = state_threads<R>() / 32;
     const long long blocks = std::max<long long>(1, std::min<long long>(static_cast<long long>(c->sm_count) * per_sm, (warps_needed + wpb - 1) / wpb));
+    // Large batches of unrelated states (the roadmap sampler's candidates: most are invalid, yet nearly every warp holds a valid one and
+    // runs the whole check with most lanes idle) are SIFTED first: a pass over the distal half of the links only, then the whole check
+    // for the survivors, packed. Same decisions (a state that fails part of the check is invalid).
+    static const bool sift_env = !(getenv("B200MP_SIFT") && atoi(getenv("B200MP_SIFT")) == 0);
+    if (desc.n_grid > 0 && m >= (1 << 16) && m < 0xfffffff0LL && sift_env) {
+        auto pre = validate_states_kernel<R, false, true, true>;
+        int per_pre = 0;
+        if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(pre), state_threads<R>(), smem, &per_pre))) return rc;
+        if (per_pre >= 1) {
+            char *tmp = nullptr;
+            B200_CUDA(cudaMallocAsync(&tmp, static_cast<size_t>(m) * 4 + 256, st));
+            unsigned *count = reinterpret_cast<unsigned *>(tmp), *list = reinterpret_cast<unsigned *>(tmp + 256);
+            LaunchCounters *cnt1 = next_counter(c), *cnt2 = next_counter(c);
+            cudaMemsetAsync(cnt1, 0, sizeof(LaunchCounters), st);
+            cudaMemsetAsync(cnt2, 0, sizeof(LaunchCounters), st);
+            cudaMemsetAsync(count, 0, sizeof(unsigned), st);
+            const long long pre_blocks = std::max<long long>(1, std::min<long long>(static_cast<long long>(c->sm_count) * per_pre, (warps_needed + wpb - 1) / wpb));
+            pre<<<static_cast<unsigned>(pre_blocks), state_threads<R>(), smem, st>>>(desc, d_q, m, d_valid, cnt1, d_order, nullptr);
+            sift_survivors_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(d_valid, d_order, m, list, count);
+            kern<<<static_cast<unsigned>(blocks), state_threads<R>(), smem, st>>>(desc, d_q, m, d_valid, cnt2, list, count);
+            cudaError_t e = cudaGetLastError();
+            cudaFreeAsync(tmp, st);
+            if (e != cudaSuccess) return fail(B200MP_ERR_CUDA, "validate_states (sifted) launch failed: %s", cudaGetErrorString(e));
+            c->launches.fetch_add(3);
+            return B200MP_OK;
+        }
+    }
     LaunchCounters *cnt = next_counter(c);
     B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(LaunchCounters), st));
-    kern<<<static_cast<unsigned>(blocks), state_threads<R>(), smem, st>>>(desc, d_q, m, d_valid, cnt, d_order);
+    kern<<<static_cast<unsigned>(blocks), state_threads<R>(), smem, st>>>(desc, d_q, m, d_valid, cnt, d_order, nullptr);
     B200_CUDA(cudaGetLastError());
     c->launches.fetch_add(1);
     return B200MP_OK;

@@ -89,6 +89,21 @@ def test_attachment_seeded_vs_oracle_with_cloud_and_terrain(ctx):
     assert_validity_parity(ctx.validate_motions("fetch", env, q0, q1), want, clr_motions(pe, "fetch", q0, q1), "motions")
 
 
+def test_large_state_batches_are_sifted_with_the_same_decisions(ctx):
+    """Batches of >= 2^16 states on a candidate-grid scene go through the sifting pass + packed full pass (launch_states): decisions
+    equal the oracle's, and equal the unsifted path's on the same states in smaller batches."""
+    scene = synth.clutter_scene(seed=31, n_spheres=300, n_cuboids=300, n_capsules=60, n_zcuboids=60, n_zcapsules=60)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+    pe = synth.fill_env(port.PortEnvironment(), scene)
+    q = synth.uniform_states("panda", 100000, 23)
+    got = ctx.validate_states("panda", env, q)
+    small = np.concatenate([ctx.validate_states("panda", env, q[i:i + 20000]) for i in range(0, len(q), 20000)])
+    np.testing.assert_array_equal(got, small)
+    assert 0.02 < got.mean() < 0.98
+    want = pe.validate_states("panda", q, nthreads=8)
+    assert_validity_parity(got, want, clr_states(pe, "panda", q), "sifted states")
+
+
 def test_demo_known_answers(ctx):
     env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
     assert list(ctx.validate_states("panda", env, [synth.CAGE_START, synth.CAGE_GOAL])) == [1, 1]
