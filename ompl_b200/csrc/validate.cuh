@@ -557,18 +557,12 @@ __device__ __forceinline__ bool capt_collides_warp(const CaptView &t, float x, f
     return hit;
 }
 
-template <int T, int POLICY>
-__device__ __forceinline__ bool scan_pointclouds(const SceneDesc &d, const Tile<T> &s, bool participating) {
+// every tree for one sphere, inlined: the ordered-scan variant has exactly two sites of it (a link's bounding sphere, and ONE rolled
+// loop over its fine spheres) -- the tree query is ~250 instructions, five inlined copies of it (a bounding sphere + a tile of four fine
+// spheres) had pushed the Fetch kernel's hot code to 40 KB, past the instruction cache. `pcs`: the block's shared copy of the views.
+__device__ __forceinline__ bool pointclouds_inline(const CaptView *pcs, int n_pc, float x, float y, float z, float r, bool on, bool any_mode) {
     bool hit = false;
-    for (int p = 0; p < d.n_pc; ++p) {
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            // idle slots carry ext = -inf
-            const bool on = participating && s.ext[t] > -1e30f && !hit;
-            if (POLICY == kAnyHit && __any_sync(kFull, hit)) return hit;
-            hit |= capt_collides_warp(d.pc[p], s.x[t], s.y[t], s.z[t], s.r[t], on, POLICY == kAnyHit);
-        }
-    }
+    for (int p = 0; p < n_pc; ++p) hit |= capt_collides_warp(pcs[p], x, y, z, r, on && !hit, any_mode);
     return hit;
 }
 
@@ -715,16 +709,26 @@ __device__ __forceinline__ bool self_collision(const float *__restrict__ slots, 
         const int ab = tb.link_begin[la], ae = tb.link_begin[la + 1];
         const int bb = tb.link_begin[lb], be = tb.link_begin[lb + 1];
         bool fhit = false;
-        // Fine spheres of link a one at a time. Each is first tested against link b's bounding sphere, inflated by
-        // 0.1 mm: the bounding sphere contains every fine sphere of b (to 1e-8 m, checked when the tables are
-        // generated), so a fine-fine contact implies this test is negative and skipping on a non-negative value
+        // The pair's fine spheres in link b's frame (as in check_state_grid): Rel = F^-1 * A carries a's spheres there once, b's are
+        // then the table's frame-local constants (a rigid transform keeps distances, to rounding). Each sphere of a is first tested
+        // against b's bounding sphere, inflated by 0.1 mm: the bounding sphere contains every fine sphere of b (to 1e-8 m, checked
+        // when the tables are generated), so a fine-fine contact implies this test is negative and skipping on a non-negative value
         // cannot change a decision. Only the few spheres that pass are run against b's fine spheres.
+        Frame Rel;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float dt0 = A.t[0] - F.t[0], dt1 = A.t[1] - F.t[1], dt2 = A.t[2] - F.t[2];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Rel.r[3 * i + j] = fmaf(F.r[6 + i], A.r[6 + j], fmaf(F.r[3 + i], A.r[3 + j], F.r[i] * A.r[j]));
+            Rel.t[i] = fmaf(F.r[6 + i], dt2, fmaf(F.r[3 + i], dt1, F.r[i] * dt0));
+        }
+        const float4 cb = tb.coarse[lb];
 #pragma unroll 1
         for (int i = ab; i < ae; ++i) {
             const float4 al = tb.fine[i];
             float qx, qy, qz;
-            frame_apply(A, al.x, al.y, al.z, qx, qy, qz);
-            const float xs0 = qx - bx, ys0 = qy - by, zs0 = qz - bz;
+            frame_apply(Rel, al.x, al.y, al.z, qx, qy, qz);
+            const float xs0 = qx - cb.x, ys0 = qy - cb.y, zs0 = qz - cb.z;
             const float rs0 = al.w + rb + 1.0e-4f;
             const bool cand = (fmaf(-rs0, rs0, fmaf(zs0, zs0, fmaf(ys0, ys0, xs0 * xs0))) < 0.0f) && need && !fhit;
             if (!__any_sync(kFull, cand)) continue;
@@ -732,9 +736,7 @@ __device__ __forceinline__ bool self_collision(const float *__restrict__ slots, 
 #pragma unroll 2
             for (int j = bb; j < be; ++j) {
                 const float4 fl = tb.fine[j];
-                float px, py, pz;
-                frame_apply(F, fl.x, fl.y, fl.z, px, py, pz);
-                const float xs2 = qx - px, ys2 = qy - py, zs2 = qz - pz;
+                const float xs2 = qx - fl.x, ys2 = qy - fl.y, zs2 = qz - fl.z;
                 const float rs2 = al.w + fl.w;
                 acc |= __float_as_int(fmaf(-rs2, rs2, fmaf(zs2, zs2, fmaf(ys2, ys2, xs2 * xs2))));
             }
@@ -782,8 +784,8 @@ __device__ __forceinline__ void fk_to_slots(const float (&q)[R::kDim], float *__
 // sin / cos) and its fine spheres tested. Phase C: self_collision().
 // This is the ordered-scan variant (scenes without a candidate grid: small or unsorted).
 template <class R, int G, bool EDGE, bool KILL, bool MASKED, int BT, bool SLICED = false>
-__device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots, bool active,
-                                    unsigned kill, Share<SLICED> share = {}) {
+__device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots, const CaptView *pcs,
+                                    bool active, unsigned kill, Share<SLICED> share = {}) {
     constexpr int FT = 4;  // fine spheres processed together per lane
     constexpr int POLICY = EDGE ? kAnyHit : kUntilAllHit;
     const typename R::Tables &tb = R::tables();
@@ -805,14 +807,16 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
         if (!alive) { c.x[0] = kIdle; c.y[0] = kIdle; c.z[0] = kIdle; }  // idle lanes must never raise the sign bit
         bool chit = scan_scene<1, kUntilAllHit, MASKED>(sc, c, alive);
         if (sd.n_hf > 0 && alive && !chit) chit = heightfields_hit(sd, c.x[0], c.y[0], c.z[0], cl.w);
-        if (sd.n_pc > 0) chit |= scan_pointclouds<1, kUntilAllHit>(sd, c, alive && !chit);
+        if (sd.n_pc > 0) chit |= pointclouds_inline(pcs, sd.n_pc, c.x[0], c.y[0], c.z[0], cl.w, alive && !chit, false);
         const bool need = group_any<G>(chit && alive) && alive;
         if (!__any_sync(kFull, need)) continue;
         frame_seek<R, BT, true>(F, have, tb.link_frame[l], slots);
         const int fb = tb.link_begin[l], fe = tb.link_begin[l + 1];
-        bool fhit = false;
+        bool fhit = false, settled = false;  // settled: every lane that takes part has its hit -- nothing left to find for this link
+        // fine spheres against the primitives and height fields, four at a time (skipped when the scene has neither: point clouds only)
+        const bool prims = (sc.n_sph | sc.n_cap | sc.n_zcap | sc.n_cub | sc.n_zcub) != 0 || sd.n_hf > 0;
 #pragma unroll 1
-        for (int f0 = fb; f0 < fe; f0 += FT) {
+        for (int f0 = fb; prims && f0 < fe; f0 += FT) {
             Tile<FT> s;
 #pragma unroll
             for (int t = 0; t < FT; ++t) {
@@ -831,12 +835,28 @@ __device__ bool check_state_ordered(const float (&q)[R::kDim], const SceneDesc &
                 for (int t = 0; t < FT; ++t)
                     if (need && !fhit && s.ext[t] > -1e30f) fhit = heightfields_hit(sd, s.x[t], s.y[t], s.z[t], s.r[t]);
             }
-            if (sd.n_pc > 0) fhit |= scan_pointclouds<FT, POLICY>(sd, s, need && !fhit);
             if (EDGE) {
                 if (__any_sync(kFull, fhit)) return !fhit;
             } else {
                 if (KILL) fhit = (__ballot_sync(kFull, fhit) & kill) != 0u;
-                if (__all_sync(kFull, fhit || !need)) break;
+                if (__all_sync(kFull, fhit || !need)) { settled = true; break; }
+            }
+        }
+        // ... and against the point-cloud trees, one at a time (one inlined copy of the tree query)
+        if (sd.n_pc > 0 && !settled) {
+#pragma unroll 1
+            for (int f = fb; f < fe; ++f) {
+                const float4 fl = tb.fine[f];
+                float x, y, z;
+                frame_apply(F, fl.x, fl.y, fl.z, x, y, z);
+                const bool on = need && !fhit;
+                fhit |= pointclouds_inline(pcs, sd.n_pc, x, y, z, fl.w, on, POLICY == kAnyHit) && on;
+                if (EDGE) {
+                    if (__any_sync(kFull, fhit)) return !fhit;
+                } else {
+                    if (KILL) fhit = (__ballot_sync(kFull, fhit) & kill) != 0u;
+                    if (__all_sync(kFull, fhit || !need)) break;
+                }
             }
         }
         if (fhit) alive = false;
@@ -1210,7 +1230,7 @@ __device__ __forceinline__ bool check_state(const float (&q)[R::kDim], const Sce
                                             Share<SLICED> share = {}) {
     static_assert(!PRE || GRID, "the sifting pass exists for the candidate-grid variant only");
     bool good = GRID ? check_state_grid<R, G, EDGE, KILL, BT, SLICED, PRE>(q, sd, sc, slots, lv, sv, active, kill, share)
-                     : check_state_ordered<R, G, EDGE, KILL, MASKED, BT, SLICED>(q, sd, sc, slots, active, kill, share);
+                     : check_state_ordered<R, G, EDGE, KILL, MASKED, BT, SLICED>(q, sd, sc, slots, sv.pc, active, kill, share);
     if (!PRE && sd.n_att > 0 && share.mine(0u)) {
         // (an EDGE pass that already has a hit is over: its caller drops the motion)
         if (EDGE && __any_sync(kFull, active && !good)) return good;
@@ -1260,7 +1280,8 @@ constexpr int kStateThreads = 256, kStateBlocksPerSM = 2;
 // the motion kernel's block: as many warps as keep the per-thread slots within ~160 KB (Baxter: 33 links + 14 joints)
 template <class R>
 __host__ __device__ constexpr int motion_threads() {
-    return lane_slots<R>() * B200MP_MOTION_THREADS * 4 <= 172 * 1024 ? B200MP_MOTION_THREADS : (lane_slots<R>() * 384 * 4 <= 160 * 1024 ? 384 : 256);
+    return lane_slots<R>() * B200MP_MOTION_THREADS * 4 <= 172 * 1024 ? B200MP_MOTION_THREADS
+           : (lane_slots<R>() * 512 * 4 <= 160 * 1024 ? 512 : (lane_slots<R>() * 384 * 4 <= 160 * 1024 ? 384 : 256));
 }
 
 // the state kernel's block: one block of 20 warps where the robot's slots allow it, else two blocks of 8 warps
