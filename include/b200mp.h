@@ -170,8 +170,10 @@ int64_t b200mp_launch_count(const b200mp_ctx *ctx);
  * launch and one stream synchronise per call (~30 us). A session keeps ONE small block resident on the GPU -- the scene staged in its
  * shared memory -- polling a mailbox in mapped host memory: a call writes the two configurations and a sequence number and spins on the
  * answer. Decisions are those of b200mp_validate_motions (same states, same tests). The kernel leaves by itself after 50 ms without
- * a call (B200MP_SESSION_IDLE_MS) and is restarted by the next one, so an idle session holds no SM. A session is a snapshot of the
- * committed environment at open time (re-open it after changing the scene or the attachment); calls on one session are serialised. */
+ * a call (B200MP_SESSION_IDLE_MS) and is restarted by the next one, so an idle session holds no SM. A session reads the committed
+ * environment's device arrays: while one is open, b200mp_env_commit and b200mp_env_set_attachment on that environment fail with
+ * B200MP_ERR_STATE (close the session, change the scene, open a new one); destroy sessions before their environment. Calls on one
+ * session are serialised. */
 int b200mp_session_open(b200mp_ctx *ctx, int robot, const b200mp_env *env, b200mp_session **out);
 void b200mp_session_close(b200mp_session *session);
 /* q0, q1[dim]; resolution 0 = the robot's default. */

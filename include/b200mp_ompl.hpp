@@ -372,8 +372,8 @@ namespace ompl::b200
         }
 
         /// Serial planners (RRT-Connect ...): answer single checkMotion calls from a kernel that stays resident on the GPU
-        /// (b200mp_session_*: no launch and no synchronise per call). Same decisions. The session is a snapshot of the environment as
-        /// committed now; call again after changing the scene or the attachment. Calls from several threads are serialised.
+        /// (b200mp_session_*: no launch and no synchronise per call). Same decisions. While the session is open the environment cannot be
+        /// re-committed or given another attachment (useSession(false) first). Calls from several threads are serialised.
         void useSession(bool on = true)
         {
             session_.reset();

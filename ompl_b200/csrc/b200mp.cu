@@ -105,6 +105,7 @@ struct b200mp_env {
     bool use_grid = true;
     SceneDesc desc{};
     bool committed = false;
+    mutable std::atomic<int> open_sessions{0};  // resident kernels reading this environment's device arrays (b200mp_session_*)
 };
 
 namespace {
@@ -459,6 +460,9 @@ void b200mp_env_destroy(b200mp_env *e) {
 // or after commit: the attachment lives in its own device buffer, so grasping / releasing an object does not re-upload the scene.
 int b200mp_env_set_attachment(b200mp_env *e, const float *tf, const float *xyzr, int n) {
     if (!e || n < 0 || (n > 0 && (!tf || !xyzr))) return fail(B200MP_ERR_INVALID, "b200mp_env_set_attachment: bad argument");
+    if (e->open_sessions.load() > 0)
+        return fail(B200MP_ERR_STATE, "b200mp_env_set_attachment: %d session(s) are open on this environment (close them first: a resident kernel reads these arrays)",
+                    e->open_sessions.load());
     B200_CUDA(cudaSetDevice(e->ctx->device));
     if (e->d_att) B200_CUDA(cudaFree(e->d_att));  // (cudaFree waits for launches that still read it)
     e->d_att = nullptr;
@@ -736,6 +740,9 @@ int64_t b200mp_env_min_distances(const b200mp_env *e, int kind, float *out) {
 
 int b200mp_env_commit(b200mp_env *e) {
     if (!e) return fail(B200MP_ERR_INVALID, "b200mp_env_commit: env is NULL");
+    if (e->open_sessions.load() > 0)
+        return fail(B200MP_ERR_STATE, "b200mp_env_commit: %d session(s) are open on this environment (close them first: a resident kernel reads these arrays)",
+                    e->open_sessions.load());
     B200_CUDA(cudaSetDevice(e->ctx->device));
     std::vector<float> blob;
     auto align4 = [&]() { while (blob.size() % 4) blob.push_back(0.f); };
@@ -1098,6 +1105,7 @@ struct b200mp_session {
     unsigned seq = 0;
     unsigned long long idle_ns = 50ull * 1000 * 1000;
     long long relaunches = 0;
+    bool counted = false;  // registered in env->open_sessions
     std::mutex mu;
 };
 
@@ -1195,6 +1203,8 @@ int b200mp_session_open(b200mp_ctx *c, int robot, const b200mp_env *e, b200mp_se
     }
     std::memset(s->h, 0, sizeof(b200mp::SessionMailbox));
     if ((rc = session_launch(s))) { b200mp_session_close(s); return rc; }
+    e->open_sessions.fetch_add(1);
+    s->counted = true;
     *out = s;
     return B200MP_OK;
 }
@@ -1213,6 +1223,7 @@ void b200mp_session_close(b200mp_session *s) {
     }
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->h) cudaFreeHost(s->h);
+    if (s->counted) s->env->open_sessions.fetch_sub(1);
     cudaGetLastError();
     delete s;
 }

@@ -59,15 +59,25 @@ def test_session_restarts_after_idle_exit(ctx, monkeypatch):
     s.close()
 
 
-def test_two_sessions_and_attachment_snapshot(ctx):
+def test_two_sessions_and_environment_changes(ctx):
     env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
     a = ompl_b200.Session(ctx, "panda", env)
+    a2 = ompl_b200.Session(ctx, "panda", env)   # several sessions on one environment (one per planner thread)
     start = np.asarray(synth.CAGE_START, np.float32)
-    assert a.is_valid(start)
-    env.set_attachment(np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0.05]], np.float32), [[0, 0, 0.1, 0.3]])
+    assert a.is_valid(start) and a2.is_valid(start)
+    tf, ball = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0.05]], np.float32), [[0, 0, 0.1, 0.3]]
+    # a resident kernel reads the environment's arrays: changing them under it is refused, not undefined
+    for change in (lambda: env.set_attachment(tf, ball), env.commit):
+        with pytest.raises(ompl_b200.B200MPError) as e:
+            change()
+        assert e.value.code == 5  # B200MP_ERR_STATE
+    a.close()
+    a2.close()
+    env.set_attachment(tf, ball)
     b = ompl_b200.Session(ctx, "panda", env)   # opened after the grasp: sees the attachment
     assert not b.is_valid(start)
-    assert a.is_valid(start)                  # a session is a snapshot of the environment it was opened on
-    a.close()
     b.close()
     env.clear_attachment()
+    c = ompl_b200.Session(ctx, "panda", env)
+    assert c.is_valid(start)
+    c.close()
