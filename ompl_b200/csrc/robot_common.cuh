@@ -14,11 +14,13 @@ struct Frame {
 //   kTaskEnv   : link a against the environment (bounding sphere; its fine spheres when that touches something)
 //   kTaskSelfA : self-collision pair (a, b): bounding spheres; when they touch, the frame of link a is saved ...
 //   kTaskSelfB : ... and, with link b's frame, a's fine spheres (outer loop) are tested against b's
+//   kTaskGroup : link a against the sphere of pair group b (every member's bounding sphere lies inside it); not touched by any lane:
+//                the group's pair tasks, which follow, are skipped together
 // (one 32-bit word: a single constant load per task)
 struct RobotTask {
-    unsigned kind : 2, frame : 6, a : 12, b : 12;
+    unsigned kind : 3, frame : 5, a : 12, b : 12;
 };
-enum { kTaskFk = 0, kTaskEnv = 1, kTaskSelfA = 2, kTaskSelfB = 3 };
+enum { kTaskFk = 0, kTaskEnv = 1, kTaskSelfA = 2, kTaskSelfB = 3, kTaskGroup = 4 };
 
 __device__ __forceinline__ void frame_identity(Frame &F) {
     F.r[0] = 1.f; F.r[1] = 0.f; F.r[2] = 0.f;

@@ -976,6 +976,17 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
         const RobotTask tk = tb.tasks[t];
         const int kind = static_cast<int>(tk.kind);
         // (a sliced check: this warp's share of the links and pairs; both halves of a pair fall to the same share)
+        if (kind == kTaskGroup) {
+            // a group of pairs ruled out by one test: link a against the sphere that contains the bounding spheres of all the group's
+            // other links (centred on one of them)
+            const int la = tk.a, g = tk.b, lr = tb.group_ref[g];
+            const float xs = slots[(3 * la + 0) * BT] - slots[(3 * lr + 0) * BT], ys = slots[(3 * la + 1) * BT] - slots[(3 * lr + 1) * BT],
+                        zs = slots[(3 * la + 2) * BT] - slots[(3 * lr + 2) * BT];
+            const float rs = tb.coarse[la].w + tb.group_r[g];
+            const float d = fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs)));
+            if (!__any_sync(kFull, (d < 0.0f) && alive)) t += tb.group_skip[g];
+            continue;
+        }
         if (SLICED && kind != kTaskFk && !share.mine(tk.a + 3u * (kind == kTaskEnv ? 0u : tk.b))) continue;
         if (kind == kTaskEnv) {
             const int l = tk.a;

@@ -130,6 +130,74 @@ def gen_frame(em: Emitter, fr: dict, parent_is_world: bool):
         em.assign(f"F.t[{i}]", t[i])
 
 
+def model_fk(model: dict, q):
+    """world pose (R, t) of every frame of the JSON model for one configuration (float64; generator-side estimates only)."""
+    frames = model["frames"]
+    T = [None] * len(frames)
+    T[0] = (np.eye(3), np.zeros(3))
+    for fr in frames[1:]:
+        pr, pt = T[fr["parent"]]
+        a = pr @ np.asarray(fr["R"], dtype=np.float64)
+        t = pt + pr @ np.asarray(fr["t"], dtype=np.float64)
+        ax = np.asarray(fr["axis"], dtype=np.float64)
+        v = q[fr["q_index"]]
+        if fr["type"] in ("revolute", "continuous"):
+            u = ax / np.linalg.norm(ax)
+            k = np.array([[0, -u[2], u[1]], [u[2], 0, -u[0]], [-u[1], u[0], 0]])
+            a = a @ (np.eye(3) + math.sin(v) * k + (1 - math.cos(v)) * (k @ k))
+        else:
+            t = t + a @ (ax * v)
+        T[fr["id"]] = (a, t)
+    return T
+
+
+def pair_groups(model: dict, link_rows: list, pairs: list):
+    """Self-collision pairs that share one link x and whose other links live on ONE frame can be ruled out together: a sphere around
+    one member's bounding centre that contains every member's bounding sphere (same frame: a rigid set) stands for all of them. A
+    group is worth a test of its own when it usually fails to touch (estimated on random configurations) -- x's sphere not touching
+    the group sphere implies it touches no member, so skipping the members then changes nothing.
+    -> list of dict(x, ref, r, members=[pair index ...])"""
+    lo = np.float32(model["s_a"]).astype(np.float64)
+    hi = lo + np.float32(model["s_m"]).astype(np.float64)
+    rng = np.random.default_rng(20260202)
+    qs = rng.uniform(lo, hi, (300, len(lo)))
+    centre = np.zeros((len(qs), len(link_rows), 3))
+    for i, q in enumerate(qs):
+        T = model_fk(model, q)
+        for l, row in enumerate(link_rows):
+            r_, t_ = T[row["frame"]]
+            centre[i, l] = r_ @ np.asarray(row["coarse"]["c"]) + t_
+    rad = np.array([row["coarse"]["r"] for row in link_rows])
+    cand = {}
+    for pi, (a, b) in enumerate(pairs):
+        cand.setdefault((a, link_rows[b]["frame"]), []).append((pi, b))
+        cand.setdefault((b, link_rows[a]["frame"]), []).append((pi, a))
+    scored = []
+    for (x, f), mem in cand.items():
+        if len(mem) < 3:
+            continue
+        best = None
+        for _, ref in mem:
+            cr = np.asarray(link_rows[ref]["coarse"]["c"])
+            rg = max(np.linalg.norm(np.asarray(link_rows[m]["coarse"]["c"]) - cr) + rad[m] for _, m in mem)
+            if best is None or rg < best[0]:
+                best = (rg, ref)
+        rg, ref = best[0] + 1e-5, best[1]   # (margin: far above the rounding of the device-side test)
+        p_touch = float((np.linalg.norm(centre[:, x] - centre[:, ref], axis=1) < rad[x] + rg).mean())
+        saved = (1 - p_touch) * len(mem) - 1
+        if saved > 0.75:
+            scored.append((saved, x, ref, rg, [pi for pi, _ in mem]))
+    scored.sort(key=lambda g: -g[0])
+    used, groups = set(), []
+    for saved, x, ref, rg, mem in scored:
+        mem = [pi for pi in mem if pi not in used]
+        if len(mem) < 3:
+            continue
+        used.update(mem)
+        groups.append(dict(x=x, ref=ref, r=float(rg), members=mem))
+    return groups
+
+
 def gen_cuda(model: dict) -> str:
     name = model["name"]
     cname = name.capitalize()
@@ -177,13 +245,24 @@ def gen_cuda(model: dict) -> str:
     # The state check as a task list, so that ONE loop (one copy of the frame code) runs all of it: the forward pass over the frames
     # (bounding-sphere centres), the links against the environment tip -> base (the reference's order), the self-collision pairs
     # (first the frame of the link whose fine spheres run in the outer loop -- the one with fewer spheres --, then the other's).
-    T_FK, T_ENV, T_SELF_A, T_SELF_B = 0, 1, 2, 3
+    T_FK, T_ENV, T_SELF_A, T_SELF_B, T_GROUP = 0, 1, 2, 3, 4
     tasks = [(T_FK, k, frame_link_begin[k], frame_link_begin[k + 1]) for k in range(nfr)]
     tasks += [(T_ENV, link_rows[l]["frame"], l, 0) for l in range(len(link_rows) - 1, -1, -1)]
-    for a, b in pairs:
+
+    def pair_tasks(a, b):
         na, nb = link_rows[a]["end"] - link_rows[a]["begin"], link_rows[b]["end"] - link_rows[b]["begin"]
         o, i = (a, b) if na <= nb else (b, a)
-        tasks += [(T_SELF_A, link_rows[o]["frame"], o, i), (T_SELF_B, link_rows[i]["frame"], o, i)]
+        return [(T_SELF_A, link_rows[o]["frame"], o, i), (T_SELF_B, link_rows[i]["frame"], o, i)]
+
+    groups = pair_groups(model, link_rows, pairs)
+    grouped = {pi for g in groups for pi in g["members"]}
+    for pi, (a, b) in enumerate(pairs):
+        if pi not in grouped:
+            tasks += pair_tasks(a, b)
+    for gi, g in enumerate(groups):  # a group test, then its pairs (skipped together when the group sphere is not touched)
+        tasks.append((T_GROUP, 0, g["x"], gi))
+        for pi in g["members"]:
+            tasks += pair_tasks(*pairs[pi])
     att = model["attachment"]
     att_links = sorted((new_index[a] for a in att["links"]), key=lambda i: (link_rows[i]["frame"], i))
 
@@ -210,6 +289,8 @@ def gen_cuda(model: dict) -> str:
     w(f"    short frame_branch[{nfr}];          // first frame of the chain (arm) frame k belongs to; its parent is the world frame")
     w(f"    short att_links[{len(att_links)}];  // links tested against an attachment (Robot::fkcc_attach), in frame order")
     w(f"    RobotTask tasks[{len(tasks)}];       // the state check as one list of steps (see RobotTask in robot_common.cuh)")
+    w(f"    short group_ref[{max(1, len(groups))}], group_skip[{max(1, len(groups))}];  // pair groups: member whose bounding centre carries the group sphere; tasks to skip")
+    w(f"    float group_r[{max(1, len(groups))}];              // radius of the group sphere (contains every member's bounding sphere)")
     w("};")
     w("")
     w(f"__constant__ {cname}Tables k{cname}Tables = {{")
@@ -227,6 +308,9 @@ def gen_cuda(model: dict) -> str:
     w("    {" + ", ".join(str(v) for v in frame_branch) + "},")
     w("    {" + ", ".join(str(v) for v in att_links) + "},")
     w("    {" + ", ".join("{%d, %d, %d, %d}" % t for t in tasks) + "},")
+    w("    {" + (", ".join(str(g["ref"]) for g in groups) or "0") + "},")
+    w("    {" + (", ".join(str(2 * len(g["members"])) for g in groups) or "0") + "},")
+    w("    {" + (", ".join(f32(g["r"]) for g in groups) or "0.0f") + "},")
     w("};")
     w("")
     w(f"struct {cname} {{")
