@@ -667,8 +667,10 @@ __device__ __forceinline__ void frame_seek(Frame &F, int &have, int k, const flo
     have = k;
 }
 
-// Allowed self-collision pairs on the stored centres (collision/validity.hh:13-44); frames are rebuilt only for pairs
-// whose bounding spheres touch. Updates `alive`; returns true when the caller should return `result` immediately.
+// Allowed self-collision pairs on the stored centres (collision/validity.hh:13-44), run from the SAME task table as the
+// candidate-grid variant (check_state_grid holds the commented original of this loop): pair groups ruled out by one test, the frame of the
+// link with fewer fine spheres parked in the scratch slots, the fine tests in the second link's frame. Used by the ordered-scan variant.
+// Updates `alive`; returns true when the caller should return `result` immediately.
 // KILL (lane-per-state form only): lanes are grouped into motions by `kill` (the lanes that belong to the same motion as this
 // one); a hit in any of them ends the work of all of them.
 // SLICED (the resident single-call kernel, session.cuh): several warps check the SAME states, each a share of the links and pairs
@@ -683,53 +685,67 @@ struct Share<true> {
     __device__ __forceinline__ bool mine(unsigned i) const { return static_cast<int>(i % static_cast<unsigned>(nslice)) == slice; }
 };
 template <class R, int G, bool EDGE, bool KILL, int BT, bool SLICED = false>
-__device__ __forceinline__ bool self_collision(const float *__restrict__ slots, bool &alive, bool &result, unsigned kill, Share<SLICED> share = {}) {
+__device__ __forceinline__ bool self_collision(float *__restrict__ slots, bool &alive, bool &result, unsigned kill, Share<SLICED> share = {}) {
     const typename R::Tables &tb = R::tables();
+    float *scratch = slots + hit_slot<R>() * BT;
     Frame F;
     int have = -1;
+    bool need = false;
 #pragma unroll 1
-    for (int p = 0; p < R::kPairs; ++p) {
-        if (!share.mine(static_cast<unsigned>(p))) continue;
-        const int la = tb.pair_a[p], lb = tb.pair_b[p];
-        const float ra = tb.coarse[la].w, rb = tb.coarse[lb].w;
-        const float bx = slots[(3 * lb + 0) * BT], by = slots[(3 * lb + 1) * BT], bz = slots[(3 * lb + 2) * BT];
-        const float xs = slots[(3 * la + 0) * BT] - bx, ys = slots[(3 * la + 1) * BT] - by, zs = slots[(3 * la + 2) * BT] - bz;
-        const float rs = ra + rb;
-        const float d = fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs)));
-        const bool need = group_any<G>((d < 0.0f) && alive) && alive;
-        if (!__any_sync(kFull, need)) continue;
-        // frames of both links through the one chain walker: first link a's (kept in A), then link b's (pairs are ordered by
-        // the later link's frame, so F mostly moves forward)
-        Frame A;
-#pragma unroll 1
-        for (int w = 0; w < 2; ++w) {
-            frame_seek<R, BT, true>(F, have, tb.link_frame[w == 0 ? la : lb], slots);
-            if (w == 0) A = F;
+    for (int t = R::kFrames + R::kLinks; t < R::kTasks; ++t) {
+        const RobotTask tk = tb.tasks[t];
+        const int kind = static_cast<int>(tk.kind);
+        if (kind == kTaskGroup) {
+            const int la = tk.a, g = tk.b, lr = tb.group_ref[g];
+            const float xs = slots[(3 * la + 0) * BT] - slots[(3 * lr + 0) * BT], ys = slots[(3 * la + 1) * BT] - slots[(3 * lr + 1) * BT],
+                        zs = slots[(3 * la + 2) * BT] - slots[(3 * lr + 2) * BT];
+            const float rs = tb.coarse[la].w + tb.group_r[g];
+            const float d = fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs)));
+            if (!__any_sync(kFull, (d < 0.0f) && alive)) t += tb.group_skip[g];
+            continue;
         }
-        const int ab = tb.link_begin[la], ae = tb.link_begin[la + 1];
-        const int bb = tb.link_begin[lb], be = tb.link_begin[lb + 1];
-        bool fhit = false;
-        // The pair's fine spheres in link b's frame (as in check_state_grid): Rel = F^-1 * A carries a's spheres there once, b's are
-        // then the table's frame-local constants (a rigid transform keeps distances, to rounding). Each sphere of a is first tested
-        // against b's bounding sphere, inflated by 0.1 mm: the bounding sphere contains every fine sphere of b (to 1e-8 m, checked
-        // when the tables are generated), so a fine-fine contact implies this test is negative and skipping on a non-negative value
-        // cannot change a decision. Only the few spheres that pass are run against b's fine spheres.
+        if (SLICED && !share.mine(tk.a + 3u * tk.b)) continue;
+        const int la = tk.a, lb = tk.b;
+        if (kind == kTaskSelfA) {
+            const float xs = slots[(3 * la + 0) * BT] - slots[(3 * lb + 0) * BT], ys = slots[(3 * la + 1) * BT] - slots[(3 * lb + 1) * BT],
+                        zs = slots[(3 * la + 2) * BT] - slots[(3 * lb + 2) * BT];
+            const float rs = tb.coarse[la].w + tb.coarse[lb].w;
+            const float d = fmaf(-rs, rs, fmaf(zs, zs, fmaf(ys, ys, xs * xs)));
+            need = group_any<G>((d < 0.0f) && alive) && alive;
+            if (!__any_sync(kFull, need)) { ++t; continue; }
+        }
+        frame_seek<R, BT, true>(F, have, static_cast<int>(tk.frame), slots);
+        if (kind == kTaskSelfA) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) scratch[i * BT] = F.r[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) scratch[(9 + i) * BT] = F.t[i];
+            continue;
+        }
         Frame Rel;
+        {
+            Frame A;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float dt0 = A.t[0] - F.t[0], dt1 = A.t[1] - F.t[1], dt2 = A.t[2] - F.t[2];
+            for (int i = 0; i < 9; ++i) A.r[i] = scratch[i * BT];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) Rel.r[3 * i + j] = fmaf(F.r[6 + i], A.r[6 + j], fmaf(F.r[3 + i], A.r[3 + j], F.r[i] * A.r[j]));
-            Rel.t[i] = fmaf(F.r[6 + i], dt2, fmaf(F.r[3 + i], dt1, F.r[i] * dt0));
+            for (int i = 0; i < 3; ++i) A.t[i] = scratch[(9 + i) * BT] - F.t[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Rel.r[3 * i + j] = fmaf(F.r[6 + i], A.r[6 + j], fmaf(F.r[3 + i], A.r[3 + j], F.r[i] * A.r[j]));
+                Rel.t[i] = fmaf(F.r[6 + i], A.t[2], fmaf(F.r[3 + i], A.t[1], F.r[i] * A.t[0]));
+            }
         }
         const float4 cb = tb.coarse[lb];
+        const int ae = tb.link_begin[la + 1], bb = tb.link_begin[lb], be = tb.link_begin[lb + 1];
+        bool fhit = false;
 #pragma unroll 1
-        for (int i = ab; i < ae; ++i) {
+        for (int i = tb.link_begin[la]; i < ae; ++i) {
             const float4 al = tb.fine[i];
             float qx, qy, qz;
             frame_apply(Rel, al.x, al.y, al.z, qx, qy, qz);
             const float xs0 = qx - cb.x, ys0 = qy - cb.y, zs0 = qz - cb.z;
-            const float rs0 = al.w + rb + 1.0e-4f;
+            const float rs0 = al.w + cb.w + 1.0e-4f;
             const bool cand = (fmaf(-rs0, rs0, fmaf(zs0, zs0, fmaf(ys0, ys0, xs0 * xs0))) < 0.0f) && need && !fhit;
             if (!__any_sync(kFull, cand)) continue;
             int acc = 0;
