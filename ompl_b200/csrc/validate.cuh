@@ -975,7 +975,10 @@ __device__ __noinline__ bool fine_pair_cold(const Scene *scp, const SharedViews 
 // frame code and of every loop: the hot code of these kernels has to fit the 32 KB instruction cache.
 // PRE: only the first part of the table -- the forward pass and the DISTAL half of the links against the environment. A state that
 // fails it is invalid; one that passes needs the whole check (see launch_states: large batches of unrelated states are sifted first).
-template <class R, int G, bool EDGE, bool KILL, int BT, bool SLICED = false, bool PRE = false>
+// QUIT (a first look only): the check gives up once no more than QUIT lanes are still undecided -- they count as passed. A first look
+// gains nothing from states that pass (the motion kernel tests them again), and running the last few lanes of a pass to the end of
+// the task table is what its passes spent most of their time on.
+template <class R, int G, bool EDGE, bool KILL, int BT, bool SLICED = false, bool PRE = false, int QUIT = 0>
 __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
                                  const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill, Share<SLICED> share = {}) {
     constexpr int kTaskEnd = PRE ? R::kFrames + (R::kLinks + 1) / 2 : R::kTasks;
@@ -1090,7 +1093,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
                 }
             }
             if (fhit) alive = false;
-            if (!EDGE && !__any_sync(kFull, alive)) return false;
+            if (!EDGE && (QUIT > 0 ? __popc(__ballot_sync(kFull, alive)) <= QUIT : !__any_sync(kFull, alive))) return alive;
         } else if (kind == kTaskSelfA) {
             // the frame of the pair's first link waits in the scratch slots while F moves on to the second link's frame
 #pragma unroll
@@ -1148,7 +1151,7 @@ __device__ bool check_state_grid(const float (&q)[R::kDim], const SceneDesc &sd,
                 }
             }
             if (fhit) alive = false;
-            if (!EDGE && !__any_sync(kFull, alive)) return false;
+            if (!EDGE && (QUIT > 0 ? __popc(__ballot_sync(kFull, alive)) <= QUIT : !__any_sync(kFull, alive))) return alive;
         }
     }
     return alive;
@@ -1251,12 +1254,13 @@ __device__ __noinline__ bool attachment_hit(const float *__restrict__ slots, con
     return hit;
 }
 
-template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT, bool KILL = false, bool SLICED = false, bool PRE = false>
+template <class R, int G, bool EDGE, bool MASKED, bool GRID, int BT, bool KILL = false, bool SLICED = false, bool PRE = false, int QUIT = 0>
 __device__ __forceinline__ bool check_state(const float (&q)[R::kDim], const SceneDesc &sd, const Scene &sc, float *__restrict__ slots,
                                             const SphereLevels<R> &lv, const SharedViews &sv, bool active, unsigned kill = 0u,
                                             Share<SLICED> share = {}) {
     static_assert(!PRE || GRID, "the sifting pass exists for the candidate-grid variant only");
-    bool good = GRID ? check_state_grid<R, G, EDGE, KILL, BT, SLICED, PRE>(q, sd, sc, slots, lv, sv, active, kill, share)
+    static_assert(QUIT == 0 || (GRID && KILL && !EDGE), "only a first look on a grid scene may give up early");
+    bool good = GRID ? check_state_grid<R, G, EDGE, KILL, BT, SLICED, PRE, QUIT>(q, sd, sc, slots, lv, sv, active, kill, share)
                      : check_state_ordered<R, G, EDGE, KILL, MASKED, BT, SLICED>(q, sd, sc, slots, sv.pc, active, kill, share);
     if (!PRE && sd.n_att > 0 && share.mine(0u)) {
         // (an EDGE pass that already has a hit is over: its caller drops the motion)
@@ -1287,6 +1291,11 @@ constexpr int kRakeBuckets = 6;  // index 0 unused
 #define B200MP_FIRST_LANES 2
 #endif
 constexpr int kFirstLanes = B200MP_FIRST_LANES;
+// undecided lanes at which a first-look pass on a grid scene gives up (check_state_grid's QUIT)
+#ifndef B200MP_LOOK_QUIT
+#define B200MP_LOOK_QUIT 4
+#endif
+constexpr int kLookQuit = B200MP_LOOK_QUIT;
 struct BucketPlan {
     unsigned cnt[kRakeBuckets];       // motions per bucket
     unsigned off[kRakeBuckets];       // start of each bucket in the list
@@ -1365,56 +1374,77 @@ validate_motions_kernel(SceneDesc sd, const float *__restrict__ q0, const float 
         if (m == 0) return;
     }
 
+    // Queue entries are taken `take` at a time. After a first look that went on (pre_decision == 1) most entries of the list may already
+    // be invalid: a warp then takes several, each lane looks at one (list entry -> valid flag: two dependent loads) and the warp works
+    // through the ones still open -- one queue round trip and one load round trip per take instead of per entry (at 3 % open entries the
+    // skip loop was latency-bound: 2^20 entries x two round trips over 2960 warps). The take is sized from the first look's sample for
+    // about one open entry each, and so that a warp still gets eight takes or more (a larger one would only unbalance the tail);
+    // without a first look it is one entry.
+    unsigned take = 1u;
+    if (plan != nullptr && plan->pre_decision == 1u) {
+        const unsigned tested = plan->pre_tested, killed = min(plan->pre_killed, tested);
+        const unsigned per_open = tested / max(tested - killed, 1u);
+        const unsigned long long fair = static_cast<unsigned long long>(m) / (8ull * gridDim.x * (blockDim.x >> 5));
+        take = static_cast<unsigned>(min(static_cast<unsigned long long>(min(max(per_open, 1u), 32u)), max(fair, 1ull)));
+    }
     for (;;) {
-        unsigned long long e = 0;
-        if (lane == 0) e = atomicAdd(&cnt->next, 1ull);
-        e = __shfl_sync(kFull, e, 0);
-        if (e >= static_cast<unsigned long long>(m)) break;
-        if (list != nullptr) {
-            e = __ldg(list + e);
-            if (valid[e] == 0) continue;  // the first look (validate_rakes_kernel) already found it in collision
+        unsigned long long head = 0;
+        if (lane == 0) head = atomicAdd(&cnt->next, static_cast<unsigned long long>(take));
+        head = __shfl_sync(kFull, head, 0);
+        if (head >= static_cast<unsigned long long>(m)) break;
+        unsigned long long e_mine = head + static_cast<unsigned>(lane);
+        bool open = static_cast<unsigned>(lane) < take && e_mine < static_cast<unsigned long long>(m);
+        if (open && list != nullptr) {
+            e_mine = __ldg(list + e_mine);
+            open = valid[e_mine] != 0;  // else the first look (validate_rakes_kernel) already found it in collision
         }
+        unsigned pending = __ballot_sync(kFull, open);
+        while (pending != 0u) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1u;
+            const unsigned long long e = __shfl_sync(kFull, e_mine, src);
 
-        float a[D], v[D], q[D], back[D];
-        // roadmap edges address their end points in one state table (pairs != nullptr: q0 == q1 == the table)
-        unsigned long long ia = e, ib = e;
-        if (pairs != nullptr) {
-            const int2 pr = __ldg(pairs + e);
-            ia = static_cast<unsigned long long>(pr.x);
-            ib = static_cast<unsigned long long>(pr.y);
-        }
+            float a[D], v[D], q[D], back[D];
+            // roadmap edges address their end points in one state table (pairs != nullptr: q0 == q1 == the table)
+            unsigned long long ia = e, ib = e;
+            if (pairs != nullptr) {
+                const int2 pr = __ldg(pairs + e);
+                ia = static_cast<unsigned long long>(pr.x);
+                ib = static_cast<unsigned long long>(pr.y);
+            }
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            a[j] = __ldg(q0 + ia * D + j);
-            v[j] = __ldg(q1 + ib * D + j) - a[j];
-        }
-        const float dist = vamp_l2_norm<D>(v);
-        // n = max(ceil(dist / rake * resolution), 1)  (planning/validate.hh:41)
-        const float nf = fmaxf(ceilf(dist / 8.0f * static_cast<float>(resolution)), 1.0f);
-        const int n = static_cast<int>(nf);
-        const float denom = static_cast<float>(8 * n);
+            for (int j = 0; j < D; ++j) {
+                a[j] = __ldg(q0 + ia * D + j);
+                v[j] = __ldg(q1 + ib * D + j) - a[j];
+            }
+            const float dist = vamp_l2_norm<D>(v);
+            // n = max(ceil(dist / rake * resolution), 1)  (planning/validate.hh:41)
+            const float nf = fmaxf(ceilf(dist / 8.0f * static_cast<float>(resolution)), 1.0f);
+            const int n = static_cast<int>(nf);
+            const float denom = static_cast<float>(8 * n);
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            q[j] = fmaf(v[j], pct, a[j]);  // block = start + vector * percents
-            back[j] = v[j] / denom;        // backstep = vector / (rake * n)
-        }
-        // this lane's first rake: `rake_in_pass` sequential back-steps, exactly as the reference accumulates them
-        for (int r = 0; r < rake_in_pass; ++r) {
-#pragma unroll
-            for (int j = 0; j < D; ++j) q[j] = q[j] - back[j];
-        }
-        bool ok = true;
-        for (int base = 0; base < n; base += 4) {
-            const bool active = (base + rake_in_pass) < n;
-            const bool good = check_state<R, 8, true, MASKED, GRID, motion_threads<R>()>(q, sd, sc, slots, lv, sv, active);
-            if (__any_sync(kFull, active && !good)) { ok = false; break; }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int j = 0; j < D; ++j) {
+                q[j] = fmaf(v[j], pct, a[j]);  // block = start + vector * percents
+                back[j] = v[j] / denom;        // backstep = vector / (rake * n)
+            }
+            // this lane's first rake: `rake_in_pass` sequential back-steps, exactly as the reference accumulates them
+            for (int r = 0; r < rake_in_pass; ++r) {
 #pragma unroll
                 for (int j = 0; j < D; ++j) q[j] = q[j] - back[j];
             }
+            bool ok = true;
+            for (int base = 0; base < n; base += 4) {
+                const bool active = (base + rake_in_pass) < n;
+                const bool good = check_state<R, 8, true, MASKED, GRID, motion_threads<R>()>(q, sd, sc, slots, lv, sv, active);
+                if (__any_sync(kFull, active && !good)) { ok = false; break; }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) q[j] = q[j] - back[j];
+                }
+            }
+            if (lane == 0) valid[e] = ok ? 1 : 0;
         }
-        if (lane == 0) valid[e] = ok ? 1 : 0;
     }
 }
 
@@ -1536,7 +1566,8 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
             // (G = LPM: a first look's group of lanes is its motion; for scenes given unsorted the scan of a sphere then reaches no
             // further than the reference's own -- the group maximum is over a subset of the rake --, so it can only find what the
             // reference finds as well)
-            const bool good = check_state<R, LPM, false, MASKED, GRID, motion_threads<R>(), true>(q, sd, sc, slots, lv, sv, active, kill);
+            const bool good = check_state<R, LPM, false, MASKED, GRID, motion_threads<R>(), true, false, false, (FIRST && GRID) ? kLookQuit : 0>(
+                q, sd, sc, slots, lv, sv, active, kill);
             bad = group_any<LPM>(active && !good);
             if (bad && (lane & (LPM - 1)) == 0) valid[e] = 0;
         }
@@ -1599,7 +1630,9 @@ bucket_count_kernel(const float *__restrict__ q0, const float *__restrict__ q1, 
 
 // one block: bucket offsets and pass counts; blk_cnt[block][key] -> exclusive prefix over the blocks (in place)
 static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__restrict__ plan, unsigned *__restrict__ blk_cnt, int nb, int first_look) {
-    __shared__ unsigned s_part[1024][kRakeBuckets];
+    // [key][thread], one pad word per 32 threads: the scan below walks 32 consecutive partials per lane (bank = lane + i, no conflict;
+    // a [thread][key] layout put all 32 lanes of a step on one bank)
+    __shared__ unsigned s_part[kRakeBuckets][1024 + 32];
     const int t = threadIdx.x;
     const int chunk = (nb + 1023) / 1024, b0 = t * chunk, b1 = min(nb, b0 + chunk);
     unsigned sum[kRakeBuckets];
@@ -1609,12 +1642,12 @@ static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__
 #pragma unroll
         for (int k = 0; k < kRakeBuckets; ++k) sum[k] += blk_cnt[static_cast<size_t>(i) * 8 + k];
 #pragma unroll
-    for (int k = 0; k < kRakeBuckets; ++k) s_part[t][k] = sum[k];
+    for (int k = 0; k < kRakeBuckets; ++k) s_part[k][t + (t >> 5)] = sum[k];
     __syncthreads();
     if (t < 32 * kRakeBuckets) {  // one warp per key: exclusive scan of the 1024 partials, 32 consecutive ones per lane
         const int key = t >> 5, ln = t & 31;
         unsigned mine = 0;
-        for (int i = 0; i < 32; ++i) mine += s_part[ln * 32 + i][key];
+        for (int i = 0; i < 32; ++i) mine += s_part[key][ln * 33 + i];
         unsigned incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1623,14 +1656,14 @@ static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__
         }
         unsigned run = incl - mine;
         for (int i = 0; i < 32; ++i) {
-            const unsigned v = s_part[ln * 32 + i][key];
-            s_part[ln * 32 + i][key] = run;
+            const unsigned v = s_part[key][ln * 33 + i];
+            s_part[key][ln * 33 + i] = run;
             run += v;
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kRakeBuckets; ++k) sum[k] = s_part[t][k];
+    for (int k = 0; k < kRakeBuckets; ++k) sum[k] = s_part[k][t + (t >> 5)];
     for (int i = b0; i < b1; ++i)
 #pragma unroll
         for (int k = 0; k < kRakeBuckets; ++k) {

@@ -32,7 +32,8 @@ class B200MPError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libb200mp.so")
+    # B200MP_LIB: a differently built libb200mp.so (tools/build_variant.sh; development only)
+    return os.environ.get("B200MP_LIB") or os.path.join(_HERE, "libb200mp.so")
 
 
 def load_library():

@@ -104,6 +104,34 @@ def test_large_state_batches_are_sifted_with_the_same_decisions(ctx):
     assert_validity_parity(got, want, clr_states(pe, "panda", q), "sifted states")
 
 
+@pytest.mark.parametrize("robot", ["panda", "fetch"])
+def test_first_look_and_queue_takes_do_not_change_decisions(ctx, robot):
+    """A large mixed batch (short roadmap-like edges, long motions between random end points, the same edges backwards): the long
+    bucket gets a first look that goes on (two states per motion, passes that give up at a few undecided lanes) and the motion kernel
+    then takes its queue entries several at a time. Decisions equal those of the same motions in small batches (other sample
+    verdicts, other takes) and the oracle's."""
+    kw = dict(seed=31, n_spheres=300, n_cuboids=300, n_capsules=60, n_zcuboids=60, n_zcapsules=60)
+    if robot == "fetch":
+        kw = dict(seed=32, n_spheres=80, n_cuboids=80, n_capsules=20, n_zcuboids=20, n_zcapsules=20, rho_lo=0.6, rho_hi=1.4, z_lo=0.2, z_hi=1.6)
+    scene = synth.clutter_scene(**kw)
+    env = synth.fill_env(ompl_b200.Environment(ctx), scene)
+    pe = synth.fill_env(port.PortEnvironment(), scene)
+    q = synth.uniform_states(robot, 400000, 57)
+    ok = ctx.validate_states(robot, env, q)
+    starts = q[ok == 1][:40000]
+    a0, a1 = synth.local_edges(robot, starts, 61, 0.02, 3.0)            # short and long, many valid
+    b0, b1 = q[:30000], q[30000:60000]                                   # random end points: long, nearly all invalid
+    q0, q1 = np.concatenate([a0, b0, a1]), np.concatenate([a1, b1, a0])                # ... and the same edges backwards
+    assert len(q0) >= (1 << 16)
+    got = ctx.validate_motions(robot, env, q0, q1)
+    small = np.concatenate([ctx.validate_motions(robot, env, q0[i:i + 30000], q1[i:i + 30000]) for i in range(0, len(q0), 30000)])
+    np.testing.assert_array_equal(got, small)
+    assert 0.05 < got.mean() < 0.95
+    sub = np.random.default_rng(5).choice(len(q0), 12000, replace=False)
+    want = pe.validate_motions(robot, q0[sub], q1[sub], nthreads=8)
+    assert_validity_parity(got[sub], want, clr_motions(pe, robot, q0[sub], q1[sub]), "first look + takes")
+
+
 def test_demo_known_answers(ctx):
     env = synth.fill_env(ompl_b200.Environment(ctx), synth.cage_scene())
     assert list(ctx.validate_states("panda", env, [synth.CAGE_START, synth.CAGE_GOAL])) == [1, 1]

@@ -61,8 +61,9 @@ if "knn" in sys.argv or len(sys.argv) == 1:
             r = ctx.prm_build("panda", env, nr, 16, 42, want_weights=False)
         print(json.dumps(r["stats"]), flush=True)
 
-if "dense" in sys.argv or len(sys.argv) == 1:
-    for name, kw in (("grid", dict(sort=True)), ("sorted_ordered_scan", dict(sort=True, grid=False)), ("unsorted_ordered_scan", dict(sort=False))):
+if "dense" in sys.argv or "gridonly" in sys.argv or len(sys.argv) == 1:
+    variants = (("grid", dict(sort=True)), ("sorted_ordered_scan", dict(sort=True, grid=False)), ("unsorted_ordered_scan", dict(sort=False)))
+    for name, kw in variants[:1] if "gridonly" in sys.argv else variants:
         env = synth.fill_env(ompl_b200.Environment(ctx), scene, **kw)
         ms_mixed, v = timed(env, q0, q1, reps=3)
         vi = np.nonzero(v == 1)[0]
