@@ -1595,8 +1595,9 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
 // valid[] = 1. The list is then filled in a STABLE order: consecutive motions of a bucket stay consecutive, so the rakes that share
 // a warp pass belong to neighbouring motions of the batch (roadmap edges of one milestone: nearby states, the same links near the
 // same obstacles), which is what keeps the lock-step lanes of a pass doing the same work.
+constexpr int kBucketThreads = 1024;  // motions per block of the pre-pass (one row of per-block counts each: fewer rows for the plan kernel)
 template <class R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBucketThreads)
 bucket_count_kernel(const float *__restrict__ q0, const float *__restrict__ q1, const int2 *__restrict__ pairs, long long m, int resolution,
                     unsigned char *__restrict__ keys, uint8_t *__restrict__ valid, unsigned *__restrict__ blk_cnt, BucketPlan *__restrict__ plan) {
     constexpr int D = R::kDim;
@@ -1604,6 +1605,7 @@ bucket_count_kernel(const float *__restrict__ q0, const float *__restrict__ q1, 
     if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int key = 0;
     if (e < m) {
         long long ia = e, ib = e;
         if (pairs != nullptr) {
@@ -1616,10 +1618,14 @@ bucket_count_kernel(const float *__restrict__ q0, const float *__restrict__ q1, 
         for (int j = 0; j < D; ++j) v[j] = __ldg(q1 + ib * D + j) - __ldg(q0 + ia * D + j);
         const float dist = vamp_l2_norm<D>(v);
         const float nf = fmaxf(ceilf(dist / 8.0f * static_cast<float>(resolution)), 1.0f);
-        const int key = nf <= 4.0f ? static_cast<int>(nf) : kRakeBuckets - 1;  // (NaN lengths go to the long bucket as well)
+        key = nf <= 4.0f ? static_cast<int>(nf) : kRakeBuckets - 1;  // (NaN lengths go to the long bucket as well)
         keys[e] = static_cast<unsigned char>(key);
         valid[e] = 1;
-        atomicAdd(&s_cnt[key], 1u);
+    }
+#pragma unroll
+    for (int k = 1; k < kRakeBuckets; ++k) {  // (one shared-memory atomic per warp and key)
+        const unsigned mask = __ballot_sync(kFull, key == k);
+        if ((threadIdx.x & 31) == 0 && mask != 0u) atomicAdd(&s_cnt[k], static_cast<unsigned>(__popc(mask)));
     }
     __syncthreads();
     if (threadIdx.x < 8) {
@@ -1628,49 +1634,58 @@ bucket_count_kernel(const float *__restrict__ q0, const float *__restrict__ q1, 
     }
 }
 
-// one block: bucket offsets and pass counts; blk_cnt[block][key] -> exclusive prefix over the blocks (in place)
+// one block: bucket offsets and pass counts; blk_cnt[block][key] -> exclusive prefix over the blocks (in place). 1024 rows per round,
+// one row per thread (coalesced 32-byte rows), block-wide scan per key, carry from round to round.
 static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__restrict__ plan, unsigned *__restrict__ blk_cnt, int nb, int first_look) {
-    // [key][thread], one pad word per 32 threads: the scan below walks 32 consecutive partials per lane (bank = lane + i, no conflict;
-    // a [thread][key] layout put all 32 lanes of a step on one bank)
-    __shared__ unsigned s_part[kRakeBuckets][1024 + 32];
-    const int t = threadIdx.x;
-    const int chunk = (nb + 1023) / 1024, b0 = t * chunk, b1 = min(nb, b0 + chunk);
-    unsigned sum[kRakeBuckets];
-#pragma unroll
-    for (int k = 0; k < kRakeBuckets; ++k) sum[k] = 0;
-    for (int i = b0; i < b1; ++i)
-#pragma unroll
-        for (int k = 0; k < kRakeBuckets; ++k) sum[k] += blk_cnt[static_cast<size_t>(i) * 8 + k];
-#pragma unroll
-    for (int k = 0; k < kRakeBuckets; ++k) s_part[k][t + (t >> 5)] = sum[k];
+    __shared__ unsigned s_warp[32][8], s_tot[8], s_carry[8];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t < 8) s_carry[t] = 0;
     __syncthreads();
-    if (t < 32 * kRakeBuckets) {  // one warp per key: exclusive scan of the 1024 partials, 32 consecutive ones per lane
-        const int key = t >> 5, ln = t & 31;
-        unsigned mine = 0;
-        for (int i = 0; i < 32; ++i) mine += s_part[key][ln * 33 + i];
-        unsigned incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned up = __shfl_up_sync(kFull, incl, o);
-            if (ln >= o) incl += up;
+    uint4 *rows = reinterpret_cast<uint4 *>(blk_cnt);
+    for (int base = 0; base < nb; base += 1024) {
+        const int r = base + t;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (r < nb) {
+            lo = rows[2 * static_cast<size_t>(r)];
+            hi = rows[2 * static_cast<size_t>(r) + 1];
         }
-        unsigned run = incl - mine;
-        for (int i = 0; i < 32; ++i) {
-            const unsigned v = s_part[key][ln * 33 + i];
-            s_part[key][ln * 33 + i] = run;
-            run += v;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kRakeBuckets; ++k) sum[k] = s_part[k][t + (t >> 5)];
-    for (int i = b0; i < b1; ++i)
+        const unsigned v[kRakeBuckets] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y};
+        unsigned incl[kRakeBuckets];
 #pragma unroll
         for (int k = 0; k < kRakeBuckets; ++k) {
-            const unsigned v = blk_cnt[static_cast<size_t>(i) * 8 + k];
-            blk_cnt[static_cast<size_t>(i) * 8 + k] = sum[k];
-            sum[k] += v;
+            unsigned x = v[k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(kFull, x, o);
+                if (lane >= o) x += up;
+            }
+            incl[k] = x;
+            if (lane == 31) s_warp[w][k] = x;
         }
+        __syncthreads();
+        if (w < kRakeBuckets) {  // warp k: exclusive scan of the 32 warp totals of key k
+            const unsigned mine = s_warp[lane][w];
+            unsigned x = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(kFull, x, o);
+                if (lane >= o) x += up;
+            }
+            s_warp[lane][w] = x - mine;
+            if (lane == 31) s_tot[w] = x;
+        }
+        __syncthreads();
+        if (r < nb) {
+            unsigned ex[kRakeBuckets];
+#pragma unroll
+            for (int k = 0; k < kRakeBuckets; ++k) ex[k] = s_carry[k] + s_warp[w][k] + incl[k] - v[k];
+            rows[2 * static_cast<size_t>(r)] = make_uint4(ex[0], ex[1], ex[2], ex[3]);
+            rows[2 * static_cast<size_t>(r) + 1] = make_uint4(ex[4], ex[5], 0u, 0u);
+        }
+        __syncthreads();
+        if (t < kRakeBuckets) s_carry[t] += s_tot[t];
+        __syncthreads();
+    }
     if (t == 0) {
         unsigned off = 0, passes = 0;
         plan->off[0] = 0; plan->cursor[0] = 0; plan->pass_end[0] = 0;
@@ -1695,9 +1710,10 @@ static __global__ void __launch_bounds__(1024) bucket_plan_kernel(BucketPlan *__
     }
 }
 
-static __global__ void __launch_bounds__(256) bucket_scatter_kernel(const unsigned char *__restrict__ keys, long long m, const unsigned *__restrict__ blk_base,
-                                                                    unsigned *__restrict__ list, const BucketPlan *__restrict__ plan) {
-    __shared__ unsigned s_w[8][8];  // [warp][key]: motions of that key in the warp
+static __global__ void __launch_bounds__(kBucketThreads) bucket_scatter_kernel(const unsigned char *__restrict__ keys, long long m,
+                                                                               const unsigned *__restrict__ blk_base, unsigned *__restrict__ list,
+                                                                               const BucketPlan *__restrict__ plan) {
+    __shared__ unsigned s_w[kBucketThreads / 32][8];  // [warp][key]: motions of that key in the warp
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int key = e < m ? keys[e] : 0;

@@ -62,7 +62,7 @@ int launch_motions_bucketed(b200mp_ctx *c, const SceneDesc &desc, const float *d
     if ((rc = blocks_per_sm(c->device, reinterpret_cast<const void *>(k_long), motion_threads<R>(), smem, &per_long))) return rc;
     if (per_rakes < 1 || per_first < 1 || per_long < 1) return fail(B200MP_ERR_CAPACITY, "validate (bucketed): kernel does not fit on an SM with %zu B of scene", smem);
     // stream-ordered temporaries: keys[m] | list[m] | per-block counts[nb][8] | plan
-    const unsigned nb = static_cast<unsigned>((m + 255) / 256);
+    const unsigned nb = static_cast<unsigned>((m + kBucketThreads - 1) / kBucketThreads);
     const size_t o_list = (static_cast<size_t>(m) + 255) / 256 * 256, o_blk = o_list + (static_cast<size_t>(m) * 4 + 255) / 256 * 256;
     const size_t o_plan = o_blk + static_cast<size_t>(nb) * 8 * 4;
     char *tmp = nullptr;
@@ -72,11 +72,11 @@ int launch_motions_bucketed(b200mp_ctx *c, const SceneDesc &desc, const float *d
     unsigned *blk = reinterpret_cast<unsigned *>(tmp + o_blk);
     BucketPlan *plan = reinterpret_cast<BucketPlan *>(tmp + o_plan);
     cudaMemsetAsync(plan, 0, sizeof(BucketPlan), st);
-    bucket_count_kernel<R><<<nb, 256, 0, st>>>(d_q0, d_q1, d_pairs, m, resolution, keys, d_valid, blk, plan);
+    bucket_count_kernel<R><<<nb, kBucketThreads, 0, st>>>(d_q0, d_q1, d_pairs, m, resolution, keys, d_valid, blk, plan);
     static const bool first_look_env = !(getenv("B200MP_FIRST_LOOK") && atoi(getenv("B200MP_FIRST_LOOK")) == 0);
     const bool first_look = first_look_env && c->first_look.load() != 0;
     bucket_plan_kernel<<<1, 1024, 0, st>>>(plan, blk, static_cast<int>(nb), first_look ? 1 : 0);
-    bucket_scatter_kernel<<<nb, 256, 0, st>>>(keys, m, blk, list, plan);
+    bucket_scatter_kernel<<<nb, kBucketThreads, 0, st>>>(keys, m, blk, list, plan);
     const long long wpb = motion_threads<R>() / 32;
     const long long cap = std::max<long long>(1, (m + wpb - 1) / wpb);
     const unsigned b_rakes = static_cast<unsigned>(std::min<long long>(static_cast<long long>(c->sm_count) * per_rakes, cap));
