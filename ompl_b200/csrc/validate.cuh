@@ -1473,6 +1473,14 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
     float *slots = smem + sd.blob_floats + threadIdx.x;
     __shared__ SharedViews sv;
     fill_views(sd, sc, sv);
+    // the plan's constants (final before this kernel starts) in shared memory: a pass looks three of them up before it can load anything
+    __shared__ unsigned s_pass_end[kRakeBuckets], s_cnt[kRakeBuckets], s_off[kRakeBuckets], s_pre_sample;
+    if (threadIdx.x < kRakeBuckets) {
+        s_pass_end[threadIdx.x] = plan->pass_end[threadIdx.x];
+        s_cnt[threadIdx.x] = plan->cnt[threadIdx.x];
+        s_off[threadIdx.x] = plan->off[threadIdx.x];
+    }
+    if (threadIdx.x == 0) s_pre_sample = plan->pre_sample;
     __syncthreads();
     constexpr int D = R::kDim;
     const int lane = threadIdx.x & 31;
@@ -1480,7 +1488,10 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
     constexpr int LPM = FIRST ? kFirstLanes : 8;
     constexpr unsigned kGroupMask = (1u << LPM) - 1u;
     const int group = lane / LPM;
-    const float pct = FIRST ? static_cast<float>((8 / LPM) * ((lane & (LPM - 1)) + 1)) / 8.0f : static_cast<float>((lane & 7) + 1) / 8.0f;
+    // (a first look at roadmap edges -- both ends are milestones, known to be valid -- with two lanes: 3/8 and 6/8 instead of 4/8 and 8/8)
+    const float pct = FIRST ? (LPM == 2 && pairs != nullptr ? static_cast<float>(3 * ((lane & 1) + 1)) / 8.0f
+                                                            : static_cast<float>((8 / LPM) * ((lane & (LPM - 1)) + 1)) / 8.0f)
+                            : static_cast<float>((lane & 7) + 1) / 8.0f;
     // the short buckets take their passes four at a time from the queue (one atomic round trip per four passes; passes still run in
     // increasing order inside a warp); the first look, whose sample / verdict logic counts single passes, one at a time
     constexpr unsigned kTake = FIRST ? 1u : 4u;
@@ -1505,7 +1516,7 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
         unsigned t;
         if (first_look) {
             const unsigned lp = p - short_passes;
-            if (lp >= plan->pre_sample) {
+            if (lp >= s_pre_sample) {
                 // beyond the sample: run unless the verdict is already "skip". A warp does not idle while the sample is being
                 // finished by others -- it takes one more pass on trust -- but no more than that: past one pass per warp of the grid
                 // it waits for the verdict (where passes are slow, e.g. ordered scans of a large scene, optimism would cost too much)
@@ -1513,7 +1524,7 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
                 if (lane == 0) {
                     const volatile unsigned *flag = &plan->pre_decision;
                     dec = *flag;
-                    if (lp >= plan->pre_sample + gridDim.x * (blockDim.x >> 5))
+                    if (lp >= s_pre_sample + gridDim.x * (blockDim.x >> 5))
                         while ((dec = *flag) == 0u) __nanosleep(200);
                 }
                 dec = __shfl_sync(kFull, dec, 0);
@@ -1522,13 +1533,13 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
             b = kRakeBuckets - 1;
             t = static_cast<unsigned>(32 / LPM) * lp + static_cast<unsigned>(group);
         } else {
-            while (p >= plan->pass_end[b]) ++b;  // (warp-uniform; at most three steps)
-            t = 4u * (p - plan->pass_end[b - 1]) + static_cast<unsigned>(group);
+            while (p >= s_pass_end[b]) ++b;  // (warp-uniform; at most three steps)
+            t = 4u * (p - s_pass_end[b - 1]) + static_cast<unsigned>(group);
         }
         const unsigned ei = first_look ? t : t / static_cast<unsigned>(b);
         const int rake = first_look ? 0 : static_cast<int>(t - ei * static_cast<unsigned>(b));
-        bool active = ei < plan->cnt[b];
-        const unsigned e = active ? __ldg(list + plan->off[b] + ei) : 0xffffffffu;
+        bool active = ei < s_cnt[b];
+        const unsigned e = active ? __ldg(list + s_off[b] + ei) : 0xffffffffu;
         if (active && valid[e] == 0) active = false;  // another pass already found this motion in collision
         float a[D], v[D], q[D], back[D];
         unsigned long long ia = e, ib = e;
@@ -1571,14 +1582,14 @@ validate_rakes_kernel(SceneDesc sd, const float *__restrict__ q0, const float *_
             bad = group_any<LPM>(active && !good);
             if (bad && (lane & (LPM - 1)) == 0) valid[e] = 0;
         }
-        if (first_look && p - short_passes < plan->pre_sample) {
+        if (first_look && p - short_passes < s_pre_sample) {
             const unsigned tested = __popc(__ballot_sync(kFull, active && (lane & (LPM - 1)) == 0));
             const unsigned killed = __popc(__ballot_sync(kFull, bad && (lane & (LPM - 1)) == 0));
             if (lane == 0) {
                 atomicAdd(&plan->pre_tested, tested);
                 atomicAdd(&plan->pre_killed, killed);
                 __threadfence();
-                if (atomicAdd(&plan->pre_done, 1u) + 1u == plan->pre_sample) {
+                if (atomicAdd(&plan->pre_done, 1u) + 1u == s_pre_sample) {
                     // the sample is complete: go on with the first look only if it settles most motions
                     const unsigned k = atomicAdd(&plan->pre_killed, 0u), n = atomicAdd(&plan->pre_tested, 0u);
                     __threadfence();
