@@ -185,8 +185,9 @@ int b200mp_session_is_valid_f64(b200mp_session *session, const double *q, uint8_
 int b200mp_session_stats(const b200mp_session *session, int64_t *calls, int64_t *launches);
 
 /* Tuning switches (decisions never depend on them). B200MP_OPT_FIRST_LOOK (default 1): batches of long motions (>= 5 rakes) first get a
- * look at rake 0 of four motions per warp pass, continued only while it settles most motions (see validate_rakes_kernel); 0 sends
- * them straight to the warp-per-motion kernel (measurements of that kernel alone). */
+ * look at two states of rake 0 (the middle and the end of the motion; roadmap edges: 3/8 and 6/8), sixteen motions per warp pass,
+ * continued only while it settles enough of them (see validate_rakes_kernel); 0 sends them straight to the warp-per-motion kernel
+ * (measurements of that kernel alone). */
 enum { B200MP_OPT_FIRST_LOOK = 1 };
 int b200mp_set_option(b200mp_ctx *ctx, int option, int value);
 
