@@ -374,6 +374,7 @@ void b200mp_destroy(b200mp_ctx *c) {
     }
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;
@@ -929,6 +930,10 @@ int validate_motions_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T
     if (m >= 2 * kChunk) {
         if (!c->h2d_stream) B200_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
         if (!c->d2h_stream) B200_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        // chunks alternate between two kernel streams: the kernels are persistent (one block per SM), so a chunk's kernels end in a tail
+        // of SMs going idle one by one -- the next chunk's kernels, on the other stream, move in as they do
+        static const bool two_streams = !(getenv("B200MP_CHUNK_STREAMS") && atoi(getenv("B200MP_CHUNK_STREAMS")) == 1);
+        if (two_streams && !c->stream2) B200_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
         const size_t slot_floats = static_cast<size_t>(kChunk) * dim;  // one array of one slot
         if (!kIsFloat && c->stage_cap < 4 * slot_floats * sizeof(float)) {
             if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -979,17 +984,19 @@ int validate_motions_host(b200mp_ctx *c, int robot, const b200mp_env *e, const T
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_q0 + off, s0, bytes, cudaMemcpyHostToDevice, c->h2d_stream);
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_q1 + off, s1, bytes, cudaMemcpyHostToDevice, c->h2d_stream);
             if (ce == cudaSuccess) ce = cudaEventRecord(up[i], c->h2d_stream);
-            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(c->stream, up[i], 0);
+            cudaStream_t ks = (two_streams && (i & 1)) ? c->stream2 : c->stream;
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ks, up[i], 0);
             if (ce != cudaSuccess) { err = fail(B200MP_ERR_CUDA, "b200mp_validate_motions: upload failed: %s", cudaGetErrorString(ce)); break; }
-            err = b200mp_validate_motions_device(c, robot, e, d_q0 + off, d_q1 + off, cnt, resolution, d_valid + first, c->stream);
+            err = b200mp_validate_motions_device(c, robot, e, d_q0 + off, d_q1 + off, cnt, resolution, d_valid + first, ks);
             if (err) break;
-            ce = cudaEventRecord(done[i], c->stream);
+            ce = cudaEventRecord(done[i], ks);
             if (ce == cudaSuccess) ce = cudaStreamWaitEvent(c->d2h_stream, done[i], 0);
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(valid + first, d_valid + first, static_cast<size_t>(cnt), cudaMemcpyDeviceToHost, c->d2h_stream);
             if (ce != cudaSuccess) err = fail(B200MP_ERR_CUDA, "b200mp_validate_motions: download failed: %s", cudaGetErrorString(ce));
         }
         cudaStreamSynchronize(c->h2d_stream);
         cudaStreamSynchronize(c->stream);
+        if (c->stream2) cudaStreamSynchronize(c->stream2);
         cudaError_t ce = cudaStreamSynchronize(c->d2h_stream);
         for (int i = 0; i < n_chunks; ++i) { cudaEventDestroy(up[i]); cudaEventDestroy(done[i]); }
         if (!err && ce != cudaSuccess) err = fail(B200MP_ERR_CUDA, "b200mp_validate_motions: %s", cudaGetErrorString(ce));

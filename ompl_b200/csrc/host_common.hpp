@@ -71,6 +71,7 @@ struct b200mp_ctx {
     // small-call path (one checkMotion / isValid at a time, the way OMPL planners call): a mapped pinned buffer the kernels
     // read and write directly, so a call is one memset + one launch + one synchronise
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy streams of the chunked host entry points (created on first use)
+    cudaStream_t stream2 = nullptr;                           // second kernel stream of the chunked host entry points (odd chunks)
     void *h_small = nullptr;   // host address
     void *d_small = nullptr;   // the same memory as the device sees it
     size_t small_cap = 0;
